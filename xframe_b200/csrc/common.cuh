@@ -1,0 +1,74 @@
+// Shared device/host helpers for the xfb200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+
+#define XFB_WARP 32
+
+extern thread_local std::string g_xfb_err;
+
+#define XFB_CUDA(call)                                                                     \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            char buf__[512];                                                               \
+            snprintf(buf__, sizeof buf__, "%s:%d %s -> %s", __FILE__, __LINE__, #call,     \
+                     cudaGetErrorString(e__));                                             \
+            g_xfb_err = buf__;                                                             \
+            return 1;                                                                      \
+        }                                                                                  \
+    } while (0)
+
+#define XFB_FAIL(...)                                                                      \
+    do {                                                                                   \
+        char buf__[512];                                                                   \
+        snprintf(buf__, sizeof buf__, __VA_ARGS__);                                        \
+        g_xfb_err = buf__;                                                                 \
+        return 1;                                                                          \
+    } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------
+// FP64 tensor-core MMA, native sm_100a shape DMMA.8x8x4.
+// Fragment ownership (PTX ISA, mma.m8n8k4 .f64):
+//   A (8x4): lane holds A[lane>>2][lane&3]
+//   B (4x8): lane holds B[lane&3][lane>>2]
+//   C (8x8): lane holds C[lane>>2][2*(lane&3)+{0,1}]
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// streaming 128-bit accesses (complex128 elements)
+__device__ __forceinline__ double2 ldg2(const double2* p) { return __ldg(p); }
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }

@@ -1,0 +1,185 @@
+// FP64 tensor-core (DMMA.8x8x4) GEMM kernels:
+//   hankel_kernel      -- the radial (Hankel) contraction: complex rows x real per-order matrix
+//                         out[row][k] = (-+i)^l * scale * sum_p in[row][p+skip] * W_l[p][k]
+//                         reference: apply_weights OpenCL kernel / generate_spherical_ht
+//                         (hankel_transforms.py:642-766), restated in oracle/mtip.py:generate_spherical_ht_direct
+//   grouped_gemm_kernel-- small real GEMMs with arbitrary strides for the Procrustes step
+//                         (PD_l @ I_l and V_l @ unk_l, fxs_Projections.py:752-767,835-841)
+#pragma once
+#include "common.cuh"
+
+#define HK_BM 64
+#define HK_BN 64
+#define HK_BK 16
+#define HK_LDA (HK_BK + 4)
+#define HK_LDB (HK_BN + 4)
+
+struct HankelTile {
+    int l;        // order
+    int row0;     // first flat row (lm*nb + b) of this tile
+    int row_end;  // one past the last flat row of order l
+};
+
+__global__ void __launch_bounds__(256) hankel_kernel(const double2* __restrict__ in, double2* __restrict__ out,
+                                                     const double* __restrict__ W, const HankelTile* __restrict__ tiles,
+                                                     int n_r, int n_sum, int skip, double scale, int inverse) {
+    __shared__ double As_re[HK_BM * HK_LDA];
+    __shared__ double As_im[HK_BM * HK_LDA];
+    __shared__ double Bs[HK_BK * HK_LDB];
+    const HankelTile t = tiles[blockIdx.x];
+    const int k_tile0 = blockIdx.y * HK_BN;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps, warp tile 32 rows x 16 cols
+    const double* Wl = W + (size_t)t.l * n_sum * n_r;
+    double cre[4][2][2] = {}, cim[4][2][2] = {};
+    const int ar = lane >> 2, ak = lane & 3;
+
+    for (int p0 = 0; p0 < n_sum; p0 += HK_BK) {
+        __syncthreads();
+        // A chunk: 64 rows x 16 p (complex), 16 consecutive threads read 256 contiguous bytes
+#pragma unroll
+        for (int q = 0; q < (HK_BM * HK_BK) / 256; ++q) {
+            const int item = tid + q * 256;
+            const int row = item >> 4, pp = item & 15;
+            const int grow = t.row0 + row;
+            double2 v = make_double2(0, 0);
+            if (grow < t.row_end && (p0 + pp) < n_sum) v = ldg2(in + (size_t)grow * n_r + skip + p0 + pp);
+            As_re[row * HK_LDA + pp] = v.x;
+            As_im[row * HK_LDA + pp] = v.y;
+        }
+        // B chunk: 16 p x 64 k
+#pragma unroll
+        for (int q = 0; q < (HK_BK * HK_BN) / 256; ++q) {
+            const int item = tid + q * 256;
+            const int pp = item >> 6, kk = item & 63;
+            double v = 0.0;
+            if ((p0 + pp) < n_sum && (k_tile0 + kk) < n_r) v = __ldg(Wl + (size_t)(p0 + pp) * n_r + k_tile0 + kk);
+            Bs[pp * HK_LDB + kk] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k0 = 0; k0 < HK_BK; k0 += 4) {
+            double b[2];
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) b[nb] = Bs[(k0 + ak) * HK_LDB + wn * 16 + nb * 8 + ar];
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb) {
+                const int off = (wm * 32 + mb * 8 + ar) * HK_LDA + k0 + ak;
+                const double xr = As_re[off], xi = As_im[off];
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb) {
+                    dmma884(cre[mb][nb][0], cre[mb][nb][1], xr, b[nb]);
+                    dmma884(cim[mb][nb][0], cim[mb][nb][1], xi, b[nb]);
+                }
+            }
+        }
+    }
+    // epilogue: multiply by scale * (-i)^l (forward) or (+i)^l (inverse)
+    const int ph = t.l & 3;
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) {
+        const int grow = t.row0 + wm * 32 + mb * 8 + ar;
+        if (grow >= t.row_end) continue;
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+            const int k = k_tile0 + wn * 16 + nb * 8 + 2 * ak;
+            double2 o[2];
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const double x = cre[mb][nb][cc] * scale, y = cim[mb][nb][cc] * scale;
+                double2 r;
+                if (ph == 0) r = make_double2(x, y);
+                else if (ph == 2) r = make_double2(-x, -y);
+                else if ((ph == 1) != (inverse != 0)) r = make_double2(y, -x);   // multiply by -i
+                else r = make_double2(-y, x);                                     // multiply by +i
+                o[cc] = r;
+            }
+            if (k < n_r) out[(size_t)grow * n_r + k] = o[0];
+            if (k + 1 < n_r) out[(size_t)grow * n_r + k + 1] = o[1];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// grouped real GEMM  C = alpha * A * B, arbitrary element strides, one
+// descriptor per problem; 64x64 block tiles, 4 warps (2x2), warp tile 32x32.
+// ---------------------------------------------------------------------------
+struct GemmProblem {
+    const double* A;
+    const double* B;
+    double* C;
+    int M, N, K;
+    long long a_rs, a_cs;  // element strides of A[m][k]
+    long long b_rs, b_cs;  // B[k][n]
+    long long c_rs, c_cs;  // C[m][n]
+    double alpha;
+    int tile0;  // first tile id of this problem in the launch
+    int tiles_n;
+};
+
+#define GG_BM 64
+#define GG_BN 64
+#define GG_BK 16
+#define GG_LDA (GG_BK + 4)
+#define GG_LDB (GG_BN + 4)
+
+__global__ void __launch_bounds__(128) grouped_gemm_kernel(const GemmProblem* __restrict__ probs, const int* __restrict__ tile_prob) {
+    __shared__ double As[GG_BM * GG_LDA];
+    __shared__ double Bs[GG_BK * GG_LDB];
+    const GemmProblem pr = probs[tile_prob[blockIdx.x]];
+    const int tl = blockIdx.x - pr.tile0;
+    const int m0 = (tl / pr.tiles_n) * GG_BM, n0 = (tl % pr.tiles_n) * GG_BN;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int ar = lane >> 2, ak = lane & 3;
+    double acc[4][4][2] = {};
+    const bool a_kfast = (pr.a_cs == 1);
+    const bool b_nfast = (pr.b_cs == 1);
+    for (int k0 = 0; k0 < pr.K; k0 += GG_BK) {
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < (GG_BM * GG_BK) / 128; ++q) {
+            const int item = tid + q * 128;
+            int mm, kk;
+            if (a_kfast) { mm = item >> 4; kk = item & 15; } else { kk = item >> 6; mm = item & 63; }
+            double v = 0.0;
+            if ((m0 + mm) < pr.M && (k0 + kk) < pr.K) v = __ldg(pr.A + (m0 + mm) * pr.a_rs + (k0 + kk) * pr.a_cs);
+            As[mm * GG_LDA + kk] = v;
+        }
+#pragma unroll
+        for (int q = 0; q < (GG_BK * GG_BN) / 128; ++q) {
+            const int item = tid + q * 128;
+            int kk, nn;
+            if (b_nfast) { kk = item >> 6; nn = item & 63; } else { nn = item >> 4; kk = item & 15; }
+            double v = 0.0;
+            if ((k0 + kk) < pr.K && (n0 + nn) < pr.N) v = __ldg(pr.B + (k0 + kk) * pr.b_rs + (n0 + nn) * pr.b_cs);
+            Bs[kk * GG_LDB + nn] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kq = 0; kq < GG_BK; kq += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb) a[mb] = As[(wm * 32 + mb * 8 + ar) * GG_LDA + kq + ak];
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) b[nb] = Bs[(kq + ak) * GG_LDB + wn * 32 + nb * 8 + ar];
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+        }
+    }
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) {
+        const int m = m0 + wm * 32 + mb * 8 + ar;
+        if (m >= pr.M) continue;
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int n = n0 + wn * 32 + nb * 8 + 2 * ak + cc;
+                if (n < pr.N) pr.C[m * pr.c_rs + n * pr.c_cs] = pr.alpha * acc[mb][nb][cc];
+            }
+        }
+    }
+}

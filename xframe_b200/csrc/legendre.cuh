@@ -1,0 +1,177 @@
+// Per-m associated-Legendre contraction of the SHT as FP64 tensor-core GEMMs
+// (DMMA.8x8x4), with the north/south mirror symmetry P_l^m(-x) = (-1)^(l+m) P_l^m(x)
+// folded in: the theta contraction runs over n_theta/2 nodes, separately for
+// (l-m) even and odd.
+//
+// Reference semantics: analys_cplx / synth_cplx of shtns (shtns_plugin.py:218-261),
+// restated in oracle/sht.py:ShtCore.analys_batch / synth_batch.
+//
+// Data layouts
+//   a : [S][M2][n_theta] complex, M2 = 2L+1, mm = m (m>=0) / M2+m (m<0)   (phi-Fourier space)
+//   c : [(L+1)^2][S] complex, row index l*(l+1)+m, S shells contiguous        (internal coefficient layout)
+//   tables: FE/FO [L+1][K2][NP] (forward: w_j * 2pi/n_phi * P), IE/IO [L+1][NP][K2] (inverse: P)
+//     K2 = n_theta/2, NP = number of same-parity degrees rounded up to 8, zero padded.
+#pragma once
+#include "common.cuh"
+
+#define LEG_ROWS 32      // 16 shells x 2 signs of m
+#define LEG_NB 32        // output columns per pass (4 warps x 8)
+#define LEG_LDB (LEG_NB + 4)
+
+// acc[mb][0..1] += A[32 x K] (rows mb*8.., smem [row*lda + k]) * B[K x 8] (smem [k*ldb + n0 + n])
+__device__ __forceinline__ void leg_mma_cplx(const double* __restrict__ Are, const double* __restrict__ Aim, int lda,
+                                             const double* __restrict__ Bs, int ldb, int n0, int K, int lane,
+                                             double (&cre)[4][2], double (&cim)[4][2]) {
+    const int ar = lane >> 2, ak = lane & 3;
+    for (int k0 = 0; k0 < K; k0 += 4) {
+        const double b = Bs[(k0 + ak) * ldb + n0 + ar];
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb) {
+            const int off = (mb * 8 + ar) * lda + k0 + ak;
+            dmma884(cre[mb][0], cre[mb][1], Are[off], b);
+            dmma884(cim[mb][0], cim[mb][1], Aim[off], b);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) legendre_forward_kernel(const double2* __restrict__ a, double2* __restrict__ c,
+                                                               const double* __restrict__ FE, const double* __restrict__ FO,
+                                                               int S, int l_max, int n_theta, int NP) {
+    extern __shared__ double smem_leg[];
+    const int K2 = n_theta >> 1;
+    const int lda = K2 + 4;
+    double* Ae_re = smem_leg;
+    double* Ae_im = Ae_re + LEG_ROWS * lda;
+    double* Ao_re = Ae_im + LEG_ROWS * lda;
+    double* Ao_im = Ao_re + LEG_ROWS * lda;
+    double* Be = Ao_im + LEG_ROWS * lda;
+    double* Bo = Be + K2 * LEG_LDB;
+    const int m = blockIdx.y;
+    const int sh0 = blockIdx.x * 16;
+    const int M2 = 2 * l_max + 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- stage A: fold north/south, apply (-1)^m for the -m rows
+    for (int item = tid; item < LEG_ROWS * K2; item += 128) {
+        const int row = item / K2, j = item - row * K2;
+        const int sh = sh0 + (row & 15), sign = row >> 4;
+        double2 e = make_double2(0, 0), o = make_double2(0, 0);
+        if (sh < S && (sign == 0 || m > 0)) {
+            const int mm = sign ? (M2 - m) : m;
+            const double2* src = a + ((size_t)sh * M2 + mm) * n_theta;
+            const double2 x = ldg2(src + j), y = ldg2(src + (n_theta - 1 - j));
+            e = cadd(x, y);
+            o = csub(x, y);
+            if (sign && (m & 1)) { e.x = -e.x; e.y = -e.y; o.x = -o.x; o.y = -o.y; }
+        }
+        Ae_re[row * lda + j] = e.x; Ae_im[row * lda + j] = e.y;
+        Ao_re[row * lda + j] = o.x; Ao_im[row * lda + j] = o.y;
+    }
+    const double* FEm = FE + (size_t)m * K2 * NP;
+    const double* FOm = FO + (size_t)m * K2 * NP;
+    const int ne = (l_max - m) / 2 + 1;  // degrees l = m, m+2, ...
+    for (int nb0 = 0; nb0 < ne; nb0 += LEG_NB) {
+        __syncthreads();
+        for (int item = tid; item < K2 * LEG_NB; item += 128) {
+            const int j = item / LEG_NB, cc = item - j * LEG_NB;
+            const bool ok = (nb0 + cc) < NP;
+            Be[j * LEG_LDB + cc] = ok ? FEm[(size_t)j * NP + nb0 + cc] : 0.0;
+            Bo[j * LEG_LDB + cc] = ok ? FOm[(size_t)j * NP + nb0 + cc] : 0.0;
+        }
+        __syncthreads();
+        double ere[4][2] = {}, eim[4][2] = {}, ore_[4][2] = {}, oim[4][2] = {};
+        leg_mma_cplx(Ae_re, Ae_im, lda, Be, LEG_LDB, warp * 8, K2, lane, ere, eim);
+        leg_mma_cplx(Ao_re, Ao_im, lda, Bo, LEG_LDB, warp * 8, K2, lane, ore_, oim);
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb) {
+            const int row = mb * 8 + (lane >> 2);
+            const int sh = sh0 + (row & 15), sign = row >> 4;
+            if (sh >= S || (sign && m == 0)) continue;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int col = nb0 + warp * 8 + 2 * (lane & 3) + cc;
+                const int le = m + 2 * col, lo = le + 1;
+                const int ms = sign ? -m : m;
+                if (le <= l_max) c[(size_t)(le * (le + 1) + ms) * S + sh] = make_double2(ere[mb][cc], eim[mb][cc]);
+                if (lo <= l_max) c[(size_t)(lo * (lo + 1) + ms) * S + sh] = make_double2(ore_[mb][cc], oim[mb][cc]);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) legendre_inverse_kernel(const double2* __restrict__ c, double2* __restrict__ a,
+                                                               const double* __restrict__ IE, const double* __restrict__ IO,
+                                                               int S, int l_max, int n_theta, int NP) {
+    extern __shared__ double smem_leg[];
+    const int K2 = n_theta >> 1;
+    const int lda = NP + 4;
+    double* Ce_re = smem_leg;
+    double* Ce_im = Ce_re + LEG_ROWS * lda;
+    double* Co_re = Ce_im + LEG_ROWS * lda;
+    double* Co_im = Co_re + LEG_ROWS * lda;
+    double* Be = Co_im + LEG_ROWS * lda;
+    double* Bo = Be + NP * LEG_LDB;
+    const int m = blockIdx.y;
+    const int sh0 = blockIdx.x * 16;
+    const int M2 = 2 * l_max + 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- stage A: gather coefficients of order +-m, (-1)^m on the -m rows; shells fastest for coalescing
+    for (int item = tid; item < 2 * NP * LEG_ROWS; item += 128) {
+        const int rr = item & 15;
+        int rest = item >> 4;
+        const int sign = rest & 1;
+        rest >>= 1;
+        const int i = rest % NP, par = rest / NP;
+        const int l = m + par + 2 * i;
+        const int sh = sh0 + rr;
+        double2 v = make_double2(0, 0);
+        if (l <= l_max && sh < S && (sign == 0 || m > 0)) {
+            v = ldg2(c + (size_t)(l * (l + 1) + (sign ? -m : m)) * S + sh);
+            if (sign && (m & 1)) { v.x = -v.x; v.y = -v.y; }
+        }
+        const int row = sign * 16 + rr;
+        if (par == 0) { Ce_re[row * lda + i] = v.x; Ce_im[row * lda + i] = v.y; }
+        else          { Co_re[row * lda + i] = v.x; Co_im[row * lda + i] = v.y; }
+    }
+    const double* IEm = IE + (size_t)m * NP * K2;
+    const double* IOm = IO + (size_t)m * NP * K2;
+    for (int j0 = 0; j0 < K2; j0 += LEG_NB) {
+        __syncthreads();
+        for (int item = tid; item < NP * LEG_NB; item += 128) {
+            const int i = item / LEG_NB, cc = item - i * LEG_NB;
+            const bool ok = (j0 + cc) < K2;
+            Be[i * LEG_LDB + cc] = ok ? IEm[(size_t)i * K2 + j0 + cc] : 0.0;
+            Bo[i * LEG_LDB + cc] = ok ? IOm[(size_t)i * K2 + j0 + cc] : 0.0;
+        }
+        __syncthreads();
+        double ere[4][2] = {}, eim[4][2] = {}, ore_[4][2] = {}, oim[4][2] = {};
+        leg_mma_cplx(Ce_re, Ce_im, lda, Be, LEG_LDB, warp * 8, NP, lane, ere, eim);
+        leg_mma_cplx(Co_re, Co_im, lda, Bo, LEG_LDB, warp * 8, NP, lane, ore_, oim);
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb) {
+            const int row = mb * 8 + (lane >> 2);
+            const int sh = sh0 + (row & 15), sign = row >> 4;
+            if (sh >= S || (sign && m == 0)) continue;
+            const int mm = sign ? (M2 - m) : m;
+            double2* dst = a + ((size_t)sh * M2 + mm) * n_theta;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int j = j0 + warp * 8 + 2 * (lane & 3) + cc;
+                if (j < K2) {
+                    dst[j] = make_double2(ere[mb][cc] + ore_[mb][cc], eim[mb][cc] + oim[mb][cc]);
+                    dst[n_theta - 1 - j] = make_double2(ere[mb][cc] - ore_[mb][cc], eim[mb][cc] - oim[mb][cc]);
+                }
+            }
+        }
+    }
+}
+
+static inline size_t legendre_fwd_smem(int n_theta) {
+    const int K2 = n_theta / 2;
+    return (size_t)(4 * LEG_ROWS * (K2 + 4) + 2 * K2 * LEG_LDB) * sizeof(double);
+}
+static inline size_t legendre_inv_smem(int n_theta, int NP) {
+    (void)n_theta;
+    return (size_t)(4 * LEG_ROWS * (NP + 4) + 2 * NP * LEG_LDB) * sizeof(double);
+}

@@ -1,0 +1,289 @@
+// Bandwidth-bound elementwise / reduction kernels of the MTIP loop.  Every kernel
+// touches each grid point once with 128-bit accesses; reductions are two-stage
+// and deterministic (per-block partials summed in a fixed order).
+#pragma once
+#include "common.cuh"
+
+// A batch of per-run grids that may live in one of several slots of a pool
+// (history / best-density bookkeeping without copies, reconstruct.py:924-938).
+struct SlotView {
+    double2* base;
+    const int* slot;        // per-run slot index or nullptr
+    long long slot_stride;  // elements between slots
+    long long run_stride;   // elements between runs
+};
+__device__ __forceinline__ double2* slot_run_ptr(const SlotView& v, int b) {
+    return v.base + (v.slot ? (long long)v.slot[b] * v.slot_stride : 0ll) + (long long)b * v.run_stride;
+}
+
+// misk.py:159-168  square_grid: data * conj(data)
+__global__ void square_kernel(const double2* __restrict__ in, double2* __restrict__ out, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double2 v = ldg2(in + i);
+        out[i] = make_double2(__dadd_rn(__dmul_rn(v.x, v.x), __dmul_rn(v.y, v.y)), 0.0);
+    }
+}
+
+// misk.py:221-225 abs_value
+__global__ void abs_kernel(SlotView in, double2* __restrict__ out, long long per_run) {
+    const int b = blockIdx.y;
+    const double2* src = slot_run_ptr(in, b);
+    double2* dst = out + (long long)b * per_run;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_run; i += (long long)gridDim.x * blockDim.x) {
+        const double2 v = src[i];
+        dst[i] = make_double2(sqrt(__dadd_rn(__dmul_rn(v.x, v.x), __dmul_rn(v.y, v.y))), 0.0);
+    }
+}
+
+// fxs_Projections.py:899-909 project_to_modified_intensity
+__global__ void modify_intensity_kernel(const double2* __restrict__ rho_hat, const double2* __restrict__ i_proj, SlotView out,
+                                        long long per_run) {
+    const int b = blockIdx.y;
+    const double2* rh = rho_hat + (long long)b * per_run;
+    const double2* ip = i_proj + (long long)b * per_run;
+    double2* dst = slot_run_ptr(out, b);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_run; i += (long long)gridDim.x * blockDim.x) {
+        const double2 v = ldg2(rh + i);
+        const double sq = __dadd_rn(__dmul_rn(v.x, v.x), __dmul_rn(v.y, v.y));
+        const double ni = ldg2(ip + i).x;
+        double mult = 0.0;
+        if (sq >= 0.0 && ni >= 0.0) mult = sqrt(ni / sq);
+        dst[i] = make_double2(v.x * mult, v.y * mult);
+    }
+}
+
+// mathLibrary.py:616-624 (sic: q**4) and fxs_Projections.py:294-298 multiply_with_ft_gaussian
+__global__ void mul_gauss_kernel(double2* __restrict__ data, const double* __restrict__ q, double sigma, int n_r, long long shell) {
+    const int r = blockIdx.x % n_r;
+    const long long base = (long long)blockIdx.x * shell;
+    const double a = 1.0 / (2.0 * sigma * sigma);
+    const double pi = 3.141592653589793;
+    const double qq = q[r] * q[r];
+    const double g = sqrt(pi / a) * exp(-(pi * pi) * (qq * qq) / a);
+    for (long long i = blockIdx.y * (long long)blockDim.x + threadIdx.x; i < shell; i += (long long)gridDim.y * blockDim.x) {
+        double2 v = data[base + i];
+        v.x *= g; v.y *= g;
+        data[base + i] = v;
+    }
+}
+
+struct RealDesc {
+    int n_ops;
+    int ops[4];
+    int considered[4];
+    int use_lo, use_hi;
+    double lo, hi, imag_limit;
+    int err_inside;
+};
+
+#define RU_THREADS 256
+// real_projection + HIO/ER + l2_projection_diff partial sums.
+//   rho_new = rho_ift (+ (rho_prev - rho_rt) for radial index >= 1 when rho_rt != nullptr)   reconstruct.py:584-593, misk.py:325-329
+//   projection chain                                                                         fxs_Projections.py:72-130
+//   HIO: where(mask, rho_prev - beta (rho_new - proj), proj) ; ER: proj                      fxs_IO_methods.py:56-68
+//   partial[b][block][0..1] = sum w |rho_new-proj|^2 , sum w |rho_new|^2 over the error region
+__global__ void __launch_bounds__(RU_THREADS) real_update_kernel(const double2* __restrict__ rho_ift, const double2* __restrict__ rho_rt,
+                                                                 SlotView rho_prev, SlotView rho_next, const uint8_t* __restrict__ support,
+                                                                 const int* __restrict__ support_slot, long long support_slot_stride,
+                                                                 const int* __restrict__ enforce, const uint8_t* __restrict__ init_support,
+                                                                 const double* __restrict__ wt, RealDesc rd, int method, double beta,
+                                                                 int n_theta, int n_phi, long long per_run, double* __restrict__ partial) {
+    const int b = blockIdx.y;
+    const double2* ri = rho_ift + (long long)b * per_run;
+    const double2* rt = rho_rt ? rho_rt + (long long)b * per_run : nullptr;
+    const double2* rp = slot_run_ptr(rho_prev, b);
+    double2* rn = slot_run_ptr(rho_next, b);
+    const uint8_t* sup = support + (support_slot ? (long long)support_slot[b] * support_slot_stride : 0ll) + (long long)b * per_run;
+    const bool enf = enforce ? (enforce[b] != 0) : true;
+    const long long shell = (long long)n_theta * n_phi;
+    double s_diff = 0.0, s_val = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_run; i += (long long)gridDim.x * blockDim.x) {
+        double2 v = ldg2(ri + i);
+        const double2 prev = rp[i];
+        if (rt && i >= shell) {
+            const double2 t = ldg2(rt + i);
+            v.x += prev.x - t.x;
+            v.y += prev.y - t.y;
+        }
+        const bool in_init = init_support[i] != 0;
+        const bool outside = enf ? (!in_init || sup[i] == 0) : (sup[i] == 0);
+        double2 p = v;
+        bool msel = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k >= rd.n_ops) break;
+            bool changed = false;
+            const int op = rd.ops[k];
+            if (op == 1) {
+                if (outside) { p = make_double2(0.0, 0.0); changed = true; }
+            } else if (op == 2) {
+                const bool lo = rd.use_lo && (p.x < rd.lo);
+                const bool hi = rd.use_hi && (p.x > rd.hi);
+                if (lo) p.x = rd.lo;
+                if (hi) p.x = rd.hi;
+                changed = lo || hi;
+            } else if (op == 3) {
+                if (fabs(p.y) >= rd.imag_limit) { p.y = 0.0; changed = true; }
+            }
+            if (rd.considered[k]) msel = msel || changed;
+        }
+        double2 o = p;
+        if (method == 0 && msel) o = make_double2(prev.x - beta * (v.x - p.x), prev.y - beta * (v.y - p.y));
+        rn[i] = o;
+        if (!rd.err_inside || in_init) {
+            const double w = wt[i / n_phi];
+            const double dx = v.x - p.x, dy = v.y - p.y;
+            s_diff += w * (dx * dx + dy * dy);
+            s_val += w * (v.x * v.x + v.y * v.y);
+        }
+    }
+    __shared__ double red[2][RU_THREADS / 32];
+    s_diff = warp_sum(s_diff);
+    s_val = warp_sum(s_val);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s_diff; red[1][threadIdx.x >> 5] = s_val; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, c = 0.0;
+        for (int w = 0; w < RU_THREADS / 32; ++w) { a += red[0][w]; c += red[1][w]; }
+        partial[((long long)b * gridDim.x + blockIdx.x) * 2 + 0] = a;
+        partial[((long long)b * gridDim.x + blockIdx.x) * 2 + 1] = c;
+    }
+}
+
+// second stage: fixed-order sum of partials -> err[b][2]
+__global__ void reduce_pairs_kernel(const double* __restrict__ partial, int n_blocks, double* __restrict__ err) {
+    const int b = blockIdx.x;
+    double a = 0.0, c = 0.0;
+    for (int i = threadIdx.x; i < n_blocks; i += 32) {
+        a += partial[((long long)b * n_blocks + i) * 2 + 0];
+        c += partial[((long long)b * n_blocks + i) * 2 + 1];
+    }
+    a = warp_sum(a); c = warp_sum(c);
+    if (threadIdx.x == 0) { err[b * 2 + 0] = a; err[b * 2 + 1] = c; }
+}
+
+// shrink wrap: min / max of max(Re c, 0) per run (fxs_Projections.py:245-258)
+__global__ void __launch_bounds__(256) sw_minmax_kernel(const double2* __restrict__ conv, long long per_run, double* __restrict__ partial) {
+    const int b = blockIdx.y;
+    const double2* c = conv + (long long)b * per_run;
+    double mn = INFINITY, mx = -INFINITY;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_run; i += (long long)gridDim.x * blockDim.x) {
+        double v = ldg2(c + i).x;
+        if (v < 0.0) v = 0.0;
+        mn = fmin(mn, v); mx = fmax(mx, v);
+    }
+    __shared__ double red[2][8];
+    mn = warp_min(mn); mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = mn; red[1][threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { mn = fmin(mn, red[0][w]); mx = fmax(mx, red[1][w]); }
+        partial[((long long)b * gridDim.x + blockIdx.x) * 2 + 0] = mn;
+        partial[((long long)b * gridDim.x + blockIdx.x) * 2 + 1] = mx;
+    }
+}
+__global__ void sw_minmax_final_kernel(const double* __restrict__ partial, int n_blocks, double* __restrict__ mm) {
+    const int b = blockIdx.x;
+    double mn = INFINITY, mx = -INFINITY;
+    for (int i = threadIdx.x; i < n_blocks; i += 32) {
+        mn = fmin(mn, partial[((long long)b * n_blocks + i) * 2 + 0]);
+        mx = fmax(mx, partial[((long long)b * n_blocks + i) * 2 + 1]);
+    }
+    mn = warp_min(mn); mx = warp_max(mx);
+    if (threadIdx.x == 0) { mm[b * 2] = mn; mm[b * 2 + 1] = mx; }
+}
+__global__ void sw_mask_kernel(const double2* __restrict__ conv, const double* __restrict__ mm, double threshold,
+                               uint8_t* __restrict__ out, const int* __restrict__ out_slot, long long out_slot_stride, long long per_run) {
+    const int b = blockIdx.y;
+    const double2* c = conv + (long long)b * per_run;
+    uint8_t* dst = out + (out_slot ? (long long)out_slot[b] * out_slot_stride : 0ll) + (long long)b * per_run;
+    const double mn = mm[b * 2], mx = mm[b * 2 + 1];
+    const double lim = mn + threshold * (mx - mn);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_run; i += (long long)gridDim.x * blockDim.x) {
+        double v = ldg2(c + i).x;
+        if (v < 0.0) v = 0.0;
+        dst[i] = (v >= lim) ? 1 : 0;
+    }
+}
+
+// ---- coefficient layout conversion: direct [S][NLM] <-> internal [NLM][S] (complex), 32x32 tiles
+__global__ void transpose_c128_kernel(const double2* __restrict__ in, double2* __restrict__ out, int rows, int cols) {
+    __shared__ double2 tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = r0 + j, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[j][threadIdx.x] = in[(size_t)r * cols + c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) out[(size_t)c * rows + r] = tile[threadIdx.x][j];
+    }
+}
+
+// ---- loop bookkeeping (reconstruct.py:927-939): error history, best-so-far, slot rotation
+struct LoopState {
+    int* rho_cur; int* rho_best; int* rho_next;       // slots in the rho pool
+    int* rh_cur;  int* rh_best;  int* rh_next;        // slots in the rho_hat' pool
+    int* mask_cur; int* mask_best; int* mask_next;    // slots in the support pool
+    int* enforce_cur; int* enforce_best;              // enforce_initial_support at the time
+    double* best_err; double* last_err; double* hist; int hist_cap;
+};
+__device__ __forceinline__ int free_slot(int a, int b) {   // smallest slot in {0,1,2} different from a and b
+    for (int s = 0; s < 3; ++s) if (s != a && s != b) return s;
+    return 0;
+}
+__global__ void loop_update_kernel(LoopState st, const double* __restrict__ err, int it, int n_batch) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_batch) return;
+    const double num = err[b * 2], den = err[b * 2 + 1];
+    const double e = (den != 0.0) ? num / den : INFINITY;
+    if (it < st.hist_cap) st.hist[(long long)b * st.hist_cap + it] = e;
+    st.last_err[b] = e;
+    st.rho_cur[b] = st.rho_next[b];
+    st.rh_cur[b] = st.rh_next[b];
+    if (st.best_err[b] > e) {
+        st.best_err[b] = e;
+        st.rho_best[b] = st.rho_cur[b];
+        st.rh_best[b] = st.rh_cur[b];
+        st.mask_best[b] = st.mask_cur[b];
+        st.enforce_best[b] = st.enforce_cur[b];
+    }
+    st.rho_next[b] = free_slot(st.rho_cur[b], st.rho_best[b]);
+    st.rh_next[b] = free_slot(st.rh_cur[b], st.rh_best[b]);
+}
+// SW bookkeeping (reconstruct.py:877-885): enforce decision from the last main error, new mask becomes current
+__global__ void sw_update_kernel(LoopState st, double error_limit, int have_error, int n_batch) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_batch) return;
+    st.enforce_cur[b] = (have_error && st.last_err[b] > error_limit) ? 1 : 0;
+    st.mask_cur[b] = st.mask_next[b];
+    st.mask_next[b] = free_slot(st.mask_cur[b], st.mask_best[b]);
+}
+// effective support mask = ~_mask[0] (fxs_Projections.py:50-58)
+__global__ void effective_support_kernel(const uint8_t* __restrict__ pool, const int* __restrict__ slot, const int* __restrict__ enforce,
+                                         const uint8_t* __restrict__ init_support, long long slot_stride, long long per_run,
+                                         uint8_t* __restrict__ out) {
+    const int b = blockIdx.y;
+    const uint8_t* src = pool + (long long)slot[b] * slot_stride + (long long)b * per_run;
+    const bool enf = enforce[b] != 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_run; i += (long long)gridDim.x * blockDim.x)
+        out[(long long)b * per_run + i] = (src[i] != 0 && (!enf || init_support[i] != 0)) ? 1 : 0;
+}
+__global__ void gather_slot_kernel(SlotView in, double2* __restrict__ out, long long per_run) {
+    const int b = blockIdx.y;
+    const double2* src = slot_run_ptr(in, b);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_run; i += (long long)gridDim.x * blockDim.x)
+        out[(long long)b * per_run + i] = src[i];
+}
+__global__ void fill_u8_kernel(uint8_t* p, uint8_t v, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void fill_i32_kernel(int* p, int v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void fill_f64_kernel(double* p, double v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}

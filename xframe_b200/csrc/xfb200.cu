@@ -1,0 +1,616 @@
+// xfb200: plan object, C-ABI entry points (include/xfb200.h) and the device-resident MTIP loop driver.
+#include "../../include/xfb200.h"
+#include "common.cuh"
+#include "pointwise.cuh"
+#include "fft.cuh"
+#include "legendre.cuh"
+#include "gemm.cuh"
+#include "procrustes.cuh"
+
+#include <algorithm>
+
+thread_local std::string g_xfb_err;
+
+enum ProfGroup { PG_FFT = 0, PG_LEGENDRE, PG_HANKEL, PG_PROC_GEMM, PG_PROC_JACOBI, PG_PROC_PACK, PG_POINTWISE, PG_REAL_UPDATE, PG_MISC, PG_COUNT };
+static const char* kProfNames[PG_COUNT] = {"fft_phi", "legendre", "hankel", "procrustes_gemm", "procrustes_jacobi",
+                                           "procrustes_pack", "pointwise", "real_update", "misc"};
+
+struct ProfEvent { cudaEvent_t a, b; int group; };
+
+struct xfb_plan {
+    int L = 0, n_r = 0, n_theta = 0, n_phi = 0, max_batch = 0, NLM = 0, M2 = 0, K2 = 0, NP = 0;
+    int hankel_skip = 0, hankel_n_sum = 0;
+    double hk_fwd_scale = 0, hk_inv_scale = 0;
+    long long G = 0, C = 0;
+    // tables
+    double2* tw = nullptr;
+    double *FE = nullptr, *FO = nullptr, *IE = nullptr, *IO = nullptr, *hankel_w = nullptr, *int_wt = nullptr, *q_pts = nullptr;
+    // workspaces
+    double2 *A0 = nullptr, *C0 = nullptr, *C1 = nullptr, *W0 = nullptr, *W1 = nullptr, *W2 = nullptr;
+    HankelTile* hk_tiles = nullptr; int hk_tiles_n = 0, hk_tiles_nb = -1, hk_tiles_cap = 0;
+    // projection
+    bool has_proj = false;
+    std::vector<ProcOrder> orders;
+    ProcOrder* orders_dev = nullptr;
+    int *kind_dev = nullptr, *act_index_dev = nullptr;
+    uint8_t* radial_mask_dev = nullptr;
+    double* v0_dev = nullptr;
+    double inv_sqrt_np = 1.0, sv_cutoff = 1e-15; int max_sweeps = 40;
+    double *pd_dev = nullptr, *vt_dev = nullptr;
+    long long xt_run = 0, g_run = 0, vw_run = 0;
+    double *xt = nullptr, *tt = nullptr, *g = nullptr, *gn = nullptr, *vw = nullptr, *sigma = nullptr;
+    int* sweeps_dev = nullptr;
+    GemmProblem *gemmM_dev = nullptr, *gemmT_dev = nullptr; int *gemmM_tp = nullptr, *gemmT_tp = nullptr;
+    int gemmM_tiles = 0, gemmT_tiles = 0, gemm_nb = -1;
+    size_t jacobi_smem = 0;
+    // real projection
+    bool has_real = false; RealDesc rd{}; uint8_t* init_support_dev = nullptr;
+    // loop state
+    double2 *rho_pool = nullptr, *rh_pool = nullptr; uint8_t* mask_pool = nullptr;
+    LoopState ls{}; int* ls_ints = nullptr; double* ls_dbl = nullptr;
+    int n_batch = 0, it_done = 0; double *partial = nullptr, *err = nullptr, *mm = nullptr; int red_blocks = 0;
+    bool loop_alloc = false;
+    int64_t launches = 0, bytes = 0;
+    // profiling
+    bool prof = false; std::vector<ProfEvent> prof_events; double prof_ms[PG_COUNT] = {}; int64_t prof_n[PG_COUNT] = {};
+};
+
+// ---- launch bookkeeping ---------------------------------------------------------------
+static inline void prof_begin(xfb_plan* p, int group, cudaStream_t st) {
+    if (!p->prof) return;
+    ProfEvent e; e.group = group;
+    cudaEventCreate(&e.a); cudaEventCreate(&e.b);
+    cudaEventRecord(e.a, st);
+    p->prof_events.push_back(e);
+}
+static inline void prof_end(xfb_plan* p, cudaStream_t st) {
+    if (!p->prof) return;
+    cudaEventRecord(p->prof_events.back().b, st);
+}
+#define XFB_LAUNCH(p, group, st, ...)            \
+    do {                                         \
+        prof_begin((p), (group), (st));          \
+        __VA_ARGS__;                             \
+        prof_end((p), (st));                     \
+        (p)->launches++;                         \
+        XFB_CUDA(cudaGetLastError());            \
+    } while (0)
+
+template <typename T>
+static int dev_alloc(xfb_plan* p, T** ptr, size_t n) {
+    XFB_CUDA(cudaMalloc((void**)ptr, n * sizeof(T)));
+    p->bytes += (int64_t)(n * sizeof(T));
+    return 0;
+}
+template <typename T>
+static int dev_upload(xfb_plan* p, T** ptr, const T* host, size_t n) {
+    if (dev_alloc(p, ptr, n)) return 1;
+    XFB_CUDA(cudaMemcpy(*ptr, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static inline SlotView flat_view(const double2* ptr, long long run_stride) {
+    SlotView v; v.base = const_cast<double2*>(ptr); v.slot = nullptr; v.slot_stride = 0; v.run_stride = run_stride; return v;
+}
+static inline int ew_blocks(long long n) { return (int)std::min<long long>(cdiv64(n, 256 * 4), 148 * 16); }
+
+extern "C" {
+
+const char* xfb_last_error(void) { return g_xfb_err.c_str(); }
+
+int xfb_device_count(int* n) { XFB_CUDA(cudaGetDeviceCount(n)); return 0; }
+int xfb_set_device(int dev) { XFB_CUDA(cudaSetDevice(dev)); return 0; }
+
+int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
+    if (!out || !d) XFB_FAIL("null argument");
+    if (d->n_theta % 8 != 0) XFB_FAIL("n_theta=%d must be a multiple of 8", d->n_theta);
+    if (d->n_theta <= d->l_max) XFB_FAIL("n_theta=%d must exceed l_max=%d (exact Gauss quadrature)", d->n_theta, d->l_max);
+    if (d->n_phi <= 2 * d->l_max) XFB_FAIL("n_phi=%d must exceed 2*l_max", d->n_phi);
+    if (d->n_phi < 16 || d->n_phi > 512 || (d->n_phi & (d->n_phi - 1))) XFB_FAIL("n_phi=%d must be a power of two in [16,512]", d->n_phi);
+    if (d->max_batch < 1) XFB_FAIL("max_batch must be >= 1");
+    int ndev = 0;
+    XFB_CUDA(cudaGetDeviceCount(&ndev));
+    if (ndev == 0) XFB_FAIL("no CUDA device: xfb200 has no CPU fallback");
+    xfb_plan* p = new xfb_plan();
+    p->L = d->l_max; p->n_r = d->n_r; p->n_theta = d->n_theta; p->n_phi = d->n_phi; p->max_batch = d->max_batch;
+    p->NLM = (p->L + 1) * (p->L + 1); p->M2 = 2 * p->L + 1; p->K2 = p->n_theta / 2;
+    p->NP = ((p->L / 2 + 1) + 7) / 8 * 8;
+    p->hankel_skip = d->hankel_skip; p->hankel_n_sum = d->hankel_n_sum;
+    p->hk_fwd_scale = d->hankel_fwd_scale; p->hk_inv_scale = d->hankel_inv_scale;
+    p->G = (long long)p->n_r * p->n_theta * p->n_phi;
+    p->C = (long long)p->NLM * p->n_r;
+    const size_t tab = (size_t)(p->L + 1) * p->K2 * p->NP;
+    if (d->legendre_len != (int64_t)(4 * tab)) { delete p; XFB_FAIL("legendre table length %lld != %lld", (long long)d->legendre_len, (long long)(4 * tab)); }
+    // twiddles exp(-2 pi i k / n) in extended precision
+    std::vector<double2> tw(p->n_phi);
+    for (int k = 0; k < p->n_phi; ++k) {
+        const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)p->n_phi;
+        tw[k] = make_double2((double)cosl(ang), (double)sinl(ang));
+    }
+    if (dev_upload(p, &p->tw, tw.data(), tw.size())) return 1;
+    if (dev_upload(p, &p->FE, d->legendre, tab)) return 1;
+    if (dev_upload(p, &p->FO, d->legendre + tab, tab)) return 1;
+    if (dev_upload(p, &p->IE, d->legendre + 2 * tab, tab)) return 1;
+    if (dev_upload(p, &p->IO, d->legendre + 3 * tab, tab)) return 1;
+    if (dev_upload(p, &p->hankel_w, d->hankel_w, (size_t)(p->L + 1) * p->hankel_n_sum * p->n_r)) return 1;
+    if (dev_upload(p, &p->int_wt, d->int_weight, (size_t)p->n_r * p->n_theta)) return 1;
+    if (dev_upload(p, &p->q_pts, d->q_points, (size_t)p->n_r)) return 1;
+    const size_t B = p->max_batch;
+    if (dev_alloc(p, &p->A0, B * p->n_r * p->M2 * p->n_theta)) return 1;
+    if (dev_alloc(p, &p->C0, B * p->C)) return 1;
+    if (dev_alloc(p, &p->C1, B * p->C)) return 1;
+    if (dev_alloc(p, &p->W0, B * p->G)) return 1;
+    if (dev_alloc(p, &p->W1, B * p->G)) return 1;
+    if (dev_alloc(p, &p->W2, B * p->G)) return 1;
+    XFB_CUDA(cudaFuncSetAttribute(legendre_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre_fwd_smem(p->n_theta)));
+    XFB_CUDA(cudaFuncSetAttribute(legendre_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre_inv_smem(p->n_theta, p->NP)));
+    *out = p;
+    return 0;
+}
+
+int xfb_plan_destroy(xfb_plan* p) {
+    if (!p) return 0;
+    void* ptrs[] = {p->tw, p->FE, p->FO, p->IE, p->IO, p->hankel_w, p->int_wt, p->q_pts, p->A0, p->C0, p->C1, p->W0, p->W1, p->W2,
+                    p->hk_tiles, p->orders_dev, p->kind_dev, p->act_index_dev, p->radial_mask_dev, p->v0_dev, p->pd_dev, p->vt_dev,
+                    p->xt, p->tt, p->g, p->gn, p->vw, p->sigma, p->sweeps_dev, p->gemmM_dev, p->gemmT_dev, p->gemmM_tp, p->gemmT_tp,
+                    p->init_support_dev, p->rho_pool, p->rh_pool, p->mask_pool, p->ls_ints, p->ls_dbl, p->partial, p->err, p->mm};
+    for (void* q : ptrs) if (q) cudaFree(q);
+    for (auto& e : p->prof_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    delete p;
+    return 0;
+}
+
+int64_t xfb_plan_workspace_bytes(const xfb_plan* p) { return p ? p->bytes : 0; }
+int64_t xfb_plan_launch_count(const xfb_plan* p) { return p ? p->launches : 0; }
+
+int xfb_profile_enable(xfb_plan* p, int32_t on) {
+    p->prof = on != 0;
+    for (auto& e : p->prof_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    p->prof_events.clear();
+    for (int i = 0; i < PG_COUNT; ++i) { p->prof_ms[i] = 0; p->prof_n[i] = 0; }
+    return 0;
+}
+int xfb_profile_read(xfb_plan* p, int32_t n_max, char* names, double* ms, int64_t* launches, int32_t* n_out) {
+    XFB_CUDA(cudaDeviceSynchronize());
+    for (auto& e : p->prof_events) {
+        float t = 0;
+        XFB_CUDA(cudaEventElapsedTime(&t, e.a, e.b));
+        p->prof_ms[e.group] += t; p->prof_n[e.group]++;
+        cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    }
+    p->prof_events.clear();
+    int n = std::min<int>(n_max, PG_COUNT);
+    for (int i = 0; i < n; ++i) {
+        strncpy(names + i * 32, kProfNames[i], 31); names[i * 32 + 31] = 0;
+        ms[i] = p->prof_ms[i]; launches[i] = p->prof_n[i];
+    }
+    *n_out = n;
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- internal building blocks -----------------------------------------------------------
+static int sht_forward_i(xfb_plan* p, SlotView in, int shells_per_run, double2* c_out, int S, cudaStream_t st) {
+    XFB_LAUNCH(p, PG_FFT, st, if (launch_fft(true, p->n_phi, in, shells_per_run, p->A0, p->tw, S, p->n_theta, p->L, st)) return 1);
+    dim3 g(cdiv(S, 16), p->L + 1);
+    XFB_LAUNCH(p, PG_LEGENDRE, st,
+               legendre_forward_kernel<<<g, 128, legendre_fwd_smem(p->n_theta), st>>>(p->A0, c_out, p->FE, p->FO, S, p->L, p->n_theta, p->NP));
+    return 0;
+}
+static int sht_inverse_i(xfb_plan* p, const double2* c_in, double2* grid_out, int S, cudaStream_t st) {
+    dim3 g(cdiv(S, 16), p->L + 1);
+    XFB_LAUNCH(p, PG_LEGENDRE, st,
+               legendre_inverse_kernel<<<g, 128, legendre_inv_smem(p->n_theta, p->NP), st>>>(c_in, p->A0, p->IE, p->IO, S, p->L, p->n_theta, p->NP));
+    XFB_LAUNCH(p, PG_FFT, st,
+               if (launch_fft(false, p->n_phi, flat_view(p->A0, 0), 1, grid_out, p->tw, S, p->n_theta, p->L, st)) return 1);
+    return 0;
+}
+static int hankel_i(xfb_plan* p, int dir, const double2* c_in, double2* c_out, int nb, cudaStream_t st) {
+    if (p->hk_tiles_nb != nb) {
+        std::vector<HankelTile> tiles;
+        for (int l = p->L; l >= 0; --l) {   // largest orders first
+            const int r0 = l * l * nb, r1 = (l + 1) * (l + 1) * nb;
+            for (int r = r0; r < r1; r += HK_BM) tiles.push_back(HankelTile{l, r, r1});
+        }
+        if ((int)tiles.size() > p->hk_tiles_cap) {
+            if (p->hk_tiles) cudaFree(p->hk_tiles);
+            p->hk_tiles_cap = (int)tiles.size();
+            XFB_CUDA(cudaMalloc((void**)&p->hk_tiles, tiles.size() * sizeof(HankelTile)));
+        }
+        XFB_CUDA(cudaMemcpyAsync(p->hk_tiles, tiles.data(), tiles.size() * sizeof(HankelTile), cudaMemcpyHostToDevice, st));
+        XFB_CUDA(cudaStreamSynchronize(st));
+        p->hk_tiles_n = (int)tiles.size(); p->hk_tiles_nb = nb;
+    }
+    dim3 g(p->hk_tiles_n, cdiv(p->n_r, HK_BN));
+    XFB_LAUNCH(p, PG_HANKEL, st,
+               hankel_kernel<<<g, 256, 0, st>>>(c_in, c_out, p->hankel_w, p->hk_tiles, p->n_r, p->hankel_n_sum, p->hankel_skip,
+                                                dir == 0 ? p->hk_fwd_scale : p->hk_inv_scale, dir));
+    return 0;
+}
+static int ft_i(xfb_plan* p, int dir, SlotView in, double2* out, int nb, cudaStream_t st) {
+    const int S = nb * p->n_r;
+    if (sht_forward_i(p, in, p->n_r, p->C0, S, st)) return 1;
+    if (hankel_i(p, dir, p->C0, p->C1, nb, st)) return 1;
+    return sht_inverse_i(p, p->C1, out, S, st);
+}
+
+static int build_gemm_groups(xfb_plan* p, int nb, cudaStream_t st) {
+    if (p->gemm_nb == nb) return 0;
+    std::vector<GemmProblem> pm, pt; std::vector<int> tpm, tpt;
+    for (int b = 0; b < nb; ++b) {
+        for (const ProcOrder& o : p->orders) {
+            GemmProblem a{};
+            a.A = p->pd_dev + o.pd_off; a.a_rs = p->n_r; a.a_cs = 1;
+            a.B = p->xt + (size_t)b * p->xt_run + o.xt_off; a.b_rs = 1; a.b_cs = p->n_r;
+            a.C = p->g + (size_t)b * p->g_run + o.g_off; a.c_rs = o.n_c; a.c_cs = 1;
+            a.M = o.n_cols; a.N = o.n_c; a.K = p->n_r; a.alpha = 1.0;
+            a.tile0 = (int)tpm.size(); a.tiles_n = cdiv(a.N, GG_BN);
+            for (int t = 0; t < cdiv(a.M, GG_BM) * a.tiles_n; ++t) tpm.push_back((int)pm.size());
+            pm.push_back(a);
+            GemmProblem c{};
+            c.A = p->gn + (size_t)b * p->g_run + o.g_off; c.a_rs = 1; c.a_cs = o.n_c;
+            c.B = p->vw + (size_t)b * p->vw_run + o.vw_off; c.b_rs = p->n_r; c.b_cs = 1;
+            c.C = p->tt + (size_t)b * p->xt_run + o.xt_off; c.c_rs = p->n_r; c.c_cs = 1;
+            c.M = o.n_c; c.N = p->n_r; c.K = o.n_cols; c.alpha = 1.0;
+            c.tile0 = (int)tpt.size(); c.tiles_n = cdiv(c.N, GG_BN);
+            for (int t = 0; t < cdiv(c.M, GG_BM) * c.tiles_n; ++t) tpt.push_back((int)pt.size());
+            pt.push_back(c);
+        }
+    }
+    XFB_CUDA(cudaMemcpyAsync(p->gemmM_dev, pm.data(), pm.size() * sizeof(GemmProblem), cudaMemcpyHostToDevice, st));
+    XFB_CUDA(cudaMemcpyAsync(p->gemmT_dev, pt.data(), pt.size() * sizeof(GemmProblem), cudaMemcpyHostToDevice, st));
+    XFB_CUDA(cudaMemcpyAsync(p->gemmM_tp, tpm.data(), tpm.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    XFB_CUDA(cudaMemcpyAsync(p->gemmT_tp, tpt.data(), tpt.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    XFB_CUDA(cudaStreamSynchronize(st));
+    p->gemmM_tiles = (int)tpm.size(); p->gemmT_tiles = (int)tpt.size(); p->gemm_nb = nb;
+    return 0;
+}
+
+// I coefficients (internal layout) -> projected coefficients
+static int project_i(xfb_plan* p, const double2* c_in, double2* c_out, int nb, cudaStream_t st) {
+    if (!p->has_proj) XFB_FAIL("projection constants not set (xfb_plan_set_projection)");
+    const int S = nb * p->n_r;
+    const int na = (int)p->orders.size();
+    if (na > 0) {
+        if (build_gemm_groups(p, nb, st)) return 1;
+        XFB_LAUNCH(p, PG_PROC_PACK, st,
+                   procrustes_pack_kernel<<<dim3(na, nb), 256, 0, st>>>(c_in, p->xt, p->orders_dev, p->n_r, S, p->xt_run));
+        XFB_LAUNCH(p, PG_PROC_GEMM, st, grouped_gemm_kernel<<<p->gemmM_tiles, 128, 0, st>>>(p->gemmM_dev, p->gemmM_tp));
+        XFB_LAUNCH(p, PG_PROC_JACOBI, st,
+                   procrustes_jacobi_kernel<<<na * nb, 512, p->jacobi_smem, st>>>(p->g, p->gn, p->vw, p->vt_dev, p->sigma, p->orders_dev, na,
+                                                                                   p->n_r, p->g_run, p->vw_run, (long long)na * p->n_r,
+                                                                                   p->sv_cutoff, 1e-15, p->max_sweeps, p->sweeps_dev));
+        XFB_LAUNCH(p, PG_PROC_GEMM, st, grouped_gemm_kernel<<<p->gemmT_tiles, 128, 0, st>>>(p->gemmT_dev, p->gemmT_tp));
+    }
+    XFB_LAUNCH(p, PG_PROC_PACK, st,
+               procrustes_unpack_kernel<<<dim3(p->L + 1, nb), 256, 0, st>>>(c_in, c_out, p->tt, p->orders_dev, p->kind_dev, p->act_index_dev,
+                                                                            p->radial_mask_dev, p->v0_dev, p->inv_sqrt_np, p->L, p->n_r, S,
+                                                                            p->xt_run));
+    return 0;
+}
+
+static int transpose_i(xfb_plan* p, const double2* in, double2* out, int rows, int cols, cudaStream_t st) {
+    dim3 g(cdiv(cols, 32), cdiv(rows, 32)), b(32, 8);
+    XFB_LAUNCH(p, PG_MISC, st, transpose_c128_kernel<<<g, b, 0, st>>>(in, out, rows, cols));
+    return 0;
+}
+
+static int ensure_loop_alloc(xfb_plan* p) {
+    if (p->loop_alloc) return 0;
+    const size_t B = p->max_batch;
+    if (dev_alloc(p, &p->rho_pool, 3 * B * p->G)) return 1;
+    if (dev_alloc(p, &p->rh_pool, 3 * B * p->G)) return 1;
+    if (dev_alloc(p, &p->mask_pool, 3 * B * p->G)) return 1;
+    if (dev_alloc(p, &p->ls_ints, 11 * B)) return 1;
+    const int hist_cap = 1 << 14;
+    if (dev_alloc(p, &p->ls_dbl, 2 * B + B * hist_cap)) return 1;
+    int* q = p->ls_ints;
+    p->ls.rho_cur = q; p->ls.rho_best = q + B; p->ls.rho_next = q + 2 * B;
+    p->ls.rh_cur = q + 3 * B; p->ls.rh_best = q + 4 * B; p->ls.rh_next = q + 5 * B;
+    p->ls.mask_cur = q + 6 * B; p->ls.mask_best = q + 7 * B; p->ls.mask_next = q + 8 * B;
+    p->ls.enforce_cur = q + 9 * B; p->ls.enforce_best = q + 10 * B;
+    p->ls.best_err = p->ls_dbl; p->ls.last_err = p->ls_dbl + B; p->ls.hist = p->ls_dbl + 2 * B; p->ls.hist_cap = hist_cap;
+    p->loop_alloc = true;
+    return 0;
+}
+static int ensure_reduce_alloc(xfb_plan* p) {
+    if (p->partial) return 0;
+    p->red_blocks = 148 * 2;
+    if (dev_alloc(p, &p->partial, (size_t)p->max_batch * p->red_blocks * 2)) return 1;
+    if (dev_alloc(p, &p->err, (size_t)p->max_batch * 2)) return 1;
+    if (dev_alloc(p, &p->mm, (size_t)p->max_batch * 2)) return 1;
+    return 0;
+}
+
+static int real_update_i(xfb_plan* p, int method, double beta, const double2* rho_ift, const double2* rho_rt, SlotView prev, SlotView next,
+                         const uint8_t* support, const int* support_slot, long long support_slot_stride, const int* enforce, double* err_out,
+                         int nb, cudaStream_t st) {
+    if (!p->has_real) XFB_FAIL("real projection options not set (xfb_plan_set_real)");
+    if (ensure_reduce_alloc(p)) return 1;
+    // blocks per run: keep the whole launch near a few waves of 148 SMs
+    int bpr = std::max(1, std::min(p->red_blocks, (148 * 8 + nb - 1) / nb));
+    bpr = (int)std::min<long long>(bpr, cdiv64(p->G, RU_THREADS));
+    XFB_LAUNCH(p, PG_REAL_UPDATE, st,
+               real_update_kernel<<<dim3(bpr, nb), RU_THREADS, 0, st>>>(rho_ift, rho_rt, prev, next, support, support_slot, support_slot_stride,
+                                                                        enforce, p->init_support_dev, p->int_wt, p->rd, method, beta,
+                                                                        p->n_theta, p->n_phi, p->G, p->partial));
+    XFB_LAUNCH(p, PG_MISC, st, reduce_pairs_kernel<<<nb, 32, 0, st>>>(p->partial, bpr, err_out));
+    return 0;
+}
+
+static int shrinkwrap_i(xfb_plan* p, SlotView rho, double sigma, double threshold, uint8_t* out, const int* out_slot,
+                        long long out_slot_stride, int nb, cudaStream_t st) {
+    if (ensure_reduce_alloc(p)) return 1;
+    const int eb = ew_blocks(p->G);
+    XFB_LAUNCH(p, PG_POINTWISE, st, abs_kernel<<<dim3(eb, nb), 256, 0, st>>>(rho, p->W0, p->G));
+    if (ft_i(p, 0, flat_view(p->W0, p->G), p->W1, nb, st)) return 1;
+    const long long shell = (long long)p->n_theta * p->n_phi;
+    XFB_LAUNCH(p, PG_POINTWISE, st,
+               mul_gauss_kernel<<<dim3(nb * p->n_r, (int)std::min<long long>(cdiv64(shell, 256), 8)), 256, 0, st>>>(p->W1, p->q_pts, sigma, p->n_r, shell));
+    if (ft_i(p, 1, flat_view(p->W1, p->G), p->W0, nb, st)) return 1;
+    int bpr = std::max(1, std::min(p->red_blocks, (148 * 8 + nb - 1) / nb));
+    XFB_LAUNCH(p, PG_POINTWISE, st, sw_minmax_kernel<<<dim3(bpr, nb), 256, 0, st>>>(p->W0, p->G, p->partial));
+    XFB_LAUNCH(p, PG_MISC, st, sw_minmax_final_kernel<<<nb, 32, 0, st>>>(p->partial, bpr, p->mm));
+    XFB_LAUNCH(p, PG_POINTWISE, st, sw_mask_kernel<<<dim3(eb, nb), 256, 0, st>>>(p->W0, p->mm, threshold, out, out_slot, out_slot_stride, p->G));
+    return 0;
+}
+
+extern "C" {
+
+int xfb_plan_set_projection(xfb_plan* p, const xfb_projection_desc* d) {
+    if (!p || !d) XFB_FAIL("null argument");
+    if (p->has_proj) XFB_FAIL("projection already set on this plan");
+    const int L = p->L, n_r = p->n_r;
+    std::vector<int> kind(L + 1, ORD_PASS), act(L + 1, -1);
+    std::vector<double> pd, vt, v0(n_r, 0.0);
+    std::vector<double> q(n_r);
+    XFB_CUDA(cudaMemcpy(q.data(), p->q_pts, n_r * sizeof(double), cudaMemcpyDeviceToHost));
+    struct Tmp { int l, n_cols; std::vector<double> pd, vt; };
+    std::vector<Tmp> tmp;
+    for (int l = 0; l < d->n_orders && l <= L; ++l) {
+        const int nc = d->n_cols[l];
+        const double* V = d->v[l];
+        if (nc > n_r) XFB_FAIL("order %d: n_cols=%d exceeds N_r=%d", l, nc, n_r);
+        if (l == 0) {
+            kind[0] = ORD_ZEROTH;
+            for (int k = 0; k < n_r; ++k) v0[k] = V[(size_t)k * nc];
+            continue;
+        }
+        bool zero = true;
+        for (size_t i = 0; i < (size_t)n_r * nc; ++i) if (V[i] != 0.0) { zero = false; break; }
+        if (zero) { kind[l] = ORD_ZERO; continue; }
+        kind[l] = ORD_ACTIVE;
+        Tmp t; t.l = l; t.n_cols = nc; t.pd.resize((size_t)nc * n_r); t.vt.resize((size_t)nc * n_r);
+        for (int i = 0; i < nc; ++i)
+            for (int k = 0; k < n_r; ++k) {
+                const double v = V[(size_t)k * nc + i];
+                t.vt[(size_t)i * n_r + k] = v;
+                t.pd[(size_t)i * n_r + k] = v * (q[k] * q[k]);     // V^T diag(q)^2  (fxs_Projections.py:753-754)
+            }
+        tmp.push_back(std::move(t));
+    }
+    std::sort(tmp.begin(), tmp.end(), [](const Tmp& a, const Tmp& b) { return a.l > b.l; });   // largest first
+    long long pd_off = 0, xt_off = 0, g_off = 0, vw_off = 0;
+    size_t smem_max = 0;
+    for (size_t i = 0; i < tmp.size(); ++i) {
+        ProcOrder o{};
+        o.l = tmp[i].l; o.n_cols = tmp[i].n_cols; o.n_c = 2 * o.l + 1;
+        o.pd_off = pd_off; o.xt_off = xt_off; o.g_off = g_off; o.vw_off = vw_off;
+        pd_off += (long long)o.n_cols * n_r; xt_off += (long long)o.n_c * n_r; g_off += (long long)o.n_cols * o.n_c; vw_off += (long long)o.n_cols * n_r;
+        act[o.l] = (int)i;
+        p->orders.push_back(o);
+        pd.insert(pd.end(), tmp[i].pd.begin(), tmp[i].pd.end());
+        vt.insert(vt.end(), tmp[i].vt.begin(), tmp[i].vt.end());
+        smem_max = std::max(smem_max, (size_t)o.n_cols * o.n_c * 8 + (size_t)o.n_cols * 12 + 64);
+    }
+    p->xt_run = xt_off; p->g_run = g_off; p->vw_run = vw_off;
+    p->jacobi_smem = smem_max;
+    if (smem_max > 227 * 1024) XFB_FAIL("Procrustes problem too large for shared memory (%zu bytes)", smem_max);
+    if (dev_upload(p, &p->kind_dev, kind.data(), kind.size())) return 1;
+    if (dev_upload(p, &p->act_index_dev, act.data(), act.size())) return 1;
+    if (dev_upload(p, &p->radial_mask_dev, d->radial_mask, (size_t)(L + 1) * n_r)) return 1;
+    if (dev_upload(p, &p->v0_dev, v0.data(), v0.size())) return 1;
+    const size_t B = p->max_batch, na = p->orders.size();
+    if (na > 0) {
+        if (dev_upload(p, &p->orders_dev, p->orders.data(), na)) return 1;
+        if (dev_upload(p, &p->pd_dev, pd.data(), pd.size())) return 1;
+        if (dev_upload(p, &p->vt_dev, vt.data(), vt.size())) return 1;
+        if (dev_alloc(p, &p->xt, B * p->xt_run)) return 1;
+        if (dev_alloc(p, &p->tt, B * p->xt_run)) return 1;
+        if (dev_alloc(p, &p->g, B * p->g_run)) return 1;
+        if (dev_alloc(p, &p->gn, B * p->g_run)) return 1;
+        if (dev_alloc(p, &p->vw, B * p->vw_run)) return 1;
+        if (dev_alloc(p, &p->sigma, B * na * n_r)) return 1;
+        if (dev_alloc(p, &p->sweeps_dev, B * na)) return 1;
+        if (dev_alloc(p, &p->gemmM_dev, B * na)) return 1;
+        if (dev_alloc(p, &p->gemmT_dev, B * na)) return 1;
+        size_t tiles_m = 0, tiles_t = 0;
+        for (const ProcOrder& o : p->orders) {
+            tiles_m += (size_t)cdiv(o.n_cols, GG_BM) * cdiv(o.n_c, GG_BN);
+            tiles_t += (size_t)cdiv(o.n_c, GG_BM) * cdiv(n_r, GG_BN);
+        }
+        if (dev_alloc(p, &p->gemmM_tp, B * tiles_m)) return 1;
+        if (dev_alloc(p, &p->gemmT_tp, B * tiles_t)) return 1;
+        XFB_CUDA(cudaFuncSetAttribute(procrustes_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    } else {
+        // dummy so the unpack kernel has valid pointers
+        ProcOrder o{};
+        if (dev_upload(p, &p->orders_dev, &o, 1)) return 1;
+        if (dev_alloc(p, &p->tt, 1)) return 1;
+    }
+    p->inv_sqrt_np = 1.0 / d->sqrt_n_particles;
+    p->sv_cutoff = d->sv_cutoff > 0 ? d->sv_cutoff : 1e-15;
+    p->max_sweeps = d->max_sweeps > 0 ? d->max_sweeps : 40;
+    p->has_proj = true;
+    return 0;
+}
+
+int xfb_plan_set_real(xfb_plan* p, const xfb_real_desc* d, const uint8_t* init_support_host) {
+    if (!p || !d || !init_support_host) XFB_FAIL("null argument");
+    if (d->n_ops < 0 || d->n_ops > 4) XFB_FAIL("n_ops out of range");
+    p->rd.n_ops = d->n_ops;
+    for (int i = 0; i < 4; ++i) { p->rd.ops[i] = d->ops[i]; p->rd.considered[i] = d->hio_considered[i]; }
+    p->rd.use_lo = d->use_lo; p->rd.use_hi = d->use_hi; p->rd.lo = d->lo; p->rd.hi = d->hi; p->rd.imag_limit = d->imag_limit;
+    p->rd.err_inside = d->error_inside_initial_support;
+    if (!p->init_support_dev) { if (dev_alloc(p, &p->init_support_dev, (size_t)p->G)) return 1; }
+    XFB_CUDA(cudaMemcpy(p->init_support_dev, init_support_host, (size_t)p->G, cudaMemcpyHostToDevice));
+    p->has_real = true;
+    return 0;
+}
+
+// ---- operator level -------------------------------------------------------------------------
+int xfb_sht_forward(xfb_plan* p, const double* grid, double* direct, int32_t n_shells, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_shells < 1 || n_shells > p->max_batch * p->n_r) XFB_FAIL("n_shells=%d outside plan capacity", n_shells);
+    if (sht_forward_i(p, flat_view((const double2*)grid, 0), n_shells, p->C0, n_shells, st)) return 1;
+    return transpose_i(p, p->C0, (double2*)direct, p->NLM, n_shells, st);
+}
+int xfb_sht_inverse(xfb_plan* p, const double* direct, double* grid, int32_t n_shells, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_shells < 1 || n_shells > p->max_batch * p->n_r) XFB_FAIL("n_shells=%d outside plan capacity", n_shells);
+    if (transpose_i(p, (const double2*)direct, p->C0, n_shells, p->NLM, st)) return 1;
+    return sht_inverse_i(p, p->C0, (double2*)grid, n_shells, st);
+}
+int xfb_hankel_apply(xfb_plan* p, int32_t dir, const double* in, double* out, int32_t nb, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nb < 1 || nb > p->max_batch) XFB_FAIL("n_batch=%d outside plan capacity", nb);
+    const int S = nb * p->n_r;
+    if (transpose_i(p, (const double2*)in, p->C0, S, p->NLM, st)) return 1;
+    if (hankel_i(p, dir, p->C0, p->C1, nb, st)) return 1;
+    return transpose_i(p, p->C1, (double2*)out, p->NLM, S, st);
+}
+int xfb_ft(xfb_plan* p, int32_t dir, const double* in, double* out, int32_t nb, void* stream) {
+    if (nb < 1 || nb > p->max_batch) XFB_FAIL("n_batch=%d outside plan capacity", nb);
+    return ft_i(p, dir, flat_view((const double2*)in, p->G), (double2*)out, nb, (cudaStream_t)stream);
+}
+int xfb_project_invariants(xfb_plan* p, const double* in, double* out, int32_t nb, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nb < 1 || nb > p->max_batch) XFB_FAIL("n_batch=%d outside plan capacity", nb);
+    const int S = nb * p->n_r;
+    if (transpose_i(p, (const double2*)in, p->C0, S, p->NLM, st)) return 1;
+    if (project_i(p, p->C0, p->C1, nb, st)) return 1;
+    return transpose_i(p, p->C1, (double2*)out, p->NLM, S, st);
+}
+int xfb_get_unknowns(xfb_plan*, int32_t, int32_t, double*, void*) { XFB_FAIL("xfb_get_unknowns: not implemented in this round"); }
+
+int xfb_modify_intensity(xfb_plan* p, const double* rho_hat, const double* i_proj, double* out, int32_t nb, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nb < 1 || nb > p->max_batch) XFB_FAIL("n_batch=%d outside plan capacity", nb);
+    XFB_LAUNCH(p, PG_POINTWISE, st,
+               modify_intensity_kernel<<<dim3(ew_blocks(p->G), nb), 256, 0, st>>>((const double2*)rho_hat, (const double2*)i_proj,
+                                                                                  flat_view((const double2*)out, p->G), p->G));
+    return 0;
+}
+int xfb_real_update(xfb_plan* p, int32_t method, double beta, const double* rho_ift, const double* rho_rt, const double* rho_prev,
+                    const uint8_t* support, const int32_t* enforce, double* rho_next, double* err, int32_t nb, void* stream) {
+    if (nb < 1 || nb > p->max_batch) XFB_FAIL("n_batch=%d outside plan capacity", nb);
+    return real_update_i(p, method, beta, (const double2*)rho_ift, (const double2*)rho_rt, flat_view((const double2*)rho_prev, p->G),
+                         flat_view((const double2*)rho_next, p->G), support, nullptr, 0, enforce, err, nb, (cudaStream_t)stream);
+}
+int xfb_shrinkwrap(xfb_plan* p, const double* rho, double sigma, double threshold, uint8_t* support_out, int32_t nb, void* stream) {
+    if (nb < 1 || nb > p->max_batch) XFB_FAIL("n_batch=%d outside plan capacity", nb);
+    return shrinkwrap_i(p, flat_view((const double2*)rho, p->G), sigma, threshold, support_out, nullptr, 0, nb, (cudaStream_t)stream);
+}
+
+// ---- loop level -----------------------------------------------------------------------------
+static SlotView pool_view(double2* pool, const int* slot, const xfb_plan* p) {
+    SlotView v; v.base = pool; v.slot = slot; v.slot_stride = (long long)p->max_batch * p->G; v.run_stride = p->G; return v;
+}
+
+int xfb_mtip_init(xfb_plan* p, const double* rho0, int32_t nb, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nb < 1 || nb > p->max_batch) XFB_FAIL("n_batch=%d outside plan capacity", nb);
+    if (!p->has_proj || !p->has_real) XFB_FAIL("plan needs projection and real options before xfb_mtip_init");
+    if (ensure_loop_alloc(p) || ensure_reduce_alloc(p)) return 1;
+    p->n_batch = nb; p->it_done = 0;
+    const int B = p->max_batch, tb = 128, gb = cdiv(B, tb);
+    auto fill_i = [&](int* q, int v) { fill_i32_kernel<<<gb, tb, 0, st>>>(q, v, B); p->launches++; };
+    fill_i(p->ls.rho_cur, 0); fill_i(p->ls.rho_best, 0); fill_i(p->ls.rho_next, 1);
+    fill_i(p->ls.rh_cur, 0); fill_i(p->ls.rh_best, 0); fill_i(p->ls.rh_next, 1);
+    fill_i(p->ls.mask_cur, 0); fill_i(p->ls.mask_best, 0); fill_i(p->ls.mask_next, 1);
+    fill_i(p->ls.enforce_cur, 1); fill_i(p->ls.enforce_best, 1);
+    fill_f64_kernel<<<gb, tb, 0, st>>>(p->ls.best_err, INFINITY, B);
+    fill_f64_kernel<<<gb, tb, 0, st>>>(p->ls.last_err, INFINITY, B);
+    fill_u8_kernel<<<ew_blocks((long long)B * p->G), 256, 0, st>>>(p->mask_pool, 1, (long long)B * p->G);
+    p->launches += 3;
+    XFB_CUDA(cudaGetLastError());
+    // reconstruct.py:959-962: rho_hat0 = FT(rho0); rho = IFT(rho_hat0); both go to slot 0
+    if (ft_i(p, 0, flat_view((const double2*)rho0, p->G), p->rh_pool, nb, st)) return 1;
+    if (ft_i(p, 1, flat_view(p->rh_pool, p->G), p->rho_pool, nb, st)) return 1;
+    return 0;
+}
+
+int xfb_mtip_iterate(xfb_plan* p, int32_t method, int32_t ft_stab, int32_t n_iter, const double* betas, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = p->n_batch;
+    if (nb < 1) XFB_FAIL("xfb_mtip_init has not been called");
+    const int S = nb * p->n_r;
+    const int eb = ew_blocks(p->G);
+    for (int it = 0; it < n_iter; ++it) {
+        // 1. rho_hat = FT(rho)                                   (reconstruct.py:585)
+        if (ft_i(p, 0, pool_view(p->rho_pool, p->ls.rho_cur, p), p->W0, nb, st)) return 1;
+        // 2. |rho_hat|^2 -> I_lm                                 (:519-520)
+        XFB_LAUNCH(p, PG_POINTWISE, st, square_kernel<<<ew_blocks((long long)nb * p->G), 256, 0, st>>>(p->W0, p->W1, (long long)nb * p->G));
+        if (sht_forward_i(p, flat_view(p->W1, p->G), p->n_r, p->C0, S, st)) return 1;
+        // 3. projection onto the invariants                      (:521-523)
+        if (project_i(p, p->C0, p->C1, nb, st)) return 1;
+        // 4. I_proj on the grid, modified intensity              (:524-525)
+        if (sht_inverse_i(p, p->C1, p->W1, S, st)) return 1;
+        XFB_LAUNCH(p, PG_POINTWISE, st,
+                   modify_intensity_kernel<<<dim3(eb, nb), 256, 0, st>>>(p->W0, p->W1, pool_view(p->rh_pool, p->ls.rh_next, p), p->G));
+        // 5. back to real space (+ ft_stab correction terms)     (:586-588 / :579)
+        if (ft_i(p, 1, pool_view(p->rh_pool, p->ls.rh_next, p), p->W1, nb, st)) return 1;
+        if (ft_stab) { if (ft_i(p, 1, flat_view(p->W0, p->G), p->W2, nb, st)) return 1; }
+        // 6. real projection + HIO/ER + error                    (:589-590)
+        if (real_update_i(p, method, betas ? betas[it] : 0.0, p->W1, ft_stab ? p->W2 : nullptr, pool_view(p->rho_pool, p->ls.rho_cur, p),
+                          pool_view(p->rho_pool, p->ls.rho_next, p), p->mask_pool, p->ls.mask_cur, (long long)p->max_batch * p->G,
+                          p->ls.enforce_cur, p->err, nb, st)) return 1;
+        // 7. bookkeeping                                         (:924-939)
+        XFB_LAUNCH(p, PG_MISC, st, loop_update_kernel<<<cdiv(nb, 128), 128, 0, st>>>(p->ls, p->err, p->it_done, nb));
+        p->it_done++;
+    }
+    return 0;
+}
+
+int xfb_mtip_shrinkwrap(xfb_plan* p, double sigma, double threshold, double error_limit, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = p->n_batch;
+    if (nb < 1) XFB_FAIL("xfb_mtip_init has not been called");
+    if (shrinkwrap_i(p, pool_view(p->rho_pool, p->ls.rho_cur, p), sigma, threshold, p->mask_pool, p->ls.mask_next,
+                     (long long)p->max_batch * p->G, nb, st)) return 1;
+    XFB_LAUNCH(p, PG_MISC, st, sw_update_kernel<<<cdiv(nb, 128), 128, 0, st>>>(p->ls, error_limit, p->it_done > 0 ? 1 : 0, nb));
+    return 0;
+}
+
+int xfb_mtip_get_grid(xfb_plan* p, int32_t which, void* out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = p->n_batch;
+    if (nb < 1) XFB_FAIL("xfb_mtip_init has not been called");
+    const int eb = ew_blocks(p->G);
+    switch (which) {
+        case 0: XFB_LAUNCH(p, PG_MISC, st, gather_slot_kernel<<<dim3(eb, nb), 256, 0, st>>>(pool_view(p->rho_pool, p->ls.rho_cur, p), (double2*)out, p->G)); break;
+        case 1: XFB_LAUNCH(p, PG_MISC, st, gather_slot_kernel<<<dim3(eb, nb), 256, 0, st>>>(pool_view(p->rh_pool, p->ls.rh_cur, p), (double2*)out, p->G)); break;
+        case 2: XFB_LAUNCH(p, PG_MISC, st, gather_slot_kernel<<<dim3(eb, nb), 256, 0, st>>>(pool_view(p->rho_pool, p->ls.rho_best, p), (double2*)out, p->G)); break;
+        case 3: XFB_LAUNCH(p, PG_MISC, st, gather_slot_kernel<<<dim3(eb, nb), 256, 0, st>>>(pool_view(p->rh_pool, p->ls.rh_best, p), (double2*)out, p->G)); break;
+        case 4: XFB_LAUNCH(p, PG_MISC, st, effective_support_kernel<<<dim3(eb, nb), 256, 0, st>>>(p->mask_pool, p->ls.mask_cur, p->ls.enforce_cur, p->init_support_dev, (long long)p->max_batch * p->G, p->G, (uint8_t*)out)); break;
+        case 5: XFB_LAUNCH(p, PG_MISC, st, effective_support_kernel<<<dim3(eb, nb), 256, 0, st>>>(p->mask_pool, p->ls.mask_best, p->ls.enforce_best, p->init_support_dev, (long long)p->max_batch * p->G, p->G, (uint8_t*)out)); break;
+        default: XFB_FAIL("which=%d unknown", which);
+    }
+    return 0;
+}
+
+int xfb_mtip_get_errors(xfb_plan* p, double* hist, int32_t cap, double* best, int32_t* n_done, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = p->n_batch;
+    if (nb < 1) XFB_FAIL("xfb_mtip_init has not been called");
+    const int n = std::min(std::min(p->it_done, (int)cap), p->ls.hist_cap);
+    if (hist && n > 0)
+        XFB_CUDA(cudaMemcpy2DAsync(hist, (size_t)cap * sizeof(double), p->ls.hist, (size_t)p->ls.hist_cap * sizeof(double), (size_t)n * sizeof(double), nb,
+                                   cudaMemcpyDeviceToDevice, st));
+    if (best) XFB_CUDA(cudaMemcpyAsync(best, p->ls.best_err, nb * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (n_done) *n_done = p->it_done;
+    return 0;
+}
+
+}  // extern "C"

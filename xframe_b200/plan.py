@@ -1,0 +1,268 @@
+"""Plan: owns the device tables / workspaces of one (L, N_r, n_theta, n_phi, batch) configuration and exposes
+the hot-path operators on torch CUDA tensors (torch is plumbing only: device memory + streams).
+
+Shapes follow the reference:
+  grid   [nb, N_r, n_theta, n_phi] complex128
+  direct [nb, N_r, (L+1)^2]       complex128   (index l(l+1)+m; shtns_plugin.py:110-112,250-261)
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, tables
+
+HIO, ER = 0, 1
+_OPS = {'support': 1, 'value_threshold': 2, 'limit_imag': 3}
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Plan:
+    def __init__(self, l_max, n_r, max_q, n_theta=0, n_phi=0, reciprocity_coefficient=2.0, ft_type='midpoint',
+                 max_batch=1, device=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.XfbError("no CUDA device visible: xframe_b200 has no CPU fallback")
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+        torch.cuda.set_device(self.device)
+        _lib.check(self.lib.xfb_set_device(self.device.index))
+        self.l_max, self.n_r = int(l_max), int(n_r)
+        self.n_theta, self.n_phi = tables.default_angular_sizes(self.l_max, n_theta, n_phi)
+        self.max_batch = int(max_batch)
+        self.n_lm = (self.l_max + 1) ** 2
+        self.rc, self.ft_type, self.max_q = float(reciprocity_coefficient), ft_type, float(max_q)
+        self.rs, self.qs = tables.radial_grids(ft_type, self.max_q, self.n_r, self.rc)
+        self.cos_theta, self.gauss_w = tables.gauss_grid(self.n_theta)
+        self.thetas = np.arccos(self.cos_theta)                         # shtns_plugin.py:133
+        self.phis = 2 * np.pi * np.arange(self.n_phi) / self.n_phi      # shtns_plugin.py:132
+        leg, self.NP = tables.pack_legendre(self.l_max, self.n_theta, self.n_phi)
+        self.hankel_w = tables.hankel_weights(self.l_max, self.n_r, self.rc, ft_type)
+        fs, iscale = tables.hankel_scales(float(np.max(self.rs)), self.n_r, self.rc)
+        self.int_weight = tables.integration_weights(self.rs, self.n_theta)
+        d = _lib.PlanDesc()
+        d.l_max, d.n_r, d.n_theta, d.n_phi, d.max_batch = self.l_max, self.n_r, self.n_theta, self.n_phi, self.max_batch
+        d.hankel_skip = 1 if ft_type in ('trapz', 'Zernike') else 0
+        keep = [np.ascontiguousarray(a, dtype=np.float64) for a in
+                (self.cos_theta, self.gauss_w, leg, self.hankel_w, self.int_weight, self.rs, self.qs)]
+        d.cos_theta, d.gauss_w, d.legendre = _dp(keep[0]), _dp(keep[1]), _dp(keep[2])
+        d.legendre_len = keep[2].size
+        d.hankel_w, d.hankel_n_sum = _dp(keep[3]), self.hankel_w.shape[1]
+        d.hankel_fwd_scale, d.hankel_inv_scale = fs, iscale
+        d.int_weight, d.r_points, d.q_points = _dp(keep[4]), _dp(keep[5]), _dp(keep[6])
+        h = C.c_void_p()
+        _lib.check(self.lib.xfb_plan_create(C.byref(h), C.byref(d)))
+        self.h = h
+        self.n_batch = 0
+        self.initial_support = None
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.xfb_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _c128(self, t, shape_tail):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.complex128 and t.is_contiguous()):
+            raise TypeError("expected a contiguous CUDA complex128 tensor")
+        if tuple(t.shape[-len(shape_tail):]) != tuple(shape_tail):
+            raise ValueError(f"trailing shape {tuple(t.shape)} does not end with {tuple(shape_tail)}")
+        return t
+
+    @property
+    def grid_shape(self):
+        return (self.n_r, self.n_theta, self.n_phi)
+
+    def workspace_bytes(self):
+        return int(self.lib.xfb_plan_workspace_bytes(self.h))
+
+    def launch_count(self):
+        return int(self.lib.xfb_plan_launch_count(self.h))
+
+    # ------------------------------------------------------------------ transforms
+    def sht_forward(self, grid):
+        """sh.forward_d (shtns_plugin.py:250-255): [..., n_theta, n_phi] -> [..., (L+1)^2]."""
+        self._c128(grid, (self.n_theta, self.n_phi))
+        lead = grid.shape[:-2]
+        n = int(np.prod(lead)) if lead else 1
+        out = torch.empty(lead + (self.n_lm,), dtype=torch.complex128, device=grid.device)
+        _lib.check(self.lib.xfb_sht_forward(self.h, _ptr(grid), _ptr(out), n, _stream()))
+        return out
+
+    def sht_inverse(self, direct):
+        """sh.inverse_d (shtns_plugin.py:257-261)."""
+        self._c128(direct, (self.n_lm,))
+        lead = direct.shape[:-1]
+        n = int(np.prod(lead)) if lead else 1
+        out = torch.empty(lead + (self.n_theta, self.n_phi), dtype=torch.complex128, device=direct.device)
+        _lib.check(self.lib.xfb_sht_inverse(self.h, _ptr(direct), _ptr(out), n, _stream()))
+        return out
+
+    def _nb(self, t, tail):
+        self._c128(t, tail)
+        lead = t.shape[:-len(tail)]
+        return int(np.prod(lead)) if lead else 1
+
+    def hankel(self, direct, inverse=False):
+        """zht / izht of generate_spherical_ht_gpu (hankel_transforms.py:660-766) on [nb, N_r, (L+1)^2]."""
+        nb = self._nb(direct, (self.n_r, self.n_lm))
+        out = torch.empty_like(direct)
+        _lib.check(self.lib.xfb_hankel_apply(self.h, 1 if inverse else 0, _ptr(direct), _ptr(out), nb, _stream()))
+        return out
+
+    def ft(self, grid, inverse=False):
+        """ft / ift of generate_ft (fourier_transforms.py:57-85)."""
+        nb = self._nb(grid, self.grid_shape)
+        out = torch.empty_like(grid)
+        _lib.check(self.lib.xfb_ft(self.h, 1 if inverse else 0, _ptr(grid), _ptr(out), nb, _stream()))
+        return out
+
+    def ift(self, grid):
+        return self.ft(grid, inverse=True)
+
+    # ------------------------------------------------------------------ projection constants
+    def set_projection(self, projection_matrices, radial_mask, number_of_particles=1.0, sv_cutoff=1e-15, max_sweeps=40):
+        """projection_matrices: list over used orders of the FINAL V_l (after regrid / odd->0 / V_0 / *2,
+        fxs_Projections.py:679-714), shape [N_r, n_l]; must be real (imag == 0)."""
+        n = len(projection_matrices)
+        vs, ncols = [], (C.c_int32 * n)()
+        for l, v in enumerate(projection_matrices):
+            v = np.asarray(v)
+            if np.iscomplexobj(v):
+                if np.abs(v.imag).max() > 0:
+                    raise _lib.XfbError(f"projection matrix of order {l} has a non-zero imaginary part: the real-arithmetic "
+                                        "Procrustes path of xframe_b200 needs real V_l (as produced by fxs extract)")
+                v = v.real
+            v = np.ascontiguousarray(v, dtype=np.float64)
+            if v.shape[0] != self.n_r:
+                raise ValueError(f"order {l}: expected {self.n_r} radial rows, got {v.shape[0]}")
+            vs.append(v)
+            ncols[l] = v.shape[1]
+        arr = (C.POINTER(C.c_double) * n)(*[_dp(v) for v in vs])
+        rm = np.ascontiguousarray(np.broadcast_to(np.asarray(radial_mask, dtype=bool), (self.l_max + 1, self.n_r)), dtype=np.uint8)
+        d = _lib.ProjectionDesc()
+        d.n_orders, d.n_cols, d.v = n, ncols, arr
+        d.radial_mask = rm.ctypes.data_as(C.POINTER(C.c_uint8))
+        d.sqrt_n_particles = float(np.sqrt(number_of_particles))
+        d.sv_cutoff, d.max_sweeps = float(sv_cutoff), int(max_sweeps)
+        _lib.check(self.lib.xfb_plan_set_projection(self.h, C.byref(d)))
+
+    def set_real(self, apply, initial_support, value_threshold=(0, False), limit_imag=2.0, considered=('all',),
+                 error_inside_initial_support=True):
+        """Options of RealProjection (fxs_Projections.py:72-130) and of the real l2 error (fxs_IO_methods.py:287-300)."""
+        d = _lib.RealDesc()
+        apply = list(apply)
+        if len(apply) > 4:
+            raise ValueError("at most 4 real projections")
+        d.n_ops = len(apply)
+        for i, name in enumerate(apply):
+            if name not in _OPS:
+                raise _lib.XfbError(f"real projection '{name}' is not supported by xframe_b200 ({sorted(_OPS)})")
+            d.ops[i] = _OPS[name]
+            d.hio_considered[i] = 1 if ('all' in considered or name in considered) else 0
+
+        def num(v):
+            return isinstance(v, (float, int)) and not isinstance(v, bool)
+        d.use_lo, d.use_hi = int(num(value_threshold[0])), int(num(value_threshold[1]))
+        d.lo = float(value_threshold[0]) if d.use_lo else 0.0
+        d.hi = float(value_threshold[1]) if d.use_hi else 0.0
+        d.imag_limit = float(limit_imag)
+        d.error_inside_initial_support = int(bool(error_inside_initial_support))
+        sup = np.ascontiguousarray(np.asarray(initial_support, dtype=bool), dtype=np.uint8)
+        if sup.shape != self.grid_shape:
+            raise ValueError(f"initial_support shape {sup.shape} != {self.grid_shape}")
+        self.initial_support = sup.astype(bool)
+        _lib.check(self.lib.xfb_plan_set_real(self.h, C.byref(d), sup.ctypes.data_as(C.c_void_p)))
+
+    # ------------------------------------------------------------------ operators
+    def project_invariants(self, direct):
+        """approximate_unknowns + mtip_projection (fxs_Projections.py:752-872) on [nb, N_r, (L+1)^2]."""
+        nb = self._nb(direct, (self.n_r, self.n_lm))
+        out = torch.empty_like(direct)
+        _lib.check(self.lib.xfb_project_invariants(self.h, _ptr(direct), _ptr(out), nb, _stream()))
+        return out
+
+    def modify_intensity(self, rho_hat, i_proj):
+        nb = self._nb(rho_hat, self.grid_shape)
+        self._c128(i_proj, self.grid_shape)
+        out = torch.empty_like(rho_hat)
+        _lib.check(self.lib.xfb_modify_intensity(self.h, _ptr(rho_hat), _ptr(i_proj), _ptr(out), nb, _stream()))
+        return out
+
+    def real_update(self, method, beta, rho_ift, rho_prev, support, rho_rt=None, enforce=None):
+        """-> (rho_next, err[nb,2]) ; support: uint8/bool [nb, grid] (1 inside the shrink-wrap support)."""
+        nb = self._nb(rho_ift, self.grid_shape)
+        sup = support.to(torch.uint8).contiguous()
+        out = torch.empty_like(rho_ift)
+        err = torch.empty((nb, 2), dtype=torch.float64, device=rho_ift.device)
+        enf = None if enforce is None else enforce.to(torch.int32).contiguous()
+        _lib.check(self.lib.xfb_real_update(self.h, int(method), float(beta), _ptr(rho_ift), _ptr(rho_rt), _ptr(rho_prev),
+                                            _ptr(sup), _ptr(enf), _ptr(out), _ptr(err), nb, _stream()))
+        return out, err
+
+    def shrinkwrap(self, rho, sigma, threshold):
+        nb = self._nb(rho, self.grid_shape)
+        out = torch.empty(rho.shape, dtype=torch.uint8, device=rho.device)
+        _lib.check(self.lib.xfb_shrinkwrap(self.h, _ptr(rho), float(sigma), float(threshold), _ptr(out), nb, _stream()))
+        return out.bool()
+
+    # ------------------------------------------------------------------ device-resident loop
+    def mtip_init(self, rho0):
+        nb = self._nb(rho0, self.grid_shape)
+        _lib.check(self.lib.xfb_mtip_init(self.h, _ptr(rho0), nb, _stream()))
+        self.n_batch = nb
+
+    def mtip_iterate(self, method, ft_stab, betas):
+        betas = np.ascontiguousarray(np.atleast_1d(np.asarray(betas, dtype=np.float64)))
+        _lib.check(self.lib.xfb_mtip_iterate(self.h, int(method), int(bool(ft_stab)), betas.size, _dp(betas), _stream()))
+
+    def mtip_shrinkwrap(self, sigma, threshold, error_limit):
+        _lib.check(self.lib.xfb_mtip_shrinkwrap(self.h, float(sigma), float(threshold), float(error_limit), _stream()))
+
+    def mtip_grid(self, which):
+        names = {'last_real': 0, 'last_reciprocal': 1, 'best_real': 2, 'best_reciprocal': 3, 'last_support': 4, 'best_support': 5}
+        w = names[which]
+        dt = torch.complex128 if w < 4 else torch.uint8
+        out = torch.empty((self.n_batch,) + self.grid_shape, dtype=dt, device=self.device)
+        _lib.check(self.lib.xfb_mtip_get_grid(self.h, w, _ptr(out), _stream()))
+        return out if w < 4 else out.bool()
+
+    def mtip_errors(self, capacity=16384):
+        n = C.c_int32(0)
+        hist = torch.zeros((self.n_batch, capacity), dtype=torch.float64, device=self.device)
+        best = torch.zeros((self.n_batch,), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.xfb_mtip_get_errors(self.h, _ptr(hist), capacity, _ptr(best), C.byref(n), _stream()))
+        return hist[:, :min(n.value, capacity)], best
+
+    # ------------------------------------------------------------------ profiling
+    def profile(self, on=True):
+        _lib.check(self.lib.xfb_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        nmax = 16
+        names = C.create_string_buffer(nmax * 32)
+        ms = (C.c_double * nmax)()
+        ln = (C.c_int64 * nmax)()
+        n = C.c_int32(0)
+        _lib.check(self.lib.xfb_profile_read(self.h, nmax, names, ms, ln, C.byref(n)))
+        out = {}
+        for i in range(n.value):
+            nm = names.raw[i * 32:(i + 1) * 32].split(b'\0')[0].decode()
+            out[nm] = {'ms': ms[i], 'launches': int(ln[i])}
+        return out
