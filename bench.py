@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- MTIP iterations/s at L=63, N_r=128 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[2]): 128 independent MTIP runs of the tutorial reconstruction
+(six-sphere model, L=63, N_r=128, 64x128 angular grid), sharded over the N GPUs of one box (strong scaling:
+128/N runs per GPU, no per-iteration collective).  One "step" = one default MTIP iteration
+(HIO_ft_stab sketch, reconstruct.py:584-593: 4+4 SHT, 3 Hankel, Procrustes projection, real update) of every run.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA, C-ABI)
+  python bench.py --impl reference --steps K --warmup W    reference CPU path (oracle port, all host threads)
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L_MAX, N_R, N_THETA, N_PHI, MAX_Q = 63, 128, 64, 128, 0.322416
+TOTAL_RUNS = 128
+METRIC = "mtip_iterations_per_s_L63_Nr128"
+UNIT = "iterations/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get('hbm_gbs', 6650.0), 'measured (MEASURED_PEAKS.json, copy)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows, self.stop, self.index = [], threading.Event(), index
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}', '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        reasons = set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        mx = max((int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()), default=None)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic bytes per launch of each kernel group (DESIGN.md "kernels"; c128 = 16 B), nb runs per launch
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(nb):
+    G = N_R * N_THETA * N_PHI
+    C = N_R * (L_MAX + 1) ** 2
+    A = N_R * (2 * L_MAX + 1) * N_THETA
+    return {
+        'fft_phi': nb * (G + A) * 16,          # one grid read/written + one phi-Fourier array written/read
+        'legendre': nb * (A + C) * 16,
+        'hankel': nb * 2 * C * 16,
+        'real_update': nb * (4 * G * 16 + G),  # rho_ift, rho_rt, rho_prev in, rho_next out, support mask
+    }
+
+
+def hankel_flops(nb):
+    return nb * 8.0 * N_R * N_R * (L_MAX + 1) ** 2     # complex x real: 2 real GEMMs, 2 flops per MAC
+
+
+# ------------------------------------------------------------------------------------------------
+# reference CPU path (oracle port) -- also the cpu_baseline leg of our arm
+# ------------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_worker(args):
+    seed, budget_s = args
+    import numpy as np
+    from oracle import mtip as O
+    m = O.MTIP(_CPU['settings'], _CPU['data'])
+    m.results['errors'] = {'real': {'l2_projection_diff': []}, 'reciprocal': {}, 'main': []}
+    rho = m.density_guess(np.random.default_rng(seed))
+    rho = m.ift(m.ft(rho))
+    m.beta = 0.5
+    rho = m.io_step('HIO', rho, True)[1]          # warm-up iteration (untimed)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        rho = m.io_step('HIO', rho, True)[1]
+        n += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s:
+            return n, el
+
+
+def cpu_reference(budget_s=15.0, n_workers=None):
+    """it/s of the reference CPU path: one single-threaded process per reconstruction (the reference's process model,
+    xframe/__init__.py:5-8, reconstruct.py:141-157) on every usable host thread; each process iterates for ~budget_s."""
+    import multiprocessing as mp
+    for k in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'NUMEXPR_NUM_THREADS'):
+        os.environ[k] = '1'
+    import numpy as np
+    from oracle import mtip as O
+    from xframe_b200.settings import tutorial_settings
+    sd = tutorial_settings(grid={'max_q': MAX_Q, 'max_order': L_MAX, 'n_phi': N_PHI, 'n_theta': N_THETA, 'n_radial_points': N_R})
+    qs = O.radial_grids('midpoint', MAX_Q, N_R, 2.0)[1]
+    boot = O.MTIP(sd, {'data_radial_points': qs, 'average_intensity': np.ones(N_R), 'max_order': L_MAX,
+                       'data_projection_matrices': [np.zeros((N_R, min(N_R, 2 * l + 1)), complex) for l in range(L_MAX + 1)]})
+    _CPU['settings'] = sd
+    _CPU['data'] = O.invariants_from_density(O.six_sphere_density(boot.real_grid), boot.ft, boot.sh, boot.qs)
+    if n_workers is None:
+        n_workers = len(os.sched_getaffinity(0))
+    ctx = mp.get_context('fork')
+    t0 = time.perf_counter()
+    with ctx.Pool(n_workers) as pool:
+        res = pool.map(_cpu_worker, [(1000 + i, budget_s) for i in range(n_workers)])
+    wall = time.perf_counter() - t0
+    rates = [n / el for n, el in res]
+    its = float(sum(rates))                     # concurrent processes: aggregate = sum of per-process rates
+    cpu_model = ''
+    try:
+        with open('/proc/cpuinfo') as f:
+            cpu_model = next((ln.split(':', 1)[1].strip() for ln in f if ln.startswith('model name')), '')
+    except OSError:
+        pass
+    return {'value': its, 'unit': UNIT, 'cores': n_workers, 'kind': 'port',
+            'sample': f'{n_workers} concurrent single-thread processes, each running HIO_ft_stab iterations of the L=63/N_r=128 tutorial '
+                      f'run for ~{budget_s:.0f}s after 1 warm-up ({sum(n for n, _ in res)} iterations total); numpy oracle port of the '
+                      f'reference CPU path (shtns absent: SHT timed with the numpy restatement); per-process '
+                      f'{min(rates):.3f}..{max(rates):.3f} it/s; pool wall {wall:.1f}s; cpu "{cpu_model}"'}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cb = cpu_reference(budget_s=args.budget)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 / cb['value'] * cb['cores'] if cb['value'] else None, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'fxs 3D reconstruct: independent MTIP runs (six-sphere tutorial model) at L=63/N_r=128, 64x128 angular '
+                                   'grid, HIO_ft_stab iteration; reference CPU path, one process per run', 'runs': cb['cores']},
+            'cpu_baseline': cb, 'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def build_problem(nb, device_index, seeds):
+    import numpy as np
+    import torch
+    from xframe_b200.plan import Plan
+    from xframe_b200 import setup_host as S
+    from xframe_b200.settings import tutorial_settings
+    sd = tutorial_settings(grid={'max_q': MAX_Q, 'max_order': L_MAX, 'n_phi': N_PHI, 'n_theta': N_THETA, 'n_radial_points': N_R})
+    plan = Plan(L_MAX, N_R, MAX_Q, n_theta=N_THETA, n_phi=N_PHI, max_batch=nb, device=device_index)
+    data = S.invariants_from_density(plan, S.six_sphere_density(plan))
+    ps = S.ProjectionSetup(plan.qs, data, L_MAX, sd['projections']['reciprocal'])
+    ps.apply_to(plan)
+    popt = sd['projections']['real']['projections']
+    plan.set_real(popt['apply'], S.initial_support(plan, popt['support']['initial_support']), popt['value_threshold']['threshold'],
+                  popt['limit_imag']['threshold'])
+    rho0 = torch.empty((nb,) + plan.grid_shape, dtype=torch.complex128, device=plan.device)
+    for i, s in enumerate(seeds):
+        rho0[i] = torch.from_numpy(S.density_guess(plan, sd['density_guess'], sd['particle_radius'], ps.integrated_intensity,
+                                                   np.random.default_rng(s))).to(plan.device)
+    return plan, sd, rho0
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from xframe_b200.plan import HIO
+    from xframe_b200.ramps import ExponentialRamp
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    total = args.runs
+    ids = [i for i in range(total) if i % world == rank]       # run i -> rank i mod n_gpu
+    nb = len(ids)
+    plan, sd, rho0 = build_problem(nb, local, [1000 + i for i in ids])
+    plan.mtip_init(rho0)
+    beta = ExponentialRamp(*sd['projections']['real']['HIO']['beta'][0])
+    K, W = args.steps, args.warmup
+    for s in range(W):
+        plan.mtip_iterate(HIO, True, [beta.eval(s)])
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region: K steps, device resident, per-kernel CUDA events on the launching stream
+    plan.profile(True)
+    launches0 = plan.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local) as clk:
+        ev0.record()
+        for s in range(K):
+            plan.mtip_iterate(HIO, True, [beta.eval(W + s)])
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = plan.launch_count() - launches0
+    prof = plan.profile_read()
+    plan.profile(False)
+    t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = total * K / (ms_max / 1e3)
+
+    # ---- end-to-end: every step takes its densities from pinned HOST memory and returns densities + errors to the host
+    Ke = max(1, min(K, 5))
+    h_in = torch.empty((nb,) + plan.grid_shape, dtype=torch.complex128).pin_memory()
+    h_out = torch.empty_like(h_in).pin_memory()
+    h_err = torch.empty((nb, 2), dtype=torch.float64).pin_memory()
+    h_in.copy_(plan.mtip_grid('last_real').cpu())
+    plan.mtip_step_host(HIO, True, beta.eval(W + K), h_in, h_out, h_err)      # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(Ke):
+        plan.mtip_step_host(HIO, True, beta.eval(W + K + 1 + s), h_in, h_out, h_err)
+        h_in, h_out = h_out, h_in
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = total * Ke / float(t.item())
+    finite = bool(torch.isfinite(h_err).all())
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        ab = algorithmic_bytes(nb)
+        groups = {k: v for k, v in prof.items() if v['launches'] > 0}
+        tot_ms = sum(v['ms'] for v in groups.values())
+        dom = max(groups, key=lambda k: groups[k]['ms'])
+        per_launch_ms = groups[dom]['ms'] / groups[dom]['launches']
+        if dom in ab:
+            achieved = ab[dom] / (per_launch_ms * 1e-3) / 1e9
+            roof = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                    'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': ab[dom], 'launch_ms': per_launch_ms,
+                    'share_of_step': groups[dom]['ms'] / tot_ms}
+        else:
+            roof = {'bound': 'hbm', 'kernel': dom, 'achieved': None, 'peak': peak, 'unit': 'GB/s', 'frac': None, 'traffic': None,
+                    'peak_source': peak_src, 'launch_ms': per_launch_ms, 'share_of_step': groups[dom]['ms'] / tot_ms,
+                    'note': 'latency/compute-bound kernel: no HBM roofline applies'}
+        roof['groups'] = {k: {'ms_per_step': v['ms'] / K, 'launches_per_step': v['launches'] / K,
+                              **({'GBps': ab[k] * v['launches'] / (v['ms'] * 1e-3) / 1e9} if k in ab else {}),
+                              **({'TFLOPs_fp64': hankel_flops(nb) * v['launches'] / (v['ms'] * 1e-3) / 1e12} if k == 'hankel' else {})}
+                          for k, v in groups.items()}
+        cb = None
+        if world == 1 and not args.no_cpu:
+            # fresh interpreter: BLAS thread pins must be in the environment before numpy loads, and no CUDA context is forked
+            try:
+                env = dict(os.environ, RANK='0', WORLD_SIZE='1')
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--budget', '15'],
+                                     capture_output=True, text=True, timeout=900, env=env).stdout.strip().splitlines()
+                cb = json.loads(out[-1])['cpu_baseline']
+            except Exception as e:      # noqa: BLE001
+                cb = {'value': None, 'unit': UNIT, 'cores': 0, 'kind': 'port', 'sample': f'failed: {e}'}
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_max / K,
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'fxs 3D reconstruct: 128 independent MTIP runs (six-sphere tutorial model) at L=63/N_r=128, 64x128 '
+                                   'angular grid, sharded over the GPUs; step = one HIO_ft_stab iteration of every run',
+                       'runs_total': total, 'runs_per_gpu': nb, 'l2_policy': 'inputs larger than L2 (per-step working set '
+                                                                            f'{nb * 16 * 11} MiB per GPU)',
+                       'reconstructions_per_hour': value * 3600.0 / 606.0,
+                       'reconstruction_definition': '600 iterations + 6 shrink-wrap steps (tutorial.yaml:52-72)'},
+            'roofline': roof, 'cpu_baseline': cb,
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': nb * int(np.prod(plan.grid_shape)) * 16 * world,
+                    'd2h_bytes_per_step': (nb * int(np.prod(plan.grid_shape)) * 16 + nb * 16) * world, 'steps': Ke,
+                    'api': 'xfb_mtip_step_host (C-ABI, pinned host buffers, H2D + iteration + D2H per step)', 'finite': finite},
+            'gpu_launches': int(launches), 'clocks': clk.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--runs', type=int, default=TOTAL_RUNS)
+    ap.add_argument('--budget', type=float, default=20.0, help='seconds of timed CPU work per process (reference arm)')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

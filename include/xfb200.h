@@ -126,6 +126,11 @@ int xfb_mtip_init(xfb_plan* p, const double* rho0_dev, int32_t n_batch, void* st
 int xfb_mtip_iterate(xfb_plan* p, int32_t method, int32_t ft_stab, int32_t n_iter, const double* betas_host, void* stream);
 /* SW step incl. enforce_initial_support decision (:877-885); error_limit = if_error_bigger_than or +inf */
 int xfb_mtip_shrinkwrap(xfb_plan* p, double sigma, double threshold, double error_limit, void* stream);
+/* One iteration driven from HOST buffers (the end-to-end shape of one reference `process.run`, reconstruct.py:924,
+ * whose inputs and outputs are numpy arrays): H2D of rho [n_batch grids], iterate, D2H of rho_next and of
+ * err [n_batch][2]. Synchronises `stream` before returning. */
+int xfb_mtip_step_host(xfb_plan* p, int32_t method, int32_t ft_stab, double beta, const double* rho_in_host,
+                       double* rho_out_host, double* err_out_host, void* stream);
 /* outputs; which: 0 last real, 1 last reciprocal, 2 best real, 3 best reciprocal (grids);
  *          4 last support, 5 best support (uint8 grids); */
 int xfb_mtip_get_grid(xfb_plan* p, int32_t which, void* out_dev, void* stream);

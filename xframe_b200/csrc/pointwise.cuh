@@ -276,6 +276,12 @@ __global__ void gather_slot_kernel(SlotView in, double2* __restrict__ out, long 
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_run; i += (long long)gridDim.x * blockDim.x)
         out[(long long)b * per_run + i] = src[i];
 }
+__global__ void scatter_slot_kernel(const double2* __restrict__ in, SlotView out, long long per_run) {
+    const int b = blockIdx.y;
+    double2* dst = slot_run_ptr(out, b);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_run; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = in[(long long)b * per_run + i];
+}
 __global__ void fill_u8_kernel(uint8_t* p, uint8_t v, long long n) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }

@@ -600,6 +600,25 @@ int xfb_mtip_get_grid(xfb_plan* p, int32_t which, void* out, void* stream) {
     return 0;
 }
 
+// End-to-end step with HOST buffers (pinned recommended): H2D of the batch's densities, one iteration, D2H of the
+// updated densities and of the per-run (numerator, denominator) of the real-space error.
+int xfb_mtip_step_host(xfb_plan* p, int32_t method, int32_t ft_stab, double beta, const double* rho_in_host, double* rho_out_host,
+                       double* err_out_host, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = p->n_batch;
+    if (nb < 1) XFB_FAIL("xfb_mtip_init has not been called");
+    const size_t bytes = (size_t)nb * p->G * sizeof(double2);
+    const int eb = ew_blocks(p->G);
+    XFB_CUDA(cudaMemcpyAsync(p->W2, rho_in_host, bytes, cudaMemcpyHostToDevice, st));
+    XFB_LAUNCH(p, PG_MISC, st, scatter_slot_kernel<<<dim3(eb, nb), 256, 0, st>>>(p->W2, pool_view(p->rho_pool, p->ls.rho_cur, p), p->G));
+    if (xfb_mtip_iterate(p, method, ft_stab, 1, &beta, stream)) return 1;
+    XFB_LAUNCH(p, PG_MISC, st, gather_slot_kernel<<<dim3(eb, nb), 256, 0, st>>>(pool_view(p->rho_pool, p->ls.rho_cur, p), p->W0, p->G));
+    XFB_CUDA(cudaMemcpyAsync(rho_out_host, p->W0, bytes, cudaMemcpyDeviceToHost, st));
+    XFB_CUDA(cudaMemcpyAsync(err_out_host, p->err, (size_t)nb * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    XFB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
 int xfb_mtip_get_errors(xfb_plan* p, double* hist, int32_t cap, double* best, int32_t* n_done, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = p->n_batch;

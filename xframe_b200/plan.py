@@ -232,6 +232,14 @@ class Plan:
         betas = np.ascontiguousarray(np.atleast_1d(np.asarray(betas, dtype=np.float64)))
         _lib.check(self.lib.xfb_mtip_iterate(self.h, int(method), int(bool(ft_stab)), betas.size, _dp(betas), _stream()))
 
+    def mtip_step_host(self, method, ft_stab, beta, rho_in, rho_out, err_out):
+        """One iteration with HOST tensors (pinned): rho_in/rho_out complex128 [nb, grid], err_out float64 [nb, 2]."""
+        for t in (rho_in, rho_out, err_out):
+            if t.is_cuda or not t.is_contiguous():
+                raise TypeError("mtip_step_host expects contiguous CPU (pinned) tensors")
+        _lib.check(self.lib.xfb_mtip_step_host(self.h, int(method), int(bool(ft_stab)), float(beta), _ptr(rho_in), _ptr(rho_out),
+                                               _ptr(err_out), _stream()))
+
     def mtip_shrinkwrap(self, sigma, threshold, error_limit):
         _lib.check(self.lib.xfb_mtip_shrinkwrap(self.h, float(sigma), float(threshold), float(error_limit), _stream()))
 

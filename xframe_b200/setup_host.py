@@ -1,0 +1,165 @@
+"""One-off host-side setup of a reconstruction (numpy/scipy): everything the reference computes once per run
+before the phasing loop starts.  The loop itself never comes back here.
+
+  * projection constants    ReciprocalProjection.__init__ / _regrid_data / modify_projection_matrices /
+                            generate_radial_mask            (projectLibrary/fxs_Projections.py:471-537,578-714)
+  * initial support         RealProjection.generate_initial_support_mask (fxs_Projections.py:133-155)
+  * initial density guess   MTIP.generate_density_guess_method           (reconstruct.py:1115-1174)
+  * synthetic invariants    simulate_ccd._bl_from_density + deg2_invariant_to_projection_matrices_3d
+                            (simulate_ccd.py:194-230, fxs_invariant_tools.py:1114-1207) -- bench / test inputs
+"""
+import numpy as np
+
+from ._lib import XfbError
+
+
+def midpoint_rule(samples, pts):                               # mathLibrary.py:1492-1497
+    return (pts[1] - pts[0]) * np.sum(samples, axis=0)
+
+
+class ProjectionSetup:
+    """Final V_l, radial mask and integrated intensity for a reconstruction grid `qs`."""
+
+    def __init__(self, qs, data, l_max, ropt):
+        qs = np.asarray(qs, dtype=np.float64)
+        dq = np.asarray(data['data_radial_points'], dtype=np.float64)
+        avg = np.asarray(getattr(data['average_intensity'], 'data', data['average_intensity']), dtype=np.float64)
+        self.integrated_intensity = float(midpoint_rule(avg * dq ** 2, dq) * 2 * np.sqrt(np.pi))      # :476
+        used = np.asarray(ropt['used_order_ids'])
+        used = used[(used <= int(data['max_order'])) & (used <= l_max)]                               # :548-559
+        n_used = min(len(used), l_max + 1)
+        if list(used[:n_used]) != list(range(n_used)):
+            raise XfbError("xframe_b200 supports used_order_ids = arange(n) (the only setting under which the "
+                           "reference indexes its projection matrices consistently, fxs_Projections.py:837-840)")
+        self.n_used = n_used
+        self.number_of_particles = float(ropt['number_of_particles']['initial'])
+        pms = [np.asarray(data['data_projection_matrices'][i]) for i in range(n_used)]
+        same = dq.shape == qs.shape and bool((dq == qs).all())                                         # :642-651
+        if not same:
+            # the reference regrids with scipy griddata column by column (gridLibrary.py:635-651), fill value 0
+            from scipy.interpolate import griddata
+            kind = ropt.get('regrid', {}).get('interpolation', 'cubic')
+            avg = griddata(dq[:, None], avg, qs[:, None], method=kind, fill_value=0.0).reshape(len(qs))
+            pms = [np.stack([griddata(dq[:, None], col, qs[:, None], method=kind, fill_value=0.0).reshape(len(qs))
+                             for col in np.moveaxis(p, 1, 0)], axis=1) for p in pms]
+        proj = [np.array(p, dtype=complex) for p in pms]
+        if ropt.get('odd_orders_to_0', False):                                                         # :693-698
+            for l in range(1, n_used, 2):
+                proj[l][:] = 0
+        if ropt.get('use_averaged_intensity', False):                                                  # :700-708
+            proj[0] = (avg[:, None] * 2 * np.sqrt(np.pi)).astype(complex)
+        for p in proj:                                                                                 # :711-713
+            p *= 2
+        self.projection_matrices = proj
+        nq = len(qs)
+        mask = np.full((l_max + 1, nq), False)
+        data_mask = mask | ((qs >= dq.min()) & (qs <= dq.max()))                                       # :585-586
+        mopt = ropt.get('q_mask', {'type': 'none'})
+        if mopt['type'] == 'none':
+            mask = True
+        elif mopt['type'] == 'manual' and mopt['manual']['type'] == 'region':                          # :603-617
+            lo, hi = mopt['manual']['region']
+            if (lo == False) and (hi != False):      # noqa: E712
+                mask[:] = (qs < hi)[None, :]
+            elif (lo != False) and (hi == False):    # noqa: E712
+                mask[:] = (qs >= lo)[None, :]
+            elif (lo != False) and (hi != False):    # noqa: E712
+                mask[:] = ((qs >= lo) & (qs < hi))[None, :]
+            else:
+                mask[:] = True
+        else:
+            raise XfbError(f"q_mask type '{mopt['type']}' is not supported by xframe_b200 (none, manual/region)")
+        self.radial_mask = np.ascontiguousarray(np.broadcast_to(mask & data_mask, (l_max + 1, nq)))
+
+    def apply_to(self, plan, sv_cutoff=1e-15):
+        plan.set_projection(self.projection_matrices, self.radial_mask, self.number_of_particles, sv_cutoff=sv_cutoff)
+
+    def masked_projection_matrices(self):                                                              # reconstruct.py:998-1002
+        out = []
+        for l, p in enumerate(self.projection_matrices):
+            t = np.array(p)
+            t[~self.radial_mask[l]] = 0
+            out.append(t)
+        return out
+
+
+def initial_support(plan, sup_opt):
+    """max_radius initial support on the plan's real grid (fxs_Projections.py:137-140)."""
+    if sup_opt['type'] != 'max_radius':
+        raise XfbError(f"initial_support type '{sup_opt['type']}' is not supported by xframe_b200 (max_radius)")
+    r = plan.rs[:, None, None]
+    return np.broadcast_to(r < sup_opt['max_radius'], plan.grid_shape).copy()
+
+
+def bump(r, radius, slope):                                      # mathLibrary.py:1456-1466
+    v = np.zeros_like(r)
+    nz = (r > -radius) & (r < radius)
+    v[nz] = np.exp(-slope * radius ** 2 / (radius ** 2 - r[nz] ** 2))
+    return v
+
+
+def integrate(plan, values):
+    """SphericalIntegrator.integrate (mathLibrary.py:1223-1235) with the plan's quadrature weights."""
+    return float(np.sum(plan.int_weight[:, :, None] * values))
+
+
+def density_guess(plan, dopt, particle_radius, integrated_intensity, rng):
+    """'bump' guess with a random amplitude (reconstruct.py:1117-1120,1155-1174); `rng` replaces os.urandom seeding."""
+    if dopt['type'] != 'bump' or dopt['amplitude_function'] != 'random':
+        raise XfbError("density_guess: xframe_b200 supports type 'bump' with amplitude_function 'random'")
+    radius = dopt.get('radius', particle_radius)
+    if isinstance(radius, bool):
+        radius = particle_radius
+    if radius < 0:
+        radius = float(plan.rs.max())
+    A = 1 + 1 / dopt['random']['SNR'] * rng.random(plan.grid_shape)
+    r = np.broadcast_to(plan.rs[:, None, None], plan.grid_shape)
+    density = A * bump(np.ascontiguousarray(r), radius, dopt['bump']['slope'])
+    total = integrate(plan, density * density)
+    return (density * np.sqrt(integrated_intensity / total)).astype(complex)
+
+
+def six_sphere_density(plan, centers=None, radius=70.0, densities=(25, 50, 25, 50, 25, 50)):
+    """The bundled tutorial model (settings/simulate_ccd/tutorial.yaml:11-20)."""
+    if centers is None:
+        centers = [(0.0, 0.0, 0.0)] + [(140.0, np.pi / 2, k * 2 * np.pi / 5) for k in range(5)]
+    r = plan.rs[:, None, None]
+    t = plan.thetas[None, :, None]
+    p = plan.phis[None, None, :]
+    x, y, z = r * np.sin(t) * np.cos(p), r * np.sin(t) * np.sin(p), r * np.cos(t) + 0 * p
+    rho = np.zeros(plan.grid_shape)
+    for (cr, ct, cp), d in zip(centers, densities):
+        c = (cr * np.sin(ct) * np.cos(cp), cr * np.sin(ct) * np.sin(cp), cr * np.cos(ct))
+        rho += d * (np.sqrt((x - c[0]) ** 2 + (y - c[1]) ** 2 + (z - c[2]) ** 2) < radius)
+    return rho
+
+
+def invariants_from_density(plan, density):
+    """density -> B_l -> V_l record in the layout `reconstruct` loads; transforms on the GPU.
+
+    V_l is divided by 2 to cancel fxs_Projections.py:711-713, as SURVEY.md section 8d prescribes for synthetic inputs.
+    """
+    import torch
+    d = torch.from_numpy(np.ascontiguousarray(density.astype(complex)))[None].to(plan.device)
+    fd = plan.ft(d)
+    inten = (fd * fd.conj()).contiguous()
+    I = plan.sht_forward(inten)[0].cpu().numpy()                 # [N_r, (L+1)^2]
+    pms, Bl = [], []
+    for l in range(plan.l_max + 1):
+        Il = I[:, l * l:(l + 1) * (l + 1)]
+        b = Il @ Il.conj().T                                     # fxs_invariant_tools.py:915-923
+        Bl.append(b)
+        b = ((b + b.T.conj()) / 2).real
+        ev, evec = np.linalg.eigh(b)
+        order = np.argsort(ev)[::-1]
+        ev, evec = ev[order], evec[:, order]
+        n = min(len(evec), 2 * l + 1)
+        ev, evec = ev[:n].copy(), evec[:, :n].copy()
+        neg = ev < 0
+        ev[neg] = 0
+        evec[:, neg] = 0
+        pms.append(((evec @ np.diag(np.sqrt(ev))) / 2).astype(complex))
+    avg = np.sqrt(np.diag(Bl[0]).real / (4 * np.pi))             # simulate_ccd.py:227-230
+    return {'dimensions': 3, 'xray_wavelength': 1.23984, 'average_intensity': avg, 'data_radial_points': plan.qs.copy(),
+            'data_angular_points': plan.phis.copy(), 'max_order': plan.l_max, 'data_projection_matrices': pms,
+            'number_of_particles': 1}
