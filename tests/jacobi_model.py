@@ -1,0 +1,70 @@
+"""numpy model of the device Procrustes algorithm (csrc/procrustes.cuh): real-basis change + one-sided Jacobi with
+round-robin ordering and singular-value cut-off.  Used by tests to show the ALGORITHM agrees with the reference's
+SVD-based formula independent of the GPU."""
+import numpy as np
+
+
+def to_real(Il):
+    l = (Il.shape[1] - 1) // 2
+    X = np.empty(Il.shape)
+    X[:, 0] = Il[:, l].real
+    for m in range(1, l + 1):
+        X[:, 2 * m - 1] = np.sqrt(2) * Il[:, l + m].real
+        X[:, 2 * m] = np.sqrt(2) * Il[:, l + m].imag
+    return X
+
+
+def to_cplx(X):
+    l = (X.shape[1] - 1) // 2
+    I = np.empty(X.shape, complex)
+    I[:, l] = X[:, 0]
+    for m in range(1, l + 1):
+        c = (X[:, 2 * m - 1] + 1j * X[:, 2 * m]) / np.sqrt(2)
+        I[:, l + m] = c
+        I[:, l - m] = (-1) ** m * np.conj(c)
+    return I
+
+
+def jacobi_project(V, qs, Il, eps=1e-15, tol=1e-15, max_sweeps=40):
+    """T = V polar(V^T D^2 X) in the real basis, returned as complex coefficients [N_r, 2l+1]; also sweeps used."""
+    V = np.asarray(V).real
+    X = to_real(Il)
+    M = (V.T * qs[None, :] ** 2) @ X
+    G, P = M.T.copy(), V.copy()
+    n = G.shape[1]
+    sweeps = 0
+    for sweeps in range(1, max_sweeps + 1):
+        nrm2 = (G * G).sum(0)
+        thr = eps * eps * nrm2.max()
+        lst = [c for c in range(n) if nrm2[c] > thr]
+        nact = len(lst)
+        if nact < 2:
+            break
+        npad = nact + (nact & 1)
+        rot = False
+        for r in range(npad - 1):
+            for i in range(npad // 2):
+                ka, kb = i, npad - 1 - i
+                pa = 0 if ka == 0 else 1 + ((ka - 1 - r) % (npad - 1))
+                pb = 1 + ((kb - 1 - r) % (npad - 1))
+                if pa >= nact or pb >= nact:
+                    continue
+                p, q = sorted((lst[pa], lst[pb]))
+                a, b = G[:, p].copy(), G[:, q].copy()
+                app, aqq, apq = a @ a, b @ b, a @ b
+                if app <= thr or aqq <= thr or abs(apq) <= tol * np.sqrt(app * aqq):
+                    continue
+                zeta = (aqq - app) / (2 * apq)
+                t = (1.0 if zeta >= 0 else -1.0) / (abs(zeta) + np.sqrt(1 + zeta * zeta))
+                c = 1 / np.sqrt(1 + t * t)
+                s = c * t
+                G[:, p], G[:, q] = c * a - s * b, s * a + c * b
+                pa_, pb_ = P[:, p].copy(), P[:, q].copy()
+                P[:, p], P[:, q] = c * pa_ - s * pb_, s * pa_ + c * pb_
+                rot = True
+        if not rot:
+            break
+    nrm2 = (G * G).sum(0)
+    keep = (nrm2 > eps * eps * nrm2.max()) & (nrm2 > 0)
+    Gn = np.where(keep[None, :], G / np.sqrt(np.where(keep, nrm2, 1.0))[None, :], 0.0)
+    return to_cplx(P @ Gn.T), sweeps

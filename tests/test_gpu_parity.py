@@ -1,0 +1,258 @@
+"""Parity of the CUDA path (through the C-ABI) with the oracle.  Tolerances are relative L2:
+  transforms / Hankel / FT            <= 1e-12  (FP64 path; north_star asks <= 1e-5 fp32-equivalent, tighter for FP64)
+  invariant projection                <= 1e-6   (the reference's LAPACK SVD leaves singular directions below
+                                                 ~1e-15 sigma_max undetermined; orders where that matters agree to
+                                                 ~3e-8, well-conditioned orders to 1e-12 -- see DESIGN.md)
+  elementwise                         <= 1e-14
+  full loop error history / densities <= 1e-6
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden, golden_settings, golden_data, rel_l2
+from oracle import mtip as O
+
+pytestmark = pytest.mark.gpu
+CASES = ['ref_small_ftstab', 'ref_small_plain', 'ref_medium_ops']
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to('cuda')
+
+
+def N(t):
+    return t.cpu().numpy()
+
+
+@pytest.fixture(scope='module', params=CASES)
+def case(request):
+    from xframe_b200.plan import Plan
+    g = load_golden(request.param)
+    sd = golden_settings(g)
+    m = O.MTIP(sd, golden_data(g))
+    plan = Plan(m.l_max, len(m.rs), float(g['max_q']), n_theta=int(g['n_theta']), n_phi=int(g['n_phi']), max_batch=3)
+    plan.set_projection(m.rp.projection_matrices, m.rp.radial_mask, m.rp.number_of_particles[0])
+    popt = sd['projections']['real']['projections']
+    plan.set_real(popt['apply'], m.real_pr.initial_support, popt['value_threshold']['threshold'], popt['limit_imag']['threshold'])
+    yield g, sd, m, plan
+    plan.close()
+
+
+def test_plan_grids_match_reference(case):
+    g, sd, m, plan = case
+    assert np.array_equal(plan.rs, g['rs']) and np.array_equal(plan.qs, g['qs'])
+    assert np.allclose(plan.thetas, g['thetas'], atol=1e-15) and np.allclose(plan.phis, g['phis'], atol=1e-15)
+
+
+def test_sht_golden(case):
+    g, sd, m, plan = case
+    assert rel_l2(N(plan.sht_forward(T(g['x_grid']))), g['sht_forward_direct']) < 1e-12
+    assert rel_l2(N(plan.sht_inverse(T(g['sht_forward_direct']))), g['sht_inverse_of_forward']) < 1e-12
+
+
+def test_hankel_golden(case):
+    g, sd, m, plan = case
+    x = T(g['hankel_in_direct'])[None]
+    assert rel_l2(N(plan.hankel(x))[0], g['hankel_fwd_direct']) < 1e-12
+    assert rel_l2(N(plan.hankel(x, inverse=True))[0], g['hankel_inv_direct']) < 1e-12
+
+
+def test_ft_golden_batched(case):
+    g, sd, m, plan = case
+    b3 = np.stack([g['sht_inverse_of_forward']] * 3)
+    b3[1] *= 2.0
+    f = N(plan.ft(T(b3)))
+    assert rel_l2(f[0], g['ft_x']) < 1e-12 and rel_l2(f[1], 2 * g['ft_x']) < 1e-12 and rel_l2(f[2], g['ft_x']) < 1e-12
+    assert rel_l2(N(plan.ift(T(b3)))[2], g['ift_x']) < 1e-12
+
+
+def test_projection_golden(case):
+    g, sd, m, plan = case
+    ip = N(plan.project_invariants(T(np.stack([g['I_direct'], g['I_direct']]))))
+    assert np.array_equal(ip[0], ip[1])                      # deterministic across the batch
+    assert rel_l2(ip[1], g['Iproj_direct']) < 1e-6
+    splits = np.arange(1, m.l_max + 1) ** 2
+    got, ref = np.split(ip[0], splits, axis=1), np.split(g['Iproj_direct'], splits, axis=1)
+    assert rel_l2(got[0], ref[0]) < 1e-15 and rel_l2(got[2], ref[2]) < 1e-12
+    for l in range(1, m.l_max + 1, 2):
+        assert not got[l].any()                              # odd orders are zeroed on the masked region
+    # B_l = I'_l I'_l^H reproduces the measured invariants on the resolved subspace (fxs_invariant_tools.py:915-923)
+    for l in (0, 2):
+        assert rel_l2(got[l] @ got[l].conj().T, m.rp.deg2_invariants[l]) < 1e-8
+
+
+def test_elementwise_golden(case):
+    g, sd, m, plan = case
+    from xframe_b200.plan import HIO, ER
+    assert rel_l2(N(plan.modify_intensity(T(g['rho_hat0'])[None], T(g['I_proj_grid'])[None]))[0], g['rho_hat_mod']) < 1e-14
+    sup = torch.ones((1,) + plan.grid_shape, dtype=torch.uint8, device='cuda')
+    nxt, err = plan.real_update(HIO, float(g['hio_beta']), T(g['rho_new'])[None], T(g['rho0'])[None], sup)
+    assert rel_l2(N(nxt)[0], g['hio_out']) < 1e-14
+    e = N(err)[0]
+    assert abs(e[0] / e[1] - float(g['real_err'])) < 1e-11 * float(g['real_err'])
+    nxt, _ = plan.real_update(ER, 0.0, T(g['rho_new'])[None], T(g['rho0'])[None], sup)
+    assert np.array_equal(N(nxt)[0], g['rho_proj'])
+    # ft_stab combine: rho_new = ift + (prev - rt) for radial index >= 1 (misk.py:325-329)
+    rt = g['rho0'] * 0.25
+    nxt2, _ = plan.real_update(ER, 0.0, T(g['rho_new'])[None], T(g['rho0'])[None], sup, rho_rt=T(rt)[None])
+    comb = O.add_above_zero_index(g['rho_new'], g['rho0'] - rt)
+    ref = m.real_pr.projection(comb.copy())[0]
+    assert rel_l2(N(nxt2)[0], ref) < 1e-14
+    sw = N(plan.shrinkwrap(T(g['rho0'])[None], 12.5, 0.09))[0]
+    assert (sw != g['sw_mask']).mean() < 1e-3
+
+
+@pytest.mark.parametrize('tag', ['ref_small_ftstab', 'ref_small_plain'])
+def test_full_loop_against_reference_golden(tag):
+    from xframe_b200.plan import Plan
+    from xframe_b200.reconstruct import run_schedule
+    g = load_golden(tag)
+    sd = golden_settings(g)
+    m = O.MTIP(sd, golden_data(g))
+    plan = Plan(m.l_max, len(m.rs), float(g['max_q']), n_theta=int(g['n_theta']), n_phi=int(g['n_phi']), max_batch=2)
+    plan.set_projection(m.rp.projection_matrices, m.rp.radial_mask, m.rp.number_of_particles[0])
+    popt = sd['projections']['real']['projections']
+    plan.set_real(popt['apply'], m.real_pr.initial_support, popt['value_threshold']['threshold'], popt['limit_imag']['threshold'])
+    rho0 = np.stack([g['rho0'], g['rho0'] * 1.0])
+    res = run_schedule(plan, sd, T(rho0))
+    assert res['loop_iterations'] == int(g['loop_iterations'])
+    for b in range(2):
+        assert rel_l2(res['errors'][b], g['loop_main_error']) < 1e-6
+        assert abs(res['best_error'][b] - float(g['loop_final_error'])) < 1e-6 * float(g['loop_final_error'])
+        assert rel_l2(res['initial_density'][b], g['loop_initial_density']) < 1e-12
+        assert rel_l2(res['last_real'][b], g['loop_last_real_density']) < 1e-6
+        assert rel_l2(res['best_real'][b], g['loop_real_density']) < 1e-6
+        assert rel_l2(res['last_reciprocal'][b], g['loop_last_reciprocal_density']) < 1e-6
+        assert rel_l2(res['best_reciprocal'][b], g['loop_reciprocal_density']) < 1e-6
+        assert (res['last_support'][b] != g['loop_last_support_mask']).mean() < 1e-3
+        assert (res['best_support'][b] != g['loop_support_mask']).mean() < 1e-3
+    plan.close()
+
+
+def test_host_buffer_step_matches_device_loop():
+    from xframe_b200.plan import Plan, HIO
+    g = load_golden('ref_small_ftstab')
+    sd = golden_settings(g)
+    m = O.MTIP(sd, golden_data(g))
+    plan = Plan(m.l_max, len(m.rs), float(g['max_q']), n_theta=int(g['n_theta']), n_phi=int(g['n_phi']), max_batch=2)
+    plan.set_projection(m.rp.projection_matrices, m.rp.radial_mask, m.rp.number_of_particles[0])
+    popt = sd['projections']['real']['projections']
+    plan.set_real(popt['apply'], m.real_pr.initial_support, popt['value_threshold']['threshold'], popt['limit_imag']['threshold'])
+    plan.mtip_init(T(np.stack([g['rho0'], g['rho0']])))
+    start = plan.mtip_grid('last_real').cpu()
+    plan.mtip_iterate(HIO, True, [0.5])
+    ref = N(plan.mtip_grid('last_real'))
+    h_in, h_out = start.clone().pin_memory(), torch.empty_like(start).pin_memory()
+    h_err = torch.empty((2, 2), dtype=torch.float64).pin_memory()
+    plan.mtip_step_host(HIO, True, 0.5, h_in, h_out, h_err)
+    assert np.array_equal(h_out.numpy(), ref)
+    assert torch.isfinite(h_err).all()
+    plan.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# BASELINE.json full size (L=63, N_r=128, 64x128): oracle where it finishes in seconds, properties otherwise
+# ----------------------------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def full():
+    from xframe_b200.plan import Plan
+    plan = Plan(63, 128, 0.322416, n_theta=64, n_phi=128, max_batch=4)
+    yield plan
+    plan.close()
+
+
+def test_full_size_transforms_against_oracle(full):
+    plan = full
+    from oracle.sht import sh
+    s = sh(63, n_theta=64, n_phi=128)
+    rng = np.random.default_rng(1234)
+    c = rng.normal(size=(128, 64 ** 2)) + 1j * rng.normal(size=(128, 64 ** 2))
+    x = s.inverse_d(c)                                           # band-limited synthesis
+    assert rel_l2(N(plan.sht_inverse(T(c))), x) < 1e-12
+    assert rel_l2(N(plan.sht_forward(T(x))), c) < 1e-11
+    w = O.hankel_weights(63, 128, 2.0, 'midpoint')
+    ft, ift = O.generate_ft(s, w, plan.rs.max(), 2.0, 63, 'midpoint', 'direct')
+    assert rel_l2(N(plan.ft(T(x)[None]))[0], ft(x)) < 1e-11
+    assert rel_l2(N(plan.ift(T(x)[None]))[0], ift(x)) < 1e-11
+    zht, izht = O.generate_spherical_ht_direct(O.assemble_weights(w, plan.rs.max(), 2.0), 63)
+    assert rel_l2(N(plan.hankel(T(c)[None]))[0], zht(c)) < 1e-12
+    assert rel_l2(N(plan.hankel(T(c)[None], inverse=True))[0], izht(c)) < 1e-12
+
+
+def test_full_size_properties(full):
+    plan = full
+    rng = np.random.default_rng(5)
+    c = T(rng.normal(size=(2, 128, 64 ** 2)) + 1j * rng.normal(size=(2, 128, 64 ** 2)))
+    x = plan.sht_inverse(c)
+    assert rel_l2(N(plan.sht_forward(x)), N(c)) < 1e-11                          # analysis o synthesis = id (band-limited)
+    a, b = x[0:1].contiguous(), x[1:2].contiguous()
+    lin = plan.ft((2.0 * a + (0.5 - 1.5j) * b).contiguous())
+    assert rel_l2(N(lin), N(2.0 * plan.ft(a) + (0.5 - 1.5j) * plan.ft(b))) < 1e-12   # linearity
+    xr = plan.sht_inverse(c).real.to(torch.complex128).contiguous()
+    cr = N(plan.sht_forward(xr))[0]
+    for l, mm in [(1, 1), (5, 3), (40, 17), (63, 63)]:                           # Hermitian symmetry of real fields
+        assert np.abs(cr[:, l * (l + 1) - mm] - (-1) ** mm * np.conj(cr[:, l * (l + 1) + mm])).max() < 1e-11 * np.abs(cr).max()
+
+
+def test_full_size_projection_and_iteration_against_oracle(full):
+    """L=63 / N_r=128 six-sphere inputs: projection step and one whole HIO_ft_stab iteration vs the oracle."""
+    plan = full
+    from xframe_b200 import setup_host as S
+    from xframe_b200.settings import tutorial_settings
+    from xframe_b200.plan import HIO
+    sd = tutorial_settings(grid={'max_q': 0.322416, 'max_order': 63, 'n_phi': 128, 'n_theta': 64, 'n_radial_points': 128})
+    data = S.invariants_from_density(plan, S.six_sphere_density(plan))
+    m = O.MTIP(sd, data)
+    # GPU-made invariants equal the oracle's own (same model, same transforms)
+    ref_data = O.invariants_from_density(O.six_sphere_density(m.real_grid), m.ft, m.sh, m.qs)
+    assert rel_l2(data['average_intensity'], ref_data['average_intensity']) < 1e-10
+    ps = S.ProjectionSetup(plan.qs, data, 63, sd['projections']['reciprocal'])
+    ps.apply_to(plan)
+    popt = sd['projections']['real']['projections']
+    plan.set_real(popt['apply'], S.initial_support(plan, popt['support']['initial_support']), popt['value_threshold']['threshold'],
+                  popt['limit_imag']['threshold'])
+    rho0 = m.density_guess(np.random.default_rng(1000))
+    rho_hat = m.ft(rho0)
+    I = m.sh.forward_l(O.square_grid(rho_hat))
+    Ip = m.rp.mtip_projection(I, m.rp.approximate_unknowns(I))
+    got = N(plan.project_invariants(T(np.concatenate(I, axis=1))[None]))[0]
+    assert rel_l2(got, np.concatenate(Ip, axis=1)) < 1e-6
+    # one full iteration from the same state
+    m.results['errors'] = {'real': {'l2_projection_diff': []}, 'reciprocal': {}, 'main': []}
+    m.beta = 0.5
+    rho = m.ift(rho_hat)
+    plan.mtip_init(T(rho0)[None])
+    assert rel_l2(N(plan.mtip_grid('last_real'))[0], rho) < 1e-11
+    rh_new, rho_next = m.io_step('HIO', rho, True)
+    plan.mtip_iterate(HIO, True, [0.5])
+    assert rel_l2(N(plan.mtip_grid('last_real'))[0], rho_next) < 1e-6
+    assert rel_l2(N(plan.mtip_grid('last_reciprocal'))[0], rh_new) < 1e-6
+    hist, best = plan.mtip_errors()
+    e_ref = m.results['errors']['real']['l2_projection_diff'][-1]
+    assert abs(float(hist[0, 0]) - e_ref) < 1e-6 * e_ref
+
+
+def test_worker_result_schema():
+    """Result-dict keys / dtypes / shapes as the reference's integration test asserts them
+    (tests/test_fxs_integration.py:388-421), on the reference test's own tiny grid sizes."""
+    from xframe_b200.worker import ProjectWorker
+    g = load_golden('ref_small_ftstab')
+    sd = golden_settings(g)
+    sd['GPU'] = {'use': True, 'batch': 2, 'seed': 11}
+    w = ProjectWorker(sd, golden_data(g), n_reconstructions=3)
+    res, _ = w.run()
+    assert len(res) == 3
+    shape = (int(g['n_r']), int(g['n_theta']), int(g['n_phi']))
+    n_it = len(g['loop_main_error'])
+    for r in res:
+        for k in ['real_density', 'last_real_density', 'reciprocal_density', 'last_reciprocal_density', 'initial_density']:
+            assert r[k].dtype == np.complex128 and r[k].shape == shape and np.isfinite(r[k]).all()
+        for k in ['support_mask', 'last_support_mask', 'initial_support']:
+            assert r[k].dtype == bool and r[k].shape == shape
+        assert r['error_dict']['main'].shape == (n_it,) and r['error_dict']['real']['l2_projection_diff'].shape == (n_it,)
+        assert r['loop_iterations'] == int(g['loop_iterations'])
+        assert r['last_deg2_invariant'].shape == (int(g['l_max']) + 1, shape[0], shape[0])
+        assert r['final_error'] == r['error_dict']['main'].min()
+        assert len(r['projection_matrices']) == int(g['l_max']) + 1
+    assert res[0]['final_error'] != res[1]['final_error']       # different seeds -> different runs

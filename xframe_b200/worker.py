@@ -1,0 +1,110 @@
+"""Drop-in for the fxs `reconstruct` ProjectWorker (projects/fxs/reconstruct.py:89-209).
+
+Same constructor / run() contract and result schema (reconstruct.py:1003-1021), but instead of forking one
+process per reconstruction (reconstruct.py:141-157) it runs all requested reconstructions as device-resident
+batches on the local GPU, sharded over ranks when launched under torchrun.
+
+    settings : dict in the schema of settings/reconstruct/default_0.01.yaml (see xframe_b200/settings.py)
+    data     : the invariants record `db.load('invariants')` returns
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import setup_host as S
+from ._lib import XfbError
+from .distributed import shard_run_ids
+from .plan import Plan
+from .reconstruct import run_schedule
+
+
+def number_of_gpus():
+    """Multiprocessing.get_number_of_gpus (Multiprocessing.py:892-898)."""
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+class ProjectWorker:
+    def __init__(self, settings, data, n_reconstructions=None, rank=0, world=1, device=None, seeds=None, initial_densities=None):
+        self.opt = settings
+        self.data = data
+        if settings['dimensions'] != 3:
+            raise XfbError("xframe_b200 implements the 3-D reconstruct path (dimensions: 3)")
+        if not settings['GPU']['use']:
+            raise XfbError("GPU.use is False: xframe_b200 has no CPU path (the reference falls back to CPU, reconstruct.py:96-102)")
+        if number_of_gpus() == 0:
+            raise XfbError("no CUDA device: xframe_b200 has no CPU fallback")
+        mp = settings['multi_process']
+        n = n_reconstructions
+        if n is None:
+            npr = mp.get('n_parallel_reconstructions', False)
+            n = int(npr) if (mp.get('use', True) and not isinstance(npr, bool)) else 1
+        self.n_runs = int(n)
+        self.rank, self.world = rank, world
+        self.run_ids = shard_run_ids(self.n_runs, rank, world)
+        g = settings['grid']
+        max_q = g['max_q']
+        if not isinstance(max_q, float):                                       # reconstruct.py:258-261
+            max_q = float(np.max(data['data_radial_points']))
+        fto = settings['fourier_transform']
+        batch = settings['GPU'].get('batch', 0) or len(self.run_ids)
+        self.batch = max(1, min(int(batch), max(1, len(self.run_ids))))
+        self.plan = Plan(int(g['max_order']), int(g['n_radial_points']), max_q, n_theta=g.get('n_theta', 0), n_phi=g.get('n_phi', 0),
+                         reciprocity_coefficient=fto.get('reciprocity_coefficient', np.pi), ft_type=fto['type'],
+                         max_batch=self.batch, device=device)
+        self.proj = S.ProjectionSetup(self.plan.qs, data, self.plan.l_max, settings['projections']['reciprocal'])
+        self.proj.apply_to(self.plan)
+        popt = settings['projections']['real']['projections']
+        self.initial_support = S.initial_support(self.plan, popt['support']['initial_support'])
+        err = settings['main_loop']['error']['methods']
+        if list(err['real']['calculate']) != ['l2_projection_diff'] or list(err['reciprocal'].get('calculate', [])):
+            raise XfbError("xframe_b200 computes the default error metric (real: [l2_projection_diff], reciprocal: [])")
+        inside = err['real'].get('l2_projection_diff', {}).get('inside_initial_support', False)
+        hio = settings['projections']['real']['HIO']
+        self.plan.set_real(popt['apply'], self.initial_support, popt.get('value_threshold', {}).get('threshold', (False, False)),
+                           popt.get('limit_imag', {}).get('threshold', 0.0), hio.get('considered_projections', ['all']), inside)
+        base = settings['GPU'].get('seed', None)
+        self.seeds = seeds if seeds is not None else [None if base is None else base + i for i in range(self.n_runs)]
+        self.initial_densities = initial_densities
+        self.results = {'stats': {}}
+
+    def _guess(self, run_id):
+        if self.initial_densities is not None:
+            return np.asarray(self.initial_densities[run_id], dtype=complex)
+        rng = np.random.default_rng(self.seeds[run_id])    # None -> OS entropy, like reconstruct.py:1119
+        return S.density_guess(self.plan, self.opt['density_guess'], self.opt['particle_radius'], self.proj.integrated_intensity, rng)
+
+    def run(self):
+        t0 = time.time()
+        plan, out = self.plan, []
+        rs = np.stack(np.meshgrid(plan.rs, plan.thetas, plan.phis, indexing='ij'), axis=-1)
+        qs = np.stack(np.meshgrid(plan.qs, plan.thetas, plan.phis, indexing='ij'), axis=-1)
+        masked_pm = self.proj.masked_projection_matrices()
+        for b0 in range(0, len(self.run_ids), self.batch):
+            ids = self.run_ids[b0:b0 + self.batch]
+            rho0 = torch.from_numpy(np.stack([self._guess(i) for i in ids])).to(plan.device)
+            res = run_schedule(plan, self.opt, rho0)
+            # last_deg2_invariant: B_l = I_l I_l^H of the last density (reconstruct.py:757-765,993)
+            last = torch.from_numpy(res['last_real']).to(plan.device)
+            fd = plan.ft(last)
+            I = plan.sht_forward((fd * fd.conj()).contiguous()).cpu().numpy()
+            for k, rid in enumerate(ids):
+                Il = [I[k][:, l * l:(l + 1) * (l + 1)] for l in range(plan.l_max + 1)]
+                n_it = res['errors'].shape[1]
+                out.append({
+                    'run_id': rid,
+                    'real_density': res['best_real'][k], 'last_real_density': res['last_real'][k],
+                    'reciprocal_density': res['best_reciprocal'][k], 'last_reciprocal_density': res['last_reciprocal'][k],
+                    'final_error': float(res['best_error'][k]), 'initial_density': res['initial_density'][k],
+                    'initial_support': self.initial_support.copy(),
+                    'error_dict': {'main': res['errors'][k].copy(), 'real': {'l2_projection_diff': res['errors'][k].copy()}, 'reciprocal': {}},
+                    'support_mask': res['best_support'][k], 'last_support_mask': res['last_support'][k],
+                    'loop_iterations': res['loop_iterations'], 'fxs_unknowns': None,
+                    'n_particles': np.array([[self.proj.number_of_particles]] * n_it), 'n_particles_gradients': np.array([]),
+                    'n_particles_fraction': np.array([]),
+                    'grid_pair': {'real_grid': rs, 'reciprocal_grid': qs}, 'projection_matrices': masked_pm,
+                    'last_deg2_invariant': np.array([il @ il.T.conj() for il in Il]),
+                })
+        self.results['MTIP'] = out
+        self.results['stats']['run_time'] = time.time() - t0
+        return out, {'worker': self}
