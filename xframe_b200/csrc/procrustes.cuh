@@ -48,131 +48,246 @@ __global__ void procrustes_pack_kernel(const double2* __restrict__ c, double* __
     }
 }
 
-// One CTA per (order, run).  G: [n_cols][n_c] (column i of G^T contiguous) in global, copied to smem.
-// vw: [n_cols][N_r] initialised from vt (V_l^T), rotated in global memory (L2 resident).
-// Outputs: gn = G~ / sigma (zero for dropped columns), sigma [n_cols].
-__global__ void __launch_bounds__(512) procrustes_jacobi_kernel(const double* __restrict__ g_in, double* __restrict__ gn_out,
-                                                                double* __restrict__ vw, const double* __restrict__ vt,
-                                                                double* __restrict__ sigma_out, const ProcOrder* __restrict__ orders,
-                                                                int n_orders, int n_r_grid, long long g_run_stride,
-                                                                long long vw_run_stride, long long sig_run_stride, double sv_cutoff,
-                                                                double tol, int max_sweeps, int* __restrict__ sweeps_out) {
+// One-sided Jacobi, persistent CTAs over the (order, run) problems (largest orders first).
+//   G : [n_cols][n_c] in global (column i of G = M^T contiguous), copied to shared memory with the column
+//       length padded to a multiple of 8 (zeros).
+//   vw: [n_cols][N_r] accumulator initialised from vt (V_l^T).  At the start of every sweep the ACTIVE columns are
+//       staged into shared memory (they fit once dead columns are dropped: cap columns) and written back at the
+//       end of the sweep; only if more than `cap` columns are active are they rotated in global memory (L2).
+//   A pair of columns is handled by JG = 8 lanes (4 pairs per warp, 64 pairs per 512-thread CTA = one whole
+//   round-robin round in flight); dot products are reduced with 3 xor-shuffles inside the 8-lane group; the G
+//   elements stay in registers between the dot and the rotation (one smem read + one write per element).
+//   Outputs: gn = G~ / sigma (zero for dropped columns), sigma [n_cols].
+#define JG 8                 // lanes per column pair
+__host__ __device__ inline int jacobi_stride(int len) {
+    int s = (len + JG - 1) / JG * JG;
+    if ((s & 15) == 0) s += 8;
+    return s;
+}
+#define JMAXE 16             // max elements per lane (column length <= 128)
+
+template <bool WSM>
+__device__ __forceinline__ void jacobi_sweep_rounds(double* __restrict__ Gs, int ldg, int ne, double* __restrict__ Wb, int wstride,
+                                                    int n_r_grid, int wr_e, const int* __restrict__ list, int nact, double thr,
+                                                    double tol, int slot0, int n_slots, int sub, int* s_rot) {
+    const int npad = nact + (nact & 1);
+    const int half = npad >> 1;
+    const int mod = npad - 1;
+    for (int r = 0; r < npad - 1; ++r) {
+        for (int i0 = 0; i0 < half; i0 += n_slots) {      // one pass when half <= 64
+            const int i = i0 + slot0;
+            bool valid = i < half;
+            int p = 0, q = 0, wpi = 0, wqi = 0;
+            if (valid) {
+                const int ka = i, kb = npad - 1 - i;
+                int pa = (ka == 0) ? 0 : 1 + ((ka - 1 - r) % mod + mod) % mod;
+                int pb = 1 + ((kb - 1 - r) % mod + mod) % mod;
+                valid = (pa < nact) && (pb < nact);                // bye against the padding element
+                if (valid) {
+                    p = list[pa]; q = list[pb];
+                    if (p > q) { int t_ = p; p = q; q = t_; t_ = pa; pa = pb; pb = t_; }
+                    wpi = WSM ? pa : p;                            // smem: compact slot ; global: column index
+                    wqi = WSM ? pb : q;
+                }
+            }
+            double* gp = Gs + (size_t)p * ldg + sub;
+            double* gq = Gs + (size_t)q * ldg + sub;
+            double* wp = Wb + (size_t)wpi * wstride + sub;
+            double* wq = Wb + (size_t)wqi * wstride + sub;
+            double xw[JMAXE], yw[JMAXE];
+            if (!WSM && valid) {                                    // global accumulator: prefetch before the dot products
+#pragma unroll
+                for (int t = 0; t < JMAXE; ++t)
+                    if (t < wr_e && sub + JG * t < n_r_grid) { xw[t] = __ldcg(wp + JG * t); yw[t] = __ldcg(wq + JG * t); }
+            }
+            double xg[WSM ? JMAXE : 1], yg[WSM ? JMAXE : 1];    // G stays in registers only when the accumulator is in smem
+            double app = 0.0, aqq = 0.0, apq = 0.0;
+            if (valid) {
+                if constexpr (WSM) {
+#pragma unroll
+                    for (int t = 0; t < JMAXE; ++t)
+                        if (t < ne) {
+                            xg[t] = gp[JG * t]; yg[t] = gq[JG * t];
+                            app += xg[t] * xg[t]; aqq += yg[t] * yg[t]; apq += xg[t] * yg[t];
+                        }
+                } else {
+#pragma unroll 4
+                    for (int t = 0; t < ne; ++t) {
+                        const double x = gp[JG * t], y = gq[JG * t];
+                        app += x * x; aqq += y * y; apq += x * y;
+                    }
+                }
+            }
+#pragma unroll
+            for (int off = 4; off > 0; off >>= 1) {
+                app += __shfl_xor_sync(0xffffffffu, app, off);
+                aqq += __shfl_xor_sync(0xffffffffu, aqq, off);
+                apq += __shfl_xor_sync(0xffffffffu, apq, off);
+            }
+            bool rot = valid && (app > thr) && (aqq > thr);
+            if (rot) rot = apq * apq > (tol * tol) * (app * aqq);
+            if (rot) {
+                const double zeta = (aqq - app) / (2.0 * apq);
+                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double cs = rsqrt(1.0 + t * t), sn = cs * t;
+                if constexpr (WSM) {
+#pragma unroll
+                    for (int tt = 0; tt < JMAXE; ++tt)
+                        if (tt < ne) {
+                            gp[JG * tt] = cs * xg[tt] - sn * yg[tt];
+                            gq[JG * tt] = sn * xg[tt] + cs * yg[tt];
+                        }
+                } else {
+#pragma unroll 4
+                    for (int tt = 0; tt < ne; ++tt) {
+                        const double x = gp[JG * tt], y = gq[JG * tt];
+                        gp[JG * tt] = cs * x - sn * y;
+                        gq[JG * tt] = sn * x + cs * y;
+                    }
+                }
+#pragma unroll
+                for (int tt = 0; tt < JMAXE; ++tt)
+                    if (tt < wr_e && sub + JG * tt < n_r_grid) {
+                        if (WSM) {
+                            const double x = wp[JG * tt], y = wq[JG * tt];
+                            wp[JG * tt] = cs * x - sn * y;
+                            wq[JG * tt] = sn * x + cs * y;
+                        } else {
+                            __stcg(wp + JG * tt, cs * xw[tt] - sn * yw[tt]);
+                            __stcg(wq + JG * tt, sn * xw[tt] + cs * yw[tt]);
+                        }
+                    }
+                if (sub == 0) *s_rot = 1;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(512, 1) procrustes_jacobi_kernel(const double* __restrict__ g_in, double* __restrict__ gn_out,
+                                                                   double* __restrict__ vw, const double* __restrict__ vt,
+                                                                   double* __restrict__ sigma_out, const ProcOrder* __restrict__ orders,
+                                                                   int n_orders, int n_batch, int n_r_grid, long long g_run_stride,
+                                                                   long long vw_run_stride, long long sig_run_stride, double sv_cutoff,
+                                                                   double tol, int max_sweeps, int* __restrict__ sweeps_out,
+                                                                   int smem_doubles) {
     extern __shared__ double smem_j[];
-    const int oi = blockIdx.x % n_orders;      // orders are sorted largest first
-    const int b = blockIdx.x / n_orders;
-    const ProcOrder o = orders[oi];
-    const int n = o.n_cols, len = o.n_c;
-    double* Gs = smem_j;                       // [n][len]
-    double* nrm2 = Gs + (size_t)n * len;       // [n]
-    int* list = (int*)(nrm2 + n);              // [n]
     __shared__ int s_nact, s_rot;
     __shared__ double s_thr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-    const double* g = g_in + (size_t)b * g_run_stride + o.g_off;
-    double* W = vw + (size_t)b * vw_run_stride + o.vw_off;
-    const double* V0 = vt + o.pd_off;
-    for (int i = tid; i < n * len; i += blockDim.x) Gs[i] = g[i];
-    for (int i = tid; i < n * n_r_grid; i += blockDim.x) W[i] = V0[i];
-    __syncthreads();
-    int sweep = 0;
-    for (; sweep < max_sweeps; ++sweep) {
-        // column norms
-        for (int cidx = warp; cidx < n; cidx += nwarp) {
+    const int grp = lane >> 3, sub = lane & (JG - 1);     // 4 groups of 8 lanes per warp
+    const int n_slots = nwarp * 4;
+    const int slot0 = warp * 4 + grp;
+    const int wr_e = (n_r_grid + JG - 1) / JG;            // accumulator elements per lane
+    const int wld = jacobi_stride(n_r_grid);              // smem accumulator column stride
+
+    for (int prob = blockIdx.x; prob < n_orders * n_batch; prob += gridDim.x) {
+        const int oi = prob / n_batch;                     // orders are sorted largest first
+        const int b = prob - oi * n_batch;
+        const ProcOrder o = orders[oi];
+        const int n = o.n_cols, len = o.n_c;
+        const int ne = (len + JG - 1) / JG;                // G elements per lane
+        const int ldg = jacobi_stride(len);                // column stride == 8 (mod 16) doubles: the two pair groups of a
+                                                           // half warp then fall on disjoint shared-memory banks
+        double* Gs = smem_j;                               // [n][ldg]
+        double* nrm2 = Gs + (size_t)n * ldg;               // [n]
+        int* list = (int*)(nrm2 + n);                      // [n]
+        double* Ws = nrm2 + n + (n + 1) / 2;               // [cap][wld]
+        const int cap = (smem_doubles - (n * ldg + n + (n + 1) / 2)) / wld;
+        const double* g = g_in + (size_t)b * g_run_stride + o.g_off;
+        double* W = vw + (size_t)b * vw_run_stride + o.vw_off;
+        const double* V0 = vt + o.pd_off;
+        __syncthreads();                                   // previous problem fully done with smem
+        for (int i = tid; i < n * ldg; i += blockDim.x) {
+            const int c = i / ldg, e = i - c * ldg;
+            Gs[i] = (e < len) ? g[(size_t)c * len + e] : 0.0;
+        }
+        for (int i = tid; i < n * n_r_grid; i += blockDim.x) W[i] = V0[i];
+        __syncthreads();
+        int sweep = 0;
+        for (; sweep < max_sweeps; ++sweep) {
+            // ---- column norms (one 8-lane group per column)
+            for (int c0 = warp * 4; c0 < n; c0 += n_slots) {      // warp-uniform trip count (shuffles need all lanes)
+                const int c = c0 + grp;
+                double s = 0.0;
+                if (c < n)
+                    for (int t = 0; t < ne; ++t) { const double v = Gs[c * ldg + sub + JG * t]; s += v * v; }
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                if (sub == 0 && c < n) nrm2[c] = s;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                double mx = 0.0;
+                for (int c = lane; c < n; c += 32) mx = fmax(mx, nrm2[c]);
+                mx = warp_max(mx);
+                const double thr = sv_cutoff * sv_cutoff * mx;
+                int base = 0;                              // ordered compaction of the active columns
+                for (int c0 = 0; c0 < n; c0 += 32) {
+                    const int c = c0 + lane;
+                    const bool act = (c < n) && (nrm2[c] > thr);
+                    const unsigned bal = __ballot_sync(0xffffffffu, act);
+                    if (act) list[base + __popc(bal & ((1u << lane) - 1u))] = c;
+                    base += __popc(bal);
+                }
+                if (lane == 0) { s_nact = base; s_thr = thr; s_rot = 0; }
+            }
+            __syncthreads();
+            const int nact = s_nact;
+            const double thr = s_thr;
+            if (nact < 2) break;
+            if (nact <= cap) {
+                // stage the active accumulator columns in shared memory for this sweep
+                for (int i = tid; i < nact * n_r_grid; i += blockDim.x) {
+                    const int a = i / n_r_grid, e = i - a * n_r_grid;
+                    Ws[a * wld + e] = __ldcg(W + (size_t)list[a] * n_r_grid + e);
+                }
+                __syncthreads();
+                jacobi_sweep_rounds<true>(Gs, ldg, ne, Ws, wld, n_r_grid, wr_e, list, nact, thr, tol, slot0, n_slots, sub, &s_rot);
+                for (int i = tid; i < nact * n_r_grid; i += blockDim.x) {
+                    const int a = i / n_r_grid, e = i - a * n_r_grid;
+                    __stcg(W + (size_t)list[a] * n_r_grid + e, Ws[a * wld + e]);
+                }
+            } else {
+                jacobi_sweep_rounds<false>(Gs, ldg, ne, W, n_r_grid, n_r_grid, wr_e, list, nact, thr, tol, slot0, n_slots, sub, &s_rot);
+            }
+            __syncthreads();
+            const int rotated = s_rot;
+            __syncthreads();
+            if (!rotated) { ++sweep; break; }
+        }
+        __syncthreads();
+        // ---- final norms -> sigma, normalised columns
+        for (int c0 = warp * 4; c0 < n; c0 += n_slots) {
+            const int c = c0 + grp;
             double s = 0.0;
-            for (int e = lane; e < len; e += 32) { const double v = Gs[cidx * len + e]; s += v * v; }
-            s = warp_sum(s);
-            if (lane == 0) nrm2[cidx] = s;
+            if (c < n)
+                for (int t = 0; t < ne; ++t) { const double v = Gs[c * ldg + sub + JG * t]; s += v * v; }
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            if (sub == 0 && c < n) nrm2[c] = s;
         }
         __syncthreads();
         if (warp == 0) {
             double mx = 0.0;
-            for (int cidx = lane; cidx < n; cidx += 32) mx = fmax(mx, nrm2[cidx]);
+            for (int c = lane; c < n; c += 32) mx = fmax(mx, nrm2[c]);
             mx = warp_max(mx);
-            const double thr = sv_cutoff * sv_cutoff * mx;
-            // ordered compaction of the active columns
-            int base = 0;
-            for (int c0 = 0; c0 < n; c0 += 32) {
-                const int cidx = c0 + lane;
-                const bool act = (cidx < n) && (nrm2[cidx] > thr);
-                const unsigned bal = __ballot_sync(0xffffffffu, act);
-                if (act) list[base + __popc(bal & ((1u << lane) - 1u))] = cidx;
-                base += __popc(bal);
-            }
-            if (lane == 0) { s_nact = base; s_thr = thr; s_rot = 0; }
+            if (lane == 0) s_thr = sv_cutoff * sv_cutoff * mx;
         }
         __syncthreads();
-        const int nact = s_nact;
-        const double thr = s_thr;
-        if (nact < 2) break;
-        const int npad = nact + (nact & 1);
-        const int half = npad >> 1;
-        for (int r = 0; r < npad - 1; ++r) {
-            for (int i = warp; i < half; i += nwarp) {
-                const int ka = i, kb = npad - 1 - i;
-                const int pa = (ka == 0) ? 0 : 1 + ((ka - 1 - r) % (npad - 1) + (npad - 1)) % (npad - 1);
-                const int pb = 1 + ((kb - 1 - r) % (npad - 1) + (npad - 1)) % (npad - 1);
-                if (pa >= nact || pb >= nact) continue;  // bye
-                int p = list[pa], q = list[pb];
-                if (p > q) { const int t_ = p; p = q; q = t_; }
-                double* gp = Gs + (size_t)p * len;
-                double* gq = Gs + (size_t)q * len;
-                double app = 0.0, aqq = 0.0, apq = 0.0;
-                for (int e = lane; e < len; e += 32) {
-                    const double x = gp[e], y = gq[e];
-                    app += x * x; aqq += y * y; apq += x * y;
-                }
-                app = warp_sum(app); aqq = warp_sum(aqq); apq = warp_sum(apq);
-                if (app <= thr || aqq <= thr) continue;
-                if (fabs(apq) <= tol * sqrt(app * aqq)) continue;
-                const double zeta = (aqq - app) / (2.0 * apq);
-                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
-                for (int e = lane; e < len; e += 32) {
-                    const double x = gp[e], y = gq[e];
-                    gp[e] = cs * x - sn * y;
-                    gq[e] = sn * x + cs * y;
-                }
-                double* wp = W + (size_t)p * n_r_grid;
-                double* wq = W + (size_t)q * n_r_grid;
-                for (int e = lane; e < n_r_grid; e += 32) {
-                    const double x = wp[e], y = wq[e];
-                    wp[e] = cs * x - sn * y;
-                    wq[e] = sn * x + cs * y;
-                }
-                if (lane == 0) s_rot = 1;
-            }
-            __syncthreads();
+        const double thr_f = s_thr;
+        double* gn = gn_out + (size_t)b * g_run_stride + o.g_off;
+        for (int i = tid; i < n * len; i += blockDim.x) {
+            const int c = i / len, e = i - c * len;
+            const double s2 = nrm2[c];
+            gn[i] = (s2 > thr_f && s2 > 0.0) ? Gs[c * ldg + e] / sqrt(s2) : 0.0;
         }
-        const int rot = s_rot;
-        __syncthreads();
-        if (!rot) { ++sweep; break; }
+        double* sg = sigma_out + (size_t)b * sig_run_stride + (size_t)oi * n_r_grid;
+        for (int i = tid; i < n; i += blockDim.x) sg[i] = sqrt(nrm2[i]);
+        if (tid == 0 && sweeps_out) sweeps_out[b * n_orders + oi] = sweep;
     }
-    __syncthreads();
-    // final norms -> sigma, normalised columns
-    for (int cidx = warp; cidx < n; cidx += nwarp) {
-        double s = 0.0;
-        for (int e = lane; e < len; e += 32) { const double v = Gs[cidx * len + e]; s += v * v; }
-        s = warp_sum(s);
-        if (lane == 0) nrm2[cidx] = s;
-    }
-    __syncthreads();
-    if (warp == 0) {
-        double mx = 0.0;
-        for (int cidx = lane; cidx < n; cidx += 32) mx = fmax(mx, nrm2[cidx]);
-        mx = warp_max(mx);
-        if (lane == 0) s_thr = sv_cutoff * sv_cutoff * mx;
-    }
-    __syncthreads();
-    const double thr = s_thr;
-    double* gn = gn_out + (size_t)b * g_run_stride + o.g_off;
-    for (int i = tid; i < n * len; i += blockDim.x) {
-        const int cidx = i / len;
-        const double s2 = nrm2[cidx];
-        gn[i] = (s2 > thr && s2 > 0.0) ? Gs[i] / sqrt(s2) : 0.0;
-    }
-    double* sg = sigma_out + (size_t)b * sig_run_stride + (size_t)oi * n_r_grid;
-    for (int i = tid; i < n; i += blockDim.x) sg[i] = sqrt(nrm2[i]);
-    if (tid == 0 && sweeps_out) sweeps_out[b * n_orders + oi] = sweep;
 }
 
 // Tt[b][order][m'][k] (real) + pass-through rules -> c_out [(L+1)^2][S]

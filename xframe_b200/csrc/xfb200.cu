@@ -42,7 +42,7 @@ struct xfb_plan {
     int* sweeps_dev = nullptr;
     GemmProblem *gemmM_dev = nullptr, *gemmT_dev = nullptr; int *gemmM_tp = nullptr, *gemmT_tp = nullptr;
     int gemmM_tiles = 0, gemmT_tiles = 0, gemm_nb = -1;
-    size_t jacobi_smem = 0;
+    size_t jacobi_smem = 0; int n_sm = 148;
     // real projection
     bool has_real = false; RealDesc rd{}; uint8_t* init_support_dev = nullptr;
     // loop state
@@ -278,9 +278,9 @@ static int project_i(xfb_plan* p, const double2* c_in, double2* c_out, int nb, c
                    procrustes_pack_kernel<<<dim3(na, nb), 256, 0, st>>>(c_in, p->xt, p->orders_dev, p->n_r, S, p->xt_run));
         XFB_LAUNCH(p, PG_PROC_GEMM, st, grouped_gemm_kernel<<<p->gemmM_tiles, 128, 0, st>>>(p->gemmM_dev, p->gemmM_tp));
         XFB_LAUNCH(p, PG_PROC_JACOBI, st,
-                   procrustes_jacobi_kernel<<<na * nb, 512, p->jacobi_smem, st>>>(p->g, p->gn, p->vw, p->vt_dev, p->sigma, p->orders_dev, na,
+                   procrustes_jacobi_kernel<<<std::min(na * nb, p->n_sm), 512, p->jacobi_smem, st>>>(p->g, p->gn, p->vw, p->vt_dev, p->sigma, p->orders_dev, na, nb,
                                                                                    p->n_r, p->g_run, p->vw_run, (long long)na * p->n_r,
-                                                                                   p->sv_cutoff, 1e-15, p->max_sweeps, p->sweeps_dev));
+                                                                                   p->sv_cutoff, 1e-15, p->max_sweeps, p->sweeps_dev, (int)(p->jacobi_smem / 8)));
         XFB_LAUNCH(p, PG_PROC_GEMM, st, grouped_gemm_kernel<<<p->gemmT_tiles, 128, 0, st>>>(p->gemmT_dev, p->gemmT_tp));
     }
     XFB_LAUNCH(p, PG_PROC_PACK, st,
@@ -402,11 +402,14 @@ int xfb_plan_set_projection(xfb_plan* p, const xfb_projection_desc* d) {
         p->orders.push_back(o);
         pd.insert(pd.end(), tmp[i].pd.begin(), tmp[i].pd.end());
         vt.insert(vt.end(), tmp[i].vt.begin(), tmp[i].vt.end());
-        smem_max = std::max(smem_max, (size_t)o.n_cols * o.n_c * 8 + (size_t)o.n_cols * 12 + 64);
+        smem_max = std::max(smem_max, (size_t)o.n_cols * jacobi_stride(o.n_c) * 8 + (size_t)o.n_cols * 12 + 64);
     }
     p->xt_run = xt_off; p->g_run = g_off; p->vw_run = vw_off;
+    if (smem_max > 0) smem_max = std::max(smem_max, (size_t)220 * 1024);
     p->jacobi_smem = smem_max;
     if (smem_max > 227 * 1024) XFB_FAIL("Procrustes problem too large for shared memory (%zu bytes)", smem_max);
+    if (n_r > 8 * 16) XFB_FAIL("Procrustes kernel supports N_r <= 128 in this round (got %d)", n_r);
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, dev); }
     if (dev_upload(p, &p->kind_dev, kind.data(), kind.size())) return 1;
     if (dev_upload(p, &p->act_index_dev, act.data(), act.size())) return 1;
     if (dev_upload(p, &p->radial_mask_dev, d->radial_mask, (size_t)(L + 1) * n_r)) return 1;
