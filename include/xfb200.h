@@ -95,6 +95,9 @@ int xfb_plan_destroy(xfb_plan* p);
 int xfb_plan_set_projection(xfb_plan* p, const xfb_projection_desc* d);
 int xfb_plan_set_real(xfb_plan* p, const xfb_real_desc* d, const uint8_t* initial_support_host /*[N_r][n_theta][n_phi]*/);
 int64_t xfb_plan_workspace_bytes(const xfb_plan* p);
+/* ft_stab sketch (reconstruct.py:584-593): 1 (default) evaluates IFT(rho_hat') + (rho - IFT(rho_hat)) as
+ * IFT(rho_hat' - rho_hat) + rho (linearity; one inverse transform instead of two), 0 follows the sketch literally. */
+int xfb_plan_set_fused_ft_stab(xfb_plan* p, int32_t on);
 
 /* ---- operator level: the harmonic-transform / Hankel / FT interfaces ---- */
 /* sh.forward_d / sh.inverse_d  (shtns_plugin.py:250-261): n_shells = n_batch*N_r or any count <= max_batch*N_r */

@@ -130,6 +130,30 @@ def test_full_loop_against_reference_golden(tag):
     plan.close()
 
 
+def test_fused_ft_stab_equals_literal_sketch():
+    """Default: IFT(rho_hat') + (rho - IFT(rho_hat)) evaluated as IFT(rho_hat' - rho_hat) + rho (linearity).  The literal
+    two-transform form of the sketch (reconstruct.py:584-593) must give the same iterates up to rounding."""
+    from xframe_b200.plan import Plan
+    from xframe_b200.reconstruct import run_schedule
+    g = load_golden('ref_small_ftstab')
+    sd = golden_settings(g)
+    m = O.MTIP(sd, golden_data(g))
+    out = []
+    for fused in (True, False):
+        plan = Plan(m.l_max, len(m.rs), float(g['max_q']), n_theta=int(g['n_theta']), n_phi=int(g['n_phi']), max_batch=1)
+        plan.set_projection(m.rp.projection_matrices, m.rp.radial_mask, m.rp.number_of_particles[0])
+        popt = sd['projections']['real']['projections']
+        plan.set_real(popt['apply'], m.real_pr.initial_support, popt['value_threshold']['threshold'], popt['limit_imag']['threshold'])
+        plan.set_fused_ft_stab(fused)
+        out.append(run_schedule(plan, sd, T(g['rho0'])[None]))
+        plan.close()
+    assert rel_l2(out[0]['errors'], out[1]['errors']) < 1e-9
+    assert rel_l2(out[0]['last_real'], out[1]['last_real']) < 1e-9
+    for res in out:
+        assert rel_l2(res['errors'][0], g['loop_main_error']) < 1e-6
+        assert rel_l2(res['last_real'][0], g['loop_last_real_density']) < 1e-6
+
+
 def test_host_buffer_step_matches_device_loop():
     from xframe_b200.plan import Plan, HIO
     g = load_golden('ref_small_ftstab')

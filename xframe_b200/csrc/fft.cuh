@@ -78,8 +78,9 @@ __device__ __forceinline__ void warp_fft_row(double2* __restrict__ row, const do
 
 // grid [S][n_theta][N] -> a [S][M2][n_theta], M2 = 2L+1, mm = m (m>=0) or M2+m (m<0)
 template <int N>
-__global__ void __launch_bounds__(256) fft_phi_forward_kernel(SlotView grid, int shells_per_run, double2* __restrict__ a,
-                                                              const double2* __restrict__ tw_g, int n_theta, int l_max, int th) {
+__global__ void __launch_bounds__(256) fft_phi_forward_kernel(SlotView grid, int shells_per_run, const double2* __restrict__ sub_flat,
+                                                              double2* __restrict__ a, const double2* __restrict__ tw_g, int n_theta,
+                                                              int l_max, int th) {
     extern __shared__ double2 smem_fft[];
     const int rowlen = xfb_fft_rowlen(N);
     double2* tw = smem_fft;
@@ -91,9 +92,12 @@ __global__ void __launch_bounds__(256) fft_phi_forward_kernel(SlotView grid, int
     for (int i = tid; i < N; i += blockDim.x) tw[i] = tw_g[i];
     const int run = s / shells_per_run, shell_in_run = s - run * shells_per_run;
     const double2* src = slot_run_ptr(grid, run) + ((size_t)shell_in_run * n_theta + theta0) * N;
+    const double2* sub = sub_flat ? sub_flat + ((size_t)s * n_theta + theta0) * N : nullptr;   // transform of (grid - sub)
     for (int idx = tid; idx < th * N; idx += blockDim.x) {
         const int t = idx / N, i = idx - t * N;
-        buf[t * rowlen + XFB_PHYS(i)] = src[idx];
+        double2 v = src[idx];
+        if (sub) { const double2 w = ldg2(sub + idx); v.x -= w.x; v.y -= w.y; }
+        buf[t * rowlen + XFB_PHYS(i)] = v;
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(256) fft_phi_inverse_kernel(const double2* __r
 }
 
 template <int N>
-static int launch_fft_n(bool forward, SlotView in, int shells_per_run, double2* out, const double2* tw, int n_shells, int n_theta,
+static int launch_fft_n(bool forward, SlotView in, int shells_per_run, const double2* sub, double2* out, const double2* tw, int n_shells, int n_theta,
                         int l_max, cudaStream_t st) {
     const int th = (n_theta % 16 == 0) ? 16 : 8;
     const size_t smem = (size_t)(N + th * xfb_fft_rowlen(N)) * sizeof(double2);
@@ -157,22 +161,22 @@ static int launch_fft_n(bool forward, SlotView in, int shells_per_run, double2* 
         attr_done = true;
     }
     if (forward)
-        fft_phi_forward_kernel<N><<<g, 256, smem, st>>>(in, shells_per_run, out, tw, n_theta, l_max, th);
+        fft_phi_forward_kernel<N><<<g, 256, smem, st>>>(in, shells_per_run, sub, out, tw, n_theta, l_max, th);
     else
         fft_phi_inverse_kernel<N><<<g, 256, smem, st>>>(in.base, out, tw, n_theta, l_max, th);
     XFB_CUDA(cudaGetLastError());
     return 0;
 }
 
-static int launch_fft(bool forward, int n_phi, SlotView in, int shells_per_run, double2* out, const double2* tw, int n_shells,
+static int launch_fft(bool forward, int n_phi, SlotView in, int shells_per_run, const double2* sub, double2* out, const double2* tw, int n_shells,
                       int n_theta, int l_max, cudaStream_t st) {
     switch (n_phi) {
-        case 16: return launch_fft_n<16>(forward, in, shells_per_run, out, tw, n_shells, n_theta, l_max, st);
-        case 32: return launch_fft_n<32>(forward, in, shells_per_run, out, tw, n_shells, n_theta, l_max, st);
-        case 64: return launch_fft_n<64>(forward, in, shells_per_run, out, tw, n_shells, n_theta, l_max, st);
-        case 128: return launch_fft_n<128>(forward, in, shells_per_run, out, tw, n_shells, n_theta, l_max, st);
-        case 256: return launch_fft_n<256>(forward, in, shells_per_run, out, tw, n_shells, n_theta, l_max, st);
-        case 512: return launch_fft_n<512>(forward, in, shells_per_run, out, tw, n_shells, n_theta, l_max, st);
+        case 16: return launch_fft_n<16>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st);
+        case 32: return launch_fft_n<32>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st);
+        case 64: return launch_fft_n<64>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st);
+        case 128: return launch_fft_n<128>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st);
+        case 256: return launch_fft_n<256>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st);
+        case 512: return launch_fft_n<512>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st);
         default: XFB_FAIL("n_phi=%d unsupported (power of two in [16,512])", n_phi);
     }
 }

@@ -100,6 +100,36 @@ __global__ void __launch_bounds__(256) hankel_kernel(const double2* __restrict__
     }
 }
 
+// Hankel transform evaluated at the first output radius only: out0[row] = (-+i)^l scale sum_p in[row][p+skip] W_l[p][0].
+// Used by the fused ft_stab step: only shell 0 of IFT(rho_hat) is needed.  One warp per row.
+__global__ void hankel_row0_kernel(const double2* __restrict__ in, double2* __restrict__ out0, const double* __restrict__ W, int n_rows,
+                                   int nb, int n_r, int n_sum, int skip, double scale, int inverse) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    const int lm = row / nb;
+    int l = (int)sqrt((double)lm);
+    while ((l + 1) * (l + 1) <= lm) ++l;
+    while (l * l > lm) --l;
+    const double* Wl = W + (size_t)l * n_sum * n_r;
+    double sx = 0.0, sy = 0.0;
+    for (int p = lane; p < n_sum; p += 32) {
+        const double2 v = ldg2(in + (size_t)row * n_r + skip + p);
+        const double w = __ldg(Wl + (size_t)p * n_r);
+        sx += v.x * w; sy += v.y * w;
+    }
+    sx = warp_sum(sx) * scale; sy = warp_sum(sy) * scale;
+    if (lane == 0) {
+        const int ph = l & 3;
+        double2 r;
+        if (ph == 0) r = make_double2(sx, sy);
+        else if (ph == 2) r = make_double2(-sx, -sy);
+        else if ((ph == 1) != (inverse != 0)) r = make_double2(sy, -sx);
+        else r = make_double2(-sy, sx);
+        out0[row] = r;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // grouped real GEMM  C = alpha * A * B, arbitrary element strides, one
 // descriptor per problem; 64x64 block tiles, 4 warps (2x2), warp tile 32x32.

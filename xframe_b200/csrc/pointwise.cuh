@@ -79,6 +79,8 @@ struct RealDesc {
 #define RU_THREADS 256
 // real_projection + HIO/ER + l2_projection_diff partial sums.
 //   rho_new = rho_ift (+ (rho_prev - rho_rt) for radial index >= 1 when rho_rt != nullptr)   reconstruct.py:584-593, misk.py:325-329
+//             or, fused form (rt0 != nullptr): rho_ift = IFT(rho_hat' - rho_hat) and rho_new = rho_ift + rho_prev (r >= 1),
+//             rho_ift + IFT(rho_hat)[shell 0] (r = 0) -- the same quantity by linearity of IFT
 //   projection chain                                                                         fxs_Projections.py:72-130
 //   HIO: where(mask, rho_prev - beta (rho_new - proj), proj) ; ER: proj                      fxs_IO_methods.py:56-68
 //   partial[b][block][0..1] = sum w |rho_new-proj|^2 , sum w |rho_new|^2 over the error region
@@ -87,7 +89,8 @@ __global__ void __launch_bounds__(RU_THREADS) real_update_kernel(const double2* 
                                                                  const int* __restrict__ support_slot, long long support_slot_stride,
                                                                  const int* __restrict__ enforce, const uint8_t* __restrict__ init_support,
                                                                  const double* __restrict__ wt, RealDesc rd, int method, double beta,
-                                                                 int n_theta, int n_phi, long long per_run, double* __restrict__ partial) {
+                                                                 int n_theta, int n_phi, long long per_run, double* __restrict__ partial,
+                                                                 const double2* __restrict__ rt0) {
     const int b = blockIdx.y;
     const double2* ri = rho_ift + (long long)b * per_run;
     const double2* rt = rho_rt ? rho_rt + (long long)b * per_run : nullptr;
@@ -104,6 +107,11 @@ __global__ void __launch_bounds__(RU_THREADS) real_update_kernel(const double2* 
             const double2 t = ldg2(rt + i);
             v.x += prev.x - t.x;
             v.y += prev.y - t.y;
+        }
+        if (rt0) {      // fused ft_stab: rho_ift holds IFT(rho_hat' - rho_hat); add rho (r>=1) or shell 0 of IFT(rho_hat)
+            const double2 t = (i >= shell) ? prev : ldg2(rt0 + (long long)b * shell + i);
+            v.x += t.x;
+            v.y += t.y;
         }
         const bool in_init = init_support[i] != 0;
         const bool outside = enf ? (!in_init || sup[i] == 0) : (sup[i] == 0);

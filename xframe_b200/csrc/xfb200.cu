@@ -27,6 +27,8 @@ struct xfb_plan {
     double *FE = nullptr, *FO = nullptr, *IE = nullptr, *IO = nullptr, *hankel_w = nullptr, *int_wt = nullptr, *q_pts = nullptr;
     // workspaces
     double2 *A0 = nullptr, *C0 = nullptr, *C1 = nullptr, *W0 = nullptr, *W1 = nullptr, *W2 = nullptr;
+    double2 *A0s = nullptr, *C0s = nullptr, *rt0 = nullptr;   // shell-0 side path of the fused ft_stab step
+    int fused_ft_stab = 1;
     HankelTile* hk_tiles = nullptr; int hk_tiles_n = 0, hk_tiles_nb = -1, hk_tiles_cap = 0;
     // projection
     bool has_proj = false;
@@ -142,6 +144,9 @@ int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
     if (dev_alloc(p, &p->W0, B * p->G)) return 1;
     if (dev_alloc(p, &p->W1, B * p->G)) return 1;
     if (dev_alloc(p, &p->W2, B * p->G)) return 1;
+    if (dev_alloc(p, &p->A0s, B * p->M2 * p->n_theta)) return 1;
+    if (dev_alloc(p, &p->C0s, B * p->NLM)) return 1;
+    if (dev_alloc(p, &p->rt0, B * p->n_theta * p->n_phi)) return 1;
     XFB_CUDA(cudaFuncSetAttribute(legendre_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre_fwd_smem(p->n_theta)));
     XFB_CUDA(cudaFuncSetAttribute(legendre_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre_inv_smem(p->n_theta, p->NP)));
     *out = p;
@@ -150,7 +155,7 @@ int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
 
 int xfb_plan_destroy(xfb_plan* p) {
     if (!p) return 0;
-    void* ptrs[] = {p->tw, p->FE, p->FO, p->IE, p->IO, p->hankel_w, p->int_wt, p->q_pts, p->A0, p->C0, p->C1, p->W0, p->W1, p->W2,
+    void* ptrs[] = {p->tw, p->FE, p->FO, p->IE, p->IO, p->hankel_w, p->int_wt, p->q_pts, p->A0, p->C0, p->C1, p->W0, p->W1, p->W2, p->A0s, p->C0s, p->rt0,
                     p->hk_tiles, p->orders_dev, p->kind_dev, p->act_index_dev, p->radial_mask_dev, p->v0_dev, p->pd_dev, p->vt_dev,
                     p->xt, p->tt, p->g, p->gn, p->vw, p->sigma, p->sweeps_dev, p->gemmM_dev, p->gemmT_dev, p->gemmM_tp, p->gemmT_tp,
                     p->init_support_dev, p->rho_pool, p->rh_pool, p->mask_pool, p->ls_ints, p->ls_dbl, p->partial, p->err, p->mm};
@@ -191,8 +196,9 @@ int xfb_profile_read(xfb_plan* p, int32_t n_max, char* names, double* ms, int64_
 }  // extern "C"
 
 // ---- internal building blocks -----------------------------------------------------------
-static int sht_forward_i(xfb_plan* p, SlotView in, int shells_per_run, double2* c_out, int S, cudaStream_t st) {
-    XFB_LAUNCH(p, PG_FFT, st, if (launch_fft(true, p->n_phi, in, shells_per_run, p->A0, p->tw, S, p->n_theta, p->L, st)) return 1);
+static int sht_forward_i(xfb_plan* p, SlotView in, int shells_per_run, double2* c_out, int S, cudaStream_t st,
+                         const double2* sub = nullptr) {
+    XFB_LAUNCH(p, PG_FFT, st, if (launch_fft(true, p->n_phi, in, shells_per_run, sub, p->A0, p->tw, S, p->n_theta, p->L, st)) return 1);
     dim3 g(cdiv(S, 16), p->L + 1);
     XFB_LAUNCH(p, PG_LEGENDRE, st,
                legendre_forward_kernel<<<g, 128, legendre_fwd_smem(p->n_theta), st>>>(p->A0, c_out, p->FE, p->FO, S, p->L, p->n_theta, p->NP));
@@ -203,7 +209,7 @@ static int sht_inverse_i(xfb_plan* p, const double2* c_in, double2* grid_out, in
     XFB_LAUNCH(p, PG_LEGENDRE, st,
                legendre_inverse_kernel<<<g, 128, legendre_inv_smem(p->n_theta, p->NP), st>>>(c_in, p->A0, p->IE, p->IO, S, p->L, p->n_theta, p->NP));
     XFB_LAUNCH(p, PG_FFT, st,
-               if (launch_fft(false, p->n_phi, flat_view(p->A0, 0), 1, grid_out, p->tw, S, p->n_theta, p->L, st)) return 1);
+               if (launch_fft(false, p->n_phi, flat_view(p->A0, 0), 1, nullptr, grid_out, p->tw, S, p->n_theta, p->L, st)) return 1);
     return 0;
 }
 static int hankel_i(xfb_plan* p, int dir, const double2* c_in, double2* c_out, int nb, cudaStream_t st) {
@@ -228,11 +234,24 @@ static int hankel_i(xfb_plan* p, int dir, const double2* c_in, double2* c_out, i
                                                 dir == 0 ? p->hk_fwd_scale : p->hk_inv_scale, dir));
     return 0;
 }
-static int ft_i(xfb_plan* p, int dir, SlotView in, double2* out, int nb, cudaStream_t st) {
+static int ft_i(xfb_plan* p, int dir, SlotView in, double2* out, int nb, cudaStream_t st, const double2* sub = nullptr) {
     const int S = nb * p->n_r;
-    if (sht_forward_i(p, in, p->n_r, p->C0, S, st)) return 1;
+    if (sht_forward_i(p, in, p->n_r, p->C0, S, st, sub)) return 1;
     if (hankel_i(p, dir, p->C0, p->C1, nb, st)) return 1;
     return sht_inverse_i(p, p->C1, out, S, st);
+}
+// shell 0 of IFT(f) from the reciprocal coefficients c = SHT(f) (internal layout): rt0[nb][n_theta][n_phi]
+static int ift_shell0_i(xfb_plan* p, const double2* c, int nb, cudaStream_t st) {
+    const int rows = p->NLM * nb;
+    XFB_LAUNCH(p, PG_HANKEL, st,
+               hankel_row0_kernel<<<cdiv(rows, 8), 256, 0, st>>>(c, p->C0s, p->hankel_w, rows, nb, p->n_r, p->hankel_n_sum, p->hankel_skip,
+                                                                  p->hk_inv_scale, 1));
+    dim3 g(cdiv(nb, 16), p->L + 1);
+    XFB_LAUNCH(p, PG_LEGENDRE, st,
+               legendre_inverse_kernel<<<g, 128, legendre_inv_smem(p->n_theta, p->NP), st>>>(p->C0s, p->A0s, p->IE, p->IO, nb, p->L, p->n_theta, p->NP));
+    XFB_LAUNCH(p, PG_FFT, st,
+               if (launch_fft(false, p->n_phi, flat_view(p->A0s, 0), 1, nullptr, p->rt0, p->tw, nb, p->n_theta, p->L, st)) return 1);
+    return 0;
 }
 
 static int build_gemm_groups(xfb_plan* p, int nb, cudaStream_t st) {
@@ -325,7 +344,7 @@ static int ensure_reduce_alloc(xfb_plan* p) {
 
 static int real_update_i(xfb_plan* p, int method, double beta, const double2* rho_ift, const double2* rho_rt, SlotView prev, SlotView next,
                          const uint8_t* support, const int* support_slot, long long support_slot_stride, const int* enforce, double* err_out,
-                         int nb, cudaStream_t st) {
+                         int nb, cudaStream_t st, const double2* rt0 = nullptr) {
     if (!p->has_real) XFB_FAIL("real projection options not set (xfb_plan_set_real)");
     if (ensure_reduce_alloc(p)) return 1;
     // blocks per run: keep the whole launch near a few waves of 148 SMs
@@ -334,7 +353,7 @@ static int real_update_i(xfb_plan* p, int method, double beta, const double2* rh
     XFB_LAUNCH(p, PG_REAL_UPDATE, st,
                real_update_kernel<<<dim3(bpr, nb), RU_THREADS, 0, st>>>(rho_ift, rho_rt, prev, next, support, support_slot, support_slot_stride,
                                                                         enforce, p->init_support_dev, p->int_wt, p->rd, method, beta,
-                                                                        p->n_theta, p->n_phi, p->G, p->partial));
+                                                                        p->n_theta, p->n_phi, p->G, p->partial, rt0));
     XFB_LAUNCH(p, PG_MISC, st, reduce_pairs_kernel<<<nb, 32, 0, st>>>(p->partial, bpr, err_out));
     return 0;
 }
@@ -551,8 +570,17 @@ int xfb_mtip_iterate(xfb_plan* p, int32_t method, int32_t ft_stab, int32_t n_ite
     const int S = nb * p->n_r;
     const int eb = ew_blocks(p->G);
     for (int it = 0; it < n_iter; ++it) {
+        const bool fused = ft_stab && p->fused_ft_stab;
         // 1. rho_hat = FT(rho)                                   (reconstruct.py:585)
-        if (ft_i(p, 0, pool_view(p->rho_pool, p->ls.rho_cur, p), p->W0, nb, st)) return 1;
+        if (!fused) {
+            if (ft_i(p, 0, pool_view(p->rho_pool, p->ls.rho_cur, p), p->W0, nb, st)) return 1;
+        } else {
+            if (sht_forward_i(p, pool_view(p->rho_pool, p->ls.rho_cur, p), p->n_r, p->C0, S, st)) return 1;
+            if (hankel_i(p, 0, p->C0, p->C1, nb, st)) return 1;
+            // C1 = SHT(rho_hat) (exact Gauss quadrature of a band-limited field): shell 0 of IFT(rho_hat) from it
+            if (ift_shell0_i(p, p->C1, nb, st)) return 1;
+            if (sht_inverse_i(p, p->C1, p->W0, S, st)) return 1;
+        }
         // 2. |rho_hat|^2 -> I_lm                                 (:519-520)
         XFB_LAUNCH(p, PG_POINTWISE, st, square_kernel<<<ew_blocks((long long)nb * p->G), 256, 0, st>>>(p->W0, p->W1, (long long)nb * p->G));
         if (sht_forward_i(p, flat_view(p->W1, p->G), p->n_r, p->C0, S, st)) return 1;
@@ -563,18 +591,28 @@ int xfb_mtip_iterate(xfb_plan* p, int32_t method, int32_t ft_stab, int32_t n_ite
         XFB_LAUNCH(p, PG_POINTWISE, st,
                    modify_intensity_kernel<<<dim3(eb, nb), 256, 0, st>>>(p->W0, p->W1, pool_view(p->rh_pool, p->ls.rh_next, p), p->G));
         // 5. back to real space (+ ft_stab correction terms)     (:586-588 / :579)
-        if (ft_i(p, 1, pool_view(p->rh_pool, p->ls.rh_next, p), p->W1, nb, st)) return 1;
-        if (ft_stab) { if (ft_i(p, 1, flat_view(p->W0, p->G), p->W2, nb, st)) return 1; }
         // 6. real projection + HIO/ER + error                    (:589-590)
-        if (real_update_i(p, method, betas ? betas[it] : 0.0, p->W1, ft_stab ? p->W2 : nullptr, pool_view(p->rho_pool, p->ls.rho_cur, p),
-                          pool_view(p->rho_pool, p->ls.rho_next, p), p->mask_pool, p->ls.mask_cur, (long long)p->max_batch * p->G,
-                          p->ls.enforce_cur, p->err, nb, st)) return 1;
+        if (fused) {
+            // IFT is linear: IFT(rho_hat') + (rho - IFT(rho_hat)) = IFT(rho_hat' - rho_hat) + rho   (r >= 1)
+            if (ft_i(p, 1, pool_view(p->rh_pool, p->ls.rh_next, p), p->W1, nb, st, p->W0)) return 1;
+            if (real_update_i(p, method, betas ? betas[it] : 0.0, p->W1, nullptr, pool_view(p->rho_pool, p->ls.rho_cur, p),
+                              pool_view(p->rho_pool, p->ls.rho_next, p), p->mask_pool, p->ls.mask_cur, (long long)p->max_batch * p->G,
+                              p->ls.enforce_cur, p->err, nb, st, p->rt0)) return 1;
+        } else {
+            if (ft_i(p, 1, pool_view(p->rh_pool, p->ls.rh_next, p), p->W1, nb, st)) return 1;
+            if (ft_stab) { if (ft_i(p, 1, flat_view(p->W0, p->G), p->W2, nb, st)) return 1; }
+            if (real_update_i(p, method, betas ? betas[it] : 0.0, p->W1, ft_stab ? p->W2 : nullptr, pool_view(p->rho_pool, p->ls.rho_cur, p),
+                              pool_view(p->rho_pool, p->ls.rho_next, p), p->mask_pool, p->ls.mask_cur, (long long)p->max_batch * p->G,
+                              p->ls.enforce_cur, p->err, nb, st)) return 1;
+        }
         // 7. bookkeeping                                         (:924-939)
         XFB_LAUNCH(p, PG_MISC, st, loop_update_kernel<<<cdiv(nb, 128), 128, 0, st>>>(p->ls, p->err, p->it_done, nb));
         p->it_done++;
     }
     return 0;
 }
+
+int xfb_plan_set_fused_ft_stab(xfb_plan* p, int32_t on) { p->fused_ft_stab = on ? 1 : 0; return 0; }
 
 int xfb_mtip_shrinkwrap(xfb_plan* p, double sigma, double threshold, double error_limit, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;

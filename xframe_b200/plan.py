@@ -89,6 +89,10 @@ class Plan:
     def grid_shape(self):
         return (self.n_r, self.n_theta, self.n_phi)
 
+    def set_fused_ft_stab(self, on=True):
+        """True (default): one inverse transform per ft_stab iteration (linearity of IFT); False: literal sketch."""
+        _lib.check(self.lib.xfb_plan_set_fused_ft_stab(self.h, int(bool(on))))
+
     def workspace_bytes(self):
         return int(self.lib.xfb_plan_workspace_bytes(self.h))
 
