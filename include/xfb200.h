@@ -98,6 +98,8 @@ int64_t xfb_plan_workspace_bytes(const xfb_plan* p);
 /* ft_stab sketch (reconstruct.py:584-593): 1 (default) evaluates IFT(rho_hat') + (rho - IFT(rho_hat)) as
  * IFT(rho_hat' - rho_hat) + rho (linearity; one inverse transform instead of two), 0 follows the sketch literally. */
 int xfb_plan_set_fused_ft_stab(xfb_plan* p, int32_t on);
+/* diagnostics: Jacobi sweeps of the last projection, host array [n_batch][n_active_orders]; orders_out lists the orders */
+int xfb_debug_jacobi_sweeps(xfb_plan* p, int32_t* out_host, int32_t capacity, int32_t* n_orders_out, int32_t* orders_out);
 
 /* ---- operator level: the harmonic-transform / Hankel / FT interfaces ---- */
 /* sh.forward_d / sh.inverse_d  (shtns_plugin.py:250-261): n_shells = n_batch*N_r or any count <= max_batch*N_r */

@@ -73,23 +73,27 @@ __device__ __forceinline__ void jacobi_sweep_rounds(double* __restrict__ Gs, int
     const int npad = nact + (nact & 1);
     const int half = npad >> 1;
     const int mod = npad - 1;
+    // round-robin (circle method): position 0 is fixed, the element at position k>=1 in round r is
+    // 1 + ((k-1-r) mod (npad-1)); tracked incrementally (one decrement with wrap per round, no integer division).
+    const int i = slot0;
+    const bool has_slot = i < half;                       // half <= n_slots (n <= 128 columns, 64 pair slots)
+    const int ka = i, kb = npad - 1 - i;
+    int pa = (ka == 0) ? 0 : 1 + (ka - 1) % mod;
+    int pb = has_slot ? 1 + (kb - 1) % mod : 1;
     for (int r = 0; r < npad - 1; ++r) {
-        for (int i0 = 0; i0 < half; i0 += n_slots) {      // one pass when half <= 64
-            const int i = i0 + slot0;
-            bool valid = i < half;
+        {
+            if ((slot0 & ~3) >= half) { __syncthreads(); continue; }   // warp-uniform: no pair for this warp
+            bool valid = has_slot && (pa < nact) && (pb < nact);      // bye against the padding element
             int p = 0, q = 0, wpi = 0, wqi = 0;
             if (valid) {
-                const int ka = i, kb = npad - 1 - i;
-                int pa = (ka == 0) ? 0 : 1 + ((ka - 1 - r) % mod + mod) % mod;
-                int pb = 1 + ((kb - 1 - r) % mod + mod) % mod;
-                valid = (pa < nact) && (pb < nact);                // bye against the padding element
-                if (valid) {
-                    p = list[pa]; q = list[pb];
-                    if (p > q) { int t_ = p; p = q; q = t_; t_ = pa; pa = pb; pb = t_; }
-                    wpi = WSM ? pa : p;                            // smem: compact slot ; global: column index
-                    wqi = WSM ? pb : q;
-                }
+                int sa = pa, sb = pb;
+                p = list[pa]; q = list[pb];
+                if (p > q) { int t_ = p; p = q; q = t_; sa = pb; sb = pa; }
+                wpi = WSM ? sa : p;                                // smem: compact slot ; global: column index
+                wqi = WSM ? sb : q;
             }
+            if (ka != 0) pa = (pa == 1) ? mod : pa - 1;             // positions for the next round
+            pb = (pb == 1) ? mod : pb - 1;
             double* gp = Gs + (size_t)p * ldg + sub;
             double* gq = Gs + (size_t)q * ldg + sub;
             double* wp = Wb + (size_t)wpi * wstride + sub;
@@ -127,9 +131,13 @@ __device__ __forceinline__ void jacobi_sweep_rounds(double* __restrict__ Gs, int
             bool rot = valid && (app > thr) && (aqq > thr);
             if (rot) rot = apq * apq > (tol * tol) * (app * aqq);
             if (rot) {
-                const double zeta = (aqq - app) / (2.0 * apq);
-                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                const double cs = rsqrt(1.0 + t * t), sn = cs * t;
+                // tan(2 theta) = 2 apq / (aqq - app), |theta| <= pi/4 (same rotation as the textbook zeta/t form)
+                const double d = aqq - app, s2 = 2.0 * apq;
+                const double rh = rsqrt(d * d + s2 * s2);
+                const double u = 0.5 + 0.5 * fabs(d) * rh;            // cos^2(theta)
+                const double rc = rsqrt(u);
+                const double cs = u * rc;
+                const double sn = copysign(0.5 * s2 * rh, d * s2) * rc;   // sin(2 theta) / (2 cos theta)
                 if constexpr (WSM) {
 #pragma unroll
                     for (int tt = 0; tt < JMAXE; ++tt)

@@ -612,6 +612,16 @@ int xfb_mtip_iterate(xfb_plan* p, int32_t method, int32_t ft_stab, int32_t n_ite
     return 0;
 }
 
+// diagnostics: Jacobi sweeps used by the last projection, host array [n_batch][n_active_orders] (orders largest first)
+int xfb_debug_jacobi_sweeps(xfb_plan* p, int32_t* out_host, int32_t capacity, int32_t* n_orders_out, int32_t* orders_out) {
+    const int na = (int)p->orders.size();
+    if (n_orders_out) *n_orders_out = na;
+    for (int i = 0; i < na && orders_out; ++i) orders_out[i] = p->orders[i].l;
+    const int n = std::min<int>(capacity, na * std::max(1, p->gemm_nb));
+    if (n > 0 && out_host) XFB_CUDA(cudaMemcpy(out_host, p->sweeps_dev, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int xfb_plan_set_fused_ft_stab(xfb_plan* p, int32_t on) { p->fused_ft_stab = on ? 1 : 0; return 0; }
 
 int xfb_mtip_shrinkwrap(xfb_plan* p, double sigma, double threshold, double error_limit, void* stream) {

@@ -93,6 +93,18 @@ class Plan:
         """True (default): one inverse transform per ft_stab iteration (linearity of IFT); False: literal sketch."""
         _lib.check(self.lib.xfb_plan_set_fused_ft_stab(self.h, int(bool(on))))
 
+    def jacobi_sweeps(self):
+        """Diagnostics: (orders, sweeps[n_batch, n_orders]) of the last invariant projection."""
+        cap = 4096 * 64
+        buf = (C.c_int32 * cap)()
+        orders = (C.c_int32 * 1024)()
+        n = C.c_int32(0)
+        _lib.check(self.lib.xfb_debug_jacobi_sweeps(self.h, buf, cap, C.byref(n), orders))
+        na = n.value
+        arr = np.frombuffer(buf, dtype=np.int32)
+        nb = max(1, self.n_batch)
+        return list(orders[:na]), arr[:nb * na].reshape(nb, na).copy() if na else np.zeros((nb, 0), np.int32)
+
     def workspace_bytes(self):
         return int(self.lib.xfb_plan_workspace_bytes(self.h))
 
