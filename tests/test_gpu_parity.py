@@ -204,6 +204,25 @@ def test_full_size_transforms_against_oracle(full):
     assert rel_l2(N(plan.hankel(T(c)[None], inverse=True))[0], izht(c)) < 1e-12
 
 
+@pytest.mark.parametrize('L,n_theta,n_phi', [(31, 32, 64), (100, 112, 256), (20, 24, 64), (63, 64, 256)])
+def test_sht_other_grid_sizes_against_oracle(L, n_theta, n_phi):
+    """Covers the register FFT variants (64 = 8x8, 256 = 16x16) and the generic fallback (n_theta not a multiple of the
+    CTA's theta block), incl. an anti-aliased grid (n_phi > 2L+2)."""
+    from xframe_b200.plan import Plan
+    from oracle.sht import sh
+    n_r = 8
+    plan = Plan(L, n_r, 0.05, n_theta=n_theta, n_phi=n_phi, max_batch=2)
+    s = sh(L, n_theta=n_theta, n_phi=n_phi)
+    rng = np.random.default_rng(L)
+    c = rng.normal(size=(2 * n_r, (L + 1) ** 2)) + 1j * rng.normal(size=(2 * n_r, (L + 1) ** 2))
+    x = s.inverse_d(c)
+    assert rel_l2(N(plan.sht_inverse(T(c))), x) < 1e-12
+    assert rel_l2(N(plan.sht_forward(T(x))), c) < 1e-11
+    xg = rng.normal(size=x.shape) + 1j * rng.normal(size=x.shape)          # not band limited: exercises all m > L columns
+    assert rel_l2(N(plan.sht_forward(T(xg))), s.forward_d(xg)) < 1e-11
+    plan.close()
+
+
 def test_full_size_properties(full):
     plan = full
     rng = np.random.default_rng(5)

@@ -9,6 +9,7 @@
 #pragma once
 #include "common.cuh"
 #include "pointwise.cuh"
+#include "fft2.cuh"
 
 // padded index inside a shared-memory row: one pad element every 4 keeps the
 // strided Stockham writes (stride 4 / 16 / 64 complex) off the same banks.
@@ -170,6 +171,10 @@ static int launch_fft_n(bool forward, SlotView in, int shells_per_run, const dou
 
 static int launch_fft(bool forward, int n_phi, SlotView in, int shells_per_run, const double2* sub, double2* out, const double2* tw, int n_shells,
                       int n_theta, int l_max, cudaStream_t st) {
+    {   // register two-stage FFT where it applies (64 / 128 / 256 points), generic Stockham kernel otherwise
+        const int rc = launch_fft2_any(forward, n_phi, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st);
+        if (rc >= 0) return rc;
+    }
     switch (n_phi) {
         case 16: return launch_fft_n<16>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st);
         case 32: return launch_fft_n<32>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st);
