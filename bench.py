@@ -88,7 +88,10 @@ def algorithmic_bytes(nb):
         'fft_phi': nb * (G + A) * 16,          # one grid read/written + one phi-Fourier array written/read
         'legendre': nb * (A + C) * 16,
         'hankel': nb * 2 * C * 16,
-        'real_update': nb * (4 * G * 16 + G),  # rho_ift, rho_rt, rho_prev in, rho_next out, support mask
+        'real_update': nb * (3 * G * 16 + G),  # IFT(rho_hat'-rho_hat), rho_prev in, rho_next out, support mask (fused ft_stab)
+        'pointwise': nb * int(2.5 * G * 16),   # square: G in, G out ; modify_intensity: 2G in, G out  -> average per launch
+        # Jacobi: G and V_l^T in, G~/sigma and V_l U out (Procrustes blocks, 8 B reals); latency bound, see DESIGN.md 4.4
+        'procrustes_jacobi': nb * 4 * sum((2 * l + 1) * 128 for l in range(2, L_MAX + 1, 2)) * 8,
     }
 
 
@@ -272,15 +275,14 @@ def run_ours(args):
         tot_ms = sum(v['ms'] for v in groups.values())
         dom = max(groups, key=lambda k: groups[k]['ms'])
         per_launch_ms = groups[dom]['ms'] / groups[dom]['launches']
-        if dom in ab:
-            achieved = ab[dom] / (per_launch_ms * 1e-3) / 1e9
-            roof = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                    'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': ab[dom], 'launch_ms': per_launch_ms,
-                    'share_of_step': groups[dom]['ms'] / tot_ms}
-        else:
-            roof = {'bound': 'hbm', 'kernel': dom, 'achieved': None, 'peak': peak, 'unit': 'GB/s', 'frac': None, 'traffic': None,
-                    'peak_source': peak_src, 'launch_ms': per_launch_ms, 'share_of_step': groups[dom]['ms'] / tot_ms,
-                    'note': 'latency/compute-bound kernel: no HBM roofline applies'}
+        achieved = ab[dom] / (per_launch_ms * 1e-3) / 1e9 if dom in ab else None
+        roof = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': (achieved / peak) if achieved is not None else None, 'traffic': None, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': ab.get(dom), 'launch_ms': per_launch_ms, 'share_of_step': groups[dom]['ms'] / tot_ms}
+        if dom == 'procrustes_jacobi':
+            roof['note'] = ('dominant kernel is the one-sided Jacobi polar factor: shared-memory resident, latency/sync bound '
+                            '(no HBM or tensor roofline applies; its HBM fraction is low by construction). Top HBM-bound kernel: '
+                            'fft_phi, see groups')
         roof['groups'] = {k: {'ms_per_step': v['ms'] / K, 'launches_per_step': v['launches'] / K,
                               **({'GBps': ab[k] * v['launches'] / (v['ms'] * 1e-3) / 1e9} if k in ab else {}),
                               **({'TFLOPs_fp64': hankel_flops(nb) * v['launches'] / (v['ms'] * 1e-3) / 1e12} if k == 'hankel' else {})}

@@ -18,23 +18,24 @@
 #define LEG_NB 32        // output columns per pass (4 warps x 8)
 #define LEG_LDB (LEG_NB + 4)
 
-// acc[mb][0..1] += A[32 x K] (rows mb*8.., smem [row*lda + k]) * B[K x 8] (smem [k*ldb + n0 + n])
+#define LEG_THREADS 256  // 8 warps: warp w -> output columns (w&3)*8.., rows (w>>2)*16..
+// acc[mb][0..1] += A[16 x K] (rows r0 + mb*8.., smem [row*lda + k]) * B[K x 8] (smem [k*ldb + n0 + n])
 __device__ __forceinline__ void leg_mma_cplx(const double* __restrict__ Are, const double* __restrict__ Aim, int lda,
-                                             const double* __restrict__ Bs, int ldb, int n0, int K, int lane,
-                                             double (&cre)[4][2], double (&cim)[4][2]) {
+                                             const double* __restrict__ Bs, int ldb, int n0, int r0, int K, int lane,
+                                             double (&cre)[2][2], double (&cim)[2][2]) {
     const int ar = lane >> 2, ak = lane & 3;
     for (int k0 = 0; k0 < K; k0 += 4) {
         const double b = Bs[(k0 + ak) * ldb + n0 + ar];
 #pragma unroll
-        for (int mb = 0; mb < 4; ++mb) {
-            const int off = (mb * 8 + ar) * lda + k0 + ak;
+        for (int mb = 0; mb < 2; ++mb) {
+            const int off = (r0 + mb * 8 + ar) * lda + k0 + ak;
             dmma884(cre[mb][0], cre[mb][1], Are[off], b);
             dmma884(cim[mb][0], cim[mb][1], Aim[off], b);
         }
     }
 }
 
-__global__ void __launch_bounds__(128) legendre_forward_kernel(const double2* __restrict__ a, double2* __restrict__ c,
+__global__ void __launch_bounds__(LEG_THREADS) legendre_forward_kernel(const double2* __restrict__ a, double2* __restrict__ c,
                                                                const double* __restrict__ FE, const double* __restrict__ FO,
                                                                int S, int l_max, int n_theta, int NP) {
     extern __shared__ double smem_leg[];
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(128) legendre_forward_kernel(const double2* __
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // ---- stage A: fold north/south, apply (-1)^m for the -m rows
-    for (int item = tid; item < LEG_ROWS * K2; item += 128) {
+    for (int item = tid; item < LEG_ROWS * K2; item += LEG_THREADS) {
         const int row = item / K2, j = item - row * K2;
         const int sh = sh0 + (row & 15), sign = row >> 4;
         double2 e = make_double2(0, 0), o = make_double2(0, 0);
@@ -72,34 +73,37 @@ __global__ void __launch_bounds__(128) legendre_forward_kernel(const double2* __
     const int ne = (l_max - m) / 2 + 1;  // degrees l = m, m+2, ...
     for (int nb0 = 0; nb0 < ne; nb0 += LEG_NB) {
         __syncthreads();
-        for (int item = tid; item < K2 * LEG_NB; item += 128) {
+        for (int item = tid; item < K2 * LEG_NB; item += LEG_THREADS) {
             const int j = item / LEG_NB, cc = item - j * LEG_NB;
             const bool ok = (nb0 + cc) < NP;
             Be[j * LEG_LDB + cc] = ok ? FEm[(size_t)j * NP + nb0 + cc] : 0.0;
             Bo[j * LEG_LDB + cc] = ok ? FOm[(size_t)j * NP + nb0 + cc] : 0.0;
         }
         __syncthreads();
-        double ere[4][2] = {}, eim[4][2] = {}, ore_[4][2] = {}, oim[4][2] = {};
-        leg_mma_cplx(Ae_re, Ae_im, lda, Be, LEG_LDB, warp * 8, K2, lane, ere, eim);
-        leg_mma_cplx(Ao_re, Ao_im, lda, Bo, LEG_LDB, warp * 8, K2, lane, ore_, oim);
+        const int wn = warp & 3, r0 = (warp >> 2) * 16;
+        const int no = (l_max - m + 1) / 2;              // degrees l = m+1, m+3, ...
+        const bool do_e = nb0 + wn * 8 < ne, do_o = nb0 + wn * 8 < no;   // skip column blocks that are pure padding
+        double ere[2][2] = {}, eim[2][2] = {}, ore_[2][2] = {}, oim[2][2] = {};
+        if (do_e) leg_mma_cplx(Ae_re, Ae_im, lda, Be, LEG_LDB, wn * 8, r0, K2, lane, ere, eim);
+        if (do_o) leg_mma_cplx(Ao_re, Ao_im, lda, Bo, LEG_LDB, wn * 8, r0, K2, lane, ore_, oim);
 #pragma unroll
-        for (int mb = 0; mb < 4; ++mb) {
-            const int row = mb * 8 + (lane >> 2);
+        for (int mb = 0; mb < 2; ++mb) {
+            const int row = r0 + mb * 8 + (lane >> 2);
             const int sh = sh0 + (row & 15), sign = row >> 4;
             if (sh >= S || (sign && m == 0)) continue;
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
-                const int col = nb0 + warp * 8 + 2 * (lane & 3) + cc;
+                const int col = nb0 + wn * 8 + 2 * (lane & 3) + cc;
                 const int le = m + 2 * col, lo = le + 1;
                 const int ms = sign ? -m : m;
-                if (le <= l_max) c[(size_t)(le * (le + 1) + ms) * S + sh] = make_double2(ere[mb][cc], eim[mb][cc]);
-                if (lo <= l_max) c[(size_t)(lo * (lo + 1) + ms) * S + sh] = make_double2(ore_[mb][cc], oim[mb][cc]);
+                if (do_e && le <= l_max) c[(size_t)(le * (le + 1) + ms) * S + sh] = make_double2(ere[mb][cc], eim[mb][cc]);
+                if (do_o && lo <= l_max) c[(size_t)(lo * (lo + 1) + ms) * S + sh] = make_double2(ore_[mb][cc], oim[mb][cc]);
             }
         }
     }
 }
 
-__global__ void __launch_bounds__(128) legendre_inverse_kernel(const double2* __restrict__ c, double2* __restrict__ a,
+__global__ void __launch_bounds__(LEG_THREADS) legendre_inverse_kernel(const double2* __restrict__ c, double2* __restrict__ a,
                                                                const double* __restrict__ IE, const double* __restrict__ IO,
                                                                int S, int l_max, int n_theta, int NP) {
     extern __shared__ double smem_leg[];
@@ -117,7 +121,7 @@ __global__ void __launch_bounds__(128) legendre_inverse_kernel(const double2* __
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // ---- stage A: gather coefficients of order +-m, (-1)^m on the -m rows; shells fastest for coalescing
-    for (int item = tid; item < 2 * NP * LEG_ROWS; item += 128) {
+    for (int item = tid; item < 2 * NP * LEG_ROWS; item += LEG_THREADS) {
         const int rr = item & 15;
         int rest = item >> 4;
         const int sign = rest & 1;
@@ -138,26 +142,29 @@ __global__ void __launch_bounds__(128) legendre_inverse_kernel(const double2* __
     const double* IOm = IO + (size_t)m * NP * K2;
     for (int j0 = 0; j0 < K2; j0 += LEG_NB) {
         __syncthreads();
-        for (int item = tid; item < NP * LEG_NB; item += 128) {
+        for (int item = tid; item < NP * LEG_NB; item += LEG_THREADS) {
             const int i = item / LEG_NB, cc = item - i * LEG_NB;
             const bool ok = (j0 + cc) < K2;
             Be[i * LEG_LDB + cc] = ok ? IEm[(size_t)i * K2 + j0 + cc] : 0.0;
             Bo[i * LEG_LDB + cc] = ok ? IOm[(size_t)i * K2 + j0 + cc] : 0.0;
         }
         __syncthreads();
-        double ere[4][2] = {}, eim[4][2] = {}, ore_[4][2] = {}, oim[4][2] = {};
-        leg_mma_cplx(Ce_re, Ce_im, lda, Be, LEG_LDB, warp * 8, NP, lane, ere, eim);
-        leg_mma_cplx(Co_re, Co_im, lda, Bo, LEG_LDB, warp * 8, NP, lane, ore_, oim);
+        const int wn = warp & 3, r0 = (warp >> 2) * 16;
+        const int ne = (l_max - m) / 2 + 1, no = (l_max - m + 1) / 2;
+        const int Ke = (ne + 3) & ~3, Ko = (no + 3) & ~3;   // contraction only over existing degrees (A is zero padded)
+        double ere[2][2] = {}, eim[2][2] = {}, ore_[2][2] = {}, oim[2][2] = {};
+        leg_mma_cplx(Ce_re, Ce_im, lda, Be, LEG_LDB, wn * 8, r0, Ke, lane, ere, eim);
+        leg_mma_cplx(Co_re, Co_im, lda, Bo, LEG_LDB, wn * 8, r0, Ko, lane, ore_, oim);
 #pragma unroll
-        for (int mb = 0; mb < 4; ++mb) {
-            const int row = mb * 8 + (lane >> 2);
+        for (int mb = 0; mb < 2; ++mb) {
+            const int row = r0 + mb * 8 + (lane >> 2);
             const int sh = sh0 + (row & 15), sign = row >> 4;
             if (sh >= S || (sign && m == 0)) continue;
             const int mm = sign ? (M2 - m) : m;
             double2* dst = a + ((size_t)sh * M2 + mm) * n_theta;
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
-                const int j = j0 + warp * 8 + 2 * (lane & 3) + cc;
+                const int j = j0 + wn * 8 + 2 * (lane & 3) + cc;
                 if (j < K2) {
                     dst[j] = make_double2(ere[mb][cc] + ore_[mb][cc], eim[mb][cc] + oim[mb][cc]);
                     dst[n_theta - 1 - j] = make_double2(ere[mb][cc] - ore_[mb][cc], eim[mb][cc] - oim[mb][cc]);

@@ -201,13 +201,13 @@ static int sht_forward_i(xfb_plan* p, SlotView in, int shells_per_run, double2* 
     XFB_LAUNCH(p, PG_FFT, st, if (launch_fft(true, p->n_phi, in, shells_per_run, sub, p->A0, p->tw, S, p->n_theta, p->L, st)) return 1);
     dim3 g(cdiv(S, 16), p->L + 1);
     XFB_LAUNCH(p, PG_LEGENDRE, st,
-               legendre_forward_kernel<<<g, 128, legendre_fwd_smem(p->n_theta), st>>>(p->A0, c_out, p->FE, p->FO, S, p->L, p->n_theta, p->NP));
+               legendre_forward_kernel<<<g, LEG_THREADS, legendre_fwd_smem(p->n_theta), st>>>(p->A0, c_out, p->FE, p->FO, S, p->L, p->n_theta, p->NP));
     return 0;
 }
 static int sht_inverse_i(xfb_plan* p, const double2* c_in, double2* grid_out, int S, cudaStream_t st) {
     dim3 g(cdiv(S, 16), p->L + 1);
     XFB_LAUNCH(p, PG_LEGENDRE, st,
-               legendre_inverse_kernel<<<g, 128, legendre_inv_smem(p->n_theta, p->NP), st>>>(c_in, p->A0, p->IE, p->IO, S, p->L, p->n_theta, p->NP));
+               legendre_inverse_kernel<<<g, LEG_THREADS, legendre_inv_smem(p->n_theta, p->NP), st>>>(c_in, p->A0, p->IE, p->IO, S, p->L, p->n_theta, p->NP));
     XFB_LAUNCH(p, PG_FFT, st,
                if (launch_fft(false, p->n_phi, flat_view(p->A0, 0), 1, nullptr, grid_out, p->tw, S, p->n_theta, p->L, st)) return 1);
     return 0;
@@ -243,13 +243,13 @@ static int ft_i(xfb_plan* p, int dir, SlotView in, double2* out, int nb, cudaStr
 // shell 0 of IFT(f) from the reciprocal coefficients c = SHT(f) (internal layout): rt0[nb][n_theta][n_phi]
 static int ift_shell0_i(xfb_plan* p, const double2* c, int nb, cudaStream_t st) {
     const int rows = p->NLM * nb;
-    XFB_LAUNCH(p, PG_HANKEL, st,
+    XFB_LAUNCH(p, PG_MISC, st,
                hankel_row0_kernel<<<cdiv(rows, 8), 256, 0, st>>>(c, p->C0s, p->hankel_w, rows, nb, p->n_r, p->hankel_n_sum, p->hankel_skip,
                                                                   p->hk_inv_scale, 1));
     dim3 g(cdiv(nb, 16), p->L + 1);
-    XFB_LAUNCH(p, PG_LEGENDRE, st,
-               legendre_inverse_kernel<<<g, 128, legendre_inv_smem(p->n_theta, p->NP), st>>>(p->C0s, p->A0s, p->IE, p->IO, nb, p->L, p->n_theta, p->NP));
-    XFB_LAUNCH(p, PG_FFT, st,
+    XFB_LAUNCH(p, PG_MISC, st,
+               legendre_inverse_kernel<<<g, LEG_THREADS, legendre_inv_smem(p->n_theta, p->NP), st>>>(p->C0s, p->A0s, p->IE, p->IO, nb, p->L, p->n_theta, p->NP));
+    XFB_LAUNCH(p, PG_MISC, st,
                if (launch_fft(false, p->n_phi, flat_view(p->A0s, 0), 1, nullptr, p->rt0, p->tw, nb, p->n_theta, p->L, st)) return 1);
     return 0;
 }
