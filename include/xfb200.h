@@ -136,6 +136,8 @@ int xfb_mtip_shrinkwrap(xfb_plan* p, double sigma, double threshold, double erro
  * err [n_batch][2]. Synchronises `stream` before returning. */
 int xfb_mtip_step_host(xfb_plan* p, int32_t method, int32_t ft_stab, double beta, const double* rho_in_host,
                        double* rho_out_host, double* err_out_host, void* stream);
+/* runs per chunk of the copy-in | compute | copy-out pipeline inside xfb_mtip_step_host (default 16) */
+int xfb_plan_set_host_chunk(xfb_plan* p, int32_t runs);
 /* outputs; which: 0 last real, 1 last reciprocal, 2 best real, 3 best reciprocal (grids);
  *          4 last support, 5 best support (uint8 grids); */
 int xfb_mtip_get_grid(xfb_plan* p, int32_t which, void* out_dev, void* stream);

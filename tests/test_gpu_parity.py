@@ -172,6 +172,12 @@ def test_host_buffer_step_matches_device_loop():
     plan.mtip_step_host(HIO, True, 0.5, h_in, h_out, h_err)
     assert np.array_equal(h_out.numpy(), ref)
     assert torch.isfinite(h_err).all()
+    # chunked pipeline (copy-in | compute | copy-out streams): one run per chunk must give the same bits
+    plan.set_host_chunk(1)
+    h_out2, h_err2 = torch.empty_like(start).pin_memory(), torch.empty((2, 2), dtype=torch.float64).pin_memory()
+    plan.mtip_step_host(HIO, True, 0.5, h_in, h_out2, h_err2)
+    assert np.array_equal(h_out2.numpy(), ref)
+    assert np.array_equal(h_err2.numpy(), h_err.numpy())
     plan.close()
 
 

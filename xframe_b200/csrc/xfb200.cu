@@ -29,6 +29,9 @@ struct xfb_plan {
     double2 *A0 = nullptr, *C0 = nullptr, *C1 = nullptr, *W0 = nullptr, *W1 = nullptr, *W2 = nullptr;
     double2 *A0s = nullptr, *C0s = nullptr, *rt0 = nullptr;   // shell-0 side path of the fused ft_stab step
     int fused_ft_stab = 1;
+    // host-buffer pipeline (xfb_mtip_step_host)
+    cudaStream_t s_in = nullptr, s_out = nullptr; cudaEvent_t ev_start = nullptr; std::vector<cudaEvent_t> ev_in, ev_comp;
+    double2* stage_out = nullptr; int host_chunk = 16;
     HankelTile* hk_tiles = nullptr; int hk_tiles_n = 0, hk_tiles_nb = -1, hk_tiles_cap = 0;
     // projection
     bool has_proj = false;
@@ -155,12 +158,17 @@ int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
 
 int xfb_plan_destroy(xfb_plan* p) {
     if (!p) return 0;
-    void* ptrs[] = {p->tw, p->FE, p->FO, p->IE, p->IO, p->hankel_w, p->int_wt, p->q_pts, p->A0, p->C0, p->C1, p->W0, p->W1, p->W2, p->A0s, p->C0s, p->rt0,
+    void* ptrs[] = {p->tw, p->FE, p->FO, p->IE, p->IO, p->hankel_w, p->int_wt, p->q_pts, p->A0, p->C0, p->C1, p->W0, p->W1, p->W2, p->A0s, p->C0s, p->rt0, p->stage_out,
                     p->hk_tiles, p->orders_dev, p->kind_dev, p->act_index_dev, p->radial_mask_dev, p->v0_dev, p->pd_dev, p->vt_dev,
                     p->xt, p->tt, p->g, p->gn, p->vw, p->sigma, p->sweeps_dev, p->gemmM_dev, p->gemmT_dev, p->gemmM_tp, p->gemmT_tp,
                     p->init_support_dev, p->rho_pool, p->rh_pool, p->mask_pool, p->ls_ints, p->ls_dbl, p->partial, p->err, p->mm};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& e : p->prof_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (auto e : p->ev_in) cudaEventDestroy(e);
+    for (auto e : p->ev_comp) cudaEventDestroy(e);
+    if (p->ev_start) cudaEventDestroy(p->ev_start);
+    if (p->s_in) cudaStreamDestroy(p->s_in);
+    if (p->s_out) cudaStreamDestroy(p->s_out);
     delete p;
     return 0;
 }
@@ -563,50 +571,64 @@ int xfb_mtip_init(xfb_plan* p, const double* rho0, int32_t nb, void* stream) {
     return 0;
 }
 
+// one iteration of runs [b0, b0+nb) of the loop state; `it_index` is the error-history column it writes
+static int iterate_range(xfb_plan* p, int b0, int nb, int method, int ft_stab, double beta, int it_index, cudaStream_t st) {
+    const int S = nb * p->n_r;
+    const int eb = ew_blocks(p->G);
+    const long long pool_stride = (long long)p->max_batch * p->G;
+    auto pv = [&](double2* pool, const int* slot) {
+        SlotView v; v.base = pool + (long long)b0 * p->G; v.slot = slot + b0; v.slot_stride = pool_stride; v.run_stride = p->G; return v;
+    };
+    LoopState ls = p->ls;
+    ls.rho_cur += b0; ls.rho_best += b0; ls.rho_next += b0; ls.rh_cur += b0; ls.rh_best += b0; ls.rh_next += b0;
+    ls.mask_cur += b0; ls.mask_best += b0; ls.mask_next += b0; ls.enforce_cur += b0; ls.enforce_best += b0;
+    ls.best_err += b0; ls.last_err += b0; ls.hist += (long long)b0 * ls.hist_cap;
+    double* err = p->err + 2 * b0;
+    const bool fused = ft_stab && p->fused_ft_stab;
+    // 1. rho_hat = FT(rho)                                   (reconstruct.py:585)
+    if (!fused) {
+        if (ft_i(p, 0, pv(p->rho_pool, p->ls.rho_cur), p->W0, nb, st)) return 1;
+    } else {
+        if (sht_forward_i(p, pv(p->rho_pool, p->ls.rho_cur), p->n_r, p->C0, S, st)) return 1;
+        if (hankel_i(p, 0, p->C0, p->C1, nb, st)) return 1;
+        // C1 = SHT(rho_hat) (exact Gauss quadrature of a band-limited field): shell 0 of IFT(rho_hat) from it
+        if (ift_shell0_i(p, p->C1, nb, st)) return 1;
+        if (sht_inverse_i(p, p->C1, p->W0, S, st)) return 1;
+    }
+    // 2. |rho_hat|^2 -> I_lm                                 (:519-520)
+    XFB_LAUNCH(p, PG_POINTWISE, st, square_kernel<<<ew_blocks((long long)nb * p->G), 256, 0, st>>>(p->W0, p->W1, (long long)nb * p->G));
+    if (sht_forward_i(p, flat_view(p->W1, p->G), p->n_r, p->C0, S, st)) return 1;
+    // 3. projection onto the invariants                      (:521-523)
+    if (project_i(p, p->C0, p->C1, nb, st)) return 1;
+    // 4. I_proj on the grid, modified intensity              (:524-525)
+    if (sht_inverse_i(p, p->C1, p->W1, S, st)) return 1;
+    XFB_LAUNCH(p, PG_POINTWISE, st,
+               modify_intensity_kernel<<<dim3(eb, nb), 256, 0, st>>>(p->W0, p->W1, pv(p->rh_pool, p->ls.rh_next), p->G));
+    // 5. back to real space (+ ft_stab correction terms)     (:586-588 / :579)
+    // 6. real projection + HIO/ER + error                    (:589-590)
+    const uint8_t* mask = p->mask_pool + (long long)b0 * p->G;
+    if (fused) {
+        // IFT is linear: IFT(rho_hat') + (rho - IFT(rho_hat)) = IFT(rho_hat' - rho_hat) + rho   (r >= 1)
+        if (ft_i(p, 1, pv(p->rh_pool, p->ls.rh_next), p->W1, nb, st, p->W0)) return 1;
+        if (real_update_i(p, method, beta, p->W1, nullptr, pv(p->rho_pool, p->ls.rho_cur), pv(p->rho_pool, p->ls.rho_next), mask,
+                          ls.mask_cur, pool_stride, ls.enforce_cur, err, nb, st, p->rt0)) return 1;
+    } else {
+        if (ft_i(p, 1, pv(p->rh_pool, p->ls.rh_next), p->W1, nb, st)) return 1;
+        if (ft_stab) { if (ft_i(p, 1, flat_view(p->W0, p->G), p->W2, nb, st)) return 1; }
+        if (real_update_i(p, method, beta, p->W1, ft_stab ? p->W2 : nullptr, pv(p->rho_pool, p->ls.rho_cur),
+                          pv(p->rho_pool, p->ls.rho_next), mask, ls.mask_cur, pool_stride, ls.enforce_cur, err, nb, st)) return 1;
+    }
+    // 7. bookkeeping                                         (:924-939)
+    XFB_LAUNCH(p, PG_MISC, st, loop_update_kernel<<<cdiv(nb, 128), 128, 0, st>>>(ls, err, it_index, nb));
+    return 0;
+}
+
 int xfb_mtip_iterate(xfb_plan* p, int32_t method, int32_t ft_stab, int32_t n_iter, const double* betas, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = p->n_batch;
     if (nb < 1) XFB_FAIL("xfb_mtip_init has not been called");
-    const int S = nb * p->n_r;
-    const int eb = ew_blocks(p->G);
     for (int it = 0; it < n_iter; ++it) {
-        const bool fused = ft_stab && p->fused_ft_stab;
-        // 1. rho_hat = FT(rho)                                   (reconstruct.py:585)
-        if (!fused) {
-            if (ft_i(p, 0, pool_view(p->rho_pool, p->ls.rho_cur, p), p->W0, nb, st)) return 1;
-        } else {
-            if (sht_forward_i(p, pool_view(p->rho_pool, p->ls.rho_cur, p), p->n_r, p->C0, S, st)) return 1;
-            if (hankel_i(p, 0, p->C0, p->C1, nb, st)) return 1;
-            // C1 = SHT(rho_hat) (exact Gauss quadrature of a band-limited field): shell 0 of IFT(rho_hat) from it
-            if (ift_shell0_i(p, p->C1, nb, st)) return 1;
-            if (sht_inverse_i(p, p->C1, p->W0, S, st)) return 1;
-        }
-        // 2. |rho_hat|^2 -> I_lm                                 (:519-520)
-        XFB_LAUNCH(p, PG_POINTWISE, st, square_kernel<<<ew_blocks((long long)nb * p->G), 256, 0, st>>>(p->W0, p->W1, (long long)nb * p->G));
-        if (sht_forward_i(p, flat_view(p->W1, p->G), p->n_r, p->C0, S, st)) return 1;
-        // 3. projection onto the invariants                      (:521-523)
-        if (project_i(p, p->C0, p->C1, nb, st)) return 1;
-        // 4. I_proj on the grid, modified intensity              (:524-525)
-        if (sht_inverse_i(p, p->C1, p->W1, S, st)) return 1;
-        XFB_LAUNCH(p, PG_POINTWISE, st,
-                   modify_intensity_kernel<<<dim3(eb, nb), 256, 0, st>>>(p->W0, p->W1, pool_view(p->rh_pool, p->ls.rh_next, p), p->G));
-        // 5. back to real space (+ ft_stab correction terms)     (:586-588 / :579)
-        // 6. real projection + HIO/ER + error                    (:589-590)
-        if (fused) {
-            // IFT is linear: IFT(rho_hat') + (rho - IFT(rho_hat)) = IFT(rho_hat' - rho_hat) + rho   (r >= 1)
-            if (ft_i(p, 1, pool_view(p->rh_pool, p->ls.rh_next, p), p->W1, nb, st, p->W0)) return 1;
-            if (real_update_i(p, method, betas ? betas[it] : 0.0, p->W1, nullptr, pool_view(p->rho_pool, p->ls.rho_cur, p),
-                              pool_view(p->rho_pool, p->ls.rho_next, p), p->mask_pool, p->ls.mask_cur, (long long)p->max_batch * p->G,
-                              p->ls.enforce_cur, p->err, nb, st, p->rt0)) return 1;
-        } else {
-            if (ft_i(p, 1, pool_view(p->rh_pool, p->ls.rh_next, p), p->W1, nb, st)) return 1;
-            if (ft_stab) { if (ft_i(p, 1, flat_view(p->W0, p->G), p->W2, nb, st)) return 1; }
-            if (real_update_i(p, method, betas ? betas[it] : 0.0, p->W1, ft_stab ? p->W2 : nullptr, pool_view(p->rho_pool, p->ls.rho_cur, p),
-                              pool_view(p->rho_pool, p->ls.rho_next, p), p->mask_pool, p->ls.mask_cur, (long long)p->max_batch * p->G,
-                              p->ls.enforce_cur, p->err, nb, st)) return 1;
-        }
-        // 7. bookkeeping                                         (:924-939)
-        XFB_LAUNCH(p, PG_MISC, st, loop_update_kernel<<<cdiv(nb, 128), 128, 0, st>>>(p->ls, p->err, p->it_done, nb));
+        if (iterate_range(p, 0, nb, method, ft_stab, betas ? betas[it] : 0.0, p->it_done, st)) return 1;
         p->it_done++;
     }
     return 0;
@@ -652,23 +674,62 @@ int xfb_mtip_get_grid(xfb_plan* p, int32_t which, void* out, void* stream) {
 }
 
 // End-to-end step with HOST buffers (pinned recommended): H2D of the batch's densities, one iteration, D2H of the
-// updated densities and of the per-run (numerator, denominator) of the real-space error.
+// updated densities and of the per-run (numerator, denominator) of the real-space error.  The batch is cut into
+// chunks that flow through three streams (copy-in | compute | copy-out) so PCIe transfers overlap the kernels.
 int xfb_mtip_step_host(xfb_plan* p, int32_t method, int32_t ft_stab, double beta, const double* rho_in_host, double* rho_out_host,
                        double* err_out_host, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = p->n_batch;
     if (nb < 1) XFB_FAIL("xfb_mtip_init has not been called");
-    const size_t bytes = (size_t)nb * p->G * sizeof(double2);
     const int eb = ew_blocks(p->G);
-    XFB_CUDA(cudaMemcpyAsync(p->W2, rho_in_host, bytes, cudaMemcpyHostToDevice, st));
-    XFB_LAUNCH(p, PG_MISC, st, scatter_slot_kernel<<<dim3(eb, nb), 256, 0, st>>>(p->W2, pool_view(p->rho_pool, p->ls.rho_cur, p), p->G));
-    if (xfb_mtip_iterate(p, method, ft_stab, 1, &beta, stream)) return 1;
-    XFB_LAUNCH(p, PG_MISC, st, gather_slot_kernel<<<dim3(eb, nb), 256, 0, st>>>(pool_view(p->rho_pool, p->ls.rho_cur, p), p->W0, p->G));
-    XFB_CUDA(cudaMemcpyAsync(rho_out_host, p->W0, bytes, cudaMemcpyDeviceToHost, st));
+    const bool pipelined = (!ft_stab || p->fused_ft_stab) && nb > p->host_chunk;   // W2 is free as H2D staging then
+    if (!p->s_in) {
+        XFB_CUDA(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
+        XFB_CUDA(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+        XFB_CUDA(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
+        if (dev_alloc(p, &p->stage_out, (size_t)p->max_batch * p->G)) return 1;
+    }
+    const int cs = pipelined ? p->host_chunk : nb;
+    const int nchunk = cdiv(nb, cs);
+    while ((int)p->ev_in.size() < nchunk) {
+        cudaEvent_t a, b;
+        XFB_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        XFB_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        p->ev_in.push_back(a); p->ev_comp.push_back(b);
+    }
+    // the side streams start after everything already queued on the caller's stream
+    XFB_CUDA(cudaEventRecord(p->ev_start, st));
+    XFB_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_start, 0));
+    XFB_CUDA(cudaStreamWaitEvent(p->s_out, p->ev_start, 0));
+    const double2* hin = (const double2*)rho_in_host;
+    double2* hout = (double2*)rho_out_host;
+    for (int c = 0; c < nchunk; ++c) {
+        const int b0 = c * cs, n = std::min(cs, nb - b0);
+        const size_t off = (size_t)b0 * p->G, bytes = (size_t)n * p->G * sizeof(double2);
+        XFB_CUDA(cudaMemcpyAsync(p->W2 + off, hin + off, bytes, cudaMemcpyHostToDevice, p->s_in));
+        XFB_CUDA(cudaEventRecord(p->ev_in[c], p->s_in));
+    }
+    const long long pool_stride = (long long)p->max_batch * p->G;
+    for (int c = 0; c < nchunk; ++c) {
+        const int b0 = c * cs, n = std::min(cs, nb - b0);
+        const size_t off = (size_t)b0 * p->G, bytes = (size_t)n * p->G * sizeof(double2);
+        XFB_CUDA(cudaStreamWaitEvent(st, p->ev_in[c], 0));
+        SlotView cur; cur.base = p->rho_pool + off; cur.slot = p->ls.rho_cur + b0; cur.slot_stride = pool_stride; cur.run_stride = p->G;
+        XFB_LAUNCH(p, PG_MISC, st, scatter_slot_kernel<<<dim3(eb, n), 256, 0, st>>>(p->W2 + off, cur, p->G));
+        if (iterate_range(p, b0, n, method, ft_stab, beta, p->it_done, st)) return 1;
+        XFB_LAUNCH(p, PG_MISC, st, gather_slot_kernel<<<dim3(eb, n), 256, 0, st>>>(cur, p->stage_out + off, p->G));
+        XFB_CUDA(cudaEventRecord(p->ev_comp[c], st));
+        XFB_CUDA(cudaStreamWaitEvent(p->s_out, p->ev_comp[c], 0));
+        XFB_CUDA(cudaMemcpyAsync(hout + off, p->stage_out + off, bytes, cudaMemcpyDeviceToHost, p->s_out));
+    }
+    p->it_done++;
     XFB_CUDA(cudaMemcpyAsync(err_out_host, p->err, (size_t)nb * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     XFB_CUDA(cudaStreamSynchronize(st));
+    XFB_CUDA(cudaStreamSynchronize(p->s_out));
     return 0;
 }
+
+int xfb_plan_set_host_chunk(xfb_plan* p, int32_t runs) { if (runs < 1) XFB_FAIL("chunk must be >= 1"); p->host_chunk = runs; return 0; }
 
 int xfb_mtip_get_errors(xfb_plan* p, double* hist, int32_t cap, double* best, int32_t* n_done, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;

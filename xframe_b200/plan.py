@@ -256,6 +256,9 @@ class Plan:
         _lib.check(self.lib.xfb_mtip_step_host(self.h, int(method), int(bool(ft_stab)), float(beta), _ptr(rho_in), _ptr(rho_out),
                                                _ptr(err_out), _stream()))
 
+    def set_host_chunk(self, runs):
+        _lib.check(self.lib.xfb_plan_set_host_chunk(self.h, int(runs)))
+
     def mtip_shrinkwrap(self, sigma, threshold, error_limit):
         _lib.check(self.lib.xfb_mtip_shrinkwrap(self.h, float(sigma), float(threshold), float(error_limit), _stream()))
 
