@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(RU_THREADS) real_update_kernel(const double2* 
         if (method == 0 && msel) o = make_double2(prev.x - beta * (v.x - p.x), prev.y - beta * (v.y - p.y));
         rn[i] = o;
         if (!rd.err_inside || in_init) {
-            const double w = wt[i / n_phi];
+            const double w = __ldg(wt + (unsigned)i / (unsigned)n_phi);     // per_run < 2^31: 32-bit division
             const double dx = v.x - p.x, dy = v.y - p.y;
             s_diff += w * (dx * dx + dy * dy);
             s_val += w * (v.x * v.x + v.y * v.y);
