@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libxfb200.so')
+LIB_PATH = os.environ.get('XFB200_LIB', os.path.join(_HERE, 'lib', 'libxfb200.so'))   # override: kernel experiments only
 
 
 class XfbError(RuntimeError):

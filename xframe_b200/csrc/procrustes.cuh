@@ -58,13 +58,17 @@ __global__ void procrustes_pack_kernel(const double2* __restrict__ c, double* __
 //   round-robin round in flight); dot products are reduced with 3 xor-shuffles inside the 8-lane group; the G
 //   elements stay in registers between the dot and the rotation (one smem read + one write per element).
 //   Outputs: gn = G~ / sigma (zero for dropped columns), sigma [n_cols].
-#define JG 8                 // lanes per column pair
+#ifndef JG
+#define JG 8                 // lanes per column pair (8, 16 or 32)
+#endif
+#define JGPW (32 / JG)       // pair groups per warp
+#define JPASS (64 / (16 * JGPW))   // passes per round: 64 pair slots / (16 warps x groups per warp)
 __host__ __device__ inline int jacobi_stride(int len) {
     int s = (len + JG - 1) / JG * JG;
-    if ((s & 15) == 0) s += 8;
+    if ((s & 15) == 0) s += 8;      // == 8 (mod 16) doubles: neighbouring pair groups fall on different banks
     return s;
 }
-#define JMAXE 16             // max elements per lane (column length <= 128)
+#define JMAXE (128 / JG)     // max elements per lane (column length <= 128)
 
 template <bool WSM>
 __device__ __forceinline__ void jacobi_sweep_rounds(double* __restrict__ Gs, int ldg, int ne, double* __restrict__ Wb, int wstride,
@@ -75,14 +79,22 @@ __device__ __forceinline__ void jacobi_sweep_rounds(double* __restrict__ Gs, int
     const int mod = npad - 1;
     // round-robin (circle method): position 0 is fixed, the element at position k>=1 in round r is
     // 1 + ((k-1-r) mod (npad-1)); tracked incrementally (one decrement with wrap per round, no integer division).
-    const int i = slot0;
-    const bool has_slot = i < half;                       // half <= n_slots (n <= 128 columns, 64 pair slots)
-    const int ka = i, kb = npad - 1 - i;
-    int pa = (ka == 0) ? 0 : 1 + (ka - 1) % mod;
-    int pb = has_slot ? 1 + (kb - 1) % mod : 1;
+    int pa_[JPASS], pb_[JPASS];
+#pragma unroll
+    for (int ps = 0; ps < JPASS; ++ps) {
+        const int i = slot0 + ps * n_slots;
+        const int ka = i, kb = npad - 1 - i;
+        pa_[ps] = (ka == 0) ? 0 : 1 + (ka - 1) % mod;
+        pb_[ps] = (i < half) ? 1 + (kb - 1) % mod : 1;
+    }
     for (int r = 0; r < npad - 1; ++r) {
-        {
-            if ((slot0 & ~3) >= half) { __syncthreads(); continue; }   // warp-uniform: no pair for this warp
+#pragma unroll
+        for (int ps = 0; ps < JPASS; ++ps) {
+            const int i = slot0 + ps * n_slots;
+            const int warp_first = (slot0 / JGPW) * JGPW + ps * n_slots;     // first pair slot of this warp in this pass
+            if (warp_first >= half) continue;                                // warp-uniform: nothing to do
+            const bool has_slot = i < half;
+            int pa = pa_[ps], pb = pb_[ps];
             bool valid = has_slot && (pa < nact) && (pb < nact);      // bye against the padding element
             int p = 0, q = 0, wpi = 0, wqi = 0;
             if (valid) {
@@ -92,8 +104,8 @@ __device__ __forceinline__ void jacobi_sweep_rounds(double* __restrict__ Gs, int
                 wpi = WSM ? sa : p;                                // smem: compact slot ; global: column index
                 wqi = WSM ? sb : q;
             }
-            if (ka != 0) pa = (pa == 1) ? mod : pa - 1;             // positions for the next round
-            pb = (pb == 1) ? mod : pb - 1;
+            if (i != 0) pa_[ps] = (pa == 1) ? mod : pa - 1;         // positions for the next round
+            pb_[ps] = (pb == 1) ? mod : pb - 1;
             double* gp = Gs + (size_t)p * ldg + sub;
             double* gq = Gs + (size_t)q * ldg + sub;
             double* wp = Wb + (size_t)wpi * wstride + sub;
@@ -123,7 +135,7 @@ __device__ __forceinline__ void jacobi_sweep_rounds(double* __restrict__ Gs, int
                 }
             }
 #pragma unroll
-            for (int off = 4; off > 0; off >>= 1) {
+            for (int off = JG / 2; off > 0; off >>= 1) {
                 app += __shfl_xor_sync(0xffffffffu, app, off);
                 aqq += __shfl_xor_sync(0xffffffffu, aqq, off);
                 apq += __shfl_xor_sync(0xffffffffu, apq, off);
@@ -183,9 +195,9 @@ __global__ void __launch_bounds__(512, 1) procrustes_jacobi_kernel(const double*
     __shared__ int s_nact, s_rot;
     __shared__ double s_thr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-    const int grp = lane >> 3, sub = lane & (JG - 1);     // 4 groups of 8 lanes per warp
-    const int n_slots = nwarp * 4;
-    const int slot0 = warp * 4 + grp;
+    const int grp = lane / JG, sub = lane & (JG - 1);     // JGPW groups of JG lanes per warp
+    const int n_slots = nwarp * JGPW;
+    const int slot0 = warp * JGPW + grp;
     const int wr_e = (n_r_grid + JG - 1) / JG;            // accumulator elements per lane
     const int wld = jacobi_stride(n_r_grid);              // smem accumulator column stride
 
@@ -215,14 +227,13 @@ __global__ void __launch_bounds__(512, 1) procrustes_jacobi_kernel(const double*
         int sweep = 0;
         for (; sweep < max_sweeps; ++sweep) {
             // ---- column norms (one 8-lane group per column)
-            for (int c0 = warp * 4; c0 < n; c0 += n_slots) {      // warp-uniform trip count (shuffles need all lanes)
+            for (int c0 = warp * JGPW; c0 < n; c0 += n_slots) {      // warp-uniform trip count (shuffles need all lanes)
                 const int c = c0 + grp;
                 double s = 0.0;
                 if (c < n)
                     for (int t = 0; t < ne; ++t) { const double v = Gs[c * ldg + sub + JG * t]; s += v * v; }
-                s += __shfl_xor_sync(0xffffffffu, s, 4);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
+#pragma unroll
+                for (int off = JG / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
                 if (sub == 0 && c < n) nrm2[c] = s;
             }
             __syncthreads();
@@ -267,14 +278,13 @@ __global__ void __launch_bounds__(512, 1) procrustes_jacobi_kernel(const double*
         }
         __syncthreads();
         // ---- final norms -> sigma, normalised columns
-        for (int c0 = warp * 4; c0 < n; c0 += n_slots) {
+        for (int c0 = warp * JGPW; c0 < n; c0 += n_slots) {
             const int c = c0 + grp;
             double s = 0.0;
             if (c < n)
                 for (int t = 0; t < ne; ++t) { const double v = Gs[c * ldg + sub + JG * t]; s += v * v; }
-            s += __shfl_xor_sync(0xffffffffu, s, 4);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
+#pragma unroll
+            for (int off = JG / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
             if (sub == 0 && c < n) nrm2[c] = s;
         }
         __syncthreads();
