@@ -305,3 +305,36 @@ def test_worker_result_schema():
         assert r['final_error'] == r['error_dict']['main'].min()
         assert len(r['projection_matrices']) == int(g['l_max']) + 1
     assert res[0]['final_error'] != res[1]['final_error']       # different seeds -> different runs
+
+
+def test_full_tutorial_reconstruction_statistics():
+    """Whole tutorial schedule (600 iterations + 6 SW, L=63, N_r=128) for the seeds the oracle was run with
+    (tests/golden/full_run_oracle.json, made by tools/oracle_full_run.py).  HIO is chaotic (differences grow ~2.5x per
+    iteration), so trajectories are compared where they are comparable: the first iteration tightly, the final
+    real-space error and the support size statistically."""
+    import json, os
+    from helpers import GOLDEN
+    from xframe_b200 import setup_host as S
+    from xframe_b200.plan import Plan
+    from xframe_b200.settings import tutorial_settings
+    from xframe_b200.worker import ProjectWorker
+    ref = json.load(open(os.path.join(GOLDEN, 'full_run_oracle.json')))['runs']
+    seeds = [r['seed'] for r in ref]
+    sd = tutorial_settings(grid={'max_q': 0.322416, 'max_order': 63, 'n_phi': 128, 'n_theta': 64, 'n_radial_points': 128})
+    sd['GPU'] = {'use': True, 'batch': len(seeds), 'seed': None}
+    boot = Plan(63, 128, 0.322416, n_theta=64, n_phi=128, max_batch=1)
+    data = S.invariants_from_density(boot, S.six_sphere_density(boot))
+    boot.close()
+    w = ProjectWorker(sd, data, n_reconstructions=len(seeds), seeds=seeds)
+    res, _ = w.run()
+    ref_final = np.median([r['final_error'] for r in ref])
+    ref_last = np.median([r['last_error'] for r in ref])
+    for r, o in zip(res, ref):
+        e = r['error_dict']['main']
+        assert len(e) == o['n_errors'] == 600
+        assert abs(e[0] - o['errors_every_20'][0]) < 1e-6 * o['errors_every_20'][0]      # same guess, same first iteration
+        assert np.isfinite(r['real_density']).all()
+        assert ref_final / 4 < r['final_error'] < ref_final * 4
+        assert ref_last / 3 < e[-1] < ref_last * 3
+        assert 0.03 < r['last_support_mask'].mean() < 0.25
+    w.plan.close()
