@@ -64,13 +64,14 @@ __global__ void procrustes_pack_kernel(const double2* __restrict__ c, double* __
 #define JGPW (32 / JG)       // pair groups per warp
 #define JPASS (64 / (16 * JGPW))   // passes per round: 64 pair slots / (16 warps x groups per warp)
 __host__ __device__ inline int jacobi_stride(int len) {
-    int s = (len + JG - 1) / JG * JG;
-    if ((s & 15) == 0) s += 8;      // == 8 (mod 16) doubles: neighbouring pair groups fall on different banks
-    return s;
+    return len <= 64 ? 64 : 128;    // columns are zero padded to 64 / 128 elements (NV2 = 4 / 8 double2 steps per lane)
 }
 #define JMAXE (128 / JG)     // max elements per lane (column length <= 128)
 
-template <bool WSM>
+// All rounds of one sweep.  WSM: accumulator columns staged in shared memory (the normal case) -- 128-bit shared
+// memory accesses, each lane owns the element pairs (2 sub, 2 sub + 1) + 16 t, NV2 = number of such double2 steps of
+// a G column (4 for columns up to 64 long, 8 up to 128).  !WSM: rare fallback, accumulator rotated in global memory.
+template <bool WSM, int NV2>
 __device__ __forceinline__ void jacobi_sweep_rounds(double* __restrict__ Gs, int ldg, int ne, double* __restrict__ Wb, int wstride,
                                                     int n_r_grid, int wr_e, const int* __restrict__ list, int nact, double thr,
                                                     double tol, int slot0, int n_slots, int sub, int* s_rot) {
@@ -87,6 +88,7 @@ __device__ __forceinline__ void jacobi_sweep_rounds(double* __restrict__ Gs, int
         pa_[ps] = (ka == 0) ? 0 : 1 + (ka - 1) % mod;
         pb_[ps] = (i < half) ? 1 + (kb - 1) % mod : 1;
     }
+    constexpr int WV2 = 128 / (2 * JG);                  // double2 steps of an accumulator column (N_r <= 128, zero padded)
     for (int r = 0; r < npad - 1; ++r) {
 #pragma unroll
         for (int ps = 0; ps < JPASS; ++ps) {
@@ -106,82 +108,108 @@ __device__ __forceinline__ void jacobi_sweep_rounds(double* __restrict__ Gs, int
             }
             if (i != 0) pa_[ps] = (pa == 1) ? mod : pa - 1;         // positions for the next round
             pb_[ps] = (pb == 1) ? mod : pb - 1;
-            double* gp = Gs + (size_t)p * ldg + sub;
-            double* gq = Gs + (size_t)q * ldg + sub;
-            double* wp = Wb + (size_t)wpi * wstride + sub;
-            double* wq = Wb + (size_t)wqi * wstride + sub;
-            double xw[JMAXE], yw[JMAXE];
-            if (!WSM && valid) {                                    // global accumulator: prefetch before the dot products
+            if constexpr (WSM) {
+                double2* gp = reinterpret_cast<double2*>(Gs + (size_t)p * ldg) + sub;
+                double2* gq = reinterpret_cast<double2*>(Gs + (size_t)q * ldg) + sub;
+                double2 xg[NV2], yg[NV2];
+                double app = 0.0, aqq = 0.0, apq = 0.0;
+                if (valid) {
 #pragma unroll
-                for (int t = 0; t < JMAXE; ++t)
-                    if (t < wr_e && sub + JG * t < n_r_grid) { xw[t] = __ldcg(wp + JG * t); yw[t] = __ldcg(wq + JG * t); }
-            }
-            double xg[WSM ? JMAXE : 1], yg[WSM ? JMAXE : 1];    // G stays in registers only when the accumulator is in smem
-            double app = 0.0, aqq = 0.0, apq = 0.0;
-            if (valid) {
-                if constexpr (WSM) {
+                    for (int t = 0; t < NV2; ++t) {
+                        xg[t] = gp[JG * t]; yg[t] = gq[JG * t];
+                        app += xg[t].x * xg[t].x; aqq += yg[t].x * yg[t].x; apq += xg[t].x * yg[t].x;
+                        app += xg[t].y * xg[t].y; aqq += yg[t].y * yg[t].y; apq += xg[t].y * yg[t].y;
+                    }
+                }
+#pragma unroll
+                for (int off = JG / 2; off > 0; off >>= 1) {
+                    app += __shfl_xor_sync(0xffffffffu, app, off);
+                    aqq += __shfl_xor_sync(0xffffffffu, aqq, off);
+                    apq += __shfl_xor_sync(0xffffffffu, apq, off);
+                }
+                bool rot = valid && (app > thr) && (aqq > thr);
+                if (rot) rot = apq * apq > (tol * tol) * (app * aqq);
+                if (rot) {
+                    // tan(2 theta) = 2 apq / (aqq - app), |theta| <= pi/4 (same rotation as the textbook zeta/t form)
+                    const double d = aqq - app, s2 = 2.0 * apq;
+                    const double rh = rsqrt(d * d + s2 * s2);
+                    const double u = 0.5 + 0.5 * fabs(d) * rh;            // cos^2(theta)
+                    const double rc = rsqrt(u);
+                    const double cs = u * rc;
+                    const double sn = copysign(0.5 * s2 * rh, d * s2) * rc;   // sin(2 theta) / (2 cos theta)
+#pragma unroll
+                    for (int t = 0; t < NV2; ++t) {
+                        gp[JG * t] = make_double2(cs * xg[t].x - sn * yg[t].x, cs * xg[t].y - sn * yg[t].y);
+                        gq[JG * t] = make_double2(sn * xg[t].x + cs * yg[t].x, sn * xg[t].y + cs * yg[t].y);
+                    }
+                    double2* wp = reinterpret_cast<double2*>(Wb + (size_t)wpi * wstride) + sub;
+                    double2* wq = reinterpret_cast<double2*>(Wb + (size_t)wqi * wstride) + sub;
+#pragma unroll
+                    for (int t = 0; t < WV2; ++t) {
+                        const double2 x = wp[JG * t], y = wq[JG * t];
+                        wp[JG * t] = make_double2(cs * x.x - sn * y.x, cs * x.y - sn * y.y);
+                        wq[JG * t] = make_double2(sn * x.x + cs * y.x, sn * x.y + cs * y.y);
+                    }
+                    if (sub == 0) *s_rot = 1;
+                }
+            } else {
+                double* gp = Gs + (size_t)p * ldg + sub;
+                double* gq = Gs + (size_t)q * ldg + sub;
+                double* wp = Wb + (size_t)wpi * wstride + sub;
+                double* wq = Wb + (size_t)wqi * wstride + sub;
+                double xw[JMAXE], yw[JMAXE];
+                if (valid) {                                        // global accumulator: prefetch before the dot products
 #pragma unroll
                     for (int t = 0; t < JMAXE; ++t)
-                        if (t < ne) {
-                            xg[t] = gp[JG * t]; yg[t] = gq[JG * t];
-                            app += xg[t] * xg[t]; aqq += yg[t] * yg[t]; apq += xg[t] * yg[t];
-                        }
-                } else {
+                        if (t < wr_e && sub + JG * t < n_r_grid) { xw[t] = __ldcg(wp + JG * t); yw[t] = __ldcg(wq + JG * t); }
+                }
+                double app = 0.0, aqq = 0.0, apq = 0.0;
+                if (valid) {
 #pragma unroll 4
                     for (int t = 0; t < ne; ++t) {
                         const double x = gp[JG * t], y = gq[JG * t];
                         app += x * x; aqq += y * y; apq += x * y;
                     }
                 }
-            }
 #pragma unroll
-            for (int off = JG / 2; off > 0; off >>= 1) {
-                app += __shfl_xor_sync(0xffffffffu, app, off);
-                aqq += __shfl_xor_sync(0xffffffffu, aqq, off);
-                apq += __shfl_xor_sync(0xffffffffu, apq, off);
-            }
-            bool rot = valid && (app > thr) && (aqq > thr);
-            if (rot) rot = apq * apq > (tol * tol) * (app * aqq);
-            if (rot) {
-                // tan(2 theta) = 2 apq / (aqq - app), |theta| <= pi/4 (same rotation as the textbook zeta/t form)
-                const double d = aqq - app, s2 = 2.0 * apq;
-                const double rh = rsqrt(d * d + s2 * s2);
-                const double u = 0.5 + 0.5 * fabs(d) * rh;            // cos^2(theta)
-                const double rc = rsqrt(u);
-                const double cs = u * rc;
-                const double sn = copysign(0.5 * s2 * rh, d * s2) * rc;   // sin(2 theta) / (2 cos theta)
-                if constexpr (WSM) {
-#pragma unroll
-                    for (int tt = 0; tt < JMAXE; ++tt)
-                        if (tt < ne) {
-                            gp[JG * tt] = cs * xg[tt] - sn * yg[tt];
-                            gq[JG * tt] = sn * xg[tt] + cs * yg[tt];
-                        }
-                } else {
+                for (int off = JG / 2; off > 0; off >>= 1) {
+                    app += __shfl_xor_sync(0xffffffffu, app, off);
+                    aqq += __shfl_xor_sync(0xffffffffu, aqq, off);
+                    apq += __shfl_xor_sync(0xffffffffu, apq, off);
+                }
+                bool rot = valid && (app > thr) && (aqq > thr);
+                if (rot) rot = apq * apq > (tol * tol) * (app * aqq);
+                if (rot) {
+                    const double d = aqq - app, s2 = 2.0 * apq;
+                    const double rh = rsqrt(d * d + s2 * s2);
+                    const double u = 0.5 + 0.5 * fabs(d) * rh;
+                    const double rc = rsqrt(u);
+                    const double cs = u * rc;
+                    const double sn = copysign(0.5 * s2 * rh, d * s2) * rc;
 #pragma unroll 4
                     for (int tt = 0; tt < ne; ++tt) {
                         const double x = gp[JG * tt], y = gq[JG * tt];
                         gp[JG * tt] = cs * x - sn * y;
                         gq[JG * tt] = sn * x + cs * y;
                     }
-                }
 #pragma unroll
-                for (int tt = 0; tt < JMAXE; ++tt)
-                    if (tt < wr_e && sub + JG * tt < n_r_grid) {
-                        if (WSM) {
-                            const double x = wp[JG * tt], y = wq[JG * tt];
-                            wp[JG * tt] = cs * x - sn * y;
-                            wq[JG * tt] = sn * x + cs * y;
-                        } else {
+                    for (int tt = 0; tt < JMAXE; ++tt)
+                        if (tt < wr_e && sub + JG * tt < n_r_grid) {
                             __stcg(wp + JG * tt, cs * xw[tt] - sn * yw[tt]);
                             __stcg(wq + JG * tt, sn * xw[tt] + cs * yw[tt]);
                         }
-                    }
-                if (sub == 0) *s_rot = 1;
+                    if (sub == 0) *s_rot = 1;
+                }
             }
         }
         __syncthreads();
     }
+}
+
+// rare fallback kept out of line so it does not inflate the register allocation of the shared-memory path
+__device__ __noinline__ void jacobi_sweep_global(double* Gs, int ldg, int ne, double* W, int n_r_grid, int wr_e, const int* list, int nact,
+                                                 double thr, double tol, int slot0, int n_slots, int sub, int* s_rot) {
+    jacobi_sweep_rounds<false, 1>(Gs, ldg, ne, W, n_r_grid, n_r_grid, wr_e, list, nact, thr, tol, slot0, n_slots, sub, s_rot);
 }
 
 __global__ void __launch_bounds__(512, 1) procrustes_jacobi_kernel(const double* __restrict__ g_in, double* __restrict__ gn_out,
@@ -199,7 +227,7 @@ __global__ void __launch_bounds__(512, 1) procrustes_jacobi_kernel(const double*
     const int n_slots = nwarp * JGPW;
     const int slot0 = warp * JGPW + grp;
     const int wr_e = (n_r_grid + JG - 1) / JG;            // accumulator elements per lane
-    const int wld = jacobi_stride(n_r_grid);              // smem accumulator column stride
+    const int wld = 128;                                  // smem accumulator column stride (N_r <= 128, zero padded)
 
     for (int prob = blockIdx.x; prob < n_orders * n_batch; prob += gridDim.x) {
         const int oi = prob / n_batch;                     // orders are sorted largest first
@@ -212,8 +240,9 @@ __global__ void __launch_bounds__(512, 1) procrustes_jacobi_kernel(const double*
         double* Gs = smem_j;                               // [n][ldg]
         double* nrm2 = Gs + (size_t)n * ldg;               // [n]
         int* list = (int*)(nrm2 + n);                      // [n]
-        double* Ws = nrm2 + n + (n + 1) / 2;               // [cap][wld]
-        const int cap = (smem_doubles - (n * ldg + n + (n + 1) / 2)) / wld;
+        const int ws_off = (n * ldg + n + (n + 1) / 2 + 1) & ~1;      // 16-byte aligned (double2 accesses)
+        double* Ws = smem_j + ws_off;                      // [cap][wld]
+        const int cap = (smem_doubles - ws_off) / wld;
         const double* g = g_in + (size_t)b * g_run_stride + o.g_off;
         double* W = vw + (size_t)b * vw_run_stride + o.vw_off;
         const double* V0 = vt + o.pd_off;
@@ -258,18 +287,19 @@ __global__ void __launch_bounds__(512, 1) procrustes_jacobi_kernel(const double*
             if (nact < 2) break;
             if (nact <= cap) {
                 // stage the active accumulator columns in shared memory for this sweep
-                for (int i = tid; i < nact * n_r_grid; i += blockDim.x) {
-                    const int a = i / n_r_grid, e = i - a * n_r_grid;
-                    Ws[a * wld + e] = __ldcg(W + (size_t)list[a] * n_r_grid + e);
+                for (int i = tid; i < nact * wld; i += blockDim.x) {
+                    const int a = i / wld, e = i - a * wld;
+                    Ws[i] = (e < n_r_grid) ? __ldcg(W + (size_t)list[a] * n_r_grid + e) : 0.0;
                 }
                 __syncthreads();
-                jacobi_sweep_rounds<true>(Gs, ldg, ne, Ws, wld, n_r_grid, wr_e, list, nact, thr, tol, slot0, n_slots, sub, &s_rot);
+                if (ldg <= 64) jacobi_sweep_rounds<true, 64 / (2 * JG)>(Gs, ldg, ne, Ws, wld, n_r_grid, wr_e, list, nact, thr, tol, slot0, n_slots, sub, &s_rot);
+                else jacobi_sweep_rounds<true, 128 / (2 * JG)>(Gs, ldg, ne, Ws, wld, n_r_grid, wr_e, list, nact, thr, tol, slot0, n_slots, sub, &s_rot);
                 for (int i = tid; i < nact * n_r_grid; i += blockDim.x) {
                     const int a = i / n_r_grid, e = i - a * n_r_grid;
                     __stcg(W + (size_t)list[a] * n_r_grid + e, Ws[a * wld + e]);
                 }
             } else {
-                jacobi_sweep_rounds<false>(Gs, ldg, ne, W, n_r_grid, n_r_grid, wr_e, list, nact, thr, tol, slot0, n_slots, sub, &s_rot);
+                jacobi_sweep_global(Gs, ldg, ne, W, n_r_grid, wr_e, list, nact, thr, tol, slot0, n_slots, sub, &s_rot);
             }
             __syncthreads();
             const int rotated = s_rot;
