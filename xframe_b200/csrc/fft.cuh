@@ -81,7 +81,7 @@ __device__ __forceinline__ void warp_fft_row(double2* __restrict__ row, const do
 template <int N>
 __global__ void __launch_bounds__(256) fft_phi_forward_kernel(SlotView grid, int shells_per_run, const double2* __restrict__ sub_flat,
                                                               double2* __restrict__ a, const double2* __restrict__ tw_g, int n_theta,
-                                                              int l_max, int th) {
+                                                              int l_max, int th, int pos_only) {
     extern __shared__ double2 smem_fft[];
     const int rowlen = xfb_fft_rowlen(N);
     double2* tw = smem_fft;
@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(256) fft_phi_forward_kernel(SlotView grid, int
     double2* dst = a + (size_t)s * M2 * n_theta + theta0;
     for (int idx = tid; idx < M2 * th; idx += blockDim.x) {
         const int mm = idx / th, t = idx - mm * th;
+        if (pos_only && mm > l_max) continue;                       // real input: the m<0 half is redundant
         const int mi = (mm <= l_max) ? mm : N - (M2 - mm);
         dst[(size_t)mm * n_theta + t] = buf[t * rowlen + XFB_PHYS(mi)];
     }
@@ -115,7 +116,8 @@ __global__ void __launch_bounds__(256) fft_phi_forward_kernel(SlotView grid, int
 // a [S][M2][n_theta] -> grid [S][n_theta][N]  (unnormalised inverse DFT = synthesis sum over m)
 template <int N>
 __global__ void __launch_bounds__(256) fft_phi_inverse_kernel(const double2* __restrict__ a, double2* __restrict__ grid,
-                                                              const double2* __restrict__ tw_g, int n_theta, int l_max, int th) {
+                                                              const double2* __restrict__ tw_g, int n_theta, int l_max, int th,
+                                                              int herm) {
     extern __shared__ double2 smem_fft[];
     const int rowlen = xfb_fft_rowlen(N);
     double2* tw = smem_fft;
@@ -131,8 +133,8 @@ __global__ void __launch_bounds__(256) fft_phi_inverse_kernel(const double2* __r
         const int m = (i <= N / 2) ? i : i - N;
         double2 val = make_double2(0.0, 0.0);
         if (m >= -l_max && m <= l_max) {
-            const int mm = (m >= 0) ? m : M2 + m;
-            val = ldg2(src + (size_t)mm * n_theta + t);
+            if (herm && m < 0) { val = ldg2(src + (size_t)(-m) * n_theta + t); val.y = -val.y; }   // X[-m] = conj(X[m])
+            else val = ldg2(src + (size_t)((m >= 0) ? m : M2 + m) * n_theta + t);
         }
         buf[t * rowlen + XFB_PHYS(i)] = val;
     }
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(256) fft_phi_inverse_kernel(const double2* __r
 
 template <int N>
 static int launch_fft_n(bool forward, SlotView in, int shells_per_run, const double2* sub, double2* out, const double2* tw, int n_shells, int n_theta,
-                        int l_max, cudaStream_t st) {
+                        int l_max, cudaStream_t st, int half) {
     const int th = (n_theta % 16 == 0) ? 16 : 8;
     const size_t smem = (size_t)(N + th * xfb_fft_rowlen(N)) * sizeof(double2);
     dim3 g(n_shells, n_theta / th);
@@ -162,26 +164,27 @@ static int launch_fft_n(bool forward, SlotView in, int shells_per_run, const dou
         attr_done = true;
     }
     if (forward)
-        fft_phi_forward_kernel<N><<<g, 256, smem, st>>>(in, shells_per_run, sub, out, tw, n_theta, l_max, th);
+        fft_phi_forward_kernel<N><<<g, 256, smem, st>>>(in, shells_per_run, sub, out, tw, n_theta, l_max, th, half);
     else
-        fft_phi_inverse_kernel<N><<<g, 256, smem, st>>>(in.base, out, tw, n_theta, l_max, th);
+        fft_phi_inverse_kernel<N><<<g, 256, smem, st>>>(in.base, out, tw, n_theta, l_max, th, half);
     XFB_CUDA(cudaGetLastError());
     return 0;
 }
 
+// half: forward -> write only m >= 0 (real input); inverse -> synthesise from m >= 0 with conjugate symmetry (real output)
 static int launch_fft(bool forward, int n_phi, SlotView in, int shells_per_run, const double2* sub, double2* out, const double2* tw, int n_shells,
-                      int n_theta, int l_max, cudaStream_t st) {
+                      int n_theta, int l_max, cudaStream_t st, int half = 0) {
     {   // register two-stage FFT where it applies (64 / 128 / 256 points), generic Stockham kernel otherwise
-        const int rc = launch_fft2_any(forward, n_phi, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st);
+        const int rc = launch_fft2_any(forward, n_phi, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st, half);
         if (rc >= 0) return rc;
     }
     switch (n_phi) {
-        case 16: return launch_fft_n<16>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st);
-        case 32: return launch_fft_n<32>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st);
-        case 64: return launch_fft_n<64>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st);
-        case 128: return launch_fft_n<128>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st);
-        case 256: return launch_fft_n<256>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st);
-        case 512: return launch_fft_n<512>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st);
+        case 16: return launch_fft_n<16>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st, half);
+        case 32: return launch_fft_n<32>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st, half);
+        case 64: return launch_fft_n<64>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st, half);
+        case 128: return launch_fft_n<128>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st, half);
+        case 256: return launch_fft_n<256>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st, half);
+        case 512: return launch_fft_n<512>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st, half);
         default: XFB_FAIL("n_phi=%d unsupported (power of two in [16,512])", n_phi);
     }
 }

@@ -63,7 +63,7 @@ struct Fft2Cfg {
 template <int N1, int N2>
 __global__ void __launch_bounds__(256) fft2_forward_kernel(SlotView grid, int shells_per_run, const double2* __restrict__ sub_flat,
                                                            double2* __restrict__ a, const double2* __restrict__ tw_g, int n_theta,
-                                                           int l_max) {
+                                                           int l_max, int pos_only) {
     using C = Fft2Cfg<N1, N2>;
     extern __shared__ double2 smem_f2[];
     const int s = blockIdx.x, theta0 = blockIdx.y * C::TH, tid = threadIdx.x;
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) fft2_forward_kernel(SlotView grid, int sh
         for (int k2 = 0; k2 < N2; ++k2) {
             const int k = u + N1 * k2;
             const int m = (k <= C::N / 2) ? k : k - C::N;
-            if (m >= -l_max && m <= l_max) {
+            if (m >= (pos_only ? 0 : -l_max) && m <= l_max) {     // pos_only: real input, the m<0 half is redundant
                 const int mm = (m >= 0) ? m : M2 + m;
                 dst[(size_t)mm * n_theta] = z[k2];
             }
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) fft2_forward_kernel(SlotView grid, int sh
 // a [S][M2][n_theta] -> grid [S][n_theta][N] (unnormalised inverse DFT)
 template <int N1, int N2>
 __global__ void __launch_bounds__(256) fft2_inverse_kernel(const double2* __restrict__ a, double2* __restrict__ grid,
-                                                           const double2* __restrict__ tw_g, int n_theta, int l_max) {
+                                                           const double2* __restrict__ tw_g, int n_theta, int l_max, int herm) {
     using C = Fft2Cfg<N1, N2>;
     extern __shared__ double2 smem_f2[];
     const int s = blockIdx.x, theta0 = blockIdx.y * C::TH, tid = threadIdx.x;
@@ -131,7 +131,10 @@ __global__ void __launch_bounds__(256) fft2_inverse_kernel(const double2* __rest
             const int k = u + N1 * k2;
             const int m = (k <= C::N / 2) ? k : k - C::N;
             double2 v = make_double2(0.0, 0.0);
-            if (m >= -l_max && m <= l_max) v = ldg2(src + (size_t)((m >= 0) ? m : M2 + m) * n_theta);
+            if (m >= -l_max && m <= l_max) {
+                if (herm && m < 0) { v = ldg2(src + (size_t)(-m) * n_theta); v.y = -v.y; }   // X[-m] = conj(X[m]): real output
+                else v = ldg2(src + (size_t)((m >= 0) ? m : M2 + m) * n_theta);
+            }
             z[k2] = v;
         }
         dft_reg<N2, +1>(z);
@@ -166,7 +169,7 @@ __global__ void __launch_bounds__(256) fft2_inverse_kernel(const double2* __rest
 
 template <int N1, int N2>
 static int launch_fft2(bool forward, SlotView in, int shells_per_run, const double2* sub, double2* out, const double2* tw, int n_shells,
-                       int n_theta, int l_max, cudaStream_t st) {
+                       int n_theta, int l_max, cudaStream_t st, int half) {
     using C = Fft2Cfg<N1, N2>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -176,18 +179,18 @@ static int launch_fft2(bool forward, SlotView in, int shells_per_run, const doub
     }
     dim3 g(n_shells, n_theta / C::TH);
     if (forward)
-        fft2_forward_kernel<N1, N2><<<g, 256, C::SMEM, st>>>(in, shells_per_run, sub, out, tw, n_theta, l_max);
+        fft2_forward_kernel<N1, N2><<<g, 256, C::SMEM, st>>>(in, shells_per_run, sub, out, tw, n_theta, l_max, half);
     else
-        fft2_inverse_kernel<N1, N2><<<g, 256, C::SMEM, st>>>(in.base, out, tw, n_theta, l_max);
+        fft2_inverse_kernel<N1, N2><<<g, 256, C::SMEM, st>>>(in.base, out, tw, n_theta, l_max, half);
     XFB_CUDA(cudaGetLastError());
     return 0;
 }
 
 // returns -1 when (n_phi, n_theta) is not covered by the register FFT (caller falls back to fft.cuh)
 static int launch_fft2_any(bool forward, int n_phi, SlotView in, int shells_per_run, const double2* sub, double2* out, const double2* tw,
-                           int n_shells, int n_theta, int l_max, cudaStream_t st) {
-    if (n_phi == 64 && n_theta % Fft2Cfg<8, 8>::TH == 0) return launch_fft2<8, 8>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st);
-    if (n_phi == 128 && n_theta % Fft2Cfg<8, 16>::TH == 0) return launch_fft2<8, 16>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st);
-    if (n_phi == 256 && n_theta % Fft2Cfg<16, 16>::TH == 0) return launch_fft2<16, 16>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st);
+                           int n_shells, int n_theta, int l_max, cudaStream_t st, int half) {
+    if (n_phi == 64 && n_theta % Fft2Cfg<8, 8>::TH == 0) return launch_fft2<8, 8>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st, half);
+    if (n_phi == 128 && n_theta % Fft2Cfg<8, 16>::TH == 0) return launch_fft2<8, 16>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st, half);
+    if (n_phi == 256 && n_theta % Fft2Cfg<16, 16>::TH == 0) return launch_fft2<16, 16>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st, half);
     return -1;
 }

@@ -35,7 +35,7 @@ __device__ __forceinline__ void leg_mma_cplx(const double* __restrict__ Are, con
     }
 }
 
-__global__ void __launch_bounds__(LEG_THREADS) legendre_forward_kernel(const double2* __restrict__ a, double2* __restrict__ c,
+__global__ void __launch_bounds__(LEG_THREADS, 4) legendre_forward_kernel(const double2* __restrict__ a, double2* __restrict__ c,
                                                                const double* __restrict__ FE, const double* __restrict__ FO,
                                                                int S, int l_max, int n_theta, int NP) {
     extern __shared__ double smem_leg[];
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(LEG_THREADS) legendre_forward_kernel(const dou
     }
 }
 
-__global__ void __launch_bounds__(LEG_THREADS) legendre_inverse_kernel(const double2* __restrict__ c, double2* __restrict__ a,
+__global__ void __launch_bounds__(LEG_THREADS, 4) legendre_inverse_kernel(const double2* __restrict__ c, double2* __restrict__ a,
                                                                const double* __restrict__ IE, const double* __restrict__ IO,
                                                                int S, int l_max, int n_theta, int NP) {
     extern __shared__ double smem_leg[];

@@ -30,7 +30,10 @@ def _stream():
 
 class Plan:
     def __init__(self, l_max, n_r, max_q, n_theta=0, n_phi=0, reciprocity_coefficient=2.0, ft_type='midpoint',
-                 max_batch=1, device=None):
+                 max_batch=1, device=None, hankel_weights=None, hankel_scales=None):
+        """hankel_weights / hankel_scales: optional caller-supplied radial weights [L+1, n_sum, N_r] (float64) and
+        (forward, inverse) prefactors, as the reference's generate_ht receives them (hankel_transforms.py:540-559);
+        by default they are computed for (ft_type, reciprocity_coefficient) like generate_weightDict + assemble_weights."""
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.XfbError("no CUDA device visible: xframe_b200 has no CPU fallback")
@@ -47,12 +50,21 @@ class Plan:
         self.thetas = np.arccos(self.cos_theta)                         # shtns_plugin.py:133
         self.phis = 2 * np.pi * np.arange(self.n_phi) / self.n_phi      # shtns_plugin.py:132
         leg, self.NP = tables.pack_legendre(self.l_max, self.n_theta, self.n_phi)
-        self.hankel_w = tables.hankel_weights(self.l_max, self.n_r, self.rc, ft_type)
-        fs, iscale = tables.hankel_scales(float(np.max(self.rs)), self.n_r, self.rc)
+        if hankel_weights is None:
+            self.hankel_w = tables.hankel_weights(self.l_max, self.n_r, self.rc, ft_type)
+        else:
+            self.hankel_w = np.ascontiguousarray(hankel_weights, dtype=np.float64)
+            if self.hankel_w.ndim != 3 or self.hankel_w.shape[0] != self.l_max + 1 or self.hankel_w.shape[2] != self.n_r \
+                    or self.hankel_w.shape[1] not in (self.n_r, self.n_r - 1):
+                raise ValueError(f"hankel_weights shape {self.hankel_w.shape} is not [L+1, N_r or N_r-1, N_r]")
+        if hankel_scales is None:
+            fs, iscale = tables.hankel_scales(float(np.max(self.rs)), self.n_r, self.rc)
+        else:
+            fs, iscale = (float(v) for v in hankel_scales)
         self.int_weight = tables.integration_weights(self.rs, self.n_theta)
         d = _lib.PlanDesc()
         d.l_max, d.n_r, d.n_theta, d.n_phi, d.max_batch = self.l_max, self.n_r, self.n_theta, self.n_phi, self.max_batch
-        d.hankel_skip = 1 if ft_type in ('trapz', 'Zernike') else 0
+        d.hankel_skip = self.n_r - self.hankel_w.shape[1]      # trapz / Zernike weights drop the p = 0 row (hankel_transforms.py:326-333)
         keep = [np.ascontiguousarray(a, dtype=np.float64) for a in
                 (self.cos_theta, self.gauss_w, leg, self.hankel_w, self.int_weight, self.rs, self.qs)]
         d.cos_theta, d.gauss_w, d.legendre = _dp(keep[0]), _dp(keep[1]), _dp(keep[2])
