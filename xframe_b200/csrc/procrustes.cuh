@@ -375,3 +375,49 @@ __global__ void procrustes_unpack_kernel(const double2* __restrict__ c_in, doubl
         c_out[pos] = v;
     }
 }
+
+// ---- fxs_unknowns on request (xfb_get_unknowns) ------------------------------------------------------------------
+// gn [n_cols][n_c] = U~^T (zero rows for dropped directions), vw [n_cols][n_r] = J^T (accumulator started from the
+// identity).  polar(M) = J U~^T (real basis) -> complex columns m = -l..l.  One block per row i of the unknown.
+__global__ void unknown_assemble_kernel(const double* __restrict__ gn, const double* __restrict__ vw, int n_r, int n_cols, int n_c,
+                                        int l, double2* __restrict__ out) {
+    __shared__ double row[512];
+    const int i = blockIdx.x;
+    for (int e = threadIdx.x; e < n_c; e += blockDim.x) {
+        double s = 0.0;
+        for (int c = 0; c < n_cols; ++c) s += vw[(size_t)c * n_r + i] * gn[(size_t)c * n_c + e];
+        row[e] = s;
+    }
+    __syncthreads();
+    const double is2 = 0.7071067811865476;
+    for (int m = threadIdx.x; m <= l; m += blockDim.x) {
+        if (m == 0) { out[(size_t)i * n_c + l] = make_double2(row[0], 0.0); continue; }
+        const double re = row[2 * m - 1] * is2, im = row[2 * m] * is2;
+        out[(size_t)i * n_c + l + m] = make_double2(re, im);
+        out[(size_t)i * n_c + l - m] = (m & 1) ? make_double2(-re, im) : make_double2(re, -im);
+    }
+}
+
+// l = 0: PD_0 I_0 is the scalar sum_k V_0(q_k) q_k^2 I_00(q_k); U V^H = its phase (1 for a zero scalar)
+__global__ void unknown_zeroth_kernel(const double2* __restrict__ i00, const double* __restrict__ v0, const double* __restrict__ q, int n_r,
+                                      double2* __restrict__ out) {
+    __shared__ double sx[128], sy[128];
+    double ax = 0.0, ay = 0.0;
+    for (int k = threadIdx.x; k < n_r; k += blockDim.x) {
+        const double w = v0[k] * q[k] * q[k];
+        ax += w * i00[k].x; ay += w * i00[k].y;
+    }
+    sx[threadIdx.x] = ax; sy[threadIdx.x] = ay;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double x = 0.0, y = 0.0;
+        for (int t = 0; t < blockDim.x; ++t) { x += sx[t]; y += sy[t]; }
+        const double a = hypot(x, y);
+        out[0] = (a > 0.0) ? make_double2(x / a, y / a) : make_double2(1.0, 0.0);
+    }
+}
+
+__global__ void unknown_identity_kernel(double2* __restrict__ out, int n_l, int n_c) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n_l * n_c) out[idx] = make_double2((idx / n_c) == (idx % n_c) ? 1.0 : 0.0, 0.0);
+}

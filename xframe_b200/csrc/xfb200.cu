@@ -42,6 +42,9 @@ struct xfb_plan {
     double* v0_dev = nullptr;
     double inv_sqrt_np = 1.0, sv_cutoff = 1e-15; int max_sweeps = 40;
     double *pd_dev = nullptr, *vt_dev = nullptr;
+    // fxs_unknowns on request (xfb_get_unknowns): identity accumulator table, single-run scratch, I_00 of the last projection
+    double *ident_dev = nullptr, *gn_u = nullptr, *vw_u = nullptr, *sigma_u = nullptr; double2* i00 = nullptr;
+    long long proj_calls = 0, unk_stamp = -1; int unk_run = -1, last_proj_nb = 0;
     long long xt_run = 0, g_run = 0, vw_run = 0;
     double *xt = nullptr, *tt = nullptr, *g = nullptr, *gn = nullptr, *vw = nullptr, *sigma = nullptr;
     int* sweeps_dev = nullptr;
@@ -160,7 +163,7 @@ int xfb_plan_destroy(xfb_plan* p) {
     if (!p) return 0;
     void* ptrs[] = {p->tw, p->FE, p->FO, p->IE, p->IO, p->hankel_w, p->int_wt, p->q_pts, p->A0, p->C0, p->C1, p->W0, p->W1, p->W2, p->A0s, p->C0s, p->rt0, p->stage_out,
                     p->hk_tiles, p->orders_dev, p->kind_dev, p->act_index_dev, p->radial_mask_dev, p->v0_dev, p->pd_dev, p->vt_dev,
-                    p->xt, p->tt, p->g, p->gn, p->vw, p->sigma, p->sweeps_dev, p->gemmM_dev, p->gemmT_dev, p->gemmM_tp, p->gemmT_tp,
+                    p->xt, p->tt, p->g, p->gn, p->vw, p->sigma, p->sweeps_dev, p->ident_dev, p->gn_u, p->vw_u, p->sigma_u, p->i00, p->gemmM_dev, p->gemmT_dev, p->gemmM_tp, p->gemmT_tp,
                     p->init_support_dev, p->rho_pool, p->rh_pool, p->mask_pool, p->ls_ints, p->ls_dbl, p->partial, p->err, p->mm};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& e : p->prof_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -299,6 +302,9 @@ static int project_i(xfb_plan* p, const double2* c_in, double2* c_out, int nb, c
     if (!p->has_proj) XFB_FAIL("projection constants not set (xfb_plan_set_projection)");
     const int S = nb * p->n_r;
     const int na = (int)p->orders.size();
+    // row (l=0,m=0) of the coefficient array = I_00(q) of every run: kept for xfb_get_unknowns
+    XFB_CUDA(cudaMemcpyAsync(p->i00, c_in, (size_t)S * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+    p->proj_calls++; p->last_proj_nb = nb;
     if (na > 0) {
         if (build_gemm_groups(p, nb, st)) return 1;
         XFB_LAUNCH(p, PG_PROC_PACK, st,
@@ -453,6 +459,15 @@ int xfb_plan_set_projection(xfb_plan* p, const xfb_projection_desc* d) {
         if (dev_alloc(p, &p->vw, B * p->vw_run)) return 1;
         if (dev_alloc(p, &p->sigma, B * na * n_r)) return 1;
         if (dev_alloc(p, &p->sweeps_dev, B * na)) return 1;
+        {
+            std::vector<double> ident(vt.size(), 0.0);
+            for (const ProcOrder& o : p->orders)
+                for (int c = 0; c < o.n_cols; ++c) ident[(size_t)o.pd_off + (size_t)c * n_r + c] = 1.0;
+            if (dev_upload(p, &p->ident_dev, ident.data(), ident.size())) return 1;
+        }
+        if (dev_alloc(p, &p->gn_u, (size_t)p->g_run)) return 1;
+        if (dev_alloc(p, &p->vw_u, (size_t)p->vw_run)) return 1;
+        if (dev_alloc(p, &p->sigma_u, na * n_r)) return 1;
         if (dev_alloc(p, &p->gemmM_dev, B * na)) return 1;
         if (dev_alloc(p, &p->gemmT_dev, B * na)) return 1;
         size_t tiles_m = 0, tiles_t = 0;
@@ -469,6 +484,7 @@ int xfb_plan_set_projection(xfb_plan* p, const xfb_projection_desc* d) {
         if (dev_upload(p, &p->orders_dev, &o, 1)) return 1;
         if (dev_alloc(p, &p->tt, 1)) return 1;
     }
+    if (dev_alloc(p, &p->i00, B * n_r)) return 1;
     p->inv_sqrt_np = 1.0 / d->sqrt_n_particles;
     p->sv_cutoff = d->sv_cutoff > 0 ? d->sv_cutoff : 1e-15;
     p->max_sweeps = d->max_sweeps > 0 ? d->max_sweeps : 40;
@@ -522,7 +538,44 @@ int xfb_project_invariants(xfb_plan* p, const double* in, double* out, int32_t n
     if (project_i(p, p->C0, p->C1, nb, st)) return 1;
     return transpose_i(p, p->C1, (double2*)out, p->NLM, S, st);
 }
-int xfb_get_unknowns(xfb_plan*, int32_t, int32_t, double*, void*) { XFB_FAIL("xfb_get_unknowns: not implemented in this round"); }
+// fxs_unknowns of the LAST invariant projection (approximate_unknowns, fxs_Projections.py:752-767):
+// unk_l = U V^H of svd(PD_l I_l), complex [n_l][2l+1].  Recomputed on request from the retained M^T (p->g): the Jacobi
+// kernel is run once more for that run with the accumulator started from the identity, so that it yields J itself.
+int xfb_get_unknowns(xfb_plan* p, int32_t run, int32_t order, double* out_dev, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!p->has_proj) XFB_FAIL("projection constants not set");
+    if (p->proj_calls == 0) XFB_FAIL("xfb_get_unknowns: no invariant projection has run yet");
+    if (run < 0 || run >= p->last_proj_nb) XFB_FAIL("run=%d outside the last projected batch (%d)", run, p->last_proj_nb);
+    if (order < 0 || order > p->L) XFB_FAIL("order=%d outside 0..%d", order, p->L);
+    std::vector<int> kind(p->L + 1), act(p->L + 1);
+    XFB_CUDA(cudaMemcpy(kind.data(), p->kind_dev, kind.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    XFB_CUDA(cudaMemcpy(act.data(), p->act_index_dev, act.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    const int kd = kind[order], n_c = 2 * order + 1;
+    if (kd == ORD_PASS) XFB_FAIL("order %d is not a used order", order);
+    if (kd == ORD_ZEROTH) {
+        unknown_zeroth_kernel<<<1, 128, 0, st>>>(p->i00 + (size_t)run * p->n_r, p->v0_dev, p->q_pts, p->n_r, (double2*)out_dev);
+        XFB_CUDA(cudaGetLastError());
+        return 0;
+    }
+    if (kd == ORD_ZERO) {   // PD_l = 0: numpy's svd of a zero matrix returns identity factors
+        const int n_l = std::min(p->n_r, n_c);
+        unknown_identity_kernel<<<cdiv(n_l * n_c, 256), 256, 0, st>>>((double2*)out_dev, n_l, n_c);
+        XFB_CUDA(cudaGetLastError());
+        return 0;
+    }
+    const int na = (int)p->orders.size();
+    if (p->unk_run != run || p->unk_stamp != p->proj_calls) {
+        procrustes_jacobi_kernel<<<std::min(na, p->n_sm), 512, p->jacobi_smem, st>>>(p->g + (size_t)run * p->g_run, p->gn_u, p->vw_u, p->ident_dev, p->sigma_u,
+                                                                                    p->orders_dev, na, 1, p->n_r, p->g_run, p->vw_run, (long long)na * p->n_r,
+                                                                                    p->sv_cutoff, 1e-15, p->max_sweeps, nullptr, (int)(p->jacobi_smem / 8));
+        XFB_CUDA(cudaGetLastError());
+        p->unk_run = run; p->unk_stamp = p->proj_calls;
+    }
+    const ProcOrder o = p->orders[act[order]];
+    unknown_assemble_kernel<<<o.n_cols, 128, 0, st>>>(p->gn_u + o.g_off, p->vw_u + o.vw_off, p->n_r, o.n_cols, o.n_c, o.l, (double2*)out_dev);
+    XFB_CUDA(cudaGetLastError());
+    return 0;
+}
 
 int xfb_modify_intensity(xfb_plan* p, const double* rho_hat, const double* i_proj, double* out, int32_t nb, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;

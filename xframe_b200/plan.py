@@ -190,6 +190,17 @@ class Plan:
         d.sqrt_n_particles = float(np.sqrt(number_of_particles))
         d.sv_cutoff, d.max_sweeps = float(sv_cutoff), int(max_sweeps)
         _lib.check(self.lib.xfb_plan_set_projection(self.h, C.byref(d)))
+        self._proj_ncols = [int(c) for c in ncols]
+
+    def unknowns(self, run):
+        """fxs_unknowns of the last invariant projection for one run of the batch: tuple over the used orders of
+        complex [n_l, 2l+1] arrays (approximate_unknowns, fxs_Projections.py:752-767)."""
+        out = []
+        for l, nc in enumerate(self._proj_ncols):
+            t = torch.empty((nc, 2 * l + 1), dtype=torch.complex128, device=self.device)
+            _lib.check(self.lib.xfb_get_unknowns(self.h, int(run), l, _ptr(t), _stream()))
+            out.append(t)
+        return tuple(t.cpu().numpy() for t in out)
 
     def set_real(self, apply, initial_support, value_threshold=(0, False), limit_imag=2.0, considered=('all',),
                  error_inside_initial_support=True):

@@ -88,6 +88,7 @@ class ProjectWorker:
             last = torch.from_numpy(res['last_real']).to(plan.device)
             fd = plan.ft(last)
             I = plan.sht_forward((fd * fd.conj()).contiguous()).cpu().numpy()
+            unknowns = [plan.unknowns(k) for k in range(len(ids))]      # of the last mtip_start (reconstruct.py:523,1013)
             for k, rid in enumerate(ids):
                 Il = [I[k][:, l * l:(l + 1) * (l + 1)] for l in range(plan.l_max + 1)]
                 n_it = res['errors'].shape[1]
@@ -99,7 +100,7 @@ class ProjectWorker:
                     'initial_support': self.initial_support.copy(),
                     'error_dict': {'main': res['errors'][k].copy(), 'real': {'l2_projection_diff': res['errors'][k].copy()}, 'reciprocal': {}},
                     'support_mask': res['best_support'][k], 'last_support_mask': res['last_support'][k],
-                    'loop_iterations': res['loop_iterations'], 'fxs_unknowns': None,
+                    'loop_iterations': res['loop_iterations'], 'fxs_unknowns': unknowns[k],
                     'n_particles': np.array([[self.proj.number_of_particles]] * n_it), 'n_particles_gradients': np.array([]),
                     'n_particles_fraction': np.array([]),
                     'grid_pair': {'real_grid': rs, 'reciprocal_grid': qs}, 'projection_matrices': masked_pm,
