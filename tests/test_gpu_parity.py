@@ -338,3 +338,33 @@ def test_full_tutorial_reconstruction_statistics():
         assert ref_last / 3 < e[-1] < ref_last * 3
         assert 0.03 < r['last_support_mask'].mean() < 0.25
     w.plan.close()
+
+
+@pytest.mark.parametrize('l_max,n_r', [(15, 24), (70, 40), (20, 160), (66, 136)])
+def test_projection_random_matrices_all_kernel_variants(l_max, n_r):
+    """Invariant projection on random, well-conditioned V_l against the reference formula I'_l = V_l U V^H,
+    U S V^H = svd(V_l^H D^2 I_l) (fxs_Projections.py:761-767,835-841).  The sizes select the Jacobi kernel variants:
+    column length <= 128 / N_r <= 128 (512 threads), column length > 128, N_r > 128, both (256 threads, G in global)."""
+    from xframe_b200.plan import Plan
+    rng = np.random.default_rng(l_max * 1000 + n_r)
+    plan = Plan(l_max, n_r, 0.3, max_batch=2)
+    V = [rng.standard_normal((n_r, min(n_r, 2 * l + 1))) * (1.0 if l % 2 == 0 else 0.0) for l in range(l_max + 1)]
+    plan.set_projection(V, True, 1.0)
+    f = torch.from_numpy(rng.standard_normal((2, n_r, plan.n_theta, plan.n_phi)) + 0j).cuda()
+    I = N(plan.sht_forward(f))                                               # Hermitian-symmetric coefficients of real fields
+    got = N(plan.project_invariants(T(I)))
+    D2 = plan.qs ** 2
+    for b in range(2):
+        for l in range(0, l_max + 1):
+            Il = I[b][:, l * l:(l + 1) ** 2]
+            if l == 0:
+                want = V[0].astype(complex)
+            elif l % 2 == 1:
+                want = np.zeros_like(Il)
+            else:
+                u, _, vh = np.linalg.svd((V[l].T * D2[None, :]) @ Il, full_matrices=False)
+                want = V[l] @ (u @ vh)
+            assert rel_l2(got[b][:, l * l:(l + 1) ** 2], want) < 1e-10, (b, l)
+    orders, sweeps = plan.jacobi_sweeps()
+    assert sweeps.max() < 40
+    plan.close()

@@ -23,8 +23,8 @@ struct ProcOrder {
     int n_c;      // 2l+1
     long long pd_off;   // into pd / vt constant arrays (n_cols * N_r doubles)
     long long xt_off;   // per-run offset of Xt / Tt block (n_c * N_r)
-    long long g_off;    // per-run offset of G / Gn block (n_cols * n_c)
-    long long vw_off;   // per-run offset of VW block (n_cols * N_r)
+    long long g_off;    // per-run offset of G / Gn block (n_cols * jacobi_stride(n_c), zero padded columns)
+    long long vw_off;   // per-run offset of VW block (n_cols * jacobi_wstride(N_r), zero padded columns)
 };
 
 enum { ORD_PASS = 0, ORD_ZERO = 1, ORD_ZEROTH = 2, ORD_ACTIVE = 3 };
@@ -48,223 +48,306 @@ __global__ void procrustes_pack_kernel(const double2* __restrict__ c, double* __
     }
 }
 
-// One-sided Jacobi, persistent CTAs over the (order, run) problems (largest orders first).
-//   G : [n_cols][n_c] in global (column i of G = M^T contiguous), copied to shared memory with the column
-//       length padded to a multiple of 8 (zeros).
-//   vw: [n_cols][N_r] accumulator initialised from vt (V_l^T).  At the start of every sweep the ACTIVE columns are
-//       staged into shared memory (they fit once dead columns are dropped: cap columns) and written back at the
-//       end of the sweep; only if more than `cap` columns are active are they rotated in global memory (L2).
-//   A pair of columns is handled by JG = 8 lanes (4 pairs per warp, 64 pairs per 512-thread CTA = one whole
-//   round-robin round in flight); dot products are reduced with 3 xor-shuffles inside the 8-lane group; the G
-//   elements stay in registers between the dot and the rotation (one smem read + one write per element).
-//   Outputs: gn = G~ / sigma (zero for dropped columns), sigma [n_cols].
-#ifndef JG
-#define JG 8                 // lanes per column pair (8, 16 or 32)
-#endif
-#define JGPW (32 / JG)       // pair groups per warp
-#define JPASS (64 / (16 * JGPW))   // passes per round: 64 pair slots / (16 warps x groups per warp)
-__host__ __device__ inline int jacobi_stride(int len) {
-    return len <= 64 ? 64 : 128;    // columns are zero padded to 64 / 128 elements (NV2 = 4 / 8 double2 steps per lane)
-}
-#define JMAXE (128 / JG)     // max elements per lane (column length <= 128)
+// One-sided Jacobi SVD, persistent CTAs over the (order, run) problems (largest orders first).
+//
+// Storage (all padded with zeros so every access is a 128-bit one):
+//   G : n columns (column i of G = M^T = row i of M) of length len <= ldg, ldg = 64 / 128 / 256.  Input g [n][ldg]
+//       (written by the grouped GEMM, pads zeroed once at allocation), working copy in shared memory when it fits,
+//       otherwise in the output buffer gn [n][ldg] (global memory, L2 resident).
+//   W : accumulator, n columns of length wld = 128 / 256 (>= N_r), vw [n][wld] in global memory, initialised from
+//       vt (V_l^T, or the identity for xfb_get_unknowns).  At the start of every sweep the ACTIVE columns are staged
+//       into shared memory when they fit (dead columns are dropped as the sweeps proceed) and written back afterwards.
+//
+// Register-blocked sweep: the active columns are grouped in blocks of 4; blocks are paired by the round-robin (circle)
+// method and one WARP owns a block pair (A, B) for a whole block round.  The 8 columns are loaded ONCE, the 16 cross
+// pairs (A_g, B_(g+s)%4), s = 0..3, are rotated in registers (8 lanes per pair, 4 pairs in flight per warp, the B
+// columns travel between the lane groups by shuffles) and the columns are stored ONCE: shared-memory traffic per
+// rotation is 1/4 of the pair-at-a-time scheme and there is one __syncthreads per block round (n/4 per sweep) instead
+// of one per pair round.  In block round 0 the 6 + 6 pairs inside A and inside B are rotated too, so every pair is
+// visited exactly once per sweep.  The rotation parameters are kept per warp and replayed on the accumulator columns
+// (second pass: W needs no dot products).
+#define JG 8                 // lanes per column pair
+#define JROT_STEPS 10        // 3 (inside A) + 3 (inside B) + 4 (cross)
+__host__ __device__ inline int jacobi_stride(int len) { return len <= 64 ? 64 : (len <= 128 ? 128 : 256); }
+__host__ __device__ inline int jacobi_wstride(int n_r) { return n_r <= 128 ? 128 : 256; }
 
-// All rounds of one sweep.  WSM: accumulator columns staged in shared memory (the normal case) -- 128-bit shared
-// memory accesses, each lane owns the element pairs (2 sub, 2 sub + 1) + 16 t, NV2 = number of such double2 steps of
-// a G column (4 for columns up to 64 long, 8 up to 128).  !WSM: rare fallback, accumulator rotated in global memory.
-template <bool WSM, int NV2>
-__device__ __forceinline__ void jacobi_sweep_rounds(double* __restrict__ Gs, int ldg, int ne, double* __restrict__ Wb, int wstride,
-                                                    int n_r_grid, int wr_e, const int* __restrict__ list, int nact, double thr,
-                                                    double tol, int slot0, int n_slots, int sub, int* s_rot) {
-    const int npad = nact + (nact & 1);
-    const int half = npad >> 1;
-    const int mod = npad - 1;
-    // round-robin (circle method): position 0 is fixed, the element at position k>=1 in round r is
-    // 1 + ((k-1-r) mod (npad-1)); tracked incrementally (one decrement with wrap per round, no integer division).
-    int pa_[JPASS], pb_[JPASS];
+__device__ __forceinline__ double2 shfl_d2(double2 v, int src_lane) {
+    v.x = __shfl_sync(0xffffffffu, v.x, src_lane);
+    v.y = __shfl_sync(0xffffffffu, v.y, src_lane);
+    return v;
+}
+
+// rotation of the column pair (x, y) held by one 8-lane group: returns (cs, sn) with x' = cs x - sn y, y' = sn x + cs y;
+// (1, 0) when the pair is skipped.  Symmetric under exchanging the roles of x and y (sn changes sign), so two lane
+// groups that hold the same pair with swapped roles take bitwise-consistent decisions.
+template <int NV>
+__device__ __forceinline__ double2 jacobi_pair_params(const double2 (&x)[NV], const double2 (&y)[NV], bool valid, double thr, double tol) {
+    double app = 0.0, aqq = 0.0, apq = 0.0, app2 = 0.0, aqq2 = 0.0, apq2 = 0.0;
 #pragma unroll
-    for (int ps = 0; ps < JPASS; ++ps) {
-        const int i = slot0 + ps * n_slots;
-        const int ka = i, kb = npad - 1 - i;
-        pa_[ps] = (ka == 0) ? 0 : 1 + (ka - 1) % mod;
-        pb_[ps] = (i < half) ? 1 + (kb - 1) % mod : 1;
+    for (int t = 0; t < NV; ++t) {
+        app += x[t].x * x[t].x; aqq += y[t].x * y[t].x; apq += x[t].x * y[t].x;
+        app2 += x[t].y * x[t].y; aqq2 += y[t].y * y[t].y; apq2 += x[t].y * y[t].y;
     }
-    constexpr int WV2 = 128 / (2 * JG);                  // double2 steps of an accumulator column (N_r <= 128, zero padded)
-    for (int r = 0; r < npad - 1; ++r) {
+    app += app2; aqq += aqq2; apq += apq2;
 #pragma unroll
-        for (int ps = 0; ps < JPASS; ++ps) {
-            const int i = slot0 + ps * n_slots;
-            const int warp_first = (slot0 / JGPW) * JGPW + ps * n_slots;     // first pair slot of this warp in this pass
-            if (warp_first >= half) continue;                                // warp-uniform: nothing to do
-            const bool has_slot = i < half;
-            int pa = pa_[ps], pb = pb_[ps];
-            bool valid = has_slot && (pa < nact) && (pb < nact);      // bye against the padding element
-            int p = 0, q = 0, wpi = 0, wqi = 0;
-            if (valid) {
-                int sa = pa, sb = pb;
-                p = list[pa]; q = list[pb];
-                if (p > q) { int t_ = p; p = q; q = t_; sa = pb; sb = pa; }
-                wpi = WSM ? sa : p;                                // smem: compact slot ; global: column index
-                wqi = WSM ? sb : q;
+    for (int off = JG / 2; off > 0; off >>= 1) {
+        app += __shfl_xor_sync(0xffffffffu, app, off);
+        aqq += __shfl_xor_sync(0xffffffffu, aqq, off);
+        apq += __shfl_xor_sync(0xffffffffu, apq, off);
+    }
+    bool rot = valid && (app > thr) && (aqq > thr);
+    if (rot) rot = apq * apq > (tol * tol) * (app * aqq);
+    if (!rot) return make_double2(1.0, 0.0);
+    // tan(2 theta) = 2 apq / (aqq - app), |theta| <= pi/4 (same rotation as the textbook zeta/t form)
+    const double d = aqq - app, s2 = 2.0 * apq;
+    const double rh = rsqrt(d * d + s2 * s2);
+    const double u = 0.5 + 0.5 * fabs(d) * rh;            // cos^2(theta)
+    const double rc = rsqrt(u);
+    return make_double2(u * rc, copysign(0.5 * s2 * rh, d * s2) * rc);   // cos, sin(2 theta) / (2 cos theta)
+}
+
+template <int NV>
+__device__ __forceinline__ void jacobi_load_col(double2 (&v)[NV], const double* base, long long col_off, int sub, bool valid) {
+    const double2* p = reinterpret_cast<const double2*>(base + col_off) + sub;
+#pragma unroll
+    for (int t = 0; t < NV; ++t) v[t] = valid ? p[JG * t] : make_double2(0.0, 0.0);
+}
+template <int NV>
+__device__ __forceinline__ void jacobi_store_col(const double2 (&v)[NV], double* base, long long col_off, int sub, bool valid) {
+    if (!valid) return;
+    double2* p = reinterpret_cast<double2*>(base + col_off) + sub;
+#pragma unroll
+    for (int t = 0; t < NV; ++t) p[JG * t] = v[t];
+}
+
+// One sweep over all pairs of the `nact` active columns list[0..nact).
+//   Gs / ldg : G columns (column id c at Gs + c*ldg);  Wb / wld: accumulator columns, indexed by the POSITION in the
+//   active list when w_compact (shared-memory staging) or by the column id otherwise.
+template <int NV2, int WV2>
+__device__ __forceinline__ void jacobi_sweep_blocked(double* Gs, int ldg, double* Wb, int wld, bool w_compact, const int* __restrict__ list,
+                                                     int nact, double thr, double tol, double2* rotbuf, int* s_rot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int grp = lane >> 3, sub = lane & (JG - 1);
+    const int nblk = (nact + 3) >> 2;
+    const int nblkp = max(2, nblk + (nblk & 1));
+    const int half = nblkp >> 1, mod = nblkp - 1;
+    double2* rb = rotbuf + warp * (JROT_STEPS * 4);
+    for (int r = 0; r < mod; ++r) {
+        for (int i = warp; i < half; i += nwarp) {                       // warp-uniform
+            // circle method on the blocks: position 0 is fixed, position k >= 1 holds block 1 + ((k-1-r) mod (nblkp-1))
+            const int kb = nblkp - 1 - i;
+            int ba = 0;
+            if (i != 0) { int t_ = (i - 1 - r) % mod; if (t_ < 0) t_ += mod; ba = 1 + t_; }
+            int tb = (kb - 1 - r) % mod; if (tb < 0) tb += mod;
+            const int bb = 1 + tb;
+            const int pa = ba * 4 + grp;                                   // position of A_g in the active list
+            const bool va = pa < nact;
+            const int ca = va ? list[pa] : 0;
+            int cbs[4]; bool vbs[4];                                       // B column of this group at step s
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int pb = bb * 4 + ((grp + s) & 3);
+                vbs[s] = pb < nact;
+                cbs[s] = vbs[s] ? list[pb] : 0;
             }
-            if (i != 0) pa_[ps] = (pa == 1) ? mod : pa - 1;         // positions for the next round
-            pb_[ps] = (pb == 1) ? mod : pb - 1;
-            if constexpr (WSM) {
-                double2* gp = reinterpret_cast<double2*>(Gs + (size_t)p * ldg) + sub;
-                double2* gq = reinterpret_cast<double2*>(Gs + (size_t)q * ldg) + sub;
-                double2 xg[NV2], yg[NV2];
-                double app = 0.0, aqq = 0.0, apq = 0.0;
-                if (valid) {
+            bool any_rot = false;
+            {   // ---------------- pass 1: G columns, dot products, rotation parameters
+                double2 x[NV2], y[NV2];
+                jacobi_load_col<NV2>(x, Gs, (long long)ca * ldg, sub, va);
+                jacobi_load_col<NV2>(y, Gs, (long long)cbs[0] * ldg, sub, vbs[0]);
+                if (r == 0) {
 #pragma unroll
-                    for (int t = 0; t < NV2; ++t) {
-                        xg[t] = gp[JG * t]; yg[t] = gq[JG * t];
-                        app += xg[t].x * xg[t].x; aqq += yg[t].x * yg[t].x; apq += xg[t].x * yg[t].x;
-                        app += xg[t].y * xg[t].y; aqq += yg[t].y * yg[t].y; apq += xg[t].y * yg[t].y;
-                    }
-                }
+                    for (int t = 0; t < 3; ++t) {                         // pairs inside A: partner group = grp ^ (t+1)
+                        const int pg = grp ^ (t + 1);
+                        const bool vp = (ba * 4 + pg) < nact;
+                        double2 z[NV2];
 #pragma unroll
-                for (int off = JG / 2; off > 0; off >>= 1) {
-                    app += __shfl_xor_sync(0xffffffffu, app, off);
-                    aqq += __shfl_xor_sync(0xffffffffu, aqq, off);
-                    apq += __shfl_xor_sync(0xffffffffu, apq, off);
-                }
-                bool rot = valid && (app > thr) && (aqq > thr);
-                if (rot) rot = apq * apq > (tol * tol) * (app * aqq);
-                if (rot) {
-                    // tan(2 theta) = 2 apq / (aqq - app), |theta| <= pi/4 (same rotation as the textbook zeta/t form)
-                    const double d = aqq - app, s2 = 2.0 * apq;
-                    const double rh = rsqrt(d * d + s2 * s2);
-                    const double u = 0.5 + 0.5 * fabs(d) * rh;            // cos^2(theta)
-                    const double rc = rsqrt(u);
-                    const double cs = u * rc;
-                    const double sn = copysign(0.5 * s2 * rh, d * s2) * rc;   // sin(2 theta) / (2 cos theta)
+                        for (int k = 0; k < NV2; ++k) z[k] = shfl_d2(x[k], lane ^ (8 * (t + 1)));
+                        const double2 cs = jacobi_pair_params<NV2>(x, z, va && vp, thr, tol);
+                        if (cs.y != 0.0) {
+                            any_rot = true;
 #pragma unroll
-                    for (int t = 0; t < NV2; ++t) {
-                        gp[JG * t] = make_double2(cs * xg[t].x - sn * yg[t].x, cs * xg[t].y - sn * yg[t].y);
-                        gq[JG * t] = make_double2(sn * xg[t].x + cs * yg[t].x, sn * xg[t].y + cs * yg[t].y);
-                    }
-                    double2* wp = reinterpret_cast<double2*>(Wb + (size_t)wpi * wstride) + sub;
-                    double2* wq = reinterpret_cast<double2*>(Wb + (size_t)wqi * wstride) + sub;
-#pragma unroll
-                    for (int t = 0; t < WV2; ++t) {
-                        const double2 x = wp[JG * t], y = wq[JG * t];
-                        wp[JG * t] = make_double2(cs * x.x - sn * y.x, cs * x.y - sn * y.y);
-                        wq[JG * t] = make_double2(sn * x.x + cs * y.x, sn * x.y + cs * y.y);
-                    }
-                    if (sub == 0) *s_rot = 1;
-                }
-            } else {
-                double* gp = Gs + (size_t)p * ldg + sub;
-                double* gq = Gs + (size_t)q * ldg + sub;
-                double* wp = Wb + (size_t)wpi * wstride + sub;
-                double* wq = Wb + (size_t)wqi * wstride + sub;
-                double xw[JMAXE], yw[JMAXE];
-                if (valid) {                                        // global accumulator: prefetch before the dot products
-#pragma unroll
-                    for (int t = 0; t < JMAXE; ++t)
-                        if (t < wr_e && sub + JG * t < n_r_grid) { xw[t] = __ldcg(wp + JG * t); yw[t] = __ldcg(wq + JG * t); }
-                }
-                double app = 0.0, aqq = 0.0, apq = 0.0;
-                if (valid) {
-#pragma unroll 4
-                    for (int t = 0; t < ne; ++t) {
-                        const double x = gp[JG * t], y = gq[JG * t];
-                        app += x * x; aqq += y * y; apq += x * y;
-                    }
-                }
-#pragma unroll
-                for (int off = JG / 2; off > 0; off >>= 1) {
-                    app += __shfl_xor_sync(0xffffffffu, app, off);
-                    aqq += __shfl_xor_sync(0xffffffffu, aqq, off);
-                    apq += __shfl_xor_sync(0xffffffffu, apq, off);
-                }
-                bool rot = valid && (app > thr) && (aqq > thr);
-                if (rot) rot = apq * apq > (tol * tol) * (app * aqq);
-                if (rot) {
-                    const double d = aqq - app, s2 = 2.0 * apq;
-                    const double rh = rsqrt(d * d + s2 * s2);
-                    const double u = 0.5 + 0.5 * fabs(d) * rh;
-                    const double rc = rsqrt(u);
-                    const double cs = u * rc;
-                    const double sn = copysign(0.5 * s2 * rh, d * s2) * rc;
-#pragma unroll 4
-                    for (int tt = 0; tt < ne; ++tt) {
-                        const double x = gp[JG * tt], y = gq[JG * tt];
-                        gp[JG * tt] = cs * x - sn * y;
-                        gq[JG * tt] = sn * x + cs * y;
-                    }
-#pragma unroll
-                    for (int tt = 0; tt < JMAXE; ++tt)
-                        if (tt < wr_e && sub + JG * tt < n_r_grid) {
-                            __stcg(wp + JG * tt, cs * xw[tt] - sn * yw[tt]);
-                            __stcg(wq + JG * tt, sn * xw[tt] + cs * yw[tt]);
+                            for (int k = 0; k < NV2; ++k) x[k] = make_double2(cs.x * x[k].x - cs.y * z[k].x, cs.x * x[k].y - cs.y * z[k].y);
                         }
-                    if (sub == 0) *s_rot = 1;
+                        if (sub == 0) rb[t * 4 + grp] = cs;
+                    }
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {                         // pairs inside B
+                        const int pg = grp ^ (t + 1);
+                        const bool vp = (bb * 4 + pg) < nact;
+                        double2 z[NV2];
+#pragma unroll
+                        for (int k = 0; k < NV2; ++k) z[k] = shfl_d2(y[k], lane ^ (8 * (t + 1)));
+                        const double2 cs = jacobi_pair_params<NV2>(y, z, vbs[0] && vp, thr, tol);
+                        if (cs.y != 0.0) {
+                            any_rot = true;
+#pragma unroll
+                            for (int k = 0; k < NV2; ++k) y[k] = make_double2(cs.x * y[k].x - cs.y * z[k].x, cs.x * y[k].y - cs.y * z[k].y);
+                        }
+                        if (sub == 0) rb[(3 + t) * 4 + grp] = cs;
+                    }
                 }
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {                             // cross pairs (A_g, B_(g+s)%4)
+                    const double2 cs = jacobi_pair_params<NV2>(x, y, va && vbs[s], thr, tol);
+                    if (cs.y != 0.0) {
+                        any_rot = true;
+#pragma unroll
+                        for (int k = 0; k < NV2; ++k) {
+                            const double2 a = x[k], b = y[k];
+                            x[k] = make_double2(cs.x * a.x - cs.y * b.x, cs.x * a.y - cs.y * b.y);
+                            y[k] = make_double2(cs.y * a.x + cs.x * b.x, cs.y * a.y + cs.x * b.y);
+                        }
+                    }
+                    if (sub == 0) rb[(6 + s) * 4 + grp] = cs;
+                    if (s < 3) {
+#pragma unroll
+                        for (int k = 0; k < NV2; ++k) y[k] = shfl_d2(y[k], (lane + 8) & 31);   // B columns move to the previous group
+                    }
+                }
+                jacobi_store_col<NV2>(x, Gs, (long long)ca * ldg, sub, va);
+                jacobi_store_col<NV2>(y, Gs, (long long)cbs[3] * ldg, sub, vbs[3]);
             }
+            any_rot = __any_sync(0xffffffffu, any_rot);
+            __syncwarp();
+            if (any_rot) {   // ---------------- pass 2: replay the rotations on the accumulator columns
+                double2 x[WV2], y[WV2];
+                const long long wa = (long long)(w_compact ? pa : ca) * wld;
+                jacobi_load_col<WV2>(x, Wb, wa, sub, va);
+                jacobi_load_col<WV2>(y, Wb, (long long)(w_compact ? bb * 4 + grp : cbs[0]) * wld, sub, vbs[0]);
+                if (r == 0) {
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        const double2 cs = rb[t * 4 + grp];
+                        double2 z[WV2];
+#pragma unroll
+                        for (int k = 0; k < WV2; ++k) z[k] = shfl_d2(x[k], lane ^ (8 * (t + 1)));
+                        if (cs.y != 0.0) {
+#pragma unroll
+                            for (int k = 0; k < WV2; ++k) x[k] = make_double2(cs.x * x[k].x - cs.y * z[k].x, cs.x * x[k].y - cs.y * z[k].y);
+                        }
+                    }
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        const double2 cs = rb[(3 + t) * 4 + grp];
+                        double2 z[WV2];
+#pragma unroll
+                        for (int k = 0; k < WV2; ++k) z[k] = shfl_d2(y[k], lane ^ (8 * (t + 1)));
+                        if (cs.y != 0.0) {
+#pragma unroll
+                            for (int k = 0; k < WV2; ++k) y[k] = make_double2(cs.x * y[k].x - cs.y * z[k].x, cs.x * y[k].y - cs.y * z[k].y);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const double2 cs = rb[(6 + s) * 4 + grp];
+                    if (cs.y != 0.0) {
+#pragma unroll
+                        for (int k = 0; k < WV2; ++k) {
+                            const double2 a = x[k], b = y[k];
+                            x[k] = make_double2(cs.x * a.x - cs.y * b.x, cs.x * a.y - cs.y * b.y);
+                            y[k] = make_double2(cs.y * a.x + cs.x * b.x, cs.y * a.y + cs.x * b.y);
+                        }
+                    }
+                    if (s < 3) {
+#pragma unroll
+                        for (int k = 0; k < WV2; ++k) y[k] = shfl_d2(y[k], (lane + 8) & 31);
+                    }
+                }
+                jacobi_store_col<WV2>(x, Wb, wa, sub, va);
+                jacobi_store_col<WV2>(y, Wb, (long long)(w_compact ? bb * 4 + ((grp + 3) & 3) : cbs[3]) * wld, sub, vbs[3]);
+                if (lane == 0) *s_rot = 1;
+            }
+            __syncwarp();
         }
         __syncthreads();
     }
 }
 
-// rare fallback kept out of line so it does not inflate the register allocation of the shared-memory path
-__device__ __noinline__ void jacobi_sweep_global(double* Gs, int ldg, int ne, double* W, int n_r_grid, int wr_e, const int* list, int nact,
-                                                 double thr, double tol, int slot0, int n_slots, int sub, int* s_rot) {
-    jacobi_sweep_rounds<false, 1>(Gs, ldg, ne, W, n_r_grid, n_r_grid, wr_e, list, nact, thr, tol, slot0, n_slots, sub, s_rot);
+// runtime (ldg, wld) -> compile-time register tile sizes.  MAXV2 bounds the instantiations of one kernel variant.
+template <int MAXV2>
+__device__ __forceinline__ void jacobi_sweep_dispatch(double* Gs, int ldg, double* Wb, int wld, bool w_compact, const int* list, int nact,
+                                                      double thr, double tol, double2* rotbuf, int* s_rot) {
+    if constexpr (MAXV2 >= 16) {
+        if (wld > 128) {
+            if (ldg <= 64) jacobi_sweep_blocked<4, 16>(Gs, ldg, Wb, wld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
+            else if (ldg <= 128) jacobi_sweep_blocked<8, 16>(Gs, ldg, Wb, wld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
+            else jacobi_sweep_blocked<16, 16>(Gs, ldg, Wb, wld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
+            return;
+        }
+        if (ldg > 128) { jacobi_sweep_blocked<16, 8>(Gs, ldg, Wb, wld, w_compact, list, nact, thr, tol, rotbuf, s_rot); return; }
+    }
+    if (ldg <= 64) jacobi_sweep_blocked<4, 8>(Gs, ldg, Wb, wld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
+    else jacobi_sweep_blocked<8, 8>(Gs, ldg, Wb, wld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
 }
 
-__global__ void __launch_bounds__(512, 1) procrustes_jacobi_kernel(const double* __restrict__ g_in, double* __restrict__ gn_out,
-                                                                   double* __restrict__ vw, const double* __restrict__ vt,
-                                                                   double* __restrict__ sigma_out, const ProcOrder* __restrict__ orders,
-                                                                   int n_orders, int n_batch, int n_r_grid, long long g_run_stride,
-                                                                   long long vw_run_stride, long long sig_run_stride, double sv_cutoff,
-                                                                   double tol, int max_sweeps, int* __restrict__ sweeps_out,
-                                                                   int smem_doubles) {
-    extern __shared__ double smem_j[];
+// squared norms of the n columns (one 8-lane group per column)
+__device__ __forceinline__ void jacobi_col_norms(const double* Gs, int ldg, int n, double* nrm2) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int grp = lane >> 3, sub = lane & (JG - 1);
+    for (int c0 = warp * 4; c0 < n; c0 += nwarp * 4) {                     // warp-uniform trip count (shuffles need all lanes)
+        const int c = c0 + grp;
+        double s = 0.0;
+        if (c < n) {
+            const double2* pc = reinterpret_cast<const double2*>(Gs + (size_t)c * ldg) + sub;
+            for (int t = 0; t < ldg / (2 * JG); ++t) { const double2 v = pc[JG * t]; s += v.x * v.x + v.y * v.y; }
+        }
+#pragma unroll
+        for (int off = JG / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (sub == 0 && c < n) nrm2[c] = s;
+    }
+}
+
+// MAXV2 = 8, THREADS = 512: column length <= 128 and N_r <= 128 (the L=63 / N_r=128 configuration)
+// MAXV2 = 16, THREADS = 256: up to 256 / 256 (L=127 / N_r=256); 255 registers per thread for the 2 x 16 double2 tiles
+template <int MAXV2, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) procrustes_jacobi_kernel(const double* __restrict__ g_in, double* __restrict__ gn_out,
+                                                                       double* __restrict__ vw, const double* __restrict__ vt,
+                                                                       double* __restrict__ sigma_out, const ProcOrder* __restrict__ orders,
+                                                                       int n_orders, int n_batch, int n_r_grid, long long g_run_stride,
+                                                                       long long vw_run_stride, long long sig_run_stride, double sv_cutoff,
+                                                                       double tol, int max_sweeps, int* __restrict__ sweeps_out,
+                                                                       int smem_doubles) {
+    extern __shared__ __align__(16) double smem_j[];
     __shared__ int s_nact, s_rot;
     __shared__ double s_thr;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-    const int grp = lane / JG, sub = lane & (JG - 1);     // JGPW groups of JG lanes per warp
-    const int n_slots = nwarp * JGPW;
-    const int slot0 = warp * JGPW + grp;
-    const int wr_e = (n_r_grid + JG - 1) / JG;            // accumulator elements per lane
-    const int wld = 128;                                  // smem accumulator column stride (N_r <= 128, zero padded)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = THREADS >> 5;
+    const int wld = jacobi_wstride(n_r_grid);
+    double2* rotbuf = reinterpret_cast<double2*>(smem_j);                 // [nwarp][JROT_STEPS][4]
+    const int fixed = 2 * nwarp * JROT_STEPS * 4;                         // doubles
 
     for (int prob = blockIdx.x; prob < n_orders * n_batch; prob += gridDim.x) {
         const int oi = prob / n_batch;                     // orders are sorted largest first
         const int b = prob - oi * n_batch;
         const ProcOrder o = orders[oi];
-        const int n = o.n_cols, len = o.n_c;
-        const int ne = (len + JG - 1) / JG;                // G elements per lane
-        const int ldg = jacobi_stride(len);                // column stride == 8 (mod 16) doubles: the two pair groups of a
-                                                           // half warp then fall on disjoint shared-memory banks
-        double* Gs = smem_j;                               // [n][ldg]
-        double* nrm2 = Gs + (size_t)n * ldg;               // [n]
+        const int n = o.n_cols;
+        const int ldg = jacobi_stride(o.n_c);
+        double* nrm2 = smem_j + fixed;                     // [n]
         int* list = (int*)(nrm2 + n);                      // [n]
-        const int ws_off = (n * ldg + n + (n + 1) / 2 + 1) & ~1;      // 16-byte aligned (double2 accesses)
-        double* Ws = smem_j + ws_off;                      // [cap][wld]
-        const int cap = (smem_doubles - ws_off) / wld;
+        const int var0 = (fixed + n + (n + 1) / 2 + 1) & ~1;              // 16-byte aligned
+        const bool g_smem = var0 + n * ldg <= smem_doubles;
         const double* g = g_in + (size_t)b * g_run_stride + o.g_off;
-        double* W = vw + (size_t)b * vw_run_stride + o.vw_off;
-        const double* V0 = vt + o.pd_off;
+        double* gn = gn_out + (size_t)b * g_run_stride + o.g_off;
+        double* Gs = g_smem ? smem_j + var0 : gn;          // [n][ldg]
+        double* Ws = smem_j + var0 + (g_smem ? n * ldg : 0);              // [cap][wld]
+        const int cap = (smem_doubles - (int)(Ws - smem_j)) / wld;
+        double* W = vw + (size_t)b * vw_run_stride + o.vw_off;            // [n][wld]
+        const double* V0 = vt + o.pd_off;                                 // [n][n_r_grid]
         __syncthreads();                                   // previous problem fully done with smem
-        for (int i = tid; i < n * ldg; i += blockDim.x) {
-            const int c = i / ldg, e = i - c * ldg;
-            Gs[i] = (e < len) ? g[(size_t)c * len + e] : 0.0;
+        {
+            const double2* src = reinterpret_cast<const double2*>(g);
+            double2* dst = reinterpret_cast<double2*>(Gs);
+            for (int i = tid; i < n * ldg / 2; i += THREADS) dst[i] = src[i];
         }
-        for (int i = tid; i < n * n_r_grid; i += blockDim.x) W[i] = V0[i];
+        for (int i = tid; i < n * wld; i += THREADS) {
+            const int c = i / wld, e = i - c * wld;
+            W[i] = (e < n_r_grid) ? V0[(size_t)c * n_r_grid + e] : 0.0;
+        }
         __syncthreads();
         int sweep = 0;
         for (; sweep < max_sweeps; ++sweep) {
-            // ---- column norms (one 8-lane group per column)
-            for (int c0 = warp * JGPW; c0 < n; c0 += n_slots) {      // warp-uniform trip count (shuffles need all lanes)
-                const int c = c0 + grp;
-                double s = 0.0;
-                if (c < n)
-                    for (int t = 0; t < ne; ++t) { const double v = Gs[c * ldg + sub + JG * t]; s += v * v; }
-#pragma unroll
-                for (int off = JG / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-                if (sub == 0 && c < n) nrm2[c] = s;
-            }
+            jacobi_col_norms(Gs, ldg, n, nrm2);
             __syncthreads();
             if (warp == 0) {
                 double mx = 0.0;
@@ -285,21 +368,21 @@ __global__ void __launch_bounds__(512, 1) procrustes_jacobi_kernel(const double*
             const int nact = s_nact;
             const double thr = s_thr;
             if (nact < 2) break;
-            if (nact <= cap) {
+            const bool w_smem = nact <= cap;
+            if (w_smem) {
                 // stage the active accumulator columns in shared memory for this sweep
-                for (int i = tid; i < nact * wld; i += blockDim.x) {
-                    const int a = i / wld, e = i - a * wld;
-                    Ws[i] = (e < n_r_grid) ? __ldcg(W + (size_t)list[a] * n_r_grid + e) : 0.0;
+                for (int i = tid; i < nact * (wld / 2); i += THREADS) {
+                    const int a = i / (wld / 2), e = i - a * (wld / 2);
+                    reinterpret_cast<double2*>(Ws)[i] = __ldcg(reinterpret_cast<const double2*>(W + (size_t)list[a] * wld) + e);
                 }
                 __syncthreads();
-                if (ldg <= 64) jacobi_sweep_rounds<true, 64 / (2 * JG)>(Gs, ldg, ne, Ws, wld, n_r_grid, wr_e, list, nact, thr, tol, slot0, n_slots, sub, &s_rot);
-                else jacobi_sweep_rounds<true, 128 / (2 * JG)>(Gs, ldg, ne, Ws, wld, n_r_grid, wr_e, list, nact, thr, tol, slot0, n_slots, sub, &s_rot);
-                for (int i = tid; i < nact * n_r_grid; i += blockDim.x) {
-                    const int a = i / n_r_grid, e = i - a * n_r_grid;
-                    __stcg(W + (size_t)list[a] * n_r_grid + e, Ws[a * wld + e]);
+            }
+            jacobi_sweep_dispatch<MAXV2>(Gs, ldg, w_smem ? Ws : W, wld, w_smem, list, nact, thr, tol, rotbuf, &s_rot);
+            if (w_smem) {
+                for (int i = tid; i < nact * (wld / 2); i += THREADS) {
+                    const int a = i / (wld / 2), e = i - a * (wld / 2);
+                    __stcg(reinterpret_cast<double2*>(W + (size_t)list[a] * wld) + e, reinterpret_cast<const double2*>(Ws)[i]);
                 }
-            } else {
-                jacobi_sweep_global(Gs, ldg, ne, W, n_r_grid, wr_e, list, nact, thr, tol, slot0, n_slots, sub, &s_rot);
             }
             __syncthreads();
             const int rotated = s_rot;
@@ -308,15 +391,7 @@ __global__ void __launch_bounds__(512, 1) procrustes_jacobi_kernel(const double*
         }
         __syncthreads();
         // ---- final norms -> sigma, normalised columns
-        for (int c0 = warp * JGPW; c0 < n; c0 += n_slots) {
-            const int c = c0 + grp;
-            double s = 0.0;
-            if (c < n)
-                for (int t = 0; t < ne; ++t) { const double v = Gs[c * ldg + sub + JG * t]; s += v * v; }
-#pragma unroll
-            for (int off = JG / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            if (sub == 0 && c < n) nrm2[c] = s;
-        }
+        jacobi_col_norms(Gs, ldg, n, nrm2);
         __syncthreads();
         if (warp == 0) {
             double mx = 0.0;
@@ -326,14 +401,13 @@ __global__ void __launch_bounds__(512, 1) procrustes_jacobi_kernel(const double*
         }
         __syncthreads();
         const double thr_f = s_thr;
-        double* gn = gn_out + (size_t)b * g_run_stride + o.g_off;
-        for (int i = tid; i < n * len; i += blockDim.x) {
-            const int c = i / len, e = i - c * len;
+        for (int i = tid; i < n * ldg; i += THREADS) {
+            const int c = i / ldg;
             const double s2 = nrm2[c];
-            gn[i] = (s2 > thr_f && s2 > 0.0) ? Gs[c * ldg + e] / sqrt(s2) : 0.0;
+            gn[i] = (s2 > thr_f && s2 > 0.0) ? Gs[i] / sqrt(s2) : 0.0;
         }
         double* sg = sigma_out + (size_t)b * sig_run_stride + (size_t)oi * n_r_grid;
-        for (int i = tid; i < n; i += blockDim.x) sg[i] = sqrt(nrm2[i]);
+        for (int i = tid; i < n; i += THREADS) sg[i] = sqrt(nrm2[i]);
         if (tid == 0 && sweeps_out) sweeps_out[b * n_orders + oi] = sweep;
     }
 }
@@ -377,15 +451,15 @@ __global__ void procrustes_unpack_kernel(const double2* __restrict__ c_in, doubl
 }
 
 // ---- fxs_unknowns on request (xfb_get_unknowns) ------------------------------------------------------------------
-// gn [n_cols][n_c] = U~^T (zero rows for dropped directions), vw [n_cols][n_r] = J^T (accumulator started from the
+// gn [n_cols][ldg] = U~^T (zero rows for dropped directions), vw [n_cols][wld] = J^T (accumulator started from the
 // identity).  polar(M) = J U~^T (real basis) -> complex columns m = -l..l.  One block per row i of the unknown.
-__global__ void unknown_assemble_kernel(const double* __restrict__ gn, const double* __restrict__ vw, int n_r, int n_cols, int n_c,
+__global__ void unknown_assemble_kernel(const double* __restrict__ gn, const double* __restrict__ vw, int ldg, int wld, int n_cols, int n_c,
                                         int l, double2* __restrict__ out) {
     __shared__ double row[512];
     const int i = blockIdx.x;
     for (int e = threadIdx.x; e < n_c; e += blockDim.x) {
         double s = 0.0;
-        for (int c = 0; c < n_cols; ++c) s += vw[(size_t)c * n_r + i] * gn[(size_t)c * n_c + e];
+        for (int c = 0; c < n_cols; ++c) s += vw[(size_t)c * wld + i] * gn[(size_t)c * ldg + e];
         row[e] = s;
     }
     __syncthreads();

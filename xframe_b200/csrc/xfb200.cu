@@ -50,7 +50,7 @@ struct xfb_plan {
     int* sweeps_dev = nullptr;
     GemmProblem *gemmM_dev = nullptr, *gemmT_dev = nullptr; int *gemmM_tp = nullptr, *gemmT_tp = nullptr;
     int gemmM_tiles = 0, gemmT_tiles = 0, gemm_nb = -1;
-    size_t jacobi_smem = 0; int n_sm = 148;
+    size_t jacobi_smem = 0; int n_sm = 148; bool jacobi_big = false;
     // real projection
     bool has_real = false; RealDesc rd{}; uint8_t* init_support_dev = nullptr;
     // loop state
@@ -273,14 +273,14 @@ static int build_gemm_groups(xfb_plan* p, int nb, cudaStream_t st) {
             GemmProblem a{};
             a.A = p->pd_dev + o.pd_off; a.a_rs = p->n_r; a.a_cs = 1;
             a.B = p->xt + (size_t)b * p->xt_run + o.xt_off; a.b_rs = 1; a.b_cs = p->n_r;
-            a.C = p->g + (size_t)b * p->g_run + o.g_off; a.c_rs = o.n_c; a.c_cs = 1;
+            a.C = p->g + (size_t)b * p->g_run + o.g_off; a.c_rs = jacobi_stride(o.n_c); a.c_cs = 1;
             a.M = o.n_cols; a.N = o.n_c; a.K = p->n_r; a.alpha = 1.0;
             a.tile0 = (int)tpm.size(); a.tiles_n = cdiv(a.N, GG_BN);
             for (int t = 0; t < cdiv(a.M, GG_BM) * a.tiles_n; ++t) tpm.push_back((int)pm.size());
             pm.push_back(a);
             GemmProblem c{};
-            c.A = p->gn + (size_t)b * p->g_run + o.g_off; c.a_rs = 1; c.a_cs = o.n_c;
-            c.B = p->vw + (size_t)b * p->vw_run + o.vw_off; c.b_rs = p->n_r; c.b_cs = 1;
+            c.A = p->gn + (size_t)b * p->g_run + o.g_off; c.a_rs = 1; c.a_cs = jacobi_stride(o.n_c);
+            c.B = p->vw + (size_t)b * p->vw_run + o.vw_off; c.b_rs = jacobi_wstride(p->n_r); c.b_cs = 1;
             c.C = p->tt + (size_t)b * p->xt_run + o.xt_off; c.c_rs = p->n_r; c.c_cs = 1;
             c.M = o.n_c; c.N = p->n_r; c.K = o.n_cols; c.alpha = 1.0;
             c.tile0 = (int)tpt.size(); c.tiles_n = cdiv(c.N, GG_BN);
@@ -294,6 +294,22 @@ static int build_gemm_groups(xfb_plan* p, int nb, cudaStream_t st) {
     XFB_CUDA(cudaMemcpyAsync(p->gemmT_tp, tpt.data(), tpt.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     XFB_CUDA(cudaStreamSynchronize(st));
     p->gemmM_tiles = (int)tpm.size(); p->gemmT_tiles = (int)tpt.size(); p->gemm_nb = nb;
+    return 0;
+}
+
+// one-sided Jacobi over all (order, run) problems of a batch; kernel variant by problem size (procrustes.cuh)
+static int launch_jacobi(xfb_plan* p, const double* g, double* gn, double* vw, const double* vt, double* sigma, int nb, int* sweeps,
+                         cudaStream_t st) {
+    const int na = (int)p->orders.size();
+    const int grid = std::min(na * nb, p->n_sm);
+    const int smem_doubles = (int)(p->jacobi_smem / 8);
+    if (p->jacobi_big)
+        procrustes_jacobi_kernel<16, 256><<<grid, 256, p->jacobi_smem, st>>>(g, gn, vw, vt, sigma, p->orders_dev, na, nb, p->n_r, p->g_run, p->vw_run,
+                                                                            (long long)na * p->n_r, p->sv_cutoff, 1e-15, p->max_sweeps, sweeps, smem_doubles);
+    else
+        procrustes_jacobi_kernel<8, 512><<<grid, 512, p->jacobi_smem, st>>>(g, gn, vw, vt, sigma, p->orders_dev, na, nb, p->n_r, p->g_run, p->vw_run,
+                                                                           (long long)na * p->n_r, p->sv_cutoff, 1e-15, p->max_sweeps, sweeps, smem_doubles);
+    XFB_CUDA(cudaGetLastError());
     return 0;
 }
 
@@ -311,9 +327,7 @@ static int project_i(xfb_plan* p, const double2* c_in, double2* c_out, int nb, c
                    procrustes_pack_kernel<<<dim3(na, nb), 256, 0, st>>>(c_in, p->xt, p->orders_dev, p->n_r, S, p->xt_run));
         XFB_LAUNCH(p, PG_PROC_GEMM, st, grouped_gemm_kernel<<<p->gemmM_tiles, 128, 0, st>>>(p->gemmM_dev, p->gemmM_tp));
         XFB_LAUNCH(p, PG_PROC_JACOBI, st,
-                   procrustes_jacobi_kernel<<<std::min(na * nb, p->n_sm), 512, p->jacobi_smem, st>>>(p->g, p->gn, p->vw, p->vt_dev, p->sigma, p->orders_dev, na, nb,
-                                                                                   p->n_r, p->g_run, p->vw_run, (long long)na * p->n_r,
-                                                                                   p->sv_cutoff, 1e-15, p->max_sweeps, p->sweeps_dev, (int)(p->jacobi_smem / 8)));
+                   if (launch_jacobi(p, p->g, p->gn, p->vw, p->vt_dev, p->sigma, nb, p->sweeps_dev, st)) return 1);
         XFB_LAUNCH(p, PG_PROC_GEMM, st, grouped_gemm_kernel<<<p->gemmT_tiles, 128, 0, st>>>(p->gemmT_dev, p->gemmT_tp));
     }
     XFB_LAUNCH(p, PG_PROC_PACK, st,
@@ -425,23 +439,24 @@ int xfb_plan_set_projection(xfb_plan* p, const xfb_projection_desc* d) {
     }
     std::sort(tmp.begin(), tmp.end(), [](const Tmp& a, const Tmp& b) { return a.l > b.l; });   // largest first
     long long pd_off = 0, xt_off = 0, g_off = 0, vw_off = 0;
-    size_t smem_max = 0;
+    size_t smem_max = 0; int max_nc = 0;
     for (size_t i = 0; i < tmp.size(); ++i) {
         ProcOrder o{};
         o.l = tmp[i].l; o.n_cols = tmp[i].n_cols; o.n_c = 2 * o.l + 1;
         o.pd_off = pd_off; o.xt_off = xt_off; o.g_off = g_off; o.vw_off = vw_off;
-        pd_off += (long long)o.n_cols * n_r; xt_off += (long long)o.n_c * n_r; g_off += (long long)o.n_cols * o.n_c; vw_off += (long long)o.n_cols * n_r;
+        pd_off += (long long)o.n_cols * n_r; xt_off += (long long)o.n_c * n_r;
+        g_off += (long long)o.n_cols * jacobi_stride(o.n_c); vw_off += (long long)o.n_cols * jacobi_wstride(n_r);
         act[o.l] = (int)i;
         p->orders.push_back(o);
         pd.insert(pd.end(), tmp[i].pd.begin(), tmp[i].pd.end());
         vt.insert(vt.end(), tmp[i].vt.begin(), tmp[i].vt.end());
-        smem_max = std::max(smem_max, (size_t)o.n_cols * jacobi_stride(o.n_c) * 8 + (size_t)o.n_cols * 12 + 64);
+        max_nc = std::max(max_nc, o.n_c);
     }
     p->xt_run = xt_off; p->g_run = g_off; p->vw_run = vw_off;
-    if (smem_max > 0) smem_max = std::max(smem_max, (size_t)220 * 1024);
+    smem_max = (size_t)226 * 1024;                    // the Jacobi kernel takes the whole SM: G (and W) live in shared memory when they fit
     p->jacobi_smem = smem_max;
-    if (smem_max > 227 * 1024) XFB_FAIL("Procrustes problem too large for shared memory (%zu bytes)", smem_max);
-    if (n_r > 8 * 16) XFB_FAIL("Procrustes kernel supports N_r <= 128 in this round (got %d)", n_r);
+    if (n_r > 256 || max_nc > 256) XFB_FAIL("Procrustes kernel supports N_r <= 256 and 2l+1 <= 256 (got N_r=%d, 2l+1=%d)", n_r, max_nc);
+    p->jacobi_big = (n_r > 128 || max_nc > 128);
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, dev); }
     if (dev_upload(p, &p->kind_dev, kind.data(), kind.size())) return 1;
     if (dev_upload(p, &p->act_index_dev, act.data(), act.size())) return 1;
@@ -455,6 +470,7 @@ int xfb_plan_set_projection(xfb_plan* p, const xfb_projection_desc* d) {
         if (dev_alloc(p, &p->xt, B * p->xt_run)) return 1;
         if (dev_alloc(p, &p->tt, B * p->xt_run)) return 1;
         if (dev_alloc(p, &p->g, B * p->g_run)) return 1;
+        XFB_CUDA(cudaMemset(p->g, 0, B * p->g_run * sizeof(double)));       // the column pads stay zero: the GEMM writes only [n_cols][n_c]
         if (dev_alloc(p, &p->gn, B * p->g_run)) return 1;
         if (dev_alloc(p, &p->vw, B * p->vw_run)) return 1;
         if (dev_alloc(p, &p->sigma, B * na * n_r)) return 1;
@@ -477,7 +493,8 @@ int xfb_plan_set_projection(xfb_plan* p, const xfb_projection_desc* d) {
         }
         if (dev_alloc(p, &p->gemmM_tp, B * tiles_m)) return 1;
         if (dev_alloc(p, &p->gemmT_tp, B * tiles_t)) return 1;
-        XFB_CUDA(cudaFuncSetAttribute(procrustes_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        if (p->jacobi_big) XFB_CUDA(cudaFuncSetAttribute(procrustes_jacobi_kernel<16, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        else XFB_CUDA(cudaFuncSetAttribute(procrustes_jacobi_kernel<8, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     } else {
         // dummy so the unpack kernel has valid pointers
         ProcOrder o{};
@@ -565,14 +582,12 @@ int xfb_get_unknowns(xfb_plan* p, int32_t run, int32_t order, double* out_dev, v
     }
     const int na = (int)p->orders.size();
     if (p->unk_run != run || p->unk_stamp != p->proj_calls) {
-        procrustes_jacobi_kernel<<<std::min(na, p->n_sm), 512, p->jacobi_smem, st>>>(p->g + (size_t)run * p->g_run, p->gn_u, p->vw_u, p->ident_dev, p->sigma_u,
-                                                                                    p->orders_dev, na, 1, p->n_r, p->g_run, p->vw_run, (long long)na * p->n_r,
-                                                                                    p->sv_cutoff, 1e-15, p->max_sweeps, nullptr, (int)(p->jacobi_smem / 8));
-        XFB_CUDA(cudaGetLastError());
+        if (launch_jacobi(p, p->g + (size_t)run * p->g_run, p->gn_u, p->vw_u, p->ident_dev, p->sigma_u, 1, nullptr, st)) return 1;
         p->unk_run = run; p->unk_stamp = p->proj_calls;
     }
     const ProcOrder o = p->orders[act[order]];
-    unknown_assemble_kernel<<<o.n_cols, 128, 0, st>>>(p->gn_u + o.g_off, p->vw_u + o.vw_off, p->n_r, o.n_cols, o.n_c, o.l, (double2*)out_dev);
+    unknown_assemble_kernel<<<o.n_cols, 128, 0, st>>>(p->gn_u + o.g_off, p->vw_u + o.vw_off, jacobi_stride(o.n_c), jacobi_wstride(p->n_r), o.n_cols, o.n_c, o.l,
+                                                      (double2*)out_dev);
     XFB_CUDA(cudaGetLastError());
     return 0;
 }
