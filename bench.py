@@ -26,6 +26,15 @@ L_MAX, N_R, N_THETA, N_PHI, MAX_Q = 63, 128, 64, 128, 0.322416
 TOTAL_RUNS = 128
 METRIC = "mtip_iterations_per_s_L63_Nr128"
 UNIT = "iterations/s"
+# --workload: 'l63' = BASELINE.json configs[2] (the metric's configuration, default);
+#             'l127' = configs[3] (high resolution: L=127, N_r=256, 128x256, max_q doubled; 64 runs per GPU fit the HBM)
+WORKLOADS = {'l63': (63, 128, 64, 128, 0.322416, 128, "mtip_iterations_per_s_L63_Nr128"),
+             'l127': (127, 256, 128, 256, 0.644832, 64, "mtip_iterations_per_s_L127_Nr256")}
+
+
+def select_workload(name):
+    global L_MAX, N_R, N_THETA, N_PHI, MAX_Q, TOTAL_RUNS, METRIC
+    L_MAX, N_R, N_THETA, N_PHI, MAX_Q, TOTAL_RUNS, METRIC = WORKLOADS[name]
 
 
 def peaks():
@@ -91,7 +100,7 @@ def algorithmic_bytes(nb):
         'real_update': nb * (3 * G * 16 + G),  # IFT(rho_hat'-rho_hat), rho_prev in, rho_next out, support mask (fused ft_stab)
         'pointwise': nb * int(2.5 * G * 16),   # square: G in, G out ; modify_intensity: 2G in, G out  -> average per launch
         # Jacobi: G and V_l^T in, G~/sigma and V_l U out (Procrustes blocks, 8 B reals); latency bound, see DESIGN.md 4.4
-        'procrustes_jacobi': nb * 4 * sum((2 * l + 1) * 128 for l in range(2, L_MAX + 1, 2)) * 8,
+        'procrustes_jacobi': nb * 4 * sum(min(N_R, 2 * l + 1) * N_R for l in range(2, L_MAX + 1, 2)) * 8,
     }
 
 
@@ -155,7 +164,7 @@ def cpu_reference(budget_s=15.0, n_workers=None):
     except OSError:
         pass
     return {'value': its, 'unit': UNIT, 'cores': n_workers, 'kind': 'port',
-            'sample': f'{n_workers} concurrent single-thread processes, each running HIO_ft_stab iterations of the L=63/N_r=128 tutorial '
+            'sample': f'{n_workers} concurrent single-thread processes, each running HIO_ft_stab iterations of the L={L_MAX}/N_r={N_R} tutorial '
                       f'run for ~{budget_s:.0f}s after 1 warm-up ({sum(n for n, _ in res)} iterations total); numpy oracle port of the '
                       f'reference CPU path (shtns absent: SHT timed with the numpy restatement); per-process '
                       f'{min(rates):.3f}..{max(rates):.3f} it/s; pool wall {wall:.1f}s; cpu "{cpu_model}"'}
@@ -292,7 +301,7 @@ def run_ours(args):
             # fresh interpreter: BLAS thread pins must be in the environment before numpy loads, and no CUDA context is forked
             try:
                 env = dict(os.environ, RANK='0', WORLD_SIZE='1')
-                out = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--budget', '15'],
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--budget', '15', '--workload', args.workload],
                                      capture_output=True, text=True, timeout=900, env=env).stdout.strip().splitlines()
                 cb = json.loads(out[-1])['cpu_baseline']
             except Exception as e:      # noqa: BLE001
@@ -300,10 +309,10 @@ def run_ours(args):
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_max / K,
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': 'fxs 3D reconstruct: 128 independent MTIP runs (six-sphere tutorial model) at L=63/N_r=128, 64x128 '
-                                   'angular grid, sharded over the GPUs; step = one HIO_ft_stab iteration of every run',
+            'config': {'workload': f'fxs 3D reconstruct: {total} independent MTIP runs (six-sphere tutorial model) at L={L_MAX}/N_r={N_R}, '
+                                   f'{N_THETA}x{N_PHI} angular grid, sharded over the GPUs; step = one HIO_ft_stab iteration of every run',
                        'runs_total': total, 'runs_per_gpu': nb, 'l2_policy': 'inputs larger than L2 (per-step working set '
-                                                                            f'{nb * 16 * 11} MiB per GPU)',
+                                                                            f'{nb * (N_R * N_THETA * N_PHI * 16 >> 20) * 11} MiB per GPU)',
                        'reconstructions_per_hour': value * 3600.0 / 606.0,
                        'reconstruction_definition': '600 iterations + 6 shrink-wrap steps (tutorial.yaml:52-72)'},
             'roofline': roof, 'cpu_baseline': cb,
@@ -323,10 +332,14 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--runs', type=int, default=TOTAL_RUNS)
+    ap.add_argument('--workload', default='l63', choices=sorted(WORKLOADS))
+    ap.add_argument('--runs', type=int, default=None)
     ap.add_argument('--budget', type=float, default=20.0, help='seconds of timed CPU work per process (reference arm)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     args = ap.parse_args()
+    select_workload(args.workload)
+    if args.runs is None:
+        args.runs = TOTAL_RUNS
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':
         run_reference(args)

@@ -368,3 +368,46 @@ def test_projection_random_matrices_all_kernel_variants(l_max, n_r):
     orders, sweeps = plan.jacobi_sweeps()
     assert sweeps.max() < 40
     plan.close()
+
+
+def test_config4_high_resolution_iteration_against_oracle():
+    """BASELINE.json configs[3]: L=127 / N_r=256 / 128x256, max_q doubled.  Transforms <= 1e-10 per operator
+    (SURVEY.md 8d), projection and one whole HIO_ft_stab iteration <= 1e-6 vs the oracle (256-thread Jacobi variant,
+    column length and N_r up to 256, G in global memory for the large orders)."""
+    from xframe_b200.plan import Plan, HIO
+    from xframe_b200 import setup_host as S
+    from xframe_b200.settings import tutorial_settings
+    L, NR, NT, NP, MQ = 127, 256, 128, 256, 0.644832
+    plan = Plan(L, NR, MQ, n_theta=NT, n_phi=NP, max_batch=2)
+    sd = tutorial_settings(grid={'max_q': MQ, 'max_order': L, 'n_phi': NP, 'n_theta': NT, 'n_radial_points': NR})
+    data = S.invariants_from_density(plan, S.six_sphere_density(plan))
+    m = O.MTIP(sd, data)
+    ps = S.ProjectionSetup(plan.qs, data, L, sd['projections']['reciprocal'])
+    ps.apply_to(plan)
+    popt = sd['projections']['real']['projections']
+    plan.set_real(popt['apply'], S.initial_support(plan, popt['support']['initial_support']), popt['value_threshold']['threshold'],
+                  popt['limit_imag']['threshold'])
+    rho0 = m.density_guess(np.random.default_rng(1000))
+    rho_hat = m.ft(rho0)
+    assert rel_l2(N(plan.ft(T(rho0)[None]))[0], rho_hat) < 1e-10
+    sq = O.square_grid(rho_hat)
+    I = m.sh.forward_l(sq)
+    assert rel_l2(N(plan.sht_forward(T(sq))), np.concatenate(I, axis=1)) < 1e-10
+    Ip = m.rp.mtip_projection(I, m.rp.approximate_unknowns(I))
+    got = N(plan.project_invariants(T(np.concatenate(I, axis=1))[None]))[0]
+    assert rel_l2(got, np.concatenate(Ip, axis=1)) < 1e-6
+    m.results['errors'] = {'real': {'l2_projection_diff': []}, 'reciprocal': {}, 'main': []}
+    m.beta = 0.5
+    rho = m.ift(rho_hat)
+    plan.mtip_init(T(np.stack([rho0, rho0])))
+    assert rel_l2(N(plan.mtip_grid('last_real'))[1], rho) < 1e-10
+    rh_new, rho_next = m.io_step('HIO', rho, True)
+    plan.mtip_iterate(HIO, True, [0.5])
+    assert rel_l2(N(plan.mtip_grid('last_real'))[0], rho_next) < 1e-6
+    assert rel_l2(N(plan.mtip_grid('last_reciprocal'))[1], rh_new) < 1e-6
+    hist, best = plan.mtip_errors()
+    e_ref = m.results['errors']['real']['l2_projection_diff'][-1]
+    assert abs(float(hist[1, 0]) - e_ref) < 1e-6 * e_ref
+    orders, sweeps = plan.jacobi_sweeps()
+    assert sweeps.max() < 40
+    plan.close()

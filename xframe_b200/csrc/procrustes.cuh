@@ -120,149 +120,194 @@ __device__ __forceinline__ void jacobi_store_col(const double2 (&v)[NV], double*
     for (int t = 0; t < NV; ++t) p[JG * t] = v[t];
 }
 
-// One sweep over all pairs of the `nact` active columns list[0..nact).
-//   Gs / ldg : G columns (column id c at Gs + c*ldg);  Wb / wld: accumulator columns, indexed by the POSITION in the
-//   active list when w_compact (shared-memory staging) or by the column id otherwise.
+// Block pair i of block round r (circle method on nblkp blocks: position 0 is fixed, position k >= 1 holds block
+// 1 + ((k-1-r) mod (nblkp-1))); pairs are (position i, position nblkp-1-i).
+struct JBlockPair { int ba, bb; };
+__device__ __forceinline__ JBlockPair jacobi_block_pair(int i, int r, int nblkp) {
+    const int mod = nblkp - 1;
+    JBlockPair bp;
+    bp.ba = 0;
+    if (i != 0) { int t_ = (i - 1 - r) % mod; if (t_ < 0) t_ += mod; bp.ba = 1 + t_; }
+    int tb = (nblkp - 2 - i - r) % mod; if (tb < 0) tb += mod;
+    bp.bb = 1 + tb;
+    return bp;
+}
+
+// Pass 1 of a block pair (one warp): load the 8 G columns, rotate the 16 cross pairs (and in round 0 the 6 + 6 pairs
+// inside A and B) in registers, store the columns, leave the rotation parameters in rb[JROT_STEPS][4] and
+// rb[JROT_STEPS*4].x = 1 if anything rotated.
+template <int NV2>
+__device__ __forceinline__ void jacobi_g_pass(double* Gs, int ldg, const int* __restrict__ list, int nact, JBlockPair bp, bool intra,
+                                              double thr, double tol, double2* rb) {
+    const int lane = threadIdx.x & 31, grp = lane >> 3, sub = lane & (JG - 1);
+    const int ba = bp.ba, bb = bp.bb;
+    const int pa = ba * 4 + grp;                                   // position of A_g in the active list
+    const bool va = pa < nact;
+    const int ca = va ? list[pa] : 0;
+    const int pb0 = bb * 4 + grp, pb3 = bb * 4 + ((grp + 3) & 3);
+    const bool vb0 = pb0 < nact, vb3 = pb3 < nact;
+    bool any_rot = false;
+    double2 x[NV2], y[NV2];
+    jacobi_load_col<NV2>(x, Gs, (long long)ca * ldg, sub, va);
+    jacobi_load_col<NV2>(y, Gs, (long long)(vb0 ? list[pb0] : 0) * ldg, sub, vb0);
+    if (intra) {
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {                             // pairs inside A: partner group = grp ^ (t+1)
+            const bool vp = (ba * 4 + (grp ^ (t + 1))) < nact;
+            double2 z[NV2];
+#pragma unroll
+            for (int k = 0; k < NV2; ++k) z[k] = shfl_d2(x[k], lane ^ (8 * (t + 1)));
+            const double2 cs = jacobi_pair_params<NV2>(x, z, va && vp, thr, tol);
+            if (cs.y != 0.0) {
+                any_rot = true;
+#pragma unroll
+                for (int k = 0; k < NV2; ++k) x[k] = make_double2(cs.x * x[k].x - cs.y * z[k].x, cs.x * x[k].y - cs.y * z[k].y);
+            }
+            if (sub == 0) rb[t * 4 + grp] = cs;
+        }
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {                             // pairs inside B
+            const bool vp = (bb * 4 + (grp ^ (t + 1))) < nact;
+            double2 z[NV2];
+#pragma unroll
+            for (int k = 0; k < NV2; ++k) z[k] = shfl_d2(y[k], lane ^ (8 * (t + 1)));
+            const double2 cs = jacobi_pair_params<NV2>(y, z, vb0 && vp, thr, tol);
+            if (cs.y != 0.0) {
+                any_rot = true;
+#pragma unroll
+                for (int k = 0; k < NV2; ++k) y[k] = make_double2(cs.x * y[k].x - cs.y * z[k].x, cs.x * y[k].y - cs.y * z[k].y);
+            }
+            if (sub == 0) rb[(3 + t) * 4 + grp] = cs;
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {                                 // cross pairs (A_g, B_(g+s)%4)
+        const bool vb = (bb * 4 + ((grp + s) & 3)) < nact;
+        const double2 cs = jacobi_pair_params<NV2>(x, y, va && vb, thr, tol);
+        if (cs.y != 0.0) {
+            any_rot = true;
+#pragma unroll
+            for (int k = 0; k < NV2; ++k) {
+                const double2 a = x[k], b = y[k];
+                x[k] = make_double2(cs.x * a.x - cs.y * b.x, cs.x * a.y - cs.y * b.y);
+                y[k] = make_double2(cs.y * a.x + cs.x * b.x, cs.y * a.y + cs.x * b.y);
+            }
+        }
+        if (sub == 0) rb[(6 + s) * 4 + grp] = cs;
+        if (s < 3) {
+#pragma unroll
+            for (int k = 0; k < NV2; ++k) y[k] = shfl_d2(y[k], (lane + 8) & 31);       // B columns move to the previous group
+        }
+    }
+    jacobi_store_col<NV2>(x, Gs, (long long)ca * ldg, sub, va);
+    jacobi_store_col<NV2>(y, Gs, (long long)(vb3 ? list[pb3] : 0) * ldg, sub, vb3);
+    any_rot = __any_sync(0xffffffffu, any_rot);
+    if (lane == 0) rb[JROT_STEPS * 4] = make_double2(any_rot ? 1.0 : 0.0, 0.0);
+}
+
+// Pass 2 of a block pair (one warp): replay the recorded rotations on the accumulator columns.  Returns true if
+// anything was rotated.  Wb columns are indexed by the POSITION in the active list when w_compact (shared-memory
+// staging) or by the column id otherwise.
+template <int WV2>
+__device__ __forceinline__ bool jacobi_w_pass(double* Wb, int wld, bool w_compact, const int* __restrict__ list, int nact, JBlockPair bp,
+                                              bool intra, const double2* rb) {
+    if (rb[JROT_STEPS * 4].x == 0.0) return false;                // warp-uniform
+    const int lane = threadIdx.x & 31, grp = lane >> 3, sub = lane & (JG - 1);
+    const int pa = bp.ba * 4 + grp, pb0 = bp.bb * 4 + grp, pb3 = bp.bb * 4 + ((grp + 3) & 3);
+    const bool va = pa < nact, vb0 = pb0 < nact, vb3 = pb3 < nact;
+    const long long wa = (long long)(w_compact ? pa : (va ? list[pa] : 0)) * wld;
+    const long long wb0 = (long long)(w_compact ? pb0 : (vb0 ? list[pb0] : 0)) * wld;
+    const long long wb3 = (long long)(w_compact ? pb3 : (vb3 ? list[pb3] : 0)) * wld;
+    double2 x[WV2], y[WV2];
+    jacobi_load_col<WV2>(x, Wb, wa, sub, va);
+    jacobi_load_col<WV2>(y, Wb, wb0, sub, vb0);
+    if (intra) {
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const double2 cs = rb[t * 4 + grp];
+            double2 z[WV2];
+#pragma unroll
+            for (int k = 0; k < WV2; ++k) z[k] = shfl_d2(x[k], lane ^ (8 * (t + 1)));
+            if (cs.y != 0.0) {
+#pragma unroll
+                for (int k = 0; k < WV2; ++k) x[k] = make_double2(cs.x * x[k].x - cs.y * z[k].x, cs.x * x[k].y - cs.y * z[k].y);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const double2 cs = rb[(3 + t) * 4 + grp];
+            double2 z[WV2];
+#pragma unroll
+            for (int k = 0; k < WV2; ++k) z[k] = shfl_d2(y[k], lane ^ (8 * (t + 1)));
+            if (cs.y != 0.0) {
+#pragma unroll
+                for (int k = 0; k < WV2; ++k) y[k] = make_double2(cs.x * y[k].x - cs.y * z[k].x, cs.x * y[k].y - cs.y * z[k].y);
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const double2 cs = rb[(6 + s) * 4 + grp];
+        if (cs.y != 0.0) {
+#pragma unroll
+            for (int k = 0; k < WV2; ++k) {
+                const double2 a = x[k], b = y[k];
+                x[k] = make_double2(cs.x * a.x - cs.y * b.x, cs.x * a.y - cs.y * b.y);
+                y[k] = make_double2(cs.y * a.x + cs.x * b.x, cs.y * a.y + cs.x * b.y);
+            }
+        }
+        if (s < 3) {
+#pragma unroll
+            for (int k = 0; k < WV2; ++k) y[k] = shfl_d2(y[k], (lane + 8) & 31);
+        }
+    }
+    jacobi_store_col<WV2>(x, Wb, wa, sub, va);
+    jacobi_store_col<WV2>(y, Wb, wb3, sub, vb3);
+    return true;
+}
+
+// One sweep over all pairs of the `nact` active columns list[0..nact).  rotbuf: [2][JROT_SLOTS][JROT_RB] double2.
+//  * enough block pairs for every warp: each warp runs pass 1 then pass 2 of its block pairs, one barrier per round;
+//  * fewer block pairs than warps: the warps split into a G team (pass 1 of round r) and a W team (pass 2 of round
+//    r-1, from the double-buffered rotation parameters) that run concurrently -- G and W are independent data.
+#define JROT_RB (JROT_STEPS * 4 + 1)
+#define JROT_SLOTS 32
 template <int NV2, int WV2>
 __device__ __forceinline__ void jacobi_sweep_blocked(double* Gs, int ldg, double* Wb, int wld, bool w_compact, const int* __restrict__ list,
                                                      int nact, double thr, double tol, double2* rotbuf, int* s_rot) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const int grp = lane >> 3, sub = lane & (JG - 1);
     const int nblk = (nact + 3) >> 2;
     const int nblkp = max(2, nblk + (nblk & 1));
-    const int half = nblkp >> 1, mod = nblkp - 1;
-    double2* rb = rotbuf + warp * (JROT_STEPS * 4);
-    for (int r = 0; r < mod; ++r) {
-        for (int i = warp; i < half; i += nwarp) {                       // warp-uniform
-            // circle method on the blocks: position 0 is fixed, position k >= 1 holds block 1 + ((k-1-r) mod (nblkp-1))
-            const int kb = nblkp - 1 - i;
-            int ba = 0;
-            if (i != 0) { int t_ = (i - 1 - r) % mod; if (t_ < 0) t_ += mod; ba = 1 + t_; }
-            int tb = (kb - 1 - r) % mod; if (tb < 0) tb += mod;
-            const int bb = 1 + tb;
-            const int pa = ba * 4 + grp;                                   // position of A_g in the active list
-            const bool va = pa < nact;
-            const int ca = va ? list[pa] : 0;
-            int cbs[4]; bool vbs[4];                                       // B column of this group at step s
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                const int pb = bb * 4 + ((grp + s) & 3);
-                vbs[s] = pb < nact;
-                cbs[s] = vbs[s] ? list[pb] : 0;
+    const int half = nblkp >> 1, rounds = nblkp - 1;
+    bool rotated = false;
+    if (4 * half > 3 * nwarp || nwarp < 4) {
+        for (int r = 0; r < rounds; ++r) {
+            for (int i = warp; i < half; i += nwarp) {                     // warp-uniform
+                const JBlockPair bp = jacobi_block_pair(i, r, nblkp);
+                double2* rb = rotbuf + (size_t)(i % JROT_SLOTS) * JROT_RB;
+                jacobi_g_pass<NV2>(Gs, ldg, list, nact, bp, r == 0, thr, tol, rb);
+                __syncwarp();
+                rotated |= jacobi_w_pass<WV2>(Wb, wld, w_compact, list, nact, bp, r == 0, rb);
+                __syncwarp();
             }
-            bool any_rot = false;
-            {   // ---------------- pass 1: G columns, dot products, rotation parameters
-                double2 x[NV2], y[NV2];
-                jacobi_load_col<NV2>(x, Gs, (long long)ca * ldg, sub, va);
-                jacobi_load_col<NV2>(y, Gs, (long long)cbs[0] * ldg, sub, vbs[0]);
-                if (r == 0) {
-#pragma unroll
-                    for (int t = 0; t < 3; ++t) {                         // pairs inside A: partner group = grp ^ (t+1)
-                        const int pg = grp ^ (t + 1);
-                        const bool vp = (ba * 4 + pg) < nact;
-                        double2 z[NV2];
-#pragma unroll
-                        for (int k = 0; k < NV2; ++k) z[k] = shfl_d2(x[k], lane ^ (8 * (t + 1)));
-                        const double2 cs = jacobi_pair_params<NV2>(x, z, va && vp, thr, tol);
-                        if (cs.y != 0.0) {
-                            any_rot = true;
-#pragma unroll
-                            for (int k = 0; k < NV2; ++k) x[k] = make_double2(cs.x * x[k].x - cs.y * z[k].x, cs.x * x[k].y - cs.y * z[k].y);
-                        }
-                        if (sub == 0) rb[t * 4 + grp] = cs;
-                    }
-#pragma unroll
-                    for (int t = 0; t < 3; ++t) {                         // pairs inside B
-                        const int pg = grp ^ (t + 1);
-                        const bool vp = (bb * 4 + pg) < nact;
-                        double2 z[NV2];
-#pragma unroll
-                        for (int k = 0; k < NV2; ++k) z[k] = shfl_d2(y[k], lane ^ (8 * (t + 1)));
-                        const double2 cs = jacobi_pair_params<NV2>(y, z, vbs[0] && vp, thr, tol);
-                        if (cs.y != 0.0) {
-                            any_rot = true;
-#pragma unroll
-                            for (int k = 0; k < NV2; ++k) y[k] = make_double2(cs.x * y[k].x - cs.y * z[k].x, cs.x * y[k].y - cs.y * z[k].y);
-                        }
-                        if (sub == 0) rb[(3 + t) * 4 + grp] = cs;
-                    }
-                }
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {                             // cross pairs (A_g, B_(g+s)%4)
-                    const double2 cs = jacobi_pair_params<NV2>(x, y, va && vbs[s], thr, tol);
-                    if (cs.y != 0.0) {
-                        any_rot = true;
-#pragma unroll
-                        for (int k = 0; k < NV2; ++k) {
-                            const double2 a = x[k], b = y[k];
-                            x[k] = make_double2(cs.x * a.x - cs.y * b.x, cs.x * a.y - cs.y * b.y);
-                            y[k] = make_double2(cs.y * a.x + cs.x * b.x, cs.y * a.y + cs.x * b.y);
-                        }
-                    }
-                    if (sub == 0) rb[(6 + s) * 4 + grp] = cs;
-                    if (s < 3) {
-#pragma unroll
-                        for (int k = 0; k < NV2; ++k) y[k] = shfl_d2(y[k], (lane + 8) & 31);   // B columns move to the previous group
-                    }
-                }
-                jacobi_store_col<NV2>(x, Gs, (long long)ca * ldg, sub, va);
-                jacobi_store_col<NV2>(y, Gs, (long long)cbs[3] * ldg, sub, vbs[3]);
-            }
-            any_rot = __any_sync(0xffffffffu, any_rot);
-            __syncwarp();
-            if (any_rot) {   // ---------------- pass 2: replay the rotations on the accumulator columns
-                double2 x[WV2], y[WV2];
-                const long long wa = (long long)(w_compact ? pa : ca) * wld;
-                jacobi_load_col<WV2>(x, Wb, wa, sub, va);
-                jacobi_load_col<WV2>(y, Wb, (long long)(w_compact ? bb * 4 + grp : cbs[0]) * wld, sub, vbs[0]);
-                if (r == 0) {
-#pragma unroll
-                    for (int t = 0; t < 3; ++t) {
-                        const double2 cs = rb[t * 4 + grp];
-                        double2 z[WV2];
-#pragma unroll
-                        for (int k = 0; k < WV2; ++k) z[k] = shfl_d2(x[k], lane ^ (8 * (t + 1)));
-                        if (cs.y != 0.0) {
-#pragma unroll
-                            for (int k = 0; k < WV2; ++k) x[k] = make_double2(cs.x * x[k].x - cs.y * z[k].x, cs.x * x[k].y - cs.y * z[k].y);
-                        }
-                    }
-#pragma unroll
-                    for (int t = 0; t < 3; ++t) {
-                        const double2 cs = rb[(3 + t) * 4 + grp];
-                        double2 z[WV2];
-#pragma unroll
-                        for (int k = 0; k < WV2; ++k) z[k] = shfl_d2(y[k], lane ^ (8 * (t + 1)));
-                        if (cs.y != 0.0) {
-#pragma unroll
-                            for (int k = 0; k < WV2; ++k) y[k] = make_double2(cs.x * y[k].x - cs.y * z[k].x, cs.x * y[k].y - cs.y * z[k].y);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    const double2 cs = rb[(6 + s) * 4 + grp];
-                    if (cs.y != 0.0) {
-#pragma unroll
-                        for (int k = 0; k < WV2; ++k) {
-                            const double2 a = x[k], b = y[k];
-                            x[k] = make_double2(cs.x * a.x - cs.y * b.x, cs.x * a.y - cs.y * b.y);
-                            y[k] = make_double2(cs.y * a.x + cs.x * b.x, cs.y * a.y + cs.x * b.y);
-                        }
-                    }
-                    if (s < 3) {
-#pragma unroll
-                        for (int k = 0; k < WV2; ++k) y[k] = shfl_d2(y[k], (lane + 8) & 31);
-                    }
-                }
-                jacobi_store_col<WV2>(x, Wb, wa, sub, va);
-                jacobi_store_col<WV2>(y, Wb, (long long)(w_compact ? bb * 4 + ((grp + 3) & 3) : cbs[3]) * wld, sub, vbs[3]);
-                if (lane == 0) *s_rot = 1;
-            }
-            __syncwarp();
+            __syncthreads();
         }
-        __syncthreads();
+    } else {
+        const int ng = half, nw = nwarp - half;                            // ng <= 3/4 nwarp
+        for (int r = 0; r <= rounds; ++r) {
+            if (warp < ng) {
+                if (r < rounds)
+                    jacobi_g_pass<NV2>(Gs, ldg, list, nact, jacobi_block_pair(warp, r, nblkp), r == 0, thr, tol,
+                                       rotbuf + (size_t)((r & 1) * JROT_SLOTS + warp) * JROT_RB);
+            } else if (r > 0) {
+                for (int i = warp - ng; i < half; i += nw)
+                    rotated |= jacobi_w_pass<WV2>(Wb, wld, w_compact, list, nact, jacobi_block_pair(i, r - 1, nblkp), r == 1,
+                                                  rotbuf + (size_t)(((r - 1) & 1) * JROT_SLOTS + i) * JROT_RB);
+            }
+            __syncthreads();
+        }
     }
+    if (rotated && lane == 0) *s_rot = 1;
 }
 
 // runtime (ldg, wld) -> compile-time register tile sizes.  MAXV2 bounds the instantiations of one kernel variant.
@@ -314,8 +359,8 @@ __global__ void __launch_bounds__(THREADS, 1) procrustes_jacobi_kernel(const dou
     __shared__ double s_thr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = THREADS >> 5;
     const int wld = jacobi_wstride(n_r_grid);
-    double2* rotbuf = reinterpret_cast<double2*>(smem_j);                 // [nwarp][JROT_STEPS][4]
-    const int fixed = 2 * nwarp * JROT_STEPS * 4;                         // doubles
+    double2* rotbuf = reinterpret_cast<double2*>(smem_j);                 // [2][JROT_SLOTS][JROT_RB]
+    const int fixed = 2 * 2 * JROT_SLOTS * JROT_RB;                       // doubles
 
     for (int prob = blockIdx.x; prob < n_orders * n_batch; prob += gridDim.x) {
         const int oi = prob / n_batch;                     // orders are sorted largest first
