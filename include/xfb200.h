@@ -61,6 +61,13 @@ typedef struct {
                                      (mathLibrary.py:1223-1235), phi sum weight 1               */
     const double* r_points;       /* [N_r] real radial grid                                    */
     const double* q_points;       /* [N_r] reciprocal radial grid                              */
+    int32_t dimensions;           /* 3 (or 0): spherical plan as described above.
+                                     2: polar plan (settings `dimensions: 2`): n_theta = 1, n_phi = 2*l_max+1 angular points
+                                     (harmonic_transforms.py:44-47,60), no Legendre tables; hankel_w is
+                                     [n_phi][n_k][N_r], one matrix per DFT index j with the sign of the negative orders
+                                     folded in (w_{-m} = (-1)^m w_m, hankel_transforms.py:441); scales are
+                                     (r_max/N)^2, (q_max/N)^2 (:438-439); int_weight is [N_r][n_phi], the weights of
+                                     PolarIntegrator (mathLibrary.py:1242-1265)                 */
 } xfb_plan_desc;
 
 /* Reciprocal-projection constants (fxs_Projections.py:471-537,679-714,753-754). */
@@ -93,6 +100,11 @@ int xfb_set_device(int dev);
 int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* desc);
 int xfb_plan_destroy(xfb_plan* p);
 int xfb_plan_set_projection(xfb_plan* p, const xfb_projection_desc* d);
+/* 2-D reciprocal projection constants: v = V_m(q) complex [n_orders][N_r] after regrid / odd->0 / V_0 = <I>
+ * (fxs_Projections.py:679-706), radial_mask [l_max+1][N_r], so_order_id = pinned order of SO_freedom or -1 (:743-748). */
+int xfb_plan_set_projection_2d(xfb_plan* p, int32_t n_orders, const double* v, const uint8_t* radial_mask, double sqrt_n_particles,
+                               int32_t so_order_id);
+int xfb_get_unknowns_2d(xfb_plan* p, int32_t run, double* out_dev /*[n_orders] complex*/, void* stream);
 int xfb_plan_set_real(xfb_plan* p, const xfb_real_desc* d, const uint8_t* initial_support_host /*[N_r][n_theta][n_phi]*/);
 int64_t xfb_plan_workspace_bytes(const xfb_plan* p);
 /* ft_stab sketch (reconstruct.py:584-593): 1 (default) evaluates IFT(rho_hat') + (rho - IFT(rho_hat)) as

@@ -642,7 +642,7 @@ class MTIP:
                 self.real_pr.support = state['best_mask']
                 state['mask'] = state['best_mask']
             iterations.append(it)
-        last_I = self.sh.forward_l(square_grid(self.ft(state['pair'][1])))
+        last_inv = self._last_invariants(state['pair'][1])
         return {
             'real_density': state['best_pair'][1], 'reciprocal_density': state['best_pair'][0],
             'last_real_density': state['pair'][1], 'last_reciprocal_density': state['pair'][0],
@@ -652,8 +652,11 @@ class MTIP:
             'error_dict': {'main': np.array(errors['main']),
                            'real': {k: np.array(v) for k, v in errors['real'].items()}, 'reciprocal': {}},
             'fxs_unknowns': self.results.get('fxs_unknowns'),
-            'last_deg2_invariant': harmonic_coeff_to_deg2_invariants_3d(last_I),
+            'last_deg2_invariant': last_inv,
         }
+
+    def _last_invariants(self, rho):             # reconstruct.py:757-765
+        return harmonic_coeff_to_deg2_invariants_3d(self.sh.forward_l(square_grid(self.ft(rho))))
 
 
 # --------------------------------------------------------------------------

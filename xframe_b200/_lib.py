@@ -19,7 +19,7 @@ class PlanDesc(C.Structure):
                 ('hankel_w', C.POINTER(C.c_double)), ('hankel_n_sum', C.c_int32),
                 ('hankel_fwd_scale', C.c_double), ('hankel_inv_scale', C.c_double),
                 ('int_weight', C.POINTER(C.c_double)), ('r_points', C.POINTER(C.c_double)),
-                ('q_points', C.POINTER(C.c_double))]
+                ('q_points', C.POINTER(C.c_double)), ('dimensions', C.c_int32)]
 
 
 class ProjectionDesc(C.Structure):
@@ -41,6 +41,8 @@ EXPORTS = {
     'xfb_plan_create': (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(PlanDesc)]),
     'xfb_plan_destroy': (C.c_int, [C.c_void_p]),
     'xfb_plan_set_projection': (C.c_int, [C.c_void_p, C.POINTER(ProjectionDesc)]),
+    'xfb_plan_set_projection_2d': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_int32]),
+    'xfb_get_unknowns_2d': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'xfb_plan_set_real': (C.c_int, [C.c_void_p, C.POINTER(RealDesc), C.c_void_p]),
     'xfb_plan_workspace_bytes': (C.c_int64, [C.c_void_p]),
     'xfb_debug_jacobi_sweeps': (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

@@ -15,9 +15,10 @@
 #define HK_LDB (HK_BN + 4)
 
 struct HankelTile {
-    int l;        // order
+    int l;        // index of the weight matrix (3-D: order l; 2-D: DFT index j of the order m)
     int row0;     // first flat row (lm*nb + b) of this tile
-    int row_end;  // one past the last flat row of order l
+    int row_end;  // one past the last flat row of this order
+    int ph;       // order mod 4 (non-negative): the prefactor is (-i)^ph forward, (+i)^ph inverse
 };
 
 __global__ void __launch_bounds__(256) hankel_kernel(const double2* __restrict__ in, double2* __restrict__ out,
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(256) hankel_kernel(const double2* __restrict__
         }
     }
     // epilogue: multiply by scale * (-i)^l (forward) or (+i)^l (inverse)
-    const int ph = t.l & 3;
+    const int ph = t.ph;
 #pragma unroll
     for (int mb = 0; mb < 4; ++mb) {
         const int grow = t.row0 + wm * 32 + mb * 8 + ar;

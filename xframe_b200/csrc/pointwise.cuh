@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(RU_THREADS) real_update_kernel(const double2* 
                                                                  const int* __restrict__ support_slot, long long support_slot_stride,
                                                                  const int* __restrict__ enforce, const uint8_t* __restrict__ init_support,
                                                                  const double* __restrict__ wt, RealDesc rd, int method, double beta,
-                                                                 int n_theta, int n_phi, long long per_run, double* __restrict__ partial,
+                                                                 int n_theta, int n_phi, int wt_div, long long per_run, double* __restrict__ partial,
                                                                  const double2* __restrict__ rt0) {
     const int b = blockIdx.y;
     const double2* ri = rho_ift + (long long)b * per_run;
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(RU_THREADS) real_update_kernel(const double2* 
         if (method == 0 && msel) o = make_double2(prev.x - beta * (v.x - p.x), prev.y - beta * (v.y - p.y));
         rn[i] = o;
         if (!rd.err_inside || in_init) {
-            const double w = __ldg(wt + (unsigned)i / (unsigned)n_phi);     // per_run < 2^31: 32-bit division
+            const double w = __ldg(wt + (unsigned)i / (unsigned)wt_div);    // per_run < 2^31: 32-bit division; wt_div = n_phi (3-D) or 1 (2-D)
             const double dx = v.x - p.x, dy = v.y - p.y;
             s_diff += w * (dx * dx + dy * dy);
             s_val += w * (v.x * v.x + v.y * v.y);

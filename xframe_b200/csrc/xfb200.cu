@@ -6,6 +6,7 @@
 #include "legendre.cuh"
 #include "gemm.cuh"
 #include "procrustes.cuh"
+#include "polar.cuh"
 
 #include <algorithm>
 
@@ -18,7 +19,12 @@ static const char* kProfNames[PG_COUNT] = {"fft_phi", "legendre", "hankel", "pro
 struct ProfEvent { cudaEvent_t a, b; int group; };
 
 struct xfb_plan {
+    int dims = 3;                                   // 3: spherical (SHT + spherical Hankel), 2: polar (circular harmonics + polar Hankel)
     int L = 0, n_r = 0, n_theta = 0, n_phi = 0, max_batch = 0, NLM = 0, M2 = 0, K2 = 0, NP = 0;
+    int n_hankel = 0;                               // number of radial weight matrices: L+1 (3-D) or n_phi (2-D, one per DFT index)
+    int wt_div = 1;                                 // quadrature weight index = point index / wt_div
+    // 2-D projection constants
+    double2* v2d = nullptr; double2* unk2d = nullptr; int n_orders2d = 0, so_order2d = -1;
     int hankel_skip = 0, hankel_n_sum = 0;
     double hk_fwd_scale = 0, hk_inv_scale = 0;
     long long G = 0, C = 0;
@@ -111,21 +117,48 @@ int xfb_set_device(int dev) { XFB_CUDA(cudaSetDevice(dev)); return 0; }
 
 int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
     if (!out || !d) XFB_FAIL("null argument");
-    if (d->n_theta % 8 != 0) XFB_FAIL("n_theta=%d must be a multiple of 8", d->n_theta);
-    if (d->n_theta <= d->l_max) XFB_FAIL("n_theta=%d must exceed l_max=%d (exact Gauss quadrature)", d->n_theta, d->l_max);
-    if (d->n_phi <= 2 * d->l_max) XFB_FAIL("n_phi=%d must exceed 2*l_max", d->n_phi);
-    if (d->n_phi < 16 || d->n_phi > 512 || (d->n_phi & (d->n_phi - 1))) XFB_FAIL("n_phi=%d must be a power of two in [16,512]", d->n_phi);
+    const int dims = (d->dimensions == 2) ? 2 : 3;
+    if (dims == 3) {
+        if (d->n_theta % 8 != 0) XFB_FAIL("n_theta=%d must be a multiple of 8", d->n_theta);
+        if (d->n_theta <= d->l_max) XFB_FAIL("n_theta=%d must exceed l_max=%d (exact Gauss quadrature)", d->n_theta, d->l_max);
+        if (d->n_phi <= 2 * d->l_max) XFB_FAIL("n_phi=%d must exceed 2*l_max", d->n_phi);
+        if (d->n_phi < 16 || d->n_phi > 512 || (d->n_phi & (d->n_phi - 1))) XFB_FAIL("n_phi=%d must be a power of two in [16,512]", d->n_phi);
+    } else {
+        if (d->n_theta != 1) XFB_FAIL("2-D plan: n_theta must be 1 (got %d)", d->n_theta);
+        if (d->n_phi < 3 || d->n_phi > 1023) XFB_FAIL("2-D plan: n_phi=%d outside [3,1023]", d->n_phi);
+        if (d->n_phi != 2 * d->l_max + 1) XFB_FAIL("2-D plan: n_phi=%d must be 2*max_order+1 (harmonic_transforms.py:44-47)", d->n_phi);
+    }
     if (d->max_batch < 1) XFB_FAIL("max_batch must be >= 1");
     int ndev = 0;
     XFB_CUDA(cudaGetDeviceCount(&ndev));
     if (ndev == 0) XFB_FAIL("no CUDA device: xfb200 has no CPU fallback");
     xfb_plan* p = new xfb_plan();
+    p->dims = dims;
     p->L = d->l_max; p->n_r = d->n_r; p->n_theta = d->n_theta; p->n_phi = d->n_phi; p->max_batch = d->max_batch;
-    p->NLM = (p->L + 1) * (p->L + 1); p->M2 = 2 * p->L + 1; p->K2 = p->n_theta / 2;
-    p->NP = ((p->L / 2 + 1) + 7) / 8 * 8;
     p->hankel_skip = d->hankel_skip; p->hankel_n_sum = d->hankel_n_sum;
     p->hk_fwd_scale = d->hankel_fwd_scale; p->hk_inv_scale = d->hankel_inv_scale;
     p->G = (long long)p->n_r * p->n_theta * p->n_phi;
+    if (dims == 2) {
+        // polar plan: coefficient arrays are [n_phi][S]; no Legendre stage, no phi-FFT tables
+        p->NLM = p->n_phi; p->M2 = p->n_phi; p->n_hankel = p->n_phi; p->wt_div = 1; p->fused_ft_stab = 0;
+        p->C = (long long)p->NLM * p->n_r;
+        if (dev_upload(p, &p->hankel_w, d->hankel_w, (size_t)p->n_hankel * p->hankel_n_sum * p->n_r)) return 1;
+        if (dev_upload(p, &p->int_wt, d->int_weight, (size_t)p->n_r * p->n_phi)) return 1;      // per point: trapz in phi (PolarIntegrator)
+        if (dev_upload(p, &p->q_pts, d->q_points, (size_t)p->n_r)) return 1;
+        const size_t B2 = p->max_batch;
+        if (dev_alloc(p, &p->C0, B2 * p->C)) return 1;
+        if (dev_alloc(p, &p->C1, B2 * p->C)) return 1;
+        if (dev_alloc(p, &p->W0, B2 * p->G)) return 1;
+        if (dev_alloc(p, &p->W1, B2 * p->G)) return 1;
+        if (dev_alloc(p, &p->W2, B2 * p->G)) return 1;
+        XFB_CUDA(cudaFuncSetAttribute(dft2d_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dft_smem(p->n_phi)));
+        XFB_CUDA(cudaFuncSetAttribute(dft2d_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dft_smem(p->n_phi)));
+        *out = p;
+        return 0;
+    }
+    p->NLM = (p->L + 1) * (p->L + 1); p->M2 = 2 * p->L + 1; p->K2 = p->n_theta / 2;
+    p->NP = ((p->L / 2 + 1) + 7) / 8 * 8;
+    p->n_hankel = p->L + 1; p->wt_div = p->n_phi;
     p->C = (long long)p->NLM * p->n_r;
     const size_t tab = (size_t)(p->L + 1) * p->K2 * p->NP;
     if (d->legendre_len != (int64_t)(4 * tab)) { delete p; XFB_FAIL("legendre table length %lld != %lld", (long long)d->legendre_len, (long long)(4 * tab)); }
@@ -162,7 +195,7 @@ int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
 int xfb_plan_destroy(xfb_plan* p) {
     if (!p) return 0;
     void* ptrs[] = {p->tw, p->FE, p->FO, p->IE, p->IO, p->hankel_w, p->int_wt, p->q_pts, p->A0, p->C0, p->C1, p->W0, p->W1, p->W2, p->A0s, p->C0s, p->rt0, p->stage_out,
-                    p->hk_tiles, p->orders_dev, p->kind_dev, p->act_index_dev, p->radial_mask_dev, p->v0_dev, p->pd_dev, p->vt_dev,
+                    p->hk_tiles, p->v2d, p->unk2d, p->orders_dev, p->kind_dev, p->act_index_dev, p->radial_mask_dev, p->v0_dev, p->pd_dev, p->vt_dev,
                     p->xt, p->tt, p->g, p->gn, p->vw, p->sigma, p->sweeps_dev, p->ident_dev, p->gn_u, p->vw_u, p->sigma_u, p->i00, p->gemmM_dev, p->gemmT_dev, p->gemmM_tp, p->gemmT_tp,
                     p->init_support_dev, p->rho_pool, p->rh_pool, p->mask_pool, p->ls_ints, p->ls_dbl, p->partial, p->err, p->mm};
     for (void* q : ptrs) if (q) cudaFree(q);
@@ -208,14 +241,25 @@ int xfb_profile_read(xfb_plan* p, int32_t n_max, char* names, double* ms, int64_
 
 // ---- internal building blocks -----------------------------------------------------------
 static int sht_forward_i(xfb_plan* p, SlotView in, int shells_per_run, double2* c_out, int S, cudaStream_t st,
-                         const double2* sub = nullptr) {
+                         const double2* sub = nullptr, int real_only = 0) {
+    if (p->dims == 2) {   // circular harmonic transform: fft(x)/n_phi  (mathLibrary.py:469-475,484-490)
+        XFB_LAUNCH(p, PG_FFT, st,
+                   dft2d_forward_kernel<<<cdiv(S, DFT_ROWS), DFT_THREADS, dft_smem(p->n_phi), st>>>(in, shells_per_run, sub, c_out, S, p->n_phi,
+                                                                                                   1.0 / p->n_phi, real_only));
+        return 0;
+    }
     XFB_LAUNCH(p, PG_FFT, st, if (launch_fft(true, p->n_phi, in, shells_per_run, sub, p->A0, p->tw, S, p->n_theta, p->L, st)) return 1);
     dim3 g(cdiv(S, 16), p->L + 1);
     XFB_LAUNCH(p, PG_LEGENDRE, st,
                legendre_forward_kernel<<<g, LEG_THREADS, legendre_fwd_smem(p->n_theta), st>>>(p->A0, c_out, p->FE, p->FO, S, p->L, p->n_theta, p->NP));
     return 0;
 }
-static int sht_inverse_i(xfb_plan* p, const double2* c_in, double2* grid_out, int S, cudaStream_t st) {
+static int sht_inverse_i(xfb_plan* p, const double2* c_in, double2* grid_out, int S, cudaStream_t st, int herm = 0) {
+    if (p->dims == 2) {   // ifft(c * n_phi) / irfft(c * n_phi, n_phi)  (mathLibrary.py:478-482,492-496)
+        XFB_LAUNCH(p, PG_FFT, st,
+                   dft2d_inverse_kernel<<<cdiv(S, DFT_ROWS), DFT_THREADS, dft_smem(p->n_phi), st>>>(c_in, grid_out, S, p->n_phi, herm));
+        return 0;
+    }
     dim3 g(cdiv(S, 16), p->L + 1);
     XFB_LAUNCH(p, PG_LEGENDRE, st,
                legendre_inverse_kernel<<<g, LEG_THREADS, legendre_inv_smem(p->n_theta, p->NP), st>>>(c_in, p->A0, p->IE, p->IO, S, p->L, p->n_theta, p->NP));
@@ -226,9 +270,18 @@ static int sht_inverse_i(xfb_plan* p, const double2* c_in, double2* grid_out, in
 static int hankel_i(xfb_plan* p, int dir, const double2* c_in, double2* c_out, int nb, cudaStream_t st) {
     if (p->hk_tiles_nb != nb) {
         std::vector<HankelTile> tiles;
-        for (int l = p->L; l >= 0; --l) {   // largest orders first
-            const int r0 = l * l * nb, r1 = (l + 1) * (l + 1) * nb;
-            for (int r = r0; r < r1; r += HK_BM) tiles.push_back(HankelTile{l, r, r1});
+        if (p->dims == 2) {
+            // one weight matrix per DFT index j; order m = j (j <= M) or j - N: (-i)^m = (-i)^(m mod 4)
+            for (int j = 0; j < p->n_phi; ++j) {
+                const int m = (j <= p->L) ? j : j - p->n_phi;
+                const int r0 = j * nb, r1 = (j + 1) * nb;
+                for (int r = r0; r < r1; r += HK_BM) tiles.push_back(HankelTile{j, r, r1, ((m % 4) + 4) % 4});
+            }
+        } else {
+            for (int l = p->L; l >= 0; --l) {   // largest orders first
+                const int r0 = l * l * nb, r1 = (l + 1) * (l + 1) * nb;
+                for (int r = r0; r < r1; r += HK_BM) tiles.push_back(HankelTile{l, r, r1, l & 3});
+            }
         }
         if ((int)tiles.size() > p->hk_tiles_cap) {
             if (p->hk_tiles) cudaFree(p->hk_tiles);
@@ -317,6 +370,13 @@ static int launch_jacobi(xfb_plan* p, const double* g, double* gn, double* vw, c
 static int project_i(xfb_plan* p, const double2* c_in, double2* c_out, int nb, cudaStream_t st) {
     if (!p->has_proj) XFB_FAIL("projection constants not set (xfb_plan_set_projection)");
     const int S = nb * p->n_r;
+    if (p->dims == 2) {
+        p->proj_calls++; p->last_proj_nb = nb;
+        XFB_LAUNCH(p, PG_PROC_PACK, st,
+                   project2d_kernel<<<nb, 256, 0, st>>>(c_in, c_out, p->v2d, p->radial_mask_dev, p->q_pts, p->unk2d, p->n_orders2d, p->L, p->n_phi,
+                                                        p->n_r, S, p->inv_sqrt_np, p->so_order2d));
+        return 0;
+    }
     const int na = (int)p->orders.size();
     // row (l=0,m=0) of the coefficient array = I_00(q) of every run: kept for xfb_get_unknowns
     XFB_CUDA(cudaMemcpyAsync(p->i00, c_in, (size_t)S * sizeof(double2), cudaMemcpyDeviceToDevice, st));
@@ -381,7 +441,7 @@ static int real_update_i(xfb_plan* p, int method, double beta, const double2* rh
     XFB_LAUNCH(p, PG_REAL_UPDATE, st,
                real_update_kernel<<<dim3(bpr, nb), RU_THREADS, 0, st>>>(rho_ift, rho_rt, prev, next, support, support_slot, support_slot_stride,
                                                                         enforce, p->init_support_dev, p->int_wt, p->rd, method, beta,
-                                                                        p->n_theta, p->n_phi, p->G, p->partial, rt0));
+                                                                        p->n_theta, p->n_phi, p->wt_div, p->G, p->partial, rt0));
     XFB_LAUNCH(p, PG_MISC, st, reduce_pairs_kernel<<<nb, 32, 0, st>>>(p->partial, bpr, err_out));
     return 0;
 }
@@ -408,6 +468,7 @@ extern "C" {
 int xfb_plan_set_projection(xfb_plan* p, const xfb_projection_desc* d) {
     if (!p || !d) XFB_FAIL("null argument");
     if (p->has_proj) XFB_FAIL("projection already set on this plan");
+    if (p->dims != 3) XFB_FAIL("xfb_plan_set_projection is the 3-D setter; use xfb_plan_set_projection_2d");
     const int L = p->L, n_r = p->n_r;
     std::vector<int> kind(L + 1, ORD_PASS), act(L + 1, -1);
     std::vector<double> pd, vt, v0(n_r, 0.0);
@@ -509,6 +570,31 @@ int xfb_plan_set_projection(xfb_plan* p, const xfb_projection_desc* d) {
     return 0;
 }
 
+int xfb_plan_set_projection_2d(xfb_plan* p, int32_t n_orders, const double* v, const uint8_t* radial_mask, double sqrt_n_particles,
+                               int32_t so_order_id) {
+    if (!p || !v || !radial_mask) XFB_FAIL("null argument");
+    if (p->dims != 2) XFB_FAIL("xfb_plan_set_projection_2d needs a 2-D plan");
+    if (p->has_proj) XFB_FAIL("projection already set on this plan");
+    if (n_orders < 1 || n_orders > p->L + 1) XFB_FAIL("n_orders=%d outside 1..%d", n_orders, p->L + 1);
+    if (dev_upload(p, &p->v2d, (const double2*)v, (size_t)n_orders * p->n_r)) return 1;
+    if (dev_upload(p, &p->radial_mask_dev, radial_mask, (size_t)(p->L + 1) * p->n_r)) return 1;
+    if (dev_alloc(p, &p->unk2d, (size_t)p->max_batch * n_orders)) return 1;
+    p->n_orders2d = n_orders; p->so_order2d = so_order_id;
+    p->inv_sqrt_np = 1.0 / sqrt_n_particles;
+    p->has_proj = true;
+    return 0;
+}
+
+// 2-D fxs_unknowns of the last projection: out_dev [n_orders] complex (fxs_Projections.py:727-748)
+int xfb_get_unknowns_2d(xfb_plan* p, int32_t run, double* out_dev, void* stream) {
+    if (p->dims != 2 || !p->has_proj) XFB_FAIL("xfb_get_unknowns_2d needs a 2-D plan with projection constants");
+    if (p->proj_calls == 0) XFB_FAIL("xfb_get_unknowns_2d: no invariant projection has run yet");
+    if (run < 0 || run >= p->last_proj_nb) XFB_FAIL("run=%d outside the last projected batch (%d)", run, p->last_proj_nb);
+    XFB_CUDA(cudaMemcpyAsync(out_dev, p->unk2d + (size_t)run * p->n_orders2d, (size_t)p->n_orders2d * sizeof(double2), cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)stream));
+    return 0;
+}
+
 int xfb_plan_set_real(xfb_plan* p, const xfb_real_desc* d, const uint8_t* init_support_host) {
     if (!p || !d || !init_support_host) XFB_FAIL("null argument");
     if (d->n_ops < 0 || d->n_ops > 4) XFB_FAIL("n_ops out of range");
@@ -560,6 +646,7 @@ int xfb_project_invariants(xfb_plan* p, const double* in, double* out, int32_t n
 // kernel is run once more for that run with the accumulator started from the identity, so that it yields J itself.
 int xfb_get_unknowns(xfb_plan* p, int32_t run, int32_t order, double* out_dev, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    if (p->dims != 3) XFB_FAIL("xfb_get_unknowns is the 3-D entry point; use xfb_get_unknowns_2d");
     if (!p->has_proj) XFB_FAIL("projection constants not set");
     if (p->proj_calls == 0) XFB_FAIL("xfb_get_unknowns: no invariant projection has run yet");
     if (run < 0 || run >= p->last_proj_nb) XFB_FAIL("run=%d outside the last projected batch (%d)", run, p->last_proj_nb);
@@ -665,11 +752,11 @@ static int iterate_range(xfb_plan* p, int b0, int nb, int method, int ft_stab, d
     }
     // 2. |rho_hat|^2 -> I_lm                                 (:519-520)
     XFB_LAUNCH(p, PG_POINTWISE, st, square_kernel<<<ew_blocks((long long)nb * p->G), 256, 0, st>>>(p->W0, p->W1, (long long)nb * p->G));
-    if (sht_forward_i(p, flat_view(p->W1, p->G), p->n_r, p->C0, S, st)) return 1;
+    if (sht_forward_i(p, flat_view(p->W1, p->G), p->n_r, p->C0, S, st, nullptr, p->dims == 2)) return 1;   // 2-D: 'real' transform (reconstruct.py:347-348)
     // 3. projection onto the invariants                      (:521-523)
     if (project_i(p, p->C0, p->C1, nb, st)) return 1;
     // 4. I_proj on the grid, modified intensity              (:524-525)
-    if (sht_inverse_i(p, p->C1, p->W1, S, st)) return 1;
+    if (sht_inverse_i(p, p->C1, p->W1, S, st, p->dims == 2)) return 1;
     XFB_LAUNCH(p, PG_POINTWISE, st,
                modify_intensity_kernel<<<dim3(eb, nb), 256, 0, st>>>(p->W0, p->W1, pv(p->rh_pool, p->ls.rh_next), p->G));
     // 5. back to real space (+ ft_stab correction terms)     (:586-588 / :579)
@@ -712,7 +799,7 @@ int xfb_debug_jacobi_sweeps(xfb_plan* p, int32_t* out_host, int32_t capacity, in
     return 0;
 }
 
-int xfb_plan_set_fused_ft_stab(xfb_plan* p, int32_t on) { p->fused_ft_stab = on ? 1 : 0; return 0; }
+int xfb_plan_set_fused_ft_stab(xfb_plan* p, int32_t on) { p->fused_ft_stab = (on && p->dims == 3) ? 1 : 0; return 0; }
 
 int xfb_mtip_shrinkwrap(xfb_plan* p, double sigma, double threshold, double error_limit, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;

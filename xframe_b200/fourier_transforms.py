@@ -39,43 +39,38 @@ def generate_ft(r_max, weights, harm_trf, dimensions, pos_orders=False, use_gpu=
     ht, iht = select_harmonic_transforms(harm_trf, dimensions, True)
     pair = hankel.pair
 
-    if dimensions == 3:
-        shobj = harm_trf._sh
-        n_r = pair.n_r
+    if dimensions not in (2, 3):
+        raise XfbError(f"dimensions={dimensions} not supported")
+    ang = harm_trf._sh if dimensions == 3 else harm_trf._ch
+    n_r = pair.n_r
 
-        def fused(data, inverse):
-            import torch
-            if pair._plan is None:
-                from .plan import Plan
-                pair._plan = Plan(pair.l_max, n_r, reciprocity_coefficient * n_r / r_max, n_theta=shobj.n_theta, n_phi=shobj.n_phi,
-                                  reciprocity_coefficient=reciprocity_coefficient, ft_type=mode, max_batch=max_batch,
-                                  device=harm_trf.opt.get('device'), hankel_weights=pair.weights[:pair.l_max + 1],
-                                  hankel_scales=pair.scales())
-                if shobj._plan is None:
-                    shobj.attach_plan(pair._plan)
-            plan = pair._plan
-            was_torch = isinstance(data, torch.Tensor)
-            d = data if was_torch else torch.from_numpy(np.ascontiguousarray(data, dtype=np.complex128))
-            d = d.to(device=plan.device, dtype=torch.complex128).contiguous()
-            squeeze = d.dim() == 3
-            if squeeze:
-                d = d[None]
-            outs = [plan.ft(d[i:i + plan.max_batch].contiguous(), inverse=inverse) for i in range(0, d.shape[0], plan.max_batch)]
-            out = outs[0] if len(outs) == 1 else torch.cat(outs)
-            if squeeze:
-                out = out[0]
-            return out if was_torch else out.cpu().numpy()
+    def fused(data, inverse):
+        import torch
+        if pair._plan is None:
+            from .plan import Plan
+            kw = dict(n_theta=ang.n_theta, n_phi=ang.n_phi) if dimensions == 3 else {}
+            pair._plan = Plan(pair.l_max, n_r, reciprocity_coefficient * n_r / r_max, reciprocity_coefficient=reciprocity_coefficient,
+                              ft_type=mode, max_batch=max_batch, device=harm_trf.opt.get('device'), dimensions=dimensions,
+                              hankel_weights=pair.weights[:pair.l_max + 1], hankel_scales=pair.scales(), **kw)
+            if dimensions == 3 and ang._plan is None:
+                ang.attach_plan(pair._plan)
+        plan = pair._plan
+        was_torch = isinstance(data, torch.Tensor)
+        d = data if was_torch else torch.from_numpy(np.ascontiguousarray(data, dtype=np.complex128))
+        d = d.to(device=plan.device, dtype=torch.complex128).contiguous()
+        squeeze = d.dim() == dimensions
+        if squeeze:
+            d = d[None]
+        outs = [plan.ft(d[i:i + plan.max_batch].contiguous(), inverse=inverse) for i in range(0, d.shape[0], plan.max_batch)]
+        out = outs[0] if len(outs) == 1 else torch.cat(outs)
+        if squeeze:
+            out = out[0]
+        return out if was_torch else out.cpu().numpy()
 
-        def ft(data):
-            return fused(data, False)
+    def ft(data):
+        return fused(data, False)
 
-        def ift(data):
-            return fused(data, True)
-    else:
-        def ft(data):
-            return iht(hankel(ht(data)))
-
-        def ift(data):
-            return iht(ihankel(ht(data)))
+    def ift(data):
+        return fused(data, True)
     ft.hankel, ift.hankel = hankel, ihankel
     return ft, ift

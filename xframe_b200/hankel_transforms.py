@@ -86,9 +86,10 @@ class _HankelPair:
                                   ft_type=self.mode, max_batch=self.max_batch, device=self.device,
                                   hankel_weights=self.weights[:self.l_max + 1], hankel_scales=self.scales())
             else:
-                from .circular import PolarPlan
-                self._plan = PolarPlan(self.l_max, self.n_r, self.weights[:self.l_max + 1], self.scales(), device=self.device,
-                                       max_batch=self.max_batch)
+                from .plan import Plan
+                self._plan = Plan(self.l_max, self.n_r, _q_max_from_r_max(self.r_max, self.n_r, self.rc), reciprocity_coefficient=self.rc,
+                                  ft_type=self.mode, max_batch=self.max_batch, device=self.device, dimensions=2,
+                                  hankel_weights=self.weights[:self.l_max + 1], hankel_scales=self.scales())
         return self._plan
 
     def apply(self, coeff, inverse):

@@ -30,10 +30,16 @@ def _stream():
 
 class Plan:
     def __init__(self, l_max, n_r, max_q, n_theta=0, n_phi=0, reciprocity_coefficient=2.0, ft_type='midpoint',
-                 max_batch=1, device=None, hankel_weights=None, hankel_scales=None):
+                 max_batch=1, device=None, hankel_weights=None, hankel_scales=None, dimensions=3):
         """hankel_weights / hankel_scales: optional caller-supplied radial weights [L+1, n_sum, N_r] (float64) and
         (forward, inverse) prefactors, as the reference's generate_ht receives them (hankel_transforms.py:540-559);
-        by default they are computed for (ft_type, reciprocity_coefficient) like generate_weightDict + assemble_weights."""
+        by default they are computed for (ft_type, reciprocity_coefficient) like generate_weightDict + assemble_weights.
+        dimensions=2: polar plan (settings `dimensions: 2`): grids are [.., N_r, n_phi] with n_phi = 2*l_max+1
+        (harmonic_transforms.py:44-47,60), coefficients [.., N_r, n_phi] in 'm' order (0..M, -M..-1), hankel_weights
+        [M+1, n_sum, N_r] (calc_polar_mid_weights)."""
+        self.dims = int(dimensions)
+        if self.dims not in (2, 3):
+            raise _lib.XfbError(f"dimensions={dimensions} not supported")
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.XfbError("no CUDA device visible: xframe_b200 has no CPU fallback")
@@ -41,8 +47,11 @@ class Plan:
         torch.cuda.set_device(self.device)
         _lib.check(self.lib.xfb_set_device(self.device.index))
         self.l_max, self.n_r = int(l_max), int(n_r)
-        self.n_theta, self.n_phi = tables.default_angular_sizes(self.l_max, n_theta, n_phi)
         self.max_batch = int(max_batch)
+        if self.dims == 2:
+            self._init_polar(max_q, reciprocity_coefficient, ft_type, hankel_weights, hankel_scales)
+            return
+        self.n_theta, self.n_phi = tables.default_angular_sizes(self.l_max, n_theta, n_phi)
         self.n_lm = (self.l_max + 1) ** 2
         self.rc, self.ft_type, self.max_q = float(reciprocity_coefficient), ft_type, float(max_q)
         self.rs, self.qs = tables.radial_grids(ft_type, self.max_q, self.n_r, self.rc)
@@ -78,6 +87,36 @@ class Plan:
         self.n_batch = 0
         self.initial_support = None
 
+    def _init_polar(self, max_q, rc, ft_type, hankel_weights, hankel_scales):
+        self.n_theta, self.n_phi = 1, 2 * self.l_max + 1
+        self.n_lm = self.n_phi
+        self.rc, self.ft_type, self.max_q = float(rc), ft_type, float(max_q)
+        self.rs, self.qs = tables.radial_grids(ft_type, self.max_q, self.n_r, self.rc)        # ft_grid_pairs.py:274-291 (same radial rule)
+        self.phis = np.arange(self.n_phi) / self.n_phi * 2 * np.pi                            # harmonic_transforms.py:59
+        self.thetas = None
+        w = tables.polar_hankel_weights(self.l_max, self.n_r, self.rc, ft_type) if hankel_weights is None \
+            else np.ascontiguousarray(hankel_weights, dtype=np.float64)
+        if w.ndim != 3 or w.shape[0] != self.l_max + 1 or w.shape[2] != self.n_r or w.shape[1] not in (self.n_r, self.n_r - 1):
+            raise ValueError(f"hankel_weights shape {w.shape} is not [M+1, N_r or N_r-1, N_r]")
+        self.hankel_w = w
+        fs, iscale = tables.polar_hankel_scales(float(np.max(self.rs)), self.n_r, self.rc) if hankel_scales is None \
+            else (float(v) for v in hankel_scales)
+        self.int_weight = tables.polar_integration_weights(self.rs, self.phis)
+        d = _lib.PlanDesc()
+        d.dimensions = 2
+        d.l_max, d.n_r, d.n_theta, d.n_phi, d.max_batch = self.l_max, self.n_r, 1, self.n_phi, self.max_batch
+        d.hankel_skip = self.n_r - w.shape[1]
+        keep = [np.ascontiguousarray(a, dtype=np.float64) for a in
+                (tables.polar_hankel_device_weights(w), self.int_weight, self.rs, self.qs)]
+        d.hankel_w, d.hankel_n_sum = _dp(keep[0]), w.shape[1]
+        d.hankel_fwd_scale, d.hankel_inv_scale = fs, iscale
+        d.int_weight, d.r_points, d.q_points = _dp(keep[1]), _dp(keep[2]), _dp(keep[3])
+        h = C.c_void_p()
+        _lib.check(self.lib.xfb_plan_create(C.byref(h), C.byref(d)))
+        self.h = h
+        self.n_batch = 0
+        self.initial_support = None
+
     def close(self):
         if getattr(self, 'h', None):
             self.lib.xfb_plan_destroy(self.h)
@@ -99,7 +138,11 @@ class Plan:
 
     @property
     def grid_shape(self):
-        return (self.n_r, self.n_theta, self.n_phi)
+        return (self.n_r, self.n_phi) if self.dims == 2 else (self.n_r, self.n_theta, self.n_phi)
+
+    @property
+    def _ang_shape(self):
+        return (self.n_phi,) if self.dims == 2 else (self.n_theta, self.n_phi)
 
     def set_fused_ft_stab(self, on=True):
         """True (default): one inverse transform per ft_stab iteration (linearity of IFT); False: literal sketch."""
@@ -126,8 +169,8 @@ class Plan:
     # ------------------------------------------------------------------ transforms
     def sht_forward(self, grid):
         """sh.forward_d (shtns_plugin.py:250-255): [..., n_theta, n_phi] -> [..., (L+1)^2]."""
-        self._c128(grid, (self.n_theta, self.n_phi))
-        lead = grid.shape[:-2]
+        self._c128(grid, self._ang_shape)
+        lead = grid.shape[:-len(self._ang_shape)]
         n = int(np.prod(lead)) if lead else 1
         out = torch.empty(lead + (self.n_lm,), dtype=torch.complex128, device=grid.device)
         _lib.check(self.lib.xfb_sht_forward(self.h, _ptr(grid), _ptr(out), n, _stream()))
@@ -138,7 +181,7 @@ class Plan:
         self._c128(direct, (self.n_lm,))
         lead = direct.shape[:-1]
         n = int(np.prod(lead)) if lead else 1
-        out = torch.empty(lead + (self.n_theta, self.n_phi), dtype=torch.complex128, device=direct.device)
+        out = torch.empty(lead + self._ang_shape, dtype=torch.complex128, device=direct.device)
         _lib.check(self.lib.xfb_sht_inverse(self.h, _ptr(direct), _ptr(out), n, _stream()))
         return out
 
@@ -192,9 +235,24 @@ class Plan:
         _lib.check(self.lib.xfb_plan_set_projection(self.h, C.byref(d)))
         self._proj_ncols = [int(c) for c in ncols]
 
+    def set_projection_2d(self, projection_matrices, radial_mask, number_of_particles=1.0, so_order_id=None):
+        """projection_matrices: complex [n_orders, N_r], the FINAL V_m(q) (after regrid / odd->0 / V_0 = <I>,
+        fxs_Projections.py:679-706); so_order_id pins u[so_order_id] = 1 (SO_freedom, :743-748)."""
+        v = np.ascontiguousarray(np.asarray(projection_matrices), dtype=np.complex128)
+        if v.ndim != 2 or v.shape[1] != self.n_r or v.shape[0] > self.l_max + 1:
+            raise ValueError(f"projection matrices shape {v.shape} is not [n_orders <= {self.l_max + 1}, {self.n_r}]")
+        rm = np.ascontiguousarray(np.broadcast_to(np.asarray(radial_mask, dtype=bool), (self.l_max + 1, self.n_r)), dtype=np.uint8)
+        _lib.check(self.lib.xfb_plan_set_projection_2d(self.h, v.shape[0], v.ctypes.data_as(C.c_void_p), rm.ctypes.data_as(C.c_void_p),
+                                                       float(np.sqrt(number_of_particles)), -1 if so_order_id is None else int(so_order_id)))
+        self._proj_ncols = [1] * v.shape[0]
+
     def unknowns(self, run):
         """fxs_unknowns of the last invariant projection for one run of the batch: tuple over the used orders of
         complex [n_l, 2l+1] arrays (approximate_unknowns, fxs_Projections.py:752-767)."""
+        if self.dims == 2:
+            t = torch.empty((len(self._proj_ncols),), dtype=torch.complex128, device=self.device)
+            _lib.check(self.lib.xfb_get_unknowns_2d(self.h, int(run), _ptr(t), _stream()))
+            return t.cpu().numpy()
         out = []
         for l, nc in enumerate(self._proj_ncols):
             t = torch.empty((nc, 2 * l + 1), dtype=torch.complex128, device=self.device)

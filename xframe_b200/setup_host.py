@@ -83,11 +83,82 @@ class ProjectionSetup:
         return out
 
 
+class ProjectionSetup2D:
+    """2-D flavour: V_m(q) [n_orders, N_r] complex, radial mask, integrated intensity
+    (fxs_Projections.py:473-474,657-661,679-706,578-629 with dimensions == 2)."""
+
+    def __init__(self, qs, data, m_max, ropt):
+        qs = np.asarray(qs, dtype=np.float64)
+        dq = np.asarray(data['data_radial_points'], dtype=np.float64)
+        avg = np.asarray(getattr(data['average_intensity'], 'data', data['average_intensity']), dtype=np.float64)
+        self.integrated_intensity = float(midpoint_rule(avg * dq, dq) * 2 * np.sqrt(np.pi))            # :473-474
+        used = np.asarray(ropt['used_order_ids'])
+        used = used[(used <= int(data['max_order'])) & (used <= m_max)]
+        n_used = min(len(used), m_max + 1)
+        if list(used[:n_used]) != list(range(n_used)):
+            raise XfbError("xframe_b200 supports used_order_ids = arange(n)")
+        self.n_used = n_used
+        self.number_of_particles = float(ropt['number_of_particles']['initial'])
+        pms = np.asarray(data['data_projection_matrices'])[:n_used]
+        same = dq.shape == qs.shape and bool((dq == qs).all())
+        if not same:
+            from scipy.interpolate import griddata
+            kind = ropt.get('regrid', {}).get('interpolation', 'cubic')
+            avg = griddata(dq[:, None], avg, qs[:, None], method=kind, fill_value=0.0).reshape(len(qs))
+            pms = np.array([griddata(dq[:, None], p, qs[:, None], method=kind, fill_value=0.0).reshape(len(qs)) for p in pms])
+        proj = np.array(pms, dtype=complex)
+        if ropt.get('odd_orders_to_0', False):
+            proj[1::2, :] = 0
+        if ropt.get('use_averaged_intensity', False):
+            proj[0] = avg.astype(complex)
+        self.projection_matrices = proj                                                                # no *2 in 2-D (:710-713 is 3-D only)
+        mopt = ropt.get('q_mask', {'type': 'none'})
+        if mopt['type'] != 'none':
+            raise XfbError("2-D path: only q_mask type 'none' is supported")
+        self.radial_mask = np.ascontiguousarray(np.broadcast_to((qs >= dq.min()) & (qs <= dq.max()), (m_max + 1, len(qs))))
+        so = ropt.get('SO_freedom', {'use': False})
+        if so.get('use', False):
+            raise XfbError("2-D path: projections.reciprocal.SO_freedom.use is not supported yet (set it to False)")
+        self.so_order_id = None
+
+    def apply_to(self, plan, sv_cutoff=None):
+        plan.set_projection_2d(self.projection_matrices, self.radial_mask, self.number_of_particles, self.so_order_id)
+
+    def masked_projection_matrices(self):
+        t = np.array(self.projection_matrices)
+        t[~self.radial_mask[:len(t)]] = 0
+        return t
+
+
+def disk_model_density(plan, centers=None, radius=70.0, densities=(25, 50, 25, 50, 25, 50)):
+    """2-D projection of the bundled tutorial model (settings/simulate_ccd/tutorial.yaml:11-20): six discs."""
+    if centers is None:
+        centers = [(0.0, 0.0)] + [(140.0, k * 2 * np.pi / 5) for k in range(5)]
+    r, p = plan.rs[:, None], plan.phis[None, :]
+    x, y = r * np.cos(p), r * np.sin(p)
+    rho = np.zeros(plan.grid_shape)
+    for (cr, cp), d in zip(centers, densities):
+        rho += d * (np.sqrt((x - cr * np.cos(cp)) ** 2 + (y - cr * np.sin(cp)) ** 2) < radius)
+    return rho
+
+
+def invariants_from_density_2d(plan, density):
+    """I_m(q) of |FT rho|^2 as the 2-D invariants record: V_m(q) = I_m(q), <I>(q) = I_0(q); transforms on the GPU."""
+    import torch
+    d = torch.from_numpy(np.ascontiguousarray(density.astype(complex)))[None].to(plan.device)
+    fd = plan.ft(d)
+    inten = (fd * fd.conj()).real.to(torch.complex128).contiguous()
+    I = plan.sht_forward(inten)[0].cpu().numpy()[:, :plan.l_max + 1]        # rfft half
+    return {'dimensions': 2, 'xray_wavelength': 1.23984, 'average_intensity': I[:, 0].real.copy(), 'data_radial_points': plan.qs.copy(),
+            'data_angular_points': plan.phis.copy(), 'max_order': plan.l_max, 'data_projection_matrices': np.ascontiguousarray(I.T),
+            'number_of_particles': 1}
+
+
 def initial_support(plan, sup_opt):
     """max_radius initial support on the plan's real grid (fxs_Projections.py:137-140)."""
     if sup_opt['type'] != 'max_radius':
         raise XfbError(f"initial_support type '{sup_opt['type']}' is not supported by xframe_b200 (max_radius)")
-    r = plan.rs[:, None, None]
+    r = plan.rs.reshape((-1,) + (1,) * (len(plan.grid_shape) - 1))
     return np.broadcast_to(r < sup_opt['max_radius'], plan.grid_shape).copy()
 
 
@@ -99,7 +170,10 @@ def bump(r, radius, slope):                                      # mathLibrary.p
 
 
 def integrate(plan, values):
-    """SphericalIntegrator.integrate (mathLibrary.py:1223-1235) with the plan's quadrature weights."""
+    """SphericalIntegrator.integrate (mathLibrary.py:1223-1235) / PolarIntegrator.integrate (:1254-1262) with the
+    plan's quadrature weights."""
+    if plan.dims == 2:
+        return float(np.sum(plan.int_weight * values))
     return float(np.sum(plan.int_weight[:, :, None] * values))
 
 
@@ -113,7 +187,7 @@ def density_guess(plan, dopt, particle_radius, integrated_intensity, rng):
     if radius < 0:
         radius = float(plan.rs.max())
     A = 1 + 1 / dopt['random']['SNR'] * rng.random(plan.grid_shape)
-    r = np.broadcast_to(plan.rs[:, None, None], plan.grid_shape)
+    r = np.broadcast_to(plan.rs.reshape((-1,) + (1,) * (len(plan.grid_shape) - 1)), plan.grid_shape)
     density = A * bump(np.ascontiguousarray(r), radius, dopt['bump']['slope'])
     total = integrate(plan, density * density)
     return (density * np.sqrt(integrated_intensity / total)).astype(complex)

@@ -7,7 +7,7 @@ grid; shtns_plugin.py:20,130-133) -- computed here in extended precision and
 rounded once to float64.
 """
 import numpy as np
-from scipy.special import roots_legendre, spherical_jn
+from scipy.special import jv, roots_legendre, spherical_jn
 
 
 def default_angular_sizes(l_max, n_theta=0, n_phi=0):
@@ -133,3 +133,47 @@ def integration_weights(rs, n_theta):
     tw[:-1] += d / 2
     tw[1:] += d / 2
     return np.ascontiguousarray((tw * rs ** 2)[:, None] * (np.pi / n_theta) * w[None, :])
+
+
+# ---------------------------------------------------------------------------------- 2-D (polar) tables
+def polar_hankel_weights(m_max, n_r, rc, mode='midpoint'):
+    """w[m,p,k] = p J_m(p k rc / N), m = 0..M; p is summed.  hankel_transforms.py:412-424 (midpoint), :335-347 (trapz)."""
+    ms = np.arange(m_max + 1)
+    if mode == 'midpoint':
+        ps = np.arange(n_r) + 0.5
+        ks = np.arange(n_r) + 0.5
+    elif mode == 'trapz':
+        ps = np.arange(1, n_r)
+        ks = np.arange(n_r)
+    else:
+        raise ValueError(f"hankel mode '{mode}' is not supported by xframe_b200 (midpoint, trapz)")
+    arg = ks[None, :] * ps[:, None] * rc / n_r
+    return np.ascontiguousarray(ps[None, :, None] * jv(ms[:, None, None], arg[None, :, :]))
+
+
+def polar_hankel_device_weights(w):
+    """[M+1, p, k] -> [2M+1, p, k] in DFT-index order (0..M, -M..-1) with w_{-m} = (-1)^m w_m
+    (J_{-m} = (-1)^m J_m; hankel_transforms.py:441)."""
+    m = np.arange(w.shape[0])
+    neg = ((-1.0) ** m[:0:-1])[:, None, None] * w[:0:-1]
+    return np.ascontiguousarray(np.concatenate((w, neg), axis=0))
+
+
+def polar_hankel_scales(r_max_grid, n_r, rc):
+    """(r_max/N)^2 and (q_max/N)^2, q_max = rc N / r_max (hankel_transforms.py:433-439)."""
+    q_max = rc * n_r / r_max_grid
+    return (r_max_grid / n_r) ** 2, (q_max / n_r) ** 2
+
+
+def polar_integration_weights(rs, phis):
+    """Weights of PolarIntegrator.integrate (mathLibrary.py:1254-1262): trapz over phi (NOT periodic: end points get
+    half weight) then trapz over r of r * (...)  ->  wt[r, phi]."""
+    def trapz_w(x):
+        x = np.asarray(x, dtype=np.float64)
+        w = np.zeros_like(x)
+        d = np.diff(x)
+        w[:-1] += d / 2
+        w[1:] += d / 2
+        return w
+    rs = np.asarray(rs, dtype=np.float64)
+    return np.ascontiguousarray((trapz_w(rs) * rs)[:, None] * trapz_w(phis)[None, :])

@@ -28,8 +28,13 @@ class ProjectWorker:
     def __init__(self, settings, data, n_reconstructions=None, rank=0, world=1, device=None, seeds=None, initial_densities=None):
         self.opt = settings
         self.data = data
-        if settings['dimensions'] != 3:
-            raise XfbError("xframe_b200 implements the 3-D reconstruct path (dimensions: 3)")
+        self.dims = int(settings['dimensions'])
+        if self.dims not in (2, 3):
+            raise XfbError(f"dimensions={settings['dimensions']} is not supported")
+        mods = settings.get('output_density_modifiers', {})
+        if mods.get('shift_to_center', False) or (self.dims == 2 and mods.get('fix_orientation', False)
+                                                   and settings['projections']['reciprocal'].get('SO_freedom', {}).get('use', False)):
+            raise XfbError("output_density_modifiers (shift_to_center / fix_orientation) are not implemented by xframe_b200")
         if not settings['GPU']['use']:
             raise XfbError("GPU.use is False: xframe_b200 has no CPU path (the reference falls back to CPU, reconstruct.py:96-102)")
         if number_of_gpus() == 0:
@@ -51,8 +56,9 @@ class ProjectWorker:
         self.batch = max(1, min(int(batch), max(1, len(self.run_ids))))
         self.plan = Plan(int(g['max_order']), int(g['n_radial_points']), max_q, n_theta=g.get('n_theta', 0), n_phi=g.get('n_phi', 0),
                          reciprocity_coefficient=fto.get('reciprocity_coefficient', np.pi), ft_type=fto['type'],
-                         max_batch=self.batch, device=device)
-        self.proj = S.ProjectionSetup(self.plan.qs, data, self.plan.l_max, settings['projections']['reciprocal'])
+                         max_batch=self.batch, device=device, dimensions=self.dims)
+        setup = S.ProjectionSetup if self.dims == 3 else S.ProjectionSetup2D
+        self.proj = setup(self.plan.qs, data, self.plan.l_max, settings['projections']['reciprocal'])
         self.proj.apply_to(self.plan)
         popt = settings['projections']['real']['projections']
         self.initial_support = S.initial_support(self.plan, popt['support']['initial_support'])
@@ -77,8 +83,9 @@ class ProjectWorker:
     def run(self):
         t0 = time.time()
         plan, out = self.plan, []
-        rs = np.stack(np.meshgrid(plan.rs, plan.thetas, plan.phis, indexing='ij'), axis=-1)
-        qs = np.stack(np.meshgrid(plan.qs, plan.thetas, plan.phis, indexing='ij'), axis=-1)
+        ang = (plan.thetas, plan.phis) if self.dims == 3 else (plan.phis,)
+        rs = np.stack(np.meshgrid(plan.rs, *ang, indexing='ij'), axis=-1)
+        qs = np.stack(np.meshgrid(plan.qs, *ang, indexing='ij'), axis=-1)
         masked_pm = self.proj.masked_projection_matrices()
         for b0 in range(0, len(self.run_ids), self.batch):
             ids = self.run_ids[b0:b0 + self.batch]
@@ -87,10 +94,13 @@ class ProjectWorker:
             # last_deg2_invariant: B_l = I_l I_l^H of the last density (reconstruct.py:757-765,993)
             last = torch.from_numpy(res['last_real']).to(plan.device)
             fd = plan.ft(last)
-            I = plan.sht_forward((fd * fd.conj()).contiguous()).cpu().numpy()
+            I = plan.sht_forward((fd * fd.conj()).real.to(torch.complex128).contiguous()).cpu().numpy()
             unknowns = [plan.unknowns(k) for k in range(len(ids))]      # of the last mtip_start (reconstruct.py:523,1013)
             for k, rid in enumerate(ids):
-                Il = [I[k][:, l * l:(l + 1) * (l + 1)] for l in range(plan.l_max + 1)]
+                if self.dims == 3:
+                    Il = [I[k][:, l * l:(l + 1) * (l + 1)] for l in range(plan.l_max + 1)]
+                else:                                      # B_m = I_m I_m^* (fxs_invariant_tools.py:906-914)
+                    Il = [I[k][:, m:m + 1] for m in range(plan.l_max + 1)]
                 n_it = res['errors'].shape[1]
                 out.append({
                     'run_id': rid,
