@@ -28,13 +28,16 @@ METRIC = "mtip_iterations_per_s_L63_Nr128"
 UNIT = "iterations/s"
 # --workload: 'l63' = BASELINE.json configs[2] (the metric's configuration, default);
 #             'l127' = configs[3] (high resolution: L=127, N_r=256, 128x256, max_q doubled; 64 runs per GPU fit the HBM)
-WORKLOADS = {'l63': (63, 128, 64, 128, 0.322416, 128, "mtip_iterations_per_s_L63_Nr128"),
-             'l127': (127, 256, 128, 256, 0.644832, 64, "mtip_iterations_per_s_L127_Nr256")}
+#             'polar' = configs[4] (fxs 2-D: circular harmonics + polar Hankel, max_order 63 -> 127 angular points, 1024 runs)
+WORKLOADS = {'l63': (63, 128, 64, 128, 0.322416, 128, "mtip_iterations_per_s_L63_Nr128", 3),
+             'l127': (127, 256, 128, 256, 0.644832, 64, "mtip_iterations_per_s_L127_Nr256", 3),
+             'polar': (63, 128, 1, 127, 0.322416, 1024, "mtip_iterations_per_s_2D_M63_Nr128", 2)}
+DIMS = 3
 
 
 def select_workload(name):
-    global L_MAX, N_R, N_THETA, N_PHI, MAX_Q, TOTAL_RUNS, METRIC
-    L_MAX, N_R, N_THETA, N_PHI, MAX_Q, TOTAL_RUNS, METRIC = WORKLOADS[name]
+    global L_MAX, N_R, N_THETA, N_PHI, MAX_Q, TOTAL_RUNS, METRIC, DIMS
+    L_MAX, N_R, N_THETA, N_PHI, MAX_Q, TOTAL_RUNS, METRIC, DIMS = WORKLOADS[name]
 
 
 def peaks():
@@ -91,6 +94,11 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 def algorithmic_bytes(nb):
     G = N_R * N_THETA * N_PHI
+    if DIMS == 2:
+        return {'fft_phi': nb * 2 * G * 16,            # circular-harmonic DFT: one grid in, one coefficient array out (or back)
+                'hankel': nb * 2 * G * 16,
+                'real_update': nb * (4 * G * 16 + G),  # IFT(rho_hat'), IFT(rho_hat), rho_prev in, rho_next out, support mask
+                'pointwise': nb * int(2.5 * G * 16)}
     C = N_R * (L_MAX + 1) ** 2
     A = N_R * (2 * L_MAX + 1) * N_THETA
     return {
@@ -105,6 +113,8 @@ def algorithmic_bytes(nb):
 
 
 def hankel_flops(nb):
+    if DIMS == 2:
+        return nb * 8.0 * N_R * N_R * N_PHI
     return nb * 8.0 * N_R * N_R * (L_MAX + 1) ** 2     # complex x real: 2 real GEMMs, 2 flops per MAC
 
 
@@ -118,7 +128,11 @@ def _cpu_worker(args):
     seed, budget_s = args
     import numpy as np
     from oracle import mtip as O
-    m = O.MTIP(_CPU['settings'], _CPU['data'])
+    if _CPU['dims'] == 2:
+        from oracle import mtip2d as O2
+        m = O2.MTIP2D(_CPU['settings'], _CPU['data'])
+    else:
+        m = O.MTIP(_CPU['settings'], _CPU['data'])
     m.results['errors'] = {'real': {'l2_projection_diff': []}, 'reciprocal': {}, 'main': []}
     rho = m.density_guess(np.random.default_rng(seed))
     rho = m.ift(m.ft(rho))
@@ -142,12 +156,20 @@ def cpu_reference(budget_s=15.0, n_workers=None):
     import numpy as np
     from oracle import mtip as O
     from xframe_b200.settings import tutorial_settings
-    sd = tutorial_settings(grid={'max_q': MAX_Q, 'max_order': L_MAX, 'n_phi': N_PHI, 'n_theta': N_THETA, 'n_radial_points': N_R})
     qs = O.radial_grids('midpoint', MAX_Q, N_R, 2.0)[1]
-    boot = O.MTIP(sd, {'data_radial_points': qs, 'average_intensity': np.ones(N_R), 'max_order': L_MAX,
-                       'data_projection_matrices': [np.zeros((N_R, min(N_R, 2 * l + 1)), complex) for l in range(L_MAX + 1)]})
+    _CPU['dims'] = DIMS
+    if DIMS == 2:
+        from oracle import mtip2d as O2
+        sd = tutorial_settings(dimensions=2, grid={'max_q': MAX_Q, 'max_order': L_MAX, 'n_radial_points': N_R})
+        boot = O2.MTIP2D(sd, {'data_radial_points': qs, 'average_intensity': np.ones(N_R), 'max_order': L_MAX,
+                              'data_projection_matrices': np.zeros((L_MAX + 1, N_R), complex)})
+        _CPU['data'] = O2.invariants_from_density_2d(O2.disk_model_density(boot.real_grid), boot.ft, boot.qs, boot.real_grid[0, :, 1])
+    else:
+        sd = tutorial_settings(grid={'max_q': MAX_Q, 'max_order': L_MAX, 'n_phi': N_PHI, 'n_theta': N_THETA, 'n_radial_points': N_R})
+        boot = O.MTIP(sd, {'data_radial_points': qs, 'average_intensity': np.ones(N_R), 'max_order': L_MAX,
+                           'data_projection_matrices': [np.zeros((N_R, min(N_R, 2 * l + 1)), complex) for l in range(L_MAX + 1)]})
+        _CPU['data'] = O.invariants_from_density(O.six_sphere_density(boot.real_grid), boot.ft, boot.sh, boot.qs)
     _CPU['settings'] = sd
-    _CPU['data'] = O.invariants_from_density(O.six_sphere_density(boot.real_grid), boot.ft, boot.sh, boot.qs)
     if n_workers is None:
         n_workers = len(os.sched_getaffinity(0))
     ctx = mp.get_context('fork')
@@ -193,10 +215,16 @@ def build_problem(nb, device_index, seeds):
     from xframe_b200.plan import Plan
     from xframe_b200 import setup_host as S
     from xframe_b200.settings import tutorial_settings
-    sd = tutorial_settings(grid={'max_q': MAX_Q, 'max_order': L_MAX, 'n_phi': N_PHI, 'n_theta': N_THETA, 'n_radial_points': N_R})
-    plan = Plan(L_MAX, N_R, MAX_Q, n_theta=N_THETA, n_phi=N_PHI, max_batch=nb, device=device_index)
-    data = S.invariants_from_density(plan, S.six_sphere_density(plan))
-    ps = S.ProjectionSetup(plan.qs, data, L_MAX, sd['projections']['reciprocal'])
+    if DIMS == 2:
+        sd = tutorial_settings(dimensions=2, grid={'max_q': MAX_Q, 'max_order': L_MAX, 'n_radial_points': N_R})
+        plan = Plan(L_MAX, N_R, MAX_Q, max_batch=nb, device=device_index, dimensions=2)
+        data = S.invariants_from_density_2d(plan, S.disk_model_density(plan))
+        ps = S.ProjectionSetup2D(plan.qs, data, L_MAX, sd['projections']['reciprocal'])
+    else:
+        sd = tutorial_settings(grid={'max_q': MAX_Q, 'max_order': L_MAX, 'n_phi': N_PHI, 'n_theta': N_THETA, 'n_radial_points': N_R})
+        plan = Plan(L_MAX, N_R, MAX_Q, n_theta=N_THETA, n_phi=N_PHI, max_batch=nb, device=device_index)
+        data = S.invariants_from_density(plan, S.six_sphere_density(plan))
+        ps = S.ProjectionSetup(plan.qs, data, L_MAX, sd['projections']['reciprocal'])
     ps.apply_to(plan)
     popt = sd['projections']['real']['projections']
     plan.set_real(popt['apply'], S.initial_support(plan, popt['support']['initial_support']), popt['value_threshold']['threshold'],
@@ -309,7 +337,7 @@ def run_ours(args):
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_max / K,
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': f'fxs 3D reconstruct: {total} independent MTIP runs (six-sphere tutorial model) at L={L_MAX}/N_r={N_R}, '
+            'config': {'workload': f'fxs {DIMS}D reconstruct: {total} independent MTIP runs (six-sphere tutorial model) at L={L_MAX}/N_r={N_R}, '
                                    f'{N_THETA}x{N_PHI} angular grid, sharded over the GPUs; step = one HIO_ft_stab iteration of every run',
                        'runs_total': total, 'runs_per_gpu': nb, 'l2_policy': 'inputs larger than L2 (per-step working set '
                                                                             f'{nb * (N_R * N_THETA * N_PHI * 16 >> 20) * 11} MiB per GPU)',

@@ -172,7 +172,7 @@ def bump(r, radius, slope):                                      # mathLibrary.p
 def integrate(plan, values):
     """SphericalIntegrator.integrate (mathLibrary.py:1223-1235) / PolarIntegrator.integrate (:1254-1262) with the
     plan's quadrature weights."""
-    if plan.dims == 2:
+    if getattr(plan, 'dims', 3) == 2:
         return float(np.sum(plan.int_weight * values))
     return float(np.sum(plan.int_weight[:, :, None] * values))
 
