@@ -77,33 +77,43 @@ __device__ __forceinline__ double2 shfl_d2(double2 v, int src_lane) {
     return v;
 }
 
-// rotation of the column pair (x, y) held by one 8-lane group: returns (cs, sn) with x' = cs x - sn y, y' = sn x + cs y;
-// (1, 0) when the pair is skipped.  Symmetric under exchanging the roles of x and y (sn changes sign), so two lane
-// groups that hold the same pair with swapped roles take bitwise-consistent decisions.
+// rotation of the column pair (x, y) held by one 8-lane group: (cs, sn) with x' = cs x - sn y, y' = sn x + cs y, and
+// tapq = tan(theta) * (x.y), the change of the squared norms (|x'|^2 = |x|^2 - tapq, |y'|^2 = |y|^2 + tapq);
+// (1, 0, 0) when the pair is skipped.  The squared norms app, aqq are CACHED by the caller (computed when the columns
+// are loaded, updated after every rotation), so a pair costs one dot product instead of three.  Symmetric under
+// exchanging the roles of x and y (sn and tapq change sign), so two lane groups that hold the same pair with swapped
+// roles take bitwise-consistent decisions.
+struct JRot { double cs, sn, tapq; };
 template <int NV>
-__device__ __forceinline__ double2 jacobi_pair_params(const double2 (&x)[NV], const double2 (&y)[NV], bool valid, double thr, double tol) {
-    double app = 0.0, aqq = 0.0, apq = 0.0, app2 = 0.0, aqq2 = 0.0, apq2 = 0.0;
+__device__ __forceinline__ JRot jacobi_pair_params(const double2 (&x)[NV], const double2 (&y)[NV], double app, double aqq, bool valid,
+                                                   double thr, double tol) {
+    double apq = 0.0, apq2 = 0.0;
 #pragma unroll
-    for (int t = 0; t < NV; ++t) {
-        app += x[t].x * x[t].x; aqq += y[t].x * y[t].x; apq += x[t].x * y[t].x;
-        app2 += x[t].y * x[t].y; aqq2 += y[t].y * y[t].y; apq2 += x[t].y * y[t].y;
-    }
-    app += app2; aqq += aqq2; apq += apq2;
+    for (int t = 0; t < NV; ++t) { apq += x[t].x * y[t].x; apq2 += x[t].y * y[t].y; }
+    apq += apq2;
 #pragma unroll
-    for (int off = JG / 2; off > 0; off >>= 1) {
-        app += __shfl_xor_sync(0xffffffffu, app, off);
-        aqq += __shfl_xor_sync(0xffffffffu, aqq, off);
-        apq += __shfl_xor_sync(0xffffffffu, apq, off);
-    }
+    for (int off = JG / 2; off > 0; off >>= 1) apq += __shfl_xor_sync(0xffffffffu, apq, off);
     bool rot = valid && (app > thr) && (aqq > thr);
     if (rot) rot = apq * apq > (tol * tol) * (app * aqq);
-    if (!rot) return make_double2(1.0, 0.0);
+    if (!rot) return JRot{1.0, 0.0, 0.0};
     // tan(2 theta) = 2 apq / (aqq - app), |theta| <= pi/4 (same rotation as the textbook zeta/t form)
     const double d = aqq - app, s2 = 2.0 * apq;
     const double rh = rsqrt(d * d + s2 * s2);
     const double u = 0.5 + 0.5 * fabs(d) * rh;            // cos^2(theta)
-    const double rc = rsqrt(u);
-    return make_double2(u * rc, copysign(0.5 * s2 * rh, d * s2) * rc);   // cos, sin(2 theta) / (2 cos theta)
+    const double rc = rsqrt(u);                            // 1 / cos(theta)
+    const double sn = copysign(0.5 * s2 * rh, d * s2) * rc;   // sin(2 theta) / (2 cos theta)
+    return JRot{u * rc, sn, sn * rc * apq};
+}
+
+template <int NV>
+__device__ __forceinline__ double jacobi_col_norm2(const double2 (&x)[NV]) {
+    double a = 0.0, a2 = 0.0;
+#pragma unroll
+    for (int t = 0; t < NV; ++t) { a += x[t].x * x[t].x; a2 += x[t].y * x[t].y; }
+    a += a2;
+#pragma unroll
+    for (int off = JG / 2; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+    return a;
 }
 
 template <int NV>
@@ -150,6 +160,7 @@ __device__ __forceinline__ void jacobi_g_pass(double* Gs, int ldg, const int* __
     double2 x[NV2], y[NV2];
     jacobi_load_col<NV2>(x, Gs, (long long)ca * ldg, sub, va);
     jacobi_load_col<NV2>(y, Gs, (long long)(vb0 ? list[pb0] : 0) * ldg, sub, vb0);
+    double nx = jacobi_col_norm2<NV2>(x), ny = jacobi_col_norm2<NV2>(y);      // cached squared norms, travel with the columns
     if (intra) {
 #pragma unroll
         for (int t = 0; t < 3; ++t) {                             // pairs inside A: partner group = grp ^ (t+1)
@@ -157,13 +168,15 @@ __device__ __forceinline__ void jacobi_g_pass(double* Gs, int ldg, const int* __
             double2 z[NV2];
 #pragma unroll
             for (int k = 0; k < NV2; ++k) z[k] = shfl_d2(x[k], lane ^ (8 * (t + 1)));
-            const double2 cs = jacobi_pair_params<NV2>(x, z, va && vp, thr, tol);
-            if (cs.y != 0.0) {
+            const double nz = __shfl_sync(0xffffffffu, nx, lane ^ (8 * (t + 1)));
+            const JRot R = jacobi_pair_params<NV2>(x, z, nx, nz, va && vp, thr, tol);
+            if (R.sn != 0.0) {
                 any_rot = true;
 #pragma unroll
-                for (int k = 0; k < NV2; ++k) x[k] = make_double2(cs.x * x[k].x - cs.y * z[k].x, cs.x * x[k].y - cs.y * z[k].y);
+                for (int k = 0; k < NV2; ++k) x[k] = make_double2(R.cs * x[k].x - R.sn * z[k].x, R.cs * x[k].y - R.sn * z[k].y);
+                nx -= R.tapq;
             }
-            if (sub == 0) rb[t * 4 + grp] = cs;
+            if (sub == 0) rb[t * 4 + grp] = make_double2(R.cs, R.sn);
         }
 #pragma unroll
         for (int t = 0; t < 3; ++t) {                             // pairs inside B
@@ -171,32 +184,36 @@ __device__ __forceinline__ void jacobi_g_pass(double* Gs, int ldg, const int* __
             double2 z[NV2];
 #pragma unroll
             for (int k = 0; k < NV2; ++k) z[k] = shfl_d2(y[k], lane ^ (8 * (t + 1)));
-            const double2 cs = jacobi_pair_params<NV2>(y, z, vb0 && vp, thr, tol);
-            if (cs.y != 0.0) {
+            const double nz = __shfl_sync(0xffffffffu, ny, lane ^ (8 * (t + 1)));
+            const JRot R = jacobi_pair_params<NV2>(y, z, ny, nz, vb0 && vp, thr, tol);
+            if (R.sn != 0.0) {
                 any_rot = true;
 #pragma unroll
-                for (int k = 0; k < NV2; ++k) y[k] = make_double2(cs.x * y[k].x - cs.y * z[k].x, cs.x * y[k].y - cs.y * z[k].y);
+                for (int k = 0; k < NV2; ++k) y[k] = make_double2(R.cs * y[k].x - R.sn * z[k].x, R.cs * y[k].y - R.sn * z[k].y);
+                ny -= R.tapq;
             }
-            if (sub == 0) rb[(3 + t) * 4 + grp] = cs;
+            if (sub == 0) rb[(3 + t) * 4 + grp] = make_double2(R.cs, R.sn);
         }
     }
 #pragma unroll
     for (int s = 0; s < 4; ++s) {                                 // cross pairs (A_g, B_(g+s)%4)
         const bool vb = (bb * 4 + ((grp + s) & 3)) < nact;
-        const double2 cs = jacobi_pair_params<NV2>(x, y, va && vb, thr, tol);
-        if (cs.y != 0.0) {
+        const JRot R = jacobi_pair_params<NV2>(x, y, nx, ny, va && vb, thr, tol);
+        if (R.sn != 0.0) {
             any_rot = true;
 #pragma unroll
             for (int k = 0; k < NV2; ++k) {
                 const double2 a = x[k], b = y[k];
-                x[k] = make_double2(cs.x * a.x - cs.y * b.x, cs.x * a.y - cs.y * b.y);
-                y[k] = make_double2(cs.y * a.x + cs.x * b.x, cs.y * a.y + cs.x * b.y);
+                x[k] = make_double2(R.cs * a.x - R.sn * b.x, R.cs * a.y - R.sn * b.y);
+                y[k] = make_double2(R.sn * a.x + R.cs * b.x, R.sn * a.y + R.cs * b.y);
             }
+            nx -= R.tapq; ny += R.tapq;
         }
-        if (sub == 0) rb[(6 + s) * 4 + grp] = cs;
+        if (sub == 0) rb[(6 + s) * 4 + grp] = make_double2(R.cs, R.sn);
         if (s < 3) {
 #pragma unroll
             for (int k = 0; k < NV2; ++k) y[k] = shfl_d2(y[k], (lane + 8) & 31);       // B columns move to the previous group
+            ny = __shfl_sync(0xffffffffu, ny, (lane + 8) & 31);
         }
     }
     jacobi_store_col<NV2>(x, Gs, (long long)ca * ldg, sub, va);
@@ -353,16 +370,22 @@ __global__ void __launch_bounds__(THREADS, 1) procrustes_jacobi_kernel(const dou
                                                                        int n_orders, int n_batch, int n_r_grid, long long g_run_stride,
                                                                        long long vw_run_stride, long long sig_run_stride, double sv_cutoff,
                                                                        double tol, int max_sweeps, int* __restrict__ sweeps_out,
-                                                                       int smem_doubles) {
+                                                                       int smem_doubles, int* __restrict__ work_counter) {
     extern __shared__ __align__(16) double smem_j[];
-    __shared__ int s_nact, s_rot;
+    __shared__ int s_nact, s_rot, s_prob;
     __shared__ double s_thr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = THREADS >> 5;
     const int wld = jacobi_wstride(n_r_grid);
     double2* rotbuf = reinterpret_cast<double2*>(smem_j);                 // [2][JROT_SLOTS][JROT_RB]
     const int fixed = 2 * 2 * JROT_SLOTS * JROT_RB;                       // doubles
 
-    for (int prob = blockIdx.x; prob < n_orders * n_batch; prob += gridDim.x) {
+    // dynamic work queue (largest problems first): a CTA fetches the next problem when it is done with the previous one
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_prob = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int prob = s_prob;
+        if (prob >= n_orders * n_batch) break;
         const int oi = prob / n_batch;                     // orders are sorted largest first
         const int b = prob - oi * n_batch;
         const ProcOrder o = orders[oi];

@@ -9,6 +9,7 @@
 #include "polar.cuh"
 
 #include <algorithm>
+#include <map>
 
 thread_local std::string g_xfb_err;
 
@@ -38,7 +39,9 @@ struct xfb_plan {
     // host-buffer pipeline (xfb_mtip_step_host)
     cudaStream_t s_in = nullptr, s_out = nullptr; cudaEvent_t ev_start = nullptr; std::vector<cudaEvent_t> ev_in, ev_comp;
     double2* stage_out = nullptr; int host_chunk = 16;
-    HankelTile* hk_tiles = nullptr; int hk_tiles_n = 0, hk_tiles_nb = -1, hk_tiles_cap = 0;
+    HankelTile* hk_tiles = nullptr; int hk_tiles_n = 0;
+    std::map<int, std::pair<HankelTile*, int>> hk_cache;     // tile lists per batch size (the host pipeline uses several chunk sizes)
+
     // projection
     bool has_proj = false;
     std::vector<ProcOrder> orders;
@@ -55,8 +58,8 @@ struct xfb_plan {
     double *xt = nullptr, *tt = nullptr, *g = nullptr, *gn = nullptr, *vw = nullptr, *sigma = nullptr;
     int* sweeps_dev = nullptr;
     GemmProblem *gemmM_dev = nullptr, *gemmT_dev = nullptr; int *gemmM_tp = nullptr, *gemmT_tp = nullptr;
-    int gemmM_tiles = 0, gemmT_tiles = 0, gemm_nb = -1;
-    size_t jacobi_smem = 0; int n_sm = 148; bool jacobi_big = false;
+    int gemmM_tiles = 0, gemmT_tiles = 0, gemm_nb = -1, gemmM_tiles_run = 0, gemmT_tiles_run = 0;
+    size_t jacobi_smem = 0; int n_sm = 148; bool jacobi_big = false; int* jac_counter = nullptr;
     // real projection
     bool has_real = false; RealDesc rd{}; uint8_t* init_support_dev = nullptr;
     // loop state
@@ -195,10 +198,11 @@ int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
 int xfb_plan_destroy(xfb_plan* p) {
     if (!p) return 0;
     void* ptrs[] = {p->tw, p->FE, p->FO, p->IE, p->IO, p->hankel_w, p->int_wt, p->q_pts, p->A0, p->C0, p->C1, p->W0, p->W1, p->W2, p->A0s, p->C0s, p->rt0, p->stage_out,
-                    p->hk_tiles, p->v2d, p->unk2d, p->orders_dev, p->kind_dev, p->act_index_dev, p->radial_mask_dev, p->v0_dev, p->pd_dev, p->vt_dev,
-                    p->xt, p->tt, p->g, p->gn, p->vw, p->sigma, p->sweeps_dev, p->ident_dev, p->gn_u, p->vw_u, p->sigma_u, p->i00, p->gemmM_dev, p->gemmT_dev, p->gemmM_tp, p->gemmT_tp,
+                    p->v2d, p->unk2d, p->orders_dev, p->kind_dev, p->act_index_dev, p->radial_mask_dev, p->v0_dev, p->pd_dev, p->vt_dev,
+                    p->xt, p->tt, p->g, p->gn, p->vw, p->sigma, p->sweeps_dev, p->jac_counter, p->ident_dev, p->gn_u, p->vw_u, p->sigma_u, p->i00, p->gemmM_dev, p->gemmT_dev, p->gemmM_tp, p->gemmT_tp,
                     p->init_support_dev, p->rho_pool, p->rh_pool, p->mask_pool, p->ls_ints, p->ls_dbl, p->partial, p->err, p->mm};
     for (void* q : ptrs) if (q) cudaFree(q);
+    for (auto& kv : p->hk_cache) cudaFree(kv.second.first);
     for (auto& e : p->prof_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto e : p->ev_in) cudaEventDestroy(e);
     for (auto e : p->ev_comp) cudaEventDestroy(e);
@@ -268,7 +272,8 @@ static int sht_inverse_i(xfb_plan* p, const double2* c_in, double2* grid_out, in
     return 0;
 }
 static int hankel_i(xfb_plan* p, int dir, const double2* c_in, double2* c_out, int nb, cudaStream_t st) {
-    if (p->hk_tiles_nb != nb) {
+    auto hit = p->hk_cache.find(nb);
+    if (hit == p->hk_cache.end()) {
         std::vector<HankelTile> tiles;
         if (p->dims == 2) {
             // one weight matrix per DFT index j; order m = j (j <= M) or j - N: (-i)^m = (-i)^(m mod 4)
@@ -283,15 +288,13 @@ static int hankel_i(xfb_plan* p, int dir, const double2* c_in, double2* c_out, i
                 for (int r = r0; r < r1; r += HK_BM) tiles.push_back(HankelTile{l, r, r1, l & 3});
             }
         }
-        if ((int)tiles.size() > p->hk_tiles_cap) {
-            if (p->hk_tiles) cudaFree(p->hk_tiles);
-            p->hk_tiles_cap = (int)tiles.size();
-            XFB_CUDA(cudaMalloc((void**)&p->hk_tiles, tiles.size() * sizeof(HankelTile)));
-        }
-        XFB_CUDA(cudaMemcpyAsync(p->hk_tiles, tiles.data(), tiles.size() * sizeof(HankelTile), cudaMemcpyHostToDevice, st));
+        HankelTile* dev = nullptr;
+        XFB_CUDA(cudaMalloc((void**)&dev, tiles.size() * sizeof(HankelTile)));
+        XFB_CUDA(cudaMemcpyAsync(dev, tiles.data(), tiles.size() * sizeof(HankelTile), cudaMemcpyHostToDevice, st));
         XFB_CUDA(cudaStreamSynchronize(st));
-        p->hk_tiles_n = (int)tiles.size(); p->hk_tiles_nb = nb;
+        hit = p->hk_cache.emplace(nb, std::make_pair(dev, (int)tiles.size())).first;
     }
+    p->hk_tiles = hit->second.first; p->hk_tiles_n = hit->second.second;
     dim3 g(p->hk_tiles_n, cdiv(p->n_r, HK_BN));
     XFB_LAUNCH(p, PG_HANKEL, st,
                hankel_kernel<<<g, 256, 0, st>>>(c_in, c_out, p->hankel_w, p->hk_tiles, p->n_r, p->hankel_n_sum, p->hankel_skip,
@@ -318,8 +321,14 @@ static int ift_shell0_i(xfb_plan* p, const double2* c, int nb, cudaStream_t st) 
     return 0;
 }
 
-static int build_gemm_groups(xfb_plan* p, int nb, cudaStream_t st) {
-    if (p->gemm_nb == nb) return 0;
+// Problem descriptors of the two grouped GEMMs, built ONCE for the plan capacity: the list is run-major, so the
+// descriptors (and tile ids) of a smaller batch are a prefix of it.
+static int build_gemm_groups(xfb_plan* p, int nb_req, cudaStream_t st) {
+    if (p->gemm_nb > 0) {
+        p->gemmM_tiles = nb_req * p->gemmM_tiles_run; p->gemmT_tiles = nb_req * p->gemmT_tiles_run;
+        return 0;
+    }
+    const int nb = p->max_batch;
     std::vector<GemmProblem> pm, pt; std::vector<int> tpm, tpt;
     for (int b = 0; b < nb; ++b) {
         for (const ProcOrder& o : p->orders) {
@@ -346,7 +355,8 @@ static int build_gemm_groups(xfb_plan* p, int nb, cudaStream_t st) {
     XFB_CUDA(cudaMemcpyAsync(p->gemmM_tp, tpm.data(), tpm.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     XFB_CUDA(cudaMemcpyAsync(p->gemmT_tp, tpt.data(), tpt.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     XFB_CUDA(cudaStreamSynchronize(st));
-    p->gemmM_tiles = (int)tpm.size(); p->gemmT_tiles = (int)tpt.size(); p->gemm_nb = nb;
+    p->gemmM_tiles_run = (int)tpm.size() / nb; p->gemmT_tiles_run = (int)tpt.size() / nb; p->gemm_nb = nb;
+    p->gemmM_tiles = nb_req * p->gemmM_tiles_run; p->gemmT_tiles = nb_req * p->gemmT_tiles_run;
     return 0;
 }
 
@@ -356,12 +366,14 @@ static int launch_jacobi(xfb_plan* p, const double* g, double* gn, double* vw, c
     const int na = (int)p->orders.size();
     const int grid = std::min(na * nb, p->n_sm);
     const int smem_doubles = (int)(p->jacobi_smem / 8);
+    if (!p->jac_counter) { if (dev_alloc(p, &p->jac_counter, 1)) return 1; }
+    XFB_CUDA(cudaMemsetAsync(p->jac_counter, 0, sizeof(int), st));
     if (p->jacobi_big)
         procrustes_jacobi_kernel<16, 256><<<grid, 256, p->jacobi_smem, st>>>(g, gn, vw, vt, sigma, p->orders_dev, na, nb, p->n_r, p->g_run, p->vw_run,
-                                                                            (long long)na * p->n_r, p->sv_cutoff, 1e-15, p->max_sweeps, sweeps, smem_doubles);
+                                                                            (long long)na * p->n_r, p->sv_cutoff, 1e-15, p->max_sweeps, sweeps, smem_doubles, p->jac_counter);
     else
         procrustes_jacobi_kernel<8, 512><<<grid, 512, p->jacobi_smem, st>>>(g, gn, vw, vt, sigma, p->orders_dev, na, nb, p->n_r, p->g_run, p->vw_run,
-                                                                           (long long)na * p->n_r, p->sv_cutoff, 1e-15, p->max_sweeps, sweeps, smem_doubles);
+                                                                           (long long)na * p->n_r, p->sv_cutoff, 1e-15, p->max_sweeps, sweeps, smem_doubles, p->jac_counter);
     XFB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -844,8 +856,25 @@ int xfb_mtip_step_host(xfb_plan* p, int32_t method, int32_t ft_stab, double beta
         XFB_CUDA(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
         if (dev_alloc(p, &p->stage_out, (size_t)p->max_batch * p->G)) return 1;
     }
-    const int cs = pipelined ? p->host_chunk : nb;
-    const int nchunk = cdiv(nb, cs);
+    // chunk schedule: full chunks of host_chunk runs in the middle, tapered at both ends (1/4, 1/2) so that the exposed
+    // first copy-in and last copy-out of the three-stage pipeline (copy-in | iterate | copy-out) are short
+    std::vector<int> sizes;
+    if (!pipelined) sizes.push_back(nb);
+    else {
+        const int cs = p->host_chunk;
+        std::vector<int> head, tail;
+        int left = nb;
+        for (int f = 4; f >= 2 && left > 4 * cs; f /= 2) {
+            const int h = std::max(1, cs / f);
+            head.push_back(h); tail.insert(tail.begin(), h); left -= 2 * h;
+        }
+        sizes = head;
+        while (left > 0) { const int n = std::min(cs, left); sizes.push_back(n); left -= n; }
+        sizes.insert(sizes.end(), tail.begin(), tail.end());
+    }
+    const int nchunk = (int)sizes.size();
+    std::vector<int> first(nchunk, 0);
+    for (int c = 1; c < nchunk; ++c) first[c] = first[c - 1] + sizes[c - 1];
     while ((int)p->ev_in.size() < nchunk) {
         cudaEvent_t a, b;
         XFB_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
@@ -859,14 +888,14 @@ int xfb_mtip_step_host(xfb_plan* p, int32_t method, int32_t ft_stab, double beta
     const double2* hin = (const double2*)rho_in_host;
     double2* hout = (double2*)rho_out_host;
     for (int c = 0; c < nchunk; ++c) {
-        const int b0 = c * cs, n = std::min(cs, nb - b0);
+        const int b0 = first[c], n = sizes[c];
         const size_t off = (size_t)b0 * p->G, bytes = (size_t)n * p->G * sizeof(double2);
         XFB_CUDA(cudaMemcpyAsync(p->W2 + off, hin + off, bytes, cudaMemcpyHostToDevice, p->s_in));
         XFB_CUDA(cudaEventRecord(p->ev_in[c], p->s_in));
     }
     const long long pool_stride = (long long)p->max_batch * p->G;
     for (int c = 0; c < nchunk; ++c) {
-        const int b0 = c * cs, n = std::min(cs, nb - b0);
+        const int b0 = first[c], n = sizes[c];
         const size_t off = (size_t)b0 * p->G, bytes = (size_t)n * p->G * sizeof(double2);
         XFB_CUDA(cudaStreamWaitEvent(st, p->ev_in[c], 0));
         SlotView cur; cur.base = p->rho_pool + off; cur.slot = p->ls.rho_cur + b0; cur.slot_stride = pool_stride; cur.run_stride = p->G;
