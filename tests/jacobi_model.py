@@ -68,3 +68,63 @@ def jacobi_project(V, qs, Il, eps=1e-15, tol=1e-15, max_sweeps=40):
     keep = (nrm2 > eps * eps * nrm2.max()) & (nrm2 > 0)
     Gn = np.where(keep[None, :], G / np.sqrt(np.where(keep, nrm2, 1.0))[None, :], 0.0)
     return to_cplx(P @ Gn.T), sweeps
+
+
+def mgs2(A):
+    """Column modified Gram-Schmidt with re-orthogonalisation (csrc/procrustes.cuh:mgs2_qr): Q, R."""
+    A = A.copy()
+    m, r = A.shape
+    R, Q = np.zeros((r, r)), np.zeros((m, r))
+    for j in range(r):
+        nrm = np.sqrt(A[:, j] @ A[:, j])
+        q = A[:, j] / nrm if nrm > 0 else np.zeros(m)
+        Q[:, j], R[j, j] = q, nrm
+        for _ in range(2):
+            c = q @ A[:, j + 1:]
+            A[:, j + 1:] -= np.outer(q, c)
+            R[j, j + 1:] += c
+    return Q, R
+
+
+def qr_polar(V, qs, Il, eps=1e-15, tol=1e-15, max_sweeps=40):
+    """numpy model of the QR-preconditioned device algorithm (csrc/procrustes.cuh:jacobi_qr_problem):
+    G_a = Q1 R1, R1^T = Q2 R2, Jacobi on L = R2^T with W = Q2 rotated along, polar(G_a) = Q1 U~ W^T.
+    Returns T = V polar(V^T D^2 X) as complex coefficients [N_r, 2l+1] and the number of sweeps."""
+    V = np.asarray(V).real
+    M = (V.T * qs[None, :] ** 2) @ to_real(Il)
+    G = M.T.copy()
+    nrm = (G * G).sum(0)
+    act = np.nonzero(nrm > eps * eps * nrm.max())[0]
+    Q1, R1 = mgs2(G[:, act])
+    Q2, R2 = mgs2(R1.T.copy())
+    L, W = R2.T.copy(), Q2.copy()
+    r = L.shape[1]
+    sweeps = 0
+    for sweeps in range(1, max_sweeps + 1):
+        n2 = (L * L).sum(0)
+        thr = eps * eps * n2.max()
+        lst = [c for c in range(r) if n2[c] > thr]
+        rot = False
+        for i in range(len(lst)):
+            for j in range(i + 1, len(lst)):
+                p, q = lst[i], lst[j]
+                a, b = L[:, p].copy(), L[:, q].copy()
+                app, aqq, apq = a @ a, b @ b, a @ b
+                if app <= thr or aqq <= thr or abs(apq) <= tol * np.sqrt(app * aqq):
+                    continue
+                zeta = (aqq - app) / (2 * apq)
+                t = (1.0 if zeta >= 0 else -1.0) / (abs(zeta) + np.sqrt(1 + zeta * zeta))
+                c = 1 / np.sqrt(1 + t * t)
+                s = c * t
+                L[:, p], L[:, q] = c * a - s * b, s * a + c * b
+                wa, wb = W[:, p].copy(), W[:, q].copy()
+                W[:, p], W[:, q] = c * wa - s * wb, s * wa + c * wb
+                rot = True
+        if not rot:
+            break
+    n2 = (L * L).sum(0)
+    keep = (n2 > eps * eps * n2.max()) & (n2 > 0)
+    U = np.where(keep[None, :], L / np.sqrt(np.where(keep, n2, 1.0))[None, :], 0.0)
+    P = U @ W.T                                  # polar(R1)
+    Tt = Q1 @ (P @ V.T[act])                     # [2l+1, N_r]
+    return to_cplx(Tt.T), sweeps

@@ -10,7 +10,7 @@ from oracle import mtip as O
 from oracle.sht import normalized_legendre, gauss_grid
 from xframe_b200 import tables, ramps, setup_host as S, settings as ST
 from xframe_b200.reconstruct import run_schedule, iteration_count
-from jacobi_model import jacobi_project
+from jacobi_model import jacobi_project, qr_polar
 
 
 def test_library_exports_every_declared_symbol():
@@ -203,3 +203,7 @@ def test_jacobi_algorithm_reproduces_reference_projection(tag):
         assert rel_l2(T, Ip[l]) < 1e-6, (l, rel_l2(T, Ip[l]))
         if l <= 4:
             assert rel_l2(T, Ip[l]) < 1e-10
+        # QR-preconditioned variant (the path the 512-thread kernel takes): same answer, fewer sweeps
+        Tq, sweeps_q = qr_polar(m.rp.projection_matrices[l], m.qs, I[l])
+        assert sweeps_q <= sweeps and rel_l2(Tq, Ip[l]) < 1e-6, (l, sweeps_q, sweeps, rel_l2(Tq, Ip[l]))
+        assert rel_l2(Tq, T) < 1e-7

@@ -288,7 +288,7 @@ __device__ __forceinline__ bool jacobi_w_pass(double* Wb, int wld, bool w_compac
 //  * fewer block pairs than warps: the warps split into a G team (pass 1 of round r) and a W team (pass 2 of round
 //    r-1, from the double-buffered rotation parameters) that run concurrently -- G and W are independent data.
 #define JROT_RB (JROT_STEPS * 4 + 1)
-#define JROT_SLOTS 32
+#define JROT_SLOTS 32          // block pairs per round with parameter slots (n <= 256 columns -> <= 32 block pairs)
 template <int NV2, int WV2>
 __device__ __forceinline__ void jacobi_sweep_blocked(double* Gs, int ldg, double* Wb, int wld, bool w_compact, const int* __restrict__ list,
                                                      int nact, double thr, double tol, double2* rotbuf, int* s_rot) {
@@ -344,6 +344,73 @@ __device__ __forceinline__ void jacobi_sweep_dispatch(double* Gs, int ldg, doubl
     else jacobi_sweep_blocked<8, 8>(Gs, ldg, Wb, wld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
 }
 
+// same, for the QR-preconditioned path: G = L (r x r, columns padded to ldl = 64 / 96 / 128) and the accumulator has the
+// same column length (it starts as Q2, see below)
+__device__ __forceinline__ void jacobi_sweep_dispatch_sq(double* Gs, double* Wb, int ldl, const int* list, int nact, double thr, double tol,
+                                                         double2* rotbuf, int* s_rot) {
+    if (ldl <= 64) jacobi_sweep_blocked<4, 4>(Gs, ldl, Wb, ldl, false, list, nact, thr, tol, rotbuf, s_rot);
+    else if (ldl <= 96) jacobi_sweep_blocked<6, 6>(Gs, ldl, Wb, ldl, false, list, nact, thr, tol, rotbuf, s_rot);
+    else jacobi_sweep_blocked<8, 8>(Gs, ldl, Wb, ldl, false, list, nact, thr, tol, rotbuf, s_rot);
+}
+
+// QR factorisation by modified Gram-Schmidt with re-orthogonalisation ("twice is enough"), whole CTA.
+//   A [r][lda]: r columns (zero padded), overwritten by the orthonormal Q (a column that vanishes becomes 0);
+//   Rt [r][ldr]: Rt[j][k] = R[j][k] (k >= j), i.e. column j of R^T -- the column storage of the NEXT factorisation step.
+// Step j: column j is already orthogonal to q_0..q_{j-1}; it is normalised, then every later column k gets
+// a_k -= (q_j.a_k) q_j twice, one 8-lane group per column, both passes on registers.
+template <int NV>
+__device__ __forceinline__ void mgs2_qr(double* A, int lda, int r, double* Rt, int ldr) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const int grp = lane >> 3, sub = lane & (JG - 1);
+    for (int i = tid; i < r * ldr; i += blockDim.x) Rt[i] = 0.0;
+    __syncthreads();
+    for (int j = 0; j < r; ++j) {
+        if (warp == 0) {                                   // normalise column j (group 0 does the work, all lanes shuffle)
+            double2 x[NV];
+            jacobi_load_col<NV>(x, A, (long long)j * lda, sub, grp == 0);
+            const double n2 = jacobi_col_norm2<NV>(x);
+            const double nrm = sqrt(n2), inv = (nrm > 0.0) ? 1.0 / nrm : 0.0;
+#pragma unroll
+            for (int t = 0; t < NV; ++t) { x[t].x *= inv; x[t].y *= inv; }
+            jacobi_store_col<NV>(x, A, (long long)j * lda, sub, grp == 0);
+            if (lane == 0) Rt[(size_t)j * ldr + j] = nrm;
+        }
+        __syncthreads();
+        for (int k0 = j + 1 + warp * 4; k0 < r; k0 += nwarp * 4) {      // warp-uniform trip count
+            const int k = k0 + grp;
+            const bool v = k < r;
+            double2 q[NV], a[NV];
+            jacobi_load_col<NV>(q, A, (long long)j * lda, sub, true);
+            jacobi_load_col<NV>(a, A, (long long)(v ? k : j) * lda, sub, v);
+            double c_tot = 0.0;
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                double c = 0.0, c2 = 0.0;
+#pragma unroll
+                for (int t = 0; t < NV; ++t) { c += q[t].x * a[t].x; c2 += q[t].y * a[t].y; }
+                c += c2;
+#pragma unroll
+                for (int off = JG / 2; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+#pragma unroll
+                for (int t = 0; t < NV; ++t) { a[t].x -= c * q[t].x; a[t].y -= c * q[t].y; }
+                c_tot += c;
+            }
+            jacobi_store_col<NV>(a, A, (long long)k * lda, sub, v);
+            if (v && sub == 0) Rt[(size_t)j * ldr + k] = c_tot;
+        }
+        __syncthreads();
+    }
+}
+__device__ __forceinline__ void mgs2_qr_dispatch(double* A, int lda, int r, double* Rt, int ldr) {
+    if (lda <= 64) mgs2_qr<4>(A, lda, r, Rt, ldr);
+    else if (lda <= 96) mgs2_qr<6>(A, lda, r, Rt, ldr);
+    else mgs2_qr<8>(A, lda, r, Rt, ldr);
+}
+
+// column norms of Gs -> nrm2, ordered list of the columns above the cut-off -> list, their number -> *s_nact
+__device__ __forceinline__ void jacobi_active_list(const double* Gs, int ldg, int n, double* nrm2, int* list, double sv_cutoff, int* s_nact,
+                                                   double* s_thr, int* s_rot);
+
 // squared norms of the n columns (one 8-lane group per column)
 __device__ __forceinline__ void jacobi_col_norms(const double* Gs, int ldg, int n, double* nrm2) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -361,9 +428,126 @@ __device__ __forceinline__ void jacobi_col_norms(const double* Gs, int ldg, int 
     }
 }
 
+__device__ __forceinline__ void jacobi_active_list(const double* Gs, int ldg, int n, double* nrm2, int* list, double sv_cutoff, int* s_nact,
+                                                   double* s_thr, int* s_rot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    jacobi_col_norms(Gs, ldg, n, nrm2);
+    __syncthreads();
+    if (warp == 0) {
+        double mx = 0.0;
+        for (int c = lane; c < n; c += 32) mx = fmax(mx, nrm2[c]);
+        mx = warp_max(mx);
+        const double thr = sv_cutoff * sv_cutoff * mx;
+        int base = 0;                              // ordered compaction of the active columns
+        for (int c0 = 0; c0 < n; c0 += 32) {
+            const int c = c0 + lane;
+            const bool act = (c < n) && (nrm2[c] > thr);
+            const unsigned bal = __ballot_sync(0xffffffffu, act);
+            if (act) list[base + __popc(bal & ((1u << lane) - 1u))] = c;
+            base += __popc(bal);
+        }
+        if (lane == 0) { *s_nact = base; *s_thr = thr; *s_rot = 0; }
+    }
+    __syncthreads();
+}
+
+// QR-preconditioned polar factor of one problem (Drmac-Veselic style preconditioning of the one-sided Jacobi SVD):
+//   G_a = Q1 R1 (active columns only, len x r);  R1^T = Q2 R2;  L = R2^T;  Jacobi on the columns of L with the same
+//   rotations applied to the columns of Q2:  L J = U~ Sigma,  W = Q2 J  =>  polar(R1) = U~ W^T =: P,  polar(G_a) = Q1 P.
+//   Outputs, in the layout the final grouped GEMM T^T = sum_i gn[i] (x) vw[i] consumes:
+//     gn[list[a]] = column a of Q1 (rows of inactive columns are zero),  vw[list[i]] = sum_a P[i][a] V^T[list[a]].
+// The Jacobi then works on an r x r lower-triangular, well-graded matrix: ~7 sweeps instead of ~11 and ~2.5x fewer
+// rotations on columns of length r instead of (2l+1) and N_r (numpy model: tests/jacobi_model.py:qr_polar).
+// Shared memory: A = Q1 [r][ldg] (reused for P afterwards), B [r][ldl], C [r][ldl].
+__device__ __forceinline__ int jacobi_qr_problem(const double* __restrict__ g, int n, int ldg, const double* __restrict__ V0, int n_r_grid,
+                                                 double* __restrict__ gn, double* __restrict__ W, int wld, double* nrm2, int* list, int r,
+                                                 int ldl, double* region, double2* rotbuf, double sv_cutoff, double tol, int max_sweeps,
+                                                 int* s_nact, double* s_thr, int* s_rot, double* __restrict__ sigma) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    double* A = region;                 // [r][ldg]
+    double* B = A + (size_t)r * ldg;    // [r][ldl]
+    double* C = B + (size_t)r * ldl;    // [r][ldl]
+    int* list2 = list + n;              // active columns of L (the caller reserved 2n ints)
+    // ---- gather the active columns, zero the output rows of the inactive ones
+    for (int i = tid; i < r * (ldg / 2); i += nthr) {
+        const int a = i / (ldg / 2), e = i - a * (ldg / 2);
+        reinterpret_cast<double2*>(A)[i] = __ldg(reinterpret_cast<const double2*>(g + (size_t)list[a] * ldg) + e);
+    }
+    for (int i = tid; i < n * (ldg / 2); i += nthr) reinterpret_cast<double2*>(gn)[i] = make_double2(0.0, 0.0);
+    __syncthreads();
+    mgs2_qr_dispatch(A, ldg, r, B, ldl);                  // A = Q1, B = columns of R1^T
+    for (int i = tid; i < r * (ldg / 2); i += nthr) {     // Q1 is final: rows list[a] of gn
+        const int a = i / (ldg / 2), e = i - a * (ldg / 2);
+        reinterpret_cast<double2*>(gn + (size_t)list[a] * ldg)[e] = reinterpret_cast<const double2*>(A)[i];
+    }
+    mgs2_qr_dispatch(B, ldl, r, C, ldl);                  // B = Q2, C = columns of R2^T = L
+    int sweep = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        jacobi_active_list(C, ldl, r, nrm2, list2, sv_cutoff, s_nact, s_thr, s_rot);
+        const int nact = *s_nact;
+        const double thr = *s_thr;
+        if (nact < 2) break;
+        jacobi_sweep_dispatch_sq(C, B, ldl, list2, nact, thr, tol, rotbuf, s_rot);
+        __syncthreads();
+        const int rotated = *s_rot;
+        __syncthreads();
+        if (!rotated) { ++sweep; break; }
+    }
+    __syncthreads();
+    jacobi_active_list(C, ldl, r, nrm2, list2, sv_cutoff, s_nact, s_thr, s_rot);     // final norms; list2 = resolved directions
+    const double thr_f = *s_thr;
+    // ---- P[i][a] = sum_c U~[i][c] W[a][c], U~ = C / sigma on the resolved directions;  stored P[i*ldl + a] in A's place
+    double* P = A;
+    for (int idx = tid; idx < r * r; idx += nthr) {
+        const int i = idx / r, a = idx - i * r;
+        double acc = 0.0;
+        for (int c = 0; c < r; ++c) {
+            const double s2 = nrm2[c];
+            if (s2 > thr_f && s2 > 0.0) acc += C[(size_t)c * ldl + i] * rsqrt(s2) * B[(size_t)c * ldl + a];
+        }
+        P[(size_t)i * ldl + a] = acc;
+    }
+    for (int i = tid; i < r; i += nthr) sigma[i] = sqrt(nrm2[i]);
+    __syncthreads();
+    // ---- vw[list[i]][k] = sum_a P[i][a] V^T[list[a]][k];  V^T rows staged through shared memory (B and C are free now)
+    double* Vs = B;                                        // [rows_per_chunk][n_r_grid]
+    const int chunk = max(1, min(r, (2 * r * ldl) / n_r_grid));
+    const int kq = (n_r_grid + 3) / 4;                     // each thread owns 4 consecutive k of one output row at a time
+    for (int item0 = 0; item0 < r * kq; item0 += nthr) {
+        const int item = item0 + tid;
+        const bool act = item < r * kq;
+        const int i = act ? item / kq : 0, k4 = act ? (item - i * kq) * 4 : 0;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int a0 = 0; a0 < r; a0 += chunk) {
+            const int na = min(chunk, r - a0);
+            __syncthreads();
+            for (int t = tid; t < na * n_r_grid; t += nthr) {
+                const int aa = t / n_r_grid, k = t - aa * n_r_grid;
+                Vs[t] = __ldg(V0 + (size_t)list[a0 + aa] * n_r_grid + k);
+            }
+            __syncthreads();
+            if (act) {
+                for (int aa = 0; aa < na; ++aa) {
+                    const double pv = P[(size_t)i * ldl + a0 + aa];
+                    const double* vrow = Vs + (size_t)aa * n_r_grid + k4;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (k4 + u < n_r_grid) acc[u] += pv * vrow[u];
+                }
+            }
+        }
+        if (act) {
+            double* dst = W + (size_t)list[i] * wld + k4;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (k4 + u < n_r_grid) dst[u] = acc[u];
+        }
+    }
+    __syncthreads();
+    return sweep;
+}
+
 // MAXV2 = 8, THREADS = 512: column length <= 128 and N_r <= 128 (the L=63 / N_r=128 configuration)
 // MAXV2 = 16, THREADS = 256: up to 256 / 256 (L=127 / N_r=256); 255 registers per thread for the 2 x 16 double2 tiles
-template <int MAXV2, int THREADS>
+template <int MAXV2, int THREADS, bool QR>
 __global__ void __launch_bounds__(THREADS, 1) procrustes_jacobi_kernel(const double* __restrict__ g_in, double* __restrict__ gn_out,
                                                                        double* __restrict__ vw, const double* __restrict__ vt,
                                                                        double* __restrict__ sigma_out, const ProcOrder* __restrict__ orders,
@@ -392,11 +576,26 @@ __global__ void __launch_bounds__(THREADS, 1) procrustes_jacobi_kernel(const dou
         const int n = o.n_cols;
         const int ldg = jacobi_stride(o.n_c);
         double* nrm2 = smem_j + fixed;                     // [n]
-        int* list = (int*)(nrm2 + n);                      // [n]
-        const int var0 = (fixed + n + (n + 1) / 2 + 1) & ~1;              // 16-byte aligned
+        int* list = (int*)(nrm2 + n);                      // [2n]
+        const int var0 = (fixed + 2 * n + 2) & ~1;                        // 16-byte aligned
         const bool g_smem = var0 + n * ldg <= smem_doubles;
         const double* g = g_in + (size_t)b * g_run_stride + o.g_off;
         double* gn = gn_out + (size_t)b * g_run_stride + o.g_off;
+        if constexpr (QR) {
+            // QR-preconditioned path when the three r-sized arrays fit in shared memory
+            __syncthreads();                               // previous problem fully done with smem
+            jacobi_active_list(g, ldg, n, nrm2, list, sv_cutoff, &s_nact, &s_thr, &s_rot);
+            const int r = s_nact;
+            const int ldl = r <= 64 ? 64 : (r <= 96 ? 96 : 128);
+            if (r >= 2 && var0 + r * ldg + 2 * r * ldl <= smem_doubles) {
+                __syncthreads();
+                const int sw = jacobi_qr_problem(g, n, ldg, vt + o.pd_off, n_r_grid, gn, vw + (size_t)b * vw_run_stride + o.vw_off, wld, nrm2,
+                                                 list, r, ldl, smem_j + var0, rotbuf, sv_cutoff, tol, max_sweeps, &s_nact, &s_thr, &s_rot,
+                                                 sigma_out + (size_t)b * sig_run_stride + (size_t)oi * n_r_grid);
+                if (tid == 0 && sweeps_out) sweeps_out[b * n_orders + oi] = sw;
+                continue;
+            }
+        }
         double* Gs = g_smem ? smem_j + var0 : gn;          // [n][ldg]
         double* Ws = smem_j + var0 + (g_smem ? n * ldg : 0);              // [cap][wld]
         const int cap = (smem_doubles - (int)(Ws - smem_j)) / wld;

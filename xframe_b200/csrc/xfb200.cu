@@ -369,10 +369,10 @@ static int launch_jacobi(xfb_plan* p, const double* g, double* gn, double* vw, c
     if (!p->jac_counter) { if (dev_alloc(p, &p->jac_counter, 1)) return 1; }
     XFB_CUDA(cudaMemsetAsync(p->jac_counter, 0, sizeof(int), st));
     if (p->jacobi_big)
-        procrustes_jacobi_kernel<16, 256><<<grid, 256, p->jacobi_smem, st>>>(g, gn, vw, vt, sigma, p->orders_dev, na, nb, p->n_r, p->g_run, p->vw_run,
+        procrustes_jacobi_kernel<16, 256, false><<<grid, 256, p->jacobi_smem, st>>>(g, gn, vw, vt, sigma, p->orders_dev, na, nb, p->n_r, p->g_run, p->vw_run,
                                                                             (long long)na * p->n_r, p->sv_cutoff, 1e-15, p->max_sweeps, sweeps, smem_doubles, p->jac_counter);
     else
-        procrustes_jacobi_kernel<8, 512><<<grid, 512, p->jacobi_smem, st>>>(g, gn, vw, vt, sigma, p->orders_dev, na, nb, p->n_r, p->g_run, p->vw_run,
+        procrustes_jacobi_kernel<8, 512, true><<<grid, 512, p->jacobi_smem, st>>>(g, gn, vw, vt, sigma, p->orders_dev, na, nb, p->n_r, p->g_run, p->vw_run,
                                                                            (long long)na * p->n_r, p->sv_cutoff, 1e-15, p->max_sweeps, sweeps, smem_doubles, p->jac_counter);
     XFB_CUDA(cudaGetLastError());
     return 0;
@@ -546,6 +546,7 @@ int xfb_plan_set_projection(xfb_plan* p, const xfb_projection_desc* d) {
         XFB_CUDA(cudaMemset(p->g, 0, B * p->g_run * sizeof(double)));       // the column pads stay zero: the GEMM writes only [n_cols][n_c]
         if (dev_alloc(p, &p->gn, B * p->g_run)) return 1;
         if (dev_alloc(p, &p->vw, B * p->vw_run)) return 1;
+        XFB_CUDA(cudaMemset(p->vw, 0, B * p->vw_run * sizeof(double)));     // rows of dropped columns are never written: keep them finite
         if (dev_alloc(p, &p->sigma, B * na * n_r)) return 1;
         if (dev_alloc(p, &p->sweeps_dev, B * na)) return 1;
         {
@@ -556,6 +557,7 @@ int xfb_plan_set_projection(xfb_plan* p, const xfb_projection_desc* d) {
         }
         if (dev_alloc(p, &p->gn_u, (size_t)p->g_run)) return 1;
         if (dev_alloc(p, &p->vw_u, (size_t)p->vw_run)) return 1;
+        XFB_CUDA(cudaMemset(p->vw_u, 0, (size_t)p->vw_run * sizeof(double)));
         if (dev_alloc(p, &p->sigma_u, na * n_r)) return 1;
         if (dev_alloc(p, &p->gemmM_dev, B * na)) return 1;
         if (dev_alloc(p, &p->gemmT_dev, B * na)) return 1;
@@ -566,8 +568,8 @@ int xfb_plan_set_projection(xfb_plan* p, const xfb_projection_desc* d) {
         }
         if (dev_alloc(p, &p->gemmM_tp, B * tiles_m)) return 1;
         if (dev_alloc(p, &p->gemmT_tp, B * tiles_t)) return 1;
-        if (p->jacobi_big) XFB_CUDA(cudaFuncSetAttribute(procrustes_jacobi_kernel<16, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-        else XFB_CUDA(cudaFuncSetAttribute(procrustes_jacobi_kernel<8, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        if (p->jacobi_big) XFB_CUDA(cudaFuncSetAttribute(procrustes_jacobi_kernel<16, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        else XFB_CUDA(cudaFuncSetAttribute(procrustes_jacobi_kernel<8, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     } else {
         // dummy so the unpack kernel has valid pointers
         ProcOrder o{};
