@@ -154,5 +154,5 @@ def test_unknowns_match_the_reference_formula():
                 assert rel_l2(u, r) < 1e-8
             if l % 2 == 0:
                 p = u @ u.conj().T                                               # partial isometry: projector
-                assert rel_l2(p @ p, p) < 1e-10
+                assert rel_l2(p @ p, p) < 1e-9
     plan.close()

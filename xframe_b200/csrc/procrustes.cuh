@@ -288,11 +288,13 @@ __device__ __forceinline__ bool jacobi_w_pass(double* Wb, int wld, bool w_compac
 //  * fewer block pairs than warps: the warps split into a G team (pass 1 of round r) and a W team (pass 2 of round
 //    r-1, from the double-buffered rotation parameters) that run concurrently -- G and W are independent data.
 #define JROT_RB (JROT_STEPS * 4 + 1)
-#define JROT_SLOTS 32          // block pairs per round with parameter slots (n <= 256 columns -> <= 32 block pairs)
+// block pairs per round that need a parameter slot: 512-thread variant n <= 128 columns -> 16, 256-thread variant n <= 256 -> 32
+__host__ __device__ inline int jrot_slots(int threads) { return threads >= 512 ? 16 : 32; }
 template <int NV2, int WV2>
 __device__ __forceinline__ void jacobi_sweep_blocked(double* Gs, int ldg, double* Wb, int wld, bool w_compact, const int* __restrict__ list,
                                                      int nact, double thr, double tol, double2* rotbuf, int* s_rot) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int JROT_SLOTS = jrot_slots(blockDim.x);
     const int nblk = (nact + 3) >> 2;
     const int nblkp = max(2, nblk + (nblk & 1));
     const int half = nblkp >> 1, rounds = nblkp - 1;
@@ -560,8 +562,8 @@ __global__ void __launch_bounds__(THREADS, 1) procrustes_jacobi_kernel(const dou
     __shared__ double s_thr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = THREADS >> 5;
     const int wld = jacobi_wstride(n_r_grid);
-    double2* rotbuf = reinterpret_cast<double2*>(smem_j);                 // [2][JROT_SLOTS][JROT_RB]
-    const int fixed = 2 * 2 * JROT_SLOTS * JROT_RB;                       // doubles
+    double2* rotbuf = reinterpret_cast<double2*>(smem_j);                 // [2][slots][JROT_RB]
+    const int fixed = 2 * 2 * jrot_slots(THREADS) * JROT_RB;              // doubles
 
     // dynamic work queue (largest problems first): a CTA fetches the next problem when it is done with the previous one
     for (;;) {
