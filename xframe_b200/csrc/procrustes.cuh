@@ -329,55 +329,41 @@ __device__ __forceinline__ void jacobi_sweep_blocked(double* Gs, int ldg, double
     if (rotated && lane == 0) *s_rot = 1;
 }
 
-// runtime (ldg, wld) -> compile-time register tile sizes.  MAXV2 bounds the instantiations of one kernel variant.
+// runtime column stride -> compile-time register tile size.  The accumulator columns have the same length as the G
+// columns (the accumulator starts as the identity or as Q2, see the kernel); MAXV2 bounds the instantiations.
 template <int MAXV2>
-__device__ __forceinline__ void jacobi_sweep_dispatch(double* Gs, int ldg, double* Wb, int wld, bool w_compact, const int* list, int nact,
-                                                      double thr, double tol, double2* rotbuf, int* s_rot) {
+__device__ __forceinline__ void jacobi_sweep_dispatch(double* Gs, double* Wb, int ld, bool w_compact, const int* list, int nact, double thr,
+                                                      double tol, double2* rotbuf, int* s_rot) {
     if constexpr (MAXV2 >= 16) {
-        if (wld > 128) {
-            if (ldg <= 64) jacobi_sweep_blocked<4, 16>(Gs, ldg, Wb, wld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
-            else if (ldg <= 128) jacobi_sweep_blocked<8, 16>(Gs, ldg, Wb, wld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
-            else jacobi_sweep_blocked<16, 16>(Gs, ldg, Wb, wld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
-            return;
-        }
-        if (ldg > 128) { jacobi_sweep_blocked<16, 8>(Gs, ldg, Wb, wld, w_compact, list, nact, thr, tol, rotbuf, s_rot); return; }
+        if (ld > 128) { jacobi_sweep_blocked<16, 16>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot); return; }
     }
-    if (ldg <= 64) jacobi_sweep_blocked<4, 8>(Gs, ldg, Wb, wld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
-    else jacobi_sweep_blocked<8, 8>(Gs, ldg, Wb, wld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
-}
-
-// same, for the QR-preconditioned path: G = L (r x r, columns padded to ldl = 64 / 96 / 128) and the accumulator has the
-// same column length (it starts as Q2, see below)
-__device__ __forceinline__ void jacobi_sweep_dispatch_sq(double* Gs, double* Wb, int ldl, const int* list, int nact, double thr, double tol,
-                                                         double2* rotbuf, int* s_rot) {
-    if (ldl <= 64) jacobi_sweep_blocked<4, 4>(Gs, ldl, Wb, ldl, false, list, nact, thr, tol, rotbuf, s_rot);
-    else if (ldl <= 96) jacobi_sweep_blocked<6, 6>(Gs, ldl, Wb, ldl, false, list, nact, thr, tol, rotbuf, s_rot);
-    else jacobi_sweep_blocked<8, 8>(Gs, ldl, Wb, ldl, false, list, nact, thr, tol, rotbuf, s_rot);
+    if (ld <= 64) jacobi_sweep_blocked<4, 4>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
+    else if (ld <= 96) jacobi_sweep_blocked<6, 6>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
+    else jacobi_sweep_blocked<8, 8>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
 }
 
 // QR factorisation by modified Gram-Schmidt with re-orthogonalisation ("twice is enough"), whole CTA.
 //   A [r][lda]: r columns (zero padded), overwritten by the orthonormal Q (a column that vanishes becomes 0);
 //   Rt [r][ldr]: Rt[j][k] = R[j][k] (k >= j), i.e. column j of R^T -- the column storage of the NEXT factorisation step.
-// Step j: column j is already orthogonal to q_0..q_{j-1}; it is normalised, then every later column k gets
-// a_k -= (q_j.a_k) q_j twice, one 8-lane group per column, both passes on registers.
+// Step j: q_j is final; every later column k gets a_k -= (q_j.a_k) q_j twice (one 8-lane group per column, both passes on
+// registers); the group that owns column j+1 normalises it in the same step, so there is one barrier per step.
 template <int NV>
 __device__ __forceinline__ void mgs2_qr(double* A, int lda, int r, double* Rt, int ldr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
     const int grp = lane >> 3, sub = lane & (JG - 1);
     for (int i = tid; i < r * ldr; i += blockDim.x) Rt[i] = 0.0;
     __syncthreads();
-    for (int j = 0; j < r; ++j) {
-        if (warp == 0) {                                   // normalise column j (group 0 does the work, all lanes shuffle)
-            double2 x[NV];
-            jacobi_load_col<NV>(x, A, (long long)j * lda, sub, grp == 0);
-            const double n2 = jacobi_col_norm2<NV>(x);
-            const double nrm = sqrt(n2), inv = (nrm > 0.0) ? 1.0 / nrm : 0.0;
+    if (warp == 0) {                                       // normalise column 0 (group 0 does the work, all lanes shuffle)
+        double2 x[NV];
+        jacobi_load_col<NV>(x, A, 0, sub, grp == 0);
+        const double nrm = sqrt(jacobi_col_norm2<NV>(x)), inv = (nrm > 0.0) ? 1.0 / nrm : 0.0;
 #pragma unroll
-            for (int t = 0; t < NV; ++t) { x[t].x *= inv; x[t].y *= inv; }
-            jacobi_store_col<NV>(x, A, (long long)j * lda, sub, grp == 0);
-            if (lane == 0) Rt[(size_t)j * ldr + j] = nrm;
-        }
-        __syncthreads();
+        for (int t = 0; t < NV; ++t) { x[t].x *= inv; x[t].y *= inv; }
+        jacobi_store_col<NV>(x, A, 0, sub, grp == 0);
+        if (lane == 0) Rt[0] = nrm;
+    }
+    for (int j = 0; j < r; ++j) {
+        __syncthreads();                                   // q_j is final
         for (int k0 = j + 1 + warp * 4; k0 < r; k0 += nwarp * 4) {      // warp-uniform trip count
             const int k = k0 + grp;
             const bool v = k < r;
@@ -397,11 +383,20 @@ __device__ __forceinline__ void mgs2_qr(double* A, int lda, int r, double* Rt, i
                 for (int t = 0; t < NV; ++t) { a[t].x -= c * q[t].x; a[t].y -= c * q[t].y; }
                 c_tot += c;
             }
+            if (k0 == j + 1) {                             // warp-uniform: the first trailing column becomes q_{j+1} right away
+                const double n2 = jacobi_col_norm2<NV>(a);
+                if (grp == 0) {
+                    const double nrm = sqrt(n2), inv = (nrm > 0.0) ? 1.0 / nrm : 0.0;
+#pragma unroll
+                    for (int t = 0; t < NV; ++t) { a[t].x *= inv; a[t].y *= inv; }
+                    if (sub == 0) Rt[(size_t)(j + 1) * ldr + j + 1] = nrm;
+                }
+            }
             jacobi_store_col<NV>(a, A, (long long)k * lda, sub, v);
             if (v && sub == 0) Rt[(size_t)j * ldr + k] = c_tot;
         }
-        __syncthreads();
     }
+    __syncthreads();
 }
 __device__ __forceinline__ void mgs2_qr_dispatch(double* A, int lda, int r, double* Rt, int ldr) {
     if (lda <= 64) mgs2_qr<4>(A, lda, r, Rt, ldr);
@@ -456,26 +451,29 @@ __device__ __forceinline__ void jacobi_active_list(const double* Gs, int ldg, in
 // QR-preconditioned polar factor of one problem (Drmac-Veselic style preconditioning of the one-sided Jacobi SVD):
 //   G_a = Q1 R1 (active columns only, len x r);  R1^T = Q2 R2;  L = R2^T;  Jacobi on the columns of L with the same
 //   rotations applied to the columns of Q2:  L J = U~ Sigma,  W = Q2 J  =>  polar(R1) = U~ W^T =: P,  polar(G_a) = Q1 P.
-//   Outputs, in the layout the final grouped GEMM T^T = sum_i gn[i] (x) vw[i] consumes:
-//     gn[list[a]] = column a of Q1 (rows of inactive columns are zero),  vw[list[i]] = sum_a P[i][a] V^T[list[a]].
+//   Outputs:  gn[list[a]] = column a of Q1 (rows of inactive columns are zero),  pp[list[i]][list[a]] = P[i][a].
 // The Jacobi then works on an r x r lower-triangular, well-graded matrix: ~7 sweeps instead of ~11 and ~2.5x fewer
-// rotations on columns of length r instead of (2l+1) and N_r (numpy model: tests/jacobi_model.py:qr_polar).
-// Shared memory: A = Q1 [r][ldg] (reused for P afterwards), B [r][ldl], C [r][ldl].
-__device__ __forceinline__ int jacobi_qr_problem(const double* __restrict__ g, int n, int ldg, const double* __restrict__ V0, int n_r_grid,
-                                                 double* __restrict__ gn, double* __restrict__ W, int wld, double* nrm2, int* list, int r,
-                                                 int ldl, double* region, double2* rotbuf, double sv_cutoff, double tol, int max_sweeps,
-                                                 int* s_nact, double* s_thr, int* s_rot, double* __restrict__ sigma) {
+// rotations on columns of length r instead of 2l+1 (numpy model: tests/jacobi_model.py:qr_polar).
+// Shared memory: A = Q1 [r][ldg], B [r][ldl], C [r][ldl].
+template <int MAXV2>
+__device__ __forceinline__ int jacobi_qr_problem(const double* __restrict__ g, int n, int ldg, double* __restrict__ gn, double* __restrict__ pp,
+                                                 double* nrm2, int* list, int r, int ldl, double* region, double2* rotbuf, double sv_cutoff,
+                                                 double tol, int max_sweeps, int* s_nact, double* s_thr, int* s_rot,
+                                                 double* __restrict__ sigma) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     double* A = region;                 // [r][ldg]
     double* B = A + (size_t)r * ldg;    // [r][ldl]
     double* C = B + (size_t)r * ldl;    // [r][ldl]
     int* list2 = list + n;              // active columns of L (the caller reserved 2n ints)
-    // ---- gather the active columns, zero the output rows of the inactive ones
+    // ---- gather the active columns, zero the outputs (rows / entries of inactive columns stay zero)
     for (int i = tid; i < r * (ldg / 2); i += nthr) {
         const int a = i / (ldg / 2), e = i - a * (ldg / 2);
         reinterpret_cast<double2*>(A)[i] = __ldg(reinterpret_cast<const double2*>(g + (size_t)list[a] * ldg) + e);
     }
-    for (int i = tid; i < n * (ldg / 2); i += nthr) reinterpret_cast<double2*>(gn)[i] = make_double2(0.0, 0.0);
+    for (int i = tid; i < n * (ldg / 2); i += nthr) {
+        reinterpret_cast<double2*>(gn)[i] = make_double2(0.0, 0.0);
+        reinterpret_cast<double2*>(pp)[i] = make_double2(0.0, 0.0);
+    }
     __syncthreads();
     mgs2_qr_dispatch(A, ldg, r, B, ldl);                  // A = Q1, B = columns of R1^T
     for (int i = tid; i < r * (ldg / 2); i += nthr) {     // Q1 is final: rows list[a] of gn
@@ -489,79 +487,62 @@ __device__ __forceinline__ int jacobi_qr_problem(const double* __restrict__ g, i
         const int nact = *s_nact;
         const double thr = *s_thr;
         if (nact < 2) break;
-        jacobi_sweep_dispatch_sq(C, B, ldl, list2, nact, thr, tol, rotbuf, s_rot);
+        jacobi_sweep_dispatch<MAXV2>(C, B, ldl, false, list2, nact, thr, tol, rotbuf, s_rot);
         __syncthreads();
         const int rotated = *s_rot;
         __syncthreads();
         if (!rotated) { ++sweep; break; }
     }
     __syncthreads();
-    jacobi_active_list(C, ldl, r, nrm2, list2, sv_cutoff, s_nact, s_thr, s_rot);     // final norms; list2 = resolved directions
+    jacobi_active_list(C, ldl, r, nrm2, list2, sv_cutoff, s_nact, s_thr, s_rot);     // final norms
     const double thr_f = *s_thr;
-    // ---- P[i][a] = sum_c U~[i][c] W[a][c], U~ = C / sigma on the resolved directions;  stored P[i*ldl + a] in A's place
-    double* P = A;
-    for (int idx = tid; idx < r * r; idx += nthr) {
-        const int i = idx / r, a = idx - i * r;
-        double acc = 0.0;
-        for (int c = 0; c < r; ++c) {
-            const double s2 = nrm2[c];
-            if (s2 > thr_f && s2 > 0.0) acc += C[(size_t)c * ldl + i] * rsqrt(s2) * B[(size_t)c * ldl + a];
-        }
-        P[(size_t)i * ldl + a] = acc;
-    }
     for (int i = tid; i < r; i += nthr) sigma[i] = sqrt(nrm2[i]);
+    // ---- U~ = C / sigma on the resolved directions (0 on the dropped ones)
+    for (int i = tid; i < r * ldl; i += nthr) {
+        const int c = i / ldl;
+        const double s2 = nrm2[c];
+        C[i] = (s2 > thr_f && s2 > 0.0) ? C[i] * rsqrt(s2) : 0.0;
+    }
     __syncthreads();
-    // ---- vw[list[i]][k] = sum_a P[i][a] V^T[list[a]][k];  V^T rows staged through shared memory (B and C are free now)
-    double* Vs = B;                                        // [rows_per_chunk][n_r_grid]
-    const int chunk = max(1, min(r, (2 * r * ldl) / n_r_grid));
-    const int kq = (n_r_grid + 3) / 4;                     // each thread owns 4 consecutive k of one output row at a time
-    for (int item0 = 0; item0 < r * kq; item0 += nthr) {
-        const int item = item0 + tid;
-        const bool act = item < r * kq;
-        const int i = act ? item / kq : 0, k4 = act ? (item - i * kq) * 4 : 0;
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int a0 = 0; a0 < r; a0 += chunk) {
-            const int na = min(chunk, r - a0);
-            __syncthreads();
-            for (int t = tid; t < na * n_r_grid; t += nthr) {
-                const int aa = t / n_r_grid, k = t - aa * n_r_grid;
-                Vs[t] = __ldg(V0 + (size_t)list[a0 + aa] * n_r_grid + k);
-            }
-            __syncthreads();
-            if (act) {
-                for (int aa = 0; aa < na; ++aa) {
-                    const double pv = P[(size_t)i * ldl + a0 + aa];
-                    const double* vrow = Vs + (size_t)aa * n_r_grid + k4;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) if (k4 + u < n_r_grid) acc[u] += pv * vrow[u];
-                }
-            }
+    // ---- P[i][a] = sum_c U~[c][i] W[c][a]  ->  pp[list[i]][list[a]];  each thread a 1 x 4 tile (a fastest)
+    const int aq = (r + 3) / 4;
+    for (int item = tid; item < r * aq; item += nthr) {
+        const int i = item / aq, a4 = (item - i * aq) * 4;
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+        for (int c = 0; c < r; ++c) {
+            const double u = C[(size_t)c * ldl + i];
+            const double2 b01 = *reinterpret_cast<const double2*>(B + (size_t)c * ldl + a4);
+            const double2 b23 = *reinterpret_cast<const double2*>(B + (size_t)c * ldl + a4 + 2);
+            acc0 += u * b01.x; acc1 += u * b01.y; acc2 += u * b23.x; acc3 += u * b23.y;
         }
-        if (act) {
-            double* dst = W + (size_t)list[i] * wld + k4;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) if (k4 + u < n_r_grid) dst[u] = acc[u];
-        }
+        double* dst = pp + (size_t)list[i] * ldg;
+        if (a4 < r) dst[list[a4]] = acc0;
+        if (a4 + 1 < r) dst[list[a4 + 1]] = acc1;
+        if (a4 + 2 < r) dst[list[a4 + 2]] = acc2;
+        if (a4 + 3 < r) dst[list[a4 + 3]] = acc3;
     }
     __syncthreads();
     return sweep;
 }
 
-// MAXV2 = 8, THREADS = 512: column length <= 128 and N_r <= 128 (the L=63 / N_r=128 configuration)
-// MAXV2 = 16, THREADS = 256: up to 256 / 256 (L=127 / N_r=256); 255 registers per thread for the 2 x 16 double2 tiles
+// Kernel outputs, per (run, order) problem:  gn [n][ldg], pp [n][ldg] with  polar(G) = sum_c gn[c] (x) pp[c]
+// (len x n); the host then forms  vw = pp V_l^T  and  T^T = gn^T vw  with two grouped DMMA GEMMs.
+//   QR path:        gn = Q1 (rows of the active columns), pp = P scattered to the active rows / columns
+//   direct path:    gn = U~ (normalised rotated columns of G), pp = J^T (accumulator started from the identity)
+// MAXV2 = 8, THREADS = 512: column length <= 128 (the L=63 configuration);  MAXV2 = 16, THREADS = 256: up to 256
+// (L=127), 255 registers per thread for the 2 x 16 double2 register tiles.
 template <int MAXV2, int THREADS, bool QR>
 __global__ void __launch_bounds__(THREADS, 1) procrustes_jacobi_kernel(const double* __restrict__ g_in, double* __restrict__ gn_out,
-                                                                       double* __restrict__ vw, const double* __restrict__ vt,
-                                                                       double* __restrict__ sigma_out, const ProcOrder* __restrict__ orders,
-                                                                       int n_orders, int n_batch, int n_r_grid, long long g_run_stride,
-                                                                       long long vw_run_stride, long long sig_run_stride, double sv_cutoff,
-                                                                       double tol, int max_sweeps, int* __restrict__ sweeps_out,
-                                                                       int smem_doubles, int* __restrict__ work_counter) {
+                                                                       double* __restrict__ pp_out, double* __restrict__ sigma_out,
+                                                                       const ProcOrder* __restrict__ orders, int n_orders, int n_batch,
+                                                                       int sig_ld, long long g_run_stride, long long sig_run_stride,
+                                                                       double sv_cutoff, double tol, int max_sweeps,
+                                                                       int* __restrict__ sweeps_out, int smem_doubles,
+                                                                       int* __restrict__ work_counter) {
     extern __shared__ __align__(16) double smem_j[];
     __shared__ int s_nact, s_rot, s_prob;
     __shared__ double s_thr;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = THREADS >> 5;
-    const int wld = jacobi_wstride(n_r_grid);
+    const int tid = threadIdx.x;
     double2* rotbuf = reinterpret_cast<double2*>(smem_j);                 // [2][slots][JROT_RB]
     const int fixed = 2 * 2 * jrot_slots(THREADS) * JROT_RB;              // doubles
 
@@ -580,77 +561,58 @@ __global__ void __launch_bounds__(THREADS, 1) procrustes_jacobi_kernel(const dou
         double* nrm2 = smem_j + fixed;                     // [n]
         int* list = (int*)(nrm2 + n);                      // [2n]
         const int var0 = (fixed + 2 * n + 2) & ~1;                        // 16-byte aligned
-        const bool g_smem = var0 + n * ldg <= smem_doubles;
         const double* g = g_in + (size_t)b * g_run_stride + o.g_off;
         double* gn = gn_out + (size_t)b * g_run_stride + o.g_off;
+        double* pp = pp_out + (size_t)b * g_run_stride + o.g_off;
+        double* sg = sigma_out + (size_t)b * sig_run_stride + (size_t)oi * sig_ld;
         if constexpr (QR) {
             // QR-preconditioned path when the three r-sized arrays fit in shared memory
-            __syncthreads();                               // previous problem fully done with smem
             jacobi_active_list(g, ldg, n, nrm2, list, sv_cutoff, &s_nact, &s_thr, &s_rot);
             const int r = s_nact;
             const int ldl = r <= 64 ? 64 : (r <= 96 ? 96 : 128);
             if (r >= 2 && var0 + r * ldg + 2 * r * ldl <= smem_doubles) {
                 __syncthreads();
-                const int sw = jacobi_qr_problem(g, n, ldg, vt + o.pd_off, n_r_grid, gn, vw + (size_t)b * vw_run_stride + o.vw_off, wld, nrm2,
-                                                 list, r, ldl, smem_j + var0, rotbuf, sv_cutoff, tol, max_sweeps, &s_nact, &s_thr, &s_rot,
-                                                 sigma_out + (size_t)b * sig_run_stride + (size_t)oi * n_r_grid);
+                const int sw = jacobi_qr_problem<MAXV2>(g, n, ldg, gn, pp, nrm2, list, r, ldl, smem_j + var0, rotbuf, sv_cutoff, tol, max_sweeps,
+                                                        &s_nact, &s_thr, &s_rot, sg);
                 if (tid == 0 && sweeps_out) sweeps_out[b * n_orders + oi] = sw;
                 continue;
             }
+            __syncthreads();
         }
+        // ---- direct path: Jacobi on G itself, accumulator W = J^T in pp (global), staged per sweep for the active columns
+        const bool g_smem = var0 + n * ldg <= smem_doubles;
         double* Gs = g_smem ? smem_j + var0 : gn;          // [n][ldg]
-        double* Ws = smem_j + var0 + (g_smem ? n * ldg : 0);              // [cap][wld]
-        const int cap = (smem_doubles - (int)(Ws - smem_j)) / wld;
-        double* W = vw + (size_t)b * vw_run_stride + o.vw_off;            // [n][wld]
-        const double* V0 = vt + o.pd_off;                                 // [n][n_r_grid]
-        __syncthreads();                                   // previous problem fully done with smem
+        double* Ws = smem_j + var0 + (g_smem ? n * ldg : 0);              // [cap][ldg]
+        const int cap = (smem_doubles - (int)(Ws - smem_j)) / ldg;
         {
             const double2* src = reinterpret_cast<const double2*>(g);
             double2* dst = reinterpret_cast<double2*>(Gs);
             for (int i = tid; i < n * ldg / 2; i += THREADS) dst[i] = src[i];
         }
-        for (int i = tid; i < n * wld; i += THREADS) {
-            const int c = i / wld, e = i - c * wld;
-            W[i] = (e < n_r_grid) ? V0[(size_t)c * n_r_grid + e] : 0.0;
+        for (int i = tid; i < n * ldg; i += THREADS) {
+            const int c = i / ldg, e = i - c * ldg;
+            pp[i] = (e == c) ? 1.0 : 0.0;
         }
         __syncthreads();
         int sweep = 0;
         for (; sweep < max_sweeps; ++sweep) {
-            jacobi_col_norms(Gs, ldg, n, nrm2);
-            __syncthreads();
-            if (warp == 0) {
-                double mx = 0.0;
-                for (int c = lane; c < n; c += 32) mx = fmax(mx, nrm2[c]);
-                mx = warp_max(mx);
-                const double thr = sv_cutoff * sv_cutoff * mx;
-                int base = 0;                              // ordered compaction of the active columns
-                for (int c0 = 0; c0 < n; c0 += 32) {
-                    const int c = c0 + lane;
-                    const bool act = (c < n) && (nrm2[c] > thr);
-                    const unsigned bal = __ballot_sync(0xffffffffu, act);
-                    if (act) list[base + __popc(bal & ((1u << lane) - 1u))] = c;
-                    base += __popc(bal);
-                }
-                if (lane == 0) { s_nact = base; s_thr = thr; s_rot = 0; }
-            }
-            __syncthreads();
+            jacobi_active_list(Gs, ldg, n, nrm2, list, sv_cutoff, &s_nact, &s_thr, &s_rot);
             const int nact = s_nact;
             const double thr = s_thr;
             if (nact < 2) break;
             const bool w_smem = nact <= cap;
             if (w_smem) {
-                // stage the active accumulator columns in shared memory for this sweep
-                for (int i = tid; i < nact * (wld / 2); i += THREADS) {
-                    const int a = i / (wld / 2), e = i - a * (wld / 2);
-                    reinterpret_cast<double2*>(Ws)[i] = __ldcg(reinterpret_cast<const double2*>(W + (size_t)list[a] * wld) + e);
+                for (int i = tid; i < nact * (ldg / 2); i += THREADS) {
+                    const int a = i / (ldg / 2), e = i - a * (ldg / 2);
+                    reinterpret_cast<double2*>(Ws)[i] = __ldcg(reinterpret_cast<const double2*>(pp + (size_t)list[a] * ldg) + e);
                 }
                 __syncthreads();
             }
-            jacobi_sweep_dispatch<MAXV2>(Gs, ldg, w_smem ? Ws : W, wld, w_smem, list, nact, thr, tol, rotbuf, &s_rot);
+            jacobi_sweep_dispatch<MAXV2>(Gs, w_smem ? Ws : pp, ldg, w_smem, list, nact, thr, tol, rotbuf, &s_rot);
             if (w_smem) {
-                for (int i = tid; i < nact * (wld / 2); i += THREADS) {
-                    const int a = i / (wld / 2), e = i - a * (wld / 2);
-                    __stcg(reinterpret_cast<double2*>(W + (size_t)list[a] * wld) + e, reinterpret_cast<const double2*>(Ws)[i]);
+                for (int i = tid; i < nact * (ldg / 2); i += THREADS) {
+                    const int a = i / (ldg / 2), e = i - a * (ldg / 2);
+                    __stcg(reinterpret_cast<double2*>(pp + (size_t)list[a] * ldg) + e, reinterpret_cast<const double2*>(Ws)[i]);
                 }
             }
             __syncthreads();
@@ -660,22 +622,13 @@ __global__ void __launch_bounds__(THREADS, 1) procrustes_jacobi_kernel(const dou
         }
         __syncthreads();
         // ---- final norms -> sigma, normalised columns
-        jacobi_col_norms(Gs, ldg, n, nrm2);
-        __syncthreads();
-        if (warp == 0) {
-            double mx = 0.0;
-            for (int c = lane; c < n; c += 32) mx = fmax(mx, nrm2[c]);
-            mx = warp_max(mx);
-            if (lane == 0) s_thr = sv_cutoff * sv_cutoff * mx;
-        }
-        __syncthreads();
+        jacobi_active_list(Gs, ldg, n, nrm2, list, sv_cutoff, &s_nact, &s_thr, &s_rot);
         const double thr_f = s_thr;
         for (int i = tid; i < n * ldg; i += THREADS) {
             const int c = i / ldg;
             const double s2 = nrm2[c];
             gn[i] = (s2 > thr_f && s2 > 0.0) ? Gs[i] / sqrt(s2) : 0.0;
         }
-        double* sg = sigma_out + (size_t)b * sig_run_stride + (size_t)oi * n_r_grid;
         for (int i = tid; i < n; i += THREADS) sg[i] = sqrt(nrm2[i]);
         if (tid == 0 && sweeps_out) sweeps_out[b * n_orders + oi] = sweep;
     }
@@ -720,15 +673,15 @@ __global__ void procrustes_unpack_kernel(const double2* __restrict__ c_in, doubl
 }
 
 // ---- fxs_unknowns on request (xfb_get_unknowns) ------------------------------------------------------------------
-// gn [n_cols][ldg] = U~^T (zero rows for dropped directions), vw [n_cols][wld] = J^T (accumulator started from the
-// identity).  polar(M) = J U~^T (real basis) -> complex columns m = -l..l.  One block per row i of the unknown.
-__global__ void unknown_assemble_kernel(const double* __restrict__ gn, const double* __restrict__ vw, int ldg, int wld, int n_cols, int n_c,
+// polar(G) = sum_c gn[c] (x) pp[c] (see the Jacobi kernel), polar(M) = polar(G)^T (real basis) -> complex columns
+// m = -l..l.  One block per row i of the unknown.
+__global__ void unknown_assemble_kernel(const double* __restrict__ gn, const double* __restrict__ pp, int ldg, int n_cols, int n_c,
                                         int l, double2* __restrict__ out) {
     __shared__ double row[512];
     const int i = blockIdx.x;
     for (int e = threadIdx.x; e < n_c; e += blockDim.x) {
         double s = 0.0;
-        for (int c = 0; c < n_cols; ++c) s += vw[(size_t)c * wld + i] * gn[(size_t)c * ldg + e];
+        for (int c = 0; c < n_cols; ++c) s += pp[(size_t)c * ldg + i] * gn[(size_t)c * ldg + e];
         row[e] = s;
     }
     __syncthreads();

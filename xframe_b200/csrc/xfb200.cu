@@ -52,12 +52,13 @@ struct xfb_plan {
     double inv_sqrt_np = 1.0, sv_cutoff = 1e-15; int max_sweeps = 40;
     double *pd_dev = nullptr, *vt_dev = nullptr;
     // fxs_unknowns on request (xfb_get_unknowns): identity accumulator table, single-run scratch, I_00 of the last projection
-    double *ident_dev = nullptr, *gn_u = nullptr, *vw_u = nullptr, *sigma_u = nullptr; double2* i00 = nullptr;
+    double *pp = nullptr, *gn_u = nullptr, *pp_u = nullptr, *sigma_u = nullptr; double2* i00 = nullptr;
     long long proj_calls = 0, unk_stamp = -1; int unk_run = -1, last_proj_nb = 0;
     long long xt_run = 0, g_run = 0, vw_run = 0;
     double *xt = nullptr, *tt = nullptr, *g = nullptr, *gn = nullptr, *vw = nullptr, *sigma = nullptr;
     int* sweeps_dev = nullptr;
-    GemmProblem *gemmM_dev = nullptr, *gemmT_dev = nullptr; int *gemmM_tp = nullptr, *gemmT_tp = nullptr;
+    GemmProblem *gemmM_dev = nullptr, *gemmT_dev = nullptr, *gemmY_dev = nullptr; int *gemmM_tp = nullptr, *gemmT_tp = nullptr, *gemmY_tp = nullptr;
+    int gemmY_tiles = 0, gemmY_tiles_run = 0;
     int gemmM_tiles = 0, gemmT_tiles = 0, gemm_nb = -1, gemmM_tiles_run = 0, gemmT_tiles_run = 0;
     size_t jacobi_smem = 0; int n_sm = 148; bool jacobi_big = false; int* jac_counter = nullptr;
     // real projection
@@ -199,7 +200,7 @@ int xfb_plan_destroy(xfb_plan* p) {
     if (!p) return 0;
     void* ptrs[] = {p->tw, p->FE, p->FO, p->IE, p->IO, p->hankel_w, p->int_wt, p->q_pts, p->A0, p->C0, p->C1, p->W0, p->W1, p->W2, p->A0s, p->C0s, p->rt0, p->stage_out,
                     p->v2d, p->unk2d, p->orders_dev, p->kind_dev, p->act_index_dev, p->radial_mask_dev, p->v0_dev, p->pd_dev, p->vt_dev,
-                    p->xt, p->tt, p->g, p->gn, p->vw, p->sigma, p->sweeps_dev, p->jac_counter, p->ident_dev, p->gn_u, p->vw_u, p->sigma_u, p->i00, p->gemmM_dev, p->gemmT_dev, p->gemmM_tp, p->gemmT_tp,
+                    p->xt, p->tt, p->g, p->gn, p->vw, p->sigma, p->sweeps_dev, p->jac_counter, p->pp, p->gn_u, p->pp_u, p->sigma_u, p->i00, p->gemmY_dev, p->gemmY_tp, p->gemmM_dev, p->gemmT_dev, p->gemmM_tp, p->gemmT_tp,
                     p->init_support_dev, p->rho_pool, p->rh_pool, p->mask_pool, p->ls_ints, p->ls_dbl, p->partial, p->err, p->mm};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& kv : p->hk_cache) cudaFree(kv.second.first);
@@ -325,11 +326,11 @@ static int ift_shell0_i(xfb_plan* p, const double2* c, int nb, cudaStream_t st) 
 // descriptors (and tile ids) of a smaller batch are a prefix of it.
 static int build_gemm_groups(xfb_plan* p, int nb_req, cudaStream_t st) {
     if (p->gemm_nb > 0) {
-        p->gemmM_tiles = nb_req * p->gemmM_tiles_run; p->gemmT_tiles = nb_req * p->gemmT_tiles_run;
+        p->gemmM_tiles = nb_req * p->gemmM_tiles_run; p->gemmT_tiles = nb_req * p->gemmT_tiles_run; p->gemmY_tiles = nb_req * p->gemmY_tiles_run;
         return 0;
     }
     const int nb = p->max_batch;
-    std::vector<GemmProblem> pm, pt; std::vector<int> tpm, tpt;
+    std::vector<GemmProblem> pm, pt, py; std::vector<int> tpm, tpt, tpy;
     for (int b = 0; b < nb; ++b) {
         for (const ProcOrder& o : p->orders) {
             GemmProblem a{};
@@ -348,32 +349,43 @@ static int build_gemm_groups(xfb_plan* p, int nb_req, cudaStream_t st) {
             c.tile0 = (int)tpt.size(); c.tiles_n = cdiv(c.N, GG_BN);
             for (int t = 0; t < cdiv(c.M, GG_BM) * c.tiles_n; ++t) tpt.push_back((int)pt.size());
             pt.push_back(c);
+            GemmProblem y{};      // vw = pp V_l^T : [n_cols x n_cols] . [n_cols x N_r]
+            y.A = p->pp + (size_t)b * p->g_run + o.g_off; y.a_rs = jacobi_stride(o.n_c); y.a_cs = 1;
+            y.B = p->vt_dev + o.pd_off; y.b_rs = p->n_r; y.b_cs = 1;
+            y.C = p->vw + (size_t)b * p->vw_run + o.vw_off; y.c_rs = jacobi_wstride(p->n_r); y.c_cs = 1;
+            y.M = o.n_cols; y.N = p->n_r; y.K = o.n_cols; y.alpha = 1.0;
+            y.tile0 = (int)tpy.size(); y.tiles_n = cdiv(y.N, GG_BN);
+            for (int t = 0; t < cdiv(y.M, GG_BM) * y.tiles_n; ++t) tpy.push_back((int)py.size());
+            py.push_back(y);
         }
     }
     XFB_CUDA(cudaMemcpyAsync(p->gemmM_dev, pm.data(), pm.size() * sizeof(GemmProblem), cudaMemcpyHostToDevice, st));
     XFB_CUDA(cudaMemcpyAsync(p->gemmT_dev, pt.data(), pt.size() * sizeof(GemmProblem), cudaMemcpyHostToDevice, st));
     XFB_CUDA(cudaMemcpyAsync(p->gemmM_tp, tpm.data(), tpm.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     XFB_CUDA(cudaMemcpyAsync(p->gemmT_tp, tpt.data(), tpt.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    XFB_CUDA(cudaMemcpyAsync(p->gemmY_dev, py.data(), py.size() * sizeof(GemmProblem), cudaMemcpyHostToDevice, st));
+    XFB_CUDA(cudaMemcpyAsync(p->gemmY_tp, tpy.data(), tpy.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     XFB_CUDA(cudaStreamSynchronize(st));
-    p->gemmM_tiles_run = (int)tpm.size() / nb; p->gemmT_tiles_run = (int)tpt.size() / nb; p->gemm_nb = nb;
-    p->gemmM_tiles = nb_req * p->gemmM_tiles_run; p->gemmT_tiles = nb_req * p->gemmT_tiles_run;
+    p->gemmM_tiles_run = (int)tpm.size() / nb; p->gemmT_tiles_run = (int)tpt.size() / nb; p->gemmY_tiles_run = (int)tpy.size() / nb; p->gemm_nb = nb;
+    p->gemmM_tiles = nb_req * p->gemmM_tiles_run; p->gemmT_tiles = nb_req * p->gemmT_tiles_run; p->gemmY_tiles = nb_req * p->gemmY_tiles_run;
     return 0;
 }
 
 // one-sided Jacobi over all (order, run) problems of a batch; kernel variant by problem size (procrustes.cuh)
-static int launch_jacobi(xfb_plan* p, const double* g, double* gn, double* vw, const double* vt, double* sigma, int nb, int* sweeps,
-                         cudaStream_t st) {
+static int launch_jacobi(xfb_plan* p, const double* g, double* gn, double* pp, double* sigma, int nb, int* sweeps, cudaStream_t st) {
     const int na = (int)p->orders.size();
     const int grid = std::min(na * nb, p->n_sm);
     const int smem_doubles = (int)(p->jacobi_smem / 8);
     if (!p->jac_counter) { if (dev_alloc(p, &p->jac_counter, 1)) return 1; }
     XFB_CUDA(cudaMemsetAsync(p->jac_counter, 0, sizeof(int), st));
     if (p->jacobi_big)
-        procrustes_jacobi_kernel<16, 256, false><<<grid, 256, p->jacobi_smem, st>>>(g, gn, vw, vt, sigma, p->orders_dev, na, nb, p->n_r, p->g_run, p->vw_run,
-                                                                            (long long)na * p->n_r, p->sv_cutoff, 1e-15, p->max_sweeps, sweeps, smem_doubles, p->jac_counter);
+        procrustes_jacobi_kernel<16, 256, false><<<grid, 256, p->jacobi_smem, st>>>(g, gn, pp, sigma, p->orders_dev, na, nb, p->n_r, p->g_run,
+                                                                                   (long long)na * p->n_r, p->sv_cutoff, 1e-15, p->max_sweeps,
+                                                                                   sweeps, smem_doubles, p->jac_counter);
     else
-        procrustes_jacobi_kernel<8, 512, true><<<grid, 512, p->jacobi_smem, st>>>(g, gn, vw, vt, sigma, p->orders_dev, na, nb, p->n_r, p->g_run, p->vw_run,
-                                                                           (long long)na * p->n_r, p->sv_cutoff, 1e-15, p->max_sweeps, sweeps, smem_doubles, p->jac_counter);
+        procrustes_jacobi_kernel<8, 512, true><<<grid, 512, p->jacobi_smem, st>>>(g, gn, pp, sigma, p->orders_dev, na, nb, p->n_r, p->g_run,
+                                                                                 (long long)na * p->n_r, p->sv_cutoff, 1e-15, p->max_sweeps,
+                                                                                 sweeps, smem_doubles, p->jac_counter);
     XFB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -399,7 +411,8 @@ static int project_i(xfb_plan* p, const double2* c_in, double2* c_out, int nb, c
                    procrustes_pack_kernel<<<dim3(na, nb), 256, 0, st>>>(c_in, p->xt, p->orders_dev, p->n_r, S, p->xt_run));
         XFB_LAUNCH(p, PG_PROC_GEMM, st, grouped_gemm_kernel<<<p->gemmM_tiles, 128, 0, st>>>(p->gemmM_dev, p->gemmM_tp));
         XFB_LAUNCH(p, PG_PROC_JACOBI, st,
-                   if (launch_jacobi(p, p->g, p->gn, p->vw, p->vt_dev, p->sigma, nb, p->sweeps_dev, st)) return 1);
+                   if (launch_jacobi(p, p->g, p->gn, p->pp, p->sigma, nb, p->sweeps_dev, st)) return 1);
+        XFB_LAUNCH(p, PG_PROC_GEMM, st, grouped_gemm_kernel<<<p->gemmY_tiles, 128, 0, st>>>(p->gemmY_dev, p->gemmY_tp));
         XFB_LAUNCH(p, PG_PROC_GEMM, st, grouped_gemm_kernel<<<p->gemmT_tiles, 128, 0, st>>>(p->gemmT_dev, p->gemmT_tp));
     }
     XFB_LAUNCH(p, PG_PROC_PACK, st,
@@ -549,25 +562,22 @@ int xfb_plan_set_projection(xfb_plan* p, const xfb_projection_desc* d) {
         XFB_CUDA(cudaMemset(p->vw, 0, B * p->vw_run * sizeof(double)));     // rows of dropped columns are never written: keep them finite
         if (dev_alloc(p, &p->sigma, B * na * n_r)) return 1;
         if (dev_alloc(p, &p->sweeps_dev, B * na)) return 1;
-        {
-            std::vector<double> ident(vt.size(), 0.0);
-            for (const ProcOrder& o : p->orders)
-                for (int c = 0; c < o.n_cols; ++c) ident[(size_t)o.pd_off + (size_t)c * n_r + c] = 1.0;
-            if (dev_upload(p, &p->ident_dev, ident.data(), ident.size())) return 1;
-        }
+        if (dev_alloc(p, &p->pp, B * p->g_run)) return 1;
         if (dev_alloc(p, &p->gn_u, (size_t)p->g_run)) return 1;
-        if (dev_alloc(p, &p->vw_u, (size_t)p->vw_run)) return 1;
-        XFB_CUDA(cudaMemset(p->vw_u, 0, (size_t)p->vw_run * sizeof(double)));
+        if (dev_alloc(p, &p->pp_u, (size_t)p->g_run)) return 1;
         if (dev_alloc(p, &p->sigma_u, na * n_r)) return 1;
         if (dev_alloc(p, &p->gemmM_dev, B * na)) return 1;
         if (dev_alloc(p, &p->gemmT_dev, B * na)) return 1;
-        size_t tiles_m = 0, tiles_t = 0;
+        if (dev_alloc(p, &p->gemmY_dev, B * na)) return 1;
+        size_t tiles_m = 0, tiles_t = 0, tiles_y = 0;
         for (const ProcOrder& o : p->orders) {
             tiles_m += (size_t)cdiv(o.n_cols, GG_BM) * cdiv(o.n_c, GG_BN);
             tiles_t += (size_t)cdiv(o.n_c, GG_BM) * cdiv(n_r, GG_BN);
+            tiles_y += (size_t)cdiv(o.n_cols, GG_BM) * cdiv(n_r, GG_BN);
         }
         if (dev_alloc(p, &p->gemmM_tp, B * tiles_m)) return 1;
         if (dev_alloc(p, &p->gemmT_tp, B * tiles_t)) return 1;
+        if (dev_alloc(p, &p->gemmY_tp, B * tiles_y)) return 1;
         if (p->jacobi_big) XFB_CUDA(cudaFuncSetAttribute(procrustes_jacobi_kernel<16, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
         else XFB_CUDA(cudaFuncSetAttribute(procrustes_jacobi_kernel<8, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     } else {
@@ -683,11 +693,11 @@ int xfb_get_unknowns(xfb_plan* p, int32_t run, int32_t order, double* out_dev, v
     }
     const int na = (int)p->orders.size();
     if (p->unk_run != run || p->unk_stamp != p->proj_calls) {
-        if (launch_jacobi(p, p->g + (size_t)run * p->g_run, p->gn_u, p->vw_u, p->ident_dev, p->sigma_u, 1, nullptr, st)) return 1;
+        if (launch_jacobi(p, p->g + (size_t)run * p->g_run, p->gn_u, p->pp_u, p->sigma_u, 1, nullptr, st)) return 1;
         p->unk_run = run; p->unk_stamp = p->proj_calls;
     }
     const ProcOrder o = p->orders[act[order]];
-    unknown_assemble_kernel<<<o.n_cols, 128, 0, st>>>(p->gn_u + o.g_off, p->vw_u + o.vw_off, jacobi_stride(o.n_c), jacobi_wstride(p->n_r), o.n_cols, o.n_c, o.l,
+    unknown_assemble_kernel<<<o.n_cols, 128, 0, st>>>(p->gn_u + o.g_off, p->pp_u + o.g_off, jacobi_stride(o.n_c), o.n_cols, o.n_c, o.l,
                                                       (double2*)out_dev);
     XFB_CUDA(cudaGetLastError());
     return 0;
