@@ -113,9 +113,10 @@ def algorithmic_bytes(nb):
 
 
 def hankel_flops(nb):
+    # complex rows x real matrix: per (row, k) N_r real-times-complex MACs = 2 FMAs = 4 flops
     if DIMS == 2:
-        return nb * 8.0 * N_R * N_R * N_PHI
-    return nb * 8.0 * N_R * N_R * (L_MAX + 1) ** 2     # complex x real: 2 real GEMMs, 2 flops per MAC
+        return nb * 4.0 * N_R * N_R * N_PHI
+    return nb * 4.0 * N_R * N_R * (L_MAX + 1) ** 2
 
 
 # ------------------------------------------------------------------------------------------------

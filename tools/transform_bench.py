@@ -58,7 +58,6 @@ def run(L, n_r, target_bytes, reps):
     ms_ft = bench(lambda: plan.ift(plan.ft(x)), reps)
     peak, src = peaks()
     bytes_pair = nb * 2 * (G + C) * 16                         # forward: read G write C; inverse: read C write G
-    hankel_flops = nb * 8.0 * n_r * n_r * (L + 1) ** 2         # complex rows x real matrix: 4 N_r^2 (L+1)^2 MACs... *2 flops
     out = {'L': L, 'n_r': n_r, 'n_theta': n_theta, 'n_phi': n_phi, 'batch': nb, 'grid_GiB': nb * G * 16 / 2 ** 30,
            'sht_roundtrip_rel_l2': err_sht, 'ft_linearity_rel_l2': err_lin,
            'sht_pair_ms': ms_sht, 'sht_pair_GBps': bytes_pair / ms_sht / 1e6, 'sht_pair_frac_of_hbm_peak': bytes_pair / ms_sht / 1e6 / peak,

@@ -101,6 +101,107 @@ __global__ void __launch_bounds__(256) hankel_kernel(const double2* __restrict__
     }
 }
 
+// v2: same contraction, operands fetched with cp.async into a 3-stage ring (A rows as interleaved complex: one 128-bit
+// shared load gives re and im of a fragment element), so the DMMA pipe is not idle while the next K chunk is loaded.
+// Needs N_r even (16-byte chunks of the real weight rows); the v1 kernel covers odd sizes.
+#define HK2_ST 3
+#define HK2_LDA (HK_BK + 4)      // double2 units: rows 64 B apart mod 128 -> conflict-free fragment loads
+#define HK2_LDB (HK_BN + 4)      // doubles
+static inline size_t hankel2_smem() { return (size_t)HK2_ST * (HK_BM * HK2_LDA * sizeof(double2) + HK_BK * HK2_LDB * sizeof(double)); }
+__device__ __forceinline__ void hk_cp_async16(void* smem, const void* gmem, bool valid) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    const int bytes = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(bytes));
+}
+__global__ void __launch_bounds__(256, 2) hankel2_kernel(const double2* __restrict__ in, double2* __restrict__ out,
+                                                         const double* __restrict__ W, const HankelTile* __restrict__ tiles,
+                                                         int n_r, int n_sum, int skip, double scale, int inverse) {
+    extern __shared__ __align__(16) unsigned char smem_hk[];
+    double2* As = reinterpret_cast<double2*>(smem_hk);                                     // [ST][HK_BM][HK2_LDA]
+    double* Bs = reinterpret_cast<double*>(As + HK2_ST * HK_BM * HK2_LDA);                 // [ST][HK_BK][HK2_LDB]
+    const HankelTile t = tiles[blockIdx.x];
+    const int k_tile0 = blockIdx.y * HK_BN;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps, warp tile 32 rows x 16 cols
+    const double* Wl = W + (size_t)t.l * n_sum * n_r;
+    double cre[4][2][2] = {}, cim[4][2][2] = {};
+    const int ar = lane >> 2, ak = lane & 3;
+    const int n_chunks = (n_sum + HK_BK - 1) / HK_BK;
+
+    auto fetch = [&](int ch, int st) {
+        if (ch < n_chunks) {
+            const int p0 = ch * HK_BK;
+            double2* a = As + (size_t)st * HK_BM * HK2_LDA;
+            double* b = Bs + (size_t)st * HK_BK * HK2_LDB;
+#pragma unroll
+            for (int q = 0; q < (HK_BM * HK_BK) / 256; ++q) {      // A: 64 rows x 16 p complex, 16 consecutive threads = 256 contiguous bytes
+                const int item = tid + q * 256;
+                const int row = item >> 4, pp = item & 15;
+                const int grow = t.row0 + row;
+                const bool ok = grow < t.row_end && (p0 + pp) < n_sum;
+                hk_cp_async16(a + row * HK2_LDA + pp, in + (size_t)(ok ? grow : t.row0) * n_r + skip + (ok ? p0 + pp : 0), ok);
+            }
+#pragma unroll
+            for (int q = 0; q < (HK_BK * HK_BN / 2) / 256; ++q) {  // B: 16 p x 64 k doubles as 16-byte pairs
+                const int item = tid + q * 256;
+                const int pp = item >> 5, kk = (item & 31) * 2;
+                const bool ok = (p0 + pp) < n_sum && (k_tile0 + kk) < n_r;
+                hk_cp_async16(b + pp * HK2_LDB + kk, Wl + (size_t)(ok ? p0 + pp : 0) * n_r + (ok ? k_tile0 + kk : 0), ok);
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+#pragma unroll
+    for (int s_ = 0; s_ < HK2_ST - 1; ++s_) fetch(s_, s_);
+    int st = 0;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(HK2_ST - 2));
+        __syncthreads();
+        fetch(ch + HK2_ST - 1, (st + HK2_ST - 1) % HK2_ST);
+        const double2* a = As + (size_t)st * HK_BM * HK2_LDA;
+        const double* b_ = Bs + (size_t)st * HK_BK * HK2_LDB;
+#pragma unroll
+        for (int k0 = 0; k0 < HK_BK; k0 += 4) {
+            double b[2];
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) b[nb] = b_[(k0 + ak) * HK2_LDB + wn * 16 + nb * 8 + ar];
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb) {
+                const double2 x = a[(wm * 32 + mb * 8 + ar) * HK2_LDA + k0 + ak];
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb) {
+                    dmma884(cre[mb][nb][0], cre[mb][nb][1], x.x, b[nb]);
+                    dmma884(cim[mb][nb][0], cim[mb][nb][1], x.y, b[nb]);
+                }
+            }
+        }
+        st = (st + 1) % HK2_ST;
+    }
+    const int ph = t.ph;
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) {
+        const int grow = t.row0 + wm * 32 + mb * 8 + ar;
+        if (grow >= t.row_end) continue;
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+            const int k = k_tile0 + wn * 16 + nb * 8 + 2 * ak;
+            double2 o[2];
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const double x = cre[mb][nb][cc] * scale, y = cim[mb][nb][cc] * scale;
+                double2 r;
+                if (ph == 0) r = make_double2(x, y);
+                else if (ph == 2) r = make_double2(-x, -y);
+                else if ((ph == 1) != (inverse != 0)) r = make_double2(y, -x);   // multiply by -i
+                else r = make_double2(-y, x);                                     // multiply by +i
+                o[cc] = r;
+            }
+            if (k < n_r) out[(size_t)grow * n_r + k] = o[0];
+            if (k + 1 < n_r) out[(size_t)grow * n_r + k + 1] = o[1];
+        }
+    }
+}
+
 // Hankel transform evaluated at the first output radius only: out0[row] = (-+i)^l scale sum_p in[row][p+skip] W_l[p][0].
 // Used by the fused ft_stab step: only shell 0 of IFT(rho_hat) is needed.  One warp per row.
 __global__ void hankel_row0_kernel(const double2* __restrict__ in, double2* __restrict__ out0, const double* __restrict__ W, int n_rows,

@@ -182,3 +182,121 @@ static inline size_t legendre_inv_smem(int n_theta, int NP) {
     (void)n_theta;
     return (size_t)(4 * LEG_ROWS * (NP + 4) + 2 * NP * LEG_LDB) * sizeof(double);
 }
+
+// =====================================================================================================================
+// v2 kernels for the common small configuration (n_theta <= 64, L <= 63: K2 <= 32, NP <= 32) -- the L=63 / 64 x 128
+// workload of the bench.  One CTA keeps the Legendre tables of ONE order m in shared memory and walks over many groups
+// of shells; the phi-Fourier rows (forward) / coefficient rows (inverse) of the NEXT group are fetched with cp.async
+// while the current group is multiplied, so HBM loads stay in flight all the time (the v1 kernels stall on their one
+// load phase per CTA: ncu long-scoreboard 6.9 of 16 cycles per issue).  The north/south fold is done on the fly when the
+// A fragments are read (2 x 128-bit shared loads give e = x + y and o = x - y for re and im at once).
+//   rows of a group: 16 shells x (+m, -m)   or, pos_only (real field: c_{l,-m} = (-1)^m conj c_{l,m} is redundant) and
+//   for m = 0, 32 shells x (+m).
+// =====================================================================================================================
+#define LEG2_THREADS 256
+#define LEG2_ROWS 32
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int bytes = valid ? 16 : 0;                     // src-size 0: zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+#define LEG2_FR 16          // forward: rows per group (8 shells x +-m, or 16 shells)
+#define LEG2_FST 3          // forward: cp.async stages (2 groups in flight per CTA, 3 CTAs per SM)
+static inline size_t legendre2_fwd_smem(int n_theta) {
+    return (size_t)LEG2_FST * LEG2_FR * (n_theta + 4) * sizeof(double2) + (size_t)2 * (n_theta / 2) * LEG_LDB * sizeof(double);
+}
+static inline size_t legendre2_inv_smem(int NP, int n_theta) {
+    return (size_t)2 * 2 * LEG2_ROWS * (NP + 2) * sizeof(double2) + (size_t)2 * NP * (n_theta / 2 + 4) * sizeof(double);
+}
+
+template <int R, int ST>
+__global__ void __launch_bounds__(LEG2_THREADS, 3) legendre2_forward_kernel(const double2* __restrict__ a, double2* __restrict__ c,
+                                                                           const double* __restrict__ FE, const double* __restrict__ FO,
+                                                                           int S, int l_max, int n_theta, int NP, int pos_only) {
+    extern __shared__ __align__(16) unsigned char smem_leg2[];
+    constexpr int MB = R / 16;                             // 8-row MMA blocks per warp
+    const int K2 = n_theta >> 1;
+    const int RS = n_theta + 4;                            // row stride (double2): rows 64 B apart mod 128 -> conflict-free fragments
+    double2* raw = reinterpret_cast<double2*>(smem_leg2);  // [ST][R][RS]
+    double* Be = reinterpret_cast<double*>(raw + ST * R * RS);          // [K2][LEG_LDB]
+    double* Bo = Be + K2 * LEG_LDB;
+    const int m = blockIdx.y;
+    const int M2 = 2 * l_max + 1;
+    const bool both = (!pos_only) && m > 0;
+    const int SH = both ? R / 2 : R;                       // shells per group
+    const int n_groups = (S + SH - 1) / SH;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ar = lane >> 2, ak = lane & 3;
+    const int wn = warp & 3, r0 = (warp >> 2) * (R / 2);
+    const int ne = (l_max - m) / 2 + 1, no = (l_max - m + 1) / 2;
+    const bool do_e = wn * 8 < ne, do_o = wn * 8 < no;     // column blocks that are pure padding are skipped
+
+    auto fetch = [&](int g, int buf) {
+        if (g < n_groups) {
+            double2* dst = raw + (size_t)buf * R * RS;
+            for (int item = tid; item < R * n_theta; item += LEG2_THREADS) {
+                const int row = item / n_theta, j = item - row * n_theta;
+                const int sh = g * SH + (both ? (row % (R / 2)) : row), sign = both ? (row / (R / 2)) : 0;
+                const bool ok = sh < S;
+                const int mm = sign ? (M2 - m) : m;
+                cp_async16(dst + row * RS + j, a + ((size_t)(ok ? sh : 0) * M2 + mm) * n_theta + j, ok);
+            }
+        }
+        cp_async_commit();                                 // (possibly empty) group: keeps the wait count uniform
+    };
+
+    // a CTA walks over a CONTIGUOUS range of shell groups: its stores to one coefficient row (l, m) are adjacent in time
+    // and address, so L2 merges them into long DRAM bursts
+    const int per_cta = (n_groups + gridDim.x - 1) / gridDim.x;
+    int g = blockIdx.x * per_cta;
+    const int g_end = min(n_groups, g + per_cta);
+    if (g >= g_end) return;
+#pragma unroll
+    for (int s = 0; s < ST - 1; ++s) fetch(g + s < g_end ? g + s : n_groups, s);
+    const double* FEm = FE + (size_t)m * K2 * NP;
+    const double* FOm = FO + (size_t)m * K2 * NP;
+    for (int item = tid; item < K2 * LEG_NB; item += LEG2_THREADS) {
+        const int j = item / LEG_NB, cc = item - j * LEG_NB;
+        const bool ok = cc < NP;
+        Be[j * LEG_LDB + cc] = ok ? __ldg(FEm + (size_t)j * NP + cc) : 0.0;
+        Bo[j * LEG_LDB + cc] = ok ? __ldg(FOm + (size_t)j * NP + cc) : 0.0;
+    }
+    int buf = 0;
+    for (; g < g_end; ++g) {
+        cp_async_wait<ST - 2>();                           // the oldest outstanding group (this one) has landed
+        __syncthreads();                                   // ... for every thread; and everyone is done with the buffer refilled next
+        fetch(g + ST - 1 < g_end ? g + ST - 1 : n_groups, (buf + ST - 1) % ST);
+        const double2* rw = raw + (size_t)buf * R * RS;
+        double ere[MB][2] = {}, eim[MB][2] = {}, ore_[MB][2] = {}, oim[MB][2] = {};
+        for (int k0 = 0; k0 < K2; k0 += 4) {
+            const double be = Be[(k0 + ak) * LEG_LDB + wn * 8 + ar], bo = Bo[(k0 + ak) * LEG_LDB + wn * 8 + ar];
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+                const double2* rr = rw + (r0 + mb * 8 + ar) * RS;
+                const double2 x = rr[k0 + ak], y = rr[n_theta - 1 - k0 - ak];
+                if (do_e) { dmma884(ere[mb][0], ere[mb][1], x.x + y.x, be); dmma884(eim[mb][0], eim[mb][1], x.y + y.y, be); }
+                if (do_o) { dmma884(ore_[mb][0], ore_[mb][1], x.x - y.x, bo); dmma884(oim[mb][0], oim[mb][1], x.y - y.y, bo); }
+            }
+        }
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) {
+            const int row = r0 + mb * 8 + ar;
+            const int sh = g * SH + (both ? (row % (R / 2)) : row), sign = both ? (row / (R / 2)) : 0;
+            if (sh >= S) continue;
+            const double sg = (sign && (m & 1)) ? -1.0 : 1.0;          // (-1)^m on the -m rows
+            const int ms = sign ? -m : m;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int col = wn * 8 + 2 * ak + cc;
+                const int le = m + 2 * col, lo = le + 1;
+                if (do_e && le <= l_max) c[(size_t)(le * (le + 1) + ms) * S + sh] = make_double2(sg * ere[mb][cc], sg * eim[mb][cc]);
+                if (do_o && lo <= l_max) c[(size_t)(lo * (lo + 1) + ms) * S + sh] = make_double2(sg * ore_[mb][cc], sg * oim[mb][cc]);
+            }
+        }
+        buf = (buf + 1) % ST;
+    }
+}

@@ -36,6 +36,7 @@ struct xfb_plan {
     double2 *A0 = nullptr, *C0 = nullptr, *C1 = nullptr, *W0 = nullptr, *W1 = nullptr, *W2 = nullptr;
     double2 *A0s = nullptr, *C0s = nullptr, *rt0 = nullptr;   // shell-0 side path of the fused ft_stab step
     int fused_ft_stab = 1;
+    bool leg2 = false;                              // v2 Legendre kernels (K2 <= 32, NP <= 32)
     // host-buffer pipeline (xfb_mtip_step_host)
     cudaStream_t s_in = nullptr, s_out = nullptr; cudaEvent_t ev_start = nullptr; std::vector<cudaEvent_t> ev_in, ev_comp;
     double2* stage_out = nullptr; int host_chunk = 16;
@@ -190,6 +191,9 @@ int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
     if (dev_alloc(p, &p->A0s, B * p->M2 * p->n_theta)) return 1;
     if (dev_alloc(p, &p->C0s, B * p->NLM)) return 1;
     if (dev_alloc(p, &p->rt0, B * p->n_theta * p->n_phi)) return 1;
+    p->leg2 = (p->n_theta / 2 <= 32 && p->NP <= 32 && p->n_theta % 4 == 0);
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, dev); }
+    if (p->leg2) XFB_CUDA(cudaFuncSetAttribute(legendre2_forward_kernel<LEG2_FR, LEG2_FST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre2_fwd_smem(p->n_theta)));
     XFB_CUDA(cudaFuncSetAttribute(legendre_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre_fwd_smem(p->n_theta)));
     XFB_CUDA(cudaFuncSetAttribute(legendre_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre_inv_smem(p->n_theta, p->NP)));
     *out = p;
@@ -254,6 +258,14 @@ static int sht_forward_i(xfb_plan* p, SlotView in, int shells_per_run, double2* 
         return 0;
     }
     XFB_LAUNCH(p, PG_FFT, st, if (launch_fft(true, p->n_phi, in, shells_per_run, sub, p->A0, p->tw, S, p->n_theta, p->L, st)) return 1);
+    if (p->leg2) {     // small configuration: table-resident, cp.async double-buffered kernel
+        const int groups = cdiv(S, LEG2_FR / 2);
+        dim3 g2(std::min(groups, std::max(1, (3 * p->n_sm * 4) / (p->L + 1))), p->L + 1);
+        XFB_LAUNCH(p, PG_LEGENDRE, st,
+                   legendre2_forward_kernel<LEG2_FR, LEG2_FST><<<g2, LEG2_THREADS, legendre2_fwd_smem(p->n_theta), st>>>(p->A0, c_out, p->FE, p->FO, S, p->L, p->n_theta,
+                                                                                                     p->NP, 0));
+        return 0;
+    }
     dim3 g(cdiv(S, 16), p->L + 1);
     XFB_LAUNCH(p, PG_LEGENDRE, st,
                legendre_forward_kernel<<<g, LEG_THREADS, legendre_fwd_smem(p->n_theta), st>>>(p->A0, c_out, p->FE, p->FO, S, p->L, p->n_theta, p->NP));
@@ -297,6 +309,14 @@ static int hankel_i(xfb_plan* p, int dir, const double2* c_in, double2* c_out, i
     }
     p->hk_tiles = hit->second.first; p->hk_tiles_n = hit->second.second;
     dim3 g(p->hk_tiles_n, cdiv(p->n_r, HK_BN));
+    if (p->n_r % 2 == 0) {
+        static bool attr_done = false;
+        if (!attr_done) { XFB_CUDA(cudaFuncSetAttribute(hankel2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hankel2_smem())); attr_done = true; }
+        XFB_LAUNCH(p, PG_HANKEL, st,
+                   hankel2_kernel<<<g, 256, hankel2_smem(), st>>>(c_in, c_out, p->hankel_w, p->hk_tiles, p->n_r, p->hankel_n_sum, p->hankel_skip,
+                                                                 dir == 0 ? p->hk_fwd_scale : p->hk_inv_scale, dir));
+        return 0;
+    }
     XFB_LAUNCH(p, PG_HANKEL, st,
                hankel_kernel<<<g, 256, 0, st>>>(c_in, c_out, p->hankel_w, p->hk_tiles, p->n_r, p->hankel_n_sum, p->hankel_skip,
                                                 dir == 0 ? p->hk_fwd_scale : p->hk_inv_scale, dir));
