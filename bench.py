@@ -102,8 +102,10 @@ def algorithmic_bytes(nb):
     C = N_R * (L_MAX + 1) ** 2
     A = N_R * (2 * L_MAX + 1) * N_THETA
     return {
-        'fft_phi': nb * (G + A) * 16,          # one grid read/written + one phi-Fourier array written/read
-        'legendre': nb * (A + C) * 16,
+        # per launch, averaged over the 6 launches of a step: 4 complex transforms + the 2 of the REAL intensity field, which
+        # move only the m >= 0 half of the phi-Fourier array and of the coefficients
+        'fft_phi': nb * (G + A * 5 / 6) * 16,  # one grid read/written + one phi-Fourier array written/read
+        'legendre': nb * (A + C) * 5 / 6 * 16,
         'hankel': nb * 2 * C * 16,
         'real_update': nb * (3 * G * 16 + G),  # IFT(rho_hat'-rho_hat), rho_prev in, rho_next out, support mask (fused ft_stab)
         'pointwise': nb * int(2.5 * G * 16),   # square: G in, G out ; modify_intensity: 2G in, G out  -> average per launch

@@ -103,9 +103,11 @@ __global__ void __launch_bounds__(LEG_THREADS, 4) legendre_forward_kernel(const 
     }
 }
 
+// pos_only: the field is real (c_{l,-m} = (-1)^m conj c_{l,m}), only the m >= 0 rows of `a` are produced (the phi-FFT
+// completes the spectrum by conjugate symmetry) and a CTA takes 32 shells instead of 16 shells x (+m, -m).
 __global__ void __launch_bounds__(LEG_THREADS, 4) legendre_inverse_kernel(const double2* __restrict__ c, double2* __restrict__ a,
                                                                const double* __restrict__ IE, const double* __restrict__ IO,
-                                                               int S, int l_max, int n_theta, int NP) {
+                                                               int S, int l_max, int n_theta, int NP, int pos_only) {
     extern __shared__ double smem_leg[];
     const int K2 = n_theta >> 1;
     const int lda = NP + 4;
@@ -116,15 +118,15 @@ __global__ void __launch_bounds__(LEG_THREADS, 4) legendre_inverse_kernel(const 
     double* Be = Co_im + LEG_ROWS * lda;
     double* Bo = Be + NP * LEG_LDB;
     const int m = blockIdx.y;
-    const int sh0 = blockIdx.x * 16;
+    const int sh0 = blockIdx.x * (pos_only ? 32 : 16);
     const int M2 = 2 * l_max + 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // ---- stage A: gather coefficients of order +-m, (-1)^m on the -m rows; shells fastest for coalescing
     for (int item = tid; item < 2 * NP * LEG_ROWS; item += LEG_THREADS) {
-        const int rr = item & 15;
+        const int rr = pos_only ? (item & 31) : (item & 15);
         int rest = item >> 4;
-        const int sign = rest & 1;
+        const int sign = pos_only ? 0 : (rest & 1);
         rest >>= 1;
         const int i = rest % NP, par = rest / NP;
         const int l = m + par + 2 * i;
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(LEG_THREADS, 4) legendre_inverse_kernel(const 
             v = ldg2(c + (size_t)(l * (l + 1) + (sign ? -m : m)) * S + sh);
             if (sign && (m & 1)) { v.x = -v.x; v.y = -v.y; }
         }
-        const int row = sign * 16 + rr;
+        const int row = pos_only ? rr : sign * 16 + rr;
         if (par == 0) { Ce_re[row * lda + i] = v.x; Ce_im[row * lda + i] = v.y; }
         else          { Co_re[row * lda + i] = v.x; Co_im[row * lda + i] = v.y; }
     }
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(LEG_THREADS, 4) legendre_inverse_kernel(const 
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb) {
             const int row = r0 + mb * 8 + (lane >> 2);
-            const int sh = sh0 + (row & 15), sign = row >> 4;
+            const int sh = sh0 + (pos_only ? row : (row & 15)), sign = pos_only ? 0 : (row >> 4);
             if (sh >= S || (sign && m == 0)) continue;
             const int mm = sign ? (M2 - m) : m;
             double2* dst = a + ((size_t)sh * M2 + mm) * n_theta;

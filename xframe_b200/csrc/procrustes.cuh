@@ -640,7 +640,7 @@ __global__ void procrustes_unpack_kernel(const double2* __restrict__ c_in, doubl
                                          const ProcOrder* __restrict__ orders, const int* __restrict__ kind,
                                          const int* __restrict__ act_index, const uint8_t* __restrict__ radial_mask,
                                          const double* __restrict__ v0, double inv_sqrt_np, int l_max, int n_r, int S,
-                                         long long xt_run_stride) {
+                                         long long xt_run_stride, int half) {
     const int l = blockIdx.x;
     const int b = blockIdx.y;
     const int kd = kind[l];
@@ -648,7 +648,8 @@ __global__ void procrustes_unpack_kernel(const double2* __restrict__ c_in, doubl
     const double* T = nullptr;
     if (kd == ORD_ACTIVE) T = tt + (size_t)b * xt_run_stride + orders[act_index[l]].xt_off;
     const int n_c = 2 * l + 1;
-    for (int idx = threadIdx.x; idx < n_c * n_r; idx += blockDim.x) {
+    // half: the coefficients belong to a real field -- only m >= 0 exists in c_in and only m >= 0 is written
+    for (int idx = threadIdx.x + (half ? l * n_r : 0); idx < n_c * n_r; idx += blockDim.x) {
         const int mi = idx / n_r, k = idx - mi * n_r;   // mi = m + l
         const int m = mi - l;
         const size_t pos = (size_t)(l * (l + 1) + m) * S + (size_t)b * n_r + k;

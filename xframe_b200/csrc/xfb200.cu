@@ -37,6 +37,7 @@ struct xfb_plan {
     double2 *A0s = nullptr, *C0s = nullptr, *rt0 = nullptr;   // shell-0 side path of the fused ft_stab step
     int fused_ft_stab = 1;
     bool leg2 = false;                              // v2 Legendre kernels (K2 <= 32, NP <= 32)
+    int half_spectrum = 1;                          // real intensity fields: transform only the m >= 0 half (3-D, v2 Legendre)
     // host-buffer pipeline (xfb_mtip_step_host)
     cudaStream_t s_in = nullptr, s_out = nullptr; cudaEvent_t ev_start = nullptr; std::vector<cudaEvent_t> ev_in, ev_comp;
     double2* stage_out = nullptr; int host_chunk = 16;
@@ -249,21 +250,27 @@ int xfb_profile_read(xfb_plan* p, int32_t n_max, char* names, double* ms, int64_
 }  // extern "C"
 
 // ---- internal building blocks -----------------------------------------------------------
+// real_only: the input field is real.  2-D: rfft semantics.  3-D (v2 Legendre only): only the m >= 0 half of the spectrum
+// is produced (c_{l,-m} = (-1)^m conj c_{l,m} is redundant) -- the caller must consume m >= 0 only.  Returns the mode used
+// in *half_used.
 static int sht_forward_i(xfb_plan* p, SlotView in, int shells_per_run, double2* c_out, int S, cudaStream_t st,
-                         const double2* sub = nullptr, int real_only = 0) {
+                         const double2* sub = nullptr, int real_only = 0, int* half_used = nullptr) {
+    if (half_used) *half_used = 0;
     if (p->dims == 2) {   // circular harmonic transform: fft(x)/n_phi  (mathLibrary.py:469-475,484-490)
         XFB_LAUNCH(p, PG_FFT, st,
                    dft2d_forward_kernel<<<cdiv(S, DFT_ROWS), DFT_THREADS, dft_smem(p->n_phi), st>>>(in, shells_per_run, sub, c_out, S, p->n_phi,
                                                                                                    1.0 / p->n_phi, real_only));
         return 0;
     }
-    XFB_LAUNCH(p, PG_FFT, st, if (launch_fft(true, p->n_phi, in, shells_per_run, sub, p->A0, p->tw, S, p->n_theta, p->L, st)) return 1);
+    const int half = (real_only && p->leg2 && p->half_spectrum) ? 1 : 0;
+    if (half_used) *half_used = half;
+    XFB_LAUNCH(p, PG_FFT, st, if (launch_fft(true, p->n_phi, in, shells_per_run, sub, p->A0, p->tw, S, p->n_theta, p->L, st, half)) return 1);
     if (p->leg2) {     // small configuration: table-resident, cp.async double-buffered kernel
-        const int groups = cdiv(S, LEG2_FR / 2);
+        const int groups = cdiv(S, half ? LEG2_FR : LEG2_FR / 2);
         dim3 g2(std::min(groups, std::max(1, (3 * p->n_sm * 4) / (p->L + 1))), p->L + 1);
         XFB_LAUNCH(p, PG_LEGENDRE, st,
                    legendre2_forward_kernel<LEG2_FR, LEG2_FST><<<g2, LEG2_THREADS, legendre2_fwd_smem(p->n_theta), st>>>(p->A0, c_out, p->FE, p->FO, S, p->L, p->n_theta,
-                                                                                                     p->NP, 0));
+                                                                                                     p->NP, half));
         return 0;
     }
     dim3 g(cdiv(S, 16), p->L + 1);
@@ -277,11 +284,13 @@ static int sht_inverse_i(xfb_plan* p, const double2* c_in, double2* grid_out, in
                    dft2d_inverse_kernel<<<cdiv(S, DFT_ROWS), DFT_THREADS, dft_smem(p->n_phi), st>>>(c_in, grid_out, S, p->n_phi, herm));
         return 0;
     }
-    dim3 g(cdiv(S, 16), p->L + 1);
+    // herm (3-D): the coefficients belong to a real field and only m >= 0 is valid in c_in
+    dim3 g(cdiv(S, herm ? 32 : 16), p->L + 1);
     XFB_LAUNCH(p, PG_LEGENDRE, st,
-               legendre_inverse_kernel<<<g, LEG_THREADS, legendre_inv_smem(p->n_theta, p->NP), st>>>(c_in, p->A0, p->IE, p->IO, S, p->L, p->n_theta, p->NP));
+               legendre_inverse_kernel<<<g, LEG_THREADS, legendre_inv_smem(p->n_theta, p->NP), st>>>(c_in, p->A0, p->IE, p->IO, S, p->L, p->n_theta, p->NP,
+                                                                                                     herm));
     XFB_LAUNCH(p, PG_FFT, st,
-               if (launch_fft(false, p->n_phi, flat_view(p->A0, 0), 1, nullptr, grid_out, p->tw, S, p->n_theta, p->L, st)) return 1);
+               if (launch_fft(false, p->n_phi, flat_view(p->A0, 0), 1, nullptr, grid_out, p->tw, S, p->n_theta, p->L, st, herm)) return 1);
     return 0;
 }
 static int hankel_i(xfb_plan* p, int dir, const double2* c_in, double2* c_out, int nb, cudaStream_t st) {
@@ -336,7 +345,7 @@ static int ift_shell0_i(xfb_plan* p, const double2* c, int nb, cudaStream_t st) 
                                                                   p->hk_inv_scale, 1));
     dim3 g(cdiv(nb, 16), p->L + 1);
     XFB_LAUNCH(p, PG_MISC, st,
-               legendre_inverse_kernel<<<g, LEG_THREADS, legendre_inv_smem(p->n_theta, p->NP), st>>>(p->C0s, p->A0s, p->IE, p->IO, nb, p->L, p->n_theta, p->NP));
+               legendre_inverse_kernel<<<g, LEG_THREADS, legendre_inv_smem(p->n_theta, p->NP), st>>>(p->C0s, p->A0s, p->IE, p->IO, nb, p->L, p->n_theta, p->NP, 0));
     XFB_LAUNCH(p, PG_MISC, st,
                if (launch_fft(false, p->n_phi, flat_view(p->A0s, 0), 1, nullptr, p->rt0, p->tw, nb, p->n_theta, p->L, st)) return 1);
     return 0;
@@ -411,7 +420,7 @@ static int launch_jacobi(xfb_plan* p, const double* g, double* gn, double* pp, d
 }
 
 // I coefficients (internal layout) -> projected coefficients
-static int project_i(xfb_plan* p, const double2* c_in, double2* c_out, int nb, cudaStream_t st) {
+static int project_i(xfb_plan* p, const double2* c_in, double2* c_out, int nb, cudaStream_t st, int half = 0) {
     if (!p->has_proj) XFB_FAIL("projection constants not set (xfb_plan_set_projection)");
     const int S = nb * p->n_r;
     if (p->dims == 2) {
@@ -438,7 +447,7 @@ static int project_i(xfb_plan* p, const double2* c_in, double2* c_out, int nb, c
     XFB_LAUNCH(p, PG_PROC_PACK, st,
                procrustes_unpack_kernel<<<dim3(p->L + 1, nb), 256, 0, st>>>(c_in, c_out, p->tt, p->orders_dev, p->kind_dev, p->act_index_dev,
                                                                             p->radial_mask_dev, p->v0_dev, p->inv_sqrt_np, p->L, p->n_r, S,
-                                                                            p->xt_run));
+                                                                            p->xt_run, half));
     return 0;
 }
 
@@ -796,11 +805,12 @@ static int iterate_range(xfb_plan* p, int b0, int nb, int method, int ft_stab, d
     }
     // 2. |rho_hat|^2 -> I_lm                                 (:519-520)
     XFB_LAUNCH(p, PG_POINTWISE, st, square_kernel<<<ew_blocks((long long)nb * p->G), 256, 0, st>>>(p->W0, p->W1, (long long)nb * p->G));
-    if (sht_forward_i(p, flat_view(p->W1, p->G), p->n_r, p->C0, S, st, nullptr, p->dims == 2)) return 1;   // 2-D: 'real' transform (reconstruct.py:347-348)
+    int half = 0;                                             // |rho_hat|^2 is real: half spectrum (2-D: the 'real' transform, reconstruct.py:347-348)
+    if (sht_forward_i(p, flat_view(p->W1, p->G), p->n_r, p->C0, S, st, nullptr, 1, &half)) return 1;
     // 3. projection onto the invariants                      (:521-523)
-    if (project_i(p, p->C0, p->C1, nb, st)) return 1;
+    if (project_i(p, p->C0, p->C1, nb, st, half)) return 1;
     // 4. I_proj on the grid, modified intensity              (:524-525)
-    if (sht_inverse_i(p, p->C1, p->W1, S, st, p->dims == 2)) return 1;
+    if (sht_inverse_i(p, p->C1, p->W1, S, st, p->dims == 2 ? 1 : half)) return 1;
     XFB_LAUNCH(p, PG_POINTWISE, st,
                modify_intensity_kernel<<<dim3(eb, nb), 256, 0, st>>>(p->W0, p->W1, pv(p->rh_pool, p->ls.rh_next), p->G));
     // 5. back to real space (+ ft_stab correction terms)     (:586-588 / :579)
