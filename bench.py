@@ -104,7 +104,8 @@ def algorithmic_bytes(nb):
     return {
         # per launch, averaged over the 6 launches of a step: 4 complex transforms + the 2 of the REAL intensity field, which
         # move only the m >= 0 half of the phi-Fourier array and of the coefficients
-        'fft_phi': nb * (G + A * 5 / 6) * 16,  # one grid read/written + one phi-Fourier array written/read
+        # fft: 6 launches move 6 grids + 5 phi-Fourier arrays + 1 extra grid (rho_hat read by the fused modified-intensity epilogue)
+        'fft_phi': nb * (7 * G + 5 * A) / 6 * 16,
         'legendre': nb * (A + C) * 5 / 6 * 16,
         'hankel': nb * 2 * C * 16,
         'real_update': nb * (3 * G * 16 + G),  # IFT(rho_hat'-rho_hat), rho_prev in, rho_next out, support mask (fused ft_stab)

@@ -230,6 +230,39 @@ def generate_ft(sh, weights, r_max, rc, l_max, mode='midpoint', flavour='ml'):
 
 
 # --------------------------------------------------------------------------
+# coordinate conversions -- library/mathLibrary.py:628-698
+# --------------------------------------------------------------------------
+
+def spherical_to_cartesian(grid):
+    out = np.array(grid, dtype=float)
+    if grid.shape[-1] == 2:
+        r, phi = grid[..., 0], grid[..., 1]
+        out[..., 0], out[..., 1] = r * np.cos(phi), r * np.sin(phi)
+    else:
+        r, theta, phi = grid[..., 0], grid[..., 1], grid[..., 2]
+        xy = r * np.sin(theta)
+        out[..., 0], out[..., 1], out[..., 2] = np.cos(phi) * xy, np.sin(phi) * xy, r * np.cos(theta)
+    return out
+
+
+def cartesian_to_spherical(grid):
+    out = np.array(grid, dtype=float)
+    if grid.shape[-1] == 2:
+        x, y = grid[..., 0], grid[..., 1]
+        phi = np.arctan2(y, x)
+        out[..., 0], out[..., 1] = np.sqrt(x * x + y * y), np.where(phi < 0, phi + 2 * np.pi, phi)
+    else:
+        x, y, z = grid[..., 0], grid[..., 1], grid[..., 2]
+        r = np.sqrt(x * x + y * y + z * z)
+        theta = np.zeros(np.shape(r))
+        nz = r != 0
+        theta[nz] = np.arccos(np.asarray(z)[nz] / r[nz])
+        phi = np.arctan2(y, x)
+        out[..., 0], out[..., 1], out[..., 2] = r, theta, np.where(phi < 0, phi + 2 * np.pi, phi)
+    return out
+
+
+# --------------------------------------------------------------------------
 # elementwise helpers -- projects/fxs/projectLibrary/misk.py
 # --------------------------------------------------------------------------
 
@@ -642,10 +675,13 @@ class MTIP:
                 self.real_pr.support = state['best_mask']
                 state['mask'] = state['best_mask']
             iterations.append(it)
-        last_inv = self._last_invariants(state['pair'][1])
+        best_out, last_out = state['best_pair'], state['pair']
+        if opt.get('output_density_modifiers', {}).get('shift_to_center', False):      # reconstruct.py:988-993
+            best_out, last_out = self._shift_to_center(*best_out[:2]), self._shift_to_center(*last_out[:2])
+        last_inv = self._last_invariants(last_out[1])
         return {
-            'real_density': state['best_pair'][1], 'reciprocal_density': state['best_pair'][0],
-            'last_real_density': state['pair'][1], 'last_reciprocal_density': state['pair'][0],
+            'real_density': best_out[1], 'reciprocal_density': best_out[0],
+            'last_real_density': last_out[1], 'last_reciprocal_density': last_out[0],
             'final_error': state['best_error'], 'initial_density': initial[1],
             'initial_support': self.real_pr.initial_support, 'support_mask': state['best_mask'],
             'last_support_mask': state['mask'], 'loop_iterations': np.sum(iterations) + 1,
@@ -654,6 +690,20 @@ class MTIP:
             'fxs_unknowns': self.results.get('fxs_unknowns'),
             'last_deg2_invariant': last_inv,
         }
+
+    # -- output modifiers (reconstruct.py:721-755): only shift_to_center is restated ----------------------------
+    def _shift_to_center(self, rho_hat, rho):
+        """shift_center sketch (:732-738): (rho_hat * e^{+i q.c}, IFT(FT(rho) * e^{+i q.c})), c = centre of mass of Re rho
+        (misk.py:295-312), phases of generate_shift_by_operator(..., opposite_direction=True) (fxs_Projections.py:1419-1444)."""
+        cart_r, cart_q = spherical_to_cartesian(self.real_grid), spherical_to_cartesian(self.reciprocal_grid)
+        total = self.integrator.integrate(rho.real)
+        if total == 0:
+            total = 1
+        center = self.integrator.integrate(cart_r * rho[..., None].real) / total
+        center = spherical_to_cartesian(cartesian_to_spherical(center))
+        phases = np.exp(1.j * (cart_q * center).sum(axis=-1))
+        self.results['neg_center_pos'] = center
+        return rho_hat * phases, self.ift(self.ft(rho) * phases)
 
     def _last_invariants(self, rho):             # reconstruct.py:757-765
         return harmonic_coeff_to_deg2_invariants_3d(self.sh.forward_l(square_grid(self.ft(rho))))

@@ -114,7 +114,7 @@ class FakeDB:
         pass
 
 
-def build_case(xframe, n_r, l_max, n_theta, n_phi, ft_stab, tag, run_loop=True, seed=7):
+def build_case(xframe, n_r, l_max, n_theta, n_phi, ft_stab, tag, run_loop=True, seed=7, shift_to_center=False):
     from xframe.library.pythonLibrary import DictNamespace
     from xframe.library.gridLibrary import SampledFunction, NestedArray
     from xframe import settings
@@ -124,6 +124,7 @@ def build_case(xframe, n_r, l_max, n_theta, n_phi, ft_stab, tag, run_loop=True, 
     r_max_domain = 794.0
     max_q = 2.0 * n_r / r_max_domain
     sd = settings_dict(n_r, l_max, n_theta, n_phi, max_q, ft_stab)
+    sd['output_density_modifiers'] = {'shift_to_center': bool(shift_to_center)}
     settings.project = DictNamespace.dict_to_dictnamespace(sd)
     settings.general.cache_aware = False
     settings.general.n_control_workers = 0
@@ -165,7 +166,7 @@ def build_case(xframe, n_r, l_max, n_theta, n_phi, ft_stab, tag, run_loop=True, 
 
     rng = np.random.default_rng(seed)
     gshape = m.grid_pair.realGrid[:].shape[:-1]
-    out = {'n_r': n_r, 'l_max': l_max, 'n_theta': n_theta, 'n_phi': n_phi, 'max_q': max_q, 'ft_stab': ft_stab,
+    out = {'n_r': n_r, 'l_max': l_max, 'n_theta': n_theta, 'n_phi': n_phi, 'max_q': max_q, 'ft_stab': ft_stab, 'shift_to_center': bool(shift_to_center),
            'avg_intensity': inv['average_intensity'], 'data_q': inv['data_radial_points']}
     for l, p in enumerate(inv['data_projection_matrices']):
         out[f'pm_{l}'] = p
@@ -284,3 +285,4 @@ if __name__ == '__main__':
     build_case(xf, n_r=16, l_max=7, n_theta=8, n_phi=16, ft_stab=True, tag='ref_small_ftstab')
     build_case(xf, n_r=16, l_max=7, n_theta=8, n_phi=16, ft_stab=False, tag='ref_small_plain')
     build_case(xf, n_r=32, l_max=15, n_theta=16, n_phi=32, ft_stab=True, tag='ref_medium_ops', run_loop=False)
+    build_case(xf, n_r=16, l_max=7, n_theta=8, n_phi=16, ft_stab=True, tag='ref_small_shift', shift_to_center=True)

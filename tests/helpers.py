@@ -15,7 +15,9 @@ def load_golden(tag):
 
 def golden_settings(g):
     from make_golden import settings_dict
-    return settings_dict(int(g['n_r']), int(g['l_max']), int(g['n_theta']), int(g['n_phi']), float(g['max_q']), bool(g['ft_stab']))
+    sd = settings_dict(int(g['n_r']), int(g['l_max']), int(g['n_theta']), int(g['n_phi']), float(g['max_q']), bool(g['ft_stab']))
+    sd['output_density_modifiers'] = {'shift_to_center': bool(g['shift_to_center']) if 'shift_to_center' in g else False}
+    return sd
 
 
 def golden_data(g):

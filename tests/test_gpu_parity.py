@@ -411,3 +411,21 @@ def test_config4_high_resolution_iteration_against_oracle():
     orders, sweeps = plan.jacobi_sweeps()
     assert sweeps.max() < 40
     plan.close()
+
+
+def test_worker_shift_to_center_matches_reference():
+    """output_density_modifiers.shift_to_center (reconstruct.py:732-738): full reference loop with the modifier on."""
+    from xframe_b200.worker import ProjectWorker
+    g = load_golden('ref_small_shift')
+    sd = golden_settings(g)
+    assert sd['output_density_modifiers']['shift_to_center']
+    sd['GPU'] = {'use': True, 'batch': 2, 'seed': 3}
+    w = ProjectWorker(sd, golden_data(g), n_reconstructions=2, initial_densities=[g['rho0'], g['rho0']])
+    res, _ = w.run()
+    for r in res:
+        assert rel_l2(r['error_dict']['main'], g['loop_main_error']) < 1e-6
+        assert rel_l2(r['last_real_density'], g['loop_last_real_density']) < 1e-6
+        assert rel_l2(r['real_density'], g['loop_real_density']) < 1e-6
+        assert rel_l2(r['last_reciprocal_density'], g['loop_last_reciprocal_density']) < 1e-6
+        assert rel_l2(r['reciprocal_density'], g['loop_reciprocal_density']) < 1e-6
+        assert rel_l2(r['last_deg2_invariant'], g['loop_last_deg2']) < 1e-6

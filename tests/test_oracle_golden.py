@@ -94,7 +94,7 @@ def test_density_guess(case):
     assert rel_l2(rho0, g['rho0']) < 1e-14
 
 
-@pytest.mark.parametrize('tag', ['ref_small_ftstab', 'ref_small_plain'])
+@pytest.mark.parametrize('tag', ['ref_small_ftstab', 'ref_small_plain', 'ref_small_shift'])   # the last one: shift_to_center output modifier
 def test_full_loop(tag):
     g = load_golden(tag)
     m = O.MTIP(golden_settings(g), golden_data(g))
@@ -107,6 +107,7 @@ def test_full_loop(tag):
     assert rel_l2(res['last_real_density'], g['loop_last_real_density']) < 1e-7
     assert rel_l2(res['real_density'], g['loop_real_density']) < 1e-7
     assert rel_l2(res['last_reciprocal_density'], g['loop_last_reciprocal_density']) < 1e-7
+    assert rel_l2(res['reciprocal_density'], g['loop_reciprocal_density']) < 1e-7
     assert (res['last_support_mask'] != g['loop_last_support_mask']).mean() < 1e-3
     assert (res['support_mask'] != g['loop_support_mask']).mean() < 1e-3
     assert rel_l2(res['last_deg2_invariant'], g['loop_last_deg2']) < 1e-7

@@ -172,12 +172,17 @@ static int launch_fft_n(bool forward, SlotView in, int shells_per_run, const dou
 }
 
 // half: forward -> write only m >= 0 (real input); inverse -> synthesise from m >= 0 with conjugate symmetry (real output)
+// half: bit 0 = real field (forward: write m >= 0 only; inverse: conjugate-symmetric synthesis); bit 1 (forward, register
+// FFT only) = transform |x|^2.  mod_rho_hat / mod_out (inverse, register FFT only): fused modified-intensity epilogue.
 static int launch_fft(bool forward, int n_phi, SlotView in, int shells_per_run, const double2* sub, double2* out, const double2* tw, int n_shells,
-                      int n_theta, int l_max, cudaStream_t st, int half = 0) {
+                      int n_theta, int l_max, cudaStream_t st, int half = 0, const double2* mod_rho_hat = nullptr,
+                      SlotView mod_out = SlotView{}) {
     {   // register two-stage FFT where it applies (64 / 128 / 256 points), generic Stockham kernel otherwise
-        const int rc = launch_fft2_any(forward, n_phi, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st, half);
+        const int rc = launch_fft2_any(forward, n_phi, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st, half, mod_rho_hat, mod_out);
         if (rc >= 0) return rc;
     }
+    if ((half & 2) || mod_rho_hat) XFB_FAIL("fused square / modified-intensity FFT variants need the register FFT (n_phi 64/128/256)");
+    half &= 1;
     switch (n_phi) {
         case 16: return launch_fft_n<16>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st, half);
         case 32: return launch_fft_n<32>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st, half);

@@ -63,9 +63,11 @@ struct Fft2Cfg {
 template <int N1, int N2>
 __global__ void __launch_bounds__(256) fft2_forward_kernel(SlotView grid, int shells_per_run, const double2* __restrict__ sub_flat,
                                                            double2* __restrict__ a, const double2* __restrict__ tw_g, int n_theta,
-                                                           int l_max, int pos_only) {
+                                                           int l_max, int flags) {
+    // flags: bit 0 = real input, write only m >= 0;  bit 1 = transform |x|^2 instead of x (square_grid fused, misk.py:159-168)
     using C = Fft2Cfg<N1, N2>;
     extern __shared__ double2 smem_f2[];
+    const int pos_only = flags & 1, square = flags & 2;
     const int s = blockIdx.x, theta0 = blockIdx.y * C::TH, tid = threadIdx.x;
     const int M2 = 2 * l_max + 1;
     const int run = s / shells_per_run, shell_in_run = s - run * shells_per_run;
@@ -82,6 +84,7 @@ __global__ void __launch_bounds__(256) fft2_forward_kernel(SlotView grid, int sh
             for (int j = 0; j < N1; ++j) {
                 x[j] = src[(size_t)row * C::N + t + N2 * j];
                 if (sub) { const double2 w = ldg2(sub + (size_t)row * C::N + t + N2 * j); x[j].x -= w.x; x[j].y -= w.y; }
+                if (square) x[j] = make_double2(__dadd_rn(__dmul_rn(x[j].x, x[j].x), __dmul_rn(x[j].y, x[j].y)), 0.0);
             }
             dft_reg<N1, -1>(x);
 #pragma unroll
@@ -115,8 +118,11 @@ __global__ void __launch_bounds__(256) fft2_forward_kernel(SlotView grid, int sh
 
 // a [S][M2][n_theta] -> grid [S][n_theta][N] (unnormalised inverse DFT)
 template <int N1, int N2>
+// mod_rho_hat != nullptr: the transform output is I_proj and the kernel writes the modified-intensity density instead
+// (project_to_modified_intensity fused, fxs_Projections.py:899-909): mod_out[x] = rho_hat[x] sqrt(Re I_proj[x] / |rho_hat[x]|^2)
 __global__ void __launch_bounds__(256) fft2_inverse_kernel(const double2* __restrict__ a, double2* __restrict__ grid,
-                                                           const double2* __restrict__ tw_g, int n_theta, int l_max, int herm) {
+                                                           const double2* __restrict__ tw_g, int n_theta, int l_max, int herm,
+                                                           const double2* __restrict__ mod_rho_hat, SlotView mod_out, int shells_per_run) {
     using C = Fft2Cfg<N1, N2>;
     extern __shared__ double2 smem_f2[];
     const int s = blockIdx.x, theta0 = blockIdx.y * C::TH, tid = threadIdx.x;
@@ -154,6 +160,12 @@ __global__ void __launch_bounds__(256) fft2_inverse_kernel(const double2* __rest
     {
         const int t = tid % N2, row0 = tid / N2;
         double2* dst = grid + ((size_t)s * n_theta + theta0) * C::N;
+        const double2* rh = nullptr;
+        if (mod_rho_hat) {
+            const int run = s / shells_per_run, shell_in_run = s - run * shells_per_run;
+            rh = mod_rho_hat + ((size_t)s * n_theta + theta0) * C::N;
+            dst = slot_run_ptr(mod_out, run) + ((size_t)shell_in_run * n_theta + theta0) * C::N;
+        }
 #pragma unroll
         for (int ps = 0; ps < C::PASSES; ++ps) {
             const int row = row0 + ps * (256 / N2);
@@ -162,14 +174,24 @@ __global__ void __launch_bounds__(256) fft2_inverse_kernel(const double2* __rest
             for (int u = 0; u < N1; ++u) y[u] = smem_f2[row * C::ROWLEN + u * N2 + t];
             dft_reg<N1, +1>(y);
 #pragma unroll
-            for (int j = 0; j < N1; ++j) dst[(size_t)row * C::N + t + N2 * j] = y[j];
+            for (int j = 0; j < N1; ++j) {
+                double2 o = y[j];
+                if (rh) {
+                    const double2 v = ldg2(rh + (size_t)row * C::N + t + N2 * j);
+                    const double sq = __dadd_rn(__dmul_rn(v.x, v.x), __dmul_rn(v.y, v.y));
+                    double mult = 0.0;
+                    if (sq >= 0.0 && o.x >= 0.0) mult = sqrt(o.x / sq);
+                    o = make_double2(v.x * mult, v.y * mult);
+                }
+                dst[(size_t)row * C::N + t + N2 * j] = o;
+            }
         }
     }
 }
 
 template <int N1, int N2>
 static int launch_fft2(bool forward, SlotView in, int shells_per_run, const double2* sub, double2* out, const double2* tw, int n_shells,
-                       int n_theta, int l_max, cudaStream_t st, int half) {
+                       int n_theta, int l_max, cudaStream_t st, int half, const double2* mod_rho_hat, SlotView mod_out) {
     using C = Fft2Cfg<N1, N2>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -181,16 +203,21 @@ static int launch_fft2(bool forward, SlotView in, int shells_per_run, const doub
     if (forward)
         fft2_forward_kernel<N1, N2><<<g, 256, C::SMEM, st>>>(in, shells_per_run, sub, out, tw, n_theta, l_max, half);
     else
-        fft2_inverse_kernel<N1, N2><<<g, 256, C::SMEM, st>>>(in.base, out, tw, n_theta, l_max, half);
+        fft2_inverse_kernel<N1, N2><<<g, 256, C::SMEM, st>>>(in.base, out, tw, n_theta, l_max, half, mod_rho_hat, mod_out, shells_per_run);
     XFB_CUDA(cudaGetLastError());
     return 0;
 }
 
 // returns -1 when (n_phi, n_theta) is not covered by the register FFT (caller falls back to fft.cuh)
+static inline bool fft2_covers(int n_phi, int n_theta) {
+    return (n_phi == 64 && n_theta % Fft2Cfg<8, 8>::TH == 0) || (n_phi == 128 && n_theta % Fft2Cfg<8, 16>::TH == 0) ||
+           (n_phi == 256 && n_theta % Fft2Cfg<16, 16>::TH == 0);
+}
 static int launch_fft2_any(bool forward, int n_phi, SlotView in, int shells_per_run, const double2* sub, double2* out, const double2* tw,
-                           int n_shells, int n_theta, int l_max, cudaStream_t st, int half) {
-    if (n_phi == 64 && n_theta % Fft2Cfg<8, 8>::TH == 0) return launch_fft2<8, 8>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st, half);
-    if (n_phi == 128 && n_theta % Fft2Cfg<8, 16>::TH == 0) return launch_fft2<8, 16>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st, half);
-    if (n_phi == 256 && n_theta % Fft2Cfg<16, 16>::TH == 0) return launch_fft2<16, 16>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st, half);
+                           int n_shells, int n_theta, int l_max, cudaStream_t st, int half, const double2* mod_rho_hat = nullptr,
+                           SlotView mod_out = SlotView{}) {
+    if (n_phi == 64 && n_theta % Fft2Cfg<8, 8>::TH == 0) return launch_fft2<8, 8>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st, half, mod_rho_hat, mod_out);
+    if (n_phi == 128 && n_theta % Fft2Cfg<8, 16>::TH == 0) return launch_fft2<8, 16>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st, half, mod_rho_hat, mod_out);
+    if (n_phi == 256 && n_theta % Fft2Cfg<16, 16>::TH == 0) return launch_fft2<16, 16>(forward, in, shells_per_run, sub, out, tw, n_shells, n_theta, l_max, st, half, mod_rho_hat, mod_out);
     return -1;
 }

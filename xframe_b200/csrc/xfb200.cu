@@ -254,7 +254,7 @@ int xfb_profile_read(xfb_plan* p, int32_t n_max, char* names, double* ms, int64_
 // is produced (c_{l,-m} = (-1)^m conj c_{l,m} is redundant) -- the caller must consume m >= 0 only.  Returns the mode used
 // in *half_used.
 static int sht_forward_i(xfb_plan* p, SlotView in, int shells_per_run, double2* c_out, int S, cudaStream_t st,
-                         const double2* sub = nullptr, int real_only = 0, int* half_used = nullptr) {
+                         const double2* sub = nullptr, int real_only = 0, int* half_used = nullptr, int square = 0) {
     if (half_used) *half_used = 0;
     if (p->dims == 2) {   // circular harmonic transform: fft(x)/n_phi  (mathLibrary.py:469-475,484-490)
         XFB_LAUNCH(p, PG_FFT, st,
@@ -264,7 +264,7 @@ static int sht_forward_i(xfb_plan* p, SlotView in, int shells_per_run, double2* 
     }
     const int half = (real_only && p->leg2 && p->half_spectrum) ? 1 : 0;
     if (half_used) *half_used = half;
-    XFB_LAUNCH(p, PG_FFT, st, if (launch_fft(true, p->n_phi, in, shells_per_run, sub, p->A0, p->tw, S, p->n_theta, p->L, st, half)) return 1);
+    XFB_LAUNCH(p, PG_FFT, st, if (launch_fft(true, p->n_phi, in, shells_per_run, sub, p->A0, p->tw, S, p->n_theta, p->L, st, half | (square ? 2 : 0))) return 1);
     if (p->leg2) {     // small configuration: table-resident, cp.async double-buffered kernel
         const int groups = cdiv(S, half ? LEG2_FR : LEG2_FR / 2);
         dim3 g2(std::min(groups, std::max(1, (3 * p->n_sm * 4) / (p->L + 1))), p->L + 1);
@@ -278,7 +278,8 @@ static int sht_forward_i(xfb_plan* p, SlotView in, int shells_per_run, double2* 
                legendre_forward_kernel<<<g, LEG_THREADS, legendre_fwd_smem(p->n_theta), st>>>(p->A0, c_out, p->FE, p->FO, S, p->L, p->n_theta, p->NP));
     return 0;
 }
-static int sht_inverse_i(xfb_plan* p, const double2* c_in, double2* grid_out, int S, cudaStream_t st, int herm = 0) {
+static int sht_inverse_i(xfb_plan* p, const double2* c_in, double2* grid_out, int S, cudaStream_t st, int herm = 0,
+                         const double2* mod_rho_hat = nullptr, SlotView mod_out = SlotView{}, int shells_per_run = 1) {
     if (p->dims == 2) {   // ifft(c * n_phi) / irfft(c * n_phi, n_phi)  (mathLibrary.py:478-482,492-496)
         XFB_LAUNCH(p, PG_FFT, st,
                    dft2d_inverse_kernel<<<cdiv(S, DFT_ROWS), DFT_THREADS, dft_smem(p->n_phi), st>>>(c_in, grid_out, S, p->n_phi, herm));
@@ -290,7 +291,8 @@ static int sht_inverse_i(xfb_plan* p, const double2* c_in, double2* grid_out, in
                legendre_inverse_kernel<<<g, LEG_THREADS, legendre_inv_smem(p->n_theta, p->NP), st>>>(c_in, p->A0, p->IE, p->IO, S, p->L, p->n_theta, p->NP,
                                                                                                      herm));
     XFB_LAUNCH(p, PG_FFT, st,
-               if (launch_fft(false, p->n_phi, flat_view(p->A0, 0), 1, nullptr, grid_out, p->tw, S, p->n_theta, p->L, st, herm)) return 1);
+               if (launch_fft(false, p->n_phi, flat_view(p->A0, 0), shells_per_run, nullptr, grid_out, p->tw, S, p->n_theta, p->L, st, herm, mod_rho_hat,
+                              mod_out)) return 1);
     return 0;
 }
 static int hankel_i(xfb_plan* p, int dir, const double2* c_in, double2* c_out, int nb, cudaStream_t st) {
@@ -804,15 +806,26 @@ static int iterate_range(xfb_plan* p, int b0, int nb, int method, int ft_stab, d
         if (sht_inverse_i(p, p->C1, p->W0, S, st)) return 1;
     }
     // 2. |rho_hat|^2 -> I_lm                                 (:519-520)
-    XFB_LAUNCH(p, PG_POINTWISE, st, square_kernel<<<ew_blocks((long long)nb * p->G), 256, 0, st>>>(p->W0, p->W1, (long long)nb * p->G));
+    // with the register phi-FFT both pointwise kernels are fused into the transforms: |.|^2 when the rows are loaded,
+    // the modified-intensity formula when the synthesised rows are stored
+    const bool fuse_pw = p->dims == 3 && fft2_covers(p->n_phi, p->n_theta);
     int half = 0;                                             // |rho_hat|^2 is real: half spectrum (2-D: the 'real' transform, reconstruct.py:347-348)
-    if (sht_forward_i(p, flat_view(p->W1, p->G), p->n_r, p->C0, S, st, nullptr, 1, &half)) return 1;
+    if (fuse_pw) {
+        if (sht_forward_i(p, flat_view(p->W0, p->G), p->n_r, p->C0, S, st, nullptr, 1, &half, 1)) return 1;
+    } else {
+        XFB_LAUNCH(p, PG_POINTWISE, st, square_kernel<<<ew_blocks((long long)nb * p->G), 256, 0, st>>>(p->W0, p->W1, (long long)nb * p->G));
+        if (sht_forward_i(p, flat_view(p->W1, p->G), p->n_r, p->C0, S, st, nullptr, 1, &half)) return 1;
+    }
     // 3. projection onto the invariants                      (:521-523)
     if (project_i(p, p->C0, p->C1, nb, st, half)) return 1;
     // 4. I_proj on the grid, modified intensity              (:524-525)
-    if (sht_inverse_i(p, p->C1, p->W1, S, st, p->dims == 2 ? 1 : half)) return 1;
-    XFB_LAUNCH(p, PG_POINTWISE, st,
-               modify_intensity_kernel<<<dim3(eb, nb), 256, 0, st>>>(p->W0, p->W1, pv(p->rh_pool, p->ls.rh_next), p->G));
+    if (fuse_pw) {
+        if (sht_inverse_i(p, p->C1, p->W1, S, st, half, p->W0, pv(p->rh_pool, p->ls.rh_next), p->n_r)) return 1;
+    } else {
+        if (sht_inverse_i(p, p->C1, p->W1, S, st, p->dims == 2 ? 1 : half)) return 1;
+        XFB_LAUNCH(p, PG_POINTWISE, st,
+                   modify_intensity_kernel<<<dim3(eb, nb), 256, 0, st>>>(p->W0, p->W1, pv(p->rh_pool, p->ls.rh_next), p->G));
+    }
     // 5. back to real space (+ ft_stab correction terms)     (:586-588 / :579)
     // 6. real projection + HIO/ER + error                    (:589-590)
     const uint8_t* mask = p->mask_pool + (long long)b0 * p->G;

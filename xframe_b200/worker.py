@@ -32,9 +32,9 @@ class ProjectWorker:
         if self.dims not in (2, 3):
             raise XfbError(f"dimensions={settings['dimensions']} is not supported")
         mods = settings.get('output_density_modifiers', {})
-        if mods.get('shift_to_center', False) or (self.dims == 2 and mods.get('fix_orientation', False)
-                                                   and settings['projections']['reciprocal'].get('SO_freedom', {}).get('use', False)):
-            raise XfbError("output_density_modifiers (shift_to_center / fix_orientation) are not implemented by xframe_b200")
+        self.shift_to_center = bool(mods.get('shift_to_center', False))
+        if self.dims == 2 and mods.get('fix_orientation', False) and settings['projections']['reciprocal'].get('SO_freedom', {}).get('use', False):
+            raise XfbError("output_density_modifiers.fix_orientation (2-D SO_freedom) is not implemented by xframe_b200")
         if not settings['GPU']['use']:
             raise XfbError("GPU.use is False: xframe_b200 has no CPU path (the reference falls back to CPU, reconstruct.py:96-102)")
         if number_of_gpus() == 0:
@@ -80,6 +80,32 @@ class ProjectWorker:
         rng = np.random.default_rng(self.seeds[run_id])    # None -> OS entropy, like reconstruct.py:1119
         return S.density_guess(self.plan, self.opt['density_guess'], self.opt['particle_radius'], self.proj.integrated_intensity, rng)
 
+    def _shift_to_center(self, rho_hat, rho):
+        """Output modifier `shift_to_center` (reconstruct.py:732-738) for a batch on the device:
+        (rho_hat e^{+i q.c}, IFT(FT(rho) e^{+i q.c})), c = centre of mass of Re rho (misk.py:295-312,
+        fxs_Projections.py:1419-1444).  One-off post-processing: transforms through the plan, elementwise work in torch."""
+        plan = self.plan
+        if not hasattr(self, '_cart'):
+            ang = (plan.thetas, plan.phis) if self.dims == 3 else (plan.phis,)
+
+            def cart(radial):
+                g = np.meshgrid(radial, *ang, indexing='ij')
+                if self.dims == 3:
+                    r, t, p = g
+                    return np.stack((np.cos(p) * r * np.sin(t), np.sin(p) * r * np.sin(t), r * np.cos(t)), axis=-1)
+                r, p = g
+                return np.stack((r * np.cos(p), r * np.sin(p)), axis=-1)
+            w = plan.int_weight[:, :, None] * np.ones(plan.grid_shape) if self.dims == 3 else plan.int_weight
+            self._cart = (torch.from_numpy(cart(plan.rs)).to(plan.device), torch.from_numpy(cart(plan.qs)).to(plan.device),
+                          torch.from_numpy(np.ascontiguousarray(w)).to(plan.device))
+        cart_r, cart_q, w = self._cart
+        dims = tuple(range(1, rho.dim()))
+        total = (w * rho.real).sum(dim=dims)
+        total = torch.where(total == 0, torch.ones_like(total), total)
+        center = (w[None, ..., None] * cart_r[None] * rho.real[..., None]).sum(dim=dims) / total[:, None]     # [nb, dims]
+        phases = torch.exp(1j * (cart_q[None] * center.reshape((-1,) + (1,) * (rho.dim() - 1) + (self.dims,))).sum(-1))
+        return rho_hat * phases, plan.ift((plan.ft(rho.contiguous()) * phases).contiguous()), center
+
     def run(self):
         t0 = time.time()
         plan, out = self.plan, []
@@ -91,11 +117,15 @@ class ProjectWorker:
             ids = self.run_ids[b0:b0 + self.batch]
             rho0 = torch.from_numpy(np.stack([self._guess(i) for i in ids])).to(plan.device)
             res = run_schedule(plan, self.opt, rho0)
+            unknowns = [plan.unknowns(k) for k in range(len(ids))]      # of the last mtip_start (reconstruct.py:523,1013)
+            if self.shift_to_center:                                    # output modifier on the best and the last pair (:988-989)
+                for a, b in (('best_reciprocal', 'best_real'), ('last_reciprocal', 'last_real')):
+                    rh, rr, _ = self._shift_to_center(torch.from_numpy(res[a]).to(plan.device), torch.from_numpy(res[b]).to(plan.device))
+                    res[a], res[b] = rh.cpu().numpy(), rr.cpu().numpy()
             # last_deg2_invariant: B_l = I_l I_l^H of the last density (reconstruct.py:757-765,993)
             last = torch.from_numpy(res['last_real']).to(plan.device)
             fd = plan.ft(last)
             I = plan.sht_forward((fd * fd.conj()).real.to(torch.complex128).contiguous()).cpu().numpy()
-            unknowns = [plan.unknowns(k) for k in range(len(ids))]      # of the last mtip_start (reconstruct.py:523,1013)
             for k, rid in enumerate(ids):
                 if self.dims == 3:
                     Il = [I[k][:, l * l:(l + 1) * (l + 1)] for l in range(plan.l_max + 1)]
