@@ -100,21 +100,15 @@ __global__ void __launch_bounds__(RU_THREADS) real_update_kernel(const double2* 
     const bool enf = enforce ? (enforce[b] != 0) : true;
     const long long shell = (long long)n_theta * n_phi;
     double s_diff = 0.0, s_val = 0.0;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_run; i += (long long)gridDim.x * blockDim.x) {
-        double2 v = ldg2(ri + i);
-        const double2 prev = rp[i];
-        if (rt && i >= shell) {
-            const double2 t = ldg2(rt + i);
-            v.x += prev.x - t.x;
-            v.y += prev.y - t.y;
-        }
+    // one grid point: combine, project, HIO/ER, error integrands
+    auto point = [&](long long i, double2 v, double2 prev, double2 t_rt, double2 t_rt0, uint8_t sup_i, uint8_t init_i) -> double2 {
+        if (rt && i >= shell) { v.x += prev.x - t_rt.x; v.y += prev.y - t_rt.y; }
         if (rt0) {      // fused ft_stab: rho_ift holds IFT(rho_hat' - rho_hat); add rho (r>=1) or shell 0 of IFT(rho_hat)
-            const double2 t = (i >= shell) ? prev : ldg2(rt0 + (long long)b * shell + i);
-            v.x += t.x;
-            v.y += t.y;
+            const double2 t = (i >= shell) ? prev : t_rt0;
+            v.x += t.x; v.y += t.y;
         }
-        const bool in_init = init_support[i] != 0;
-        const bool outside = enf ? (!in_init || sup[i] == 0) : (sup[i] == 0);
+        const bool in_init = init_i != 0;
+        const bool outside = enf ? (!in_init || sup_i == 0) : (sup_i == 0);
         double2 p = v;
         bool msel = false;
 #pragma unroll
@@ -137,12 +131,38 @@ __global__ void __launch_bounds__(RU_THREADS) real_update_kernel(const double2* 
         }
         double2 o = p;
         if (method == 0 && msel) o = make_double2(prev.x - beta * (v.x - p.x), prev.y - beta * (v.y - p.y));
-        rn[i] = o;
         if (!rd.err_inside || in_init) {
             const double w = __ldg(wt + (unsigned)i / (unsigned)wt_div);    // per_run < 2^31: 32-bit division; wt_div = n_phi (3-D) or 1 (2-D)
             const double dx = v.x - p.x, dy = v.y - p.y;
             s_diff += w * (dx * dx + dy * dy);
             s_val += w * (v.x * v.x + v.y * v.y);
+        }
+        return o;
+    };
+    const double2 zero2 = make_double2(0.0, 0.0);
+    if ((per_run & 3) == 0 && (shell & 3) == 0) {
+        // 4 consecutive points per thread and iteration: 4 x 128-bit density loads per array, masks as 32-bit words
+        const long long n4 = per_run >> 2;
+        for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
+            const long long i0 = q << 2;
+            double2 v[4], pr[4], trt[4], trt0[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { v[u] = ldg2(ri + i0 + u); pr[u] = rp[i0 + u]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                trt[u] = (rt && i0 >= shell) ? ldg2(rt + i0 + u) : zero2;
+                trt0[u] = (rt0 && i0 < shell) ? ldg2(rt0 + (long long)b * shell + i0 + u) : zero2;
+            }
+            const uchar4 s4 = *reinterpret_cast<const uchar4*>(sup + i0), n4m = __ldg(reinterpret_cast<const uchar4*>(init_support + i0));
+            const uint8_t sb[4] = {s4.x, s4.y, s4.z, s4.w}, ib[4] = {n4m.x, n4m.y, n4m.z, n4m.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) rn[i0 + u] = point(i0 + u, v[u], pr[u], trt[u], trt0[u], sb[u], ib[u]);
+        }
+    } else {
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_run; i += (long long)gridDim.x * blockDim.x) {
+            const double2 t_rt = (rt && i >= shell) ? ldg2(rt + i) : zero2;
+            const double2 t_rt0 = (rt0 && i < shell) ? ldg2(rt0 + (long long)b * shell + i) : zero2;
+            rn[i] = point(i, ldg2(ri + i), rp[i], t_rt, t_rt0, sup[i], init_support[i]);
         }
     }
     __shared__ double red[2][RU_THREADS / 32];
