@@ -113,9 +113,11 @@ __device__ __forceinline__ void hk_cp_async16(void* smem, const void* gmem, bool
     const int bytes = valid ? 16 : 0;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(bytes));
 }
+// ldw: leading dimension of the weight rows (>= n_r, even); accumulate: out += result (second pass of a complex matrix,
+// used by the 2-D DFT: X (C -+ i S) = X C -+ i (X S)).
 __global__ void __launch_bounds__(256, 2) hankel2_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                                                          const double* __restrict__ W, const HankelTile* __restrict__ tiles,
-                                                         int n_r, int n_sum, int skip, double scale, int inverse) {
+                                                         int n_r, int n_sum, int skip, double scale, int inverse, int ldw, int accumulate) {
     extern __shared__ __align__(16) unsigned char smem_hk[];
     double2* As = reinterpret_cast<double2*>(smem_hk);                                     // [ST][HK_BM][HK2_LDA]
     double* Bs = reinterpret_cast<double*>(As + HK2_ST * HK_BM * HK2_LDA);                 // [ST][HK_BK][HK2_LDB]
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(256, 2) hankel2_kernel(const double2* __restri
     const int k_tile0 = blockIdx.y * HK_BN;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps, warp tile 32 rows x 16 cols
-    const double* Wl = W + (size_t)t.l * n_sum * n_r;
+    const double* Wl = W + (size_t)t.l * n_sum * ldw;
     double cre[4][2][2] = {}, cim[4][2][2] = {};
     const int ar = lane >> 2, ak = lane & 3;
     const int n_chunks = (n_sum + HK_BK - 1) / HK_BK;
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(256, 2) hankel2_kernel(const double2* __restri
                 const int item = tid + q * 256;
                 const int pp = item >> 5, kk = (item & 31) * 2;
                 const bool ok = (p0 + pp) < n_sum && (k_tile0 + kk) < n_r;
-                hk_cp_async16(b + pp * HK2_LDB + kk, Wl + (size_t)(ok ? p0 + pp : 0) * n_r + (ok ? k_tile0 + kk : 0), ok);
+                hk_cp_async16(b + pp * HK2_LDB + kk, Wl + (size_t)(ok ? p0 + pp : 0) * ldw + (ok ? k_tile0 + kk : 0), ok);
             }
         }
         asm volatile("cp.async.commit_group;\n" ::);
@@ -195,6 +197,10 @@ __global__ void __launch_bounds__(256, 2) hankel2_kernel(const double2* __restri
                 else if ((ph == 1) != (inverse != 0)) r = make_double2(y, -x);   // multiply by -i
                 else r = make_double2(-y, x);                                     // multiply by +i
                 o[cc] = r;
+            }
+            if (accumulate) {
+                if (k < n_r) { const double2 c = out[(size_t)grow * n_r + k]; o[0].x += c.x; o[0].y += c.y; }
+                if (k + 1 < n_r) { const double2 c = out[(size_t)grow * n_r + k + 1]; o[1].x += c.x; o[1].y += c.y; }
             }
             if (k < n_r) out[(size_t)grow * n_r + k] = o[0];
             if (k + 1 < n_r) out[(size_t)grow * n_r + k + 1] = o[1];

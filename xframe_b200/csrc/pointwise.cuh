@@ -249,6 +249,18 @@ __global__ void transpose_c128_kernel(const double2* __restrict__ in, double2* _
     }
 }
 
+// 2-D helper: Hermitian completion of the 'real' coefficient rows before the complex inverse DFT (irfft semantics,
+// numpy.fft.irfft with odd N): rows [S][N], c[N-j] = conj(c[j]) for j = 1..N/2, Im c[0] = 0
+__global__ void hermitian_complete_rows_kernel(double2* __restrict__ c, int S, int N) {
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int half = N / 2 + 1;
+    if (idx >= (long long)S * half) return;
+    const int s = (int)(idx / half), j = (int)(idx - (long long)s * half);
+    double2* row = c + (size_t)s * N;
+    if (j == 0) row[0].y = 0.0;
+    else { const double2 v = row[j]; row[N - j] = make_double2(v.x, -v.y); }
+}
+
 // ---- loop bookkeeping (reconstruct.py:927-939): error history, best-so-far, slot rotation
 struct LoopState {
     int* rho_cur; int* rho_best; int* rho_next;       // slots in the rho pool

@@ -26,6 +26,9 @@ struct xfb_plan {
     int wt_div = 1;                                 // quadrature weight index = point index / wt_div
     // 2-D projection constants
     double2* v2d = nullptr; double2* unk2d = nullptr; int n_orders2d = 0, so_order2d = -1;
+    // 2-D DFT as two real DMMA GEMMs per transform: cos / sin matrices [2][N][ldw], row-major temporaries [B*G]
+    double* dft_cs = nullptr; int dft_ldw = 0; double2 *T2a = nullptr, *T2b = nullptr;
+    std::map<int, std::pair<HankelTile*, int>> dft_tiles;     // per number of shells S: tiles for the C pass and the S pass
     int hankel_skip = 0, hankel_n_sum = 0;
     double hk_fwd_scale = 0, hk_inv_scale = 0;
     long long G = 0, C = 0;
@@ -157,6 +160,21 @@ int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
         if (dev_alloc(p, &p->W0, B2 * p->G)) return 1;
         if (dev_alloc(p, &p->W1, B2 * p->G)) return 1;
         if (dev_alloc(p, &p->W2, B2 * p->G)) return 1;
+        {   // cos / sin matrices of the DFT, extended precision, rows padded to an even leading dimension
+            const int N = p->n_phi;
+            p->dft_ldw = (N + 1) & ~1;
+            std::vector<double> cs((size_t)2 * N * p->dft_ldw, 0.0);
+            for (int a = 0; a < N; ++a)
+                for (int b = 0; b < N; ++b) {
+                    const long double ang = 2.0L * 3.14159265358979323846264338327950288L * (long double)(((long long)a * b) % N) / (long double)N;
+                    cs[(size_t)a * p->dft_ldw + b] = (double)cosl(ang);
+                    cs[(size_t)(N + a) * p->dft_ldw + b] = (double)sinl(ang);
+                }
+            if (dev_upload(p, &p->dft_cs, cs.data(), cs.size())) return 1;
+            if (dev_alloc(p, &p->T2a, B2 * p->G)) return 1;
+            if (dev_alloc(p, &p->T2b, B2 * p->G)) return 1;
+            XFB_CUDA(cudaFuncSetAttribute(hankel2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hankel2_smem()));
+        }
         XFB_CUDA(cudaFuncSetAttribute(dft2d_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dft_smem(p->n_phi)));
         XFB_CUDA(cudaFuncSetAttribute(dft2d_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dft_smem(p->n_phi)));
         *out = p;
@@ -204,11 +222,12 @@ int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
 int xfb_plan_destroy(xfb_plan* p) {
     if (!p) return 0;
     void* ptrs[] = {p->tw, p->FE, p->FO, p->IE, p->IO, p->hankel_w, p->int_wt, p->q_pts, p->A0, p->C0, p->C1, p->W0, p->W1, p->W2, p->A0s, p->C0s, p->rt0, p->stage_out,
-                    p->v2d, p->unk2d, p->orders_dev, p->kind_dev, p->act_index_dev, p->radial_mask_dev, p->v0_dev, p->pd_dev, p->vt_dev,
+                    p->v2d, p->unk2d, p->dft_cs, p->T2a, p->T2b, p->orders_dev, p->kind_dev, p->act_index_dev, p->radial_mask_dev, p->v0_dev, p->pd_dev, p->vt_dev,
                     p->xt, p->tt, p->g, p->gn, p->vw, p->sigma, p->sweeps_dev, p->jac_counter, p->pp, p->gn_u, p->pp_u, p->sigma_u, p->i00, p->gemmY_dev, p->gemmY_tp, p->gemmM_dev, p->gemmT_dev, p->gemmM_tp, p->gemmT_tp,
                     p->init_support_dev, p->rho_pool, p->rh_pool, p->mask_pool, p->ls_ints, p->ls_dbl, p->partial, p->err, p->mm};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& kv : p->hk_cache) cudaFree(kv.second.first);
+    for (auto& kv : p->dft_tiles) cudaFree(kv.second.first);
     for (auto& e : p->prof_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto e : p->ev_in) cudaEventDestroy(e);
     for (auto e : p->ev_comp) cudaEventDestroy(e);
@@ -250,6 +269,32 @@ int xfb_profile_read(xfb_plan* p, int32_t n_max, char* names, double* ms, int64_
 }  // extern "C"
 
 // ---- internal building blocks -----------------------------------------------------------
+static int transpose_i(xfb_plan* p, const double2* in, double2* out, int rows, int cols, cudaStream_t st);
+
+// 2-D circular-harmonic DFT of S rows as two passes of the DMMA GEMM kernel: rows [S][N] complex times the real cos and
+// sin matrices, out = scale (X C -+ i X S)  (forward: exp(-i..), inverse: exp(+i..)).
+static int dft2d_gemm_i(xfb_plan* p, const double2* rows_in, double2* rows_out, int S, int inverse, double scale, cudaStream_t st) {
+    const int N = p->n_phi;
+    auto hit = p->dft_tiles.find(S);
+    if (hit == p->dft_tiles.end()) {
+        std::vector<HankelTile> tiles;
+        for (int pass = 0; pass < 2; ++pass)                      // matrix 0 = cos (phase 1), matrix 1 = sin (phase -+i)
+            for (int r = 0; r < S; r += HK_BM) tiles.push_back(HankelTile{pass, r, S, pass});
+        HankelTile* dev = nullptr;
+        XFB_CUDA(cudaMalloc((void**)&dev, tiles.size() * sizeof(HankelTile)));
+        XFB_CUDA(cudaMemcpyAsync(dev, tiles.data(), tiles.size() * sizeof(HankelTile), cudaMemcpyHostToDevice, st));
+        XFB_CUDA(cudaStreamSynchronize(st));
+        hit = p->dft_tiles.emplace(S, std::make_pair(dev, (int)tiles.size() / 2)).first;
+    }
+    const HankelTile* tl = hit->second.first;
+    const int nt = hit->second.second;
+    dim3 g(nt, cdiv(N, HK_BN));
+    // phase of the sin pass: forward multiplies by -i (ph = 1, inverse = 0), inverse by +i (ph = 1, inverse = 1)
+    XFB_LAUNCH(p, PG_FFT, st, hankel2_kernel<<<g, 256, hankel2_smem(), st>>>(rows_in, rows_out, p->dft_cs, tl, N, N, 0, scale, inverse, p->dft_ldw, 0));
+    XFB_LAUNCH(p, PG_FFT, st, hankel2_kernel<<<g, 256, hankel2_smem(), st>>>(rows_in, rows_out, p->dft_cs, tl + nt, N, N, 0, scale, inverse, p->dft_ldw, 1));
+    return 0;
+}
+
 // real_only: the input field is real.  2-D: rfft semantics.  3-D (v2 Legendre only): only the m >= 0 half of the spectrum
 // is produced (c_{l,-m} = (-1)^m conj c_{l,m} is redundant) -- the caller must consume m >= 0 only.  Returns the mode used
 // in *half_used.
@@ -257,6 +302,19 @@ static int sht_forward_i(xfb_plan* p, SlotView in, int shells_per_run, double2* 
                          const double2* sub = nullptr, int real_only = 0, int* half_used = nullptr, int square = 0) {
     if (half_used) *half_used = 0;
     if (p->dims == 2) {   // circular harmonic transform: fft(x)/n_phi  (mathLibrary.py:469-475,484-490)
+        if (!sub && S <= p->max_batch * p->n_r) {
+            // DMMA path: rows (gathered out of their slots if needed) x [cos | sin] -> row-major coefficients -> [N][S]
+            // (real_only needs nothing here: the callers pass fields whose imaginary part is exactly zero)
+            const double2* rows = in.base;
+            const bool flat = !in.slot && (in.run_stride == (long long)shells_per_run * p->n_phi || S <= shells_per_run);
+            if (!flat) {
+                const int nb_ = cdiv(S, shells_per_run);
+                XFB_LAUNCH(p, PG_MISC, st, gather_slot_kernel<<<dim3(ew_blocks(p->G), nb_), 256, 0, st>>>(in, p->T2a, p->G));
+                rows = p->T2a;
+            }
+            if (dft2d_gemm_i(p, rows, p->T2b, S, 0, 1.0 / p->n_phi, st)) return 1;
+            return transpose_i(p, p->T2b, c_out, S, p->n_phi, st);
+        }
         XFB_LAUNCH(p, PG_FFT, st,
                    dft2d_forward_kernel<<<cdiv(S, DFT_ROWS), DFT_THREADS, dft_smem(p->n_phi), st>>>(in, shells_per_run, sub, c_out, S, p->n_phi,
                                                                                                    1.0 / p->n_phi, real_only));
@@ -281,6 +339,14 @@ static int sht_forward_i(xfb_plan* p, SlotView in, int shells_per_run, double2* 
 static int sht_inverse_i(xfb_plan* p, const double2* c_in, double2* grid_out, int S, cudaStream_t st, int herm = 0,
                          const double2* mod_rho_hat = nullptr, SlotView mod_out = SlotView{}, int shells_per_run = 1) {
     if (p->dims == 2) {   // ifft(c * n_phi) / irfft(c * n_phi, n_phi)  (mathLibrary.py:478-482,492-496)
+        if (S <= p->max_batch * p->n_r) {
+            if (transpose_i(p, c_in, p->T2a, p->n_phi, S, st)) return 1;                 // [N][S] -> rows [S][N]
+            if (herm) {
+                const long long n = (long long)S * (p->n_phi / 2 + 1);
+                XFB_LAUNCH(p, PG_MISC, st, hermitian_complete_rows_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(p->T2a, S, p->n_phi));
+            }
+            return dft2d_gemm_i(p, p->T2a, grid_out, S, 1, 1.0, st);
+        }
         XFB_LAUNCH(p, PG_FFT, st,
                    dft2d_inverse_kernel<<<cdiv(S, DFT_ROWS), DFT_THREADS, dft_smem(p->n_phi), st>>>(c_in, grid_out, S, p->n_phi, herm));
         return 0;
@@ -325,7 +391,7 @@ static int hankel_i(xfb_plan* p, int dir, const double2* c_in, double2* c_out, i
         if (!attr_done) { XFB_CUDA(cudaFuncSetAttribute(hankel2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hankel2_smem())); attr_done = true; }
         XFB_LAUNCH(p, PG_HANKEL, st,
                    hankel2_kernel<<<g, 256, hankel2_smem(), st>>>(c_in, c_out, p->hankel_w, p->hk_tiles, p->n_r, p->hankel_n_sum, p->hankel_skip,
-                                                                 dir == 0 ? p->hk_fwd_scale : p->hk_inv_scale, dir));
+                                                                 dir == 0 ? p->hk_fwd_scale : p->hk_inv_scale, dir, p->n_r, 0));
         return 0;
     }
     XFB_LAUNCH(p, PG_HANKEL, st,
