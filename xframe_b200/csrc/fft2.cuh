@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) fft2_forward_kernel(SlotView grid, int sh
 }
 
 // a [S][M2][n_theta] -> grid [S][n_theta][N] (unnormalised inverse DFT)
-template <int N1, int N2>
+template <int N1, int N2, bool MOD>
 // mod_rho_hat != nullptr: the transform output is I_proj and the kernel writes the modified-intensity density instead
 // (project_to_modified_intensity fused, fxs_Projections.py:899-909): mod_out[x] = rho_hat[x] sqrt(Re I_proj[x] / |rho_hat[x]|^2)
 __global__ void __launch_bounds__(256) fft2_inverse_kernel(const double2* __restrict__ a, double2* __restrict__ grid,
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) fft2_inverse_kernel(const double2* __rest
         const int t = tid % N2, row0 = tid / N2;
         double2* dst = grid + ((size_t)s * n_theta + theta0) * C::N;
         const double2* rh = nullptr;
-        if (mod_rho_hat) {
+        if constexpr (MOD) {
             const int run = s / shells_per_run, shell_in_run = s - run * shells_per_run;
             rh = mod_rho_hat + ((size_t)s * n_theta + theta0) * C::N;
             dst = slot_run_ptr(mod_out, run) + ((size_t)shell_in_run * n_theta + theta0) * C::N;
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(256) fft2_inverse_kernel(const double2* __rest
 #pragma unroll
             for (int j = 0; j < N1; ++j) {
                 double2 o = y[j];
-                if (rh) {
+                if constexpr (MOD) {
                     const double2 v = ldg2(rh + (size_t)row * C::N + t + N2 * j);
                     const double sq = __dadd_rn(__dmul_rn(v.x, v.x), __dmul_rn(v.y, v.y));
                     double mult = 0.0;
@@ -196,14 +196,17 @@ static int launch_fft2(bool forward, SlotView in, int shells_per_run, const doub
     static bool attr_done = false;
     if (!attr_done) {
         XFB_CUDA(cudaFuncSetAttribute(fft2_forward_kernel<N1, N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        XFB_CUDA(cudaFuncSetAttribute(fft2_inverse_kernel<N1, N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        XFB_CUDA(cudaFuncSetAttribute(fft2_inverse_kernel<N1, N2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        XFB_CUDA(cudaFuncSetAttribute(fft2_inverse_kernel<N1, N2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         attr_done = true;
     }
     dim3 g(n_shells, n_theta / C::TH);
     if (forward)
         fft2_forward_kernel<N1, N2><<<g, 256, C::SMEM, st>>>(in, shells_per_run, sub, out, tw, n_theta, l_max, half);
+    else if (mod_rho_hat)
+        fft2_inverse_kernel<N1, N2, true><<<g, 256, C::SMEM, st>>>(in.base, out, tw, n_theta, l_max, half, mod_rho_hat, mod_out, shells_per_run);
     else
-        fft2_inverse_kernel<N1, N2><<<g, 256, C::SMEM, st>>>(in.base, out, tw, n_theta, l_max, half, mod_rho_hat, mod_out, shells_per_run);
+        fft2_inverse_kernel<N1, N2, false><<<g, 256, C::SMEM, st>>>(in.base, out, tw, n_theta, l_max, half, mod_rho_hat, mod_out, shells_per_run);
     XFB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -211,8 +211,10 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 static inline size_t legendre2_fwd_smem(int n_theta) {
     return (size_t)LEG2_FST * LEG2_FR * (n_theta + 4) * sizeof(double2) + (size_t)2 * (n_theta / 2) * LEG_LDB * sizeof(double);
 }
-static inline size_t legendre2_inv_smem(int NP, int n_theta) {
-    return (size_t)2 * 2 * LEG2_ROWS * (NP + 2) * sizeof(double2) + (size_t)2 * NP * (n_theta / 2 + 4) * sizeof(double);
+#define LEG2_IR 16          // inverse: rows per group
+#define LEG2_IST 3          // inverse: cp.async stages
+static inline size_t legendre2_inv_smem(int NP) {
+    return (size_t)LEG2_IST * 2 * LEG2_IR * (NP + 4) * sizeof(double2) + (size_t)2 * NP * LEG_LDB * sizeof(double);
 }
 
 template <int R, int ST>
@@ -297,6 +299,106 @@ __global__ void __launch_bounds__(LEG2_THREADS, 3) legendre2_forward_kernel(cons
                 const int le = m + 2 * col, lo = le + 1;
                 if (do_e && le <= l_max) c[(size_t)(le * (le + 1) + ms) * S + sh] = make_double2(sg * ere[mb][cc], sg * eim[mb][cc]);
                 if (do_o && lo <= l_max) c[(size_t)(lo * (lo + 1) + ms) * S + sh] = make_double2(sg * ore_[mb][cc], sg * oim[mb][cc]);
+            }
+        }
+        buf = (buf + 1) % ST;
+    }
+}
+
+
+// inverse (synthesis) counterpart: coefficients c [(L+1)^2][S] -> phi-Fourier rows a [S][M2][n_theta] for one order m per CTA.
+// The coefficient rows of the next shell groups are gathered with cp.async (16-byte elements, 8 / 16 consecutive shells
+// of one (l, +-m) row are contiguous) while the current group is multiplied with the resident tables IE / IO [NP][K2].
+template <int R, int ST>
+__global__ void __launch_bounds__(LEG2_THREADS, 3) legendre2_inverse_kernel(const double2* __restrict__ c, double2* __restrict__ a,
+                                                                           const double* __restrict__ IE, const double* __restrict__ IO,
+                                                                           int S, int l_max, int n_theta, int NP, int pos_only) {
+    extern __shared__ __align__(16) unsigned char smem_leg2[];
+    const int K2 = n_theta >> 1;
+    const int RS = NP + 4;                                 // row stride (double2): rows 64 B apart mod 128
+    double2* raw = reinterpret_cast<double2*>(smem_leg2);  // [ST][2 parities][R][RS]
+    double* Be = reinterpret_cast<double*>(raw + ST * 2 * R * RS);      // [NP][LEG_LDB]
+    double* Bo = Be + NP * LEG_LDB;
+    const int m = blockIdx.y;
+    const int M2 = 2 * l_max + 1;
+    const bool both = (!pos_only) && m > 0;
+    const int SH = both ? R / 2 : R;
+    const int n_groups = (S + SH - 1) / SH;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ar = lane >> 2, ak = lane & 3;
+    const int wn = warp & 3, r0 = (warp >> 2) * (R / 2);
+    const int ne = (l_max - m) / 2 + 1, no = (l_max - m + 1) / 2;
+    const int Ke = (ne + 3) & ~3, Ko = (no + 3) & ~3;      // contraction only over existing degrees (zero padded)
+    const bool jok = wn * 8 < K2;
+
+    auto fetch = [&](int g, int buf) {
+        if (g < n_groups) {
+            double2* dst = raw + (size_t)buf * 2 * R * RS;
+            for (int item = tid; item < 2 * NP * R; item += LEG2_THREADS) {
+                const int shl = item % SH;                 // shells fastest: contiguous 16-byte elements of one coefficient row
+                int rest = item / SH;
+                const int sign = both ? (rest & 1) : 0;
+                if (both) rest >>= 1;
+                const int i = rest % NP, par = rest / NP;
+                const int l = m + par + 2 * i;
+                const int sh = g * SH + shl;
+                const bool ok = (l <= l_max) && (sh < S);
+                const int row = sign * (R / 2) + shl;
+                cp_async16(dst + ((size_t)par * R + row) * RS + i, c + (size_t)(ok ? l * (l + 1) + (sign ? -m : m) : 0) * S + (ok ? sh : 0), ok);
+            }
+        }
+        cp_async_commit();
+    };
+
+    const int per_cta = (n_groups + gridDim.x - 1) / gridDim.x;
+    int g = blockIdx.x * per_cta;
+    const int g_end = min(n_groups, g + per_cta);
+    if (g >= g_end) return;
+#pragma unroll
+    for (int s_ = 0; s_ < ST - 1; ++s_) fetch(g + s_ < g_end ? g + s_ : n_groups, s_);
+    const double* IEm = IE + (size_t)m * NP * K2;
+    const double* IOm = IO + (size_t)m * NP * K2;
+    for (int item = tid; item < NP * LEG_NB; item += LEG2_THREADS) {
+        const int i = item / LEG_NB, cc = item - i * LEG_NB;
+        const bool ok = cc < K2;
+        Be[i * LEG_LDB + cc] = ok ? __ldg(IEm + (size_t)i * K2 + cc) : 0.0;
+        Bo[i * LEG_LDB + cc] = ok ? __ldg(IOm + (size_t)i * K2 + cc) : 0.0;
+    }
+    int buf = 0;
+    for (; g < g_end; ++g) {
+        cp_async_wait<ST - 2>();
+        __syncthreads();
+        fetch(g + ST - 1 < g_end ? g + ST - 1 : n_groups, (buf + ST - 1) % ST);
+        const double2* ce = raw + (size_t)buf * 2 * R * RS + (size_t)(r0 + ar) * RS;
+        const double2* co = ce + (size_t)R * RS;
+        double ere[2] = {}, eim[2] = {}, ore_[2] = {}, oim[2] = {};
+        if (jok) {
+            for (int k0 = 0; k0 < Ke; k0 += 4) {
+                const double2 x = ce[k0 + ak];
+                const double be = Be[(k0 + ak) * LEG_LDB + wn * 8 + ar];
+                dmma884(ere[0], ere[1], x.x, be);
+                dmma884(eim[0], eim[1], x.y, be);
+            }
+            for (int k0 = 0; k0 < Ko; k0 += 4) {
+                const double2 x = co[k0 + ak];
+                const double bo = Bo[(k0 + ak) * LEG_LDB + wn * 8 + ar];
+                dmma884(ore_[0], ore_[1], x.x, bo);
+                dmma884(oim[0], oim[1], x.y, bo);
+            }
+            const int row = r0 + ar;
+            const int sh = g * SH + (both ? (row % (R / 2)) : row), sign = both ? (row / (R / 2)) : 0;
+            if (sh < S) {
+                const double sg = (sign && (m & 1)) ? -1.0 : 1.0;      // (-1)^m on the -m rows
+                const int mm = sign ? (M2 - m) : m;
+                double2* dst = a + ((size_t)sh * M2 + mm) * n_theta;
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int j = wn * 8 + 2 * ak + cc;
+                    if (j < K2) {
+                        dst[j] = make_double2(sg * (ere[cc] + ore_[cc]), sg * (eim[cc] + oim[cc]));
+                        dst[n_theta - 1 - j] = make_double2(sg * (ere[cc] - ore_[cc]), sg * (eim[cc] - oim[cc]));
+                    }
+                }
             }
         }
         buf = (buf + 1) % ST;

@@ -213,6 +213,7 @@ int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
     p->leg2 = (p->n_theta / 2 <= 32 && p->NP <= 32 && p->n_theta % 4 == 0);
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, dev); }
     if (p->leg2) XFB_CUDA(cudaFuncSetAttribute(legendre2_forward_kernel<LEG2_FR, LEG2_FST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre2_fwd_smem(p->n_theta)));
+    if (p->leg2) XFB_CUDA(cudaFuncSetAttribute(legendre2_inverse_kernel<LEG2_IR, LEG2_IST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre2_inv_smem(p->NP)));
     XFB_CUDA(cudaFuncSetAttribute(legendre_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre_fwd_smem(p->n_theta)));
     XFB_CUDA(cudaFuncSetAttribute(legendre_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre_inv_smem(p->n_theta, p->NP)));
     *out = p;
@@ -352,10 +353,18 @@ static int sht_inverse_i(xfb_plan* p, const double2* c_in, double2* grid_out, in
         return 0;
     }
     // herm (3-D): the coefficients belong to a real field and only m >= 0 is valid in c_in
+    if (p->leg2) {
+        const int groups = cdiv(S, herm ? LEG2_IR : LEG2_IR / 2);
+        dim3 g2(std::min(groups, std::max(1, (3 * p->n_sm * 4) / (p->L + 1))), p->L + 1);
+        XFB_LAUNCH(p, PG_LEGENDRE, st,
+                   legendre2_inverse_kernel<LEG2_IR, LEG2_IST><<<g2, LEG2_THREADS, legendre2_inv_smem(p->NP), st>>>(c_in, p->A0, p->IE, p->IO, S, p->L,
+                                                                                                                  p->n_theta, p->NP, herm));
+    } else {
     dim3 g(cdiv(S, herm ? 32 : 16), p->L + 1);
     XFB_LAUNCH(p, PG_LEGENDRE, st,
                legendre_inverse_kernel<<<g, LEG_THREADS, legendre_inv_smem(p->n_theta, p->NP), st>>>(c_in, p->A0, p->IE, p->IO, S, p->L, p->n_theta, p->NP,
                                                                                                      herm));
+    }
     XFB_LAUNCH(p, PG_FFT, st,
                if (launch_fft(false, p->n_phi, flat_view(p->A0, 0), shells_per_run, nullptr, grid_out, p->tw, S, p->n_theta, p->L, st, herm, mod_rho_hat,
                               mod_out)) return 1);
