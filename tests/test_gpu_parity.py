@@ -429,3 +429,31 @@ def test_worker_shift_to_center_matches_reference():
         assert rel_l2(r['last_reciprocal_density'], g['loop_last_reciprocal_density']) < 1e-6
         assert rel_l2(r['reciprocal_density'], g['loop_reciprocal_density']) < 1e-6
         assert rel_l2(r['last_deg2_invariant'], g['loop_last_deg2']) < 1e-6
+
+
+def test_results_do_not_depend_on_the_batch(full):
+    """A run gives bit-identical densities and errors whether it is iterated alone or inside a batch (L=63 / N_r=128,
+    several problems per CTA in the Jacobi work queue, multi-group cp.async rings in the Legendre kernels), and every
+    Procrustes problem of the batch is solved."""
+    import bench
+    from xframe_b200.plan import HIO
+    nb = 12
+    bench.select_workload('l63')
+    plan, sd, rho0 = bench.build_problem(nb, 0, [1000 + i for i in range(nb)])
+    plan.mtip_init(rho0)
+    for _ in range(3):
+        plan.mtip_iterate(HIO, True, [0.5])
+    orders, sw = plan.jacobi_sweeps()
+    assert sw.shape == (nb, len(orders)) and sw.min() >= 1 and sw.max() < 40
+    hist, _ = plan.mtip_errors()
+    big = N(plan.mtip_grid('last_real'))
+    hist = N(hist)
+    plan.close()
+    for k in (0, 7, nb - 1):
+        p1, _, r1 = bench.build_problem(1, 0, [1000 + k])
+        p1.mtip_init(r1)
+        for _ in range(3):
+            p1.mtip_iterate(HIO, True, [0.5])
+        assert np.array_equal(N(p1.mtip_grid('last_real'))[0], big[k])
+        assert np.array_equal(N(p1.mtip_errors()[0])[0], hist[k])
+        p1.close()
