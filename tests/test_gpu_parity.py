@@ -431,7 +431,7 @@ def test_worker_shift_to_center_matches_reference():
         assert rel_l2(r['last_deg2_invariant'], g['loop_last_deg2']) < 1e-6
 
 
-def test_results_do_not_depend_on_the_batch(full):
+def test_results_do_not_depend_on_the_batch():
     """A run gives bit-identical densities and errors whether it is iterated alone or inside a batch (L=63 / N_r=128,
     several problems per CTA in the Jacobi work queue, multi-group cp.async rings in the Legendre kernels), and every
     Procrustes problem of the batch is solved."""
