@@ -432,7 +432,7 @@ def test_worker_shift_to_center_matches_reference():
 
 
 def test_results_do_not_depend_on_the_batch():
-    """A run gives bit-identical densities and errors whether it is iterated alone or inside a batch (L=63 / N_r=128,
+    """A run gives bit-identical densities (and errors equal to rounding) whether it is iterated alone or inside a batch (L=63 / N_r=128,
     several problems per CTA in the Jacobi work queue, multi-group cp.async rings in the Legendre kernels), and every
     Procrustes problem of the batch is solved."""
     import bench
@@ -455,5 +455,6 @@ def test_results_do_not_depend_on_the_batch():
         for _ in range(3):
             p1.mtip_iterate(HIO, True, [0.5])
         assert np.array_equal(N(p1.mtip_grid('last_real'))[0], big[k])
-        assert np.array_equal(N(p1.mtip_errors()[0])[0], hist[k])
+        # the error integrals are summed over a batch-dependent number of blocks: equal to rounding, not bitwise
+        assert np.allclose(N(p1.mtip_errors()[0])[0], hist[k], rtol=1e-12, atol=0)
         p1.close()
