@@ -110,8 +110,10 @@ def algorithmic_bytes(nb):
         'hankel': nb * 2 * C * 16,
         'real_update': nb * (3 * G * 16 + G),  # IFT(rho_hat'-rho_hat), rho_prev in, rho_next out, support mask (fused ft_stab)
         'pointwise': nb * int(2.5 * G * 16),   # square: G in, G out ; modify_intensity: 2G in, G out  -> average per launch
-        # Jacobi: G and V_l^T in, G~/sigma and V_l U out (Procrustes blocks, 8 B reals); latency bound, see DESIGN.md 4.4
-        'procrustes_jacobi': nb * 4 * sum(min(N_R, 2 * l + 1) * N_R for l in range(2, L_MAX + 1, 2)) * 8,
+        # Jacobi: M^T in, the two factors of the polar matrix (gn, pp) out, zero-padded column blocks of 8 B reals; the kernel
+        # is shared-memory resident and latency / FP64-pipe bound: its HBM fraction is low by construction
+        'procrustes_jacobi': nb * 3 * sum(min(N_R, 2 * l + 1) * (64 if 2 * l + 1 <= 64 else 128 if 2 * l + 1 <= 128 else 256)
+                                         for l in range(2, L_MAX + 1, 2)) * 8,
     }
 
 
@@ -321,9 +323,13 @@ def run_ours(args):
                 'frac': (achieved / peak) if achieved is not None else None, 'traffic': None, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': ab.get(dom), 'launch_ms': per_launch_ms, 'share_of_step': groups[dom]['ms'] / tot_ms}
         if dom == 'procrustes_jacobi':
-            roof['note'] = ('dominant kernel is the one-sided Jacobi polar factor: shared-memory resident, latency/sync bound '
-                            '(no HBM or tensor roofline applies; its HBM fraction is low by construction). Top HBM-bound kernel: '
-                            'fft_phi, see groups')
+            if METRIC.endswith('L63_Nr128') and nb == 128:
+                # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full, profiles/r01j_jacobi_ncu_details.txt
+                roof['traffic'] = 233537024 + 425556992
+            roof['note'] = ('dominant kernel is the QR-preconditioned one-sided Jacobi polar factor: shared-memory resident, bound by the '
+                            'sequential rotation steps and the FP64 pipe (ncu: FP64 pipe 19 % of issue peak, barrier wait the top stall); '
+                            'neither the HBM nor the tensor roofline applies and its HBM fraction is low by construction. '
+                            'Roofline-bound kernels: fft_phi (HBM), legendre / hankel (FP64 DMMA), see groups and profiles/README.md')
         roof['groups'] = {k: {'ms_per_step': v['ms'] / K, 'launches_per_step': v['launches'] / K,
                               **({'GBps': ab[k] * v['launches'] / (v['ms'] * 1e-3) / 1e9} if k in ab else {}),
                               **({'TFLOPs_fp64': hankel_flops(nb) * v['launches'] / (v['ms'] * 1e-3) / 1e12} if k == 'hankel' else {})}
