@@ -80,7 +80,8 @@ class PolarIntegrator:                           # mathLibrary.py:1242-1265
     def integrate(self, values):
         trapz = getattr(np, 'trapezoid', None) or np.trapz
         s = trapz(values, x=self.phis, axis=1)
-        return trapz(s * self.rs, x=self.rs, axis=0)
+        rs = self.rs.reshape(self.rs.shape + (1,) * (values.ndim - 2))
+        return trapz(s * rs, x=self.rs, axis=0)
 
 
 # ------------------------------------------------------------------ reciprocal projection, 2-D branches
@@ -120,10 +121,23 @@ class ReciprocalProjection2D:
         self.radial_mask = np.broadcast_to(True & data_mask, mask.shape).copy()
         so = ropt.get('SO_freedom', {'use': False})
         self.so_order_id = None
-        if so.get('use', False):
-            raise AssertionError('SO_freedom not restated')
+        self.use_SO_freedom = bool(so.get('use', False))
+        self.radial_high_pass = so.get('radial_high_pass', 0.2)
+        if self.use_SO_freedom:
+            self.so_order_id = self.rank_projection_matrix_orders_2d()[0][0]                        # :964-971
         self.n_half = (grid_shape[1] + 1) // 2
         self.deg2_invariants = np.array(tuple(Im[:, None] * Im[None, :].conj() for Im in proj))      # fxs_invariant_tools.py:906-914
+
+    def rank_projection_matrix_orders_2d(self):  # :933-962
+        hp = int((len(self.radial_points) - 1) * self.radial_high_pass)
+        radial_points = self.radial_points[hp:]
+        orders = np.array(list(self.used_orders.keys()))
+        order_mask = (orders % 2 == 0) & (orders != 0)
+        vect = self.projection_matrices[order_mask, hp:].T * radial_points[:, None]
+        metric = np.mean(np.abs(vect), axis=0)
+        sorted_indices = np.argsort(metric)[::-1]
+        so_ids = order_mask.nonzero()[0][sorted_indices]
+        return so_ids, orders[so_ids], sorted_indices
 
     def approximate_unknowns(self, I):           # :727-748 ; I [N_r, M+1]
         ids = list(self.used_orders.values())
@@ -132,7 +146,46 @@ class ReciprocalProjection2D:
         unk = np.ones(len(ids), dtype=complex)
         nz = s != 0
         unk[nz] = s[nz] / np.abs(s[nz])
+        if self.use_SO_freedom:
+            unk[self.so_order_id] = 1
         return unk
+
+    def generate_remaining_SO_projection(self, n_angular_points):    # :1022-1095
+        orders = np.array(list(self.used_orders.keys()))
+        projection_orders = np.concatenate((np.arange(int(n_angular_points / 2) + 1),
+                                            -1 * np.arange(int(n_angular_points / 2) + n_angular_points % 2)[:0:-1]))
+        order_mask = (orders % 2 == 0) & (orders != 0)
+        harmonic_orders = orders[order_mask]
+        max_order = np.max(harmonic_orders)
+        so_ids, so_orders, sorted_order_indices = self.rank_projection_matrix_orders_2d()
+        remaining_rotations = current_order = so_orders[0]
+        free_orders_mask = True
+        order_indices, angle_coeffs, angles, gcds = (), (), (), ()
+        while remaining_rotations > 2:
+            multiples = np.arange(current_order, max_order + 1, current_order)
+            multiple_indices = np.where(np.isin(harmonic_orders, multiples))
+            free_orders_mask = free_orders_mask * ~np.isin(sorted_order_indices, multiple_indices)
+            if not free_orders_mask.any():
+                break
+            current_order_index = sorted_order_indices[free_orders_mask][0]
+            current_order = harmonic_orders[current_order_index]
+            gcd = np.gcd(remaining_rotations, current_order)
+            n_ind = remaining_rotations / gcd
+            smallest_angle = 2 * np.pi / n_ind
+            coeff = np.argmin((np.arange(1, n_ind) * current_order / gcd) % n_ind) + 1
+            order_indices += (current_order_index,)
+            angle_coeffs += (coeff,)
+            angles += (smallest_angle,)
+            gcds += (gcd,)
+            remaining_rotations = gcd
+
+        def apply_SO_freedom(harmonic_coefficients, fxs_unknowns):
+            phases = (-1.j * np.log(fxs_unknowns[order_mask])).real
+            rotation_phase = 0
+            for oi, angle, ac, gcd in zip(order_indices, angles, angle_coeffs, gcds):
+                rotation_phase -= (phases[oi] // angle) * ac * angle / gcd
+            return harmonic_coefficients * np.exp(1.j * projection_orders * rotation_phase)
+        return apply_SO_freedom
 
     def mtip_projection(self, I, unknowns):      # :804-826 + :852-862
         ids = np.array(list(self.used_orders.values()))
@@ -198,6 +251,24 @@ class MTIP2D(O.MTIP):
         Ip = self.rp.mtip_projection(I, unk)
         I_proj = cht_real_inverse(Ip, self.n_phi)
         return self.rp.project_to_modified_intensity(rho_hat, np.array(sq), I_proj)
+
+    def run(self, rho0=None, rng=None):
+        # output modifiers (reconstruct.py:721-755): in 2-D `fix_orientation` (with SO_freedom) = shift_to_center + orientation fix
+        mods = self.opt.get('output_density_modifiers', {})
+        self._fix = bool(mods.get('fix_orientation', False)) and self.rp.use_SO_freedom
+        if self._fix:
+            self.opt = dict(self.opt)
+            self.opt['output_density_modifiers'] = dict(mods, shift_to_center=True)
+            self._apply_so = self.rp.generate_remaining_SO_projection(self.n_phi)
+        return super().run(rho0=rho0, rng=rng)
+
+    def _shift_to_center(self, rho_hat, rho):
+        a, b = super()._shift_to_center(rho_hat, rho)
+        if getattr(self, '_fix', False):         # fix_orientation sketch (:740-745)
+            unk = self.results['fxs_unknowns']
+            a = cht_complex_inverse(self._apply_so(cht_complex_forward(a), unk))
+            b = cht_complex_inverse(self._apply_so(cht_complex_forward(b), unk))
+        return a, b
 
     def _last_invariants(self, rho):             # fxs_invariant_tools.py:906-914
         I = cht_real_forward(O.square_grid(self.ft(rho)))

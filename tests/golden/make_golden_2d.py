@@ -19,15 +19,16 @@ sys.path.insert(0, HERE)
 from make_golden import import_reference, settings_dict, FakeDB          # noqa: E402
 
 
-def settings_dict_2d(n_r, m_max, max_q, ft_stab, particle_radius=250.0):
+def settings_dict_2d(n_r, m_max, max_q, ft_stab, particle_radius=250.0, so_freedom=False):
     sd = settings_dict(n_r, m_max, 1, 2 * m_max + 1, max_q, ft_stab, particle_radius)
     sd['dimensions'] = 2
     sd['grid'] = {'max_q': float(max_q), 'max_order': m_max, 'n_radial_points': n_r}
-    sd['output_density_modifiers'] = {'shift_to_center': False, 'fix_orientation': False}
+    sd['output_density_modifiers'] = {'shift_to_center': False, 'fix_orientation': bool(so_freedom)}
+    sd['projections']['reciprocal']['SO_freedom'] = {'use': bool(so_freedom), 'radial_high_pass': 0.2}
     return sd
 
 
-def build_case_2d(xframe, n_r, m_max, ft_stab, tag, seed=11):
+def build_case_2d(xframe, n_r, m_max, ft_stab, tag, seed=11, so_freedom=False):
     from xframe.library.pythonLibrary import DictNamespace, RecipeFactory
     from xframe.library.gridLibrary import SampledFunction, NestedArray
     from xframe import settings
@@ -36,7 +37,7 @@ def build_case_2d(xframe, n_r, m_max, ft_stab, tag, seed=11):
     from oracle import mtip as O, mtip2d as O2
 
     max_q = 2.0 * n_r / 794.0
-    sd = settings_dict_2d(n_r, m_max, max_q, ft_stab)
+    sd = settings_dict_2d(n_r, m_max, max_q, ft_stab, so_freedom=so_freedom)
     settings.project = DictNamespace.dict_to_dictnamespace(copy.deepcopy(sd))
     settings.general.cache_aware = False
     settings.general.n_control_workers = 0
@@ -69,7 +70,7 @@ def build_case_2d(xframe, n_r, m_max, ft_stab, tag, seed=11):
 
     rng = np.random.default_rng(seed)
     gshape = m.grid_pair.realGrid[:].shape[:-1]
-    out = {'n_r': n_r, 'm_max': m_max, 'n_phi': gshape[1], 'max_q': max_q, 'ft_stab': ft_stab,
+    out = {'n_r': n_r, 'm_max': m_max, 'n_phi': gshape[1], 'max_q': max_q, 'ft_stab': ft_stab, 'so_freedom': bool(so_freedom),
            'avg_intensity': inv['average_intensity'], 'data_q': inv['data_radial_points'], 'pm': inv['data_projection_matrices'],
            'phis': m.grid_pair.realGrid[0, :, 1], 'rs': m.grid_pair.realGrid[:, 0, 0], 'qs': m.grid_pair.reciprocalGrid[:, 0, 0]}
     x = rng.normal(size=gshape) + 1j * rng.normal(size=gshape)
@@ -145,3 +146,4 @@ if __name__ == '__main__':
     xf = import_reference()
     build_case_2d(xf, n_r=16, m_max=7, ft_stab=True, tag='ref2d_small_ftstab')
     build_case_2d(xf, n_r=24, m_max=15, ft_stab=False, tag='ref2d_medium_plain')
+    build_case_2d(xf, n_r=24, m_max=15, ft_stab=True, tag='ref2d_medium_so', so_freedom=True)   # the 2-D defaults: SO_freedom + fix_orientation

@@ -115,6 +115,20 @@ def test_projection_and_pointwise(case):
 
 def test_full_loop_against_reference(case):
     g, sd, plan, ps = case
+    if bool(g['so_freedom']):
+        # the 2-D defaults: SO_freedom pin during phasing + shift_to_center / fix_orientation output modifiers -> through the worker
+        from xframe_b200.worker import ProjectWorker
+        sdw = dict(sd)
+        sdw['GPU'] = {'use': True, 'batch': 2, 'seed': 1}
+        res, _ = ProjectWorker(sdw, data_2d(g), n_reconstructions=2, initial_densities=[g['rho0'], g['rho0']]).run()
+        for r in res:
+            assert rel_l2(r['error_dict']['main'], g['loop_main_error']) < 1e-6
+            assert rel_l2(r['fxs_unknowns'], g['loop_unknowns']) < 1e-6
+            assert rel_l2(r['last_real_density'], g['loop_last_real_density']) < 1e-6
+            assert rel_l2(r['real_density'], g['loop_real_density']) < 1e-6
+            assert rel_l2(r['last_reciprocal_density'], g['loop_last_reciprocal_density']) < 1e-6
+            assert rel_l2(r['last_deg2_invariant'], g['loop_last_deg2']) < 1e-6
+        return
     from xframe_b200.reconstruct import run_schedule
     res = run_schedule(plan, sd, T(np.stack([g['rho0'], g['rho0']])))
     assert rel_l2(res['errors'][0], g['loop_main_error']) < 1e-6 and np.array_equal(res['errors'][0], res['errors'][1])

@@ -7,12 +7,13 @@ from helpers import load_golden, rel_l2
 from oracle import mtip as O
 from oracle import mtip2d as O2
 
-CASES = ['ref2d_small_ftstab', 'ref2d_medium_plain']
+CASES = ['ref2d_small_ftstab', 'ref2d_medium_plain', 'ref2d_medium_so']
 
 
 def settings_2d(g):
     from make_golden_2d import settings_dict_2d
-    return settings_dict_2d(int(g['n_r']), int(g['m_max']), float(g['max_q']), bool(g['ft_stab']))
+    return settings_dict_2d(int(g['n_r']), int(g['m_max']), float(g['max_q']), bool(g['ft_stab']),
+                            so_freedom=bool(g['so_freedom']) if 'so_freedom' in g else False)
 
 
 def data_2d(g):

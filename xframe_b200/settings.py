@@ -37,10 +37,10 @@ def default_settings():
                 'used_order_ids': np.arange(64),
                 'odd_orders_to_0': True, 'use_averaged_intensity': True,
                 'q_mask': {'type': 'none'},
-                'SO_freedom': {'use': False},
+                'SO_freedom': {'use': None, 'radial_high_pass': 0.2},     # None: resolved from `dimensions` (False in 3-D, True in 2-D)
             },
         },
-        'output_density_modifiers': {'shift_to_center': False},
+        'output_density_modifiers': {'shift_to_center': False, 'fix_orientation': None},   # fix_orientation: True in 2-D only
         'main_loop': {
             'error': {'methods': {
                 'real': {'calculate': ['l2_projection_diff'], 'l2_projection_diff': {'inside_initial_support': True}},
@@ -115,6 +115,16 @@ def finalize(opt):
     sup = opt['projections']['real']['projections']['support']['initial_support']
     if sup.get('max_radius') is None:
         sup['max_radius'] = opt['particle_radius']
+    # `_if` / `_only_if` switches on /dimensions (default_0.01.yaml:185-200)
+    so = opt['projections']['reciprocal'].setdefault('SO_freedom', {})
+    if so.get('use') is None:
+        so['use'] = opt['dimensions'] == 2
+    so.setdefault('radial_high_pass', 0.2)
+    mods = opt.setdefault('output_density_modifiers', {})
+    if mods.get('fix_orientation') is None:
+        mods['fix_orientation'] = opt['dimensions'] == 2
+    if opt['dimensions'] != 2:
+        mods['fix_orientation'] = False
     return opt
 
 

@@ -117,9 +117,56 @@ class ProjectionSetup2D:
             raise XfbError("2-D path: only q_mask type 'none' is supported")
         self.radial_mask = np.ascontiguousarray(np.broadcast_to((qs >= dq.min()) & (qs <= dq.max()), (m_max + 1, len(qs))))
         so = ropt.get('SO_freedom', {'use': False})
-        if so.get('use', False):
-            raise XfbError("2-D path: projections.reciprocal.SO_freedom.use is not supported yet (set it to False)")
-        self.so_order_id = None
+        self.use_SO_freedom = bool(so.get('use', False))
+        self.radial_high_pass = so.get('radial_high_pass', 0.2)
+        self.qs = qs
+        self.so_order_id = int(self.rank_orders()[0][0]) if self.use_SO_freedom else None           # :964-971
+
+    def rank_orders(self):
+        """rank_projection_matrix_orders_2d (fxs_Projections.py:933-962): even non-zero orders by mean |V_m(q)| q beyond the
+        radial high pass."""
+        hp = int((len(self.qs) - 1) * self.radial_high_pass)
+        orders = np.arange(self.n_used)
+        order_mask = (orders % 2 == 0) & (orders != 0)
+        metric = np.mean(np.abs(self.projection_matrices[order_mask, hp:].T * self.qs[hp:, None]), axis=0)
+        sorted_indices = np.argsort(metric)[::-1]
+        so_ids = order_mask.nonzero()[0][sorted_indices]
+        return so_ids, orders[so_ids], sorted_indices
+
+    def remaining_so_rotation(self, n_angular_points):
+        """generate_remaining_SO_projection_2D (fxs_Projections.py:1022-1095): returns f(unknowns) -> rotation phase; the
+        harmonic coefficients of order m are then multiplied by exp(i m phase)."""
+        orders = np.arange(self.n_used)
+        order_mask = (orders % 2 == 0) & (orders != 0)
+        harmonic_orders = orders[order_mask]
+        max_order = np.max(harmonic_orders)
+        _, so_orders, sorted_order_indices = self.rank_orders()
+        remaining = current = so_orders[0]
+        free = True
+        steps = []
+        while remaining > 2:
+            multiples = np.arange(current, max_order + 1, current)
+            free = free * ~np.isin(sorted_order_indices, np.where(np.isin(harmonic_orders, multiples)))
+            if not np.any(free):
+                break
+            idx = sorted_order_indices[free][0]
+            current = harmonic_orders[idx]
+            gcd = np.gcd(remaining, current)
+            n_ind = remaining / gcd
+            angle = 2 * np.pi / n_ind
+            coeff = np.argmin((np.arange(1, n_ind) * current / gcd) % n_ind) + 1
+            steps.append((idx, angle, coeff, gcd))
+            remaining = gcd
+        projection_orders = np.concatenate((np.arange(int(n_angular_points / 2) + 1),
+                                            -1 * np.arange(int(n_angular_points / 2) + n_angular_points % 2)[:0:-1]))
+
+        def rotation_phase(unknowns):
+            phases = (-1.j * np.log(np.asarray(unknowns)[order_mask])).real
+            rot = 0.0
+            for idx, angle, coeff, gcd in steps:
+                rot -= (phases[idx] // angle) * coeff * angle / gcd
+            return rot
+        return rotation_phase, projection_orders
 
     def apply_to(self, plan, sv_cutoff=None):
         plan.set_projection_2d(self.projection_matrices, self.radial_mask, self.number_of_particles, self.so_order_id)

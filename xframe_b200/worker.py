@@ -33,8 +33,11 @@ class ProjectWorker:
             raise XfbError(f"dimensions={settings['dimensions']} is not supported")
         mods = settings.get('output_density_modifiers', {})
         self.shift_to_center = bool(mods.get('shift_to_center', False))
-        if self.dims == 2 and mods.get('fix_orientation', False) and settings['projections']['reciprocal'].get('SO_freedom', {}).get('use', False):
-            raise XfbError("output_density_modifiers.fix_orientation (2-D SO_freedom) is not implemented by xframe_b200")
+        # 2-D: fix_orientation (with SO_freedom) = shift_to_center followed by the orientation fix (reconstruct.py:745-751)
+        self.fix_orientation = bool(self.dims == 2 and mods.get('fix_orientation', False)
+                                    and settings['projections']['reciprocal'].get('SO_freedom', {}).get('use', False))
+        if self.fix_orientation:
+            self.shift_to_center = True
         if not settings['GPU']['use']:
             raise XfbError("GPU.use is False: xframe_b200 has no CPU path (the reference falls back to CPU, reconstruct.py:96-102)")
         if number_of_gpus() == 0:
@@ -119,8 +122,16 @@ class ProjectWorker:
             res = run_schedule(plan, self.opt, rho0)
             unknowns = [plan.unknowns(k) for k in range(len(ids))]      # of the last mtip_start (reconstruct.py:523,1013)
             if self.shift_to_center:                                    # output modifier on the best and the last pair (:988-989)
+                if self.fix_orientation and not hasattr(self, '_so_rot'):
+                    self._so_rot = self.proj.remaining_so_rotation(plan.n_phi)
                 for a, b in (('best_reciprocal', 'best_real'), ('last_reciprocal', 'last_real')):
                     rh, rr, _ = self._shift_to_center(torch.from_numpy(res[a]).to(plan.device), torch.from_numpy(res[b]).to(plan.device))
+                    if self.fix_orientation:                            # fix_orientation sketch (:740-745, fxs_Projections.py:1081-1094)
+                        rot_fn, orders_m = self._so_rot
+                        rot = torch.tensor([rot_fn(u) for u in unknowns], dtype=torch.float64, device=plan.device)
+                        ramp = torch.exp(1j * rot[:, None, None] * torch.from_numpy(orders_m.astype(np.float64)).to(plan.device)[None, None, :])
+                        rh = plan.sht_inverse((plan.sht_forward(rh.contiguous()) * ramp).contiguous())
+                        rr = plan.sht_inverse((plan.sht_forward(rr.contiguous()) * ramp).contiguous())
                     res[a], res[b] = rh.cpu().numpy(), rr.cpu().numpy()
             # last_deg2_invariant: B_l = I_l I_l^H of the last density (reconstruct.py:757-765,993)
             last = torch.from_numpy(res['last_real']).to(plan.device)
