@@ -115,7 +115,7 @@ def test_projection_and_pointwise(case):
 
 def test_full_loop_against_reference(case):
     g, sd, plan, ps = case
-    if bool(g['so_freedom']):
+    if 'so_freedom' in g and bool(g['so_freedom']):
         # the 2-D defaults: SO_freedom pin during phasing + shift_to_center / fix_orientation output modifiers -> through the worker
         from xframe_b200.worker import ProjectWorker
         sdw = dict(sd)
