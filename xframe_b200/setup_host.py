@@ -32,6 +32,9 @@ class ProjectionSetup:
             raise XfbError("xframe_b200 supports used_order_ids = arange(n) (the only setting under which the "
                            "reference indexes its projection matrices consistently, fxs_Projections.py:837-840)")
         self.n_used = n_used
+        if ropt.get('SO_freedom', {}).get('use', False):
+            raise XfbError("projections.reciprocal.SO_freedom.use is a 2-D option (default False in 3-D, default_0.01.yaml:185-191); "
+                           "the reference's 3-D variant only drops one imaginary part (fxs_Projections.py:766-786) and is not implemented")
         self.number_of_particles = float(ropt['number_of_particles']['initial'])
         pms = [np.asarray(data['data_projection_matrices'][i]) for i in range(n_used)]
         same = dq.shape == qs.shape and bool((dq == qs).all())                                         # :642-651
