@@ -458,3 +458,42 @@ def test_results_do_not_depend_on_the_batch():
         # the error integrals are summed over a batch-dependent number of blocks: equal to rounding, not bitwise
         assert np.allclose(N(p1.mtip_errors()[0])[0], hist[k], rtol=1e-12, atol=0)
         p1.close()
+
+
+@pytest.mark.parametrize('l_max,n_r,n_theta,n_phi,ft_type', [(10, 33, 16, 32, 'midpoint'), (6, 20, 8, 16, 'trapz'), (21, 48, 24, 64, 'midpoint')])
+def test_ragged_sizes_iterations_against_oracle(l_max, n_r, n_theta, n_phi, ft_type):
+    """Odd / small / non-power-of-two radial sizes and the trapz radial rule: HIO_ft_stab, shrink wrap and plain ER
+    iterations of a batch of 3 against the oracle (odd N_r takes the non-cp.async Hankel kernel, n_phi = 32 / 16 the generic
+    Stockham FFT without the fused pointwise variants, n_theta = 24 the 8-row FFT tiles)."""
+    from xframe_b200.plan import Plan, HIO, ER
+    from xframe_b200 import setup_host as S
+    from xframe_b200.settings import tutorial_settings
+    max_q = 2.0 * n_r / 794.0
+    sd = tutorial_settings(grid={'max_q': max_q, 'max_order': l_max, 'n_phi': n_phi, 'n_theta': n_theta, 'n_radial_points': n_r},
+                           fourier_transform={'type': ft_type, 'reciprocity_coefficient': 2.0})
+    sd['projections']['reciprocal']['used_order_ids'] = np.arange(l_max + 1)
+    plan = Plan(l_max, n_r, max_q, n_theta=n_theta, n_phi=n_phi, ft_type=ft_type, max_batch=3)
+    data = S.invariants_from_density(plan, S.six_sphere_density(plan))
+    m = O.MTIP(sd, data)
+    S.ProjectionSetup(plan.qs, data, l_max, sd['projections']['reciprocal']).apply_to(plan)
+    popt = sd['projections']['real']['projections']
+    plan.set_real(popt['apply'], S.initial_support(plan, popt['support']['initial_support']), popt['value_threshold']['threshold'],
+                  popt['limit_imag']['threshold'])
+    rho0 = np.stack([m.density_guess(np.random.default_rng(5 + i)) for i in range(3)])
+    plan.mtip_init(T(rho0))
+    m.results['errors'] = {'real': {'l2_projection_diff': []}, 'reciprocal': {}, 'main': []}
+    rho = m.ift(m.ft(rho0[1]))
+    for it, (name, code, stab, beta) in enumerate([('HIO', HIO, True, 0.5), ('HIO', HIO, False, 0.45), ('ER', ER, True, 0.0)]):
+        m.beta = beta
+        rh, rho = m.io_step(name, rho, stab)
+        plan.mtip_iterate(code, stab, [beta])
+        assert rel_l2(N(plan.mtip_grid('last_real'))[1], rho) < 1e-7, (it, name)
+        assert rel_l2(N(plan.mtip_grid('last_reciprocal'))[1], rh) < 1e-7, (it, name)
+    hist, _ = plan.mtip_errors()
+    assert np.allclose(N(hist)[1], m.results['errors']['real']['l2_projection_diff'], rtol=1e-7, atol=0)
+    m.sw.set_sigma(15.0)
+    m.sw.set_threshold(0.09)
+    mask = m.shrink_wrap(rho)
+    plan.mtip_shrinkwrap(15.0, 0.09, 6e-3)
+    assert (N(plan.mtip_grid('last_support'))[1] != mask).mean() < 1e-3
+    plan.close()
