@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) fft2_forward_kernel(SlotView grid, int sh
 template <int N1, int N2, bool MOD>
 // mod_rho_hat != nullptr: the transform output is I_proj and the kernel writes the modified-intensity density instead
 // (project_to_modified_intensity fused, fxs_Projections.py:899-909): mod_out[x] = rho_hat[x] sqrt(Re I_proj[x] / |rho_hat[x]|^2)
-__global__ void __launch_bounds__(256) fft2_inverse_kernel(const double2* __restrict__ a, double2* __restrict__ grid,
+__global__ void __launch_bounds__(256, MOD ? 3 : 2) fft2_inverse_kernel(const double2* __restrict__ a, double2* __restrict__ grid,
                                                            const double2* __restrict__ tw_g, int n_theta, int l_max, int herm,
                                                            const double2* __restrict__ mod_rho_hat, SlotView mod_out, int shells_per_run) {
     using C = Fft2Cfg<N1, N2>;
