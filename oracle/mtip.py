@@ -119,6 +119,10 @@ def radial_grids(ft_type, q_max, n_r, rc):
     elif ft_type in ('trapz', 'Zernike'):
         rs = np.linspace(0, r_max, n_r, endpoint=True)
         qs = np.linspace(0, q_max, n_r, endpoint=True)
+    elif ft_type == 'gauss':                       # radial_grid_gauss, ft_grid_pairs.py:293-300
+        xs = roots_legendre(n_r)[0]
+        rs = r_max / 2 * xs + r_max / 2
+        qs = q_max / 2 * xs + q_max / 2
     else:
         raise AssertionError(f'ft type {ft_type} not restated')
     return rs, qs
@@ -156,8 +160,13 @@ class SphericalIntegrator:
 # --------------------------------------------------------------------------
 
 def hankel_weights(l_max, n_r, rc, mode='midpoint'):
-    """w[l,p,k]; p summed. midpoint: :399-410, trapz: :322-333."""
+    """w[l,p,k]; p summed. midpoint: :399-410, trapz: :322-333, gauss: :477-490."""
     ls = np.arange(l_max + 1)
+    if mode == 'gauss':                            # Gauss-Legendre nodes on [0, 2] with their weights
+        xi, wg = roots_legendre(n_r)
+        ps = ks = xi + 1
+        j = spherical_jn(ls[:, None, None], (ks[None, :] * ps[:, None] * rc * n_r / 4)[None, :, :])
+        return ps[None, :, None] ** 2 * j * wg[None, :, None]
     if mode == 'midpoint':
         ps = np.arange(n_r) + 0.5
         ks = np.arange(n_r) + 0.5
@@ -171,13 +180,15 @@ def hankel_weights(l_max, n_r, rc, mode='midpoint'):
     return ps[None, :, None] ** 2 * j
 
 
-def assemble_weights(weights, r_max, rc):
-    """-> forward/inverse complex [p,k,l]; :349-375 / :426-452 (identical prefactors)."""
+def assemble_weights(weights, r_max, rc, mode='midpoint'):
+    """-> forward/inverse complex [p,k,l]; trapz :349-375 / midpoint :426-452 (identical prefactors), gauss :505-535
+    (step r_max/2 of the [-1,1] -> [0,r_max] map instead of r_max/N)."""
     n_r = weights.shape[-1]
     q_max = rc * n_r / r_max
     orders = np.arange(weights.shape[0])
-    fwd = (-1.j) ** (orders[None, None, :]) * (r_max / n_r) ** 3 * np.sqrt(2 / np.pi)
-    inv = (1.j) ** (orders[None, None, :]) * (q_max / n_r) ** 3 * np.sqrt(2 / np.pi)
+    div = 2 if mode == 'gauss' else n_r
+    fwd = (-1.j) ** (orders[None, None, :]) * (r_max / div) ** 3 * np.sqrt(2 / np.pi)
+    inv = (1.j) ** (orders[None, None, :]) * (q_max / div) ** 3 * np.sqrt(2 / np.pi)
     w = np.moveaxis(weights, 0, 2)
     return {'forward': w * fwd, 'inverse': w * inv}
 
@@ -213,7 +224,7 @@ def generate_spherical_ht_direct(w, l_max, mode='midpoint'):
 
 def generate_ft(sh, weights, r_max, rc, l_max, mode='midpoint', flavour='ml'):
     """projects/fxs/projectLibrary/fourier_transforms.py:39-86."""
-    w = assemble_weights(weights, r_max, rc)
+    w = assemble_weights(weights, r_max, rc, mode)
     if flavour == 'ml':
         hankel, ihankel = generate_spherical_ht(w, l_max, mode)
         ht, iht = sh.forward_m, sh.inverse_m

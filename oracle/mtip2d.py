@@ -11,7 +11,7 @@ Pinned against the UNMODIFIED reference by tests/golden/make_golden_2d.py -> tes
 (tests/test_oracle_golden_2d.py).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline legs may import this.
 """
 import numpy as np
-from scipy.special import jv
+from scipy.special import jv, roots_legendre
 
 from . import mtip as O
 
@@ -35,6 +35,10 @@ def cht_real_inverse(c, size):                   # :492-496
 
 def polar_hankel_weights(m_max, n_r, rc, mode='midpoint'):      # hankel_transforms.py:412-424 / :335-347
     ms = np.arange(m_max + 1)
+    if mode == 'gauss':                          # :492-503
+        xi, wg = roots_legendre(n_r)
+        ps = ks = xi + 1
+        return ps[None, :, None] * jv(ms[:, None, None], (ks[None, :] * ps[:, None] * rc * n_r / 4)[None]) * wg[None, :, None]
     if mode == 'midpoint':
         ps, ks = np.arange(n_r) + 0.5, np.arange(n_r) + 0.5
     elif mode == 'trapz':
@@ -44,13 +48,14 @@ def polar_hankel_weights(m_max, n_r, rc, mode='midpoint'):      # hankel_transfo
     return ps[None, :, None] * jv(ms[:, None, None], (ks[None, :] * ps[:, None] * rc / n_r)[None])
 
 
-def assemble_weights_2d(weights, r_max, rc):     # hankel_transforms.py:426-452 (dimensions == 2)
+def assemble_weights_2d(weights, r_max, rc, mode='midpoint'):     # hankel_transforms.py:426-452 (dimensions == 2), gauss :505-535
     n_r = weights.shape[-1]
     q_max = rc * n_r / r_max
     orders = np.arange(weights.shape[0])
     all_orders = np.concatenate((orders, -orders[:0:-1]))
-    fwd = (-1.j) ** (all_orders[None, None, :]) * (r_max / n_r) ** 2
-    inv = (1.j) ** (all_orders[None, None, :]) * (q_max / n_r) ** 2
+    div = 2 if mode == 'gauss' else n_r
+    fwd = (-1.j) ** (all_orders[None, None, :]) * (r_max / div) ** 2
+    inv = (1.j) ** (all_orders[None, None, :]) * (q_max / div) ** 2
     w = np.concatenate((weights, (-1.0) ** orders[:0:-1, None, None] * weights[:0:-1]), axis=0)
     w = np.moveaxis(w, 0, 2)
     return {'forward': w * fwd, 'inverse': w * inv}
@@ -63,7 +68,7 @@ def generate_polar_ht(w, mode='midpoint'):       # hankel_transforms.py:602-640 
 
 
 def generate_ft_2d(weights, r_max, rc, mode='midpoint'):        # fourier_transforms.py:53-85 with the 'm' transforms
-    hankel, ihankel = generate_polar_ht(assemble_weights_2d(weights, r_max, rc), mode)
+    hankel, ihankel = generate_polar_ht(assemble_weights_2d(weights, r_max, rc, mode), mode)
     return (lambda d: cht_complex_inverse(hankel(cht_complex_forward(d)))), \
            (lambda d: cht_complex_inverse(ihankel(cht_complex_forward(d))))
 

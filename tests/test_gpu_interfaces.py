@@ -69,7 +69,7 @@ def test_harmonic_transform_class():
     assert ht2.max_order == NT - 1
 
 
-@pytest.mark.parametrize('mode', ['midpoint', 'trapz'])
+@pytest.mark.parametrize('mode', ['midpoint', 'trapz', 'gauss'])
 def test_generate_ht_and_ft(mode):
     from xframe_b200.harmonic_transforms import HarmonicTransform
     from xframe_b200.hankel_transforms import generate_weightDict, generate_ht
@@ -80,7 +80,7 @@ def test_generate_ht_and_ft(mode):
     wd = generate_weightDict(L, NR, reciprocity_coefficient=rc, dimensions=3, mode=mode)
     assert np.array_equal(wd['weights'], O.hankel_weights(L, NR, rc, mode))
     zht, izht = generate_ht(wd['weights'], wd['posHarmOrders'], r_max, reciprocity_coefficient=rc, dimensions=3, use_gpu=True, mode=mode)
-    w = O.assemble_weights(wd['weights'], r_max, rc)
+    w = O.assemble_weights(wd['weights'], r_max, rc, mode)
     fwd, inv = O.generate_spherical_ht_direct(w, L, mode)
     c = _field(np.random.default_rng(4), (NR, (L + 1) ** 2))
     assert rel_l2(zht(c), fwd(c)) < 1e-12 and rel_l2(izht(c), inv(c)) < 1e-12

@@ -460,9 +460,10 @@ def test_results_do_not_depend_on_the_batch():
         p1.close()
 
 
-@pytest.mark.parametrize('l_max,n_r,n_theta,n_phi,ft_type', [(10, 33, 16, 32, 'midpoint'), (6, 20, 8, 16, 'trapz'), (21, 48, 24, 64, 'midpoint')])
+@pytest.mark.parametrize('l_max,n_r,n_theta,n_phi,ft_type', [(10, 33, 16, 32, 'midpoint'), (6, 20, 8, 16, 'trapz'), (21, 48, 24, 64, 'midpoint'),
+                                                              (8, 24, 16, 32, 'gauss')])
 def test_ragged_sizes_iterations_against_oracle(l_max, n_r, n_theta, n_phi, ft_type):
-    """Odd / small / non-power-of-two radial sizes and the trapz radial rule: HIO_ft_stab, shrink wrap and plain ER
+    """Odd / small / non-power-of-two radial sizes and the trapz / gauss radial rules: HIO_ft_stab, shrink wrap and plain ER
     iterations of a batch of 3 against the oracle (odd N_r takes the non-cp.async Hankel kernel, n_phi = 32 / 16 the generic
     Stockham FFT without the fused pointwise variants, n_theta = 24 the 8-row FFT tiles)."""
     from xframe_b200.plan import Plan, HIO, ER

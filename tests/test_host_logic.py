@@ -56,13 +56,13 @@ def test_legendre_tables_match_oracle():
         assert np.allclose(full[:, ::-1], sign * full, atol=1e-13)
 
 
-@pytest.mark.parametrize('mode', ['midpoint', 'trapz'])
+@pytest.mark.parametrize('mode', ['midpoint', 'trapz', 'gauss'])
 def test_hankel_and_grids_match_oracle(mode):
     assert np.array_equal(tables.hankel_weights(9, 12, 2.0, mode), O.hankel_weights(9, 12, 2.0, mode))
     a, b = tables.radial_grids(mode, 0.3, 12, 2.0), O.radial_grids(mode, 0.3, 12, 2.0)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
-    w = O.assemble_weights(O.hankel_weights(3, 12, 2.0, mode), a[0].max(), 2.0)
-    fs, iscale = tables.hankel_scales(a[0].max(), 12, 2.0)
+    w = O.assemble_weights(O.hankel_weights(3, 12, 2.0, mode), a[0].max(), 2.0, mode)
+    fs, iscale = tables.hankel_scales(a[0].max(), 12, 2.0, mode)
     assert np.allclose(w['forward'][..., 1], (-1j) * fs * np.moveaxis(O.hankel_weights(3, 12, 2.0, mode), 0, 2)[..., 1])
     assert np.allclose(w['inverse'][..., 2], (1j) ** 2 * iscale * np.moveaxis(O.hankel_weights(3, 12, 2.0, mode), 0, 2)[..., 2])
 

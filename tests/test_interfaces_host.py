@@ -36,11 +36,11 @@ def test_angular_size_helpers():
 
 def test_weight_dict_and_assembly():
     from xframe_b200.hankel_transforms import generate_weightDict, assemble_weights
-    for mode in ('midpoint', 'trapz'):
+    for mode in ('midpoint', 'trapz', 'gauss'):
         wd = generate_weightDict(7, 12, reciprocity_coefficient=2.0, dimensions=3, mode=mode)
         assert wd['mode'] == mode and np.array_equal(wd['posHarmOrders'], np.arange(8))
         assert np.array_equal(wd['weights'], O.hankel_weights(7, 12, 2.0, mode))
-        a, b = assemble_weights(wd['weights'], wd['posHarmOrders'], 33.0, 2.0, 3, mode), O.assemble_weights(wd['weights'], 33.0, 2.0)
+        a, b = assemble_weights(wd['weights'], wd['posHarmOrders'], 33.0, 2.0, 3, mode), O.assemble_weights(wd['weights'], 33.0, 2.0, mode)
         assert np.allclose(a['forward'], b['forward'], rtol=1e-15) and np.allclose(a['inverse'], b['inverse'], rtol=1e-15)
 
 

@@ -111,3 +111,45 @@ def test_full_loop(tag):
     assert (res['last_support_mask'] != g['loop_last_support_mask']).mean() < 1e-3
     assert (res['support_mask'] != g['loop_support_mask']).mean() < 1e-3
     assert rel_l2(res['last_deg2_invariant'], g['loop_last_deg2']) < 1e-7
+
+
+# ----------------------------------------------------------------------------------------------
+# radial-transform modes (midpoint, trapz, gauss; 3-D and 2-D) against the reference's own weight workers, assembly and
+# CPU Hankel transforms -- tests/golden/make_golden_hankel_modes.py
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('mode', ['midpoint', 'trapz', 'gauss'])
+def test_hankel_modes_against_reference(mode):
+    import os
+    from oracle import mtip2d as O2
+    from xframe_b200 import tables
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_hankel_modes.npz'))
+    l_max, n_r, rc, q_max = int(g['l_max']), int(g['n_r']), float(g['rc']), float(g['q_max'])
+    rs, qs = O.radial_grids(mode, q_max, n_r, rc)
+    assert np.allclose(rs, g[f'{mode}_rs'], rtol=1e-15, atol=0) and np.allclose(qs, g[f'{mode}_qs'], rtol=1e-15, atol=0)
+    r_max = rs.max()
+    # 3-D
+    w = O.hankel_weights(l_max, n_r, rc, mode)
+    assert rel_l2(w, g[f'{mode}_3_weights']) < 1e-15
+    aw = O.assemble_weights(w, r_max, rc, mode)
+    assert rel_l2(aw['forward'], g[f'{mode}_3_forward']) < 1e-15 and rel_l2(aw['inverse'], g[f'{mode}_3_inverse']) < 1e-15
+    zht, izht = O.generate_spherical_ht(aw, l_max, mode)
+    cm = [g[f'{mode}_3_in_{i}'] for i in range(2 * l_max + 1)]
+    f, b = zht(cm), izht(cm)
+    for i in range(2 * l_max + 1):
+        assert rel_l2(f[i], g[f'{mode}_3_zht_{i}']) < 1e-14 and rel_l2(b[i], g[f'{mode}_3_izht_{i}']) < 1e-14
+    # the device-side split (real weights x scalar prefactor, phase in the kernel epilogue) reproduces the assembled arrays
+    fs, iscale = tables.hankel_scales(r_max, n_r, rc, mode)
+    tw = np.moveaxis(tables.hankel_weights(l_max, n_r, rc, mode), 0, 2)
+    ls = np.arange(l_max + 1)
+    assert rel_l2(tw * fs * (-1j) ** ls, g[f'{mode}_3_forward']) < 1e-15 and rel_l2(tw * iscale * (1j) ** ls, g[f'{mode}_3_inverse']) < 1e-15
+    # 2-D
+    w2 = O2.polar_hankel_weights(l_max, n_r, rc, mode)
+    assert rel_l2(w2, g[f'{mode}_2_weights']) < 1e-15
+    aw2 = O2.assemble_weights_2d(w2, r_max, rc, mode)
+    assert rel_l2(aw2['forward'], g[f'{mode}_2_forward']) < 1e-15 and rel_l2(aw2['inverse'], g[f'{mode}_2_inverse']) < 1e-15
+    z2, iz2 = O2.generate_polar_ht(aw2, mode)
+    assert rel_l2(z2(g[f'{mode}_2_in']), g[f'{mode}_2_zht']) < 1e-14 and rel_l2(iz2(g[f'{mode}_2_in']), g[f'{mode}_2_izht']) < 1e-14
+    fs2, is2 = tables.polar_hankel_scales(r_max, n_r, rc, mode)
+    m_all = np.concatenate((ls, -ls[:0:-1]))
+    tw2 = np.moveaxis(tables.polar_hankel_device_weights(tables.polar_hankel_weights(l_max, n_r, rc, mode)), 0, 2)
+    assert rel_l2(tw2 * fs2 * (-1j) ** m_all, g[f'{mode}_2_forward']) < 1e-15 and rel_l2(tw2 * is2 * (1j) ** m_all, g[f'{mode}_2_inverse']) < 1e-15

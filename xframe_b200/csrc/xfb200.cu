@@ -979,7 +979,11 @@ int xfb_mtip_step_host(xfb_plan* p, int32_t method, int32_t ft_stab, double beta
     const int nb = p->n_batch;
     if (nb < 1) XFB_FAIL("xfb_mtip_init has not been called");
     const int eb = ew_blocks(p->G);
-    const bool pipelined = (!ft_stab || p->fused_ft_stab) && nb > p->host_chunk;   // W2 is free as H2D staging then
+    // chunk size: host_chunk runs for large batches, nb/8 (>= 4: below that the kernels are latency bound) for small
+    // ones, so that a shard of 16 or 32 runs (the per-GPU share of 128 runs on 8 / 4 GPUs) is pipelined as well
+    int chunk = p->host_chunk;
+    while (chunk > 4 && chunk * 8 > nb) chunk /= 2;
+    const bool pipelined = (!ft_stab || p->fused_ft_stab) && nb > chunk;   // W2 is free as H2D staging then
     if (!p->s_in) {
         XFB_CUDA(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
         XFB_CUDA(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
@@ -991,7 +995,7 @@ int xfb_mtip_step_host(xfb_plan* p, int32_t method, int32_t ft_stab, double beta
     std::vector<int> sizes;
     if (!pipelined) sizes.push_back(nb);
     else {
-        const int cs = p->host_chunk;
+        const int cs = chunk;
         std::vector<int> head, tail;
         int left = nb;
         for (int f = 4; f >= 2 && left > 4 * cs; f /= 2) {

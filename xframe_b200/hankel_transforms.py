@@ -24,8 +24,8 @@ def _q_max_from_r_max(r_max, n_r, rc):
 
 def generate_weightDict(max_order, n_radial_points, reciprocity_coefficient=np.pi, dimensions=3, n_cpus=False, mode=ht_modes[0], **kwargs):
     """{'weights': [orders, summed radial index, new radial index], 'posHarmOrders', 'mode'} (:22-35, :377-397, :299-320)."""
-    if mode not in ('trapz', 'midpoint'):
-        raise XfbError(f"Hankel weights mode '{mode}' is not implemented by xframe_b200 (trapz, midpoint)")
+    if mode not in ('trapz', 'midpoint', 'gauss'):
+        raise XfbError(f"Hankel weights mode '{mode}' is not implemented by xframe_b200 (trapz, midpoint, gauss)")
     if dimensions == 3:
         w = tables.hankel_weights(int(max_order), int(n_radial_points), float(reciprocity_coefficient), mode)
     elif dimensions == 2:
@@ -37,19 +37,20 @@ def generate_weightDict(max_order, n_radial_points, reciprocity_coefficient=np.p
 
 def assemble_weights(weights, pos_orders, r_max, reciprocity_coefficient=np.pi, dimensions=3, mode=ht_modes[0]):
     """Complex forward / inverse weight arrays [p, k, order] exactly as the reference assembles them
-    (assemble_weights_trapz :349-375, assemble_weights_mid :426-452)."""
+    (assemble_weights_trapz :349-375, assemble_weights_mid :426-452, assemble_weights_gauss :505-535)."""
     weights = np.asarray(weights)
     n_r = weights.shape[-1]
     orders = np.arange(weights.shape[0]) if mode == ht_modes[0] else np.asarray(pos_orders)
     q_max = _q_max_from_r_max(r_max, n_r, reciprocity_coefficient)
+    div = 2 if mode == 'gauss' else n_r             # gauss: the [-1,1] -> [0,r_max] map instead of the uniform step
     if dimensions == 2:
         all_orders = np.concatenate((orders, -orders[:0:-1]))
-        fpre = (-1.j) ** (all_orders[None, None, :]) * (r_max / n_r) ** 2
-        ipre = (1.j) ** (all_orders[None, None, :]) * (q_max / n_r) ** 2
+        fpre = (-1.j) ** (all_orders[None, None, :]) * (r_max / div) ** 2
+        ipre = (1.j) ** (all_orders[None, None, :]) * (q_max / div) ** 2
         weights = np.concatenate((weights, (-1.0) ** orders[:0:-1, None, None] * weights[:0:-1]), axis=0)
     elif dimensions == 3:
-        fpre = (-1.j) ** (orders[None, None, :]) * (r_max / n_r) ** 3 * np.sqrt(2 / np.pi)
-        ipre = (1.j) ** (orders[None, None, :]) * (q_max / n_r) ** 3 * np.sqrt(2 / np.pi)
+        fpre = (-1.j) ** (orders[None, None, :]) * (r_max / div) ** 3 * np.sqrt(2 / np.pi)
+        ipre = (1.j) ** (orders[None, None, :]) * (q_max / div) ** 3 * np.sqrt(2 / np.pi)
     else:
         raise XfbError(f"dimensions={dimensions} not supported")
     w = np.moveaxis(weights, 0, 2)
@@ -72,11 +73,9 @@ class _HankelPair:
         self.device, self.max_batch, self._plan = device, int(max_batch), plan
 
     def scales(self):
-        q_max = _q_max_from_r_max(self.r_max, self.n_r, self.rc)
         if self.dim == 3:
-            c = np.sqrt(2 / np.pi)
-            return (self.r_max / self.n_r) ** 3 * c, (q_max / self.n_r) ** 3 * c
-        return (self.r_max / self.n_r) ** 2, (q_max / self.n_r) ** 2
+            return tables.hankel_scales(self.r_max, self.n_r, self.rc, self.mode)
+        return tables.polar_hankel_scales(self.r_max, self.n_r, self.rc, self.mode)
 
     def plan(self):
         if self._plan is None:
@@ -115,8 +114,8 @@ def generate_ht(weights, used_orders, r_max, reciprocity_coefficient=np.pi, dime
     GPU flavours (hankel_transforms.py:540-559,660-870).  `use_gpu=False` is refused: there is no CPU path here."""
     if not use_gpu:
         raise XfbError("xframe_b200.generate_ht: use_gpu=False requested, but this package has no CPU path")
-    if mode not in ('trapz', 'midpoint'):
-        raise XfbError(f"Hankel transform mode '{mode}' is not implemented by xframe_b200 (trapz, midpoint)")
+    if mode not in ('trapz', 'midpoint', 'gauss'):
+        raise XfbError(f"Hankel transform mode '{mode}' is not implemented by xframe_b200 (trapz, midpoint, gauss)")
     pair = _HankelPair(weights, used_orders, r_max, reciprocity_coefficient, dimensions, mode, device, max_batch, plan)
 
     def zht(harmonic_coeff):

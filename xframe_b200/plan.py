@@ -67,7 +67,7 @@ class Plan:
                     or self.hankel_w.shape[1] not in (self.n_r, self.n_r - 1):
                 raise ValueError(f"hankel_weights shape {self.hankel_w.shape} is not [L+1, N_r or N_r-1, N_r]")
         if hankel_scales is None:
-            fs, iscale = tables.hankel_scales(float(np.max(self.rs)), self.n_r, self.rc)
+            fs, iscale = tables.hankel_scales(float(np.max(self.rs)), self.n_r, self.rc, ft_type)
         else:
             fs, iscale = (float(v) for v in hankel_scales)
         self.int_weight = tables.integration_weights(self.rs, self.n_theta)
@@ -99,7 +99,7 @@ class Plan:
         if w.ndim != 3 or w.shape[0] != self.l_max + 1 or w.shape[2] != self.n_r or w.shape[1] not in (self.n_r, self.n_r - 1):
             raise ValueError(f"hankel_weights shape {w.shape} is not [M+1, N_r or N_r-1, N_r]")
         self.hankel_w = w
-        fs, iscale = tables.polar_hankel_scales(float(np.max(self.rs)), self.n_r, self.rc) if hankel_scales is None \
+        fs, iscale = tables.polar_hankel_scales(float(np.max(self.rs)), self.n_r, self.rc, ft_type) if hankel_scales is None \
             else (float(v) for v in hankel_scales)
         self.int_weight = tables.polar_integration_weights(self.rs, self.phis)
         d = _lib.PlanDesc()

@@ -95,14 +95,24 @@ def radial_grids(ft_type, q_max, n_r, rc):
     elif ft_type in ('trapz', 'Zernike'):
         rs = np.linspace(0, r_max, n_r, endpoint=True)
         qs = np.linspace(0, q_max, n_r, endpoint=True)
+    elif ft_type == 'gauss':                         # Gauss-Legendre nodes mapped to [0, r_max] (ft_grid_pairs.py:293-300)
+        xs = roots_legendre(n_r)[0]
+        rs = r_max / 2 * xs + r_max / 2
+        qs = q_max / 2 * xs + q_max / 2
     else:
-        raise ValueError(f"fourier_transform.type '{ft_type}' is not supported by xframe_b200 (midpoint, trapz)")
+        raise ValueError(f"fourier_transform.type '{ft_type}' is not supported by xframe_b200 (midpoint, trapz, gauss)")
     return rs, qs
 
 
 def hankel_weights(l_max, n_r, rc, mode='midpoint'):
-    """w[l,p,k] = p^2 j_l(p k rc / N); p is summed. hankel_transforms.py:399-410 (midpoint), :322-333 (trapz)."""
+    """w[l,p,k] = p^2 j_l(p k rc / N); p is summed. hankel_transforms.py:399-410 (midpoint), :322-333 (trapz);
+    gauss (:477-490): p, k = Gauss-Legendre nodes on [0, 2], w = p^2 j_l(p k rc N / 4) w_gauss(p)."""
     ls = np.arange(l_max + 1)
+    if mode == 'gauss':
+        xi, wg = roots_legendre(n_r)
+        ps = ks = xi + 1
+        arg = ks[None, :] * ps[:, None] * rc * n_r / 4
+        return np.ascontiguousarray(ps[None, :, None] ** 2 * spherical_jn(ls[:, None, None], arg[None, :, :]) * wg[None, :, None])
     if mode == 'midpoint':
         ps = np.arange(n_r) + 0.5
         ks = np.arange(n_r) + 0.5
@@ -110,17 +120,19 @@ def hankel_weights(l_max, n_r, rc, mode='midpoint'):
         ps = np.arange(1, n_r)
         ks = np.arange(n_r)
     else:
-        raise ValueError(f"hankel mode '{mode}' is not supported by xframe_b200 (midpoint, trapz)")
+        raise ValueError(f"hankel mode '{mode}' is not supported by xframe_b200 (midpoint, trapz, gauss)")
     arg = ks[None, :] * ps[:, None] * rc / n_r
     return np.ascontiguousarray(ps[None, :, None] ** 2 * spherical_jn(ls[:, None, None], arg[None, :, :]))
 
 
-def hankel_scales(r_max_grid, n_r, rc):
+def hankel_scales(r_max_grid, n_r, rc, mode='midpoint'):
     """(r_max/N)^3 sqrt(2/pi) and (q_max/N)^3 sqrt(2/pi) with q_max = rc N / r_max; r_max is the LARGEST GRID
-    POINT as the reference passes it (reconstruct.py:329, hankel_transforms.py:432-445)."""
+    POINT as the reference passes it (reconstruct.py:329, hankel_transforms.py:432-445).  gauss: r_max/2 and q_max/2
+    instead of the uniform steps (:523-531)."""
     q_max = rc * n_r / r_max_grid
     c = np.sqrt(2 / np.pi)
-    return (r_max_grid / n_r) ** 3 * c, (q_max / n_r) ** 3 * c
+    div = 2 if mode == 'gauss' else n_r
+    return (r_max_grid / div) ** 3 * c, (q_max / div) ** 3 * c
 
 
 def integration_weights(rs, n_theta):
@@ -139,6 +151,11 @@ def integration_weights(rs, n_theta):
 def polar_hankel_weights(m_max, n_r, rc, mode='midpoint'):
     """w[m,p,k] = p J_m(p k rc / N), m = 0..M; p is summed.  hankel_transforms.py:412-424 (midpoint), :335-347 (trapz)."""
     ms = np.arange(m_max + 1)
+    if mode == 'gauss':                              # :492-503
+        xi, wg = roots_legendre(n_r)
+        ps = ks = xi + 1
+        arg = ks[None, :] * ps[:, None] * rc * n_r / 4
+        return np.ascontiguousarray(ps[None, :, None] * jv(ms[:, None, None], arg[None, :, :]) * wg[None, :, None])
     if mode == 'midpoint':
         ps = np.arange(n_r) + 0.5
         ks = np.arange(n_r) + 0.5
@@ -146,7 +163,7 @@ def polar_hankel_weights(m_max, n_r, rc, mode='midpoint'):
         ps = np.arange(1, n_r)
         ks = np.arange(n_r)
     else:
-        raise ValueError(f"hankel mode '{mode}' is not supported by xframe_b200 (midpoint, trapz)")
+        raise ValueError(f"hankel mode '{mode}' is not supported by xframe_b200 (midpoint, trapz, gauss)")
     arg = ks[None, :] * ps[:, None] * rc / n_r
     return np.ascontiguousarray(ps[None, :, None] * jv(ms[:, None, None], arg[None, :, :]))
 
@@ -159,10 +176,11 @@ def polar_hankel_device_weights(w):
     return np.ascontiguousarray(np.concatenate((w, neg), axis=0))
 
 
-def polar_hankel_scales(r_max_grid, n_r, rc):
-    """(r_max/N)^2 and (q_max/N)^2, q_max = rc N / r_max (hankel_transforms.py:433-439)."""
+def polar_hankel_scales(r_max_grid, n_r, rc, mode='midpoint'):
+    """(r_max/N)^2 and (q_max/N)^2, q_max = rc N / r_max (hankel_transforms.py:433-439); gauss: r_max/2, q_max/2 (:517-519)."""
     q_max = rc * n_r / r_max_grid
-    return (r_max_grid / n_r) ** 2, (q_max / n_r) ** 2
+    div = 2 if mode == 'gauss' else n_r
+    return (r_max_grid / div) ** 2, (q_max / div) ** 2
 
 
 def polar_integration_weights(rs, phis):
