@@ -334,6 +334,19 @@ def run_ours(args):
                               **({'GBps': ab[k] * v['launches'] / (v['ms'] * 1e-3) / 1e9} if k in ab else {}),
                               **({'TFLOPs_fp64': hankel_flops(nb) * v['launches'] / (v['ms'] * 1e-3) / 1e12} if k == 'hankel' else {})}
                           for k, v in groups.items()}
+        for k, gk in roof['groups'].items():
+            if 'TFLOPs_fp64' in gk:
+                gk['frac_of_fp64_tensor_nominal_40TF'] = gk['TFLOPs_fp64'] / 40.0
+            elif 'GBps' in gk and k != 'procrustes_jacobi':
+                gk['frac_of_hbm_peak'] = gk['GBps'] / peak
+        if DIMS == 3:
+            # whole iteration against the HBM roofline (every logical operator reads its inputs once and writes its
+            # outputs once, fused ft_stab sketch): 19.5 G s + 18 C s + G bytes per run and iteration, s = 16 B
+            Gp, Cp = N_R * N_THETA * N_PHI, N_R * (L_MAX + 1) ** 2
+            it_bytes = nb * (19.5 * Gp * 16 + 18 * Cp * 16 + Gp)
+            floor_ms = it_bytes / (peak * 1e9) * 1e3
+            roof['iteration'] = {'algorithmic_bytes_per_step': it_bytes, 'hbm_floor_ms': floor_ms, 'measured_ms': ms_max / K,
+                                 'frac': floor_ms / (ms_max / K)}
         cb = None
         if world == 1 and not args.no_cpu:
             # fresh interpreter: BLAS thread pins must be in the environment before numpy loads, and no CUDA context is forked

@@ -331,14 +331,17 @@ __device__ __forceinline__ void jacobi_sweep_blocked(double* Gs, int ldg, double
 
 // runtime column stride -> compile-time register tile size.  The accumulator columns have the same length as the G
 // columns (the accumulator starts as the identity or as Q2, see the kernel); MAXV2 bounds the instantiations.
+// `len` <= ld is the number of leading column entries that can be non-zero (the rest is zero padding): the register tiles
+// cover ceil(len / 16) double2 per lane only.
 template <int MAXV2>
-__device__ __forceinline__ void jacobi_sweep_dispatch(double* Gs, double* Wb, int ld, bool w_compact, const int* list, int nact, double thr,
-                                                      double tol, double2* rotbuf, int* s_rot) {
+__device__ __forceinline__ void jacobi_sweep_dispatch(double* Gs, double* Wb, int ld, int len, bool w_compact, const int* list, int nact,
+                                                      double thr, double tol, double2* rotbuf, int* s_rot) {
     if constexpr (MAXV2 >= 16) {
-        if (ld > 128) { jacobi_sweep_blocked<16, 16>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot); return; }
+        if (len > 128) { jacobi_sweep_blocked<16, 16>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot); return; }
     }
-    if (ld <= 64) jacobi_sweep_blocked<4, 4>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
-    else if (ld <= 96) jacobi_sweep_blocked<6, 6>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
+    if (len <= 64) jacobi_sweep_blocked<4, 4>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
+    else if (len <= 80) jacobi_sweep_blocked<5, 5>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
+    else if (len <= 96) jacobi_sweep_blocked<6, 6>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
     else jacobi_sweep_blocked<8, 8>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
 }
 
@@ -398,9 +401,11 @@ __device__ __forceinline__ void mgs2_qr(double* A, int lda, int r, double* Rt, i
     }
     __syncthreads();
 }
-__device__ __forceinline__ void mgs2_qr_dispatch(double* A, int lda, int r, double* Rt, int ldr) {
-    if (lda <= 64) mgs2_qr<4>(A, lda, r, Rt, ldr);
-    else if (lda <= 96) mgs2_qr<6>(A, lda, r, Rt, ldr);
+__device__ __forceinline__ void mgs2_qr_dispatch(double* A, int lda, int len, int r, double* Rt, int ldr) {
+    if (len <= 64) mgs2_qr<4>(A, lda, r, Rt, ldr);
+    else if (len <= 80) mgs2_qr<5>(A, lda, r, Rt, ldr);
+    else if (len <= 96) mgs2_qr<6>(A, lda, r, Rt, ldr);
+    else if (len <= 112) mgs2_qr<7>(A, lda, r, Rt, ldr);
     else mgs2_qr<8>(A, lda, r, Rt, ldr);
 }
 
@@ -456,7 +461,7 @@ __device__ __forceinline__ void jacobi_active_list(const double* Gs, int ldg, in
 // rotations on columns of length r instead of 2l+1 (numpy model: tests/jacobi_model.py:qr_polar).
 // Shared memory: A = Q1 [r][ldg], B [r][ldl], C [r][ldl].
 template <int MAXV2>
-__device__ __forceinline__ int jacobi_qr_problem(const double* __restrict__ g, int n, int ldg, double* __restrict__ gn, double* __restrict__ pp,
+__device__ __forceinline__ int jacobi_qr_problem(const double* __restrict__ g, int n, int ldg, int len_g, double* __restrict__ gn, double* __restrict__ pp,
                                                  double* nrm2, int* list, int r, int ldl, double* region, double2* rotbuf, double sv_cutoff,
                                                  double tol, int max_sweeps, int* s_nact, double* s_thr, int* s_rot,
                                                  double* __restrict__ sigma) {
@@ -475,19 +480,19 @@ __device__ __forceinline__ int jacobi_qr_problem(const double* __restrict__ g, i
         reinterpret_cast<double2*>(pp)[i] = make_double2(0.0, 0.0);
     }
     __syncthreads();
-    mgs2_qr_dispatch(A, ldg, r, B, ldl);                  // A = Q1, B = columns of R1^T
+    mgs2_qr_dispatch(A, ldg, len_g, r, B, ldl);           // A = Q1, B = columns of R1^T
     for (int i = tid; i < r * (ldg / 2); i += nthr) {     // Q1 is final: rows list[a] of gn
         const int a = i / (ldg / 2), e = i - a * (ldg / 2);
         reinterpret_cast<double2*>(gn + (size_t)list[a] * ldg)[e] = reinterpret_cast<const double2*>(A)[i];
     }
-    mgs2_qr_dispatch(B, ldl, r, C, ldl);                  // B = Q2, C = columns of R2^T = L
+    mgs2_qr_dispatch(B, ldl, r, r, C, ldl);               // B = Q2, C = columns of R2^T = L
     int sweep = 0;
     for (; sweep < max_sweeps; ++sweep) {
         jacobi_active_list(C, ldl, r, nrm2, list2, sv_cutoff, s_nact, s_thr, s_rot);
         const int nact = *s_nact;
         const double thr = *s_thr;
         if (nact < 2) break;
-        jacobi_sweep_dispatch<MAXV2>(C, B, ldl, false, list2, nact, thr, tol, rotbuf, s_rot);
+        jacobi_sweep_dispatch<MAXV2>(C, B, ldl, r, false, list2, nact, thr, tol, rotbuf, s_rot);
         __syncthreads();
         const int rotated = *s_rot;
         __syncthreads();
@@ -572,7 +577,7 @@ __global__ void __launch_bounds__(THREADS, 1) procrustes_jacobi_kernel(const dou
             const int ldl = r <= 64 ? 64 : (r <= 96 ? 96 : 128);
             if (r >= 2 && var0 + r * ldg + 2 * r * ldl <= smem_doubles) {
                 __syncthreads();
-                const int sw = jacobi_qr_problem<MAXV2>(g, n, ldg, gn, pp, nrm2, list, r, ldl, smem_j + var0, rotbuf, sv_cutoff, tol, max_sweeps,
+                const int sw = jacobi_qr_problem<MAXV2>(g, n, ldg, o.n_c, gn, pp, nrm2, list, r, ldl, smem_j + var0, rotbuf, sv_cutoff, tol, max_sweeps,
                                                         &s_nact, &s_thr, &s_rot, sg);
                 if (tid == 0 && sweeps_out) sweeps_out[b * n_orders + oi] = sw;
                 continue;
@@ -608,7 +613,7 @@ __global__ void __launch_bounds__(THREADS, 1) procrustes_jacobi_kernel(const dou
                 }
                 __syncthreads();
             }
-            jacobi_sweep_dispatch<MAXV2>(Gs, w_smem ? Ws : pp, ldg, w_smem, list, nact, thr, tol, rotbuf, &s_rot);
+            jacobi_sweep_dispatch<MAXV2>(Gs, w_smem ? Ws : pp, ldg, ldg, w_smem, list, nact, thr, tol, rotbuf, &s_rot);
             if (w_smem) {
                 for (int i = tid; i < nact * (ldg / 2); i += THREADS) {
                     const int a = i / (ldg / 2), e = i - a * (ldg / 2);
