@@ -339,7 +339,9 @@ __device__ __forceinline__ void jacobi_sweep_dispatch(double* Gs, double* Wb, in
     if constexpr (MAXV2 >= 16) {
         if (len > 128) { jacobi_sweep_blocked<16, 16>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot); return; }
     }
-    if (len <= 64) jacobi_sweep_blocked<4, 4>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
+    if (len <= 32) jacobi_sweep_blocked<2, 2>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
+    else if (len <= 48) jacobi_sweep_blocked<3, 3>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
+    else if (len <= 64) jacobi_sweep_blocked<4, 4>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
     else if (len <= 80) jacobi_sweep_blocked<5, 5>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
     else if (len <= 96) jacobi_sweep_blocked<6, 6>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
     else jacobi_sweep_blocked<8, 8>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
@@ -359,7 +361,7 @@ __device__ __forceinline__ void mgs2_qr(double* A, int lda, int r, double* Rt, i
     if (warp == 0) {                                       // normalise column 0 (group 0 does the work, all lanes shuffle)
         double2 x[NV];
         jacobi_load_col<NV>(x, A, 0, sub, grp == 0);
-        const double nrm = sqrt(jacobi_col_norm2<NV>(x)), inv = (nrm > 0.0) ? 1.0 / nrm : 0.0;
+        const double n2 = jacobi_col_norm2<NV>(x), inv = (n2 > 0.0) ? rsqrt(n2) : 0.0, nrm = n2 * inv;
 #pragma unroll
         for (int t = 0; t < NV; ++t) { x[t].x *= inv; x[t].y *= inv; }
         jacobi_store_col<NV>(x, A, 0, sub, grp == 0);
@@ -389,7 +391,7 @@ __device__ __forceinline__ void mgs2_qr(double* A, int lda, int r, double* Rt, i
             if (k0 == j + 1) {                             // warp-uniform: the first trailing column becomes q_{j+1} right away
                 const double n2 = jacobi_col_norm2<NV>(a);
                 if (grp == 0) {
-                    const double nrm = sqrt(n2), inv = (nrm > 0.0) ? 1.0 / nrm : 0.0;
+                    const double inv = (n2 > 0.0) ? rsqrt(n2) : 0.0, nrm = n2 * inv;     // one MUFU + Newton instead of sqrt and a division
 #pragma unroll
                     for (int t = 0; t < NV; ++t) { a[t].x *= inv; a[t].y *= inv; }
                     if (sub == 0) Rt[(size_t)(j + 1) * ldr + j + 1] = nrm;
@@ -402,7 +404,9 @@ __device__ __forceinline__ void mgs2_qr(double* A, int lda, int r, double* Rt, i
     __syncthreads();
 }
 __device__ __forceinline__ void mgs2_qr_dispatch(double* A, int lda, int len, int r, double* Rt, int ldr) {
-    if (len <= 64) mgs2_qr<4>(A, lda, r, Rt, ldr);
+    if (len <= 32) mgs2_qr<2>(A, lda, r, Rt, ldr);
+    else if (len <= 48) mgs2_qr<3>(A, lda, r, Rt, ldr);
+    else if (len <= 64) mgs2_qr<4>(A, lda, r, Rt, ldr);
     else if (len <= 80) mgs2_qr<5>(A, lda, r, Rt, ldr);
     else if (len <= 96) mgs2_qr<6>(A, lda, r, Rt, ldr);
     else if (len <= 112) mgs2_qr<7>(A, lda, r, Rt, ldr);
