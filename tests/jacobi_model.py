@@ -70,19 +70,40 @@ def jacobi_project(V, qs, Il, eps=1e-15, tol=1e-15, max_sweeps=40):
     return to_cplx(P @ Gn.T), sweeps
 
 
-def mgs2(A):
-    """Column modified Gram-Schmidt with re-orthogonalisation (csrc/procrustes.cuh:mgs2_qr): Q, R."""
+def mgs2(A, selective=True):
+    """Column modified Gram-Schmidt with re-orthogonalisation (csrc/procrustes.cuh:mgs2_qr): Q, R.
+    selective: the second projection pass runs only for groups of 4 columns (one warp) in which the first pass removed more
+    than half of a column's squared norm, or whose downdated cached norm fell below 1e-6 of the last fresh value -- the
+    device rule; selective=False is the always-twice variant."""
     A = A.copy()
     m, r = A.shape
     R, Q = np.zeros((r, r)), np.zeros((m, r))
+    n2 = (A * A).sum(0)
+    nref = n2.copy()
     for j in range(r):
         nrm = np.sqrt(A[:, j] @ A[:, j])
         q = A[:, j] / nrm if nrm > 0 else np.zeros(m)
         Q[:, j], R[j, j] = q, nrm
-        for _ in range(2):
-            c = q @ A[:, j + 1:]
-            A[:, j + 1:] -= np.outer(q, c)
-            R[j, j + 1:] += c
+        if j + 1 == r:
+            break
+        t = slice(j + 1, r)
+        c = q @ A[:, t]
+        A[:, t] -= np.outer(q, c)
+        R[j, t] += c
+        n2n = n2[t] - c * c
+        need = (c * c > 0.5 * n2[t]) | (n2n < 1e-6 * nref[t]) if selective else np.ones(r - j - 1, bool)
+        for k0 in range(0, r - j - 1, 4):                  # warp granularity
+            if need[k0:k0 + 4].any():
+                need[k0:k0 + 4] = True
+        idx = np.nonzero(need)[0] + j + 1
+        if len(idx):
+            c2 = q @ A[:, idx]
+            A[:, idx] -= np.outer(q, c2)
+            R[j, idx] += c2
+        n2[t] = n2n
+        fresh = np.union1d(idx, np.arange(j + 1, min(r, j + 5)))
+        n2[fresh] = (A[:, fresh] * A[:, fresh]).sum(0)
+        nref[fresh] = n2[fresh]
     return Q, R
 
 

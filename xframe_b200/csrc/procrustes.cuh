@@ -347,17 +347,27 @@ __device__ __forceinline__ void jacobi_sweep_dispatch(double* Gs, double* Wb, in
     else jacobi_sweep_blocked<8, 8>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
 }
 
+__device__ __forceinline__ void jacobi_col_norms(const double* Gs, int ldg, int n, double* nrm2);
+
 // QR factorisation by modified Gram-Schmidt with re-orthogonalisation ("twice is enough"), whole CTA.
 //   A [r][lda]: r columns (zero padded), overwritten by the orthonormal Q (a column that vanishes becomes 0);
 //   Rt [r][ldr]: Rt[j][k] = R[j][k] (k >= j), i.e. column j of R^T -- the column storage of the NEXT factorisation step.
-// Step j: q_j is final; every later column k gets a_k -= (q_j.a_k) q_j twice (one 8-lane group per column, both passes on
-// registers); the group that owns column j+1 normalises it in the same step, so there is one barrier per step.
+// Step j: q_j is final; every later column k gets a_k -= (q_j.a_k) q_j (one 8-lane group per column, on registers); the
+// group that owns column j+1 normalises it in the same step, so there is one barrier per step.
+// Selective re-orthogonalisation (Daniel-Gragg-Kaufman-Stewart criterion per projection): the projection is repeated only
+// where the first pass removed more than half of the column's squared norm.  The squared norms are cached in n2c [r]
+// and downdated (|a - c q|^2 = |a|^2 - c^2); nref [r] keeps the high word of the last freshly computed value, and a column
+// whose downdated norm fell below 1e-6 of it is recomputed (the downdate has lost its digits by then).  On the fxs
+// problems 1 - 20 % of the projections take the second pass; the factors agree with the always-twice variant to 1e-16
+// (tests/jacobi_model.py:mgs2).
 template <int NV>
-__device__ __forceinline__ void mgs2_qr(double* A, int lda, int r, double* Rt, int ldr) {
+__device__ __forceinline__ void mgs2_qr(double* A, int lda, int r, double* Rt, int ldr, double* n2c, int* nref) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
     const int grp = lane >> 3, sub = lane & (JG - 1);
     for (int i = tid; i < r * ldr; i += blockDim.x) Rt[i] = 0.0;
+    jacobi_col_norms(A, lda, r, n2c);
     __syncthreads();
+    for (int i = tid; i < r; i += blockDim.x) nref[i] = __double2hiint(n2c[i]);
     if (warp == 0) {                                       // normalise column 0 (group 0 does the work, all lanes shuffle)
         double2 x[NV];
         jacobi_load_col<NV>(x, A, 0, sub, grp == 0);
@@ -372,13 +382,27 @@ __device__ __forceinline__ void mgs2_qr(double* A, int lda, int r, double* Rt, i
         for (int k0 = j + 1 + warp * 4; k0 < r; k0 += nwarp * 4) {      // warp-uniform trip count
             const int k = k0 + grp;
             const bool v = k < r;
+            const bool first = (k0 == j + 1);              // warp-uniform: this task holds the next pivot column (group 0)
             double2 q[NV], a[NV];
             jacobi_load_col<NV>(q, A, (long long)j * lda, sub, true);
             jacobi_load_col<NV>(a, A, (long long)(v ? k : j) * lda, sub, v);
-            double c_tot = 0.0;
+            const double n2k = v ? n2c[k] : 0.0;
+            const double n2ref = v ? __hiloint2double(nref[k], 0) : 0.0;
+            double c = 0.0, c2 = 0.0;
 #pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                double c = 0.0, c2 = 0.0;
+            for (int t = 0; t < NV; ++t) { c += q[t].x * a[t].x; c2 += q[t].y * a[t].y; }
+            c += c2;
+#pragma unroll
+            for (int off = JG / 2; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+#pragma unroll
+            for (int t = 0; t < NV; ++t) { a[t].x -= c * q[t].x; a[t].y -= c * q[t].y; }
+            double c_tot = c;
+            double n2n = n2k - c * c;                      // |a - c q|^2 for a unit q
+            // second pass only where the first one cancelled more than half of the squared norm (or the downdated norm
+            // has lost its digits); decided per warp, a superfluous second pass is harmless
+            const bool slow = __any_sync(0xffffffffu, v && (c * c > 0.5 * n2k || n2n < 1e-6 * n2ref));
+            if (slow) {
+                c = 0.0; c2 = 0.0;
 #pragma unroll
                 for (int t = 0; t < NV; ++t) { c += q[t].x * a[t].x; c2 += q[t].y * a[t].y; }
                 c += c2;
@@ -388,29 +412,32 @@ __device__ __forceinline__ void mgs2_qr(double* A, int lda, int r, double* Rt, i
                 for (int t = 0; t < NV; ++t) { a[t].x -= c * q[t].x; a[t].y -= c * q[t].y; }
                 c_tot += c;
             }
-            if (k0 == j + 1) {                             // warp-uniform: the first trailing column becomes q_{j+1} right away
-                const double n2 = jacobi_col_norm2<NV>(a);
-                if (grp == 0) {
-                    const double inv = (n2 > 0.0) ? rsqrt(n2) : 0.0, nrm = n2 * inv;     // one MUFU + Newton instead of sqrt and a division
+            const bool fresh = slow || first;
+            if (fresh) n2n = jacobi_col_norm2<NV>(a);
+            if (first && grp == 0) {                       // the first trailing column becomes q_{j+1} right away
+                const double inv = (n2n > 0.0) ? rsqrt(n2n) : 0.0, nrm = n2n * inv;     // one MUFU + Newton instead of sqrt and a division
 #pragma unroll
-                    for (int t = 0; t < NV; ++t) { a[t].x *= inv; a[t].y *= inv; }
-                    if (sub == 0) Rt[(size_t)(j + 1) * ldr + j + 1] = nrm;
-                }
+                for (int t = 0; t < NV; ++t) { a[t].x *= inv; a[t].y *= inv; }
+                if (sub == 0) Rt[(size_t)(j + 1) * ldr + j + 1] = nrm;
             }
             jacobi_store_col<NV>(a, A, (long long)k * lda, sub, v);
-            if (v && sub == 0) Rt[(size_t)j * ldr + k] = c_tot;
+            if (v && sub == 0) {
+                Rt[(size_t)j * ldr + k] = c_tot;
+                n2c[k] = n2n;
+                if (fresh) nref[k] = __double2hiint(n2n);
+            }
         }
     }
     __syncthreads();
 }
-__device__ __forceinline__ void mgs2_qr_dispatch(double* A, int lda, int len, int r, double* Rt, int ldr) {
-    if (len <= 32) mgs2_qr<2>(A, lda, r, Rt, ldr);
-    else if (len <= 48) mgs2_qr<3>(A, lda, r, Rt, ldr);
-    else if (len <= 64) mgs2_qr<4>(A, lda, r, Rt, ldr);
-    else if (len <= 80) mgs2_qr<5>(A, lda, r, Rt, ldr);
-    else if (len <= 96) mgs2_qr<6>(A, lda, r, Rt, ldr);
-    else if (len <= 112) mgs2_qr<7>(A, lda, r, Rt, ldr);
-    else mgs2_qr<8>(A, lda, r, Rt, ldr);
+__device__ __forceinline__ void mgs2_qr_dispatch(double* A, int lda, int len, int r, double* Rt, int ldr, double* n2c, int* nref) {
+    if (len <= 32) mgs2_qr<2>(A, lda, r, Rt, ldr, n2c, nref);
+    else if (len <= 48) mgs2_qr<3>(A, lda, r, Rt, ldr, n2c, nref);
+    else if (len <= 64) mgs2_qr<4>(A, lda, r, Rt, ldr, n2c, nref);
+    else if (len <= 80) mgs2_qr<5>(A, lda, r, Rt, ldr, n2c, nref);
+    else if (len <= 96) mgs2_qr<6>(A, lda, r, Rt, ldr, n2c, nref);
+    else if (len <= 112) mgs2_qr<7>(A, lda, r, Rt, ldr, n2c, nref);
+    else mgs2_qr<8>(A, lda, r, Rt, ldr, n2c, nref);
 }
 
 // column norms of Gs -> nrm2, ordered list of the columns above the cut-off -> list, their number -> *s_nact
@@ -484,12 +511,12 @@ __device__ __forceinline__ int jacobi_qr_problem(const double* __restrict__ g, i
         reinterpret_cast<double2*>(pp)[i] = make_double2(0.0, 0.0);
     }
     __syncthreads();
-    mgs2_qr_dispatch(A, ldg, len_g, r, B, ldl);           // A = Q1, B = columns of R1^T
+    mgs2_qr_dispatch(A, ldg, len_g, r, B, ldl, nrm2, list2);     // A = Q1, B = columns of R1^T (nrm2 / list2 are free until the sweeps)
     for (int i = tid; i < r * (ldg / 2); i += nthr) {     // Q1 is final: rows list[a] of gn
         const int a = i / (ldg / 2), e = i - a * (ldg / 2);
         reinterpret_cast<double2*>(gn + (size_t)list[a] * ldg)[e] = reinterpret_cast<const double2*>(A)[i];
     }
-    mgs2_qr_dispatch(B, ldl, r, r, C, ldl);               // B = Q2, C = columns of R2^T = L
+    mgs2_qr_dispatch(B, ldl, r, r, C, ldl, nrm2, list2);         // B = Q2, C = columns of R2^T = L
     int sweep = 0;
     for (; sweep < max_sweeps; ++sweep) {
         jacobi_active_list(C, ldl, r, nrm2, list2, sv_cutoff, s_nact, s_thr, s_rot);
