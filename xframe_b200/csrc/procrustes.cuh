@@ -134,11 +134,13 @@ __device__ __forceinline__ void jacobi_store_col(const double2 (&v)[NV], double*
 // 1 + ((k-1-r) mod (nblkp-1))); pairs are (position i, position nblkp-1-i).
 struct JBlockPair { int ba, bb; };
 __device__ __forceinline__ JBlockPair jacobi_block_pair(int i, int r, int nblkp) {
+    // 0 <= i < nblkp / 2 and 0 <= r <= mod, so both differences lie in (-2 mod, mod): two conditional additions instead of
+    // an integer modulo (the division sat on the critical path of every round)
     const int mod = nblkp - 1;
     JBlockPair bp;
     bp.ba = 0;
-    if (i != 0) { int t_ = (i - 1 - r) % mod; if (t_ < 0) t_ += mod; bp.ba = 1 + t_; }
-    int tb = (nblkp - 2 - i - r) % mod; if (tb < 0) tb += mod;
+    if (i != 0) { int t_ = i - 1 - r; if (t_ < 0) t_ += mod; if (t_ < 0) t_ += mod; bp.ba = 1 + t_; }
+    int tb = mod - 1 - i - r; if (tb < 0) tb += mod; if (tb < 0) tb += mod;
     bp.bb = 1 + tb;
     return bp;
 }
@@ -540,22 +542,31 @@ __device__ __forceinline__ int jacobi_qr_problem(const double* __restrict__ g, i
         C[i] = (s2 > thr_f && s2 > 0.0) ? C[i] * rsqrt(s2) : 0.0;
     }
     __syncthreads();
-    // ---- P[i][a] = sum_c U~[c][i] W[c][a]  ->  pp[list[i]][list[a]];  each thread a 1 x 4 tile (a fastest)
-    const int aq = (r + 3) / 4;
-    for (int item = tid; item < r * aq; item += nthr) {
-        const int i = item / aq, a4 = (item - i * aq) * 4;
-        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    // ---- P[i][a] = sum_c U~[c][i] W[c][a]  ->  pp[list[i]][list[a]];  each thread a 2 x 4 tile (a fastest); rows / columns
+    //      beyond r read the zero padding (ldl >= r rounded up to 16)
+    const int aq = (r + 3) / 4, iq = (r + 1) / 2;
+    for (int item = tid; item < iq * aq; item += nthr) {
+        const int i = (item / aq) * 2, a4 = (item - (item / aq) * aq) * 4;
+        double acc00 = 0.0, acc01 = 0.0, acc02 = 0.0, acc03 = 0.0, acc10 = 0.0, acc11 = 0.0, acc12 = 0.0, acc13 = 0.0;
         for (int c = 0; c < r; ++c) {
-            const double u = C[(size_t)c * ldl + i];
+            const double2 u = *reinterpret_cast<const double2*>(C + (size_t)c * ldl + i);
             const double2 b01 = *reinterpret_cast<const double2*>(B + (size_t)c * ldl + a4);
             const double2 b23 = *reinterpret_cast<const double2*>(B + (size_t)c * ldl + a4 + 2);
-            acc0 += u * b01.x; acc1 += u * b01.y; acc2 += u * b23.x; acc3 += u * b23.y;
+            acc00 += u.x * b01.x; acc01 += u.x * b01.y; acc02 += u.x * b23.x; acc03 += u.x * b23.y;
+            acc10 += u.y * b01.x; acc11 += u.y * b01.y; acc12 += u.y * b23.x; acc13 += u.y * b23.y;
         }
         double* dst = pp + (size_t)list[i] * ldg;
-        if (a4 < r) dst[list[a4]] = acc0;
-        if (a4 + 1 < r) dst[list[a4 + 1]] = acc1;
-        if (a4 + 2 < r) dst[list[a4 + 2]] = acc2;
-        if (a4 + 3 < r) dst[list[a4 + 3]] = acc3;
+        if (a4 < r) dst[list[a4]] = acc00;
+        if (a4 + 1 < r) dst[list[a4 + 1]] = acc01;
+        if (a4 + 2 < r) dst[list[a4 + 2]] = acc02;
+        if (a4 + 3 < r) dst[list[a4 + 3]] = acc03;
+        if (i + 1 < r) {
+            dst = pp + (size_t)list[i + 1] * ldg;
+            if (a4 < r) dst[list[a4]] = acc10;
+            if (a4 + 1 < r) dst[list[a4 + 1]] = acc11;
+            if (a4 + 2 < r) dst[list[a4 + 2]] = acc12;
+            if (a4 + 3 < r) dst[list[a4 + 3]] = acc13;
+        }
     }
     __syncthreads();
     return sweep;
