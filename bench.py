@@ -324,12 +324,12 @@ def run_ours(args):
                 'algorithmic_bytes_per_launch': ab.get(dom), 'launch_ms': per_launch_ms, 'share_of_step': groups[dom]['ms'] / tot_ms}
         if dom == 'procrustes_jacobi':
             if METRIC.endswith('L63_Nr128') and nb == 128:
-                # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full, profiles/r01j_jacobi_ncu_details.txt
-                roof['traffic'] = 233537024 + 425556992
+                # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full, profiles/r01k_jacobi_ncu_details.txt
+                roof['traffic'] = 232848640 + 428813568
             roof['note'] = ('dominant kernel is the QR-preconditioned one-sided Jacobi polar factor: shared-memory resident, bound by the '
-                            'sequential rotation steps and the FP64 pipe (ncu: FP64 pipe 19 % of issue peak, barrier wait the top stall); '
+                            'sequential rotation steps and the FP64 pipe (ncu: FP64 pipe 18 % of issue peak, 44 % of the warp time at barriers next to a latency-bound critical path); '
                             'neither the HBM nor the tensor roofline applies and its HBM fraction is low by construction. '
-                            'Roofline-bound kernels: fft_phi (HBM), legendre / hankel (FP64 DMMA), see groups and profiles/README.md')
+                            'Roofline-bound kernels: fft_phi / real_update (HBM), legendre / hankel (FP64 DMMA): see the per-group fractions in groups, the whole-iteration HBM floor in iteration, and profiles/README.md')
         roof['groups'] = {k: {'ms_per_step': v['ms'] / K, 'launches_per_step': v['launches'] / K,
                               **({'GBps': ab[k] * v['launches'] / (v['ms'] * 1e-3) / 1e9} if k in ab else {}),
                               **({'TFLOPs_fp64': hankel_flops(nb) * v['launches'] / (v['ms'] * 1e-3) / 1e12} if k == 'hankel' else {})}
