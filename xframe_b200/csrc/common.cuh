@@ -72,3 +72,26 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
 }
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+
+// 1 / sqrt(x) for x > 0 (normal range): MUFU.RSQ64H seed (2^-22) + two Newton steps, 1-2 ulp, no slow-path call -- the
+// library rsqrt() branches to a subroutine for special operands, which serialises unrolled epilogues.
+__device__ __forceinline__ double rsqrt_pos(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double xh = 0.5 * x;
+    double r = fma(-(xh * y), y, 0.5);
+    y = fma(y, r, y);
+    r = fma(-(xh * y), y, 0.5);
+    return fma(y, r, y);
+}
+
+// sqrt(ni / sq) restricted to (sq >= 0) & (ni >= 0), 0 elsewhere -- the multiplier of project_to_modified_intensity
+// (fxs_Projections.py:899-909) with the reference's IEEE corner cases (sq = 0: inf, or NaN for ni = 0).  Two independent
+// branch-free rsqrt sequences instead of a division followed by a square root: the fused FFT epilogue evaluates 8 of
+// them per thread and needs the instruction-level parallelism.  2-3 ulp; subnormal operands are treated as zero.
+__device__ __forceinline__ double mod_intensity_multiplier(double ni, double sq) {
+    const double tiny = 2.2250738585072014e-308;              // DBL_MIN
+    const double a = (sq >= tiny) ? rsqrt_pos(sq) : __longlong_as_double(0x7ff0000000000000LL);     // 1 / sqrt(sq), inf at 0
+    const double b = (ni >= tiny) ? ni * rsqrt_pos(ni) : 0.0;                                        // sqrt(ni)
+    return (sq >= 0.0 && ni >= 0.0) ? a * b : 0.0;
+}

@@ -179,8 +179,7 @@ __global__ void __launch_bounds__(256, MOD ? 3 : 2) fft2_inverse_kernel(const do
                 if constexpr (MOD) {
                     const double2 v = ldg2(rh + (size_t)row * C::N + t + N2 * j);
                     const double sq = __dadd_rn(__dmul_rn(v.x, v.x), __dmul_rn(v.y, v.y));
-                    double mult = 0.0;
-                    if (sq >= 0.0 && o.x >= 0.0) mult = sqrt(o.x / sq);
+                    const double mult = mod_intensity_multiplier(o.x, sq);
                     o = make_double2(v.x * mult, v.y * mult);
                 }
                 dst[(size_t)row * C::N + t + N2 * j] = o;

@@ -46,8 +46,7 @@ __global__ void modify_intensity_kernel(const double2* __restrict__ rho_hat, con
         const double2 v = ldg2(rh + i);
         const double sq = __dadd_rn(__dmul_rn(v.x, v.x), __dmul_rn(v.y, v.y));
         const double ni = ldg2(ip + i).x;
-        double mult = 0.0;
-        if (sq >= 0.0 && ni >= 0.0) mult = sqrt(ni / sq);
+        const double mult = mod_intensity_multiplier(ni, sq);
         dst[i] = make_double2(v.x * mult, v.y * mult);
     }
 }
