@@ -306,6 +306,114 @@ __global__ void __launch_bounds__(LEG2_THREADS, 3) legendre2_forward_kernel(cons
 }
 
 
+// v3 forward: the same pipeline as legendre2_forward_kernel, but the table fragments live in REGISTERS and a warp owns two
+// 8-column blocks.  The tables FE / FO of the CTA's order m are constant over its whole life, and an 8 x 4 x 8 DMMA takes
+// its B operand one double per lane: K2 / 4 (<= 8) k-steps x 2 column blocks x 2 parities = 32 doubles per lane, loaded
+// once from L2.  Per k-step a warp then reads only its two A rows (x at theta_j, y at the mirrored node: 2 x 128-bit
+// shared loads) and issues 8 DMMAs, against 4 DMMAs per (2 x 128-bit + 2 x 64-bit) loads before: 1 instead of 3 shared
+// wavefronts per DMMA, half the fold additions per DMMA, and no table staging in shared memory (52 KB per CTA).
+//   128 threads: warp = (row block of 8 rows) x (column-block pair cg: degrees m + 2 (16 cg + 0..15) [+1])
+#define LEG3_THREADS 128
+static inline size_t legendre3_fwd_smem(int n_theta) { return (size_t)LEG2_FST * LEG2_FR * (n_theta + 4) * sizeof(double2); }
+
+template <int R, int ST>
+__global__ void __launch_bounds__(LEG3_THREADS, 4) legendre3_forward_kernel(const double2* __restrict__ a, double2* __restrict__ c,
+                                                                           const double* __restrict__ FE, const double* __restrict__ FO,
+                                                                           int S, int l_max, int n_theta, int NP, int pos_only) {
+    static_assert(R == 16, "two row blocks of 8 rows x two column-block pairs = 4 warps");
+    extern __shared__ __align__(16) unsigned char smem_leg2[];
+    const int K2 = n_theta >> 1;
+    const int RS = n_theta + 4;                            // row stride (double2): rows 64 B apart mod 128 -> conflict-free fragments
+    double2* raw = reinterpret_cast<double2*>(smem_leg2);  // [ST][R][RS]
+    const int m = blockIdx.y;
+    const int M2 = 2 * l_max + 1;
+    const bool both = (!pos_only) && m > 0;
+    const int SH = both ? R / 2 : R;                       // shells per group
+    const int n_groups = (S + SH - 1) / SH;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ar = lane >> 2, ak = lane & 3;
+    const int cg = warp & 1, r0 = (warp >> 1) * 8;
+    const int ne = (l_max - m) / 2 + 1, no = (l_max - m + 1) / 2;
+    bool do_e[2], do_o[2];
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb) { do_e[nb] = (2 * cg + nb) * 8 < ne; do_o[nb] = (2 * cg + nb) * 8 < no; }
+
+    auto fetch = [&](int g, int buf) {
+        if (g < n_groups) {
+            double2* dst = raw + (size_t)buf * R * RS;
+            for (int item = tid; item < R * n_theta; item += LEG3_THREADS) {
+                const int row = item / n_theta, j = item - row * n_theta;
+                const int sh = g * SH + (both ? (row % (R / 2)) : row), sign = both ? (row / (R / 2)) : 0;
+                const bool ok = sh < S;
+                const int mm = sign ? (M2 - m) : m;
+                cp_async16(dst + row * RS + j, a + ((size_t)(ok ? sh : 0) * M2 + mm) * n_theta + j, ok);
+            }
+        }
+        cp_async_commit();                                 // (possibly empty) group: keeps the wait count uniform
+    };
+
+    const int per_cta = (n_groups + gridDim.x - 1) / gridDim.x;
+    int g = blockIdx.x * per_cta;
+    const int g_end = min(n_groups, g + per_cta);
+    if (g >= g_end) return;
+#pragma unroll
+    for (int s = 0; s < ST - 1; ++s) fetch(g + s < g_end ? g + s : n_groups, s);
+    // table fragments: B[k][n] of k-step t is FE[m][4 t + ak][8 (2 cg + nb) + ar]
+    double be[2][8], bo[2][8];
+    {
+        const double* FEm = FE + (size_t)m * K2 * NP;
+        const double* FOm = FO + (size_t)m * K2 * NP;
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) {
+                const int col = (2 * cg + nb) * 8 + ar, j = 4 * t + ak;
+                const bool ok = (j < K2) && (col < NP);
+                be[nb][t] = (ok && do_e[nb]) ? __ldg(FEm + (size_t)j * NP + col) : 0.0;
+                bo[nb][t] = (ok && do_o[nb]) ? __ldg(FOm + (size_t)j * NP + col) : 0.0;
+            }
+    }
+    int buf = 0;
+    for (; g < g_end; ++g) {
+        cp_async_wait<ST - 2>();                           // the oldest outstanding group (this one) has landed
+        __syncthreads();                                   // ... for every thread; and everyone is done with the buffer refilled next
+        fetch(g + ST - 1 < g_end ? g + ST - 1 : n_groups, (buf + ST - 1) % ST);
+        const double2* rr = raw + (size_t)buf * R * RS + (r0 + ar) * RS;
+        double ere[2][2] = {}, eim[2][2] = {}, ore_[2][2] = {}, oim[2][2] = {};
+        if (do_e[0]) {                                     // warp-uniform: a column-block pair that is pure padding has nothing to do
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                if (4 * t < K2) {
+                    const double2 x = rr[4 * t + ak], y = rr[n_theta - 1 - 4 * t - ak];
+                    const double er = x.x + y.x, ei = x.y + y.y, orr = x.x - y.x, oi = x.y - y.y;
+#pragma unroll
+                    for (int nb = 0; nb < 2; ++nb) {
+                        if (do_e[nb]) { dmma884(ere[nb][0], ere[nb][1], er, be[nb][t]); dmma884(eim[nb][0], eim[nb][1], ei, be[nb][t]); }
+                        if (do_o[nb]) { dmma884(ore_[nb][0], ore_[nb][1], orr, bo[nb][t]); dmma884(oim[nb][0], oim[nb][1], oi, bo[nb][t]); }
+                    }
+                }
+            }
+            const int row = r0 + ar;
+            const int sh = g * SH + (both ? (row % (R / 2)) : row), sign = both ? (row / (R / 2)) : 0;
+            if (sh < S) {
+                const double sg = (sign && (m & 1)) ? -1.0 : 1.0;      // (-1)^m on the -m rows
+                const int ms = sign ? -m : m;
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int col = (2 * cg + nb) * 8 + 2 * ak + cc;
+                        const int le = m + 2 * col, lo = le + 1;
+                        if (do_e[nb] && le <= l_max) c[(size_t)(le * (le + 1) + ms) * S + sh] = make_double2(sg * ere[nb][cc], sg * eim[nb][cc]);
+                        if (do_o[nb] && lo <= l_max) c[(size_t)(lo * (lo + 1) + ms) * S + sh] = make_double2(sg * ore_[nb][cc], sg * oim[nb][cc]);
+                    }
+            }
+        }
+        buf = (buf + 1) % ST;
+    }
+}
+
+
 // inverse (synthesis) counterpart: coefficients c [(L+1)^2][S] -> phi-Fourier rows a [S][M2][n_theta] for one order m per CTA.
 // The coefficient rows of the next shell groups are gathered with cp.async (16-byte elements, 8 / 16 consecutive shells
 // of one (l, +-m) row are contiguous) while the current group is multiplied with the resident tables IE / IO [NP][K2].
@@ -399,6 +507,119 @@ __global__ void __launch_bounds__(LEG2_THREADS, 3) legendre2_inverse_kernel(cons
                         dst[n_theta - 1 - j] = make_double2(sg * (ere[cc] - ore_[cc]), sg * (eim[cc] - oim[cc]));
                     }
                 }
+            }
+        }
+        buf = (buf + 1) % ST;
+    }
+}
+
+
+// v3 inverse: table fragments in registers, two 8-node blocks per warp (see legendre3_forward_kernel): per k-step one 128-bit
+// shared load feeds 4 DMMAs.   128 threads: warp = (row block of 8 rows) x (node-block pair cg: theta_j, j = 16 cg + 0..15)
+static inline size_t legendre3_inv_smem(int NP) { return (size_t)LEG2_IST * 2 * LEG2_IR * (NP + 4) * sizeof(double2); }
+
+template <int R, int ST>
+__global__ void __launch_bounds__(LEG3_THREADS, 4) legendre3_inverse_kernel(const double2* __restrict__ c, double2* __restrict__ a,
+                                                                           const double* __restrict__ IE, const double* __restrict__ IO,
+                                                                           int S, int l_max, int n_theta, int NP, int pos_only) {
+    static_assert(R == 16, "two row blocks of 8 rows x two node-block pairs = 4 warps");
+    extern __shared__ __align__(16) unsigned char smem_leg2[];
+    const int K2 = n_theta >> 1;
+    const int RS = NP + 4;                                 // row stride (double2): rows 64 B apart mod 128
+    double2* raw = reinterpret_cast<double2*>(smem_leg2);  // [ST][2 parities][R][RS]
+    const int m = blockIdx.y;
+    const int M2 = 2 * l_max + 1;
+    const bool both = (!pos_only) && m > 0;
+    const int SH = both ? R / 2 : R;
+    const int n_groups = (S + SH - 1) / SH;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ar = lane >> 2, ak = lane & 3;
+    const int cg = warp & 1, r0 = (warp >> 1) * 8;
+    const int ne = (l_max - m) / 2 + 1, no = (l_max - m + 1) / 2;
+    const int Ke = (ne + 3) & ~3, Ko = (no + 3) & ~3;      // contraction only over existing degrees (zero padded)
+    bool jok[2];
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb) jok[nb] = (2 * cg + nb) * 8 < K2;
+
+    auto fetch = [&](int g, int buf) {
+        if (g < n_groups) {
+            double2* dst = raw + (size_t)buf * 2 * R * RS;
+            for (int item = tid; item < 2 * NP * R; item += LEG3_THREADS) {
+                const int shl = item % SH;                 // shells fastest: contiguous 16-byte elements of one coefficient row
+                int rest = item / SH;
+                const int sign = both ? (rest & 1) : 0;
+                if (both) rest >>= 1;
+                const int i = rest % NP, par = rest / NP;
+                const int l = m + par + 2 * i;
+                const int sh = g * SH + shl;
+                const bool ok = (l <= l_max) && (sh < S);
+                const int row = sign * (R / 2) + shl;
+                cp_async16(dst + ((size_t)par * R + row) * RS + i, c + (size_t)(ok ? l * (l + 1) + (sign ? -m : m) : 0) * S + (ok ? sh : 0), ok);
+            }
+        }
+        cp_async_commit();
+    };
+
+    const int per_cta = (n_groups + gridDim.x - 1) / gridDim.x;
+    int g = blockIdx.x * per_cta;
+    const int g_end = min(n_groups, g + per_cta);
+    if (g >= g_end) return;
+#pragma unroll
+    for (int s_ = 0; s_ < ST - 1; ++s_) fetch(g + s_ < g_end ? g + s_ : n_groups, s_);
+    // table fragments: B[k][n] of k-step t is IE[m][4 t + ak][8 (2 cg + nb) + ar]   (degree index x northern node)
+    double be[2][8], bo[2][8];
+    {
+        const double* IEm = IE + (size_t)m * NP * K2;
+        const double* IOm = IO + (size_t)m * NP * K2;
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) {
+                const int j = (2 * cg + nb) * 8 + ar, i = 4 * t + ak;
+                be[nb][t] = (i < Ke && i < NP && j < K2) ? __ldg(IEm + (size_t)i * K2 + j) : 0.0;
+                bo[nb][t] = (i < Ko && i < NP && j < K2) ? __ldg(IOm + (size_t)i * K2 + j) : 0.0;
+            }
+    }
+    int buf = 0;
+    for (; g < g_end; ++g) {
+        cp_async_wait<ST - 2>();
+        __syncthreads();
+        fetch(g + ST - 1 < g_end ? g + ST - 1 : n_groups, (buf + ST - 1) % ST);
+        const double2* ce = raw + (size_t)buf * 2 * R * RS + (size_t)(r0 + ar) * RS;
+        const double2* co = ce + (size_t)R * RS;
+        double ere[2][2] = {}, eim[2][2] = {}, ore_[2][2] = {}, oim[2][2] = {};
+        if (jok[0]) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                if (4 * t < Ke) {
+                    const double2 x = ce[4 * t + ak];
+#pragma unroll
+                    for (int nb = 0; nb < 2; ++nb)
+                        if (jok[nb]) { dmma884(ere[nb][0], ere[nb][1], x.x, be[nb][t]); dmma884(eim[nb][0], eim[nb][1], x.y, be[nb][t]); }
+                }
+                if (4 * t < Ko) {
+                    const double2 x = co[4 * t + ak];
+#pragma unroll
+                    for (int nb = 0; nb < 2; ++nb)
+                        if (jok[nb]) { dmma884(ore_[nb][0], ore_[nb][1], x.x, bo[nb][t]); dmma884(oim[nb][0], oim[nb][1], x.y, bo[nb][t]); }
+                }
+            }
+            const int row = r0 + ar;
+            const int sh = g * SH + (both ? (row % (R / 2)) : row), sign = both ? (row / (R / 2)) : 0;
+            if (sh < S) {
+                const double sg = (sign && (m & 1)) ? -1.0 : 1.0;      // (-1)^m on the -m rows
+                const int mm = sign ? (M2 - m) : m;
+                double2* dst = a + ((size_t)sh * M2 + mm) * n_theta;
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int j = (2 * cg + nb) * 8 + 2 * ak + cc;
+                        if (jok[nb] && j < K2) {
+                            dst[j] = make_double2(sg * (ere[nb][cc] + ore_[nb][cc]), sg * (eim[nb][cc] + oim[nb][cc]));
+                            dst[n_theta - 1 - j] = make_double2(sg * (ere[nb][cc] - ore_[nb][cc]), sg * (eim[nb][cc] - oim[nb][cc]));
+                        }
+                    }
             }
         }
         buf = (buf + 1) % ST;

@@ -212,8 +212,8 @@ int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
     if (dev_alloc(p, &p->rt0, B * p->n_theta * p->n_phi)) return 1;
     p->leg2 = (p->n_theta / 2 <= 32 && p->NP <= 32 && p->n_theta % 4 == 0);
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, dev); }
-    if (p->leg2) XFB_CUDA(cudaFuncSetAttribute(legendre2_forward_kernel<LEG2_FR, LEG2_FST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre2_fwd_smem(p->n_theta)));
-    if (p->leg2) XFB_CUDA(cudaFuncSetAttribute(legendre2_inverse_kernel<LEG2_IR, LEG2_IST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre2_inv_smem(p->NP)));
+    if (p->leg2) XFB_CUDA(cudaFuncSetAttribute(legendre3_forward_kernel<LEG2_FR, LEG2_FST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre3_fwd_smem(p->n_theta)));
+    if (p->leg2) XFB_CUDA(cudaFuncSetAttribute(legendre3_inverse_kernel<LEG2_IR, LEG2_IST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre3_inv_smem(p->NP)));
     XFB_CUDA(cudaFuncSetAttribute(legendre_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre_fwd_smem(p->n_theta)));
     XFB_CUDA(cudaFuncSetAttribute(legendre_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre_inv_smem(p->n_theta, p->NP)));
     *out = p;
@@ -326,9 +326,9 @@ static int sht_forward_i(xfb_plan* p, SlotView in, int shells_per_run, double2* 
     XFB_LAUNCH(p, PG_FFT, st, if (launch_fft(true, p->n_phi, in, shells_per_run, sub, p->A0, p->tw, S, p->n_theta, p->L, st, half | (square ? 2 : 0))) return 1);
     if (p->leg2) {     // small configuration: table-resident, cp.async double-buffered kernel
         const int groups = cdiv(S, half ? LEG2_FR : LEG2_FR / 2);
-        dim3 g2(std::min(groups, std::max(1, (3 * p->n_sm * 4) / (p->L + 1))), p->L + 1);
+        dim3 g2(std::min(groups, std::max(1, (4 * p->n_sm * 4) / (p->L + 1))), p->L + 1);
         XFB_LAUNCH(p, PG_LEGENDRE, st,
-                   legendre2_forward_kernel<LEG2_FR, LEG2_FST><<<g2, LEG2_THREADS, legendre2_fwd_smem(p->n_theta), st>>>(p->A0, c_out, p->FE, p->FO, S, p->L, p->n_theta,
+                   legendre3_forward_kernel<LEG2_FR, LEG2_FST><<<g2, LEG3_THREADS, legendre3_fwd_smem(p->n_theta), st>>>(p->A0, c_out, p->FE, p->FO, S, p->L, p->n_theta,
                                                                                                      p->NP, half));
         return 0;
     }
@@ -355,9 +355,9 @@ static int sht_inverse_i(xfb_plan* p, const double2* c_in, double2* grid_out, in
     // herm (3-D): the coefficients belong to a real field and only m >= 0 is valid in c_in
     if (p->leg2) {
         const int groups = cdiv(S, herm ? LEG2_IR : LEG2_IR / 2);
-        dim3 g2(std::min(groups, std::max(1, (3 * p->n_sm * 4) / (p->L + 1))), p->L + 1);
+        dim3 g2(std::min(groups, std::max(1, (4 * p->n_sm * 4) / (p->L + 1))), p->L + 1);
         XFB_LAUNCH(p, PG_LEGENDRE, st,
-                   legendre2_inverse_kernel<LEG2_IR, LEG2_IST><<<g2, LEG2_THREADS, legendre2_inv_smem(p->NP), st>>>(c_in, p->A0, p->IE, p->IO, S, p->L,
+                   legendre3_inverse_kernel<LEG2_IR, LEG2_IST><<<g2, LEG3_THREADS, legendre3_inv_smem(p->NP), st>>>(c_in, p->A0, p->IE, p->IO, S, p->L,
                                                                                                                   p->n_theta, p->NP, herm));
     } else {
     dim3 g(cdiv(S, herm ? 32 : 16), p->L + 1);
