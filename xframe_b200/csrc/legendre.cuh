@@ -312,15 +312,17 @@ __global__ void __launch_bounds__(LEG2_THREADS, 3) legendre2_forward_kernel(cons
 // once from L2.  Per k-step a warp then reads only its two A rows (x at theta_j, y at the mirrored node: 2 x 128-bit
 // shared loads) and issues 8 DMMAs, against 4 DMMAs per (2 x 128-bit + 2 x 64-bit) loads before: 1 instead of 3 shared
 // wavefronts per DMMA, half the fold additions per DMMA, and no table staging in shared memory (52 KB per CTA).
-//   128 threads: warp = (row block of 8 rows) x (column-block pair cg: degrees m + 2 (16 cg + 0..15) [+1])
-#define LEG3_THREADS 128
+//   64 NCG threads: warp = (row block of 8 rows) x (column-block pair cg < NCG: degrees m + 2 (16 cg + 0..15) [+1]);
+//   KS = k-steps held in registers.  <KS 8, NCG 2>: n_theta <= 64, NP <= 32 (L = 63), 4 CTAs per SM;
+//   <KS 16, NCG 4>: n_theta <= 128, NP <= 64 (L = 127), 64 table doubles per lane, 1 CTA of 8 warps per SM.
 static inline size_t legendre3_fwd_smem(int n_theta) { return (size_t)LEG2_FST * LEG2_FR * (n_theta + 4) * sizeof(double2); }
 
-template <int R, int ST>
-__global__ void __launch_bounds__(LEG3_THREADS, 4) legendre3_forward_kernel(const double2* __restrict__ a, double2* __restrict__ c,
+template <int R, int ST, int KS, int NCG>
+__global__ void __launch_bounds__(64 * NCG, KS <= 8 ? 4 : 1) legendre3_forward_kernel(const double2* __restrict__ a, double2* __restrict__ c,
                                                                            const double* __restrict__ FE, const double* __restrict__ FO,
                                                                            int S, int l_max, int n_theta, int NP, int pos_only) {
-    static_assert(R == 16, "two row blocks of 8 rows x two column-block pairs = 4 warps");
+    static_assert(R == 16, "two row blocks of 8 rows x NCG column-block pairs");
+    constexpr int LEG3_THREADS = 64 * NCG;
     extern __shared__ __align__(16) unsigned char smem_leg2[];
     const int K2 = n_theta >> 1;
     const int RS = n_theta + 4;                            // row stride (double2): rows 64 B apart mod 128 -> conflict-free fragments
@@ -332,7 +334,7 @@ __global__ void __launch_bounds__(LEG3_THREADS, 4) legendre3_forward_kernel(cons
     const int n_groups = (S + SH - 1) / SH;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ar = lane >> 2, ak = lane & 3;
-    const int cg = warp & 1, r0 = (warp >> 1) * 8;
+    const int cg = warp % NCG, r0 = (warp / NCG) * 8;
     const int ne = (l_max - m) / 2 + 1, no = (l_max - m + 1) / 2;
     bool do_e[2], do_o[2];
 #pragma unroll
@@ -359,12 +361,12 @@ __global__ void __launch_bounds__(LEG3_THREADS, 4) legendre3_forward_kernel(cons
 #pragma unroll
     for (int s = 0; s < ST - 1; ++s) fetch(g + s < g_end ? g + s : n_groups, s);
     // table fragments: B[k][n] of k-step t is FE[m][4 t + ak][8 (2 cg + nb) + ar]
-    double be[2][8], bo[2][8];
+    double be[2][KS], bo[2][KS];
     {
         const double* FEm = FE + (size_t)m * K2 * NP;
         const double* FOm = FO + (size_t)m * K2 * NP;
 #pragma unroll
-        for (int t = 0; t < 8; ++t)
+        for (int t = 0; t < KS; ++t)
 #pragma unroll
             for (int nb = 0; nb < 2; ++nb) {
                 const int col = (2 * cg + nb) * 8 + ar, j = 4 * t + ak;
@@ -382,7 +384,7 @@ __global__ void __launch_bounds__(LEG3_THREADS, 4) legendre3_forward_kernel(cons
         double ere[2][2] = {}, eim[2][2] = {}, ore_[2][2] = {}, oim[2][2] = {};
         if (do_e[0]) {                                     // warp-uniform: a column-block pair that is pure padding has nothing to do
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
+            for (int t = 0; t < KS; ++t) {
                 if (4 * t < K2) {
                     const double2 x = rr[4 * t + ak], y = rr[n_theta - 1 - 4 * t - ak];
                     const double er = x.x + y.x, ei = x.y + y.y, orr = x.x - y.x, oi = x.y - y.y;
@@ -518,11 +520,12 @@ __global__ void __launch_bounds__(LEG2_THREADS, 3) legendre2_inverse_kernel(cons
 // shared load feeds 4 DMMAs.   128 threads: warp = (row block of 8 rows) x (node-block pair cg: theta_j, j = 16 cg + 0..15)
 static inline size_t legendre3_inv_smem(int NP) { return (size_t)LEG2_IST * 2 * LEG2_IR * (NP + 4) * sizeof(double2); }
 
-template <int R, int ST>
-__global__ void __launch_bounds__(LEG3_THREADS, 4) legendre3_inverse_kernel(const double2* __restrict__ c, double2* __restrict__ a,
+template <int R, int ST, int KS, int NCG>
+__global__ void __launch_bounds__(64 * NCG, KS <= 8 ? 4 : 1) legendre3_inverse_kernel(const double2* __restrict__ c, double2* __restrict__ a,
                                                                            const double* __restrict__ IE, const double* __restrict__ IO,
                                                                            int S, int l_max, int n_theta, int NP, int pos_only) {
-    static_assert(R == 16, "two row blocks of 8 rows x two node-block pairs = 4 warps");
+    static_assert(R == 16, "two row blocks of 8 rows x NCG node-block pairs");
+    constexpr int LEG3_THREADS = 64 * NCG;
     extern __shared__ __align__(16) unsigned char smem_leg2[];
     const int K2 = n_theta >> 1;
     const int RS = NP + 4;                                 // row stride (double2): rows 64 B apart mod 128
@@ -534,7 +537,7 @@ __global__ void __launch_bounds__(LEG3_THREADS, 4) legendre3_inverse_kernel(cons
     const int n_groups = (S + SH - 1) / SH;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ar = lane >> 2, ak = lane & 3;
-    const int cg = warp & 1, r0 = (warp >> 1) * 8;
+    const int cg = warp % NCG, r0 = (warp / NCG) * 8;
     const int ne = (l_max - m) / 2 + 1, no = (l_max - m + 1) / 2;
     const int Ke = (ne + 3) & ~3, Ko = (no + 3) & ~3;      // contraction only over existing degrees (zero padded)
     bool jok[2];
@@ -567,12 +570,12 @@ __global__ void __launch_bounds__(LEG3_THREADS, 4) legendre3_inverse_kernel(cons
 #pragma unroll
     for (int s_ = 0; s_ < ST - 1; ++s_) fetch(g + s_ < g_end ? g + s_ : n_groups, s_);
     // table fragments: B[k][n] of k-step t is IE[m][4 t + ak][8 (2 cg + nb) + ar]   (degree index x northern node)
-    double be[2][8], bo[2][8];
+    double be[2][KS], bo[2][KS];
     {
         const double* IEm = IE + (size_t)m * NP * K2;
         const double* IOm = IO + (size_t)m * NP * K2;
 #pragma unroll
-        for (int t = 0; t < 8; ++t)
+        for (int t = 0; t < KS; ++t)
 #pragma unroll
             for (int nb = 0; nb < 2; ++nb) {
                 const int j = (2 * cg + nb) * 8 + ar, i = 4 * t + ak;
@@ -590,7 +593,7 @@ __global__ void __launch_bounds__(LEG3_THREADS, 4) legendre3_inverse_kernel(cons
         double ere[2][2] = {}, eim[2][2] = {}, ore_[2][2] = {}, oim[2][2] = {};
         if (jok[0]) {
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
+            for (int t = 0; t < KS; ++t) {
                 if (4 * t < Ke) {
                     const double2 x = ce[4 * t + ak];
 #pragma unroll

@@ -39,7 +39,8 @@ struct xfb_plan {
     double2 *A0 = nullptr, *C0 = nullptr, *C1 = nullptr, *W0 = nullptr, *W1 = nullptr, *W2 = nullptr;
     double2 *A0s = nullptr, *C0s = nullptr, *rt0 = nullptr;   // shell-0 side path of the fused ft_stab step
     int fused_ft_stab = 1;
-    bool leg2 = false;                              // v2 Legendre kernels (K2 <= 32, NP <= 32)
+    bool leg2 = false;                              // v3 Legendre kernels (K2 <= 64, NP <= 64)
+    bool leg3_big = false;                          // ... the <KS 16, NCG 4> instantiation (K2 > 32 or NP > 32)
     int half_spectrum = 1;                          // real intensity fields: transform only the m >= 0 half (3-D, v2 Legendre)
     // host-buffer pipeline (xfb_mtip_step_host)
     cudaStream_t s_in = nullptr, s_out = nullptr; cudaEvent_t ev_start = nullptr; std::vector<cudaEvent_t> ev_in, ev_comp;
@@ -210,10 +211,13 @@ int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
     if (dev_alloc(p, &p->A0s, B * p->M2 * p->n_theta)) return 1;
     if (dev_alloc(p, &p->C0s, B * p->NLM)) return 1;
     if (dev_alloc(p, &p->rt0, B * p->n_theta * p->n_phi)) return 1;
-    p->leg2 = (p->n_theta / 2 <= 32 && p->NP <= 32 && p->n_theta % 4 == 0);
+    p->leg2 = (p->n_theta / 2 <= 64 && p->NP <= 64 && p->n_theta % 4 == 0);
+    p->leg3_big = p->leg2 && (p->n_theta / 2 > 32 || p->NP > 32);
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, dev); }
-    if (p->leg2) XFB_CUDA(cudaFuncSetAttribute(legendre3_forward_kernel<LEG2_FR, LEG2_FST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre3_fwd_smem(p->n_theta)));
-    if (p->leg2) XFB_CUDA(cudaFuncSetAttribute(legendre3_inverse_kernel<LEG2_IR, LEG2_IST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre3_inv_smem(p->NP)));
+    if (p->leg2 && !p->leg3_big) XFB_CUDA(cudaFuncSetAttribute(legendre3_forward_kernel<LEG2_FR, LEG2_FST, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre3_fwd_smem(p->n_theta)));
+    if (p->leg3_big) XFB_CUDA(cudaFuncSetAttribute(legendre3_forward_kernel<LEG2_FR, LEG2_FST, 16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre3_fwd_smem(p->n_theta)));
+    if (p->leg2 && !p->leg3_big) XFB_CUDA(cudaFuncSetAttribute(legendre3_inverse_kernel<LEG2_IR, LEG2_IST, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre3_inv_smem(p->NP)));
+    if (p->leg3_big) XFB_CUDA(cudaFuncSetAttribute(legendre3_inverse_kernel<LEG2_IR, LEG2_IST, 16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre3_inv_smem(p->NP)));
     XFB_CUDA(cudaFuncSetAttribute(legendre_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre_fwd_smem(p->n_theta)));
     XFB_CUDA(cudaFuncSetAttribute(legendre_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre_inv_smem(p->n_theta, p->NP)));
     *out = p;
@@ -326,10 +330,16 @@ static int sht_forward_i(xfb_plan* p, SlotView in, int shells_per_run, double2* 
     XFB_LAUNCH(p, PG_FFT, st, if (launch_fft(true, p->n_phi, in, shells_per_run, sub, p->A0, p->tw, S, p->n_theta, p->L, st, half | (square ? 2 : 0))) return 1);
     if (p->leg2) {     // small configuration: table-resident, cp.async double-buffered kernel
         const int groups = cdiv(S, half ? LEG2_FR : LEG2_FR / 2);
-        dim3 g2(std::min(groups, std::max(1, (4 * p->n_sm * 4) / (p->L + 1))), p->L + 1);
-        XFB_LAUNCH(p, PG_LEGENDRE, st,
-                   legendre3_forward_kernel<LEG2_FR, LEG2_FST><<<g2, LEG3_THREADS, legendre3_fwd_smem(p->n_theta), st>>>(p->A0, c_out, p->FE, p->FO, S, p->L, p->n_theta,
-                                                                                                     p->NP, half));
+        // 4 waves of the resident CTAs (4 per SM for the small instantiation, 1 for the big one)
+        dim3 g2(std::min(groups, std::max(1, ((p->leg3_big ? 1 : 4) * p->n_sm * 4) / (p->L + 1))), p->L + 1);
+        if (p->leg3_big)
+            XFB_LAUNCH(p, PG_LEGENDRE, st,
+                       legendre3_forward_kernel<LEG2_FR, LEG2_FST, 16, 4><<<g2, 256, legendre3_fwd_smem(p->n_theta), st>>>(p->A0, c_out, p->FE, p->FO, S, p->L,
+                                                                                                                       p->n_theta, p->NP, half));
+        else
+            XFB_LAUNCH(p, PG_LEGENDRE, st,
+                       legendre3_forward_kernel<LEG2_FR, LEG2_FST, 8, 2><<<g2, 128, legendre3_fwd_smem(p->n_theta), st>>>(p->A0, c_out, p->FE, p->FO, S, p->L,
+                                                                                                                      p->n_theta, p->NP, half));
         return 0;
     }
     dim3 g(cdiv(S, 16), p->L + 1);
@@ -355,9 +365,14 @@ static int sht_inverse_i(xfb_plan* p, const double2* c_in, double2* grid_out, in
     // herm (3-D): the coefficients belong to a real field and only m >= 0 is valid in c_in
     if (p->leg2) {
         const int groups = cdiv(S, herm ? LEG2_IR : LEG2_IR / 2);
-        dim3 g2(std::min(groups, std::max(1, (4 * p->n_sm * 4) / (p->L + 1))), p->L + 1);
-        XFB_LAUNCH(p, PG_LEGENDRE, st,
-                   legendre3_inverse_kernel<LEG2_IR, LEG2_IST><<<g2, LEG3_THREADS, legendre3_inv_smem(p->NP), st>>>(c_in, p->A0, p->IE, p->IO, S, p->L,
+        dim3 g2(std::min(groups, std::max(1, ((p->leg3_big ? 1 : 4) * p->n_sm * 4) / (p->L + 1))), p->L + 1);
+        if (p->leg3_big)
+            XFB_LAUNCH(p, PG_LEGENDRE, st,
+                       legendre3_inverse_kernel<LEG2_IR, LEG2_IST, 16, 4><<<g2, 256, legendre3_inv_smem(p->NP), st>>>(c_in, p->A0, p->IE, p->IO, S, p->L,
+                                                                                                                   p->n_theta, p->NP, herm));
+        else
+            XFB_LAUNCH(p, PG_LEGENDRE, st,
+                       legendre3_inverse_kernel<LEG2_IR, LEG2_IST, 8, 2><<<g2, 128, legendre3_inv_smem(p->NP), st>>>(c_in, p->A0, p->IE, p->IO, S, p->L,
                                                                                                                   p->n_theta, p->NP, herm));
     } else {
     dim3 g(cdiv(S, herm ? 32 : 16), p->L + 1);
