@@ -186,17 +186,15 @@ static inline size_t legendre_inv_smem(int n_theta, int NP) {
 }
 
 // =====================================================================================================================
-// v2 kernels for the common small configuration (n_theta <= 64, L <= 63: K2 <= 32, NP <= 32) -- the L=63 / 64 x 128
-// workload of the bench.  One CTA keeps the Legendre tables of ONE order m in shared memory and walks over many groups
-// of shells; the phi-Fourier rows (forward) / coefficient rows (inverse) of the NEXT group are fetched with cp.async
-// while the current group is multiplied, so HBM loads stay in flight all the time (the v1 kernels stall on their one
-// load phase per CTA: ncu long-scoreboard 6.9 of 16 cycles per issue).  The north/south fold is done on the fly when the
-// A fragments are read (2 x 128-bit shared loads give e = x + y and o = x - y for re and im at once).
-//   rows of a group: 16 shells x (+m, -m)   or, pos_only (real field: c_{l,-m} = (-1)^m conj c_{l,m} is redundant) and
-//   for m = 0, 32 shells x (+m).
+// Pipelined kernels (n_theta <= 128, NP <= 64: the L=63 / 64 x 128 workload of the bench and L=127 / 128 x 256).  One CTA
+// works on ONE order m and walks over many groups of shells; the phi-Fourier rows (forward) / coefficient rows (inverse)
+// of the NEXT groups are fetched with cp.async while the current group is multiplied, so HBM loads stay in flight all
+// the time (the v1 kernels above stall on their one load phase per CTA: ncu long-scoreboard 6.9 of 16 cycles per
+// issue).  The north/south fold is done on the fly when the A fragments are read (2 x 128-bit shared loads give
+// e = x + y and o = x - y for re and im at once).
+//   rows of a group: 8 shells x (+m, -m)   or, pos_only (real field: c_{l,-m} = (-1)^m conj c_{l,m} is redundant) and
+//   for m = 0, 16 shells x (+m).
 // =====================================================================================================================
-#define LEG2_THREADS 256
-#define LEG2_ROWS 32
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     const int bytes = valid ? 16 : 0;                     // src-size 0: zero fill
@@ -208,106 +206,10 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 #define LEG2_FR 16          // forward: rows per group (8 shells x +-m, or 16 shells)
 #define LEG2_FST 3          // forward: cp.async stages (2 groups in flight per CTA, 3 CTAs per SM)
-static inline size_t legendre2_fwd_smem(int n_theta) {
-    return (size_t)LEG2_FST * LEG2_FR * (n_theta + 4) * sizeof(double2) + (size_t)2 * (n_theta / 2) * LEG_LDB * sizeof(double);
-}
 #define LEG2_IR 16          // inverse: rows per group
 #define LEG2_IST 3          // inverse: cp.async stages
-static inline size_t legendre2_inv_smem(int NP) {
-    return (size_t)LEG2_IST * 2 * LEG2_IR * (NP + 4) * sizeof(double2) + (size_t)2 * NP * LEG_LDB * sizeof(double);
-}
 
-template <int R, int ST>
-__global__ void __launch_bounds__(LEG2_THREADS, 3) legendre2_forward_kernel(const double2* __restrict__ a, double2* __restrict__ c,
-                                                                           const double* __restrict__ FE, const double* __restrict__ FO,
-                                                                           int S, int l_max, int n_theta, int NP, int pos_only) {
-    extern __shared__ __align__(16) unsigned char smem_leg2[];
-    constexpr int MB = R / 16;                             // 8-row MMA blocks per warp
-    const int K2 = n_theta >> 1;
-    const int RS = n_theta + 4;                            // row stride (double2): rows 64 B apart mod 128 -> conflict-free fragments
-    double2* raw = reinterpret_cast<double2*>(smem_leg2);  // [ST][R][RS]
-    double* Be = reinterpret_cast<double*>(raw + ST * R * RS);          // [K2][LEG_LDB]
-    double* Bo = Be + K2 * LEG_LDB;
-    const int m = blockIdx.y;
-    const int M2 = 2 * l_max + 1;
-    const bool both = (!pos_only) && m > 0;
-    const int SH = both ? R / 2 : R;                       // shells per group
-    const int n_groups = (S + SH - 1) / SH;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ar = lane >> 2, ak = lane & 3;
-    const int wn = warp & 3, r0 = (warp >> 2) * (R / 2);
-    const int ne = (l_max - m) / 2 + 1, no = (l_max - m + 1) / 2;
-    const bool do_e = wn * 8 < ne, do_o = wn * 8 < no;     // column blocks that are pure padding are skipped
-
-    auto fetch = [&](int g, int buf) {
-        if (g < n_groups) {
-            double2* dst = raw + (size_t)buf * R * RS;
-            for (int item = tid; item < R * n_theta; item += LEG2_THREADS) {
-                const int row = item / n_theta, j = item - row * n_theta;
-                const int sh = g * SH + (both ? (row % (R / 2)) : row), sign = both ? (row / (R / 2)) : 0;
-                const bool ok = sh < S;
-                const int mm = sign ? (M2 - m) : m;
-                cp_async16(dst + row * RS + j, a + ((size_t)(ok ? sh : 0) * M2 + mm) * n_theta + j, ok);
-            }
-        }
-        cp_async_commit();                                 // (possibly empty) group: keeps the wait count uniform
-    };
-
-    // a CTA walks over a CONTIGUOUS range of shell groups: its stores to one coefficient row (l, m) are adjacent in time
-    // and address, so L2 merges them into long DRAM bursts
-    const int per_cta = (n_groups + gridDim.x - 1) / gridDim.x;
-    int g = blockIdx.x * per_cta;
-    const int g_end = min(n_groups, g + per_cta);
-    if (g >= g_end) return;
-#pragma unroll
-    for (int s = 0; s < ST - 1; ++s) fetch(g + s < g_end ? g + s : n_groups, s);
-    const double* FEm = FE + (size_t)m * K2 * NP;
-    const double* FOm = FO + (size_t)m * K2 * NP;
-    for (int item = tid; item < K2 * LEG_NB; item += LEG2_THREADS) {
-        const int j = item / LEG_NB, cc = item - j * LEG_NB;
-        const bool ok = cc < NP;
-        Be[j * LEG_LDB + cc] = ok ? __ldg(FEm + (size_t)j * NP + cc) : 0.0;
-        Bo[j * LEG_LDB + cc] = ok ? __ldg(FOm + (size_t)j * NP + cc) : 0.0;
-    }
-    int buf = 0;
-    for (; g < g_end; ++g) {
-        cp_async_wait<ST - 2>();                           // the oldest outstanding group (this one) has landed
-        __syncthreads();                                   // ... for every thread; and everyone is done with the buffer refilled next
-        fetch(g + ST - 1 < g_end ? g + ST - 1 : n_groups, (buf + ST - 1) % ST);
-        const double2* rw = raw + (size_t)buf * R * RS;
-        double ere[MB][2] = {}, eim[MB][2] = {}, ore_[MB][2] = {}, oim[MB][2] = {};
-        for (int k0 = 0; k0 < K2; k0 += 4) {
-            const double be = Be[(k0 + ak) * LEG_LDB + wn * 8 + ar], bo = Bo[(k0 + ak) * LEG_LDB + wn * 8 + ar];
-#pragma unroll
-            for (int mb = 0; mb < MB; ++mb) {
-                const double2* rr = rw + (r0 + mb * 8 + ar) * RS;
-                const double2 x = rr[k0 + ak], y = rr[n_theta - 1 - k0 - ak];
-                if (do_e) { dmma884(ere[mb][0], ere[mb][1], x.x + y.x, be); dmma884(eim[mb][0], eim[mb][1], x.y + y.y, be); }
-                if (do_o) { dmma884(ore_[mb][0], ore_[mb][1], x.x - y.x, bo); dmma884(oim[mb][0], oim[mb][1], x.y - y.y, bo); }
-            }
-        }
-#pragma unroll
-        for (int mb = 0; mb < MB; ++mb) {
-            const int row = r0 + mb * 8 + ar;
-            const int sh = g * SH + (both ? (row % (R / 2)) : row), sign = both ? (row / (R / 2)) : 0;
-            if (sh >= S) continue;
-            const double sg = (sign && (m & 1)) ? -1.0 : 1.0;          // (-1)^m on the -m rows
-            const int ms = sign ? -m : m;
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                const int col = wn * 8 + 2 * ak + cc;
-                const int le = m + 2 * col, lo = le + 1;
-                if (do_e && le <= l_max) c[(size_t)(le * (le + 1) + ms) * S + sh] = make_double2(sg * ere[mb][cc], sg * eim[mb][cc]);
-                if (do_o && lo <= l_max) c[(size_t)(lo * (lo + 1) + ms) * S + sh] = make_double2(sg * ore_[mb][cc], sg * oim[mb][cc]);
-            }
-        }
-        buf = (buf + 1) % ST;
-    }
-}
-
-
-// v3 forward: the same pipeline as legendre2_forward_kernel, but the table fragments live in REGISTERS and a warp owns two
-// 8-column blocks.  The tables FE / FO of the CTA's order m are constant over its whole life, and an 8 x 4 x 8 DMMA takes
+// v3 forward: the table fragments live in REGISTERS and a warp owns two 8-column blocks.  The tables FE / FO of the CTA's order m are constant over its whole life, and an 8 x 4 x 8 DMMA takes
 // its B operand one double per lane: K2 / 4 (<= 8) k-steps x 2 column blocks x 2 parities = 32 doubles per lane, loaded
 // once from L2.  Per k-step a warp then reads only its two A rows (x at theta_j, y at the mirrored node: 2 x 128-bit
 // shared loads) and issues 8 DMMAs, against 4 DMMAs per (2 x 128-bit + 2 x 64-bit) loads before: 1 instead of 3 shared
@@ -416,107 +318,9 @@ __global__ void __launch_bounds__(64 * NCG, KS <= 8 ? 4 : 1) legendre3_forward_k
 }
 
 
-// inverse (synthesis) counterpart: coefficients c [(L+1)^2][S] -> phi-Fourier rows a [S][M2][n_theta] for one order m per CTA.
-// The coefficient rows of the next shell groups are gathered with cp.async (16-byte elements, 8 / 16 consecutive shells
-// of one (l, +-m) row are contiguous) while the current group is multiplied with the resident tables IE / IO [NP][K2].
-template <int R, int ST>
-__global__ void __launch_bounds__(LEG2_THREADS, 3) legendre2_inverse_kernel(const double2* __restrict__ c, double2* __restrict__ a,
-                                                                           const double* __restrict__ IE, const double* __restrict__ IO,
-                                                                           int S, int l_max, int n_theta, int NP, int pos_only) {
-    extern __shared__ __align__(16) unsigned char smem_leg2[];
-    const int K2 = n_theta >> 1;
-    const int RS = NP + 4;                                 // row stride (double2): rows 64 B apart mod 128
-    double2* raw = reinterpret_cast<double2*>(smem_leg2);  // [ST][2 parities][R][RS]
-    double* Be = reinterpret_cast<double*>(raw + ST * 2 * R * RS);      // [NP][LEG_LDB]
-    double* Bo = Be + NP * LEG_LDB;
-    const int m = blockIdx.y;
-    const int M2 = 2 * l_max + 1;
-    const bool both = (!pos_only) && m > 0;
-    const int SH = both ? R / 2 : R;
-    const int n_groups = (S + SH - 1) / SH;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ar = lane >> 2, ak = lane & 3;
-    const int wn = warp & 3, r0 = (warp >> 2) * (R / 2);
-    const int ne = (l_max - m) / 2 + 1, no = (l_max - m + 1) / 2;
-    const int Ke = (ne + 3) & ~3, Ko = (no + 3) & ~3;      // contraction only over existing degrees (zero padded)
-    const bool jok = wn * 8 < K2;
-
-    auto fetch = [&](int g, int buf) {
-        if (g < n_groups) {
-            double2* dst = raw + (size_t)buf * 2 * R * RS;
-            for (int item = tid; item < 2 * NP * R; item += LEG2_THREADS) {
-                const int shl = item % SH;                 // shells fastest: contiguous 16-byte elements of one coefficient row
-                int rest = item / SH;
-                const int sign = both ? (rest & 1) : 0;
-                if (both) rest >>= 1;
-                const int i = rest % NP, par = rest / NP;
-                const int l = m + par + 2 * i;
-                const int sh = g * SH + shl;
-                const bool ok = (l <= l_max) && (sh < S);
-                const int row = sign * (R / 2) + shl;
-                cp_async16(dst + ((size_t)par * R + row) * RS + i, c + (size_t)(ok ? l * (l + 1) + (sign ? -m : m) : 0) * S + (ok ? sh : 0), ok);
-            }
-        }
-        cp_async_commit();
-    };
-
-    const int per_cta = (n_groups + gridDim.x - 1) / gridDim.x;
-    int g = blockIdx.x * per_cta;
-    const int g_end = min(n_groups, g + per_cta);
-    if (g >= g_end) return;
-#pragma unroll
-    for (int s_ = 0; s_ < ST - 1; ++s_) fetch(g + s_ < g_end ? g + s_ : n_groups, s_);
-    const double* IEm = IE + (size_t)m * NP * K2;
-    const double* IOm = IO + (size_t)m * NP * K2;
-    for (int item = tid; item < NP * LEG_NB; item += LEG2_THREADS) {
-        const int i = item / LEG_NB, cc = item - i * LEG_NB;
-        const bool ok = cc < K2;
-        Be[i * LEG_LDB + cc] = ok ? __ldg(IEm + (size_t)i * K2 + cc) : 0.0;
-        Bo[i * LEG_LDB + cc] = ok ? __ldg(IOm + (size_t)i * K2 + cc) : 0.0;
-    }
-    int buf = 0;
-    for (; g < g_end; ++g) {
-        cp_async_wait<ST - 2>();
-        __syncthreads();
-        fetch(g + ST - 1 < g_end ? g + ST - 1 : n_groups, (buf + ST - 1) % ST);
-        const double2* ce = raw + (size_t)buf * 2 * R * RS + (size_t)(r0 + ar) * RS;
-        const double2* co = ce + (size_t)R * RS;
-        double ere[2] = {}, eim[2] = {}, ore_[2] = {}, oim[2] = {};
-        if (jok) {
-            for (int k0 = 0; k0 < Ke; k0 += 4) {
-                const double2 x = ce[k0 + ak];
-                const double be = Be[(k0 + ak) * LEG_LDB + wn * 8 + ar];
-                dmma884(ere[0], ere[1], x.x, be);
-                dmma884(eim[0], eim[1], x.y, be);
-            }
-            for (int k0 = 0; k0 < Ko; k0 += 4) {
-                const double2 x = co[k0 + ak];
-                const double bo = Bo[(k0 + ak) * LEG_LDB + wn * 8 + ar];
-                dmma884(ore_[0], ore_[1], x.x, bo);
-                dmma884(oim[0], oim[1], x.y, bo);
-            }
-            const int row = r0 + ar;
-            const int sh = g * SH + (both ? (row % (R / 2)) : row), sign = both ? (row / (R / 2)) : 0;
-            if (sh < S) {
-                const double sg = (sign && (m & 1)) ? -1.0 : 1.0;      // (-1)^m on the -m rows
-                const int mm = sign ? (M2 - m) : m;
-                double2* dst = a + ((size_t)sh * M2 + mm) * n_theta;
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int j = wn * 8 + 2 * ak + cc;
-                    if (j < K2) {
-                        dst[j] = make_double2(sg * (ere[cc] + ore_[cc]), sg * (eim[cc] + oim[cc]));
-                        dst[n_theta - 1 - j] = make_double2(sg * (ere[cc] - ore_[cc]), sg * (eim[cc] - oim[cc]));
-                    }
-                }
-            }
-        }
-        buf = (buf + 1) % ST;
-    }
-}
-
-
-// v3 inverse: table fragments in registers, two 8-node blocks per warp (see legendre3_forward_kernel): per k-step one 128-bit
+// v3 inverse (synthesis) counterpart: coefficients c [(L+1)^2][S] -> phi-Fourier rows a [S][M2][n_theta] for one order m per
+// CTA; the coefficient rows of the next shell groups are gathered with cp.async (8 / 16 consecutive shells of one (l, +-m) row
+// are contiguous).  Table fragments in registers, two 8-node blocks per warp (see legendre3_forward_kernel): per k-step one 128-bit
 // shared load feeds 4 DMMAs.   128 threads: warp = (row block of 8 rows) x (node-block pair cg: theta_j, j = 16 cg + 0..15)
 static inline size_t legendre3_inv_smem(int NP) { return (size_t)LEG2_IST * 2 * LEG2_IR * (NP + 4) * sizeof(double2); }
 
