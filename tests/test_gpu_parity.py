@@ -103,6 +103,31 @@ def test_elementwise_golden(case):
     assert (sw != g['sw_mask']).mean() < 1e-3
 
 
+def test_modified_intensity_corner_cases(case):
+    """project_to_modified_intensity (fxs_Projections.py:899-909) on crafted points: negative / zero / tiny / huge projected
+    intensities and vanishing rho_hat -- zeros, infs and NaNs land exactly where numpy puts them (the device multiplier is
+    two rsqrt sequences instead of a division and a square root; only SUBNORMAL operands are treated as zero)."""
+    g, sd, m, plan = case
+    rng = np.random.default_rng(5)
+    rh = (rng.normal(size=plan.grid_shape) + 1j * rng.normal(size=plan.grid_shape))
+    ip = rng.random(plan.grid_shape) * 3.0 + 0j
+    flat_r, flat_i = rh.reshape(-1), ip.reshape(-1)
+    flat_r[0:4] = [0.0, 0.0, 1e-160 + 0j, 3.0 - 4.0j]          # |rho_hat|^2 = 0, 0, underflow to 0, 25
+    flat_i[0:4] = [2.0, 0.0, 1.0, -1.0]                        # -> NaN (0 * inf), NaN, inf / NaN components, 0 (masked)
+    flat_r[4:8] = [1e-120 + 1e-120j, 1e120 - 1e120j, 2.0 + 0j, -1.0 + 1.0j]
+    flat_i[4:8] = [1e-250, 1e250, 0.0, 1e-300]                 # tiny / huge ratios, zero intensity, tiny normal intensity
+    with np.errstate(all='ignore'):
+        ref = m.rp.project_to_modified_intensity(rh.copy(), (rh * rh.conj()).real.copy(), ip.copy())
+    got = N(plan.modify_intensity(T(rh)[None], T(ip)[None]))[0]
+    r, q = ref.reshape(-1), got.reshape(-1)
+    for part in (np.real, np.imag):
+        a, b = part(r), part(q)
+        assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(np.isinf(a), np.isinf(b))
+        assert np.array_equal(a == 0.0, b == 0.0)
+        fin = np.isfinite(a)
+        assert np.allclose(a[fin], b[fin], rtol=4e-15, atol=0.0)
+
+
 @pytest.mark.parametrize('tag', ['ref_small_ftstab', 'ref_small_plain'])
 def test_full_loop_against_reference_golden(tag):
     from xframe_b200.plan import Plan
