@@ -95,3 +95,15 @@ __device__ __forceinline__ double mod_intensity_multiplier(double ni, double sq)
     const double b = (ni >= tiny) ? ni * rsqrt_pos(ni) : 0.0;                                        // sqrt(ni)
     return (sq >= 0.0 && ni >= 0.0) ? a * b : 0.0;
 }
+
+// 256-bit global store of two consecutive complex values (sm_100: STG.E.256); p must be 32-byte aligned
+__device__ __forceinline__ void st_global_256(double2* p, double2 a, double2 b) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+}
+// 256-bit global loads of two consecutive complex values (LDG.E.256); p must be 32-byte aligned.  _nc: read-only data
+__device__ __forceinline__ void ld_global_256_nc(const double2* p, double2& a, double2& b) {
+    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+}
+__device__ __forceinline__ void ld_global_256(const double2* p, double2& a, double2& b) {
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p) : "memory");
+}

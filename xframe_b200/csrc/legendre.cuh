@@ -417,16 +417,18 @@ __global__ void __launch_bounds__(64 * NCG, KS <= 8 ? 4 : 1) legendre3_inverse_k
                 const double sg = (sign && (m & 1)) ? -1.0 : 1.0;      // (-1)^m on the -m rows
                 const int mm = sign ? (M2 - m) : m;
                 double2* dst = a + ((size_t)sh * M2 + mm) * n_theta;
+                // a lane holds the nodes j, j + 1 (j even): one 256-bit store for the northern pair and one for the mirrored
+                // southern pair (n_theta - 2 - j, n_theta - 1 - j); n_theta is a multiple of 8, so both are 32-byte aligned
 #pragma unroll
-                for (int nb = 0; nb < 2; ++nb)
-#pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) {
-                        const int j = (2 * cg + nb) * 8 + 2 * ak + cc;
-                        if (jok[nb] && j < K2) {
-                            dst[j] = make_double2(sg * (ere[nb][cc] + ore_[nb][cc]), sg * (eim[nb][cc] + oim[nb][cc]));
-                            dst[n_theta - 1 - j] = make_double2(sg * (ere[nb][cc] - ore_[nb][cc]), sg * (eim[nb][cc] - oim[nb][cc]));
-                        }
+                for (int nb = 0; nb < 2; ++nb) {
+                    const int j = (2 * cg + nb) * 8 + 2 * ak;
+                    if (jok[nb] && j < K2) {
+                        st_global_256(dst + j, make_double2(sg * (ere[nb][0] + ore_[nb][0]), sg * (eim[nb][0] + oim[nb][0])),
+                                      make_double2(sg * (ere[nb][1] + ore_[nb][1]), sg * (eim[nb][1] + oim[nb][1])));
+                        st_global_256(dst + n_theta - 2 - j, make_double2(sg * (ere[nb][1] - ore_[nb][1]), sg * (eim[nb][1] - oim[nb][1])),
+                                      make_double2(sg * (ere[nb][0] - ore_[nb][0]), sg * (eim[nb][0] - oim[nb][0])));
                     }
+                }
             }
         }
         buf = (buf + 1) % ST;

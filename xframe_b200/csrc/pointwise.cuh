@@ -145,8 +145,9 @@ __global__ void __launch_bounds__(RU_THREADS) real_update_kernel(const double2* 
         for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
             const long long i0 = q << 2;
             double2 v[4], pr[4], trt[4], trt0[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { v[u] = ldg2(ri + i0 + u); pr[u] = rp[i0 + u]; }
+            // 256-bit accesses: a thread's 64 contiguous bytes of an array are two full 32-byte sectors per instruction
+            ld_global_256_nc(ri + i0, v[0], v[1]); ld_global_256_nc(ri + i0 + 2, v[2], v[3]);
+            ld_global_256(rp + i0, pr[0], pr[1]); ld_global_256(rp + i0 + 2, pr[2], pr[3]);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 trt[u] = (rt && i0 >= shell) ? ldg2(rt + i0 + u) : zero2;
@@ -154,8 +155,10 @@ __global__ void __launch_bounds__(RU_THREADS) real_update_kernel(const double2* 
             }
             const uchar4 s4 = *reinterpret_cast<const uchar4*>(sup + i0), n4m = __ldg(reinterpret_cast<const uchar4*>(init_support + i0));
             const uint8_t sb[4] = {s4.x, s4.y, s4.z, s4.w}, ib[4] = {n4m.x, n4m.y, n4m.z, n4m.w};
+            double2 o[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) rn[i0 + u] = point(i0 + u, v[u], pr[u], trt[u], trt0[u], sb[u], ib[u]);
+            for (int u = 0; u < 4; ++u) o[u] = point(i0 + u, v[u], pr[u], trt[u], trt0[u], sb[u], ib[u]);
+            st_global_256(rn + i0, o[0], o[1]); st_global_256(rn + i0 + 2, o[2], o[3]);
         }
     } else {
         for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_run; i += (long long)gridDim.x * blockDim.x) {
