@@ -150,7 +150,7 @@ __device__ __forceinline__ JBlockPair jacobi_block_pair(int i, int r, int nblkp)
 // rb[JROT_STEPS*4].x = 1 if anything rotated.
 template <int NV2>
 __device__ __forceinline__ void jacobi_g_pass(double* Gs, int ldg, const int* __restrict__ list, int nact, JBlockPair bp, bool intra,
-                                              double thr, double tol, double2* rb) {
+                                              double thr, double tol, double2* rb, double* nrm2) {
     const int lane = threadIdx.x & 31, grp = lane >> 3, sub = lane & (JG - 1);
     const int ba = bp.ba, bb = bp.bb;
     const int pa = ba * 4 + grp;                                   // position of A_g in the active list
@@ -162,7 +162,10 @@ __device__ __forceinline__ void jacobi_g_pass(double* Gs, int ldg, const int* __
     double2 x[NV2], y[NV2];
     jacobi_load_col<NV2>(x, Gs, (long long)ca * ldg, sub, va);
     jacobi_load_col<NV2>(y, Gs, (long long)(vb0 ? list[pb0] : 0) * ldg, sub, vb0);
-    double nx = jacobi_col_norm2<NV2>(x), ny = jacobi_col_norm2<NV2>(y);      // cached squared norms, travel with the columns
+    // squared norms: computed once per sweep (jacobi_active_list), then carried in nrm2 [column] and updated by every
+    // rotation (|x'|^2 = |x|^2 - tan(theta) x.y), as LAPACK's one-sided Jacobi does; they travel with the columns
+    const int cb0 = vb0 ? list[pb0] : 0;
+    double nx = va ? nrm2[ca] : 0.0, ny = vb0 ? nrm2[cb0] : 0.0;
     if (intra) {
 #pragma unroll
         for (int t = 0; t < 3; ++t) {                             // pairs inside A: partner group = grp ^ (t+1)
@@ -219,7 +222,12 @@ __device__ __forceinline__ void jacobi_g_pass(double* Gs, int ldg, const int* __
         }
     }
     jacobi_store_col<NV2>(x, Gs, (long long)ca * ldg, sub, va);
-    jacobi_store_col<NV2>(y, Gs, (long long)(vb3 ? list[pb3] : 0) * ldg, sub, vb3);
+    const int cb3 = vb3 ? list[pb3] : 0;
+    jacobi_store_col<NV2>(y, Gs, (long long)cb3 * ldg, sub, vb3);
+    if (sub == 0) {
+        if (va) nrm2[ca] = nx;
+        if (vb3) nrm2[cb3] = ny;
+    }
     any_rot = __any_sync(0xffffffffu, any_rot);
     if (lane == 0) rb[JROT_STEPS * 4] = make_double2(any_rot ? 1.0 : 0.0, 0.0);
 }
@@ -294,7 +302,7 @@ __device__ __forceinline__ bool jacobi_w_pass(double* Wb, int wld, bool w_compac
 __host__ __device__ inline int jrot_slots(int threads) { return threads >= 512 ? 16 : 32; }
 template <int NV2, int WV2>
 __device__ __forceinline__ void jacobi_sweep_blocked(double* Gs, int ldg, double* Wb, int wld, bool w_compact, const int* __restrict__ list,
-                                                     int nact, double thr, double tol, double2* rotbuf, int* s_rot) {
+                                                     int nact, double thr, double tol, double2* rotbuf, int* s_rot, double* nrm2) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int JROT_SLOTS = jrot_slots(blockDim.x);
     const int nblk = (nact + 3) >> 2;
@@ -306,7 +314,7 @@ __device__ __forceinline__ void jacobi_sweep_blocked(double* Gs, int ldg, double
             for (int i = warp; i < half; i += nwarp) {                     // warp-uniform
                 const JBlockPair bp = jacobi_block_pair(i, r, nblkp);
                 double2* rb = rotbuf + (size_t)(i % JROT_SLOTS) * JROT_RB;
-                jacobi_g_pass<NV2>(Gs, ldg, list, nact, bp, r == 0, thr, tol, rb);
+                jacobi_g_pass<NV2>(Gs, ldg, list, nact, bp, r == 0, thr, tol, rb, nrm2);
                 __syncwarp();
                 rotated |= jacobi_w_pass<WV2>(Wb, wld, w_compact, list, nact, bp, r == 0, rb);
                 __syncwarp();
@@ -319,7 +327,7 @@ __device__ __forceinline__ void jacobi_sweep_blocked(double* Gs, int ldg, double
             if (warp < ng) {
                 if (r < rounds)
                     jacobi_g_pass<NV2>(Gs, ldg, list, nact, jacobi_block_pair(warp, r, nblkp), r == 0, thr, tol,
-                                       rotbuf + (size_t)((r & 1) * JROT_SLOTS + warp) * JROT_RB);
+                                       rotbuf + (size_t)((r & 1) * JROT_SLOTS + warp) * JROT_RB, nrm2);
             } else if (r > 0) {
                 for (int i = warp - ng; i < half; i += nw)
                     rotated |= jacobi_w_pass<WV2>(Wb, wld, w_compact, list, nact, jacobi_block_pair(i, r - 1, nblkp), r == 1,
@@ -337,16 +345,16 @@ __device__ __forceinline__ void jacobi_sweep_blocked(double* Gs, int ldg, double
 // cover ceil(len / 16) double2 per lane only.
 template <int MAXV2>
 __device__ __forceinline__ void jacobi_sweep_dispatch(double* Gs, double* Wb, int ld, int len, bool w_compact, const int* list, int nact,
-                                                      double thr, double tol, double2* rotbuf, int* s_rot) {
+                                                      double thr, double tol, double2* rotbuf, int* s_rot, double* nrm2) {
     if constexpr (MAXV2 >= 16) {
-        if (len > 128) { jacobi_sweep_blocked<16, 16>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot); return; }
+        if (len > 128) { jacobi_sweep_blocked<16, 16>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot, nrm2); return; }
     }
-    if (len <= 32) jacobi_sweep_blocked<2, 2>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
-    else if (len <= 48) jacobi_sweep_blocked<3, 3>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
-    else if (len <= 64) jacobi_sweep_blocked<4, 4>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
-    else if (len <= 80) jacobi_sweep_blocked<5, 5>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
-    else if (len <= 96) jacobi_sweep_blocked<6, 6>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
-    else jacobi_sweep_blocked<8, 8>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot);
+    if (len <= 32) jacobi_sweep_blocked<2, 2>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot, nrm2);
+    else if (len <= 48) jacobi_sweep_blocked<3, 3>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot, nrm2);
+    else if (len <= 64) jacobi_sweep_blocked<4, 4>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot, nrm2);
+    else if (len <= 80) jacobi_sweep_blocked<5, 5>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot, nrm2);
+    else if (len <= 96) jacobi_sweep_blocked<6, 6>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot, nrm2);
+    else jacobi_sweep_blocked<8, 8>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot, nrm2);
 }
 
 __device__ __forceinline__ void jacobi_col_norms(const double* Gs, int ldg, int n, double* nrm2);
@@ -525,7 +533,7 @@ __device__ __forceinline__ int jacobi_qr_problem(const double* __restrict__ g, i
         const int nact = *s_nact;
         const double thr = *s_thr;
         if (nact < 2) break;
-        jacobi_sweep_dispatch<MAXV2>(C, B, ldl, r, false, list2, nact, thr, tol, rotbuf, s_rot);
+        jacobi_sweep_dispatch<MAXV2>(C, B, ldl, r, false, list2, nact, thr, tol, rotbuf, s_rot, nrm2);
         __syncthreads();
         const int rotated = *s_rot;
         __syncthreads();
@@ -655,7 +663,7 @@ __global__ void __launch_bounds__(THREADS, 1) procrustes_jacobi_kernel(const dou
                 }
                 __syncthreads();
             }
-            jacobi_sweep_dispatch<MAXV2>(Gs, w_smem ? Ws : pp, ldg, ldg, w_smem, list, nact, thr, tol, rotbuf, &s_rot);
+            jacobi_sweep_dispatch<MAXV2>(Gs, w_smem ? Ws : pp, ldg, ldg, w_smem, list, nact, thr, tol, rotbuf, &s_rot, nrm2);
             if (w_smem) {
                 for (int i = tid; i < nact * (ldg / 2); i += THREADS) {
                     const int a = i / (ldg / 2), e = i - a * (ldg / 2);
