@@ -205,9 +205,16 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 #define LEG2_FR 16          // forward: rows per group (8 shells x +-m, or 16 shells)
-#define LEG2_FST 3          // forward: cp.async stages (2 groups in flight per CTA, 3 CTAs per SM)
+#ifndef LEG2_FST
+#define LEG2_FST 3          // forward: cp.async stages (2 groups in flight per CTA)
+#endif
 #define LEG2_IR 16          // inverse: rows per group
+#ifndef LEG2_IST
 #define LEG2_IST 3          // inverse: cp.async stages
+#endif
+#ifndef LEG3_WAVES
+#define LEG3_WAVES 8        // CTAs per order m: this many waves of the resident CTAs over the whole grid (2 .. 32 measured: 3.72, 3.67, 3.62, 3.60, 3.62 ms)
+#endif
 
 // v3 forward: the table fragments live in REGISTERS and a warp owns two 8-column blocks.  The tables FE / FO of the CTA's order m are constant over its whole life, and an 8 x 4 x 8 DMMA takes
 // its B operand one double per lane: K2 / 4 (<= 8) k-steps x 2 column blocks x 2 parities = 32 doubles per lane, loaded

@@ -330,8 +330,8 @@ static int sht_forward_i(xfb_plan* p, SlotView in, int shells_per_run, double2* 
     XFB_LAUNCH(p, PG_FFT, st, if (launch_fft(true, p->n_phi, in, shells_per_run, sub, p->A0, p->tw, S, p->n_theta, p->L, st, half | (square ? 2 : 0))) return 1);
     if (p->leg2) {     // small configuration: table-resident, cp.async double-buffered kernel
         const int groups = cdiv(S, half ? LEG2_FR : LEG2_FR / 2);
-        // 4 waves of the resident CTAs (4 per SM for the small instantiation, 1 for the big one)
-        dim3 g2(std::min(groups, std::max(1, ((p->leg3_big ? 1 : 4) * p->n_sm * 4) / (p->L + 1))), p->L + 1);
+        // LEG3_WAVES waves of the resident CTAs (4 per SM for the small instantiation, 1 for the big one)
+        dim3 g2(std::min(groups, std::max(1, ((p->leg3_big ? 1 : 4) * p->n_sm * LEG3_WAVES) / (p->L + 1))), p->L + 1);
         if (p->leg3_big)
             XFB_LAUNCH(p, PG_LEGENDRE, st,
                        legendre3_forward_kernel<LEG2_FR, LEG2_FST, 16, 4><<<g2, 256, legendre3_fwd_smem(p->n_theta), st>>>(p->A0, c_out, p->FE, p->FO, S, p->L,
@@ -365,7 +365,7 @@ static int sht_inverse_i(xfb_plan* p, const double2* c_in, double2* grid_out, in
     // herm (3-D): the coefficients belong to a real field and only m >= 0 is valid in c_in
     if (p->leg2) {
         const int groups = cdiv(S, herm ? LEG2_IR : LEG2_IR / 2);
-        dim3 g2(std::min(groups, std::max(1, ((p->leg3_big ? 1 : 4) * p->n_sm * 4) / (p->L + 1))), p->L + 1);
+        dim3 g2(std::min(groups, std::max(1, ((p->leg3_big ? 1 : 4) * p->n_sm * LEG3_WAVES) / (p->L + 1))), p->L + 1);
         if (p->leg3_big)
             XFB_LAUNCH(p, PG_LEGENDRE, st,
                        legendre3_inverse_kernel<LEG2_IR, LEG2_IST, 16, 4><<<g2, 256, legendre3_inv_smem(p->NP), st>>>(c_in, p->A0, p->IE, p->IO, S, p->L,
