@@ -83,7 +83,10 @@ struct RealDesc {
 //   projection chain                                                                         fxs_Projections.py:72-130
 //   HIO: where(mask, rho_prev - beta (rho_new - proj), proj) ; ER: proj                      fxs_IO_methods.py:56-68
 //   partial[b][block][0..1] = sum w |rho_new-proj|^2 , sum w |rho_new|^2 over the error region
-__global__ void __launch_bounds__(RU_THREADS) real_update_kernel(const double2* __restrict__ rho_ift, const double2* __restrict__ rho_rt,
+#ifndef RU_MINB
+#define RU_MINB 2
+#endif
+__global__ void __launch_bounds__(RU_THREADS, RU_MINB) real_update_kernel(const double2* __restrict__ rho_ift, const double2* __restrict__ rho_rt,
                                                                  SlotView rho_prev, SlotView rho_next, const uint8_t* __restrict__ support,
                                                                  const int* __restrict__ support_slot, long long support_slot_stride,
                                                                  const int* __restrict__ enforce, const uint8_t* __restrict__ init_support,
