@@ -6,6 +6,10 @@
 #include "legendre.cuh"
 #include "gemm.cuh"
 #include "procrustes.cuh"
+
+#ifndef RU_WAVES
+#define RU_WAVES 32   // real_update / shrink-wrap reductions: CTAs per launch = RU_WAVES x 148 (split over the runs)
+#endif
 #include "polar.cuh"
 
 #include <algorithm>
@@ -582,9 +586,6 @@ static int real_update_i(xfb_plan* p, int method, double beta, const double2* rh
     if (!p->has_real) XFB_FAIL("real projection options not set (xfb_plan_set_real)");
     if (ensure_reduce_alloc(p)) return 1;
     // blocks per run: RU_WAVES x 148 CTAs per launch (8 .. 128 measured at 128 runs: 1.27, 1.23, 1.18, 1.20, 1.24 ms)
-    #ifndef RU_WAVES
-#define RU_WAVES 32
-#endif
     int bpr = std::max(1, std::min(p->red_blocks, (148 * RU_WAVES + nb - 1) / nb));
     bpr = (int)std::min<long long>(bpr, cdiv64(p->G, RU_THREADS));
     XFB_LAUNCH(p, PG_REAL_UPDATE, st,
@@ -605,9 +606,6 @@ static int shrinkwrap_i(xfb_plan* p, SlotView rho, double sigma, double threshol
     XFB_LAUNCH(p, PG_POINTWISE, st,
                mul_gauss_kernel<<<dim3(nb * p->n_r, (int)std::min<long long>(cdiv64(shell, 256), 8)), 256, 0, st>>>(p->W1, p->q_pts, sigma, p->n_r, shell));
     if (ft_i(p, 1, flat_view(p->W1, p->G), p->W0, nb, st)) return 1;
-    #ifndef RU_WAVES
-#define RU_WAVES 32
-#endif
     int bpr = std::max(1, std::min(p->red_blocks, (148 * RU_WAVES + nb - 1) / nb));
     XFB_LAUNCH(p, PG_POINTWISE, st, sw_minmax_kernel<<<dim3(bpr, nb), 256, 0, st>>>(p->W0, p->G, p->partial));
     XFB_LAUNCH(p, PG_MISC, st, sw_minmax_final_kernel<<<nb, 32, 0, st>>>(p->partial, bpr, p->mm));
