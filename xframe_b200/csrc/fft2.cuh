@@ -61,7 +61,19 @@ struct Fft2Cfg {
 
 // grid [S][n_theta][N] -> a [S][M2][n_theta]
 template <int N1, int N2>
-__global__ void __launch_bounds__(256) fft2_forward_kernel(SlotView grid, int shells_per_run, const double2* __restrict__ sub_flat,
+// minimum CTAs per SM of the launch bounds (= register budget).  Measured per step of 128 runs, phi-FFT group: forward 2 /
+// fused-epilogue inverse 2 / plain inverse 2 -> 4.57 ms;  3 / 3 / 2 -> 4.99;  2 / 3 / 2 -> 4.73;  3 / 2 / 2 -> 4.90;
+// 4 / 3 / 2 -> 5.57 (spills);  2 / 2 / 1 -> 5.18;  1 / 1 / 1 -> 6.03.
+#ifndef FFT2_FWD_MINB
+#define FFT2_FWD_MINB 2
+#endif
+#ifndef FFT2_MOD_MINB
+#define FFT2_MOD_MINB 2
+#endif
+#ifndef FFT2_INV_MINB
+#define FFT2_INV_MINB 2
+#endif
+__global__ void __launch_bounds__(256, FFT2_FWD_MINB) fft2_forward_kernel(SlotView grid, int shells_per_run, const double2* __restrict__ sub_flat,
                                                            double2* __restrict__ a, const double2* __restrict__ tw_g, int n_theta,
                                                            int l_max, int flags) {
     // flags: bit 0 = real input, write only m >= 0;  bit 1 = transform |x|^2 instead of x (square_grid fused, misk.py:159-168)
@@ -120,7 +132,7 @@ __global__ void __launch_bounds__(256) fft2_forward_kernel(SlotView grid, int sh
 template <int N1, int N2, bool MOD>
 // mod_rho_hat != nullptr: the transform output is I_proj and the kernel writes the modified-intensity density instead
 // (project_to_modified_intensity fused, fxs_Projections.py:899-909): mod_out[x] = rho_hat[x] sqrt(Re I_proj[x] / |rho_hat[x]|^2)
-__global__ void __launch_bounds__(256, MOD ? 3 : 2) fft2_inverse_kernel(const double2* __restrict__ a, double2* __restrict__ grid,
+__global__ void __launch_bounds__(256, MOD ? FFT2_MOD_MINB : FFT2_INV_MINB) fft2_inverse_kernel(const double2* __restrict__ a, double2* __restrict__ grid,
                                                            const double2* __restrict__ tw_g, int n_theta, int l_max, int herm,
                                                            const double2* __restrict__ mod_rho_hat, SlotView mod_out, int shells_per_run) {
     using C = Fft2Cfg<N1, N2>;
