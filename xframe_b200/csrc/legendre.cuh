@@ -212,6 +212,9 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 #ifndef LEG2_IST
 #define LEG2_IST 3          // inverse: cp.async stages
 #endif
+#ifndef LEG3_MINB
+#define LEG3_MINB 4         // CTAs per SM of the small instantiation (register budget 128)
+#endif
 #ifndef LEG3_WAVES
 #define LEG3_WAVES 8        // CTAs per order m: this many waves of the resident CTAs over the whole grid (2 .. 32 measured: 3.72, 3.67, 3.62, 3.60, 3.62 ms)
 #endif
@@ -227,7 +230,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 static inline size_t legendre3_fwd_smem(int n_theta) { return (size_t)LEG2_FST * LEG2_FR * (n_theta + 4) * sizeof(double2); }
 
 template <int R, int ST, int KS, int NCG>
-__global__ void __launch_bounds__(64 * NCG, KS <= 8 ? 4 : 1) legendre3_forward_kernel(const double2* __restrict__ a, double2* __restrict__ c,
+__global__ void __launch_bounds__(64 * NCG, KS <= 8 ? LEG3_MINB : 1) legendre3_forward_kernel(const double2* __restrict__ a, double2* __restrict__ c,
                                                                            const double* __restrict__ FE, const double* __restrict__ FO,
                                                                            int S, int l_max, int n_theta, int NP, int pos_only) {
     static_assert(R == 16, "two row blocks of 8 rows x NCG column-block pairs");
@@ -332,7 +335,7 @@ __global__ void __launch_bounds__(64 * NCG, KS <= 8 ? 4 : 1) legendre3_forward_k
 static inline size_t legendre3_inv_smem(int NP) { return (size_t)LEG2_IST * 2 * LEG2_IR * (NP + 4) * sizeof(double2); }
 
 template <int R, int ST, int KS, int NCG>
-__global__ void __launch_bounds__(64 * NCG, KS <= 8 ? 4 : 1) legendre3_inverse_kernel(const double2* __restrict__ c, double2* __restrict__ a,
+__global__ void __launch_bounds__(64 * NCG, KS <= 8 ? LEG3_MINB : 1) legendre3_inverse_kernel(const double2* __restrict__ c, double2* __restrict__ a,
                                                                            const double* __restrict__ IE, const double* __restrict__ IO,
                                                                            int S, int l_max, int n_theta, int NP, int pos_only) {
     static_assert(R == 16, "two row blocks of 8 rows x NCG node-block pairs");
