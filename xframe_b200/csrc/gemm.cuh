@@ -115,7 +115,10 @@ __device__ __forceinline__ void hk_cp_async16(void* smem, const void* gmem, bool
 }
 // ldw: leading dimension of the weight rows (>= n_r, even); accumulate: out += result (second pass of a complex matrix,
 // used by the 2-D DFT: X (C -+ i S) = X C -+ i (X S)).
-__global__ void __launch_bounds__(256, 2) hankel2_kernel(const double2* __restrict__ in, double2* __restrict__ out,
+#ifndef HK2_MINB
+#define HK2_MINB 2           // CTAs per SM (register budget): 1 / 2 / 3 measured at 3.21 / 2.42 / 2.78 ms per step
+#endif
+__global__ void __launch_bounds__(256, HK2_MINB) hankel2_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                                                          const double* __restrict__ W, const HankelTile* __restrict__ tiles,
                                                          int n_r, int n_sum, int skip, double scale, int inverse, int ldw, int accumulate) {
     extern __shared__ __align__(16) unsigned char smem_hk[];
