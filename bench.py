@@ -107,6 +107,10 @@ def algorithmic_bytes(nb):
         # fft: 6 launches move 6 grids + 5 phi-Fourier arrays + 1 extra grid (rho_hat read by the fused modified-intensity epilogue)
         'fft_phi': nb * (7 * G + 5 * A) / 6 * 16,
         'legendre': nb * (A + C) * 5 / 6 * 16,
+        # chunked transform (phi-FFT + Legendre back to back per chunk, the phi-Fourier intermediate stays in L2): per step
+        # 6 transforms move 8 grids (rho; rho_hat; rho_hat for |.|^2; rho_hat + rho_hat' of the fused modified intensity;
+        # rho_hat' and rho_hat of the fused difference; the final density) and 5 coefficient arrays (two of the six are half spectra)
+        'sht': nb * (8 * G + 5 * C) / 6 * 16,
         'hankel': nb * 2 * C * 16,
         'real_update': nb * (3 * G * 16 + G),  # IFT(rho_hat'-rho_hat), rho_prev in, rho_next out, support mask (fused ft_stab)
         'pointwise': nb * int(2.5 * G * 16),   # square: G in, G out ; modify_intensity: 2G in, G out  -> average per launch

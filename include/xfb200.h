@@ -110,6 +110,8 @@ int64_t xfb_plan_workspace_bytes(const xfb_plan* p);
 /* ft_stab sketch (reconstruct.py:584-593): 1 (default) evaluates IFT(rho_hat') + (rho - IFT(rho_hat)) as
  * IFT(rho_hat' - rho_hat) + rho (linearity; one inverse transform instead of two), 0 follows the sketch literally. */
 int xfb_plan_set_fused_ft_stab(xfb_plan* p, int32_t on);
+/* L2-resident phi-Fourier intermediate: runs per transform chunk (0 = unchunked) and streams (1..4) the chunks are spread over */
+int xfb_plan_set_sht_chunk(xfb_plan* p, int32_t runs_per_chunk, int32_t streams);
 /* diagnostics: Jacobi sweeps of the last projection, host array [n_batch][n_active_orders]; orders_out lists the orders */
 int xfb_debug_jacobi_sweeps(xfb_plan* p, int32_t* out_host, int32_t capacity, int32_t* n_orders_out, int32_t* orders_out);
 

@@ -107,3 +107,16 @@ __device__ __forceinline__ void ld_global_256_nc(const double2* p, double2& a, d
 __device__ __forceinline__ void ld_global_256(const double2* p, double2& a, double2& b) {
     asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p) : "memory");
 }
+
+// cudaFuncSetAttribute is per device: a process may hold plans on several GPUs (Plan(device=...)), so the "already set"
+// flags are kept per device index.
+struct XfbPerDeviceOnce { bool done[64] = {}; };
+static inline bool xfb_first_on_device(XfbPerDeviceOnce& f) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (f.done[dev]) return false;
+    f.done[dev] = true;
+    return true;
+}
+

@@ -157,11 +157,10 @@ static int launch_fft_n(bool forward, SlotView in, int shells_per_run, const dou
     dim3 g(n_shells, n_theta / th);
     // dynamic smem can exceed 48 KB: opt in once per instantiation, sized for the largest theta block
     const int smem_max = (int)((size_t)(N + 16 * xfb_fft_rowlen(N)) * sizeof(double2));
-    static bool attr_done = false;
-    if (!attr_done) {
+    static XfbPerDeviceOnce attr_once;
+    if (xfb_first_on_device(attr_once)) {
         XFB_CUDA(cudaFuncSetAttribute(fft_phi_forward_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         XFB_CUDA(cudaFuncSetAttribute(fft_phi_inverse_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-        attr_done = true;
     }
     if (forward)
         fft_phi_forward_kernel<N><<<g, 256, smem, st>>>(in, shells_per_run, sub, out, tw, n_theta, l_max, th, half);

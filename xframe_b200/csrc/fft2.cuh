@@ -204,12 +204,11 @@ template <int N1, int N2>
 static int launch_fft2(bool forward, SlotView in, int shells_per_run, const double2* sub, double2* out, const double2* tw, int n_shells,
                        int n_theta, int l_max, cudaStream_t st, int half, const double2* mod_rho_hat, SlotView mod_out) {
     using C = Fft2Cfg<N1, N2>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static XfbPerDeviceOnce attr_once;
+    if (xfb_first_on_device(attr_once)) {
         XFB_CUDA(cudaFuncSetAttribute(fft2_forward_kernel<N1, N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         XFB_CUDA(cudaFuncSetAttribute(fft2_inverse_kernel<N1, N2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         XFB_CUDA(cudaFuncSetAttribute(fft2_inverse_kernel<N1, N2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        attr_done = true;
     }
     dim3 g(n_shells, n_theta / C::TH);
     if (forward)

@@ -232,7 +232,9 @@ static inline size_t legendre3_fwd_smem(int n_theta) { return (size_t)LEG2_FST *
 template <int R, int ST, int KS, int NCG>
 __global__ void __launch_bounds__(64 * NCG, KS <= 8 ? LEG3_MINB : 1) legendre3_forward_kernel(const double2* __restrict__ a, double2* __restrict__ c,
                                                                            const double* __restrict__ FE, const double* __restrict__ FO,
-                                                                           int S, int l_max, int n_theta, int NP, int pos_only) {
+                                                                           int S, int l_max, int n_theta, int NP, int pos_only, long long c_stride) {
+    // S: shells handled by this launch (rows of a);  c_stride: shells per coefficient row of c (>= S: a launch may cover
+    // a chunk of the batch, c then points at the chunk's first shell)
     static_assert(R == 16, "two row blocks of 8 rows x NCG column-block pairs");
     constexpr int LEG3_THREADS = 64 * NCG;
     extern __shared__ __align__(16) unsigned char smem_leg2[];
@@ -318,8 +320,8 @@ __global__ void __launch_bounds__(64 * NCG, KS <= 8 ? LEG3_MINB : 1) legendre3_f
                     for (int cc = 0; cc < 2; ++cc) {
                         const int col = (2 * cg + nb) * 8 + 2 * ak + cc;
                         const int le = m + 2 * col, lo = le + 1;
-                        if (do_e[nb] && le <= l_max) c[(size_t)(le * (le + 1) + ms) * S + sh] = make_double2(sg * ere[nb][cc], sg * eim[nb][cc]);
-                        if (do_o[nb] && lo <= l_max) c[(size_t)(lo * (lo + 1) + ms) * S + sh] = make_double2(sg * ore_[nb][cc], sg * oim[nb][cc]);
+                        if (do_e[nb] && le <= l_max) c[(size_t)(le * (le + 1) + ms) * c_stride + sh] = make_double2(sg * ere[nb][cc], sg * eim[nb][cc]);
+                        if (do_o[nb] && lo <= l_max) c[(size_t)(lo * (lo + 1) + ms) * c_stride + sh] = make_double2(sg * ore_[nb][cc], sg * oim[nb][cc]);
                     }
             }
         }
@@ -337,7 +339,7 @@ static inline size_t legendre3_inv_smem(int NP) { return (size_t)LEG2_IST * 2 * 
 template <int R, int ST, int KS, int NCG>
 __global__ void __launch_bounds__(64 * NCG, KS <= 8 ? LEG3_MINB : 1) legendre3_inverse_kernel(const double2* __restrict__ c, double2* __restrict__ a,
                                                                            const double* __restrict__ IE, const double* __restrict__ IO,
-                                                                           int S, int l_max, int n_theta, int NP, int pos_only) {
+                                                                           int S, int l_max, int n_theta, int NP, int pos_only, long long c_stride) {
     static_assert(R == 16, "two row blocks of 8 rows x NCG node-block pairs");
     constexpr int LEG3_THREADS = 64 * NCG;
     extern __shared__ __align__(16) unsigned char smem_leg2[];
@@ -371,7 +373,7 @@ __global__ void __launch_bounds__(64 * NCG, KS <= 8 ? LEG3_MINB : 1) legendre3_i
                 const int sh = g * SH + shl;
                 const bool ok = (l <= l_max) && (sh < S);
                 const int row = sign * (R / 2) + shl;
-                cp_async16(dst + ((size_t)par * R + row) * RS + i, c + (size_t)(ok ? l * (l + 1) + (sign ? -m : m) : 0) * S + (ok ? sh : 0), ok);
+                cp_async16(dst + ((size_t)par * R + row) * RS + i, c + (size_t)(ok ? l * (l + 1) + (sign ? -m : m) : 0) * c_stride + (ok ? sh : 0), ok);
             }
         }
         cp_async_commit();

@@ -17,9 +17,9 @@
 
 thread_local std::string g_xfb_err;
 
-enum ProfGroup { PG_FFT = 0, PG_LEGENDRE, PG_HANKEL, PG_PROC_GEMM, PG_PROC_JACOBI, PG_PROC_PACK, PG_POINTWISE, PG_REAL_UPDATE, PG_MISC, PG_COUNT };
+enum ProfGroup { PG_FFT = 0, PG_LEGENDRE, PG_HANKEL, PG_PROC_GEMM, PG_PROC_JACOBI, PG_PROC_PACK, PG_POINTWISE, PG_REAL_UPDATE, PG_MISC, PG_SHT, PG_COUNT };
 static const char* kProfNames[PG_COUNT] = {"fft_phi", "legendre", "hankel", "procrustes_gemm", "procrustes_jacobi",
-                                           "procrustes_pack", "pointwise", "real_update", "misc"};
+                                           "procrustes_pack", "pointwise", "real_update", "misc", "sht"};
 
 struct ProfEvent { cudaEvent_t a, b; int group; };
 
@@ -46,6 +46,12 @@ struct xfb_plan {
     bool leg2 = false;                              // v3 Legendre kernels (K2 <= 64, NP <= 64)
     bool leg3_big = false;                          // ... the <KS 16, NCG 4> instantiation (K2 > 32 or NP > 32)
     int half_spectrum = 1;                          // real intensity fields: transform only the m >= 0 half (3-D, v2 Legendre)
+    // L2-resident phi-Fourier intermediate: a transform is cut into chunks of sht_chunk runs; chunk i runs its phi-FFT and its
+    // Legendre kernel back to back on stream i % sht_streams and always through the same slot of A0, so the m-major
+    // intermediate `a` is written and re-read inside the L2 (126 MB) instead of travelling to HBM and back
+    int sht_chunk = 2, sht_streams = 3;
+    cudaStream_t sht_side[4] = {}; cudaEvent_t sht_fork = nullptr, sht_join[4] = {};
+    long long launches_side = 0;
     // host-buffer pipeline (xfb_mtip_step_host)
     cudaStream_t s_in = nullptr, s_out = nullptr; cudaEvent_t ev_start = nullptr; std::vector<cudaEvent_t> ev_in, ev_comp;
     double2* stage_out = nullptr; int host_chunk = 16;
@@ -215,6 +221,8 @@ int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
     if (dev_alloc(p, &p->A0s, B * p->M2 * p->n_theta)) return 1;
     if (dev_alloc(p, &p->C0s, B * p->NLM)) return 1;
     if (dev_alloc(p, &p->rt0, B * p->n_theta * p->n_phi)) return 1;
+    if (const char* e = getenv("XFB_SHT_CHUNK")) p->sht_chunk = std::max(0, atoi(e));          // experiments: sweep without rebuilding
+    if (const char* e = getenv("XFB_SHT_STREAMS")) p->sht_streams = std::min(4, std::max(1, atoi(e)));
     p->leg2 = (p->n_theta / 2 <= 64 && p->NP <= 64 && p->n_theta % 4 == 0);
     p->leg3_big = p->leg2 && (p->n_theta / 2 > 32 || p->NP > 32);
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, dev); }
@@ -243,6 +251,8 @@ int xfb_plan_destroy(xfb_plan* p) {
     if (p->ev_start) cudaEventDestroy(p->ev_start);
     if (p->s_in) cudaStreamDestroy(p->s_in);
     if (p->s_out) cudaStreamDestroy(p->s_out);
+    for (int i = 1; i < 4; ++i) { if (p->sht_side[i]) cudaStreamDestroy(p->sht_side[i]); if (p->sht_join[i]) cudaEventDestroy(p->sht_join[i]); }
+    if (p->sht_fork) cudaEventDestroy(p->sht_fork);
     delete p;
     return 0;
 }
@@ -304,6 +314,116 @@ static int dft2d_gemm_i(xfb_plan* p, const double2* rows_in, double2* rows_out, 
     return 0;
 }
 
+
+// ---- v3 Legendre launch + the chunked (L2-resident intermediate) transform -------------------------------------------
+// CTAs per order m for a launch over S shells: every CTA should walk over several shell groups (the cp.async ring needs a
+// few groups to hide the load latency and the table fragments are loaded once per CTA), and the whole grid should not
+// exceed LEG3_WAVES waves of the resident CTAs.  share: number of streams that run such launches concurrently.
+static int leg3_grid_x(const xfb_plan* p, int S, int pos_only, int share) {
+    const int groups = cdiv(S, pos_only ? LEG2_FR : LEG2_FR / 2);
+    const int resident = (p->leg3_big ? 1 : LEG3_MINB) * p->n_sm;
+    const int cap = std::max(1, (resident * LEG3_WAVES) / ((p->L + 1) * std::max(1, share)));
+    int gx = std::min(groups, cap);
+    if (share > 1) gx = std::max(1, std::min(gx, cdiv(groups, 4)));       // chunked launches: at least 4 groups per CTA
+    return gx;
+}
+// forward: a [S][M2][n_theta] -> c (+ chunk offset, row stride c_stride);  inverse: c -> a
+static int launch_legendre3(xfb_plan* p, bool forward, double2* a, double2* c, int S, long long c_stride, int pos_only, int gx, cudaStream_t st) {
+    dim3 g2(gx, p->L + 1);
+    if (forward) {
+        if (p->leg3_big)
+            legendre3_forward_kernel<LEG2_FR, LEG2_FST, 16, 4><<<g2, 256, legendre3_fwd_smem(p->n_theta), st>>>(a, c, p->FE, p->FO, S, p->L, p->n_theta, p->NP, pos_only, c_stride);
+        else
+            legendre3_forward_kernel<LEG2_FR, LEG2_FST, 8, 2><<<g2, 128, legendre3_fwd_smem(p->n_theta), st>>>(a, c, p->FE, p->FO, S, p->L, p->n_theta, p->NP, pos_only, c_stride);
+    } else {
+        if (p->leg3_big)
+            legendre3_inverse_kernel<LEG2_IR, LEG2_IST, 16, 4><<<g2, 256, legendre3_inv_smem(p->NP), st>>>(c, a, p->IE, p->IO, S, p->L, p->n_theta, p->NP, pos_only, c_stride);
+        else
+            legendre3_inverse_kernel<LEG2_IR, LEG2_IST, 8, 2><<<g2, 128, legendre3_inv_smem(p->NP), st>>>(c, a, p->IE, p->IO, S, p->L, p->n_theta, p->NP, pos_only, c_stride);
+    }
+    XFB_CUDA(cudaGetLastError());
+    return 0;
+}
+static inline int sht_chunk_shells(const xfb_plan* p) { return p->sht_chunk * p->n_r; }
+static bool sht_chunkable(const xfb_plan* p, int S, int shells_per_run) {
+    if (p->dims != 3 || !p->leg2 || p->sht_chunk < 1 || p->sht_streams < 1 || shells_per_run < 1) return false;
+    const int cs = sht_chunk_shells(p);
+    return S > cs && cs % shells_per_run == 0 && S % shells_per_run == 0 && 2 * p->sht_chunk <= p->max_batch;
+}
+static int sht_streams_init(xfb_plan* p) {
+    if (p->sht_fork) return 0;
+    XFB_CUDA(cudaEventCreateWithFlags(&p->sht_fork, cudaEventDisableTiming));
+    for (int i = 1; i < 4; ++i) {
+        XFB_CUDA(cudaStreamCreateWithFlags(&p->sht_side[i], cudaStreamNonBlocking));
+        XFB_CUDA(cudaEventCreateWithFlags(&p->sht_join[i], cudaEventDisableTiming));
+    }
+    return 0;
+}
+struct ShtFork {            // streams of one chunked transform: stream 0 is the caller's, the others are forked from / joined to it
+    xfb_plan* p; cudaStream_t st; int ns; bool used[4];
+    cudaStream_t stream(int k) const { return k ? p->sht_side[k] : st; }
+};
+static int sht_fork(xfb_plan* p, cudaStream_t st, int n_chunks, ShtFork* f) {
+    if (sht_streams_init(p)) return 1;
+    f->p = p; f->st = st;
+    f->ns = std::max(1, std::min(std::min(p->sht_streams, 4), std::min(n_chunks, p->max_batch / p->sht_chunk)));
+    XFB_CUDA(cudaEventRecord(p->sht_fork, st));
+    for (int k = 1; k < f->ns; ++k) XFB_CUDA(cudaStreamWaitEvent(p->sht_side[k], p->sht_fork, 0));
+    return 0;
+}
+static int sht_join(ShtFork* f) {
+    for (int k = 1; k < f->ns; ++k) {
+        XFB_CUDA(cudaEventRecord(f->p->sht_join[k], f->p->sht_side[k]));
+        XFB_CUDA(cudaStreamWaitEvent(f->st, f->p->sht_join[k], 0));
+    }
+    return 0;
+}
+static int sht_forward_chunked(xfb_plan* p, SlotView in, int spr, double2* c_out, int S, cudaStream_t st, const double2* sub, int half, int square) {
+    const int cs = sht_chunk_shells(p), n_chunks = cdiv(S, cs);
+    const size_t a_slot = (size_t)cs * p->M2 * p->n_theta;
+    const long long shell = (long long)p->n_theta * p->n_phi;
+    ShtFork f;
+    prof_begin(p, PG_SHT, st);
+    if (sht_fork(p, st, n_chunks, &f)) return 1;
+    for (int ci = 0, s0 = 0; s0 < S; ++ci, s0 += cs) {
+        const int k = ci % f.ns, Sc = std::min(cs, S - s0), b0 = s0 / spr;
+        cudaStream_t sk = f.stream(k);
+        SlotView v = in;
+        v.base += (long long)b0 * in.run_stride;
+        if (v.slot) v.slot += b0;
+        double2* a = p->A0 + (size_t)k * a_slot;
+        if (launch_fft(true, p->n_phi, v, spr, sub ? sub + (long long)s0 * shell : nullptr, a, p->tw, Sc, p->n_theta, p->L, sk, half | (square ? 2 : 0))) return 1;
+        if (launch_legendre3(p, true, a, c_out + s0, Sc, S, half, leg3_grid_x(p, Sc, half, f.ns), sk)) return 1;
+        p->launches += 2;
+    }
+    if (sht_join(&f)) return 1;
+    prof_end(p, st);
+    return 0;
+}
+static int sht_inverse_chunked(xfb_plan* p, const double2* c_in, double2* grid_out, int S, cudaStream_t st, int herm, const double2* mod_rho_hat,
+                               SlotView mod_out, int spr) {
+    const int cs = sht_chunk_shells(p), n_chunks = cdiv(S, cs);
+    const size_t a_slot = (size_t)cs * p->M2 * p->n_theta;
+    const long long shell = (long long)p->n_theta * p->n_phi;
+    ShtFork f;
+    prof_begin(p, PG_SHT, st);
+    if (sht_fork(p, st, n_chunks, &f)) return 1;
+    for (int ci = 0, s0 = 0; s0 < S; ++ci, s0 += cs) {
+        const int k = ci % f.ns, Sc = std::min(cs, S - s0), b0 = s0 / spr;
+        cudaStream_t sk = f.stream(k);
+        double2* a = p->A0 + (size_t)k * a_slot;
+        if (launch_legendre3(p, false, a, const_cast<double2*>(c_in) + s0, Sc, S, herm, leg3_grid_x(p, Sc, herm, f.ns), sk)) return 1;
+        SlotView mo = mod_out;
+        if (mod_rho_hat) { mo.base += (long long)b0 * mod_out.run_stride; if (mo.slot) mo.slot += b0; }
+        if (launch_fft(false, p->n_phi, flat_view(a, 0), spr, nullptr, grid_out + (long long)s0 * shell, p->tw, Sc, p->n_theta, p->L, sk, herm,
+                       mod_rho_hat ? mod_rho_hat + (long long)s0 * shell : nullptr, mo)) return 1;
+        p->launches += 2;
+    }
+    if (sht_join(&f)) return 1;
+    prof_end(p, st);
+    return 0;
+}
+
 // real_only: the input field is real.  2-D: rfft semantics.  3-D (v2 Legendre only): only the m >= 0 half of the spectrum
 // is produced (c_{l,-m} = (-1)^m conj c_{l,m} is redundant) -- the caller must consume m >= 0 only.  Returns the mode used
 // in *half_used.
@@ -331,19 +451,10 @@ static int sht_forward_i(xfb_plan* p, SlotView in, int shells_per_run, double2* 
     }
     const int half = (real_only && p->leg2 && p->half_spectrum) ? 1 : 0;
     if (half_used) *half_used = half;
+    if (sht_chunkable(p, S, shells_per_run)) return sht_forward_chunked(p, in, shells_per_run, c_out, S, st, sub, half, square);
     XFB_LAUNCH(p, PG_FFT, st, if (launch_fft(true, p->n_phi, in, shells_per_run, sub, p->A0, p->tw, S, p->n_theta, p->L, st, half | (square ? 2 : 0))) return 1);
     if (p->leg2) {     // small configuration: table-resident, cp.async double-buffered kernel
-        const int groups = cdiv(S, half ? LEG2_FR : LEG2_FR / 2);
-        // LEG3_WAVES waves of the resident CTAs (4 per SM for the small instantiation, 1 for the big one)
-        dim3 g2(std::min(groups, std::max(1, ((p->leg3_big ? 1 : 4) * p->n_sm * LEG3_WAVES) / (p->L + 1))), p->L + 1);
-        if (p->leg3_big)
-            XFB_LAUNCH(p, PG_LEGENDRE, st,
-                       legendre3_forward_kernel<LEG2_FR, LEG2_FST, 16, 4><<<g2, 256, legendre3_fwd_smem(p->n_theta), st>>>(p->A0, c_out, p->FE, p->FO, S, p->L,
-                                                                                                                       p->n_theta, p->NP, half));
-        else
-            XFB_LAUNCH(p, PG_LEGENDRE, st,
-                       legendre3_forward_kernel<LEG2_FR, LEG2_FST, 8, 2><<<g2, 128, legendre3_fwd_smem(p->n_theta), st>>>(p->A0, c_out, p->FE, p->FO, S, p->L,
-                                                                                                                      p->n_theta, p->NP, half));
+        XFB_LAUNCH(p, PG_LEGENDRE, st, if (launch_legendre3(p, true, p->A0, c_out, S, S, half, leg3_grid_x(p, S, half, 1), st)) return 1);
         return 0;
     }
     dim3 g(cdiv(S, 16), p->L + 1);
@@ -367,17 +478,9 @@ static int sht_inverse_i(xfb_plan* p, const double2* c_in, double2* grid_out, in
         return 0;
     }
     // herm (3-D): the coefficients belong to a real field and only m >= 0 is valid in c_in
+    if (sht_chunkable(p, S, shells_per_run)) return sht_inverse_chunked(p, c_in, grid_out, S, st, herm, mod_rho_hat, mod_out, shells_per_run);
     if (p->leg2) {
-        const int groups = cdiv(S, herm ? LEG2_IR : LEG2_IR / 2);
-        dim3 g2(std::min(groups, std::max(1, ((p->leg3_big ? 1 : 4) * p->n_sm * LEG3_WAVES) / (p->L + 1))), p->L + 1);
-        if (p->leg3_big)
-            XFB_LAUNCH(p, PG_LEGENDRE, st,
-                       legendre3_inverse_kernel<LEG2_IR, LEG2_IST, 16, 4><<<g2, 256, legendre3_inv_smem(p->NP), st>>>(c_in, p->A0, p->IE, p->IO, S, p->L,
-                                                                                                                   p->n_theta, p->NP, herm));
-        else
-            XFB_LAUNCH(p, PG_LEGENDRE, st,
-                       legendre3_inverse_kernel<LEG2_IR, LEG2_IST, 8, 2><<<g2, 128, legendre3_inv_smem(p->NP), st>>>(c_in, p->A0, p->IE, p->IO, S, p->L,
-                                                                                                                  p->n_theta, p->NP, herm));
+        XFB_LAUNCH(p, PG_LEGENDRE, st, if (launch_legendre3(p, false, p->A0, const_cast<double2*>(c_in), S, S, herm, leg3_grid_x(p, S, herm, 1), st)) return 1);
     } else {
     dim3 g(cdiv(S, herm ? 32 : 16), p->L + 1);
     XFB_LAUNCH(p, PG_LEGENDRE, st,
@@ -415,8 +518,8 @@ static int hankel_i(xfb_plan* p, int dir, const double2* c_in, double2* c_out, i
     p->hk_tiles = hit->second.first; p->hk_tiles_n = hit->second.second;
     dim3 g(p->hk_tiles_n, cdiv(p->n_r, HK_BN));
     if (p->n_r % 2 == 0) {
-        static bool attr_done = false;
-        if (!attr_done) { XFB_CUDA(cudaFuncSetAttribute(hankel2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hankel2_smem())); attr_done = true; }
+        static XfbPerDeviceOnce attr_once;
+        if (xfb_first_on_device(attr_once)) XFB_CUDA(cudaFuncSetAttribute(hankel2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hankel2_smem()));
         XFB_LAUNCH(p, PG_HANKEL, st,
                    hankel2_kernel<<<g, 256, hankel2_smem(), st>>>(c_in, c_out, p->hankel_w, p->hk_tiles, p->n_r, p->hankel_n_sum, p->hankel_skip,
                                                                  dir == 0 ? p->hk_fwd_scale : p->hk_inv_scale, dir, p->n_r, 0));
@@ -961,6 +1064,15 @@ int xfb_debug_jacobi_sweeps(xfb_plan* p, int32_t* out_host, int32_t capacity, in
 }
 
 int xfb_plan_set_fused_ft_stab(xfb_plan* p, int32_t on) { p->fused_ft_stab = (on && p->dims == 3) ? 1 : 0; return 0; }
+
+// L2-resident phi-Fourier intermediate: runs per chunk (0 = one launch over the whole batch, the round-1
+// behaviour) and number of streams the chunks are spread over (1 .. 4).
+int xfb_plan_set_sht_chunk(xfb_plan* p, int32_t runs_per_chunk, int32_t streams) {
+    if (!p) XFB_FAIL("null plan");
+    if (runs_per_chunk < 0 || streams < 1 || streams > 4) XFB_FAIL("sht chunk: runs_per_chunk >= 0 and 1 <= streams <= 4");
+    p->sht_chunk = runs_per_chunk; p->sht_streams = streams;
+    return 0;
+}
 
 int xfb_mtip_shrinkwrap(xfb_plan* p, double sigma, double threshold, double error_limit, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;

@@ -148,6 +148,10 @@ class Plan:
         """True (default): one inverse transform per ft_stab iteration (linearity of IFT); False: literal sketch."""
         _lib.check(self.lib.xfb_plan_set_fused_ft_stab(self.h, int(bool(on))))
 
+    def set_sht_chunk(self, runs_per_chunk, streams=3):
+        """L2-resident phi-Fourier intermediate: runs per transform chunk (0 = unchunked) and number of streams (1..4)."""
+        _lib.check(self.lib.xfb_plan_set_sht_chunk(self.h, int(runs_per_chunk), int(streams)))
+
     def jacobi_sweeps(self):
         """Diagnostics: (orders, sweeps[n_batch, n_orders]) of the last invariant projection."""
         cap = 4096 * 64
