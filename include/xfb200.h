@@ -82,7 +82,7 @@ typedef struct {
 } xfb_projection_desc;
 
 /* Real-space projection options (fxs_Projections.py:72-130, pythonLibrary.py:1289-1318). */
-enum { XFB_OP_SUPPORT = 1, XFB_OP_VALUE_THRESHOLD = 2, XFB_OP_LIMIT_IMAG = 3 };
+enum { XFB_OP_SUPPORT = 1, XFB_OP_VALUE_THRESHOLD = 2, XFB_OP_LIMIT_IMAG = 3, XFB_OP_AVERAGE_CENTER = 4 };
 typedef struct {
     int32_t n_ops;
     int32_t ops[4];               /* application order, XFB_OP_*                               */
@@ -91,6 +91,7 @@ typedef struct {
     double lo, hi;                /* value_threshold                                           */
     double imag_limit;            /* limit_imag threshold                                      */
     int32_t error_inside_initial_support;   /* fxs_IO_methods.py:287-300                       */
+    int32_t average_center_shells;          /* average_center.max_radial_id (fxs_Projections.py:96-110) */
 } xfb_real_desc;
 
 const char* xfb_last_error(void);

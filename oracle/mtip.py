@@ -468,8 +468,13 @@ class RealProjection:
                 im = data.imag
                 p = np.abs(im) >= t
                 im[p] = 0
-            else:
-                raise AssertionError(f'real projection {key} not restated')
+            elif key == 'average_center':          # :96-110: the first shells are replaced by their angular mean; mask False
+                thresh = int(self.opt['average_center'].get('max_radial_id', 1))
+                axes = tuple(range(1, data.ndim))
+                data[:thresh] = np.mean(data[:thresh], axis=axes).reshape((-1,) + (1,) * (data.ndim - 1))
+                p = False
+            else:                                  # :113-118: 'projection {} not known. Ignoring it.'
+                continue
             masks[key] = p
             mask = mask | p
         masks['all'] = mask

@@ -31,7 +31,7 @@ class ProjectionDesc(C.Structure):
 class RealDesc(C.Structure):
     _fields_ = [('n_ops', C.c_int32), ('ops', C.c_int32 * 4), ('hio_considered', C.c_int32 * 4),
                 ('use_lo', C.c_int32), ('use_hi', C.c_int32), ('lo', C.c_double), ('hi', C.c_double),
-                ('imag_limit', C.c_double), ('error_inside_initial_support', C.c_int32)]
+                ('imag_limit', C.c_double), ('error_inside_initial_support', C.c_int32), ('average_center_shells', C.c_int32)]
 
 
 EXPORTS = {

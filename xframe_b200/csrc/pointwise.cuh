@@ -68,12 +68,43 @@ __global__ void mul_gauss_kernel(double2* __restrict__ data, const double* __res
 
 struct RealDesc {
     int n_ops;
-    int ops[4];
+    int ops[4];          // 1 support, 2 value_threshold, 3 limit_imag, 4 average_center
     int considered[4];
     int use_lo, use_hi;
     double lo, hi, imag_limit;
     int err_inside;
+    int avg_shells;      // average_center: the first avg_shells radial shells are replaced by their angular mean (fxs_Projections.py:96-110)
 };
+
+// one step of the real projection chain on the value p of one grid point (fxs_Projections.py:72-130); returns "changed"
+__device__ __forceinline__ bool real_chain_op(const RealDesc& rd, int k, bool outside, double2& p, const double2* avg_mean, long long i,
+                                              long long shell) {
+    const int op = rd.ops[k];
+    if (op == 1) {
+        if (outside) { p = make_double2(0.0, 0.0); return true; }
+    } else if (op == 2) {
+        const bool lo = rd.use_lo && (p.x < rd.lo);
+        const bool hi = rd.use_hi && (p.x > rd.hi);
+        if (lo) p.x = rd.lo;
+        if (hi) p.x = rd.hi;
+        return lo || hi;
+    } else if (op == 3) {
+        if (fabs(p.y) >= rd.imag_limit) { p.y = 0.0; return true; }
+    } else if (op == 4) {
+        if (avg_mean && i < (long long)rd.avg_shells * shell) p = avg_mean[i / shell];     // mask of this projection is False (:102,106)
+    }
+    return false;
+}
+// rho_new of one grid point (see real_update_kernel)
+__device__ __forceinline__ double2 real_combine(double2 v, double2 prev, double2 t_rt, double2 t_rt0, bool has_rt, bool has_rt0, long long i,
+                                                long long shell) {
+    if (has_rt && i >= shell) { v.x += prev.x - t_rt.x; v.y += prev.y - t_rt.y; }
+    if (has_rt0) {      // fused ft_stab: rho_ift holds IFT(rho_hat' - rho_hat); add rho (r>=1) or shell 0 of IFT(rho_hat)
+        const double2 t = (i >= shell) ? prev : t_rt0;
+        v.x += t.x; v.y += t.y;
+    }
+    return v;
+}
 
 #define RU_THREADS 256
 // real_projection + HIO/ER + l2_projection_diff partial sums.
@@ -92,7 +123,7 @@ __global__ void __launch_bounds__(RU_THREADS, RU_MINB) real_update_kernel(const 
                                                                  const int* __restrict__ enforce, const uint8_t* __restrict__ init_support,
                                                                  const double* __restrict__ wt, RealDesc rd, int method, double beta,
                                                                  int n_theta, int n_phi, int wt_div, long long per_run, double* __restrict__ partial,
-                                                                 const double2* __restrict__ rt0) {
+                                                                 const double2* __restrict__ rt0, const double2* __restrict__ avg_mean) {
     const int b = blockIdx.y;
     const double2* ri = rho_ift + (long long)b * per_run;
     const double2* rt = rho_rt ? rho_rt + (long long)b * per_run : nullptr;
@@ -103,12 +134,9 @@ __global__ void __launch_bounds__(RU_THREADS, RU_MINB) real_update_kernel(const 
     const long long shell = (long long)n_theta * n_phi;
     double s_diff = 0.0, s_val = 0.0;
     // one grid point: combine, project, HIO/ER, error integrands
+    const double2* avg_b = avg_mean ? avg_mean + (long long)b * rd.avg_shells : nullptr;
     auto point = [&](long long i, double2 v, double2 prev, double2 t_rt, double2 t_rt0, uint8_t sup_i, uint8_t init_i) -> double2 {
-        if (rt && i >= shell) { v.x += prev.x - t_rt.x; v.y += prev.y - t_rt.y; }
-        if (rt0) {      // fused ft_stab: rho_ift holds IFT(rho_hat' - rho_hat); add rho (r>=1) or shell 0 of IFT(rho_hat)
-            const double2 t = (i >= shell) ? prev : t_rt0;
-            v.x += t.x; v.y += t.y;
-        }
+        v = real_combine(v, prev, t_rt, t_rt0, rt != nullptr, rt0 != nullptr, i, shell);
         const bool in_init = init_i != 0;
         const bool outside = enf ? (!in_init || sup_i == 0) : (sup_i == 0);
         double2 p = v;
@@ -116,19 +144,7 @@ __global__ void __launch_bounds__(RU_THREADS, RU_MINB) real_update_kernel(const 
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (k >= rd.n_ops) break;
-            bool changed = false;
-            const int op = rd.ops[k];
-            if (op == 1) {
-                if (outside) { p = make_double2(0.0, 0.0); changed = true; }
-            } else if (op == 2) {
-                const bool lo = rd.use_lo && (p.x < rd.lo);
-                const bool hi = rd.use_hi && (p.x > rd.hi);
-                if (lo) p.x = rd.lo;
-                if (hi) p.x = rd.hi;
-                changed = lo || hi;
-            } else if (op == 3) {
-                if (fabs(p.y) >= rd.imag_limit) { p.y = 0.0; changed = true; }
-            }
+            const bool changed = real_chain_op(rd, k, outside, p, avg_b, i, shell);
             if (rd.considered[k]) msel = msel || changed;
         }
         double2 o = p;
@@ -180,6 +196,45 @@ __global__ void __launch_bounds__(RU_THREADS, RU_MINB) real_update_kernel(const 
         for (int w = 0; w < RU_THREADS / 32; ++w) { a += red[0][w]; c += red[1][w]; }
         partial[((long long)b * gridDim.x + blockIdx.x) * 2 + 0] = a;
         partial[((long long)b * gridDim.x + blockIdx.x) * 2 + 1] = c;
+    }
+}
+
+// average_center (fxs_Projections.py:96-110): angular mean of the chain value at the position of the 'average_center'
+// entry (the operations before it applied) over each of the first rd.avg_shells shells; one CTA per (shell, run), fixed
+// summation order.  The real update then substitutes the mean at those points.
+__global__ void __launch_bounds__(256) average_center_kernel(const double2* __restrict__ rho_ift, const double2* __restrict__ rho_rt, SlotView rho_prev,
+                                                             const uint8_t* __restrict__ support, const int* __restrict__ support_slot,
+                                                             long long support_slot_stride, const int* __restrict__ enforce,
+                                                             const uint8_t* __restrict__ init_support, RealDesc rd, int n_theta, int n_phi,
+                                                             long long per_run, const double2* __restrict__ rt0, double2* __restrict__ avg_mean) {
+    const int r = blockIdx.x, b = blockIdx.y;
+    const long long shell = (long long)n_theta * n_phi;
+    const double2* ri = rho_ift + (long long)b * per_run;
+    const double2* rt = rho_rt ? rho_rt + (long long)b * per_run : nullptr;
+    const double2* rp = slot_run_ptr(rho_prev, b);
+    const uint8_t* sup = support + (support_slot ? (long long)support_slot[b] * support_slot_stride : 0ll) + (long long)b * per_run;
+    const bool enf = enforce ? (enforce[b] != 0) : true;
+    int k_avg = 0;
+    while (k_avg < rd.n_ops && rd.ops[k_avg] != 4) ++k_avg;
+    double sx = 0.0, sy = 0.0;
+    const double2 zero2 = make_double2(0.0, 0.0);
+    for (long long j = threadIdx.x; j < shell; j += blockDim.x) {
+        const long long i = (long long)r * shell + j;
+        const double2 t_rt = (rt && i >= shell) ? rt[i] : zero2;
+        const double2 t_rt0 = (rt0 && i < shell) ? rt0[(long long)b * shell + i] : zero2;
+        double2 p = real_combine(ri[i], rp[i], t_rt, t_rt0, rt != nullptr, rt0 != nullptr, i, shell);
+        const bool outside = enf ? (init_support[i] == 0 || sup[i] == 0) : (sup[i] == 0);
+        for (int k = 0; k < k_avg; ++k) real_chain_op(rd, k, outside, p, nullptr, i, shell);
+        sx += p.x; sy += p.y;
+    }
+    __shared__ double red[2][8];
+    sx = warp_sum(sx); sy = warp_sum(sy);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sx; red[1][threadIdx.x >> 5] = sy; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, c = 0.0;
+        for (int w = 0; w < 8; ++w) { a += red[0][w]; c += red[1][w]; }
+        avg_mean[(long long)b * rd.avg_shells + r] = make_double2(a / (double)shell, c / (double)shell);
     }
 }
 

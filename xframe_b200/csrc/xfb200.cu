@@ -46,10 +46,11 @@ struct xfb_plan {
     bool leg2 = false;                              // v3 Legendre kernels (K2 <= 64, NP <= 64)
     bool leg3_big = false;                          // ... the <KS 16, NCG 4> instantiation (K2 > 32 or NP > 32)
     int half_spectrum = 1;                          // real intensity fields: transform only the m >= 0 half (3-D, v2 Legendre)
-    // L2-resident phi-Fourier intermediate: a transform is cut into chunks of sht_chunk runs; chunk i runs its phi-FFT and its
-    // Legendre kernel back to back on stream i % sht_streams and always through the same slot of A0, so the m-major
-    // intermediate `a` is written and re-read inside the L2 (126 MB) instead of travelling to HBM and back
-    int sht_chunk = 2, sht_streams = 3;
+    // Chunked transform (experiment, OFF by default): a transform is cut into chunks of sht_chunk runs; chunk i runs its phi-FFT
+    // and its Legendre kernel back to back on stream i % sht_streams through the same slot of A0, so that the m-major
+    // intermediate `a` could stay inside the 126 MB L2.  Measured at 128 runs (profiles/r02a_sht_chunk_sweep.md): 9.2 - 13.5 ms
+    // per step for the six transforms against 8.24 ms unchunked -- the smaller launches lose more than the L2 hits gain.
+    int sht_chunk = 0, sht_streams = 3;
     cudaStream_t sht_side[4] = {}; cudaEvent_t sht_fork = nullptr, sht_join[4] = {};
     long long launches_side = 0;
     // host-buffer pipeline (xfb_mtip_step_host)
@@ -61,6 +62,7 @@ struct xfb_plan {
     // projection
     bool has_proj = false;
     std::vector<ProcOrder> orders;
+    std::vector<int> ncols_all;                     // columns of V_l as given, per order (also for zeroed / pass-through orders)
     ProcOrder* orders_dev = nullptr;
     int *kind_dev = nullptr, *act_index_dev = nullptr;
     uint8_t* radial_mask_dev = nullptr;
@@ -78,7 +80,7 @@ struct xfb_plan {
     int gemmM_tiles = 0, gemmT_tiles = 0, gemm_nb = -1, gemmM_tiles_run = 0, gemmT_tiles_run = 0;
     size_t jacobi_smem = 0; int n_sm = 148; bool jacobi_big = false; int* jac_counter = nullptr;
     // real projection
-    bool has_real = false; RealDesc rd{}; uint8_t* init_support_dev = nullptr;
+    bool has_real = false; RealDesc rd{}; uint8_t* init_support_dev = nullptr; double2* avg_mean = nullptr;
     // loop state
     double2 *rho_pool = nullptr, *rh_pool = nullptr; uint8_t* mask_pool = nullptr;
     LoopState ls{}; int* ls_ints = nullptr; double* ls_dbl = nullptr;
@@ -135,6 +137,9 @@ const char* xfb_last_error(void) { return g_xfb_err.c_str(); }
 int xfb_device_count(int* n) { XFB_CUDA(cudaGetDeviceCount(n)); return 0; }
 int xfb_set_device(int dev) { XFB_CUDA(cudaSetDevice(dev)); return 0; }
 
+int xfb_plan_destroy(xfb_plan* p);
+namespace { struct PlanGuard { xfb_plan* p; ~PlanGuard() { if (p) xfb_plan_destroy(p); } }; }   // failure paths free the plan and its buffers
+
 int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
     if (!out || !d) XFB_FAIL("null argument");
     const int dims = (d->dimensions == 2) ? 2 : 3;
@@ -153,6 +158,7 @@ int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
     XFB_CUDA(cudaGetDeviceCount(&ndev));
     if (ndev == 0) XFB_FAIL("no CUDA device: xfb200 has no CPU fallback");
     xfb_plan* p = new xfb_plan();
+    PlanGuard guard{p};
     p->dims = dims;
     p->L = d->l_max; p->n_r = d->n_r; p->n_theta = d->n_theta; p->n_phi = d->n_phi; p->max_batch = d->max_batch;
     p->hankel_skip = d->hankel_skip; p->hankel_n_sum = d->hankel_n_sum;
@@ -188,6 +194,7 @@ int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
         }
         XFB_CUDA(cudaFuncSetAttribute(dft2d_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dft_smem(p->n_phi)));
         XFB_CUDA(cudaFuncSetAttribute(dft2d_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dft_smem(p->n_phi)));
+        guard.p = nullptr;
         *out = p;
         return 0;
     }
@@ -196,7 +203,7 @@ int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
     p->n_hankel = p->L + 1; p->wt_div = p->n_phi;
     p->C = (long long)p->NLM * p->n_r;
     const size_t tab = (size_t)(p->L + 1) * p->K2 * p->NP;
-    if (d->legendre_len != (int64_t)(4 * tab)) { delete p; XFB_FAIL("legendre table length %lld != %lld", (long long)d->legendre_len, (long long)(4 * tab)); }
+    if (d->legendre_len != (int64_t)(4 * tab)) { XFB_FAIL("legendre table length %lld != %lld", (long long)d->legendre_len, (long long)(4 * tab)); }
     // twiddles exp(-2 pi i k / n) in extended precision
     std::vector<double2> tw(p->n_phi);
     for (int k = 0; k < p->n_phi; ++k) {
@@ -232,6 +239,7 @@ int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
     if (p->leg3_big) XFB_CUDA(cudaFuncSetAttribute(legendre3_inverse_kernel<LEG2_IR, LEG2_IST, 16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre3_inv_smem(p->NP)));
     XFB_CUDA(cudaFuncSetAttribute(legendre_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre_fwd_smem(p->n_theta)));
     XFB_CUDA(cudaFuncSetAttribute(legendre_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre_inv_smem(p->n_theta, p->NP)));
+    guard.p = nullptr;
     *out = p;
     return 0;
 }
@@ -241,7 +249,7 @@ int xfb_plan_destroy(xfb_plan* p) {
     void* ptrs[] = {p->tw, p->FE, p->FO, p->IE, p->IO, p->hankel_w, p->int_wt, p->q_pts, p->A0, p->C0, p->C1, p->W0, p->W1, p->W2, p->A0s, p->C0s, p->rt0, p->stage_out,
                     p->v2d, p->unk2d, p->dft_cs, p->T2a, p->T2b, p->orders_dev, p->kind_dev, p->act_index_dev, p->radial_mask_dev, p->v0_dev, p->pd_dev, p->vt_dev,
                     p->xt, p->tt, p->g, p->gn, p->vw, p->sigma, p->sweeps_dev, p->jac_counter, p->pp, p->gn_u, p->pp_u, p->sigma_u, p->i00, p->gemmY_dev, p->gemmY_tp, p->gemmM_dev, p->gemmT_dev, p->gemmM_tp, p->gemmT_tp,
-                    p->init_support_dev, p->rho_pool, p->rh_pool, p->mask_pool, p->ls_ints, p->ls_dbl, p->partial, p->err, p->mm};
+                    p->init_support_dev, p->avg_mean, p->rho_pool, p->rh_pool, p->mask_pool, p->ls_ints, p->ls_dbl, p->partial, p->err, p->mm};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& kv : p->hk_cache) cudaFree(kv.second.first);
     for (auto& kv : p->dft_tiles) cudaFree(kv.second.first);
@@ -691,10 +699,15 @@ static int real_update_i(xfb_plan* p, int method, double beta, const double2* rh
     // blocks per run: RU_WAVES x 148 CTAs per launch (8 .. 128 measured at 128 runs: 1.27, 1.23, 1.18, 1.20, 1.24 ms)
     int bpr = std::max(1, std::min(p->red_blocks, (148 * RU_WAVES + nb - 1) / nb));
     bpr = (int)std::min<long long>(bpr, cdiv64(p->G, RU_THREADS));
+    const bool has_avg = p->rd.avg_shells > 0;
+    if (has_avg)      // average_center: angular means of the first shells at that position of the chain (fxs_Projections.py:96-110)
+        XFB_LAUNCH(p, PG_REAL_UPDATE, st,
+                   average_center_kernel<<<dim3(p->rd.avg_shells, nb), 256, 0, st>>>(rho_ift, rho_rt, prev, support, support_slot, support_slot_stride, enforce,
+                                                                                   p->init_support_dev, p->rd, p->n_theta, p->n_phi, p->G, rt0, p->avg_mean));
     XFB_LAUNCH(p, PG_REAL_UPDATE, st,
                real_update_kernel<<<dim3(bpr, nb), RU_THREADS, 0, st>>>(rho_ift, rho_rt, prev, next, support, support_slot, support_slot_stride,
                                                                         enforce, p->init_support_dev, p->int_wt, p->rd, method, beta,
-                                                                        p->n_theta, p->n_phi, p->wt_div, p->G, p->partial, rt0));
+                                                                        p->n_theta, p->n_phi, p->wt_div, p->G, p->partial, rt0, has_avg ? p->avg_mean : nullptr));
     XFB_LAUNCH(p, PG_MISC, st, reduce_pairs_kernel<<<nb, 32, 0, st>>>(p->partial, bpr, err_out));
     return 0;
 }
@@ -729,8 +742,10 @@ int xfb_plan_set_projection(xfb_plan* p, const xfb_projection_desc* d) {
     XFB_CUDA(cudaMemcpy(q.data(), p->q_pts, n_r * sizeof(double), cudaMemcpyDeviceToHost));
     struct Tmp { int l, n_cols; std::vector<double> pd, vt; };
     std::vector<Tmp> tmp;
+    p->ncols_all.assign(L + 1, 0);
     for (int l = 0; l < d->n_orders && l <= L; ++l) {
         const int nc = d->n_cols[l];
+        p->ncols_all[l] = nc;
         const double* V = d->v[l];
         if (nc > n_r) XFB_FAIL("order %d: n_cols=%d exceeds N_r=%d", l, nc, n_r);
         if (l == 0) {
@@ -854,6 +869,18 @@ int xfb_plan_set_real(xfb_plan* p, const xfb_real_desc* d, const uint8_t* init_s
     for (int i = 0; i < 4; ++i) { p->rd.ops[i] = d->ops[i]; p->rd.considered[i] = d->hio_considered[i]; }
     p->rd.use_lo = d->use_lo; p->rd.use_hi = d->use_hi; p->rd.lo = d->lo; p->rd.hi = d->hi; p->rd.imag_limit = d->imag_limit;
     p->rd.err_inside = d->error_inside_initial_support;
+    p->rd.avg_shells = 0;
+    int n_avg = 0;
+    for (int i = 0; i < d->n_ops; ++i) {
+        if (d->ops[i] < XFB_OP_SUPPORT || d->ops[i] > XFB_OP_AVERAGE_CENTER) XFB_FAIL("real projection op %d unknown", d->ops[i]);
+        n_avg += d->ops[i] == XFB_OP_AVERAGE_CENTER;
+    }
+    if (n_avg > 1) XFB_FAIL("average_center may appear once in the real projection chain");
+    if (n_avg) {
+        // density[:thresh] with thresh = int(max_radial_id): numpy clips the slice to the N_r shells (fxs_Projections.py:97,101)
+        p->rd.avg_shells = std::max(0, std::min((int)d->average_center_shells, p->n_r));
+        if (p->rd.avg_shells > 0 && !p->avg_mean) { if (dev_alloc(p, &p->avg_mean, (size_t)p->max_batch * p->n_r)) return 1; }
+    }
     if (!p->init_support_dev) { if (dev_alloc(p, &p->init_support_dev, (size_t)p->G)) return 1; }
     XFB_CUDA(cudaMemcpy(p->init_support_dev, init_support_host, (size_t)p->G, cudaMemcpyHostToDevice));
     p->has_real = true;
@@ -913,8 +940,8 @@ int xfb_get_unknowns(xfb_plan* p, int32_t run, int32_t order, double* out_dev, v
         XFB_CUDA(cudaGetLastError());
         return 0;
     }
-    if (kd == ORD_ZERO) {   // PD_l = 0: numpy's svd of a zero matrix returns identity factors
-        const int n_l = std::min(p->n_r, n_c);
+    if (kd == ORD_ZERO) {   // PD_l = 0 [n_cols x N_r]: numpy's svd of the zero [n_cols x (2l+1)] matrix returns identity factors
+        const int n_l = p->ncols_all[order];
         unknown_identity_kernel<<<cdiv(n_l * n_c, 256), 256, 0, st>>>((double2*)out_dev, n_l, n_c);
         XFB_CUDA(cudaGetLastError());
         return 0;

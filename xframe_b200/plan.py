@@ -6,6 +6,7 @@ Shapes follow the reference:
   direct [nb, N_r, (L+1)^2]       complex128   (index l(l+1)+m; shtns_plugin.py:110-112,250-261)
 """
 import ctypes as C
+import logging
 
 import numpy as np
 import torch
@@ -13,7 +14,8 @@ import torch
 from . import _lib, tables
 
 HIO, ER = 0, 1
-_OPS = {'support': 1, 'value_threshold': 2, 'limit_imag': 3}
+_OPS = {'support': 1, 'value_threshold': 2, 'limit_imag': 3, 'average_center': 4}
+log = logging.getLogger('root')          # the reference's logger name (fxs_Projections.py:24)
 
 
 def _dp(a):
@@ -265,18 +267,26 @@ class Plan:
         return tuple(t.cpu().numpy() for t in out)
 
     def set_real(self, apply, initial_support, value_threshold=(0, False), limit_imag=2.0, considered=('all',),
-                 error_inside_initial_support=True):
-        """Options of RealProjection (fxs_Projections.py:72-130) and of the real l2 error (fxs_IO_methods.py:287-300)."""
+                 error_inside_initial_support=True, average_center_shells=1):
+        """Options of RealProjection (fxs_Projections.py:72-130) and of the real l2 error (fxs_IO_methods.py:287-300).
+        Names without a generate_<name>_projection in the reference are logged and ignored, as assemble_projection does
+        (fxs_Projections.py:113-118): the reference's own default `apply` list carries such a name ('assert_real')."""
         d = _lib.RealDesc()
-        apply = list(apply)
+        kept = []
+        for name in apply:
+            if name in _OPS:
+                kept.append(name)
+            else:
+                log.error('projection {} not known. Ignoring it.'.format(name))
+        apply = kept
         if len(apply) > 4:
             raise ValueError("at most 4 real projections")
+        self.real_projections = tuple(apply)
         d.n_ops = len(apply)
         for i, name in enumerate(apply):
-            if name not in _OPS:
-                raise _lib.XfbError(f"real projection '{name}' is not supported by xframe_b200 ({sorted(_OPS)})")
             d.ops[i] = _OPS[name]
             d.hio_considered[i] = 1 if ('all' in considered or name in considered) else 0
+        d.average_center_shells = int(average_center_shells)
 
         def num(v):
             return isinstance(v, (float, int)) and not isinstance(v, bool)

@@ -71,7 +71,8 @@ class ProjectWorker:
         inside = err['real'].get('l2_projection_diff', {}).get('inside_initial_support', False)
         hio = settings['projections']['real']['HIO']
         self.plan.set_real(popt['apply'], self.initial_support, popt.get('value_threshold', {}).get('threshold', (False, False)),
-                           popt.get('limit_imag', {}).get('threshold', 0.0), hio.get('considered_projections', ['all']), inside)
+                           popt.get('limit_imag', {}).get('threshold', 0.0), hio.get('considered_projections', ['all']), inside,
+                           average_center_shells=int(popt.get('average_center', {}).get('max_radial_id', 1)))
         base = settings['GPU'].get('seed', None)
         self.seeds = seeds if seeds is not None else [None if base is None else base + i for i in range(self.n_runs)]
         self.initial_densities = initial_densities
