@@ -19,7 +19,7 @@ import types
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))      # repo root (this file lives in baseline/)
 _CANDIDATES = (os.path.join(ROOT, 'baseline', '_ref'), '/root/reference')
 
 
@@ -83,19 +83,24 @@ def fresh_data(inv):
     average_intensity in place (fxs_Projections.py:668), so every MTIP gets its own copy."""
     from xframe.library.gridLibrary import SampledFunction, NestedArray
     data = dict(inv)
-    pm = np.empty(len(inv['data_projection_matrices']), dtype=object)
-    for i, p in enumerate(inv['data_projection_matrices']):
-        pm[i] = np.array(p, dtype=complex)
+    src = inv['data_projection_matrices']
+    if isinstance(src, np.ndarray) and src.dtype != object:        # 2-D: one array [M+1, n_q]
+        pm = np.array(src, dtype=complex)
+    else:                                                          # 3-D: one [n_q, n_l] matrix per order
+        pm = np.empty(len(src), dtype=object)
+        for i, p in enumerate(src):
+            pm[i] = np.array(p, dtype=complex)
     data['data_projection_matrices'] = pm
     data['average_intensity'] = SampledFunction(NestedArray(np.asarray(inv['data_radial_points'])[:, None].copy(), 1),
                                                 np.asarray(inv['average_intensity']).copy(), coord_sys='cartesian')
     return data
 
 
-def make_mtip(settings_dict, inv, rho0=None):
-    """Populate the reference's globals, build its MTIP object and phasing loop.  rho0: injected initial density (the
-    reference draws it from os.urandom, reconstruct.py:1119).  Returns (reconstruct module, MTIP instance)."""
-    from xframe.library.pythonLibrary import DictNamespace, RecipeFactory
+def preinit(settings_dict, inv):
+    """Master-process part (ProjectWorker.__init__, reconstruct.py:89-110): populate the reference's globals and run
+    MTIP.preinit() (grids, Fourier-transform weights -- its weight workers may only be requested from the master process,
+    Multiprocessing.py:813).  Returns the reconstruct module."""
+    from xframe.library.pythonLibrary import DictNamespace
     from xframe import settings
     import xframe.database as database
     settings.project = DictNamespace.dict_to_dictnamespace(settings_dict)
@@ -108,9 +113,23 @@ def make_mtip(settings_dict, inv, rho0=None):
     os.chdir(cwd)                                   # the module does os.chdir(plugin_dir) at import (reconstruct.py:7-9)
     rec.set_globals()
     rec.MTIP.preinit()
+    return rec
+
+
+def new_mtip(rec, inv, rho0=None):
+    """Per-reconstruction part (setup_phasing_loop, reconstruct.py:113-115,141-148; runs in the child processes of the
+    reference): a fresh MTIP object with its phasing loop.  rho0: injected initial density (the reference draws it from
+    os.urandom, reconstruct.py:1119)."""
+    from xframe.library.pythonLibrary import RecipeFactory
     if rho0 is not None:
         rec.MTIP.generate_density_guess_method = lambda self, spec, grid: (lambda: np.array(rho0, dtype=complex))
     rec.MTIP.mtip_data = fresh_data(inv)
     m = rec.MTIP(RecipeFactory({}))
     m.generate_phasing_loop()
-    return rec, m
+    return m
+
+
+def make_mtip(settings_dict, inv, rho0=None):
+    """preinit + new_mtip in one process.  Returns (reconstruct module, MTIP instance)."""
+    rec = preinit(settings_dict, inv)
+    return rec, new_mtip(rec, inv, rho0)

@@ -129,13 +129,48 @@ def hankel_flops(nb):
 
 
 # ------------------------------------------------------------------------------------------------
-# reference CPU path (oracle port) -- also the cpu_baseline leg of our arm
+# reference CPU path -- `--impl reference`, and the cpu_baseline leg of our arm
+#   kind "reference": the UNMODIFIED reference from baseline/_ref (installed by __graft_entry__.build()), its own MTIP object,
+#                     operator table and HIO_ft_stab routine (reconstruct.py:515-593,768-1036); the one third-party piece that
+#                     is absent from the image, shtns, is replaced at the reference's own plugin slot by the numpy restatement
+#                     oracle/sht.py (3-D only; the 2-D path needs no plugin)
+#   kind "port"     : the numpy oracle (oracle/mtip.py), only when baseline/_ref is missing
+# Process model of the reference: one single-threaded process per reconstruction (xframe/__init__.py:5-8, reconstruct.py:141-157),
+# here one on every usable host thread; each runs `warmup` untimed and `steps` timed iterations of its own run.
 # ------------------------------------------------------------------------------------------------
 _CPU = {}
 
 
-def _cpu_worker(args):
-    seed, budget_s = args
+def workload_text(total):
+    return (f'fxs {DIMS}D reconstruct: {total} independent MTIP runs (six-sphere tutorial model) at L={L_MAX}/N_r={N_R}, '
+            f'{N_THETA}x{N_PHI} angular grid, sharded over the GPUs; step = one HIO_ft_stab iteration of every run')
+
+
+def bench_settings():
+    from xframe_b200.settings import tutorial_settings
+    if DIMS == 2:
+        return tutorial_settings(dimensions=2, grid={'max_q': MAX_Q, 'max_order': L_MAX, 'n_radial_points': N_R})
+    return tutorial_settings(grid={'max_q': MAX_Q, 'max_order': L_MAX, 'n_phi': N_PHI, 'n_theta': N_THETA, 'n_radial_points': N_R})
+
+
+def _cpu_data():
+    """Invariants of the bench model from the oracle's helpers (input synthesis, not timed)."""
+    import numpy as np
+    from oracle import mtip as O
+    qs = O.radial_grids('midpoint', MAX_Q, N_R, 2.0)[1]
+    sd = bench_settings()
+    if DIMS == 2:
+        from oracle import mtip2d as O2
+        boot = O2.MTIP2D(sd, {'data_radial_points': qs, 'average_intensity': np.ones(N_R), 'max_order': L_MAX,
+                              'data_projection_matrices': np.zeros((L_MAX + 1, N_R), complex)})
+        return sd, O2.invariants_from_density_2d(O2.disk_model_density(boot.real_grid), boot.ft, boot.qs, boot.real_grid[0, :, 1])
+    boot = O.MTIP(sd, {'data_radial_points': qs, 'average_intensity': np.ones(N_R), 'max_order': L_MAX,
+                       'data_projection_matrices': [np.zeros((N_R, min(N_R, 2 * l + 1)), complex) for l in range(L_MAX + 1)]})
+    return sd, O.invariants_from_density(O.six_sphere_density(boot.real_grid), boot.ft, boot.sh, boot.qs)
+
+
+def _cpu_worker_port(args):
+    seed, warmup, steps = args
     import numpy as np
     from oracle import mtip as O
     if _CPU['dims'] == 2:
@@ -147,71 +182,128 @@ def _cpu_worker(args):
     rho = m.density_guess(np.random.default_rng(seed))
     rho = m.ift(m.ft(rho))
     m.beta = 0.5
-    rho = m.io_step('HIO', rho, True)[1]          # warm-up iteration (untimed)
-    n, t0 = 0, time.perf_counter()
-    while True:
+    for _ in range(warmup):
         rho = m.io_step('HIO', rho, True)[1]
-        n += 1
-        el = time.perf_counter() - t0
-        if el >= budget_s:
-            return n, el
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        rho = m.io_step('HIO', rho, True)[1]
+    return time.perf_counter() - t0
 
 
-def cpu_reference(budget_s=15.0, n_workers=None):
-    """it/s of the reference CPU path: one single-threaded process per reconstruction (the reference's process model,
-    xframe/__init__.py:5-8, reconstruct.py:141-157) on every usable host thread; each process iterates for ~budget_s."""
+def _cpu_worker_reference(args):
+    """The reference's own loop: MTIP.phasing_loop() with a schedule of warmup + steps HIO iterations (ft_stab on); the timed
+    region is the last `steps` calls of its HIO_ft_stab routine (entry of call `warmup` to the return of the last call)."""
+    seed, warmup, steps = args
+    import multiprocessing
+    import numpy as np
+    # the reference names its reconstruction processes by integers and parses them back (Multiprocessing.py:93-99)
+    multiprocessing.current_process().name = str(seed - 999)
+    devnull = os.open(os.devnull, os.O_WRONLY)      # the reference prints its progress (xprint) to stdout: keep the JSON line alone there
+    os.dup2(devnull, 1)
+    sys.path.insert(0, os.path.join(ROOT, 'baseline'))
+    import ref_harness as RH
+    from oracle import mtip as O
+    sd, inv = _CPU['ref_settings'], _CPU['ref_data']
+    if _CPU['dims'] == 2:
+        from oracle import mtip2d as O2
+        rho0 = O2.MTIP2D(sd, dict(_CPU['data'])).density_guess(np.random.default_rng(seed)).astype(complex)
+    else:
+        rho0 = O.MTIP(sd, dict(_CPU['data'])).density_guess(np.random.default_rng(seed)).astype(complex)
+    m = RH.new_mtip(_CPU['ref_module'], inv, rho0=rho0)
+    stamps = []
+    for name in ('HIO_ft_stab', 'HIO'):
+        proc = m.routines[name]
+        inner = proc.run
+
+        def timed(*a, _inner=inner, **k):
+            stamps.append(time.perf_counter())
+            out = _inner(*a, **k)
+            stamps.append(time.perf_counter())
+            return out
+        proc.run = timed
+    m.phasing_loop()
+    assert len(stamps) == 2 * (warmup + steps), (len(stamps), warmup, steps)
+    return stamps[-1] - stamps[2 * warmup]
+
+
+def _reference_preinit(RH, n_iter):
+    """Master-process part of the reference worker (ProjectWorker.__init__ -> MTIP.preinit, reconstruct.py:89-110): settings,
+    invariants record, grids and Fourier weights; the forked processes inherit it like the reference's children do."""
+    import copy
+    import numpy as np
+    sd = copy.deepcopy(_CPU['settings'])
+    sd['multi_process'] = {'use': False, 'n_parallel_reconstructions': 1}
+    sd['GPU'] = {'use': False, 'n_gpu_workers': 1}
+    sd['fourier_transform']['allow_weight_saving'] = False
+    sd['main_loop']['sub_loops'] = {'order': ['main'],
+                                    'main': {'methods': {'HIO': {'iterations': n_iter, 'ft_stab': True}}, 'order': ['HIO'], 'iterations': 1,
+                                             'best_density_not_in_first_n_iterations': np.inf}}
+    inv = dict(_CPU['data'])
+    # the reference's no-regridding branch raises UnboundLocalError (fxs_Projections.py:644-676): shift the data q grid by
+    # 1e-12 relative so that its cubic regridding runs, as it does in the real pipeline (same operators, same cost)
+    dq = np.asarray(inv['data_radial_points'], dtype=float) * (1 + 1e-12)
+    dq[0] = float(inv['data_radial_points'][0]) * (1 - 1e-12)
+    inv['data_radial_points'] = dq
+    inv.setdefault('dimensions', _CPU['dims'])
+    inv.setdefault('xray_wavelength', 1.23984)
+    inv.setdefault('number_of_particles', 1)
+    _CPU['ref_settings'], _CPU['ref_data'] = sd, inv
+    _CPU['ref_module'] = RH.preinit(sd, inv)
+
+
+def cpu_reference(steps=8, warmup=1, n_workers=None):
+    """iterations/s of the reference CPU path on every usable host thread; see the block comment above."""
     import multiprocessing as mp
     for k in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'NUMEXPR_NUM_THREADS'):
         os.environ[k] = '1'
-    import numpy as np
-    from oracle import mtip as O
-    from xframe_b200.settings import tutorial_settings
-    qs = O.radial_grids('midpoint', MAX_Q, N_R, 2.0)[1]
     _CPU['dims'] = DIMS
-    if DIMS == 2:
-        from oracle import mtip2d as O2
-        sd = tutorial_settings(dimensions=2, grid={'max_q': MAX_Q, 'max_order': L_MAX, 'n_radial_points': N_R})
-        boot = O2.MTIP2D(sd, {'data_radial_points': qs, 'average_intensity': np.ones(N_R), 'max_order': L_MAX,
-                              'data_projection_matrices': np.zeros((L_MAX + 1, N_R), complex)})
-        _CPU['data'] = O2.invariants_from_density_2d(O2.disk_model_density(boot.real_grid), boot.ft, boot.qs, boot.real_grid[0, :, 1])
-    else:
-        sd = tutorial_settings(grid={'max_q': MAX_Q, 'max_order': L_MAX, 'n_phi': N_PHI, 'n_theta': N_THETA, 'n_radial_points': N_R})
-        boot = O.MTIP(sd, {'data_radial_points': qs, 'average_intensity': np.ones(N_R), 'max_order': L_MAX,
-                           'data_projection_matrices': [np.zeros((N_R, min(N_R, 2 * l + 1)), complex) for l in range(L_MAX + 1)]})
-        _CPU['data'] = O.invariants_from_density(O.six_sphere_density(boot.real_grid), boot.ft, boot.sh, boot.qs)
-    _CPU['settings'] = sd
+    _CPU['settings'], _CPU['data'] = _cpu_data()
+    sys.path.insert(0, os.path.join(ROOT, 'baseline'))
+    kind, worker = 'port', _cpu_worker_port
+    try:
+        import ref_harness as RH
+        if os.path.isdir(os.path.join(ROOT, 'baseline', '_ref', 'xframe')):
+            from oracle.sht import sh as oracle_sh
+            RH.import_reference(sh_class=oracle_sh if DIMS == 3 else None)       # imported once, inherited by the forked workers
+            _reference_preinit(RH, steps + warmup)
+            kind, worker = 'reference', _cpu_worker_reference
+    except Exception as e:      # noqa: BLE001
+        print(f'reference package unusable ({e}); timing the oracle port', file=sys.stderr)
     if n_workers is None:
         n_workers = len(os.sched_getaffinity(0))
     ctx = mp.get_context('fork')
     t0 = time.perf_counter()
     with ctx.Pool(n_workers) as pool:
-        res = pool.map(_cpu_worker, [(1000 + i, budget_s) for i in range(n_workers)])
+        res = pool.map(worker, [(1000 + i, warmup, steps) for i in range(n_workers)])
     wall = time.perf_counter() - t0
-    rates = [n / el for n, el in res]
-    its = float(sum(rates))                     # concurrent processes: aggregate = sum of per-process rates
+    timed = max(res)                             # all processes run concurrently: the slowest one closes the timed region
+    its = n_workers * steps / timed
     cpu_model = ''
     try:
         with open('/proc/cpuinfo') as f:
             cpu_model = next((ln.split(':', 1)[1].strip() for ln in f if ln.startswith('model name')), '')
     except OSError:
         pass
-    return {'value': its, 'unit': UNIT, 'cores': n_workers, 'kind': 'port',
-            'sample': f'{n_workers} concurrent single-thread processes, each running HIO_ft_stab iterations of the L={L_MAX}/N_r={N_R} tutorial '
-                      f'run for ~{budget_s:.0f}s after 1 warm-up ({sum(n for n, _ in res)} iterations total); numpy oracle port of the '
-                      f'reference CPU path (shtns absent: SHT timed with the numpy restatement); per-process '
-                      f'{min(rates):.3f}..{max(rates):.3f} it/s; pool wall {wall:.1f}s; cpu "{cpu_model}"'}
+    what = ('the UNMODIFIED reference from baseline/_ref (its own MTIP / HIO_ft_stab routine'
+            + ('; shtns is absent from the image, so its SHT plugin slot holds the numpy restatement oracle/sht.py)' if DIMS == 3 else ')')) \
+        if kind == 'reference' else 'numpy oracle port of the reference CPU path (baseline/_ref missing)'
+    return {'value': its, 'unit': UNIT, 'cores': n_workers, 'kind': kind, 'timed_s': timed, 'steps': steps, 'warmup': warmup,
+            'sample': f'{n_workers} of the workload\'s runs, one single-thread process each on the {n_workers} usable host threads, {warmup} warm-up + '
+                      f'{steps} timed HIO_ft_stab iterations per process at L={L_MAX}/N_r={N_R}; {what}; slowest / fastest process '
+                      f'{max(res):.2f} / {min(res):.2f} s; pool wall {wall:.1f}s incl. set-up; cpu "{cpu_model}"'}
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cb = cpu_reference(budget_s=args.budget)
+    cb = cpu_reference(steps=args.steps, warmup=args.warmup)
     line = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': 1e3 / cb['value'] * cb['cores'] if cb['value'] else None, 'higher_is_better': True, 'scaling': 'strong',
+            'warmup': args.warmup, 'ms_per_step': cb['timed_s'] / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': 'fxs 3D reconstruct: independent MTIP runs (six-sphere tutorial model) at L=63/N_r=128, 64x128 angular '
-                                   'grid, HIO_ft_stab iteration; reference CPU path, one process per run', 'runs': cb['cores']},
+            'config': {'workload': workload_text(args.runs), 'runs_total': args.runs,
+                       'note': f'CPU arm: each step iterates a bounded sample of {cb["cores"]} of the {args.runs} runs (one per host thread); '
+                               'value = sample runs x steps / time of the slowest process'},
             'cpu_baseline': cb, 'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
 
@@ -356,17 +448,16 @@ def run_ours(args):
             # fresh interpreter: BLAS thread pins must be in the environment before numpy loads, and no CUDA context is forked
             try:
                 env = dict(os.environ, RANK='0', WORLD_SIZE='1')
-                out = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--budget', '15', '--workload', args.workload],
-                                     capture_output=True, text=True, timeout=900, env=env).stdout.strip().splitlines()
+                kc = {'l63': 8, 'l127': 1, 'polar': 150}[args.workload]      # bounded sample: ~10-30 s of CPU work
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', str(kc), '--warmup', '1',
+                                      '--workload', args.workload], capture_output=True, text=True, timeout=1500, env=env).stdout.strip().splitlines()
                 cb = json.loads(out[-1])['cpu_baseline']
             except Exception as e:      # noqa: BLE001
                 cb = {'value': None, 'unit': UNIT, 'cores': 0, 'kind': 'port', 'sample': f'failed: {e}'}
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_max / K,
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': f'fxs {DIMS}D reconstruct: {total} independent MTIP runs (six-sphere tutorial model) at L={L_MAX}/N_r={N_R}, '
-                                   f'{N_THETA}x{N_PHI} angular grid, sharded over the GPUs; step = one HIO_ft_stab iteration of every run',
-                       'runs_total': total, 'runs_per_gpu': nb, 'l2_policy': 'inputs larger than L2 (per-step working set '
+            'config': {'workload': workload_text(total), 'runs_total': total, 'runs_per_gpu': nb, 'l2_policy': 'inputs larger than L2 (per-step working set '
                                                                             f'{nb * (N_R * N_THETA * N_PHI * 16 >> 20) * 11} MiB per GPU)',
                        'reconstructions_per_hour': value * 3600.0 / 606.0,
                        'reconstruction_definition': '600 iterations + 6 shrink-wrap steps (tutorial.yaml:52-72)'},
@@ -389,7 +480,6 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='l63', choices=sorted(WORKLOADS))
     ap.add_argument('--runs', type=int, default=None)
-    ap.add_argument('--budget', type=float, default=20.0, help='seconds of timed CPU work per process (reference arm)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     args = ap.parse_args()
     select_workload(args.workload)

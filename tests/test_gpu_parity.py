@@ -103,6 +103,62 @@ def test_elementwise_golden(case):
     assert (sw != g['sw_mask']).mean() < 1e-3
 
 
+def test_real_projection_chain_like_the_reference(case):
+    """assemble_projection (fxs_Projections.py:110-130): names without a generate_<name>_projection are logged and ignored
+    (the reference's default list carries 'assert_real'), average_center (:96-110) replaces the first shells by their angular
+    mean at its position in the chain and never marks a point as changed."""
+    g, sd, m, plan = case
+    import copy
+    from xframe_b200.plan import Plan, HIO, ER
+    popt = copy.deepcopy(sd['projections']['real']['projections'])
+    popt['apply'] = ['support', 'assert_real', 'average_center', 'value_threshold', 'limit_imag']
+    popt['average_center'] = {'max_radial_id': 2}
+    rp = O.RealProjection(popt, m.real_grid)
+    p2 = Plan(m.l_max, len(m.rs), float(g['max_q']), n_theta=int(g['n_theta']), n_phi=int(g['n_phi']), max_batch=2)
+    try:
+        p2.set_real(popt['apply'], rp.initial_support, popt['value_threshold']['threshold'], popt['limit_imag']['threshold'],
+                    average_center_shells=2)
+        assert p2.real_projections == ('support', 'average_center', 'value_threshold', 'limit_imag')
+        rng = np.random.default_rng(9)
+        x = np.stack([g['rho_new'], g['rho_new'] * (1 + 0.3 * rng.standard_normal(g['rho_new'].shape))])
+        prev = np.stack([g['rho0'], g['rho0']])
+        sup = torch.ones((2,) + p2.grid_shape, dtype=torch.uint8, device='cuda')
+        nxt, err = p2.real_update(ER, 0.0, T(x), T(prev), sup)
+        for b in range(2):
+            want, masks = rp.projection(x[b].copy())
+            assert rel_l2(N(nxt)[b], want) < 1e-14
+            assert rel_l2(N(nxt)[b][:2], want[:2]) < 1e-13            # the averaged shells
+            hio = O.hybrid_input_output(0.4, x[b].copy(), [want, masks], prev[b])
+            got, _ = p2.real_update(HIO, 0.4, T(x), T(prev), sup)
+            assert rel_l2(N(got)[b], hio) < 1e-14
+    finally:
+        p2.close()
+
+
+def test_unknowns_of_a_zeroed_order_keep_the_column_count():
+    """xfb_get_unknowns for an order whose V_l was zeroed (odd_orders_to_0): the reference's svd of the zero [n_cols x 2l+1]
+    matrix gives identity factors with n_cols rows -- also when n_cols < min(N_r, 2l+1)."""
+    from xframe_b200.plan import Plan, HIO
+    l_max, n_r = 5, 16
+    plan = Plan(l_max, n_r, 0.2, n_theta=8, n_phi=16, max_batch=1)
+    try:
+        rng = np.random.default_rng(2)
+        ncols = [1, 3, 5, 4, 9, 6]                       # orders 3 and 5: fewer columns than 2l+1 < N_r
+        pm = [rng.standard_normal((n_r, c)) for c in ncols]
+        for l in (1, 3, 5):
+            pm[l][:] = 0
+        plan.set_projection(pm, True, 1.0)
+        plan.set_real(['support'], np.ones(plan.grid_shape, bool))
+        c = rng.standard_normal((1, n_r, (l_max + 1) ** 2)) + 1j * rng.standard_normal((1, n_r, (l_max + 1) ** 2))
+        plan.project_invariants(T(c))
+        unk = plan.unknowns(0)
+        for l in (3, 5):
+            assert unk[l].shape == (ncols[l], 2 * l + 1)
+            assert np.array_equal(unk[l], np.eye(ncols[l], 2 * l + 1).astype(complex))
+    finally:
+        plan.close()
+
+
 def test_modified_intensity_corner_cases(case):
     """project_to_modified_intensity (fxs_Projections.py:899-909) on crafted points: negative / zero / tiny / huge projected
     intensities and vanishing rho_hat -- zeros, infs and NaNs land exactly where numpy puts them (the device multiplier is

@@ -298,13 +298,12 @@ __device__ __forceinline__ bool jacobi_w_pass(double* Wb, int wld, bool w_compac
 //  * fewer block pairs than warps: the warps split into a G team (pass 1 of round r) and a W team (pass 2 of round
 //    r-1, from the double-buffered rotation parameters) that run concurrently -- G and W are independent data.
 #define JROT_RB (JROT_STEPS * 4 + 1)
-// block pairs per round that need a parameter slot: 512-thread variant n <= 128 columns -> 16, 256-thread variant n <= 256 -> 32
-__host__ __device__ inline int jrot_slots(int threads) { return threads >= 512 ? 16 : 32; }
+// block pairs per round that need a parameter slot (kernel template parameter SLOTS): n <= 128 columns -> 16, n <= 256 -> 32,
+// n <= 64 (the two-CTAs-per-SM variant for the small orders) -> 8
 template <int NV2, int WV2>
 __device__ __forceinline__ void jacobi_sweep_blocked(double* Gs, int ldg, double* Wb, int wld, bool w_compact, const int* __restrict__ list,
-                                                     int nact, double thr, double tol, double2* rotbuf, int* s_rot, double* nrm2) {
+                                                     int nact, double thr, double tol, double2* rotbuf, int* s_rot, double* nrm2, int JROT_SLOTS) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const int JROT_SLOTS = jrot_slots(blockDim.x);
     const int nblk = (nact + 3) >> 2;
     const int nblkp = max(2, nblk + (nblk & 1));
     const int half = nblkp >> 1, rounds = nblkp - 1;
@@ -345,16 +344,18 @@ __device__ __forceinline__ void jacobi_sweep_blocked(double* Gs, int ldg, double
 // cover ceil(len / 16) double2 per lane only.
 template <int MAXV2>
 __device__ __forceinline__ void jacobi_sweep_dispatch(double* Gs, double* Wb, int ld, int len, bool w_compact, const int* list, int nact,
-                                                      double thr, double tol, double2* rotbuf, int* s_rot, double* nrm2) {
+                                                      double thr, double tol, double2* rotbuf, int* s_rot, double* nrm2, int slots) {
     if constexpr (MAXV2 >= 16) {
-        if (len > 128) { jacobi_sweep_blocked<16, 16>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot, nrm2); return; }
+        if (len > 128) { jacobi_sweep_blocked<16, 16>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot, nrm2, slots); return; }
     }
-    if (len <= 32) jacobi_sweep_blocked<2, 2>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot, nrm2);
-    else if (len <= 48) jacobi_sweep_blocked<3, 3>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot, nrm2);
-    else if (len <= 64) jacobi_sweep_blocked<4, 4>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot, nrm2);
-    else if (len <= 80) jacobi_sweep_blocked<5, 5>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot, nrm2);
-    else if (len <= 96) jacobi_sweep_blocked<6, 6>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot, nrm2);
-    else jacobi_sweep_blocked<8, 8>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot, nrm2);
+    if (len <= 32) jacobi_sweep_blocked<2, 2>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot, nrm2, slots);
+    else if (len <= 48) jacobi_sweep_blocked<3, 3>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot, nrm2, slots);
+    else if (len <= 64) jacobi_sweep_blocked<4, 4>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot, nrm2, slots);
+    else if constexpr (MAXV2 >= 8) {
+        if (len <= 80) jacobi_sweep_blocked<5, 5>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot, nrm2, slots);
+        else if (len <= 96) jacobi_sweep_blocked<6, 6>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot, nrm2, slots);
+        else jacobi_sweep_blocked<8, 8>(Gs, ld, Wb, ld, w_compact, list, nact, thr, tol, rotbuf, s_rot, nrm2, slots);
+    }
 }
 
 __device__ __forceinline__ void jacobi_col_norms(const double* Gs, int ldg, int n, double* nrm2);
@@ -440,14 +441,17 @@ __device__ __forceinline__ void mgs2_qr(double* A, int lda, int r, double* Rt, i
     }
     __syncthreads();
 }
+template <int MAXV2>
 __device__ __forceinline__ void mgs2_qr_dispatch(double* A, int lda, int len, int r, double* Rt, int ldr, double* n2c, int* nref) {
     if (len <= 32) mgs2_qr<2>(A, lda, r, Rt, ldr, n2c, nref);
     else if (len <= 48) mgs2_qr<3>(A, lda, r, Rt, ldr, n2c, nref);
     else if (len <= 64) mgs2_qr<4>(A, lda, r, Rt, ldr, n2c, nref);
-    else if (len <= 80) mgs2_qr<5>(A, lda, r, Rt, ldr, n2c, nref);
-    else if (len <= 96) mgs2_qr<6>(A, lda, r, Rt, ldr, n2c, nref);
-    else if (len <= 112) mgs2_qr<7>(A, lda, r, Rt, ldr, n2c, nref);
-    else mgs2_qr<8>(A, lda, r, Rt, ldr, n2c, nref);
+    else if constexpr (MAXV2 >= 8) {
+        if (len <= 80) mgs2_qr<5>(A, lda, r, Rt, ldr, n2c, nref);
+        else if (len <= 96) mgs2_qr<6>(A, lda, r, Rt, ldr, n2c, nref);
+        else if (len <= 112) mgs2_qr<7>(A, lda, r, Rt, ldr, n2c, nref);
+        else mgs2_qr<8>(A, lda, r, Rt, ldr, n2c, nref);
+    }
 }
 
 // column norms of Gs -> nrm2, ordered list of the columns above the cut-off -> list, their number -> *s_nact
@@ -505,7 +509,7 @@ template <int MAXV2>
 __device__ __forceinline__ int jacobi_qr_problem(const double* __restrict__ g, int n, int ldg, int len_g, double* __restrict__ gn, double* __restrict__ pp,
                                                  double* nrm2, int* list, int r, int ldl, double* region, double2* rotbuf, double sv_cutoff,
                                                  double tol, int max_sweeps, int* s_nact, double* s_thr, int* s_rot,
-                                                 double* __restrict__ sigma) {
+                                                 double* __restrict__ sigma, int slots) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     double* A = region;                 // [r][ldg]
     double* B = A + (size_t)r * ldg;    // [r][ldl]
@@ -521,19 +525,19 @@ __device__ __forceinline__ int jacobi_qr_problem(const double* __restrict__ g, i
         reinterpret_cast<double2*>(pp)[i] = make_double2(0.0, 0.0);
     }
     __syncthreads();
-    mgs2_qr_dispatch(A, ldg, len_g, r, B, ldl, nrm2, list2);     // A = Q1, B = columns of R1^T (nrm2 / list2 are free until the sweeps)
+    mgs2_qr_dispatch<MAXV2>(A, ldg, len_g, r, B, ldl, nrm2, list2);     // A = Q1, B = columns of R1^T (nrm2 / list2 are free until the sweeps)
     for (int i = tid; i < r * (ldg / 2); i += nthr) {     // Q1 is final: rows list[a] of gn
         const int a = i / (ldg / 2), e = i - a * (ldg / 2);
         reinterpret_cast<double2*>(gn + (size_t)list[a] * ldg)[e] = reinterpret_cast<const double2*>(A)[i];
     }
-    mgs2_qr_dispatch(B, ldl, r, r, C, ldl, nrm2, list2);         // B = Q2, C = columns of R2^T = L
+    mgs2_qr_dispatch<MAXV2>(B, ldl, r, r, C, ldl, nrm2, list2);         // B = Q2, C = columns of R2^T = L
     int sweep = 0;
     for (; sweep < max_sweeps; ++sweep) {
         jacobi_active_list(C, ldl, r, nrm2, list2, sv_cutoff, s_nact, s_thr, s_rot);
         const int nact = *s_nact;
         const double thr = *s_thr;
         if (nact < 2) break;
-        jacobi_sweep_dispatch<MAXV2>(C, B, ldl, r, false, list2, nact, thr, tol, rotbuf, s_rot, nrm2);
+        jacobi_sweep_dispatch<MAXV2>(C, B, ldl, r, false, list2, nact, thr, tol, rotbuf, s_rot, nrm2, slots);
         __syncthreads();
         const int rotated = *s_rot;
         __syncthreads();
@@ -586,20 +590,25 @@ __device__ __forceinline__ int jacobi_qr_problem(const double* __restrict__ g, i
 //   direct path:    gn = U~ (normalised rotated columns of G), pp = J^T (accumulator started from the identity)
 // MAXV2 = 8, THREADS = 512: column length <= 128 (the L=63 configuration);  MAXV2 = 16, THREADS = 256: up to 256
 // (L=127), 255 registers per thread for the 2 x 16 double2 register tiles.
-template <int MAXV2, int THREADS, bool QR>
-__global__ void __launch_bounds__(THREADS, 1) procrustes_jacobi_kernel(const double* __restrict__ g_in, double* __restrict__ gn_out,
+// MAXV2 = 4, THREADS = 256, MINB = 2, SLOTS = 8: the orders with 2l+1 <= 64 (column length and rank <= 64) run TWO problems per SM
+// (half the shared memory each): the kernel is bound by the latency of its sequential rotation steps with a third of the
+// issue slots used, so a second resident problem fills the idle cycles.
+template <int MAXV2, int THREADS, bool QR, int MINB, int SLOTS>
+__global__ void __launch_bounds__(THREADS, MINB) procrustes_jacobi_kernel(const double* __restrict__ g_in, double* __restrict__ gn_out,
                                                                        double* __restrict__ pp_out, double* __restrict__ sigma_out,
                                                                        const ProcOrder* __restrict__ orders, int n_orders, int n_batch,
                                                                        int sig_ld, long long g_run_stride, long long sig_run_stride,
                                                                        double sv_cutoff, double tol, int max_sweeps,
                                                                        int* __restrict__ sweeps_out, int smem_doubles,
-                                                                       int* __restrict__ work_counter) {
+                                                                       int* __restrict__ work_counter, int order0, int n_orders_all) {
+    // orders [order0, order0 + n_orders) of the plan's list (largest first) are this launch's problems; sigma / sweeps are
+    // indexed by the position in the whole list (n_orders_all entries per run)
     extern __shared__ __align__(16) double smem_j[];
     __shared__ int s_nact, s_rot, s_prob;
     __shared__ double s_thr;
     const int tid = threadIdx.x;
     double2* rotbuf = reinterpret_cast<double2*>(smem_j);                 // [2][slots][JROT_RB]
-    const int fixed = 2 * 2 * jrot_slots(THREADS) * JROT_RB;              // doubles
+    const int fixed = 2 * 2 * SLOTS * JROT_RB;                            // doubles
 
     // dynamic work queue (largest problems first): a CTA fetches the next problem when it is done with the previous one
     for (;;) {
@@ -608,8 +617,8 @@ __global__ void __launch_bounds__(THREADS, 1) procrustes_jacobi_kernel(const dou
         __syncthreads();
         const int prob = s_prob;
         if (prob >= n_orders * n_batch) break;
-        const int oi = prob / n_batch;                     // orders are sorted largest first
-        const int b = prob - oi * n_batch;
+        const int oi = order0 + prob / n_batch;            // orders are sorted largest first
+        const int b = prob - (oi - order0) * n_batch;
         const ProcOrder o = orders[oi];
         const int n = o.n_cols;
         const int ldg = jacobi_stride(o.n_c);
@@ -628,8 +637,8 @@ __global__ void __launch_bounds__(THREADS, 1) procrustes_jacobi_kernel(const dou
             if (r >= 2 && var0 + r * ldg + 2 * r * ldl <= smem_doubles) {
                 __syncthreads();
                 const int sw = jacobi_qr_problem<MAXV2>(g, n, ldg, o.n_c, gn, pp, nrm2, list, r, ldl, smem_j + var0, rotbuf, sv_cutoff, tol, max_sweeps,
-                                                        &s_nact, &s_thr, &s_rot, sg);
-                if (tid == 0 && sweeps_out) sweeps_out[b * n_orders + oi] = sw;
+                                                        &s_nact, &s_thr, &s_rot, sg, SLOTS);
+                if (tid == 0 && sweeps_out) sweeps_out[b * n_orders_all + oi] = sw;
                 continue;
             }
             __syncthreads();
@@ -663,7 +672,7 @@ __global__ void __launch_bounds__(THREADS, 1) procrustes_jacobi_kernel(const dou
                 }
                 __syncthreads();
             }
-            jacobi_sweep_dispatch<MAXV2>(Gs, w_smem ? Ws : pp, ldg, ldg, w_smem, list, nact, thr, tol, rotbuf, &s_rot, nrm2);
+            jacobi_sweep_dispatch<MAXV2>(Gs, w_smem ? Ws : pp, ldg, ldg, w_smem, list, nact, thr, tol, rotbuf, &s_rot, nrm2, SLOTS);
             if (w_smem) {
                 for (int i = tid; i < nact * (ldg / 2); i += THREADS) {
                     const int a = i / (ldg / 2), e = i - a * (ldg / 2);
@@ -685,7 +694,7 @@ __global__ void __launch_bounds__(THREADS, 1) procrustes_jacobi_kernel(const dou
             gn[i] = (s2 > thr_f && s2 > 0.0) ? Gs[i] / sqrt(s2) : 0.0;
         }
         for (int i = tid; i < n; i += THREADS) sg[i] = sqrt(nrm2[i]);
-        if (tid == 0 && sweeps_out) sweeps_out[b * n_orders + oi] = sweep;
+        if (tid == 0 && sweeps_out) sweeps_out[b * n_orders_all + oi] = sweep;
     }
 }
 

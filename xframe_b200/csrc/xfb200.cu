@@ -79,6 +79,7 @@ struct xfb_plan {
     int gemmY_tiles = 0, gemmY_tiles_run = 0;
     int gemmM_tiles = 0, gemmT_tiles = 0, gemm_nb = -1, gemmM_tiles_run = 0, gemmT_tiles_run = 0;
     size_t jacobi_smem = 0; int n_sm = 148; bool jacobi_big = false; int* jac_counter = nullptr;
+    int jac_split = 1, jac_n_big = 0;               // orders [0, jac_n_big) have 2l+1 > 64: one problem per SM; the rest two per SM
     // real projection
     bool has_real = false; RealDesc rd{}; uint8_t* init_support_dev = nullptr; double2* avg_mean = nullptr;
     // loop state
@@ -607,22 +608,43 @@ static int build_gemm_groups(xfb_plan* p, int nb_req, cudaStream_t st) {
     return 0;
 }
 
-// one-sided Jacobi over all (order, run) problems of a batch; kernel variant by problem size (procrustes.cuh)
+// one-sided Jacobi over all (order, run) problems of a batch; kernel variant by problem size (procrustes.cuh).
+// L <= 63 class: the orders with 2l+1 > 64 (one problem per SM, 512 threads) are launched on the caller's stream, the
+// orders with 2l+1 <= 64 (two problems per SM, 256 threads each) on a forked stream: their CTAs fill the SMs as the
+// large problems drain, and both launches pull their problems from their own work queue.
+#define JAC_SMALL_SMEM (111 * 1024)
 static int launch_jacobi(xfb_plan* p, const double* g, double* gn, double* pp, double* sigma, int nb, int* sweeps, cudaStream_t st) {
     const int na = (int)p->orders.size();
-    const int grid = std::min(na * nb, p->n_sm);
     const int smem_doubles = (int)(p->jacobi_smem / 8);
-    if (!p->jac_counter) { if (dev_alloc(p, &p->jac_counter, 1)) return 1; }
-    XFB_CUDA(cudaMemsetAsync(p->jac_counter, 0, sizeof(int), st));
-    if (p->jacobi_big)
-        procrustes_jacobi_kernel<16, 256, false><<<grid, 256, p->jacobi_smem, st>>>(g, gn, pp, sigma, p->orders_dev, na, nb, p->n_r, p->g_run,
-                                                                                   (long long)na * p->n_r, p->sv_cutoff, 1e-15, p->max_sweeps,
-                                                                                   sweeps, smem_doubles, p->jac_counter);
-    else
-        procrustes_jacobi_kernel<8, 512, true><<<grid, 512, p->jacobi_smem, st>>>(g, gn, pp, sigma, p->orders_dev, na, nb, p->n_r, p->g_run,
-                                                                                 (long long)na * p->n_r, p->sv_cutoff, 1e-15, p->max_sweeps,
-                                                                                 sweeps, smem_doubles, p->jac_counter);
+    if (!p->jac_counter) { if (dev_alloc(p, &p->jac_counter, 2)) return 1; }
+    XFB_CUDA(cudaMemsetAsync(p->jac_counter, 0, 2 * sizeof(int), st));
+    const long long sig_run = (long long)na * p->n_r;
+    if (p->jacobi_big) {
+        procrustes_jacobi_kernel<16, 256, false, 1, 32><<<std::min(na * nb, p->n_sm), 256, p->jacobi_smem, st>>>(
+            g, gn, pp, sigma, p->orders_dev, na, nb, p->n_r, p->g_run, sig_run, p->sv_cutoff, 1e-15, p->max_sweeps, sweeps, smem_doubles, p->jac_counter, 0, na);
+        XFB_CUDA(cudaGetLastError());
+        return 0;
+    }
+    const int n_big = p->jac_split ? p->jac_n_big : na, n_small = na - n_big;
+    cudaStream_t s_small = st;
+    if (n_big > 0 && n_small > 0) {          // fork: the small-order launch goes to a side stream
+        if (sht_streams_init(p)) return 1;
+        s_small = p->sht_side[1];
+        XFB_CUDA(cudaEventRecord(p->sht_fork, st));
+        XFB_CUDA(cudaStreamWaitEvent(s_small, p->sht_fork, 0));
+    }
+    if (n_big > 0)
+        procrustes_jacobi_kernel<8, 512, true, 1, 16><<<std::min(n_big * nb, p->n_sm), 512, p->jacobi_smem, st>>>(
+            g, gn, pp, sigma, p->orders_dev, n_big, nb, p->n_r, p->g_run, sig_run, p->sv_cutoff, 1e-15, p->max_sweeps, sweeps, smem_doubles, p->jac_counter, 0, na);
+    if (n_small > 0)
+        procrustes_jacobi_kernel<4, 256, true, 2, 8><<<std::min(n_small * nb, 2 * p->n_sm), 256, JAC_SMALL_SMEM, s_small>>>(
+            g, gn, pp, sigma, p->orders_dev, n_small, nb, p->n_r, p->g_run, sig_run, p->sv_cutoff, 1e-15, p->max_sweeps, sweeps, JAC_SMALL_SMEM / 8,
+            p->jac_counter + 1, n_big, na);
     XFB_CUDA(cudaGetLastError());
+    if (n_big > 0 && n_small > 0) {          // join
+        XFB_CUDA(cudaEventRecord(p->sht_join[1], s_small));
+        XFB_CUDA(cudaStreamWaitEvent(st, p->sht_join[1], 0));
+    }
     return 0;
 }
 
@@ -821,8 +843,14 @@ int xfb_plan_set_projection(xfb_plan* p, const xfb_projection_desc* d) {
         if (dev_alloc(p, &p->gemmM_tp, B * tiles_m)) return 1;
         if (dev_alloc(p, &p->gemmT_tp, B * tiles_t)) return 1;
         if (dev_alloc(p, &p->gemmY_tp, B * tiles_y)) return 1;
-        if (p->jacobi_big) XFB_CUDA(cudaFuncSetAttribute(procrustes_jacobi_kernel<16, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-        else XFB_CUDA(cudaFuncSetAttribute(procrustes_jacobi_kernel<8, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        if (p->jacobi_big) XFB_CUDA(cudaFuncSetAttribute(procrustes_jacobi_kernel<16, 256, false, 1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        else {
+            XFB_CUDA(cudaFuncSetAttribute(procrustes_jacobi_kernel<8, 512, true, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+            XFB_CUDA(cudaFuncSetAttribute(procrustes_jacobi_kernel<4, 256, true, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, JAC_SMALL_SMEM));
+        }
+        p->jac_n_big = 0;
+        for (const ProcOrder& o : p->orders) if (o.n_c > 64) p->jac_n_big++;        // sorted largest first: a prefix
+        if (const char* e = getenv("XFB_JACOBI_SPLIT")) p->jac_split = atoi(e) != 0;   // experiments
     } else {
         // dummy so the unpack kernel has valid pointers
         ProcOrder o{};
