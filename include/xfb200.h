@@ -129,6 +129,16 @@ int xfb_project_invariants(xfb_plan* p, const double* direct_in_dev, double* dir
 /* unknowns of the last xfb_project_invariants / iteration: out [n_l][2l+1] complex128 for (run,order) */
 int xfb_get_unknowns(xfb_plan* p, int32_t run, int32_t order, double* out_dev, void* stream);
 /* project_to_modified_intensity (fxs_Projections.py:899-909) */
+/* B_l = I_l I_l^H of the harmonic coefficients of a REAL field (harmonic_coeff_to_deg2_invariants_3d, fxs_invariant_tools.py:915-923):
+ * direct_in [nb][N_r][(L+1)^2] complex -> bl_out [nb][L+1][N_r][N_r] real (the invariants of a real field are real symmetric). */
+int xfb_deg2_invariants(xfb_plan* p, const double* direct_in_dev, double* bl_out_dev, int32_t n_batch, void* stream);
+/* deg2_invariant_l2_diff (fxs_IO_methods.py:412-447): reference = masked V_l V_l^H with order 0 already divided by the number of
+ * particles [L+1][N_r][N_r] real, norms = sum |masked reference|^2 per order BEFORE that division; err_out [nb][L+1], -1 where norm = 0. */
+int xfb_plan_set_deg2_reference(xfb_plan* p, const double* bref_host, const double* norm_host);
+int xfb_deg2_invariant_diff(xfb_plan* p, const double* direct_in_dev, double* err_out_dev, int32_t n_batch, void* stream);
+/* the same metric inside the loop (settings main_loop.error.methods.reciprocal.calculate: [deg2_invariant_l2_diff]) */
+int xfb_mtip_enable_deg2_metric(xfb_plan* p, int32_t on, int32_t history_capacity);
+int xfb_mtip_get_deg2_errors(xfb_plan* p, double* out_dev /*[n_batch][capacity][L+1]*/, int32_t capacity, void* stream);
 int xfb_modify_intensity(xfb_plan* p, const double* rho_hat_dev, const double* i_proj_dev, double* out_dev, int32_t n_batch, void* stream);
 /* real_projection + HIO/ER + l2_projection_diff (fxs_Projections.py:110-130, fxs_IO_methods.py:56-68,97-128).
  * method 0 = HIO, 1 = ER. rho_rt_dev may be NULL (no ft_stab). support_dev: 1 inside SW support.

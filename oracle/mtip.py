@@ -295,6 +295,24 @@ def harmonic_coeff_to_deg2_invariants_3d(Ilm):   # fxs_invariant_tools.py:915-92
     return np.array(tuple(Il @ Il.T.conj() for Il in Ilm))
 
 
+def deg2_invariant_l2_diff(reference_invariant, radial_mask, n_particles, Ilm):
+    """_generate_deg2_invariant_diff_3d (fxs_IO_methods.py:412-447) for used_order_ids = arange(n): per-order error array."""
+    ref = np.array(reference_invariant)
+    rm = np.broadcast_to(np.asarray(radial_mask, dtype=bool), ref.shape[:2])
+    mask = ~(rm[:, :, None] & rm[:, None, :])                       # invariant_mask = outer(radial_mask) (reconstruct.py:471)
+    ref[mask] = 0
+    norm = np.sum(ref * ref.conj(), axis=(1, 2))
+    nz = norm != 0
+    errors = np.full(len(norm), -1, dtype=float)
+    Bl = harmonic_coeff_to_deg2_invariants_3d(Ilm)[:len(norm)].copy()
+    Bl[mask] = 0
+    ref = ref.copy()
+    ref[0] = ref[0] / n_particles
+    diff = ref - Bl
+    errors[nz] = (np.sum((diff * diff.conj()).real, axis=(1, 2))[nz] / norm[nz]).real
+    return errors
+
+
 def gaussian_fourier_transformed_spherical(points, sigma):   # mathLibrary.py:616-624 (q**4, sic)
     a = 1 / (2 * sigma ** 2)
     return np.sqrt(np.pi / a) * np.exp(-np.pi ** 2 * np.square(points[..., 0]) ** 2 / a)

@@ -159,6 +159,56 @@ def test_unknowns_of_a_zeroed_order_keep_the_column_count():
         plan.close()
 
 
+def test_deg2_invariants_and_l2_diff_on_the_device(case):
+    """B_l = I_l I_l^H (fxs_invariant_tools.py:915-923) and deg2_invariant_l2_diff (fxs_IO_methods.py:412-447) for the coefficients
+    of real fields, against the oracle restatement (pinned to the reference in tests/test_under_reference.py).  Tolerance 1e-12."""
+    g, sd, m, plan = case
+    rng = np.random.default_rng(21)
+    x = rng.standard_normal((2,) + plan.grid_shape) ** 2 + 0j                    # real, non-negative like |rho_hat|^2
+    I = plan.sht_forward(T(x))
+    got = N(plan.deg2_invariants(I))
+    In = N(I)
+    for b in range(2):
+        Il = [In[b][:, l * l:(l + 1) * (l + 1)] for l in range(m.l_max + 1)]
+        want = O.harmonic_coeff_to_deg2_invariants_3d(Il)
+        assert np.abs(want.imag).max() < 1e-12 * np.abs(want).max()
+        assert rel_l2(got[b], want.real) < 1e-12
+    ref = O.harmonic_coeff_to_deg2_invariants_3d(m.rp.projection_matrices)
+    rmask = np.broadcast_to(np.asarray(m.rp.radial_mask, bool), (m.l_max + 1, len(m.qs))).copy()
+    rmask[:, :1] = False                                                          # exercise the invariant mask
+    plan.set_deg2_reference(ref, rmask, 3.0)
+    err = N(plan.deg2_invariant_diff(I))
+    for b in range(2):
+        Il = [In[b][:, l * l:(l + 1) * (l + 1)] for l in range(m.l_max + 1)]
+        want = O.deg2_invariant_l2_diff(ref, rmask, 3.0, Il)
+        assert np.array_equal(want == -1, err[b] == -1)                           # odd orders: zero reference
+        ok = want != -1
+        assert np.allclose(err[b][ok], want[ok], rtol=1e-11, atol=0)
+
+
+def test_worker_reports_the_deg2_metric_per_iteration():
+    """settings main_loop.error.methods.reciprocal.calculate: [deg2_invariant_l2_diff] -> error_dict['reciprocal'][...] [n_it, n_orders]
+    (reconstruct.py:526, arrayfy_error_dict); the first row is the metric of the initial density's intensity coefficients."""
+    import copy
+    from xframe_b200.worker import ProjectWorker
+    g = load_golden('ref_small_ftstab')
+    sd = copy.deepcopy(golden_settings(g))
+    sd['GPU'] = {'use': True, 'n_gpu_workers': 1}
+    sd['main_loop']['error']['methods']['reciprocal'] = {'calculate': ['deg2_invariant_l2_diff']}
+    w = ProjectWorker(sd, golden_data(g), n_reconstructions=2, initial_densities=[g['rho0'], g['rho0'] * 1.1])
+    res, _ = w.run()
+    plan = w.plan
+    for k, r in enumerate(res):
+        h = r['error_dict']['reciprocal']['deg2_invariant_l2_diff']
+        assert h.shape == (len(r['error_dict']['main']), int(g['l_max']) + 1) and np.isfinite(h).all()
+        rho0 = T(r['initial_density'])[None]
+        fd = plan.ft(rho0)
+        I = plan.sht_forward((fd * fd.conj()).real.to(torch.complex128).contiguous())
+        assert np.allclose(N(plan.deg2_invariant_diff(I))[0][:h.shape[1]], h[0], rtol=1e-9, atol=1e-300)
+    assert rel_l2(res[0]['error_dict']['main'], g['loop_main_error']) < 1e-6
+    w.plan.close()
+
+
 def test_modified_intensity_corner_cases(case):
     """project_to_modified_intensity (fxs_Projections.py:899-909) on crafted points: negative / zero / tiny / huge projected
     intensities and vanishing rho_hat -- zeros, infs and NaNs land exactly where numpy puts them (the device multiplier is

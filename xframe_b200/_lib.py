@@ -54,6 +54,11 @@ EXPORTS = {
     'xfb_ft': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'xfb_project_invariants': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'xfb_get_unknowns': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    'xfb_deg2_invariants': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    'xfb_plan_set_deg2_reference': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    'xfb_deg2_invariant_diff': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    'xfb_mtip_enable_deg2_metric': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
+    'xfb_mtip_get_deg2_errors': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'xfb_modify_intensity': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'xfb_real_update': (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),

@@ -782,3 +782,52 @@ __global__ void unknown_identity_kernel(double2* __restrict__ out, int n_l, int 
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < n_l * n_c) out[idx] = make_double2((idx / n_c) == (idx % n_c) ? 1.0 : 0.0, 0.0);
 }
+
+// ---- degree-2 invariants  B_l = I_l I_l^H  (fxs_invariant_tools.py:915-923) and their distance to the data ----------------
+// The coefficients belong to a REAL field (|rho_hat|^2), so with the real-harmonic columns X (see procrustes_pack_kernel)
+// B_l = X_l X_l^T is real symmetric: one real [N_r x (2l+1)] . [(2l+1) x N_r] product per (run, order) on the grouped DMMA GEMM.
+// c [(L+1)^2][S] complex (m >= 0 valid) -> x[b][l^2 + m'][k] real, ALL orders l = 0..L
+__global__ void pack_real_all_kernel(const double2* __restrict__ c, double* __restrict__ x, int n_r, int S, long long run_stride) {
+    const int l = blockIdx.x, b = blockIdx.y;
+    const double s2 = 1.4142135623730951;
+    double* dst = x + (size_t)b * run_stride + (size_t)l * l * n_r;
+    for (int idx = threadIdx.x; idx < (l + 1) * n_r; idx += blockDim.x) {
+        const int m = idx / n_r, k = idx - m * n_r;
+        const double2 v = ldg2(c + (size_t)(l * (l + 1) + m) * S + (size_t)b * n_r + k);
+        if (m == 0) {
+            dst[k] = v.x;
+        } else {
+            dst[(size_t)(2 * m - 1) * n_r + k] = s2 * v.x;
+            dst[(size_t)(2 * m) * n_r + k] = s2 * v.y;
+        }
+    }
+}
+// deg2_invariant_l2_diff (fxs_IO_methods.py:412-447): err[l] = sum_{q,q'} |Bref_l - mask B_l|^2 / sum |Bref_l|^2, -1 where the
+// reference vanishes.  bref is the masked reference with order 0 already divided by the number of particles (:440), norm the
+// sums of the masked reference BEFORE that division (:425-426).  One CTA per (order, run); fixed summation order.
+__global__ void __launch_bounds__(256) deg2_diff_kernel(const double* __restrict__ bl, const double* __restrict__ bref, const double* __restrict__ norm,
+                                                        const uint8_t* __restrict__ radial_mask, int n_r, int n_orders, long long bl_run_stride,
+                                                        double* __restrict__ err_out, long long err_run_stride) {
+    const int l = blockIdx.x, b = blockIdx.y;
+    const double* B = bl + (size_t)b * bl_run_stride + (size_t)l * n_r * n_r;
+    const double* R = bref + (size_t)l * n_r * n_r;
+    const uint8_t* rm = radial_mask + (size_t)l * n_r;
+    double acc = 0.0;
+    for (int idx = threadIdx.x; idx < n_r * n_r; idx += blockDim.x) {
+        const int q = idx / n_r, q2 = idx - q * n_r;
+        const double v = (rm[q] && rm[q2]) ? B[idx] : 0.0;
+        const double d = R[idx] - v;
+        acc += d * d;
+    }
+    __shared__ double red[8];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        const double nl = norm[l];
+        err_out[(size_t)b * err_run_stride + l] = (nl != 0.0) ? t / nl : -1.0;
+    }
+}
+

@@ -79,7 +79,11 @@ struct xfb_plan {
     int gemmY_tiles = 0, gemmY_tiles_run = 0;
     int gemmM_tiles = 0, gemmT_tiles = 0, gemm_nb = -1, gemmM_tiles_run = 0, gemmT_tiles_run = 0;
     size_t jacobi_smem = 0; int n_sm = 148; bool jacobi_big = false; int* jac_counter = nullptr;
+    int sig_ld = 0;                                 // singular values per (run, order): max(N_r, largest n_cols)
     int jac_split = 1, jac_n_big = 0;               // orders [0, jac_n_big) have 2l+1 > 64: one problem per SM; the rest two per SM
+    // degree-2 invariants B_l = I_l I_l^H of a batch and deg2_invariant_l2_diff (procrustes.cuh)
+    double *d2_x = nullptr, *d2_b = nullptr, *d2_ref = nullptr, *d2_norm = nullptr, *d2_hist = nullptr;
+    GemmProblem* d2_gemm = nullptr; int* d2_tp = nullptr; int d2_tiles_run = 0; int d2_hist_cap = 0; bool d2_metric = false;
     // real projection
     bool has_real = false; RealDesc rd{}; uint8_t* init_support_dev = nullptr; double2* avg_mean = nullptr;
     // loop state
@@ -250,7 +254,7 @@ int xfb_plan_destroy(xfb_plan* p) {
     void* ptrs[] = {p->tw, p->FE, p->FO, p->IE, p->IO, p->hankel_w, p->int_wt, p->q_pts, p->A0, p->C0, p->C1, p->W0, p->W1, p->W2, p->A0s, p->C0s, p->rt0, p->stage_out,
                     p->v2d, p->unk2d, p->dft_cs, p->T2a, p->T2b, p->orders_dev, p->kind_dev, p->act_index_dev, p->radial_mask_dev, p->v0_dev, p->pd_dev, p->vt_dev,
                     p->xt, p->tt, p->g, p->gn, p->vw, p->sigma, p->sweeps_dev, p->jac_counter, p->pp, p->gn_u, p->pp_u, p->sigma_u, p->i00, p->gemmY_dev, p->gemmY_tp, p->gemmM_dev, p->gemmT_dev, p->gemmM_tp, p->gemmT_tp,
-                    p->init_support_dev, p->avg_mean, p->rho_pool, p->rh_pool, p->mask_pool, p->ls_ints, p->ls_dbl, p->partial, p->err, p->mm};
+                    p->init_support_dev, p->avg_mean, p->d2_x, p->d2_b, p->d2_ref, p->d2_norm, p->d2_hist, p->d2_gemm, p->d2_tp, p->rho_pool, p->rh_pool, p->mask_pool, p->ls_ints, p->ls_dbl, p->partial, p->err, p->mm};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& kv : p->hk_cache) cudaFree(kv.second.first);
     for (auto& kv : p->dft_tiles) cudaFree(kv.second.first);
@@ -618,10 +622,10 @@ static int launch_jacobi(xfb_plan* p, const double* g, double* gn, double* pp, d
     const int smem_doubles = (int)(p->jacobi_smem / 8);
     if (!p->jac_counter) { if (dev_alloc(p, &p->jac_counter, 2)) return 1; }
     XFB_CUDA(cudaMemsetAsync(p->jac_counter, 0, 2 * sizeof(int), st));
-    const long long sig_run = (long long)na * p->n_r;
+    const long long sig_run = (long long)na * p->sig_ld;
     if (p->jacobi_big) {
         procrustes_jacobi_kernel<16, 256, false, 1, 32><<<std::min(na * nb, p->n_sm), 256, p->jacobi_smem, st>>>(
-            g, gn, pp, sigma, p->orders_dev, na, nb, p->n_r, p->g_run, sig_run, p->sv_cutoff, 1e-15, p->max_sweeps, sweeps, smem_doubles, p->jac_counter, 0, na);
+            g, gn, pp, sigma, p->orders_dev, na, nb, p->sig_ld, p->g_run, sig_run, p->sv_cutoff, 1e-15, p->max_sweeps, sweeps, smem_doubles, p->jac_counter, 0, na);
         XFB_CUDA(cudaGetLastError());
         return 0;
     }
@@ -635,10 +639,10 @@ static int launch_jacobi(xfb_plan* p, const double* g, double* gn, double* pp, d
     }
     if (n_big > 0)
         procrustes_jacobi_kernel<8, 512, true, 1, 16><<<std::min(n_big * nb, p->n_sm), 512, p->jacobi_smem, st>>>(
-            g, gn, pp, sigma, p->orders_dev, n_big, nb, p->n_r, p->g_run, sig_run, p->sv_cutoff, 1e-15, p->max_sweeps, sweeps, smem_doubles, p->jac_counter, 0, na);
+            g, gn, pp, sigma, p->orders_dev, n_big, nb, p->sig_ld, p->g_run, sig_run, p->sv_cutoff, 1e-15, p->max_sweeps, sweeps, smem_doubles, p->jac_counter, 0, na);
     if (n_small > 0)
         procrustes_jacobi_kernel<4, 256, true, 2, 8><<<std::min(n_small * nb, 2 * p->n_sm), 256, JAC_SMALL_SMEM, s_small>>>(
-            g, gn, pp, sigma, p->orders_dev, n_small, nb, p->n_r, p->g_run, sig_run, p->sv_cutoff, 1e-15, p->max_sweeps, sweeps, JAC_SMALL_SMEM / 8,
+            g, gn, pp, sigma, p->orders_dev, n_small, nb, p->sig_ld, p->g_run, sig_run, p->sv_cutoff, 1e-15, p->max_sweeps, sweeps, JAC_SMALL_SMEM / 8,
             p->jac_counter + 1, n_big, na);
     XFB_CUDA(cudaGetLastError());
     if (n_big > 0 && n_small > 0) {          // join
@@ -677,6 +681,51 @@ static int project_i(xfb_plan* p, const double2* c_in, double2* c_out, int nb, c
                procrustes_unpack_kernel<<<dim3(p->L + 1, nb), 256, 0, st>>>(c_in, c_out, p->tt, p->orders_dev, p->kind_dev, p->act_index_dev,
                                                                             p->radial_mask_dev, p->v0_dev, p->inv_sqrt_np, p->L, p->n_r, S,
                                                                             p->xt_run, half));
+    return 0;
+}
+
+// ---- degree-2 invariants of a batch of coefficient arrays (internal layout, real field) ---------------------------------
+static int ensure_deg2_alloc(xfb_plan* p, cudaStream_t st) {
+    if (p->d2_x) return 0;
+    if (p->dims != 3) XFB_FAIL("degree-2 invariants on the device are built for the 3-D plan");
+    const size_t B = p->max_batch, n_r = p->n_r, L1 = p->L + 1;
+    if (dev_alloc(p, &p->d2_x, B * (size_t)p->NLM * n_r)) return 1;
+    if (dev_alloc(p, &p->d2_b, B * L1 * n_r * n_r)) return 1;
+    std::vector<GemmProblem> pr; std::vector<int> tp;
+    for (size_t b = 0; b < B; ++b)
+        for (int l = 0; l <= p->L; ++l) {
+            GemmProblem g{};       // B_l [N_r x N_r] = X_l^T-view [N_r x (2l+1)] . X_l [(2l+1) x N_r]
+            const double* X = p->d2_x + b * (size_t)p->NLM * n_r + (size_t)l * l * n_r;
+            g.A = X; g.a_rs = 1; g.a_cs = (long long)n_r;
+            g.B = X; g.b_rs = (long long)n_r; g.b_cs = 1;
+            g.C = p->d2_b + (b * L1 + l) * n_r * n_r; g.c_rs = (long long)n_r; g.c_cs = 1;
+            g.M = (int)n_r; g.N = (int)n_r; g.K = 2 * l + 1; g.alpha = 1.0;
+            g.tile0 = (int)tp.size(); g.tiles_n = cdiv(g.N, GG_BN);
+            for (int t = 0; t < cdiv(g.M, GG_BM) * g.tiles_n; ++t) tp.push_back((int)pr.size());
+            pr.push_back(g);
+        }
+    if (dev_alloc(p, &p->d2_gemm, pr.size())) return 1;
+    if (dev_alloc(p, &p->d2_tp, tp.size())) return 1;
+    XFB_CUDA(cudaMemcpyAsync(p->d2_gemm, pr.data(), pr.size() * sizeof(GemmProblem), cudaMemcpyHostToDevice, st));
+    XFB_CUDA(cudaMemcpyAsync(p->d2_tp, tp.data(), tp.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    XFB_CUDA(cudaStreamSynchronize(st));
+    p->d2_tiles_run = (int)(tp.size() / B);
+    return 0;
+}
+// c: coefficients [(L+1)^2][S] of a real field (m >= 0 valid) -> p->d2_b [nb][L+1][N_r][N_r] real
+static int deg2_invariants_i(xfb_plan* p, const double2* c, int nb, cudaStream_t st) {
+    if (ensure_deg2_alloc(p, st)) return 1;
+    const int S = nb * p->n_r;
+    XFB_LAUNCH(p, PG_PROC_PACK, st, pack_real_all_kernel<<<dim3(p->L + 1, nb), 256, 0, st>>>(c, p->d2_x, p->n_r, S, (long long)p->NLM * p->n_r));
+    XFB_LAUNCH(p, PG_PROC_GEMM, st, grouped_gemm_kernel<<<nb * p->d2_tiles_run, 128, 0, st>>>(p->d2_gemm, p->d2_tp));
+    return 0;
+}
+static int deg2_diff_i(xfb_plan* p, const double2* c, int nb, double* err_out, long long err_run_stride, cudaStream_t st) {
+    if (!p->d2_ref) XFB_FAIL("deg2_invariant_l2_diff: reference invariants not set (xfb_plan_set_deg2_reference)");
+    if (deg2_invariants_i(p, c, nb, st)) return 1;
+    XFB_LAUNCH(p, PG_MISC, st,
+               deg2_diff_kernel<<<dim3(p->L + 1, nb), 256, 0, st>>>(p->d2_b, p->d2_ref, p->d2_norm, p->radial_mask_dev, p->n_r, p->L + 1,
+                                                                   (long long)(p->L + 1) * p->n_r * p->n_r, err_out, err_run_stride));
     return 0;
 }
 
@@ -769,7 +818,8 @@ int xfb_plan_set_projection(xfb_plan* p, const xfb_projection_desc* d) {
         const int nc = d->n_cols[l];
         p->ncols_all[l] = nc;
         const double* V = d->v[l];
-        if (nc > n_r) XFB_FAIL("order %d: n_cols=%d exceeds N_r=%d", l, nc, n_r);
+        // n_cols > N_r happens when the data come on a finer q grid (n_cols = min(N_q_data, 2l+1)) and are regridded to N_r points
+        if (nc < 1 || nc > 2 * l + 1) XFB_FAIL("order %d: n_cols=%d outside 1..2l+1", l, nc);
         if (l == 0) {
             kind[0] = ORD_ZEROTH;
             for (int k = 0; k < n_r; ++k) v0[k] = V[(size_t)k * nc];
@@ -825,12 +875,14 @@ int xfb_plan_set_projection(xfb_plan* p, const xfb_projection_desc* d) {
         if (dev_alloc(p, &p->gn, B * p->g_run)) return 1;
         if (dev_alloc(p, &p->vw, B * p->vw_run)) return 1;
         XFB_CUDA(cudaMemset(p->vw, 0, B * p->vw_run * sizeof(double)));     // rows of dropped columns are never written: keep them finite
-        if (dev_alloc(p, &p->sigma, B * na * n_r)) return 1;
+        p->sig_ld = n_r;
+        for (const ProcOrder& o : p->orders) p->sig_ld = std::max(p->sig_ld, o.n_cols);
+        if (dev_alloc(p, &p->sigma, B * na * p->sig_ld)) return 1;
         if (dev_alloc(p, &p->sweeps_dev, B * na)) return 1;
         if (dev_alloc(p, &p->pp, B * p->g_run)) return 1;
         if (dev_alloc(p, &p->gn_u, (size_t)p->g_run)) return 1;
         if (dev_alloc(p, &p->pp_u, (size_t)p->g_run)) return 1;
-        if (dev_alloc(p, &p->sigma_u, na * n_r)) return 1;
+        if (dev_alloc(p, &p->sigma_u, na * p->sig_ld)) return 1;
         if (dev_alloc(p, &p->gemmM_dev, B * na)) return 1;
         if (dev_alloc(p, &p->gemmT_dev, B * na)) return 1;
         if (dev_alloc(p, &p->gemmY_dev, B * na)) return 1;
@@ -986,6 +1038,53 @@ int xfb_get_unknowns(xfb_plan* p, int32_t run, int32_t order, double* out_dev, v
     return 0;
 }
 
+// ---- degree-2 invariants (fxs_invariant_tools.py:915-923) and deg2_invariant_l2_diff (fxs_IO_methods.py:412-447) ----------
+int xfb_plan_set_deg2_reference(xfb_plan* p, const double* bref_host, const double* norm_host) {
+    if (!p || !bref_host || !norm_host) XFB_FAIL("null argument");
+    if (p->dims != 3) XFB_FAIL("xfb_plan_set_deg2_reference: 3-D plans only");
+    if (!p->has_proj) XFB_FAIL("set the projection constants first (the radial mask is shared)");
+    const size_t n = (size_t)(p->L + 1) * p->n_r * p->n_r;
+    if (!p->d2_ref) { if (dev_alloc(p, &p->d2_ref, n)) return 1; if (dev_alloc(p, &p->d2_norm, (size_t)p->L + 1)) return 1; }
+    XFB_CUDA(cudaMemcpy(p->d2_ref, bref_host, n * sizeof(double), cudaMemcpyHostToDevice));
+    XFB_CUDA(cudaMemcpy(p->d2_norm, norm_host, (size_t)(p->L + 1) * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+int xfb_deg2_invariants(xfb_plan* p, const double* direct_in, double* bl_out, int32_t nb, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nb < 1 || nb > p->max_batch) XFB_FAIL("n_batch=%d outside plan capacity", nb);
+    const int S = nb * p->n_r;
+    if (transpose_i(p, (const double2*)direct_in, p->C0, S, p->NLM, st)) return 1;
+    if (deg2_invariants_i(p, p->C0, nb, st)) return 1;
+    XFB_CUDA(cudaMemcpyAsync(bl_out, p->d2_b, (size_t)nb * (p->L + 1) * p->n_r * p->n_r * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+int xfb_deg2_invariant_diff(xfb_plan* p, const double* direct_in, double* err_out, int32_t nb, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nb < 1 || nb > p->max_batch) XFB_FAIL("n_batch=%d outside plan capacity", nb);
+    const int S = nb * p->n_r;
+    if (transpose_i(p, (const double2*)direct_in, p->C0, S, p->NLM, st)) return 1;
+    return deg2_diff_i(p, p->C0, nb, err_out, p->L + 1, st);
+}
+int xfb_mtip_enable_deg2_metric(xfb_plan* p, int32_t on, int32_t history_capacity) {
+    if (!on) { p->d2_metric = false; return 0; }
+    if (!p->d2_ref) XFB_FAIL("deg2 metric: reference invariants not set (xfb_plan_set_deg2_reference)");
+    if (history_capacity < 1) XFB_FAIL("deg2 metric: history capacity must be >= 1");
+    if (p->d2_hist && history_capacity > p->d2_hist_cap) { cudaFree(p->d2_hist); p->d2_hist = nullptr; }
+    if (!p->d2_hist) {
+        if (dev_alloc(p, &p->d2_hist, (size_t)p->max_batch * history_capacity * (p->L + 1))) return 1;
+        p->d2_hist_cap = history_capacity;
+    }
+    p->d2_metric = true;
+    return 0;
+}
+// out_dev [n_batch][capacity][L+1] (the first min(iterations done, capacity) rows of every run are valid)
+int xfb_mtip_get_deg2_errors(xfb_plan* p, double* out_dev, int32_t capacity, void* stream) {
+    if (!p->d2_hist) XFB_FAIL("deg2 metric was not enabled");
+    if (capacity != p->d2_hist_cap) XFB_FAIL("capacity %d != the enabled history capacity %d", capacity, p->d2_hist_cap);
+    XFB_CUDA(cudaMemcpyAsync(out_dev, p->d2_hist, (size_t)p->n_batch * capacity * (p->L + 1) * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
 int xfb_modify_intensity(xfb_plan* p, const double* rho_hat, const double* i_proj, double* out, int32_t nb, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (nb < 1 || nb > p->max_batch) XFB_FAIL("n_batch=%d outside plan capacity", nb);
@@ -1067,6 +1166,11 @@ static int iterate_range(xfb_plan* p, int b0, int nb, int method, int ft_stab, d
     } else {
         XFB_LAUNCH(p, PG_POINTWISE, st, square_kernel<<<ew_blocks((long long)nb * p->G), 256, 0, st>>>(p->W0, p->W1, (long long)nb * p->G));
         if (sht_forward_i(p, flat_view(p->W1, p->G), p->n_r, p->C0, S, st, nullptr, 1, &half)) return 1;
+    }
+    // optional reciprocal metric deg2_invariant_l2_diff of the current iterate's I_lm (MTIP_start sketch, reconstruct.py:526)
+    if (p->d2_metric && it_index < p->d2_hist_cap) {
+        const long long rs = (long long)p->d2_hist_cap * (p->L + 1);
+        if (deg2_diff_i(p, p->C0, nb, p->d2_hist + (long long)b0 * rs + (long long)it_index * (p->L + 1), rs, st)) return 1;
     }
     // 3. projection onto the invariants                      (:521-523)
     if (project_i(p, p->C0, p->C1, nb, st, half)) return 1;

@@ -309,6 +309,46 @@ class Plan:
         _lib.check(self.lib.xfb_project_invariants(self.h, _ptr(direct), _ptr(out), nb, _stream()))
         return out
 
+    # ------------------------------------------------------------------ degree-2 invariants
+    def deg2_invariants(self, direct):
+        """harmonic_coeff_to_deg2_invariants_3d (fxs_invariant_tools.py:915-923) for the coefficients of a REAL field:
+        direct [nb, N_r, (L+1)^2] complex -> B_l [nb, L+1, N_r, N_r] float64 (real symmetric)."""
+        nb = self._nb(direct, (self.n_r, self.n_lm))
+        out = torch.empty((nb, self.l_max + 1, self.n_r, self.n_r), dtype=torch.float64, device=direct.device)
+        _lib.check(self.lib.xfb_deg2_invariants(self.h, _ptr(direct), _ptr(out), nb, _stream()))
+        return out
+
+    def set_deg2_reference(self, reference_invariants, radial_mask, number_of_particles=1.0):
+        """Constants of deg2_invariant_l2_diff (_generate_deg2_invariant_diff_3d, fxs_IO_methods.py:412-447):
+        reference_invariants [L+1, N_r, N_r] = V_l V_l^H of the final projection matrices (fxs_Projections.py:631-637)."""
+        ref = np.asarray(reference_invariants)
+        if np.iscomplexobj(ref):
+            if np.abs(ref.imag).max() > 0:
+                raise _lib.XfbError("deg2 reference invariants must be real (real projection matrices)")
+            ref = ref.real
+        rm = np.broadcast_to(np.asarray(radial_mask, dtype=bool), (self.l_max + 1, self.n_r))
+        ref = np.where(rm[:, :, None] & rm[:, None, :], ref, 0.0)                       # reference_masked[mask] = 0  (:422-424)
+        norm = np.ascontiguousarray((ref * ref).sum(axis=(1, 2)), dtype=np.float64)    # :426
+        ref = np.ascontiguousarray(ref, dtype=np.float64).copy()
+        ref[0] = ref[0] / float(number_of_particles)                                    # :440
+        _lib.check(self.lib.xfb_plan_set_deg2_reference(self.h, _dp(ref), _dp(norm)))
+
+    def deg2_invariant_diff(self, direct):
+        """Per-order error array [nb, L+1] of deg2_invariant_l2_diff for coefficient arrays [nb, N_r, (L+1)^2]."""
+        nb = self._nb(direct, (self.n_r, self.n_lm))
+        out = torch.empty((nb, self.l_max + 1), dtype=torch.float64, device=direct.device)
+        _lib.check(self.lib.xfb_deg2_invariant_diff(self.h, _ptr(direct), _ptr(out), nb, _stream()))
+        return out
+
+    def mtip_enable_deg2_metric(self, on, capacity=1):
+        self._deg2_cap = int(capacity)
+        _lib.check(self.lib.xfb_mtip_enable_deg2_metric(self.h, int(bool(on)), int(capacity)))
+
+    def mtip_deg2_errors(self, n_done):
+        out = torch.empty((self.n_batch, self._deg2_cap, self.l_max + 1), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.xfb_mtip_get_deg2_errors(self.h, _ptr(out), self._deg2_cap, _stream()))
+        return out[:, :min(int(n_done), self._deg2_cap)]
+
     def modify_intensity(self, rho_hat, i_proj):
         nb = self._nb(rho_hat, self.grid_shape)
         self._c128(i_proj, self.grid_shape)

@@ -66,13 +66,26 @@ class ProjectWorker:
         popt = settings['projections']['real']['projections']
         self.initial_support = S.initial_support(self.plan, popt['support']['initial_support'])
         err = settings['main_loop']['error']['methods']
-        if list(err['real']['calculate']) != ['l2_projection_diff'] or list(err['reciprocal'].get('calculate', [])):
-            raise XfbError("xframe_b200 computes the default error metric (real: [l2_projection_diff], reciprocal: [])")
+        recip = list(err['reciprocal'].get('calculate', []))
+        main_metrics = err.get('main', {}).get('metrics', {'real': ['l2_projection_diff'], 'reciprocal': []})
+        if list(err['real']['calculate']) != ['l2_projection_diff'] or list(main_metrics.get('real', [])) != ['l2_projection_diff'] \
+                or list(main_metrics.get('reciprocal', [])):
+            raise XfbError("xframe_b200 drives the loop with the default main error (real: [l2_projection_diff])")
+        if recip not in ([], ['deg2_invariant_l2_diff']) or (recip and self.dims != 3):
+            raise XfbError(f"reciprocal error metrics {recip}: xframe_b200 computes deg2_invariant_l2_diff (3-D) only")
+        self.deg2_metric = bool(recip)
         inside = err['real'].get('l2_projection_diff', {}).get('inside_initial_support', False)
         hio = settings['projections']['real']['HIO']
         self.plan.set_real(popt['apply'], self.initial_support, popt.get('value_threshold', {}).get('threshold', (False, False)),
                            popt.get('limit_imag', {}).get('threshold', 0.0), hio.get('considered_projections', ['all']), inside,
                            average_center_shells=int(popt.get('average_center', {}).get('max_radial_id', 1)))
+        if self.deg2_metric:      # reference invariants V_l V_l^H of the final projection matrices (fxs_Projections.py:631-637)
+            pm = self.proj.projection_matrices
+            ref = np.zeros((self.plan.l_max + 1, self.plan.n_r, self.plan.n_r))
+            for l, v in enumerate(pm):
+                ref[l] = np.asarray(v).real @ np.asarray(v).real.T
+            self.n_used_orders = len(pm)
+            self.plan.set_deg2_reference(ref, self.proj.radial_mask, self.proj.number_of_particles)
         base = settings['GPU'].get('seed', None)
         self.seeds = seeds if seeds is not None else [None if base is None else base + i for i in range(self.n_runs)]
         self.initial_densities = initial_densities
@@ -120,7 +133,11 @@ class ProjectWorker:
         for b0 in range(0, len(self.run_ids), self.batch):
             ids = self.run_ids[b0:b0 + self.batch]
             rho0 = torch.from_numpy(np.stack([self._guess(i) for i in ids])).to(plan.device)
+            if self.deg2_metric:
+                from .reconstruct import iteration_count
+                plan.mtip_enable_deg2_metric(True, iteration_count(self.opt)[0])
             res = run_schedule(plan, self.opt, rho0)
+            deg2_hist = plan.mtip_deg2_errors(res['errors'].shape[1]).cpu().numpy()[..., :self.n_used_orders] if self.deg2_metric else None
             unknowns = [plan.unknowns(k) for k in range(len(ids))]      # of the last mtip_start (reconstruct.py:523,1013)
             if self.shift_to_center:                                    # output modifier on the best and the last pair (:988-989)
                 if self.fix_orientation and not hasattr(self, '_so_rot'):
@@ -137,12 +154,13 @@ class ProjectWorker:
             # last_deg2_invariant: B_l = I_l I_l^H of the last density (reconstruct.py:757-765,993)
             last = torch.from_numpy(res['last_real']).to(plan.device)
             fd = plan.ft(last)
-            I = plan.sht_forward((fd * fd.conj()).real.to(torch.complex128).contiguous()).cpu().numpy()
+            I = plan.sht_forward((fd * fd.conj()).real.to(torch.complex128).contiguous())
+            if self.dims == 3:                             # B_l = I_l I_l^H on the device (grouped DMMA GEMM, csrc/procrustes.cuh)
+                deg2 = plan.deg2_invariants(I).to(torch.complex128).cpu().numpy()
+            else:                                          # B_m = I_m I_m^* (fxs_invariant_tools.py:906-914): outer products
+                Im = I[..., :plan.l_max + 1]
+                deg2 = torch.einsum('bqm,bpm->bmqp', Im, Im.conj()).cpu().numpy()
             for k, rid in enumerate(ids):
-                if self.dims == 3:
-                    Il = [I[k][:, l * l:(l + 1) * (l + 1)] for l in range(plan.l_max + 1)]
-                else:                                      # B_m = I_m I_m^* (fxs_invariant_tools.py:906-914)
-                    Il = [I[k][:, m:m + 1] for m in range(plan.l_max + 1)]
                 n_it = res['errors'].shape[1]
                 out.append({
                     'run_id': rid,
@@ -150,13 +168,14 @@ class ProjectWorker:
                     'reciprocal_density': res['best_reciprocal'][k], 'last_reciprocal_density': res['last_reciprocal'][k],
                     'final_error': float(res['best_error'][k]), 'initial_density': res['initial_density'][k],
                     'initial_support': self.initial_support.copy(),
-                    'error_dict': {'main': res['errors'][k].copy(), 'real': {'l2_projection_diff': res['errors'][k].copy()}, 'reciprocal': {}},
+                    'error_dict': {'main': res['errors'][k].copy(), 'real': {'l2_projection_diff': res['errors'][k].copy()},
+                                   'reciprocal': {'deg2_invariant_l2_diff': deg2_hist[k].copy()} if self.deg2_metric else {}},
                     'support_mask': res['best_support'][k], 'last_support_mask': res['last_support'][k],
                     'loop_iterations': res['loop_iterations'], 'fxs_unknowns': unknowns[k],
                     'n_particles': np.array([[self.proj.number_of_particles]] * n_it), 'n_particles_gradients': np.array([]),
                     'n_particles_fraction': np.array([]),
                     'grid_pair': {'real_grid': rs, 'reciprocal_grid': qs}, 'projection_matrices': masked_pm,
-                    'last_deg2_invariant': np.array([il @ il.T.conj() for il in Il]),
+                    'last_deg2_invariant': deg2[k],
                 })
         self.results['MTIP'] = out
         self.results['stats']['run_time'] = time.time() - t0
