@@ -407,6 +407,29 @@ def run_ours(args):
     e2e_value = total * Ke / float(t.item())
     finite = bool(torch.isfinite(h_err).all())
 
+    # ---- final gather of the densities to rank 0 over NCCL (the only exchange of the path, reconstruct.py:160-183); timed on
+    #      its own, outside the step
+    gather = None
+    if world > 1:
+        from xframe_b200.distributed import gather_results
+        loc = {'last_real_density': plan.mtip_grid('last_real'), 'final_error': plan.mtip_errors()[1]}
+        gather_results({'final_error': loc['final_error']}, total)          # warm-up: communicator set-up
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        g0.record()
+        full = gather_results(loc, total)
+        g1.record()
+        barrier()
+        gms = g0.elapsed_time(g1)
+        moved = (total - nb) * int(np.prod(plan.grid_shape)) * 16
+        ok = True
+        if rank == 0:
+            mine = full['last_real_density'][torch.as_tensor(ids, device=full['last_real_density'].device)]
+            ok = bool(torch.equal(mine, loc['last_real_density'])) and full['last_real_density'].shape[0] == total
+        gather = {'api': 'xframe_b200.distributed.gather_results (ncclGather of last_real_density + final_error to rank 0)',
+                  'bytes_over_nvlink': moved, 'ms': gms, 'GBps': moved / (gms * 1e-3) / 1e9 if gms > 0 else None, 'rank0_check': ok}
+        del full
+
     if rank == 0:
         peak, peak_src = peaks()
         ab = algorithmic_bytes(nb)
@@ -465,7 +488,7 @@ def run_ours(args):
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': nb * int(np.prod(plan.grid_shape)) * 16 * world,
                     'd2h_bytes_per_step': (nb * int(np.prod(plan.grid_shape)) * 16 + nb * 16) * world, 'steps': Ke,
                     'api': 'xfb_mtip_step_host (C-ABI, pinned host buffers, H2D + iteration + D2H per step)', 'finite': finite},
-            'gpu_launches': int(launches), 'clocks': clk.summary(),
+            'gpu_launches': int(launches), 'clocks': clk.summary(), 'gather': gather,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -51,6 +51,7 @@ struct xfb_plan {
     // intermediate `a` could stay inside the 126 MB L2.  Measured at 128 runs (profiles/r02a_sht_chunk_sweep.md): 9.2 - 13.5 ms
     // per step for the six transforms against 8.24 ms unchunked -- the smaller launches lose more than the L2 hits gain.
     int sht_chunk = 0, sht_streams = 3;
+    int leg_min_groups = 8;
     cudaStream_t sht_side[4] = {}; cudaEvent_t sht_fork = nullptr, sht_join[4] = {};
     long long launches_side = 0;
     // host-buffer pipeline (xfb_mtip_step_host)
@@ -235,6 +236,7 @@ int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
     if (dev_alloc(p, &p->rt0, B * p->n_theta * p->n_phi)) return 1;
     if (const char* e = getenv("XFB_SHT_CHUNK")) p->sht_chunk = std::max(0, atoi(e));          // experiments: sweep without rebuilding
     if (const char* e = getenv("XFB_SHT_STREAMS")) p->sht_streams = std::min(4, std::max(1, atoi(e)));
+    if (const char* e = getenv("XFB_LEG_MINGROUPS")) p->leg_min_groups = std::max(0, atoi(e));
     p->leg2 = (p->n_theta / 2 <= 64 && p->NP <= 64 && p->n_theta % 4 == 0);
     p->leg3_big = p->leg2 && (p->n_theta / 2 > 32 || p->NP > 32);
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, dev); }
@@ -338,7 +340,10 @@ static int leg3_grid_x(const xfb_plan* p, int S, int pos_only, int share) {
     const int cap = std::max(1, (resident * LEG3_WAVES) / ((p->L + 1) * std::max(1, share)));
     int gx = std::min(groups, cap);
     if (share > 1) gx = std::max(1, std::min(gx, cdiv(groups, 4)));       // chunked launches: at least 4 groups per CTA
-    return gx;
+    // small batches (the 16 / 32-run shards of 8 / 4 GPUs): at least leg_min_groups shell groups per CTA, so the table fragments
+    // and the pipeline fill are amortised, unless that leaves less than one wave of CTAs
+    if (p->leg_min_groups > 0) gx = std::min(gx, std::max(cdiv(resident, p->L + 1), cdiv(groups, p->leg_min_groups)));
+    return std::max(1, gx);
 }
 // forward: a [S][M2][n_theta] -> c (+ chunk offset, row stride c_stride);  inverse: c -> a
 static int launch_legendre3(xfb_plan* p, bool forward, double2* a, double2* c, int S, long long c_stride, int pos_only, int gx, cudaStream_t st) {

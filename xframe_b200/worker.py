@@ -180,3 +180,81 @@ class ProjectWorker:
         self.results['MTIP'] = out
         self.results['stats']['run_time'] = time.time() - t0
         return out, {'worker': self}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# post-processing and the multi-GPU entry point
+# ---------------------------------------------------------------------------------------------------------------------
+def assemble_reconstruction_record(results, stats, xray_wavelength, reciprocity_coefficient):
+    """The dict the reference hands to db.save('reconstructions', ...) (post_processing, reconstruct.py:160-183; layout read
+    back by _database_.py:223-390 and asserted in tests/test_fxs_integration.py:388-421): results ranked by their LAST main
+    error, grid pair and projection matrices stored once."""
+    results = [dict(r) for r in results]
+    errors, grid_pair, projection_matrices = [], None, None
+    for r in results:
+        grid_pair = r.pop('grid_pair')
+        projection_matrices = r.pop('projection_matrices')
+        r.pop('run_id', None)
+        errors.append(r['error_dict']['main'][-1])
+    order = np.argsort(errors)
+    return {'configuration': {'internal_grid': grid_pair, 'xray_wavelength': xray_wavelength, 'reciprocity_coefficient': reciprocity_coefficient},
+            'reconstruction_results': {str(i): results[i] for i in order},
+            'projection_matrices': projection_matrices, 'stats': stats}
+
+
+_GATHERED = ('real_density', 'last_real_density', 'reciprocal_density', 'last_reciprocal_density', 'initial_density',
+             'support_mask', 'last_support_mask', 'last_deg2_invariant')
+
+
+def run_distributed(settings, data, n_reconstructions=None, seeds=None, initial_densities=None):
+    """`torchrun --nproc-per-node N` entry: run i -> rank i mod N (reconstruct.py:141-157 forks one process per run instead),
+    no per-iteration collective, one final gather of every run's arrays to rank 0 over NCCL (NVLink / NVSwitch) where the
+    reference's post_processing builds the ranked record.  Returns the record on rank 0, None elsewhere."""
+    import os
+    import torch.distributed as dist
+    from .distributed import gather_results
+    rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    own_group = False
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        own_group = True
+    w = ProjectWorker(settings, data, n_reconstructions=n_reconstructions, rank=rank, world=world, device=local, seeds=seeds,
+                      initial_densities=initial_densities)
+    res, _ = w.run()
+    dev = w.plan.device
+    n_unk = sum(int(np.prod(u.shape)) for u in res[0]['fxs_unknowns']) if res else 0
+    local_t = {k: torch.from_numpy(np.stack([np.asarray(r[k]) for r in res])).to(dev) for k in _GATHERED}
+    local_t['main_error'] = torch.from_numpy(np.stack([r['error_dict']['main'] for r in res])).to(dev)
+    local_t['final_error'] = torch.tensor([r['final_error'] for r in res], dtype=torch.float64, device=dev)
+    if n_unk:
+        local_t['fxs_unknowns'] = torch.from_numpy(np.stack([np.concatenate([np.asarray(u).ravel() for u in r['fxs_unknowns']]) for r in res])).to(dev)
+    full = gather_results(local_t, w.n_runs, device=dev)
+    record = None
+    if rank == 0:
+        shapes = [u.shape for u in res[0]['fxs_unknowns']]
+        out = []
+        for i in range(w.n_runs):
+            r = dict(res[0])                      # run-independent entries (grid pair, projection matrices, initial support, ...)
+            r.update({k: full[k][i].cpu().numpy() for k in _GATHERED})
+            err = full['main_error'][i].cpu().numpy()
+            r['error_dict'] = {'main': err, 'real': {'l2_projection_diff': err.copy()}, 'reciprocal': {}}
+            r['final_error'] = float(full['final_error'][i])
+            if n_unk:
+                flat, unk, o = full['fxs_unknowns'][i].cpu().numpy(), [], 0
+                for sh in shapes:
+                    n = int(np.prod(sh))
+                    unk.append(flat[o:o + n].reshape(sh))
+                    o += n
+                r['fxs_unknowns'] = tuple(unk)
+            r['run_id'] = i
+            out.append(r)
+        fto = settings['fourier_transform']
+        record = assemble_reconstruction_record(out, dict(w.results['stats']), data.get('xray_wavelength', None),
+                                                fto.get('reciprocity_coefficient', np.pi))
+    if own_group:
+        dist.barrier()
+        dist.destroy_process_group()
+    w.plan.close()
+    return record
+
