@@ -429,6 +429,16 @@ class ReciprocalProjection:
             return reciprocal_density * mult
 
 
+    def project_to_fixed_intensity(self, reciprocal_density, square, fixed_intensity):   # :889-925, use_fixed_intensity=True
+        nz = (square.real >= 0) & (fixed_intensity >= 0)
+        temp = np.zeros(reciprocal_density.shape)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            temp[nz] = fixed_intensity[nz] / square[nz].real
+            mult = np.sqrt(temp).astype(complex)
+            mult[~nz] = 0
+            return reciprocal_density * mult
+
+
 # --------------------------------------------------------------------------
 # real projection / HIO / ER / errors / shrink wrap
 # --------------------------------------------------------------------------
@@ -592,9 +602,12 @@ class MTIP:
         I_proj = self.sh.inverse_l(Ip)
         return rp.project_to_modified_intensity(rho_hat, np.array(sq), I_proj)
 
-    def io_step(self, method, rho, ft_stab):
+    def io_step(self, method, rho, ft_stab, fixed_intensity=None):
         rho_hat = self.ft(rho)
-        rho_hat_new = self.mtip_start(rho_hat)
+        if fixed_intensity is None:
+            rho_hat_new = self.mtip_start(rho_hat)
+        else:                                    # MTIP_start_non_FXS sketch (reconstruct.py:529-534)
+            rho_hat_new = self.rp.project_to_fixed_intensity(rho_hat, np.array(square_grid(rho_hat)), fixed_intensity)
         if ft_stab:
             rho_rt = self.ift(rho_hat)
             rho_new = add_above_zero_index(self.ift(rho_hat_new), rho - rho_rt)
@@ -602,7 +615,7 @@ class MTIP:
             rho_new = self.ift(rho_hat_new)
         rho_new_copy = np.array(rho_new)
         proj = self.real_pr.projection(rho_new)
-        if method == 'HIO':
+        if method.startswith('HIO'):
             considered = self.opt['projections']['real']['HIO'].get('considered_projections', ['all'])
             rho_next = hybrid_input_output(self.beta, rho_new_copy, proj, rho, considered)
         else:
@@ -679,6 +692,10 @@ class MTIP:
                 update_sw(0, lid)
             step, sw_step = 0, 0
             it = 0
+            # `hist` of the reference's loop (reconstruct.py:853,911): bound at the start of the sub-loop and re-bound at the start
+            # of every HIO/ER iteration, i.e. after an iteration it still names the pair that iteration STARTED from
+            hist_last = state['pair']
+            latest_intensity = None
             for it in range(1, lopt['iterations'] + 1):
                 for key in lopt['order']:
                     mo = lopt['methods'][key]
@@ -692,11 +709,33 @@ class MTIP:
                         state['mask'] = self.real_pr.support
                         sw_step += 1
                         update_sw(sw_step, lid)
+                    elif key == 'SW_center':             # reconstruct.py:886-897 with the sketch :606-613
+                        # The sketch ends in ['calculate_support_mask','id','id'] on (conv, x, FT(x), x); get_new_mask takes ONE
+                        # argument (fxs_Projections.py:247), so the process returns (support, x, FT(x)) and the loop binds
+                        # `support, ft_density, density` to it: the history pair becomes (reciprocal = x, real = FT(x)) -- the
+                        # real and reciprocal densities are exchanged (a quirk of the reference, reproduced here and on the device).
+                        enforce = np.float64(errors['main'][-1]) > limit    # scalar against the one-element list (:887)
+                        self.real_pr.enforce_initial_support = enforce
+                        enforce_list.append(enforce)
+                        for _ in range(repeats):
+                            rho_c = state['pair'][1]
+                            support = self.shrink_wrap(rho_c)
+                            self.real_pr.support = support
+                            state['mask'] = self.real_pr.support
+                            state['pair'] = (np.array(rho_c), self.ft(rho_c))
+                            sw_step += 1
+                            update_sw(sw_step, lid)
                     else:
+                        if key in ('ER_non_FXS', 'HIO_non_FXS'):     # :899-904
+                            if latest_intensity is None:
+                                latest_intensity = np.abs(hist_last[0]).real
+                        else:
+                            latest_intensity = None
                         ft_stab = bool(mo.get('ft_stab', False)) if isinstance(mo, dict) else False
                         for _ in range(repeats):
                             self.beta = beta_ramp.eval(step)
-                            new_pair = self.io_step(key, state['pair'][1], ft_stab)
+                            hist_last = state['pair']
+                            new_pair = self.io_step(key, state['pair'][1], ft_stab, latest_intensity)
                             new_pair = tuple(np.array(a) for a in new_pair)
                             state['pair'] = new_pair
                             main = float(np.mean([errors['real']['l2_projection_diff'][-1]]))

@@ -78,6 +78,38 @@ def test_reference_loop_with_default_apply_list_matches_oracle(n_r):
     assert got['loop_iterations'] == ref['loop_iterations']
 
 
+def sketch_tail_settings(gpu):
+    """SW_center, the non-FXS methods (fixed-intensity projection) and a finite best_density_not_in_first_n_iterations
+    (reconstruct.py:529-534,606-613,886-904,945-949) in one schedule."""
+    sd = reference_test_settings(gpu, n_r=16)
+    sd['main_loop']['sub_loops'] = {
+        'order': ['main', 'refinement'],
+        'main': {'iterations': 2, 'order': ['HIO', 'SW_center', 'HIO_non_FXS', 'ER_non_FXS', 'ER'], 'best_density_not_in_first_n_iterations': 0,
+                 'methods': {'HIO': {'iterations': 3, 'ft_stab': True}, 'SW_center': {'iterations': 2}, 'HIO_non_FXS': {'iterations': 2, 'ft_stab': True},
+                             'ER_non_FXS': {'iterations': 2, 'ft_stab': False}, 'ER': {'iterations': 2, 'ft_stab': True}}},
+        'refinement': {'iterations': 1, 'order': ['ER_non_FXS', 'SW', 'ER'], 'best_density_not_in_first_n_iterations': np.inf,
+                       'methods': {'ER_non_FXS': {'iterations': 2, 'ft_stab': True}, 'SW': 1, 'ER': {'iterations': 2, 'ft_stab': True}}}}
+    return sd
+
+
+@needs_ref
+def test_reference_sketch_tail_matches_oracle():
+    from oracle.sht import sh
+    sd = sketch_tail_settings(gpu=False)
+    inv = synthetic_invariants(sd)
+    RH.import_reference(sh_class=sh)
+    mo = O.MTIP(sd, dict(inv))
+    rho0 = initial_density(mo)
+    rec, m = RH.make_mtip(sd, inv, rho0=rho0)
+    ref = m.phasing_loop()
+    got = mo.run(rho0=rho0.copy())
+    assert min(ref['error_dict']['main']) > 0 and len(ref['error_dict']['main']) == 22
+    assert np.allclose(got['error_dict']['main'], ref['error_dict']['main'], rtol=1e-7, atol=0)
+    for k in ('last_real_density', 'real_density', 'last_reciprocal_density', 'reciprocal_density'):
+        assert rel_l2(got[k], ref[k]) < 1e-7, k
+    assert np.array_equal(got['support_mask'], ref['support_mask']) and np.array_equal(got['last_support_mask'], ref['last_support_mask'])
+
+
 @needs_ref
 def test_oracle_deg2_invariant_l2_diff_matches_reference():
     """oracle.deg2_invariant_l2_diff against the reference's generate_deg2_invariant_l2_diff (fxs_IO_methods.py:331-346,412-447)."""

@@ -51,7 +51,7 @@ struct xfb_plan {
     // intermediate `a` could stay inside the 126 MB L2.  Measured at 128 runs (profiles/r02a_sht_chunk_sweep.md): 9.2 - 13.5 ms
     // per step for the six transforms against 8.24 ms unchunked -- the smaller launches lose more than the L2 hits gain.
     int sht_chunk = 0, sht_streams = 3;
-    int leg_min_groups = 8;
+    int leg_min_groups = 0;                         // >0: at least that many shell groups per Legendre CTA (measured at 16 / 32 runs: 8 and 16 are not faster than the wave rule)
     cudaStream_t sht_side[4] = {}; cudaEvent_t sht_fork = nullptr, sht_join[4] = {};
     long long launches_side = 0;
     // host-buffer pipeline (xfb_mtip_step_host)
