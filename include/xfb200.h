@@ -165,6 +165,13 @@ int xfb_mtip_step_host(xfb_plan* p, int32_t method, int32_t ft_stab, double beta
 int xfb_plan_set_host_chunk(xfb_plan* p, int32_t runs);
 /* outputs; which: 0 last real, 1 last reciprocal, 2 best real, 3 best reciprocal (grids);
  *          4 last support, 5 best support (uint8 grids); */
+/* sketch / option tail of the loop driver (reconstruct.py:529-534,606-613,886-904,945-949) */
+int xfb_mtip_set_outer_iteration(xfb_plan* p, int32_t outer_iteration);        /* state['best_iteration'] bookkeeping */
+int xfb_mtip_select_best(xfb_plan* p, int32_t n_first, void* stream);          /* finite best_density_not_in_first_n_iterations */
+int xfb_mtip_snapshot_intensity(xfb_plan* p, void* stream);                    /* candidate <- |current reciprocal density| */
+int xfb_mtip_fix_intensity(xfb_plan* p, void* stream);                         /* fixed intensity <- candidate (non-FXS methods) */
+int xfb_mtip_set_non_fxs(xfb_plan* p, int32_t on);                             /* following iterations run MTIP_start_non_FXS */
+int xfb_mtip_shrinkwrap_center(xfb_plan* p, double sigma, double threshold, double error_limit, void* stream);   /* SW_center */
 int xfb_mtip_get_grid(xfb_plan* p, int32_t which, void* out_dev, void* stream);
 /* error history [n_batch][n_done] (real l2_projection_diff), best_error [n_batch], n_done */
 int xfb_mtip_get_errors(xfb_plan* p, double* hist_dev, int32_t hist_capacity, double* best_dev, int32_t* n_done_host, void* stream);

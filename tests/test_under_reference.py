@@ -190,3 +190,28 @@ def test_reference_loop_on_cuda_plugins_matches_project_worker(n_r):
         assert np.asarray(got[k]).shape == np.asarray(ref[k]).shape and np.asarray(got[k]).dtype == np.asarray(ref[k]).dtype, k
     for a, b in zip(got['fxs_unknowns'], ref['fxs_unknowns']):
         assert a.shape == b.shape
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_reference_sketch_tail_on_cuda_matches_project_worker():
+    """SW_center, HIO_non_FXS / ER_non_FXS and a finite best_density_not_in_first_n_iterations: the reference's loop (on the CUDA
+    plugins) against the device-resident loop of xframe_b200."""
+    from xframe_b200.harmonic_transforms import sh
+    from xframe_b200.worker import ProjectWorker
+    sd = sketch_tail_settings(gpu=True)
+    inv = synthetic_invariants(sd)
+    RH.import_reference(sh_class=sh, cuda_gpu_layer=True)
+    rho0 = initial_density(O.MTIP(sd, dict(inv)))
+    rec, m = RH.make_mtip(sd, inv, rho0=rho0)
+    ref = m.phasing_loop()
+    w = ProjectWorker(sd, dict(inv), n_reconstructions=2, initial_densities=[rho0, rho0 * 1.05])
+    res, _ = w.run()
+    got = res[0]
+    assert np.allclose(got['error_dict']['main'], ref['error_dict']['main'], rtol=1e-6, atol=0)
+    for k in ('last_real_density', 'real_density', 'last_reciprocal_density', 'reciprocal_density'):
+        assert rel_l2(got[k], ref[k]) < 1e-6, k
+    assert (got['support_mask'] != ref['support_mask']).mean() < 1e-3 and (got['last_support_mask'] != ref['last_support_mask']).mean() < 1e-3
+    assert got['loop_iterations'] == ref['loop_iterations'] and abs(got['final_error'] - ref['final_error']) < 1e-6 * ref['final_error']
+    w.plan.close()
+

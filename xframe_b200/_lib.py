@@ -68,6 +68,12 @@ EXPORTS = {
     'xfb_mtip_shrinkwrap': (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p]),
     'xfb_mtip_step_host': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'xfb_plan_set_host_chunk': (C.c_int, [C.c_void_p, C.c_int32]),
+    'xfb_mtip_set_outer_iteration': (C.c_int, [C.c_void_p, C.c_int32]),
+    'xfb_mtip_select_best': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    'xfb_mtip_snapshot_intensity': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'xfb_mtip_fix_intensity': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'xfb_mtip_set_non_fxs': (C.c_int, [C.c_void_p, C.c_int32]),
+    'xfb_mtip_shrinkwrap_center': (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p]),
     'xfb_mtip_get_grid': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'xfb_mtip_get_errors': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     'xfb_plan_launch_count': (C.c_int64, [C.c_void_p]),

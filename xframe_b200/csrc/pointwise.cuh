@@ -327,13 +327,15 @@ struct LoopState {
     int* rh_cur;  int* rh_best;  int* rh_next;        // slots in the rho_hat' pool
     int* mask_cur; int* mask_best; int* mask_next;    // slots in the support pool
     int* enforce_cur; int* enforce_best;              // enforce_initial_support at the time
+    int* enforce_rep;                                 // enforce flag of the REPORTED current mask (state['mask'], reconstruct.py:883,948)
+    int* best_iter;                                   // sub-loop iteration of the best error (state['best_iteration'], :938)
     double* best_err; double* last_err; double* hist; int hist_cap;
 };
 __device__ __forceinline__ int free_slot(int a, int b) {   // smallest slot in {0,1,2} different from a and b
     for (int s = 0; s < 3; ++s) if (s != a && s != b) return s;
     return 0;
 }
-__global__ void loop_update_kernel(LoopState st, const double* __restrict__ err, int it, int n_batch) {
+__global__ void loop_update_kernel(LoopState st, const double* __restrict__ err, int it, int n_batch, int outer_it) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_batch) return;
     const double num = err[b * 2], den = err[b * 2 + 1];
@@ -347,7 +349,8 @@ __global__ void loop_update_kernel(LoopState st, const double* __restrict__ err,
         st.rho_best[b] = st.rho_cur[b];
         st.rh_best[b] = st.rh_cur[b];
         st.mask_best[b] = st.mask_cur[b];
-        st.enforce_best[b] = st.enforce_cur[b];
+        st.enforce_best[b] = st.enforce_rep[b];
+        st.best_iter[b] = outer_it;
     }
     st.rho_next[b] = free_slot(st.rho_cur[b], st.rho_best[b]);
     st.rh_next[b] = free_slot(st.rh_cur[b], st.rh_best[b]);
@@ -357,8 +360,57 @@ __global__ void sw_update_kernel(LoopState st, double error_limit, int have_erro
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_batch) return;
     st.enforce_cur[b] = (have_error && st.last_err[b] > error_limit) ? 1 : 0;
+    st.enforce_rep[b] = st.enforce_cur[b];
     st.mask_cur[b] = st.mask_next[b];
     st.mask_next[b] = free_slot(st.mask_cur[b], st.mask_best[b]);
+}
+// End of a sub-loop with a finite best_density_not_in_first_n_iterations (reconstruct.py:945-949): runs whose best error came
+// after iteration n_first continue from the best pair and the best mask.  real_pr.support = best_mask re-applies the CURRENT
+// enforce flag on top of the (already effective) best mask, while the reported state['mask'] is the best mask itself.
+__global__ void select_best_kernel(LoopState st, int n_first, int n_batch) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_batch || st.best_iter[b] <= n_first) return;
+    st.rho_cur[b] = st.rho_best[b];
+    st.rh_cur[b] = st.rh_best[b];
+    st.mask_cur[b] = st.mask_best[b];
+    st.enforce_rep[b] = st.enforce_best[b];
+    st.enforce_cur[b] = (st.enforce_cur[b] || st.enforce_best[b]) ? 1 : 0;
+    st.rho_next[b] = free_slot(st.rho_cur[b], st.rho_best[b]);
+    st.rh_next[b] = free_slot(st.rh_cur[b], st.rh_best[b]);
+    st.mask_next[b] = free_slot(st.mask_cur[b], st.mask_best[b]);
+}
+// SW_center bookkeeping (reconstruct.py:886-897 with the reference's exchanged pair, see oracle/mtip.py): the freshly written
+// next slots of both pools become current
+__global__ void rotate_pair_kernel(LoopState st, int n_batch) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_batch) return;
+    st.rho_cur[b] = st.rho_next[b];
+    st.rh_cur[b] = st.rh_next[b];
+    st.rho_next[b] = free_slot(st.rho_cur[b], st.rho_best[b]);
+    st.rh_next[b] = free_slot(st.rh_cur[b], st.rh_best[b]);
+}
+// |x| of a slot view -> real array [nb][per_run]  (np.abs(hist[-1][0]).real, reconstruct.py:901)
+__global__ void abs_real_kernel(SlotView in, double* __restrict__ out, long long per_run) {
+    const int b = blockIdx.y;
+    const double2* src = slot_run_ptr(in, b);
+    double* dst = out + (long long)b * per_run;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_run; i += (long long)gridDim.x * blockDim.x) {
+        const double2 v = src[i];
+        dst[i] = sqrt(__dadd_rn(__dmul_rn(v.x, v.x), __dmul_rn(v.y, v.y)));
+    }
+}
+// project_to_fixed_intensity (fxs_Projections.py:911-922): rho_hat sqrt(fixed / |rho_hat|^2) where both are >= 0, else 0
+__global__ void fixed_intensity_kernel(const double2* __restrict__ rho_hat, const double* __restrict__ fixed, SlotView out, long long per_run) {
+    const int b = blockIdx.y;
+    const double2* rh = rho_hat + (long long)b * per_run;
+    const double* fx = fixed + (long long)b * per_run;
+    double2* dst = slot_run_ptr(out, b);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_run; i += (long long)gridDim.x * blockDim.x) {
+        const double2 v = ldg2(rh + i);
+        const double sq = __dadd_rn(__dmul_rn(v.x, v.x), __dmul_rn(v.y, v.y));
+        const double mult = mod_intensity_multiplier(fx[i], sq);
+        dst[i] = make_double2(v.x * mult, v.y * mult);
+    }
 }
 // effective support mask = ~_mask[0] (fxs_Projections.py:50-58)
 __global__ void effective_support_kernel(const uint8_t* __restrict__ pool, const int* __restrict__ slot, const int* __restrict__ enforce,
@@ -381,6 +433,12 @@ __global__ void scatter_slot_kernel(const double2* __restrict__ in, SlotView out
     double2* dst = slot_run_ptr(out, b);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_run; i += (long long)gridDim.x * blockDim.x)
         dst[i] = in[(long long)b * per_run + i];
+}
+__global__ void copy_slot_kernel(SlotView in, SlotView out, long long per_run) {
+    const int b = blockIdx.y;
+    const double2* src = slot_run_ptr(in, b);
+    double2* dst = slot_run_ptr(out, b);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_run; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 __global__ void fill_u8_kernel(uint8_t* p, uint8_t v, long long n) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;

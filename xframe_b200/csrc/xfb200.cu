@@ -90,7 +90,7 @@ struct xfb_plan {
     // loop state
     double2 *rho_pool = nullptr, *rh_pool = nullptr; uint8_t* mask_pool = nullptr;
     LoopState ls{}; int* ls_ints = nullptr; double* ls_dbl = nullptr;
-    int n_batch = 0, it_done = 0; double *partial = nullptr, *err = nullptr, *mm = nullptr; int red_blocks = 0;
+    int n_batch = 0, it_done = 0, outer_it = 0; bool non_fxs = false; double *fix_int = nullptr, *fix_cand = nullptr; double *partial = nullptr, *err = nullptr, *mm = nullptr; int red_blocks = 0;
     bool loop_alloc = false;
     int64_t launches = 0, bytes = 0;
     // profiling
@@ -256,7 +256,7 @@ int xfb_plan_destroy(xfb_plan* p) {
     void* ptrs[] = {p->tw, p->FE, p->FO, p->IE, p->IO, p->hankel_w, p->int_wt, p->q_pts, p->A0, p->C0, p->C1, p->W0, p->W1, p->W2, p->A0s, p->C0s, p->rt0, p->stage_out,
                     p->v2d, p->unk2d, p->dft_cs, p->T2a, p->T2b, p->orders_dev, p->kind_dev, p->act_index_dev, p->radial_mask_dev, p->v0_dev, p->pd_dev, p->vt_dev,
                     p->xt, p->tt, p->g, p->gn, p->vw, p->sigma, p->sweeps_dev, p->jac_counter, p->pp, p->gn_u, p->pp_u, p->sigma_u, p->i00, p->gemmY_dev, p->gemmY_tp, p->gemmM_dev, p->gemmT_dev, p->gemmM_tp, p->gemmT_tp,
-                    p->init_support_dev, p->avg_mean, p->d2_x, p->d2_b, p->d2_ref, p->d2_norm, p->d2_hist, p->d2_gemm, p->d2_tp, p->rho_pool, p->rh_pool, p->mask_pool, p->ls_ints, p->ls_dbl, p->partial, p->err, p->mm};
+                    p->init_support_dev, p->avg_mean, p->fix_int, p->fix_cand, p->d2_x, p->d2_b, p->d2_ref, p->d2_norm, p->d2_hist, p->d2_gemm, p->d2_tp, p->rho_pool, p->rh_pool, p->mask_pool, p->ls_ints, p->ls_dbl, p->partial, p->err, p->mm};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& kv : p->hk_cache) cudaFree(kv.second.first);
     for (auto& kv : p->dft_tiles) cudaFree(kv.second.first);
@@ -746,14 +746,14 @@ static int ensure_loop_alloc(xfb_plan* p) {
     if (dev_alloc(p, &p->rho_pool, 3 * B * p->G)) return 1;
     if (dev_alloc(p, &p->rh_pool, 3 * B * p->G)) return 1;
     if (dev_alloc(p, &p->mask_pool, 3 * B * p->G)) return 1;
-    if (dev_alloc(p, &p->ls_ints, 11 * B)) return 1;
+    if (dev_alloc(p, &p->ls_ints, 13 * B)) return 1;
     const int hist_cap = 1 << 14;
     if (dev_alloc(p, &p->ls_dbl, 2 * B + B * hist_cap)) return 1;
     int* q = p->ls_ints;
     p->ls.rho_cur = q; p->ls.rho_best = q + B; p->ls.rho_next = q + 2 * B;
     p->ls.rh_cur = q + 3 * B; p->ls.rh_best = q + 4 * B; p->ls.rh_next = q + 5 * B;
     p->ls.mask_cur = q + 6 * B; p->ls.mask_best = q + 7 * B; p->ls.mask_next = q + 8 * B;
-    p->ls.enforce_cur = q + 9 * B; p->ls.enforce_best = q + 10 * B;
+    p->ls.enforce_cur = q + 9 * B; p->ls.enforce_best = q + 10 * B; p->ls.enforce_rep = q + 11 * B; p->ls.best_iter = q + 12 * B;
     p->ls.best_err = p->ls_dbl; p->ls.last_err = p->ls_dbl + B; p->ls.hist = p->ls_dbl + 2 * B; p->ls.hist_cap = hist_cap;
     p->loop_alloc = true;
     return 0;
@@ -1125,7 +1125,8 @@ int xfb_mtip_init(xfb_plan* p, const double* rho0, int32_t nb, void* stream) {
     fill_i(p->ls.rho_cur, 0); fill_i(p->ls.rho_best, 0); fill_i(p->ls.rho_next, 1);
     fill_i(p->ls.rh_cur, 0); fill_i(p->ls.rh_best, 0); fill_i(p->ls.rh_next, 1);
     fill_i(p->ls.mask_cur, 0); fill_i(p->ls.mask_best, 0); fill_i(p->ls.mask_next, 1);
-    fill_i(p->ls.enforce_cur, 1); fill_i(p->ls.enforce_best, 1);
+    fill_i(p->ls.enforce_cur, 1); fill_i(p->ls.enforce_best, 1); fill_i(p->ls.enforce_rep, 1); fill_i(p->ls.best_iter, 0);
+    p->outer_it = 0;
     fill_f64_kernel<<<gb, tb, 0, st>>>(p->ls.best_err, INFINITY, B);
     fill_f64_kernel<<<gb, tb, 0, st>>>(p->ls.last_err, INFINITY, B);
     fill_u8_kernel<<<ew_blocks((long long)B * p->G), 256, 0, st>>>(p->mask_pool, 1, (long long)B * p->G);
@@ -1147,7 +1148,7 @@ static int iterate_range(xfb_plan* p, int b0, int nb, int method, int ft_stab, d
     };
     LoopState ls = p->ls;
     ls.rho_cur += b0; ls.rho_best += b0; ls.rho_next += b0; ls.rh_cur += b0; ls.rh_best += b0; ls.rh_next += b0;
-    ls.mask_cur += b0; ls.mask_best += b0; ls.mask_next += b0; ls.enforce_cur += b0; ls.enforce_best += b0;
+    ls.mask_cur += b0; ls.mask_best += b0; ls.mask_next += b0; ls.enforce_cur += b0; ls.enforce_best += b0; ls.enforce_rep += b0; ls.best_iter += b0;
     ls.best_err += b0; ls.last_err += b0; ls.hist += (long long)b0 * ls.hist_cap;
     double* err = p->err + 2 * b0;
     const bool fused = ft_stab && p->fused_ft_stab;
@@ -1165,6 +1166,11 @@ static int iterate_range(xfb_plan* p, int b0, int nb, int method, int ft_stab, d
     // with the register phi-FFT both pointwise kernels are fused into the transforms: |.|^2 when the rows are loaded,
     // the modified-intensity formula when the synthesised rows are stored
     const bool fuse_pw = p->dims == 3 && fft2_covers(p->n_phi, p->n_theta);
+    if (p->non_fxs) {      // MTIP_start_non_FXS (reconstruct.py:529-534): no invariant projection, fixed intensity instead
+        if (!p->fix_int) XFB_FAIL("non-FXS iteration without a fixed intensity (xfb_mtip_fix_intensity)");
+        XFB_LAUNCH(p, PG_POINTWISE, st,
+                   fixed_intensity_kernel<<<dim3(eb, nb), 256, 0, st>>>(p->W0, p->fix_int + (long long)b0 * p->G, pv(p->rh_pool, p->ls.rh_next), p->G));
+    } else {
     int half = 0;                                             // |rho_hat|^2 is real: half spectrum (2-D: the 'real' transform, reconstruct.py:347-348)
     if (fuse_pw) {
         if (sht_forward_i(p, flat_view(p->W0, p->G), p->n_r, p->C0, S, st, nullptr, 1, &half, 1)) return 1;
@@ -1187,6 +1193,7 @@ static int iterate_range(xfb_plan* p, int b0, int nb, int method, int ft_stab, d
         XFB_LAUNCH(p, PG_POINTWISE, st,
                    modify_intensity_kernel<<<dim3(eb, nb), 256, 0, st>>>(p->W0, p->W1, pv(p->rh_pool, p->ls.rh_next), p->G));
     }
+    }
     // 5. back to real space (+ ft_stab correction terms)     (:586-588 / :579)
     // 6. real projection + HIO/ER + error                    (:589-590)
     const uint8_t* mask = p->mask_pool + (long long)b0 * p->G;
@@ -1202,7 +1209,7 @@ static int iterate_range(xfb_plan* p, int b0, int nb, int method, int ft_stab, d
                           pv(p->rho_pool, p->ls.rho_next), mask, ls.mask_cur, pool_stride, ls.enforce_cur, err, nb, st)) return 1;
     }
     // 7. bookkeeping                                         (:924-939)
-    XFB_LAUNCH(p, PG_MISC, st, loop_update_kernel<<<cdiv(nb, 128), 128, 0, st>>>(ls, err, it_index, nb));
+    XFB_LAUNCH(p, PG_MISC, st, loop_update_kernel<<<cdiv(nb, 128), 128, 0, st>>>(ls, err, it_index, nb, p->outer_it));
     return 0;
 }
 
@@ -1248,6 +1255,56 @@ int xfb_mtip_shrinkwrap(xfb_plan* p, double sigma, double threshold, double erro
     return 0;
 }
 
+// ---- sketch / option tail of the loop driver ---------------------------------------------------------------------------
+// sub-loop iteration index recorded with a new best error (state['best_iteration'], reconstruct.py:938)
+int xfb_mtip_set_outer_iteration(xfb_plan* p, int32_t outer_iteration) { p->outer_it = outer_iteration; return 0; }
+
+// end of a sub-loop with a finite best_density_not_in_first_n_iterations (reconstruct.py:945-949)
+int xfb_mtip_select_best(xfb_plan* p, int32_t n_first, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = p->n_batch;
+    if (nb < 1) XFB_FAIL("xfb_mtip_init has not been called");
+    XFB_LAUNCH(p, PG_MISC, st, select_best_kernel<<<cdiv(nb, 128), 128, 0, st>>>(p->ls, n_first, nb));
+    return 0;
+}
+
+// non-FXS methods (HIO_non_FXS / ER_non_FXS, reconstruct.py:899-904): the intensity is fixed to |reciprocal density| of the pair
+// the reference's `hist` variable names when the block starts.  snapshot: candidate <- |current reciprocal density| (the host
+// takes it at the start of a sub-loop and before the last iteration of every HIO / ER block); fix: fixed <- candidate.
+int xfb_mtip_snapshot_intensity(xfb_plan* p, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = p->n_batch;
+    if (nb < 1) XFB_FAIL("xfb_mtip_init has not been called");
+    if (!p->fix_cand) { if (dev_alloc(p, &p->fix_cand, (size_t)p->max_batch * p->G)) return 1; }
+    XFB_LAUNCH(p, PG_POINTWISE, st, abs_real_kernel<<<dim3(ew_blocks(p->G), nb), 256, 0, st>>>(pool_view(p->rh_pool, p->ls.rh_cur, p), p->fix_cand, p->G));
+    return 0;
+}
+int xfb_mtip_fix_intensity(xfb_plan* p, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!p->fix_cand) XFB_FAIL("xfb_mtip_fix_intensity: no intensity snapshot has been taken");
+    if (!p->fix_int) { if (dev_alloc(p, &p->fix_int, (size_t)p->max_batch * p->G)) return 1; }
+    XFB_CUDA(cudaMemcpyAsync(p->fix_int, p->fix_cand, (size_t)p->n_batch * p->G * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+int xfb_mtip_set_non_fxs(xfb_plan* p, int32_t on) { p->non_fxs = on != 0; return 0; }
+
+// SW_center (reconstruct.py:606-613,886-897): shrink-wrap of the current density x, then the history pair becomes
+// (reciprocal = x, real = FT(x)) -- the reference's sketch returns (support, x, FT(x)) and the loop binds it to
+// (support, ft_density, density); see oracle/mtip.py.  Called once per repeat.
+int xfb_mtip_shrinkwrap_center(xfb_plan* p, double sigma, double threshold, double error_limit, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = p->n_batch;
+    if (nb < 1) XFB_FAIL("xfb_mtip_init has not been called");
+    if (p->it_done < 1) XFB_FAIL("SW_center before the first iteration: the reference reads error_dict['main'][-1] (reconstruct.py:887)");
+    if (xfb_mtip_shrinkwrap(p, sigma, threshold, error_limit, stream)) return 1;
+    const int eb = ew_blocks(p->G);
+    XFB_LAUNCH(p, PG_MISC, st, copy_slot_kernel<<<dim3(eb, nb), 256, 0, st>>>(pool_view(p->rho_pool, p->ls.rho_cur, p), pool_view(p->rh_pool, p->ls.rh_next, p), p->G));
+    if (ft_i(p, 0, pool_view(p->rho_pool, p->ls.rho_cur, p), p->W2, nb, st)) return 1;
+    XFB_LAUNCH(p, PG_MISC, st, scatter_slot_kernel<<<dim3(eb, nb), 256, 0, st>>>(p->W2, pool_view(p->rho_pool, p->ls.rho_next, p), p->G));
+    XFB_LAUNCH(p, PG_MISC, st, rotate_pair_kernel<<<cdiv(nb, 128), 128, 0, st>>>(p->ls, nb));
+    return 0;
+}
+
 int xfb_mtip_get_grid(xfb_plan* p, int32_t which, void* out, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = p->n_batch;
@@ -1258,7 +1315,7 @@ int xfb_mtip_get_grid(xfb_plan* p, int32_t which, void* out, void* stream) {
         case 1: XFB_LAUNCH(p, PG_MISC, st, gather_slot_kernel<<<dim3(eb, nb), 256, 0, st>>>(pool_view(p->rh_pool, p->ls.rh_cur, p), (double2*)out, p->G)); break;
         case 2: XFB_LAUNCH(p, PG_MISC, st, gather_slot_kernel<<<dim3(eb, nb), 256, 0, st>>>(pool_view(p->rho_pool, p->ls.rho_best, p), (double2*)out, p->G)); break;
         case 3: XFB_LAUNCH(p, PG_MISC, st, gather_slot_kernel<<<dim3(eb, nb), 256, 0, st>>>(pool_view(p->rh_pool, p->ls.rh_best, p), (double2*)out, p->G)); break;
-        case 4: XFB_LAUNCH(p, PG_MISC, st, effective_support_kernel<<<dim3(eb, nb), 256, 0, st>>>(p->mask_pool, p->ls.mask_cur, p->ls.enforce_cur, p->init_support_dev, (long long)p->max_batch * p->G, p->G, (uint8_t*)out)); break;
+        case 4: XFB_LAUNCH(p, PG_MISC, st, effective_support_kernel<<<dim3(eb, nb), 256, 0, st>>>(p->mask_pool, p->ls.mask_cur, p->ls.enforce_rep, p->init_support_dev, (long long)p->max_batch * p->G, p->G, (uint8_t*)out)); break;
         case 5: XFB_LAUNCH(p, PG_MISC, st, effective_support_kernel<<<dim3(eb, nb), 256, 0, st>>>(p->mask_pool, p->ls.mask_best, p->ls.enforce_best, p->init_support_dev, (long long)p->max_batch * p->G, p->G, (uint8_t*)out)); break;
         default: XFB_FAIL("which=%d unknown", which);
     }

@@ -397,6 +397,25 @@ class Plan:
     def mtip_shrinkwrap(self, sigma, threshold, error_limit):
         _lib.check(self.lib.xfb_mtip_shrinkwrap(self.h, float(sigma), float(threshold), float(error_limit), _stream()))
 
+    # sketch / option tail (reconstruct.py:529-534,606-613,886-904,945-949); the schedule logic lives in reconstruct.run_schedule
+    def mtip_set_outer_iteration(self, it):
+        _lib.check(self.lib.xfb_mtip_set_outer_iteration(self.h, int(it)))
+
+    def mtip_select_best(self, n_first):
+        _lib.check(self.lib.xfb_mtip_select_best(self.h, int(n_first), _stream()))
+
+    def mtip_snapshot_intensity(self):
+        _lib.check(self.lib.xfb_mtip_snapshot_intensity(self.h, _stream()))
+
+    def mtip_fix_intensity(self):
+        _lib.check(self.lib.xfb_mtip_fix_intensity(self.h, _stream()))
+
+    def mtip_set_non_fxs(self, on):
+        _lib.check(self.lib.xfb_mtip_set_non_fxs(self.h, int(bool(on))))
+
+    def mtip_shrinkwrap_center(self, sigma, threshold, error_limit):
+        _lib.check(self.lib.xfb_mtip_shrinkwrap_center(self.h, float(sigma), float(threshold), float(error_limit), _stream()))
+
     def mtip_grid(self, which):
         names = {'last_real': 0, 'last_reciprocal': 1, 'best_real': 2, 'best_reciprocal': 3, 'last_support': 4, 'best_support': 5}
         w = names[which]

@@ -11,7 +11,7 @@ from .plan import HIO, ER
 from .ramps import ExponentialRamp, LinearRamp
 from ._lib import XfbError
 
-_METHODS = {'HIO': HIO, 'ER': ER}
+_METHODS = {'HIO': HIO, 'ER': ER, 'HIO_non_FXS': HIO, 'ER_non_FXS': ER}
 
 
 def _sw_ramps(opt, default_sigma):
@@ -56,8 +56,8 @@ def iteration_count(opt):
         for key in lopt['order']:
             mo = lopt['methods'][key]
             rep = mo['iterations'] if isinstance(mo, dict) else mo
-            if key == 'SW':
-                n_sw += lopt['iterations']
+            if key in ('SW', 'SW_center'):
+                n_sw += lopt['iterations'] * (rep if key == 'SW_center' else 1)
             else:
                 n_it += lopt['iterations'] * rep
     return n_it, n_sw
@@ -85,19 +85,23 @@ def run_schedule(plan, opt, rho0, default_sigma=None, collect=True):
 
     plan.mtip_init(rho0)
     initial = plan.mtip_grid('last_real').cpu().numpy() if collect else None
+    has_non_fxs = any(k.endswith('_non_FXS') for name in loops['order'] for k in loops[name]['order'])
     iterations = []
     for lid, name in enumerate(loops['order']):
         lopt = loops[name]
         beta = hio_opt['beta'][lid] if len(hio_opt['beta']) - 1 >= lid else [0.5, 0.5, -1 / 700, 1600]
         beta_ramp = ExponentialRamp(*beta)
         limit = sup_opt['if_error_bigger_than'] if sup_opt['apply'] else np.inf
-        if np.isfinite(lopt.get('best_density_not_in_first_n_iterations', np.inf)):
-            raise XfbError("best_density_not_in_first_n_iterations is not supported by xframe_b200 (default: inf)")
+        n_first = lopt.get('best_density_not_in_first_n_iterations', np.inf)
         if 'SW' in lopt['order']:
             update_sw(0, lid)
+        if has_non_fxs:
+            plan.mtip_snapshot_intensity()        # `hist` is bound at the start of the sub-loop (reconstruct.py:853)
+        fixed = False                             # latest_intensity (:862,899-904)
         step = sw_step = 0
         it = 0
         for it in range(1, lopt['iterations'] + 1):
+            plan.mtip_set_outer_iteration(it)
             for key in lopt['order']:
                 mo = lopt['methods'][key]
                 repeats = mo['iterations'] if isinstance(mo, dict) else mo
@@ -105,15 +109,36 @@ def run_schedule(plan, opt, rho0, default_sigma=None, collect=True):
                     plan.mtip_shrinkwrap(sw.sigma, sw.threshold, limit)
                     sw_step += 1
                     update_sw(sw_step, lid)
+                elif key == 'SW_center':          # :886-897 (the reference's exchanged pair included, see oracle/mtip.py)
+                    for _ in range(repeats):
+                        plan.mtip_shrinkwrap_center(sw.sigma, sw.threshold, limit)
+                        sw_step += 1
+                        update_sw(sw_step, lid)
                 elif key in _METHODS:
                     ft_stab = mo.get('ft_stab', False) if isinstance(mo, dict) else False
                     if not isinstance(ft_stab, bool):
                         raise XfbError(f"ft_stab: '{ft_stab}' is not supported by xframe_b200 (True / False)")
+                    non_fxs = key.endswith('_non_FXS')
+                    if non_fxs and not fixed:
+                        plan.mtip_fix_intensity()
+                    fixed = non_fxs
+                    plan.mtip_set_non_fxs(non_fxs)
                     betas = [beta_ramp.eval(step + i) for i in range(repeats)]
-                    plan.mtip_iterate(_METHODS[key], ft_stab, betas)
+                    if has_non_fxs and repeats > 0:
+                        # `hist` is re-bound at the start of every iteration (:911): after the block it names the pair its LAST
+                        # iteration started from
+                        if repeats > 1:
+                            plan.mtip_iterate(_METHODS[key], ft_stab, betas[:-1])
+                        plan.mtip_snapshot_intensity()
+                        plan.mtip_iterate(_METHODS[key], ft_stab, betas[-1:])
+                    elif repeats > 0:
+                        plan.mtip_iterate(_METHODS[key], ft_stab, betas)
                     step += repeats
                 else:
-                    raise XfbError(f"method '{key}' is not supported by xframe_b200 (HIO, ER, SW)")
+                    raise XfbError(f"method '{key}' is not supported by xframe_b200 (HIO, ER, HIO_non_FXS, ER_non_FXS, SW, SW_center)")
+        plan.mtip_set_non_fxs(False)
+        if np.isfinite(n_first):                  # :945-949
+            plan.mtip_select_best(int(np.floor(n_first)))
         iterations.append(it)
     if not collect:
         return None
