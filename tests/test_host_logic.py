@@ -165,6 +165,25 @@ class FakePlan:
     def mtip_grid(self, which):
         raise AssertionError('collect=False must not read grids')
 
+    # sketch / option tail: recorded under their own kinds
+    def mtip_set_outer_iteration(self, it):
+        self.outer = it
+
+    def mtip_set_non_fxs(self, on):
+        self.non_fxs = bool(on)
+
+    def mtip_snapshot_intensity(self):
+        self.calls.append(('snap',))
+
+    def mtip_fix_intensity(self):
+        self.calls.append(('fix',))
+
+    def mtip_select_best(self, n_first):
+        self.calls.append(('best', n_first))
+
+    def mtip_shrinkwrap_center(self, sigma, thr, limit):
+        self.calls.append(('swc', sigma, thr, limit))
+
 
 def test_run_schedule_follows_reference_schedule():
     sd = ST.tutorial_settings()
@@ -185,6 +204,27 @@ def test_run_schedule_follows_reference_schedule():
     ds = np.pi / fp.qs.max()
     assert [round(s[1], 9) for s in sws[:5]] == [round(max(20 - 2 * i, ds), 9) for i in range(5)]   # sigma ramp 20,-2/step, floor default
     assert abs(sws[5][1] - ds) < 1e-12 and all(s[2] == 0.09 and s[3] == 6e-3 for s in sws)
+
+
+def test_run_schedule_sketch_tail():
+    """SW_center, non-FXS blocks and a finite best_density_not_in_first_n_iterations (reconstruct.py:886-904,945-949): the
+    intensity snapshot is taken at the start of a sub-loop and before the LAST iteration of every block (the pair the
+    reference's `hist` variable names afterwards), the fixed intensity is set when a non-FXS block follows a FXS one."""
+    import copy
+    sd = copy.deepcopy(ST.tutorial_settings())
+    sd['main_loop']['sub_loops'] = {
+        'order': ['main'],
+        'main': {'iterations': 2, 'order': ['HIO', 'SW_center', 'HIO_non_FXS', 'ER_non_FXS', 'ER'], 'best_density_not_in_first_n_iterations': 1,
+                 'methods': {'HIO': {'iterations': 3, 'ft_stab': True}, 'SW_center': {'iterations': 2}, 'HIO_non_FXS': {'iterations': 2},
+                             'ER_non_FXS': {'iterations': 1}, 'ER': {'iterations': 2}}}}
+    fp = FakePlan()
+    run_schedule(fp, sd, None, collect=False)
+    kinds = [c[0] for c in fp.calls]
+    one = ['it', 'snap', 'it', 'swc', 'swc', 'fix', 'it', 'snap', 'it', 'snap', 'it', 'it', 'snap', 'it']
+    assert kinds == ['init', 'snap'] + one + one + ['best']
+    its = [c for c in fp.calls if c[0] == 'it']
+    assert [len(c[3]) for c in its[:7]] == [2, 1, 1, 1, 1, 1, 1] and fp.calls[-1] == ('best', 1) and fp.non_fxs is False
+    assert iteration_count(sd) == (16, 4)
 
 
 @pytest.mark.parametrize('tag', ['ref_medium_ops'])
