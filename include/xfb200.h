@@ -111,6 +111,9 @@ int64_t xfb_plan_workspace_bytes(const xfb_plan* p);
 /* ft_stab sketch (reconstruct.py:584-593): 1 (default) evaluates IFT(rho_hat') + (rho - IFT(rho_hat)) as
  * IFT(rho_hat' - rho_hat) + rho (linearity; one inverse transform instead of two), 0 follows the sketch literally. */
 int xfb_plan_set_fused_ft_stab(xfb_plan* p, int32_t on);
+/* Two halves of the batch in flight on two streams inside xfb_mtip_iterate (the Jacobi kernel of one half overlaps the
+ * HBM-bound transforms of the other): enable, minimum batch, SMs given to the two Jacobi launches (<= 0 keeps the value). */
+int xfb_plan_set_dual_stream(xfb_plan* p, int32_t on, int32_t min_batch, int32_t big_sms, int32_t small_sms);
 /* L2-resident phi-Fourier intermediate: runs per transform chunk (0 = unchunked) and streams (1..4) the chunks are spread over */
 int xfb_plan_set_sht_chunk(xfb_plan* p, int32_t runs_per_chunk, int32_t streams);
 /* diagnostics: Jacobi sweeps of the last projection, host array [n_batch][n_active_orders]; orders_out lists the orders */

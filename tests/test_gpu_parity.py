@@ -591,6 +591,31 @@ def test_results_do_not_depend_on_the_batch():
         p1.close()
 
 
+def test_two_stream_halves_give_the_same_bits():
+    """xfb_mtip_iterate with the batch cut into two halves on two streams (the second half one projection behind, Jacobi launches on a
+    share of the SMs) against the single-stream path: identical densities, error histories and unknowns for every run."""
+    import bench
+    from xframe_b200.plan import HIO, ER
+    nb = 6
+    bench.select_workload('l63')
+    out = []
+    for dual in (False, True):
+        plan, sd, rho0 = bench.build_problem(nb, 0, [2000 + i for i in range(nb)])
+        plan.set_dual_stream(dual, min_batch=2, big_sms=40, small_sms=16)
+        plan.mtip_init(rho0)
+        plan.mtip_iterate(HIO, True, [0.5, 0.45, 0.4])
+        plan.mtip_shrinkwrap(20.0, 0.09, 6e-3)
+        plan.mtip_iterate(ER, True, [0.0, 0.0])
+        unk = plan.unknowns(nb - 1)
+        out.append((N(plan.mtip_grid('last_real')), N(plan.mtip_grid('best_reciprocal')), N(plan.mtip_errors()[0]), N(plan.mtip_grid('last_support')), unk))
+        plan.close()
+    a, b = out
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[3], b[3])
+    assert np.allclose(a[2], b[2], rtol=1e-12, atol=0)           # error integrals: block count per run depends on the launch batch
+    for u, v in zip(a[4], b[4]):
+        assert np.array_equal(u, v)
+
+
 @pytest.mark.parametrize('l_max,n_r,n_theta,n_phi,ft_type', [(10, 33, 16, 32, 'midpoint'), (6, 20, 8, 16, 'trapz'), (21, 48, 24, 64, 'midpoint'),
                                                               (8, 24, 16, 32, 'gauss')])
 def test_ragged_sizes_iterations_against_oracle(l_max, n_r, n_theta, n_phi, ft_type):

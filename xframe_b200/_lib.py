@@ -47,6 +47,7 @@ EXPORTS = {
     'xfb_plan_workspace_bytes': (C.c_int64, [C.c_void_p]),
     'xfb_debug_jacobi_sweeps': (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     'xfb_plan_set_fused_ft_stab': (C.c_int, [C.c_void_p, C.c_int32]),
+    'xfb_plan_set_dual_stream': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     'xfb_plan_set_sht_chunk': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     'xfb_sht_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'xfb_sht_inverse': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),

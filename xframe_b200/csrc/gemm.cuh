@@ -264,11 +264,13 @@ struct GemmProblem {
 #define GG_LDA (GG_BK + 4)
 #define GG_LDB (GG_BN + 4)
 
-__global__ void __launch_bounds__(128) grouped_gemm_kernel(const GemmProblem* __restrict__ probs, const int* __restrict__ tile_prob) {
+// tile_base: first tile of this launch in the (run-major) tile list -- a launch may cover the runs [b0, b0 + n) of the batch
+__global__ void __launch_bounds__(128) grouped_gemm_kernel(const GemmProblem* __restrict__ probs, const int* __restrict__ tile_prob, int tile_base) {
     __shared__ double As[GG_BM * GG_LDA];
     __shared__ double Bs[GG_BK * GG_LDB];
-    const GemmProblem pr = probs[tile_prob[blockIdx.x]];
-    const int tl = blockIdx.x - pr.tile0;
+    const int tile = blockIdx.x + tile_base;
+    const GemmProblem pr = probs[tile_prob[tile]];
+    const int tl = tile - pr.tile0;
     const int m0 = (tl / pr.tiles_n) * GG_BM, n0 = (tl % pr.tiles_n) * GG_BN;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wn = warp & 1;

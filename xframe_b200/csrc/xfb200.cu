@@ -90,6 +90,12 @@ struct xfb_plan {
     // loop state
     double2 *rho_pool = nullptr, *rh_pool = nullptr; uint8_t* mask_pool = nullptr;
     LoopState ls{}; int* ls_ints = nullptr; double* ls_dbl = nullptr;
+    // Two halves of the batch in flight on two streams (xfb_mtip_iterate): while one half sits in the latency-bound Jacobi kernel
+    // on a part of the SMs, the HBM-bound transform kernels of the other half run on the rest.
+    int dual = 1, dual_min = 32, dual_big_sms = 50, dual_small_sms = 20; bool dual_active = false;
+    cudaStream_t s_half = nullptr; cudaEvent_t ev_hfork = nullptr, ev_hjoin = nullptr, ev_stagger = nullptr; cudaEvent_t stagger_pending = nullptr;
+    cudaEvent_t jac_fork[2] = {}, jac_join[2] = {};
+    int run_base = 0, ctx = 0;                      // scratch of the current enqueue starts at this run; stream / event set in use
     int n_batch = 0, it_done = 0, outer_it = 0; bool non_fxs = false; double *fix_int = nullptr, *fix_cand = nullptr; double *partial = nullptr, *err = nullptr, *mm = nullptr; int red_blocks = 0;
     bool loop_alloc = false;
     int64_t launches = 0, bytes = 0;
@@ -135,6 +141,28 @@ static inline SlotView flat_view(const double2* ptr, long long run_stride) {
     SlotView v; v.base = const_cast<double2*>(ptr); v.slot = nullptr; v.slot_stride = 0; v.run_stride = run_stride; return v;
 }
 static inline int ew_blocks(long long n) { return (int)std::min<long long>(cdiv64(n, 256 * 4), 148 * 16); }
+
+// Per-run scratch is indexed by the ABSOLUTE run while a part of the batch is enqueued: the pointers of the plan are moved to
+// run b0 for the duration of the enqueue (kernel arguments are taken by value at launch) and restored afterwards.  Parts of
+// the batch can then be in flight on different streams at the same time (two halves, host-pipeline chunks), and the retained
+// projection data (M^T, I_00) of every run stay where xfb_get_unknowns looks for them.
+struct ScratchShift {
+    xfb_plan* p; int b0;
+    template <typename T> static void mv(T*& q, long long n) { if (q) q += n; }
+    void apply(long long s) {
+        const long long b = (long long)b0 * s;
+        mv(p->W0, b * p->G); mv(p->W1, b * p->G); mv(p->W2, b * p->G); mv(p->C0, b * p->C); mv(p->C1, b * p->C);
+        mv(p->T2a, b * p->G); mv(p->T2b, b * p->G);
+        if (p->dims == 3) { mv(p->A0, b * p->n_r * p->M2 * p->n_theta); mv(p->A0s, b * p->M2 * p->n_theta); mv(p->C0s, b * p->NLM); mv(p->rt0, b * p->n_theta * p->n_phi); }
+        mv(p->xt, b * p->xt_run); mv(p->tt, b * p->xt_run); mv(p->g, b * p->g_run); mv(p->gn, b * p->g_run); mv(p->pp, b * p->g_run);
+        mv(p->vw, b * p->vw_run); mv(p->sigma, b * (long long)p->orders.size() * p->sig_ld); mv(p->sweeps_dev, b * (long long)p->orders.size());
+        mv(p->i00, b * p->n_r); mv(p->partial, b * p->red_blocks * 2); mv(p->avg_mean, b * p->n_r); mv(p->unk2d, b * p->n_orders2d);
+        mv(p->d2_x, b * p->NLM * p->n_r); mv(p->d2_b, b * (p->L + 1) * p->n_r * p->n_r); mv(p->fix_int, b * p->G);
+    }
+    ScratchShift(xfb_plan* p_, int b0_) : p(p_), b0(b0_) { apply(+1); p->run_base += b0; }
+    ~ScratchShift() { p->run_base -= b0; apply(-1); }
+};
+
 
 extern "C" {
 
@@ -237,6 +265,10 @@ int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
     if (const char* e = getenv("XFB_SHT_CHUNK")) p->sht_chunk = std::max(0, atoi(e));          // experiments: sweep without rebuilding
     if (const char* e = getenv("XFB_SHT_STREAMS")) p->sht_streams = std::min(4, std::max(1, atoi(e)));
     if (const char* e = getenv("XFB_LEG_MINGROUPS")) p->leg_min_groups = std::max(0, atoi(e));
+    if (const char* e = getenv("XFB_DUAL")) p->dual = atoi(e) != 0;
+    if (const char* e = getenv("XFB_DUAL_BIG")) p->dual_big_sms = std::max(1, atoi(e));
+    if (const char* e = getenv("XFB_DUAL_SMALL")) p->dual_small_sms = std::max(1, atoi(e));
+    if (const char* e = getenv("XFB_DUAL_MIN")) p->dual_min = std::max(2, atoi(e));
     p->leg2 = (p->n_theta / 2 <= 64 && p->NP <= 64 && p->n_theta % 4 == 0);
     p->leg3_big = p->leg2 && (p->n_theta / 2 > 32 || p->NP > 32);
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, dev); }
@@ -268,6 +300,8 @@ int xfb_plan_destroy(xfb_plan* p) {
     if (p->s_out) cudaStreamDestroy(p->s_out);
     for (int i = 1; i < 4; ++i) { if (p->sht_side[i]) cudaStreamDestroy(p->sht_side[i]); if (p->sht_join[i]) cudaEventDestroy(p->sht_join[i]); }
     if (p->sht_fork) cudaEventDestroy(p->sht_fork);
+    if (p->s_half) cudaStreamDestroy(p->s_half);
+    for (cudaEvent_t e : {p->ev_hfork, p->ev_hjoin, p->ev_stagger, p->jac_fork[0], p->jac_fork[1], p->jac_join[0], p->jac_join[1]}) if (e) cudaEventDestroy(e);
     delete p;
     return 0;
 }
@@ -625,34 +659,46 @@ static int build_gemm_groups(xfb_plan* p, int nb_req, cudaStream_t st) {
 static int launch_jacobi(xfb_plan* p, const double* g, double* gn, double* pp, double* sigma, int nb, int* sweeps, cudaStream_t st) {
     const int na = (int)p->orders.size();
     const int smem_doubles = (int)(p->jacobi_smem / 8);
-    if (!p->jac_counter) { if (dev_alloc(p, &p->jac_counter, 2)) return 1; }
-    XFB_CUDA(cudaMemsetAsync(p->jac_counter, 0, 2 * sizeof(int), st));
+    if (!p->jac_counter) { if (dev_alloc(p, &p->jac_counter, 4)) return 1; }
+    int* counter = p->jac_counter + 2 * p->ctx;
+    XFB_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(int), st));
     const long long sig_run = (long long)na * p->sig_ld;
+    if (p->stagger_pending) {                 // dual mode: the other half starts its first iteration when this one enters the Jacobi
+        XFB_CUDA(cudaEventRecord(p->stagger_pending, st));
+        p->stagger_pending = nullptr;
+    }
     if (p->jacobi_big) {
         procrustes_jacobi_kernel<16, 256, false, 1, 32><<<std::min(na * nb, p->n_sm), 256, p->jacobi_smem, st>>>(
-            g, gn, pp, sigma, p->orders_dev, na, nb, p->sig_ld, p->g_run, sig_run, p->sv_cutoff, 1e-15, p->max_sweeps, sweeps, smem_doubles, p->jac_counter, 0, na);
+            g, gn, pp, sigma, p->orders_dev, na, nb, p->sig_ld, p->g_run, sig_run, p->sv_cutoff, 1e-15, p->max_sweeps, sweeps, smem_doubles, counter, 0, na);
         XFB_CUDA(cudaGetLastError());
         return 0;
     }
     const int n_big = p->jac_split ? p->jac_n_big : na, n_small = na - n_big;
+    // SMs given to the two launches: all of them, or the dual-mode shares (the rest is left to the other half's transforms)
+    const int sms_big = p->dual_active ? std::max(1, std::min(p->n_sm, p->dual_big_sms)) : p->n_sm;
+    const int sms_small = p->dual_active ? std::max(1, std::min(p->n_sm, p->dual_small_sms)) : p->n_sm;
     cudaStream_t s_small = st;
     if (n_big > 0 && n_small > 0) {          // fork: the small-order launch goes to a side stream
         if (sht_streams_init(p)) return 1;
-        s_small = p->sht_side[1];
-        XFB_CUDA(cudaEventRecord(p->sht_fork, st));
-        XFB_CUDA(cudaStreamWaitEvent(s_small, p->sht_fork, 0));
+        if (!p->jac_fork[p->ctx]) {
+            XFB_CUDA(cudaEventCreateWithFlags(&p->jac_fork[p->ctx], cudaEventDisableTiming));
+            XFB_CUDA(cudaEventCreateWithFlags(&p->jac_join[p->ctx], cudaEventDisableTiming));
+        }
+        s_small = p->sht_side[1 + p->ctx];
+        XFB_CUDA(cudaEventRecord(p->jac_fork[p->ctx], st));
+        XFB_CUDA(cudaStreamWaitEvent(s_small, p->jac_fork[p->ctx], 0));
     }
     if (n_big > 0)
-        procrustes_jacobi_kernel<8, 512, true, 1, 16><<<std::min(n_big * nb, p->n_sm), 512, p->jacobi_smem, st>>>(
-            g, gn, pp, sigma, p->orders_dev, n_big, nb, p->sig_ld, p->g_run, sig_run, p->sv_cutoff, 1e-15, p->max_sweeps, sweeps, smem_doubles, p->jac_counter, 0, na);
+        procrustes_jacobi_kernel<8, 512, true, 1, 16><<<std::min(n_big * nb, sms_big), 512, p->jacobi_smem, st>>>(
+            g, gn, pp, sigma, p->orders_dev, n_big, nb, p->sig_ld, p->g_run, sig_run, p->sv_cutoff, 1e-15, p->max_sweeps, sweeps, smem_doubles, counter, 0, na);
     if (n_small > 0)
-        procrustes_jacobi_kernel<4, 256, true, 2, 8><<<std::min(n_small * nb, 2 * p->n_sm), 256, JAC_SMALL_SMEM, s_small>>>(
+        procrustes_jacobi_kernel<4, 256, true, 2, 8><<<std::min(n_small * nb, 2 * sms_small), 256, JAC_SMALL_SMEM, s_small>>>(
             g, gn, pp, sigma, p->orders_dev, n_small, nb, p->sig_ld, p->g_run, sig_run, p->sv_cutoff, 1e-15, p->max_sweeps, sweeps, JAC_SMALL_SMEM / 8,
-            p->jac_counter + 1, n_big, na);
+            counter + 1, n_big, na);
     XFB_CUDA(cudaGetLastError());
     if (n_big > 0 && n_small > 0) {          // join
-        XFB_CUDA(cudaEventRecord(p->sht_join[1], s_small));
-        XFB_CUDA(cudaStreamWaitEvent(st, p->sht_join[1], 0));
+        XFB_CUDA(cudaEventRecord(p->jac_join[p->ctx], s_small));
+        XFB_CUDA(cudaStreamWaitEvent(st, p->jac_join[p->ctx], 0));
     }
     return 0;
 }
@@ -671,16 +717,16 @@ static int project_i(xfb_plan* p, const double2* c_in, double2* c_out, int nb, c
     const int na = (int)p->orders.size();
     // row (l=0,m=0) of the coefficient array = I_00(q) of every run: kept for xfb_get_unknowns
     XFB_CUDA(cudaMemcpyAsync(p->i00, c_in, (size_t)S * sizeof(double2), cudaMemcpyDeviceToDevice, st));
-    p->proj_calls++; p->last_proj_nb = nb;
+    p->proj_calls++; p->last_proj_nb = std::max(p->run_base + nb, p->run_base ? p->last_proj_nb : 0);
     if (na > 0) {
         if (build_gemm_groups(p, nb, st)) return 1;
         XFB_LAUNCH(p, PG_PROC_PACK, st,
                    procrustes_pack_kernel<<<dim3(na, nb), 256, 0, st>>>(c_in, p->xt, p->orders_dev, p->n_r, S, p->xt_run));
-        XFB_LAUNCH(p, PG_PROC_GEMM, st, grouped_gemm_kernel<<<p->gemmM_tiles, 128, 0, st>>>(p->gemmM_dev, p->gemmM_tp));
+        XFB_LAUNCH(p, PG_PROC_GEMM, st, grouped_gemm_kernel<<<p->gemmM_tiles, 128, 0, st>>>(p->gemmM_dev, p->gemmM_tp, p->run_base * p->gemmM_tiles_run));
         XFB_LAUNCH(p, PG_PROC_JACOBI, st,
                    if (launch_jacobi(p, p->g, p->gn, p->pp, p->sigma, nb, p->sweeps_dev, st)) return 1);
-        XFB_LAUNCH(p, PG_PROC_GEMM, st, grouped_gemm_kernel<<<p->gemmY_tiles, 128, 0, st>>>(p->gemmY_dev, p->gemmY_tp));
-        XFB_LAUNCH(p, PG_PROC_GEMM, st, grouped_gemm_kernel<<<p->gemmT_tiles, 128, 0, st>>>(p->gemmT_dev, p->gemmT_tp));
+        XFB_LAUNCH(p, PG_PROC_GEMM, st, grouped_gemm_kernel<<<p->gemmY_tiles, 128, 0, st>>>(p->gemmY_dev, p->gemmY_tp, p->run_base * p->gemmY_tiles_run));
+        XFB_LAUNCH(p, PG_PROC_GEMM, st, grouped_gemm_kernel<<<p->gemmT_tiles, 128, 0, st>>>(p->gemmT_dev, p->gemmT_tp, p->run_base * p->gemmT_tiles_run));
     }
     XFB_LAUNCH(p, PG_PROC_PACK, st,
                procrustes_unpack_kernel<<<dim3(p->L + 1, nb), 256, 0, st>>>(c_in, c_out, p->tt, p->orders_dev, p->kind_dev, p->act_index_dev,
@@ -722,7 +768,7 @@ static int deg2_invariants_i(xfb_plan* p, const double2* c, int nb, cudaStream_t
     if (ensure_deg2_alloc(p, st)) return 1;
     const int S = nb * p->n_r;
     XFB_LAUNCH(p, PG_PROC_PACK, st, pack_real_all_kernel<<<dim3(p->L + 1, nb), 256, 0, st>>>(c, p->d2_x, p->n_r, S, (long long)p->NLM * p->n_r));
-    XFB_LAUNCH(p, PG_PROC_GEMM, st, grouped_gemm_kernel<<<nb * p->d2_tiles_run, 128, 0, st>>>(p->d2_gemm, p->d2_tp));
+    XFB_LAUNCH(p, PG_PROC_GEMM, st, grouped_gemm_kernel<<<nb * p->d2_tiles_run, 128, 0, st>>>(p->d2_gemm, p->d2_tp, p->run_base * p->d2_tiles_run));
     return 0;
 }
 static int deg2_diff_i(xfb_plan* p, const double2* c, int nb, double* err_out, long long err_run_stride, cudaStream_t st) {
@@ -1140,6 +1186,9 @@ int xfb_mtip_init(xfb_plan* p, const double* rho0, int32_t nb, void* stream) {
 
 // one iteration of runs [b0, b0+nb) of the loop state; `it_index` is the error-history column it writes
 static int iterate_range(xfb_plan* p, int b0, int nb, int method, int ft_stab, double beta, int it_index, cudaStream_t st) {
+    if (ensure_reduce_alloc(p)) return 1;            // before the shift: lazily allocated scratch must exist at its base address
+    if (p->d2_metric && ensure_deg2_alloc(p, st)) return 1;
+    ScratchShift shift(p, b0);
     const int S = nb * p->n_r;
     const int eb = ew_blocks(p->G);
     const long long pool_stride = (long long)p->max_batch * p->G;
@@ -1169,7 +1218,7 @@ static int iterate_range(xfb_plan* p, int b0, int nb, int method, int ft_stab, d
     if (p->non_fxs) {      // MTIP_start_non_FXS (reconstruct.py:529-534): no invariant projection, fixed intensity instead
         if (!p->fix_int) XFB_FAIL("non-FXS iteration without a fixed intensity (xfb_mtip_fix_intensity)");
         XFB_LAUNCH(p, PG_POINTWISE, st,
-                   fixed_intensity_kernel<<<dim3(eb, nb), 256, 0, st>>>(p->W0, p->fix_int + (long long)b0 * p->G, pv(p->rh_pool, p->ls.rh_next), p->G));
+                   fixed_intensity_kernel<<<dim3(eb, nb), 256, 0, st>>>(p->W0, p->fix_int, pv(p->rh_pool, p->ls.rh_next), p->G));
     } else {
     int half = 0;                                             // |rho_hat|^2 is real: half spectrum (2-D: the 'real' transform, reconstruct.py:347-348)
     if (fuse_pw) {
@@ -1217,10 +1266,55 @@ int xfb_mtip_iterate(xfb_plan* p, int32_t method, int32_t ft_stab, int32_t n_ite
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = p->n_batch;
     if (nb < 1) XFB_FAIL("xfb_mtip_init has not been called");
-    for (int it = 0; it < n_iter; ++it) {
-        if (iterate_range(p, 0, nb, method, ft_stab, betas ? betas[it] : 0.0, p->it_done, st)) return 1;
-        p->it_done++;
+    // Dual mode: the two halves of the batch run their iterations on two streams, the second half one projection behind the
+    // first, so that the latency-bound Jacobi kernel of one half (on its share of the SMs) overlaps the HBM-bound transform
+    // kernels of the other half.  The runs are independent and every run's arithmetic is unchanged (bit-identical results).
+    const bool dual = p->dual && p->dims == 3 && !p->jacobi_big && nb >= p->dual_min && n_iter > 0 && (!ft_stab || p->fused_ft_stab) && !p->sht_chunk;
+    if (!dual) {
+        for (int it = 0; it < n_iter; ++it) {
+            if (iterate_range(p, 0, nb, method, ft_stab, betas ? betas[it] : 0.0, p->it_done, st)) return 1;
+            p->it_done++;
+        }
+        return 0;
     }
+    if (!p->s_half) {
+        XFB_CUDA(cudaStreamCreateWithFlags(&p->s_half, cudaStreamNonBlocking));
+        XFB_CUDA(cudaEventCreateWithFlags(&p->ev_hfork, cudaEventDisableTiming));
+        XFB_CUDA(cudaEventCreateWithFlags(&p->ev_hjoin, cudaEventDisableTiming));
+        XFB_CUDA(cudaEventCreateWithFlags(&p->ev_stagger, cudaEventDisableTiming));
+    }
+    const int n0 = (nb + 1) / 2, n1 = nb - n0;
+    XFB_CUDA(cudaEventRecord(p->ev_hfork, st));
+    XFB_CUDA(cudaStreamWaitEvent(p->s_half, p->ev_hfork, 0));
+    p->dual_active = true;
+    int rc = 0;
+    for (int it = 0; it < n_iter && !rc; ++it) {
+        const double beta = betas ? betas[it] : 0.0;
+        p->ctx = 0;
+        if (it == 0) p->stagger_pending = p->ev_stagger;            // recorded right before the first half's first Jacobi launch
+        rc = iterate_range(p, 0, n0, method, ft_stab, beta, p->it_done + it, st);
+        if (!rc && it == 0) {
+            if (p->stagger_pending) { XFB_CUDA(cudaEventRecord(p->ev_stagger, st)); p->stagger_pending = nullptr; }   // (no Jacobi in this iteration)
+            XFB_CUDA(cudaStreamWaitEvent(p->s_half, p->ev_stagger, 0));
+        }
+        p->ctx = 1;
+        if (!rc) rc = iterate_range(p, n0, n1, method, ft_stab, beta, p->it_done + it, p->s_half);
+    }
+    p->ctx = 0; p->dual_active = false; p->stagger_pending = nullptr;
+    XFB_CUDA(cudaEventRecord(p->ev_hjoin, p->s_half));
+    XFB_CUDA(cudaStreamWaitEvent(st, p->ev_hjoin, 0));
+    if (rc) return 1;
+    p->it_done += n_iter;
+    return 0;
+}
+
+// dual mode switches: enable, minimum batch, SMs given to the one-problem-per-SM and the two-problems-per-SM Jacobi launches
+int xfb_plan_set_dual_stream(xfb_plan* p, int32_t on, int32_t min_batch, int32_t big_sms, int32_t small_sms) {
+    if (!p) XFB_FAIL("null plan");
+    p->dual = on != 0;
+    if (min_batch > 1) p->dual_min = min_batch;
+    if (big_sms > 0) p->dual_big_sms = big_sms;
+    if (small_sms > 0) p->dual_small_sms = small_sms;
     return 0;
 }
 

@@ -150,6 +150,10 @@ class Plan:
         """True (default): one inverse transform per ft_stab iteration (linearity of IFT); False: literal sketch."""
         _lib.check(self.lib.xfb_plan_set_fused_ft_stab(self.h, int(bool(on))))
 
+    def set_dual_stream(self, on=True, min_batch=0, big_sms=0, small_sms=0):
+        """Two halves of the batch on two streams inside mtip_iterate (Jacobi of one half overlaps the transforms of the other)."""
+        _lib.check(self.lib.xfb_plan_set_dual_stream(self.h, int(bool(on)), int(min_batch), int(big_sms), int(small_sms)))
+
     def set_sht_chunk(self, runs_per_chunk, streams=3):
         """L2-resident phi-Fourier intermediate: runs per transform chunk (0 = unchunked) and number of streams (1..4)."""
         _lib.check(self.lib.xfb_plan_set_sht_chunk(self.h, int(runs_per_chunk), int(streams)))
