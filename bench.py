@@ -24,6 +24,9 @@ sys.path.insert(0, ROOT)
 
 L_MAX, N_R, N_THETA, N_PHI, MAX_Q = 63, 128, 64, 128, 0.322416
 TOTAL_RUNS = 128
+# measured on this pool's B200 with tools/fp64_peak.cu (register-only mma.sync.m8n8k4.f64 chains; profiles/r02b_fp64_peak.json): 37.2 TFLOP/s
+# (fma.rn.f64 chains: 34.2); the denominator of the FP64 contractions
+FP64_DMMA_PEAK_TF = 37.2
 METRIC = "mtip_iterations_per_s_L63_Nr128"
 UNIT = "iterations/s"
 # --workload: 'l63' = BASELINE.json configs[2] (the metric's configuration, default);
@@ -454,21 +457,23 @@ def run_ours(args):
         roof = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': (achieved / peak) if achieved is not None else None, 'traffic': None, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': ab.get(dom), 'launch_ms': per_launch_ms, 'share_of_step': groups[dom]['ms'] / tot_ms}
+        # DRAM traffic of the dominant kernel is not measurable inside this run (it needs ncu): null here, the ncu capture of the same
+        # kernel is committed under profiles/ (traffic_source)
+        roof['traffic'] = None
+        roof['traffic_source'] = 'profiles/README.md (ncu --set full captures: dram__bytes_read.sum + dram__bytes_write.sum per launch)'
         if dom == 'procrustes_jacobi':
-            if METRIC.endswith('L63_Nr128') and nb == 128:
-                # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full, profiles/r01k_jacobi_ncu_details.txt
-                roof['traffic'] = 232848640 + 428813568
-            roof['note'] = ('dominant kernel is the QR-preconditioned one-sided Jacobi polar factor: shared-memory resident, bound by the '
-                            'sequential rotation steps and the FP64 pipe (ncu: FP64 pipe 18 % of issue peak, 44 % of the warp time at barriers next to a latency-bound critical path); '
-                            'neither the HBM nor the tensor roofline applies and its HBM fraction is low by construction. '
-                            'Roofline-bound kernels: fft_phi / real_update (HBM), legendre / hankel (FP64 DMMA): see the per-group fractions in groups, the whole-iteration HBM floor in iteration, and profiles/README.md')
+            roof['note'] = ('dominant kernel is the QR-preconditioned one-sided Jacobi polar factor: shared-memory resident, bound by the latency of '
+                            'its sequential rotation steps (ncu: FP64 pipe 18 %, issue slots 34 %); neither the HBM nor the tensor roofline applies and '
+                            'its HBM fraction is low by construction -- which is why the step overlaps it with the HBM-bound kernels of the other half '
+                            'of the batch (two streams).  Roofline-bound kernels: fft_phi / real_update (HBM), legendre / hankel (FP64 DMMA): per-group '
+                            'fractions in groups, whole-iteration HBM floor in iteration, profiles/README.md')
         roof['groups'] = {k: {'ms_per_step': v['ms'] / K, 'launches_per_step': v['launches'] / K,
                               **({'GBps': ab[k] * v['launches'] / (v['ms'] * 1e-3) / 1e9} if k in ab else {}),
                               **({'TFLOPs_fp64': hankel_flops(nb) * v['launches'] / (v['ms'] * 1e-3) / 1e12} if k == 'hankel' else {})}
                           for k, v in groups.items()}
         for k, gk in roof['groups'].items():
             if 'TFLOPs_fp64' in gk:
-                gk['frac_of_fp64_tensor_nominal_40TF'] = gk['TFLOPs_fp64'] / 40.0
+                gk['frac_of_fp64_dmma_measured_peak'] = gk['TFLOPs_fp64'] / FP64_DMMA_PEAK_TF
             elif 'GBps' in gk and k != 'procrustes_jacobi':
                 gk['frac_of_hbm_peak'] = gk['GBps'] / peak
         if DIMS == 3:

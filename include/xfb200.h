@@ -166,6 +166,8 @@ int xfb_mtip_step_host(xfb_plan* p, int32_t method, int32_t ft_stab, double beta
                        double* rho_out_host, double* err_out_host, void* stream);
 /* runs per chunk of the copy-in | compute | copy-out pipeline inside xfb_mtip_step_host (default 16) */
 int xfb_plan_set_host_chunk(xfb_plan* p, int32_t runs);
+/* diagnostics: iterations with a NaN / inf error metric per run (host array [n_batch]); synchronises the stream */
+int xfb_mtip_get_nonfinite(xfb_plan* p, int32_t* out_host, void* stream);
 /* outputs; which: 0 last real, 1 last reciprocal, 2 best real, 3 best reciprocal (grids);
  *          4 last support, 5 best support (uint8 grids); */
 /* sketch / option tail of the loop driver (reconstruct.py:529-534,606-613,886-904,945-949) */

@@ -68,6 +68,7 @@ EXPORTS = {
     'xfb_mtip_iterate': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_void_p]),
     'xfb_mtip_shrinkwrap': (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p]),
     'xfb_mtip_step_host': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'xfb_mtip_get_nonfinite': (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     'xfb_plan_set_host_chunk': (C.c_int, [C.c_void_p, C.c_int32]),
     'xfb_mtip_set_outer_iteration': (C.c_int, [C.c_void_p, C.c_int32]),
     'xfb_mtip_select_best': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),

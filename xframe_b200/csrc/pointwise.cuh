@@ -329,6 +329,7 @@ struct LoopState {
     int* enforce_cur; int* enforce_best;              // enforce_initial_support at the time
     int* enforce_rep;                                 // enforce flag of the REPORTED current mask (state['mask'], reconstruct.py:883,948)
     int* best_iter;                                   // sub-loop iteration of the best error (state['best_iteration'], :938)
+    int* nonfinite;                                   // iterations whose error was NaN / inf, per run (diagnostics)
     double* best_err; double* last_err; double* hist; int hist_cap;
 };
 __device__ __forceinline__ int free_slot(int a, int b) {   // smallest slot in {0,1,2} different from a and b
@@ -342,6 +343,7 @@ __global__ void loop_update_kernel(LoopState st, const double* __restrict__ err,
     const double e = (den != 0.0) ? num / den : INFINITY;
     if (it < st.hist_cap) st.hist[(long long)b * st.hist_cap + it] = e;
     st.last_err[b] = e;
+    if (!isfinite(e)) st.nonfinite[b]++;
     st.rho_cur[b] = st.rho_next[b];
     st.rh_cur[b] = st.rh_next[b];
     if (st.best_err[b] > e) {

@@ -14,6 +14,9 @@
 
 #include <algorithm>
 #include <map>
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: named ranges per stage of an iteration (visible in nsys / ncu timelines)
+
+struct NvtxRange { explicit NvtxRange(const char* name) { nvtxRangePushA(name); } ~NvtxRange() { nvtxRangePop(); } };
 
 thread_local std::string g_xfb_err;
 
@@ -91,8 +94,10 @@ struct xfb_plan {
     double2 *rho_pool = nullptr, *rh_pool = nullptr; uint8_t* mask_pool = nullptr;
     LoopState ls{}; int* ls_ints = nullptr; double* ls_dbl = nullptr;
     // Two halves of the batch in flight on two streams (xfb_mtip_iterate): while one half sits in the latency-bound Jacobi kernel
-    // on a part of the SMs, the HBM-bound transform kernels of the other half run on the rest.
-    int dual = 1, dual_min = 32, dual_big_sms = 50, dual_small_sms = 20; bool dual_active = false;
+    // on a part of the SMs, the HBM-bound transform kernels of the other half run on the rest.  OFF by default: measured at 128
+    // runs (profiles/r02e_dual_stream_sweep.md) the step takes 22.98 ms at the best SM split against 22.93 ms on one stream --
+    // the HBM-bound kernels need (nearly) all SMs to reach their bandwidth, so SM time is conserved and nothing is gained.
+    int dual = 0, dual_min = 32, dual_big_sms = 50, dual_small_sms = 20; bool dual_active = false;
     cudaStream_t s_half = nullptr; cudaEvent_t ev_hfork = nullptr, ev_hjoin = nullptr, ev_stagger = nullptr; cudaEvent_t stagger_pending = nullptr;
     cudaEvent_t jac_fork[2] = {}, jac_join[2] = {};
     int run_base = 0, ctx = 0;                      // scratch of the current enqueue starts at this run; stream / event set in use
@@ -792,14 +797,14 @@ static int ensure_loop_alloc(xfb_plan* p) {
     if (dev_alloc(p, &p->rho_pool, 3 * B * p->G)) return 1;
     if (dev_alloc(p, &p->rh_pool, 3 * B * p->G)) return 1;
     if (dev_alloc(p, &p->mask_pool, 3 * B * p->G)) return 1;
-    if (dev_alloc(p, &p->ls_ints, 13 * B)) return 1;
+    if (dev_alloc(p, &p->ls_ints, 14 * B)) return 1;
     const int hist_cap = 1 << 14;
     if (dev_alloc(p, &p->ls_dbl, 2 * B + B * hist_cap)) return 1;
     int* q = p->ls_ints;
     p->ls.rho_cur = q; p->ls.rho_best = q + B; p->ls.rho_next = q + 2 * B;
     p->ls.rh_cur = q + 3 * B; p->ls.rh_best = q + 4 * B; p->ls.rh_next = q + 5 * B;
     p->ls.mask_cur = q + 6 * B; p->ls.mask_best = q + 7 * B; p->ls.mask_next = q + 8 * B;
-    p->ls.enforce_cur = q + 9 * B; p->ls.enforce_best = q + 10 * B; p->ls.enforce_rep = q + 11 * B; p->ls.best_iter = q + 12 * B;
+    p->ls.enforce_cur = q + 9 * B; p->ls.enforce_best = q + 10 * B; p->ls.enforce_rep = q + 11 * B; p->ls.best_iter = q + 12 * B; p->ls.nonfinite = q + 13 * B;
     p->ls.best_err = p->ls_dbl; p->ls.last_err = p->ls_dbl + B; p->ls.hist = p->ls_dbl + 2 * B; p->ls.hist_cap = hist_cap;
     p->loop_alloc = true;
     return 0;
@@ -1171,7 +1176,7 @@ int xfb_mtip_init(xfb_plan* p, const double* rho0, int32_t nb, void* stream) {
     fill_i(p->ls.rho_cur, 0); fill_i(p->ls.rho_best, 0); fill_i(p->ls.rho_next, 1);
     fill_i(p->ls.rh_cur, 0); fill_i(p->ls.rh_best, 0); fill_i(p->ls.rh_next, 1);
     fill_i(p->ls.mask_cur, 0); fill_i(p->ls.mask_best, 0); fill_i(p->ls.mask_next, 1);
-    fill_i(p->ls.enforce_cur, 1); fill_i(p->ls.enforce_best, 1); fill_i(p->ls.enforce_rep, 1); fill_i(p->ls.best_iter, 0);
+    fill_i(p->ls.enforce_cur, 1); fill_i(p->ls.enforce_best, 1); fill_i(p->ls.enforce_rep, 1); fill_i(p->ls.best_iter, 0); fill_i(p->ls.nonfinite, 0);
     p->outer_it = 0;
     fill_f64_kernel<<<gb, tb, 0, st>>>(p->ls.best_err, INFINITY, B);
     fill_f64_kernel<<<gb, tb, 0, st>>>(p->ls.last_err, INFINITY, B);
@@ -1197,11 +1202,13 @@ static int iterate_range(xfb_plan* p, int b0, int nb, int method, int ft_stab, d
     };
     LoopState ls = p->ls;
     ls.rho_cur += b0; ls.rho_best += b0; ls.rho_next += b0; ls.rh_cur += b0; ls.rh_best += b0; ls.rh_next += b0;
-    ls.mask_cur += b0; ls.mask_best += b0; ls.mask_next += b0; ls.enforce_cur += b0; ls.enforce_best += b0; ls.enforce_rep += b0; ls.best_iter += b0;
+    ls.mask_cur += b0; ls.mask_best += b0; ls.mask_next += b0; ls.enforce_cur += b0; ls.enforce_best += b0; ls.enforce_rep += b0; ls.best_iter += b0; ls.nonfinite += b0;
     ls.best_err += b0; ls.last_err += b0; ls.hist += (long long)b0 * ls.hist_cap;
     double* err = p->err + 2 * b0;
     const bool fused = ft_stab && p->fused_ft_stab;
+    NvtxRange nvtx_it(method == 0 ? "xfb:HIO iteration" : "xfb:ER iteration");
     // 1. rho_hat = FT(rho)                                   (reconstruct.py:585)
+    nvtxRangePushA("xfb:FT(rho)");
     if (!fused) {
         if (ft_i(p, 0, pv(p->rho_pool, p->ls.rho_cur), p->W0, nb, st)) return 1;
     } else {
@@ -1211,7 +1218,9 @@ static int iterate_range(xfb_plan* p, int b0, int nb, int method, int ft_stab, d
         if (ift_shell0_i(p, p->C1, nb, st)) return 1;
         if (sht_inverse_i(p, p->C1, p->W0, S, st)) return 1;
     }
+    nvtxRangePop();
     // 2. |rho_hat|^2 -> I_lm                                 (:519-520)
+    nvtxRangePushA("xfb:MTIP_start (SHT, invariant projection, modified intensity)");
     // with the register phi-FFT both pointwise kernels are fused into the transforms: |.|^2 when the rows are loaded,
     // the modified-intensity formula when the synthesised rows are stored
     const bool fuse_pw = p->dims == 3 && fft2_covers(p->n_phi, p->n_theta);
@@ -1243,7 +1252,9 @@ static int iterate_range(xfb_plan* p, int b0, int nb, int method, int ft_stab, d
                    modify_intensity_kernel<<<dim3(eb, nb), 256, 0, st>>>(p->W0, p->W1, pv(p->rh_pool, p->ls.rh_next), p->G));
     }
     }
+    nvtxRangePop();
     // 5. back to real space (+ ft_stab correction terms)     (:586-588 / :579)
+    NvtxRange nvtx_real("xfb:IFT + real projection + HIO/ER + error");
     // 6. real projection + HIO/ER + error                    (:589-590)
     const uint8_t* mask = p->mask_pool + (long long)b0 * p->G;
     if (fused) {
@@ -1490,6 +1501,14 @@ int xfb_mtip_step_host(xfb_plan* p, int32_t method, int32_t ft_stab, double beta
     XFB_CUDA(cudaMemcpyAsync(err_out_host, p->err, (size_t)nb * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     XFB_CUDA(cudaStreamSynchronize(st));
     XFB_CUDA(cudaStreamSynchronize(p->s_out));
+    return 0;
+}
+
+// diagnostics: number of iterations whose error metric was NaN / inf, per run (host array [n_batch]); synchronises the stream
+int xfb_mtip_get_nonfinite(xfb_plan* p, int32_t* out_host, void* stream) {
+    if (p->n_batch < 1) XFB_FAIL("xfb_mtip_init has not been called");
+    XFB_CUDA(cudaMemcpyAsync(out_host, p->ls.nonfinite, (size_t)p->n_batch * sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    XFB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return 0;
 }
 

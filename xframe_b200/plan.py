@@ -428,6 +428,12 @@ class Plan:
         _lib.check(self.lib.xfb_mtip_get_grid(self.h, w, _ptr(out), _stream()))
         return out if w < 4 else out.bool()
 
+    def mtip_nonfinite(self):
+        """Diagnostics: per run, the number of iterations whose error metric was NaN / inf."""
+        buf = (C.c_int32 * self.n_batch)()
+        _lib.check(self.lib.xfb_mtip_get_nonfinite(self.h, buf, _stream()))
+        return np.frombuffer(buf, dtype=np.int32).copy()
+
     def mtip_errors(self, capacity=16384):
         n = C.c_int32(0)
         hist = torch.zeros((self.n_batch, capacity), dtype=torch.float64, device=self.device)

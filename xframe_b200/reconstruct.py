@@ -148,5 +148,5 @@ def run_schedule(plan, opt, rho0, default_sigma=None, collect=True):
         'last_real': plan.mtip_grid('last_real').cpu().numpy(), 'last_reciprocal': plan.mtip_grid('last_reciprocal').cpu().numpy(),
         'best_real': plan.mtip_grid('best_real').cpu().numpy(), 'best_reciprocal': plan.mtip_grid('best_reciprocal').cpu().numpy(),
         'last_support': plan.mtip_grid('last_support').cpu().numpy(), 'best_support': plan.mtip_grid('best_support').cpu().numpy(),
-        'loop_iterations': int(np.sum(iterations) + 1),
+        'loop_iterations': int(np.sum(iterations) + 1), 'nonfinite_iterations': plan.mtip_nonfinite(),
     }

@@ -138,6 +138,7 @@ class ProjectWorker:
                 plan.mtip_enable_deg2_metric(True, iteration_count(self.opt)[0])
             res = run_schedule(plan, self.opt, rho0)
             deg2_hist = plan.mtip_deg2_errors(res['errors'].shape[1]).cpu().numpy()[..., :self.n_used_orders] if self.deg2_metric else None
+            self.results['stats'].setdefault('nonfinite_iterations', {}).update({int(r): int(n) for r, n in zip(ids, res['nonfinite_iterations'])})
             unknowns = [plan.unknowns(k) for k in range(len(ids))]      # of the last mtip_start (reconstruct.py:523,1013)
             if self.shift_to_center:                                    # output modifier on the best and the last pair (:988-989)
                 if self.fix_orientation and not hasattr(self, '_so_rot'):
