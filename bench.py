@@ -300,7 +300,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cb = cpu_reference(steps=args.steps, warmup=args.warmup)
+    cb = cpu_reference(steps=args.steps, warmup=args.warmup, n_workers=args.cpu_workers)
     line = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': cb['timed_s'] / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
@@ -490,8 +490,10 @@ def run_ours(args):
             try:
                 env = dict(os.environ, RANK='0', WORLD_SIZE='1')
                 kc = {'l63': 8, 'l127': 1, 'polar': 150}[args.workload]      # bounded sample: ~10-30 s of CPU work
-                out = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', str(kc), '--warmup', '1',
-                                      '--workload', args.workload], capture_output=True, text=True, timeout=1500, env=env).stdout.strip().splitlines()
+                cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', str(kc), '--warmup', '1', '--workload', args.workload]
+                if args.workload == 'l127':
+                    cmd += ['--cpu-workers', '8']       # ~4 GB and ~40 s per iteration and process at L=127 / N_r=256: a bounded sample
+                out = subprocess.run(cmd, capture_output=True, text=True, timeout=1500, env=env).stdout.strip().splitlines()
                 cb = json.loads(out[-1])['cpu_baseline']
             except Exception as e:      # noqa: BLE001
                 cb = {'value': None, 'unit': UNIT, 'cores': 0, 'kind': 'port', 'sample': f'failed: {e}'}
@@ -523,6 +525,7 @@ def main():
     ap.add_argument('--workload', default='l63', choices=sorted(WORKLOADS))
     ap.add_argument('--runs', type=int, default=None)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--cpu-workers', type=int, default=None, help='reference arm: number of concurrent single-thread processes (default: all host threads)')
     ap.add_argument('--single-stream', action='store_true', help='disable the two-stream overlap of batch halves (diagnostics)')
     args = ap.parse_args()
     select_workload(args.workload)
