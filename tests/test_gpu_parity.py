@@ -591,6 +591,23 @@ def test_results_do_not_depend_on_the_batch():
         p1.close()
 
 
+def test_tma_fed_hankel_gives_the_same_bits(monkeypatch):
+    """hankel3_tma_kernel (operand tiles by cp.async.bulk + mbarrier) against the cp.async ring kernel: same accumulation order, so
+    bit-identical outputs -- with partially filled row tiles (rows of an order not a multiple of 64), both directions."""
+    from xframe_b200.plan import Plan
+    rng = np.random.default_rng(17)
+    out = []
+    x = None
+    for tma in ('1', '0'):
+        monkeypatch.setenv('XFB_HANKEL_TMA', tma)
+        plan = Plan(15, 128, 0.322416, n_theta=16, n_phi=32, max_batch=3)
+        if x is None:
+            x = T(rng.standard_normal((3, 128, 256)) + 1j * rng.standard_normal((3, 128, 256)))
+        out.append((N(plan.hankel(x)), N(plan.hankel(x, inverse=True))))
+        plan.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
 def test_two_stream_halves_give_the_same_bits():
     """xfb_mtip_iterate with the batch cut into two halves on two streams (the second half one projection behind, Jacobi launches on a
     share of the SMs) against the single-stream path: identical densities, error histories and unknowns for every run."""

@@ -211,6 +211,127 @@ __global__ void __launch_bounds__(256, HK2_MINB) hankel2_kernel(const double2* _
     }
 }
 
+// v3: the same contraction with the operand tiles fed by the TMA engine (bulk asynchronous copies, cp.async.bulk ->
+// SASS UBLKCP) that signal an mbarrier per pipeline stage: ONE warp issues 64 + 16 row copies per K chunk (a 256-byte run of an
+// input row, a 512-byte run of a weight row, each to its padded shared-memory row) instead of 256 threads issuing six 16-byte
+// cp.async each, and the consumers wait on the stage's mbarrier phase instead of cp.async.wait_group.  Bulk copies cannot
+// zero-fill, so this kernel takes only full K chunks and full column tiles (n_sum % 16 == 0, N_r % 64 == 0: the L=63 / N_r=128
+// and L=127 / N_r=256 workloads); rows past the end of an order are not copied -- a GEMM row only feeds its own output row,
+// which is not stored.  Same accumulation order as hankel2_kernel: bit-identical results.
+__device__ __forceinline__ unsigned hk_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void hk_mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(hk_smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void hk_mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(hk_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void hk_mbar_wait(uint64_t* bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+                     : "=r"(done) : "r"(hk_smem_addr(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void hk_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(hk_smem_addr(smem_dst)), "l"(gmem_src),
+                 "r"(bytes), "r"(hk_smem_addr(bar)) : "memory");
+}
+static inline size_t hankel3_smem() { return hankel2_smem() + 64; }
+__global__ void __launch_bounds__(256, HK2_MINB) hankel3_tma_kernel(const double2* __restrict__ in, double2* __restrict__ out,
+                                                             const double* __restrict__ W, const HankelTile* __restrict__ tiles,
+                                                             int n_r, int n_sum, int skip, double scale, int inverse, int ldw, int accumulate) {
+    extern __shared__ __align__(16) unsigned char smem_hk[];
+    double2* As = reinterpret_cast<double2*>(smem_hk);                                     // [ST][HK_BM][HK2_LDA]
+    double* Bs = reinterpret_cast<double*>(As + HK2_ST * HK_BM * HK2_LDA);                 // [ST][HK_BK][HK2_LDB]
+    uint64_t* full = reinterpret_cast<uint64_t*>(Bs + HK2_ST * HK_BK * HK2_LDB);           // [ST] one mbarrier per stage
+    const HankelTile t = tiles[blockIdx.x];
+    const int k_tile0 = blockIdx.y * HK_BN;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps, warp tile 32 rows x 16 cols
+    const double* Wl = W + (size_t)t.l * n_sum * ldw;
+    double cre[4][2][2] = {}, cim[4][2][2] = {};
+    const int ar = lane >> 2, ak = lane & 3;
+    const int n_chunks = n_sum / HK_BK;
+    const int rows_valid = min(HK_BM, t.row_end - t.row0);
+    if (tid == 0) {
+#pragma unroll
+        for (int s_ = 0; s_ < HK2_ST; ++s_) hk_mbar_init(full + s_, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int ch, int st) {            // warp 0: arm the stage's barrier with the byte count, then the row copies
+        if (warp == 0 && ch < n_chunks) {
+            const int p0 = ch * HK_BK;
+            double2* a = As + (size_t)st * HK_BM * HK2_LDA;
+            double* b = Bs + (size_t)st * HK_BK * HK2_LDB;
+            if (lane == 0) hk_mbar_expect_tx(full + st, (unsigned)(rows_valid * HK_BK * sizeof(double2) + HK_BK * HK_BN * sizeof(double)));
+            __syncwarp();
+            for (int i = lane; i < HK_BM + HK_BK; i += 32) {
+                if (i < HK_BM) {
+                    if (i < rows_valid)
+                        hk_bulk_g2s(a + i * HK2_LDA, in + (size_t)(t.row0 + i) * n_r + skip + p0, HK_BK * sizeof(double2), full + st);
+                } else {
+                    const int pp = i - HK_BM;
+                    hk_bulk_g2s(b + pp * HK2_LDB, Wl + (size_t)(p0 + pp) * ldw + k_tile0, HK_BN * sizeof(double), full + st);
+                }
+            }
+        }
+    };
+#pragma unroll
+    for (int s_ = 0; s_ < HK2_ST - 1; ++s_) issue(s_, s_);
+    int st = 0;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        hk_mbar_wait(full + st, (unsigned)((ch / HK2_ST) & 1));      // this chunk's bytes have landed
+        __syncthreads();                                             // everyone is done with the stage refilled next
+        issue(ch + HK2_ST - 1, (st + HK2_ST - 1) % HK2_ST);
+        const double2* a = As + (size_t)st * HK_BM * HK2_LDA;
+        const double* b_ = Bs + (size_t)st * HK_BK * HK2_LDB;
+#pragma unroll
+        for (int k0 = 0; k0 < HK_BK; k0 += 4) {
+            double b[2];
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) b[nb] = b_[(k0 + ak) * HK2_LDB + wn * 16 + nb * 8 + ar];
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb) {
+                const double2 x = a[(wm * 32 + mb * 8 + ar) * HK2_LDA + k0 + ak];
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb) {
+                    dmma884(cre[mb][nb][0], cre[mb][nb][1], x.x, b[nb]);
+                    dmma884(cim[mb][nb][0], cim[mb][nb][1], x.y, b[nb]);
+                }
+            }
+        }
+        st = (st + 1) % HK2_ST;
+    }
+    const int ph = t.ph;
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) {
+        const int grow = t.row0 + wm * 32 + mb * 8 + ar;
+        if (grow >= t.row_end) continue;
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+            const int k = k_tile0 + wn * 16 + nb * 8 + 2 * ak;
+            double2 o[2];
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const double x = cre[mb][nb][cc] * scale, y = cim[mb][nb][cc] * scale;
+                double2 r;
+                if (ph == 0) r = make_double2(x, y);
+                else if (ph == 2) r = make_double2(-x, -y);
+                else if ((ph == 1) != (inverse != 0)) r = make_double2(y, -x);   // multiply by -i
+                else r = make_double2(-y, x);                                     // multiply by +i
+                o[cc] = r;
+            }
+            if (accumulate) {
+                const double2 c0 = out[(size_t)grow * n_r + k], c1 = out[(size_t)grow * n_r + k + 1];
+                o[0].x += c0.x; o[0].y += c0.y; o[1].x += c1.x; o[1].y += c1.y;
+            }
+            st_global_256(out + (size_t)grow * n_r + k, o[0], o[1]);            // k even, N_r % 64 == 0: 32-byte aligned pair
+        }
+    }
+}
+
 // Hankel transform evaluated at the first output radius only: out0[row] = (-+i)^l scale sum_p in[row][p+skip] W_l[p][0].
 // Used by the fused ft_stab step: only shell 0 of IFT(rho_hat) is needed.  One warp per row.
 __global__ void hankel_row0_kernel(const double2* __restrict__ in, double2* __restrict__ out0, const double* __restrict__ W, int n_rows,

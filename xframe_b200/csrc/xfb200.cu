@@ -54,6 +54,7 @@ struct xfb_plan {
     // intermediate `a` could stay inside the 126 MB L2.  Measured at 128 runs (profiles/r02a_sht_chunk_sweep.md): 9.2 - 13.5 ms
     // per step for the six transforms against 8.24 ms unchunked -- the smaller launches lose more than the L2 hits gain.
     int sht_chunk = 0, sht_streams = 3;
+    int hankel_tma = 1;                             // TMA-fed operand tiles where the shape allows (hankel3_tma_kernel)
     int leg_min_groups = 0;                         // >0: at least that many shell groups per Legendre CTA (measured at 16 / 32 runs: 8 and 16 are not faster than the wave rule)
     cudaStream_t sht_side[4] = {}; cudaEvent_t sht_fork = nullptr, sht_join[4] = {};
     long long launches_side = 0;
@@ -270,6 +271,7 @@ int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
     if (const char* e = getenv("XFB_SHT_CHUNK")) p->sht_chunk = std::max(0, atoi(e));          // experiments: sweep without rebuilding
     if (const char* e = getenv("XFB_SHT_STREAMS")) p->sht_streams = std::min(4, std::max(1, atoi(e)));
     if (const char* e = getenv("XFB_LEG_MINGROUPS")) p->leg_min_groups = std::max(0, atoi(e));
+    if (const char* e = getenv("XFB_HANKEL_TMA")) p->hankel_tma = atoi(e) != 0;
     if (const char* e = getenv("XFB_DUAL")) p->dual = atoi(e) != 0;
     if (const char* e = getenv("XFB_DUAL_BIG")) p->dual_big_sms = std::max(1, atoi(e));
     if (const char* e = getenv("XFB_DUAL_SMALL")) p->dual_small_sms = std::max(1, atoi(e));
@@ -574,6 +576,15 @@ static int hankel_i(xfb_plan* p, int dir, const double2* c_in, double2* c_out, i
     }
     p->hk_tiles = hit->second.first; p->hk_tiles_n = hit->second.second;
     dim3 g(p->hk_tiles_n, cdiv(p->n_r, HK_BN));
+    if (p->hankel_tma && p->n_r % HK_BN == 0 && p->hankel_n_sum % HK_BK == 0) {
+        // full K chunks and column tiles: operand tiles fed by the TMA engine (bulk copies + mbarrier per stage)
+        static XfbPerDeviceOnce attr3_once;
+        if (xfb_first_on_device(attr3_once)) XFB_CUDA(cudaFuncSetAttribute(hankel3_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hankel3_smem()));
+        XFB_LAUNCH(p, PG_HANKEL, st,
+                   hankel3_tma_kernel<<<g, 256, hankel3_smem(), st>>>(c_in, c_out, p->hankel_w, p->hk_tiles, p->n_r, p->hankel_n_sum, p->hankel_skip,
+                                                                     dir == 0 ? p->hk_fwd_scale : p->hk_inv_scale, dir, p->n_r, 0));
+        return 0;
+    }
     if (p->n_r % 2 == 0) {
         static XfbPerDeviceOnce attr_once;
         if (xfb_first_on_device(attr_once)) XFB_CUDA(cudaFuncSetAttribute(hankel2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hankel2_smem()));
