@@ -227,7 +227,10 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 //   64 NCG threads: warp = (row block of 8 rows) x (column-block pair cg < NCG: degrees m + 2 (16 cg + 0..15) [+1]);
 //   KS = k-steps held in registers.  <KS 8, NCG 2>: n_theta <= 64, NP <= 32 (L = 63), 4 CTAs per SM;
 //   <KS 16, NCG 4>: n_theta <= 128, NP <= 64 (L = 127), 64 table doubles per lane, 1 CTA of 8 warps per SM.
-static inline size_t legendre3_fwd_smem(int n_theta) { return (size_t)LEG2_FST * LEG2_FR * (n_theta + 4) * sizeof(double2); }
+#ifndef LEG3_BIG_ST
+#define LEG3_BIG_ST 3      // cp.async stages of the <KS 16, NCG 4> instantiation (one CTA per SM: shared memory allows up to 6)
+#endif
+static inline size_t legendre3_fwd_smem(int n_theta, int stages = LEG2_FST) { return (size_t)stages * LEG2_FR * (n_theta + 4) * sizeof(double2); }
 
 template <int R, int ST, int KS, int NCG>
 __global__ void __launch_bounds__(64 * NCG, KS <= 8 ? LEG3_MINB : 1) legendre3_forward_kernel(const double2* __restrict__ a, double2* __restrict__ c,
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__(64 * NCG, KS <= 8 ? LEG3_MINB : 1) legendre3_f
 // CTA; the coefficient rows of the next shell groups are gathered with cp.async (8 / 16 consecutive shells of one (l, +-m) row
 // are contiguous).  Table fragments in registers, two 8-node blocks per warp (see legendre3_forward_kernel): per k-step one 128-bit
 // shared load feeds 4 DMMAs.   128 threads: warp = (row block of 8 rows) x (node-block pair cg: theta_j, j = 16 cg + 0..15)
-static inline size_t legendre3_inv_smem(int NP) { return (size_t)LEG2_IST * 2 * LEG2_IR * (NP + 4) * sizeof(double2); }
+static inline size_t legendre3_inv_smem(int NP, int stages = LEG2_IST) { return (size_t)stages * 2 * LEG2_IR * (NP + 4) * sizeof(double2); }
 
 template <int R, int ST, int KS, int NCG>
 __global__ void __launch_bounds__(64 * NCG, KS <= 8 ? LEG3_MINB : 1) legendre3_inverse_kernel(const double2* __restrict__ c, double2* __restrict__ a,

@@ -54,7 +54,10 @@ struct xfb_plan {
     // intermediate `a` could stay inside the 126 MB L2.  Measured at 128 runs (profiles/r02a_sht_chunk_sweep.md): 9.2 - 13.5 ms
     // per step for the six transforms against 8.24 ms unchunked -- the smaller launches lose more than the L2 hits gain.
     int sht_chunk = 0, sht_streams = 3;
-    int hankel_tma = 1;                             // TMA-fed operand tiles where the shape allows (hankel3_tma_kernel)
+    // TMA-fed operand tiles (hankel3_tma_kernel: per-row bulk copies + mbarrier).  OFF by default: measured at 128 runs the Hankel
+    // group takes 3.57 ms per step against 2.42 ms with the cp.async ring (profiles/r02g_hankel_tma_ab.md) -- 80 row-sized bulk
+    // copies per K chunk issued by one warp cost more than 256 threads issuing six 16-byte cp.async each.
+    int hankel_tma = 0;
     int leg_min_groups = 0;                         // >0: at least that many shell groups per Legendre CTA (measured at 16 / 32 runs: 8 and 16 are not faster than the wave rule)
     cudaStream_t sht_side[4] = {}; cudaEvent_t sht_fork = nullptr, sht_join[4] = {};
     long long launches_side = 0;
@@ -280,9 +283,9 @@ int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
     p->leg3_big = p->leg2 && (p->n_theta / 2 > 32 || p->NP > 32);
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, dev); }
     if (p->leg2 && !p->leg3_big) XFB_CUDA(cudaFuncSetAttribute(legendre3_forward_kernel<LEG2_FR, LEG2_FST, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre3_fwd_smem(p->n_theta)));
-    if (p->leg3_big) XFB_CUDA(cudaFuncSetAttribute(legendre3_forward_kernel<LEG2_FR, LEG2_FST, 16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre3_fwd_smem(p->n_theta)));
+    if (p->leg3_big) XFB_CUDA(cudaFuncSetAttribute(legendre3_forward_kernel<LEG2_FR, LEG3_BIG_ST, 16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre3_fwd_smem(p->n_theta, LEG3_BIG_ST)));
     if (p->leg2 && !p->leg3_big) XFB_CUDA(cudaFuncSetAttribute(legendre3_inverse_kernel<LEG2_IR, LEG2_IST, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre3_inv_smem(p->NP)));
-    if (p->leg3_big) XFB_CUDA(cudaFuncSetAttribute(legendre3_inverse_kernel<LEG2_IR, LEG2_IST, 16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre3_inv_smem(p->NP)));
+    if (p->leg3_big) XFB_CUDA(cudaFuncSetAttribute(legendre3_inverse_kernel<LEG2_IR, LEG3_BIG_ST, 16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre3_inv_smem(p->NP, LEG3_BIG_ST)));
     XFB_CUDA(cudaFuncSetAttribute(legendre_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre_fwd_smem(p->n_theta)));
     XFB_CUDA(cudaFuncSetAttribute(legendre_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)legendre_inv_smem(p->n_theta, p->NP)));
     guard.p = nullptr;
@@ -391,12 +394,12 @@ static int launch_legendre3(xfb_plan* p, bool forward, double2* a, double2* c, i
     dim3 g2(gx, p->L + 1);
     if (forward) {
         if (p->leg3_big)
-            legendre3_forward_kernel<LEG2_FR, LEG2_FST, 16, 4><<<g2, 256, legendre3_fwd_smem(p->n_theta), st>>>(a, c, p->FE, p->FO, S, p->L, p->n_theta, p->NP, pos_only, c_stride);
+            legendre3_forward_kernel<LEG2_FR, LEG3_BIG_ST, 16, 4><<<g2, 256, legendre3_fwd_smem(p->n_theta, LEG3_BIG_ST), st>>>(a, c, p->FE, p->FO, S, p->L, p->n_theta, p->NP, pos_only, c_stride);
         else
             legendre3_forward_kernel<LEG2_FR, LEG2_FST, 8, 2><<<g2, 128, legendre3_fwd_smem(p->n_theta), st>>>(a, c, p->FE, p->FO, S, p->L, p->n_theta, p->NP, pos_only, c_stride);
     } else {
         if (p->leg3_big)
-            legendre3_inverse_kernel<LEG2_IR, LEG2_IST, 16, 4><<<g2, 256, legendre3_inv_smem(p->NP), st>>>(c, a, p->IE, p->IO, S, p->L, p->n_theta, p->NP, pos_only, c_stride);
+            legendre3_inverse_kernel<LEG2_IR, LEG3_BIG_ST, 16, 4><<<g2, 256, legendre3_inv_smem(p->NP, LEG3_BIG_ST), st>>>(c, a, p->IE, p->IO, S, p->L, p->n_theta, p->NP, pos_only, c_stride);
         else
             legendre3_inverse_kernel<LEG2_IR, LEG2_IST, 8, 2><<<g2, 128, legendre3_inv_smem(p->NP), st>>>(c, a, p->IE, p->IO, S, p->L, p->n_theta, p->NP, pos_only, c_stride);
     }
