@@ -270,3 +270,46 @@ def test_reference_sketch_tail_on_cuda_matches_project_worker(variant):
     assert got['loop_iterations'] == ref['loop_iterations'] and abs(got['final_error'] - ref['final_error']) < 1e-6 * ref['final_error']
     w.plan.close()
 
+
+@needs_ref
+@pytest.mark.gpu
+def test_reference_plugin_worker_saves_the_reference_record():
+    """xframe_b200.reference_plugin.ProjectWorker(): the reference's no-argument constructor contract (settings.project /
+    database.project globals, reconstruct.py:89-110), run() -> (result, locals()), post_processing -> db.save('reconstructions', record)
+    with the layout the reference's integration test asserts (tests/test_fxs_integration.py:388-421)."""
+    from xframe_b200.harmonic_transforms import sh
+    RH.import_reference(sh_class=sh, cuda_gpu_layer=True)
+    from xframe.library.pythonLibrary import DictNamespace
+    from xframe import settings
+    import xframe.database as database
+    sd = reference_test_settings(gpu=True, n_r=8)
+    sd['multi_process'] = {'use': True, 'n_parallel_reconstructions': 3}
+    sd['GPU']['seed'] = 5
+    inv = synthetic_invariants(sd)
+    settings.project = DictNamespace.dict_to_dictnamespace(sd)
+    database.project = RH.FakeDB(RH.fresh_data(inv))
+    from xframe_b200.reference_plugin import ProjectWorker
+    w = ProjectWorker()
+    result, _ = w.run()
+    assert result.dtype == object and len(result) == 3
+    rec = database.project.saved['reconstructions']
+    assert set(rec) == {'configuration', 'reconstruction_results', 'projection_matrices', 'stats'}
+    assert set(rec['configuration']) == {'internal_grid', 'xray_wavelength', 'reciprocity_coefficient'}
+    n_r, l_max = 8, 15
+    shape = (n_r, 16, 32)
+    assert rec['configuration']['internal_grid']['real_grid'].shape == shape + (3,)
+    assert list(rec['reconstruction_results']) == [str(i) for i in np.argsort([r['error_dict']['main'][-1] for r in result])]
+    n_it = len(result[0]['error_dict']['main'])
+    for r in rec['reconstruction_results'].values():
+        assert 'grid_pair' not in r and 'projection_matrices' not in r
+        for k in ('real_density', 'last_real_density', 'reciprocal_density', 'last_reciprocal_density', 'initial_density'):
+            assert r[k].shape == shape and r[k].dtype == complex
+        for k in ('support_mask', 'last_support_mask', 'initial_support'):
+            assert r[k].shape == shape and r[k].dtype == bool
+        assert r['last_deg2_invariant'].shape == (l_max + 1, n_r, n_r) and r['last_deg2_invariant'].dtype == complex
+        assert r['error_dict']['real']['l2_projection_diff'].shape == (n_it,) and r['n_particles'].shape == (n_it, 1)
+        assert [u.shape for u in r['fxs_unknowns']] == [(min(2 * i + 1, 2 * n_r), 2 * i + 1) for i in range(l_max + 1)]   # data on 2 N_r q points
+        assert isinstance(r['final_error'], float) and not np.isnan(r['real_density']).any()
+    assert [p.shape[0] for p in rec['projection_matrices']] == [n_r] * (l_max + 1)
+    w.worker.plan.close()
+
