@@ -266,3 +266,61 @@ def test_selective_reorthogonalisation_matches_always_twice():
         e0 = np.abs(Q0[:, :k].T @ Q0[:, :k] - np.eye(k)).max()
         e1 = np.abs(Q1[:, :k].T @ Q1[:, :k] - np.eye(k)).max()
         assert e1 < 10 * e0 + 1e-14, (decades, e0, e1)
+
+
+REF_DEFAULTS = '/root/reference/xframe/projects/fxs/settings/reconstruct/default_0.01.yaml'
+
+
+@pytest.mark.skipif(not os.path.exists(REF_DEFAULTS), reason='reference settings file not available (build container only)')
+def test_default_settings_transcribe_the_reference_yaml():
+    """settings.default_settings() against the reference's own defaults file, parsed here with its `_value` / `command` / `_copy`
+    conventions (database.py:500-506,643-684).  Every leaf that default_settings() carries must equal the YAML's value, except the
+    documented GPU additions and the `_if` switches on /dimensions that finalize() resolves."""
+    import yaml
+    with open(REF_DEFAULTS) as f:
+        raw = yaml.safe_load(f)
+    COPY = object()
+
+    def resolve(node):
+        if isinstance(node, dict):
+            if '_value' in node:
+                v = node['_value']
+                if isinstance(v, dict) and set(v) == {'command'}:
+                    return eval(v['command'], {'np': np})
+                if isinstance(v, dict) and '_copy' in v:
+                    return COPY
+                if isinstance(v, dict) and ('_if' in v or any(k.startswith('_') for k in v)):
+                    return COPY                                   # switch on another setting: resolved by finalize()
+                return v
+            return {k: resolve(v) for k, v in node.items() if not k.startswith('_')}
+        return node
+    ref = resolve(raw)
+    ours = ST.default_settings()
+    skipped, checked = [], [0]
+
+    def same(a, b):
+        if isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
+            return np.array_equal(np.asarray(a), np.asarray(b))
+        if isinstance(a, (list, tuple)) and isinstance(b, (list, tuple)):
+            return len(a) == len(b) and all(same(x, y) for x, y in zip(a, b))
+        if isinstance(a, float) or isinstance(b, float):
+            return type(a) is not bool and type(b) is not bool and abs(float(a) - float(b)) <= 1e-15 * max(1.0, abs(float(b))) \
+                if not (isinstance(a, bool) or isinstance(b, bool)) else a is b
+        return a == b and isinstance(a, bool) == isinstance(b, bool)
+
+    def walk(o, r, path):
+        for k, v in o.items():
+            pth = path + '/' + k
+            if pth in ('/GPU/batch', '/GPU/seed'):               # the only additions (INTEGRATION.md)
+                continue
+            assert k in r, f'{pth} is not a key of the reference defaults'
+            if isinstance(v, dict) and isinstance(r[k], dict):
+                walk(v, r[k], pth)
+            elif r[k] is COPY or v is None:                      # `_copy` links / dimension switches: finalize() fills them
+                skipped.append(pth)
+            else:
+                assert same(v, r[k]), f'{pth}: {v!r} != reference {r[k]!r}'
+                checked[0] += 1
+    walk(ours, ref, '')
+    assert checked[0] >= 40, (checked[0], skipped)
+

@@ -257,15 +257,23 @@ __global__ void __launch_bounds__(64 * NCG, KS <= 8 ? LEG3_MINB : 1) legendre3_f
 #pragma unroll
     for (int nb = 0; nb < 2; ++nb) { do_e[nb] = (2 * cg + nb) * 8 < ne; do_o[nb] = (2 * cg + nb) * 8 < no; }
 
+    // item = tid + q * LEG3_THREADS of the R x n_theta tile as (row, j): decomposed ONCE per thread, then advanced by the
+    // constant step with a carry -- the runtime division per 16-byte copy was a third of the kernel's instructions (ncu:
+    // issue slots 52 % busy with 4 % of the instructions being DMMAs)
+    const int row_t0 = tid / n_theta, j_t0 = tid - row_t0 * n_theta;
+    const int d_row = LEG3_THREADS / n_theta, d_j = LEG3_THREADS - d_row * n_theta;
     auto fetch = [&](int g, int buf) {
         if (g < n_groups) {
             double2* dst = raw + (size_t)buf * R * RS;
-            for (int item = tid; item < R * n_theta; item += LEG3_THREADS) {
-                const int row = item / n_theta, j = item - row * n_theta;
-                const int sh = g * SH + (both ? (row % (R / 2)) : row), sign = both ? (row / (R / 2)) : 0;
+            const int sh0 = g * SH;
+            int row = row_t0, j = j_t0;
+            while (row < R) {
+                const int sh = sh0 + (both ? (row % (R / 2)) : row), sign = both ? (row / (R / 2)) : 0;
                 const bool ok = sh < S;
                 const int mm = sign ? (M2 - m) : m;
                 cp_async16(dst + row * RS + j, a + ((size_t)(ok ? sh : 0) * M2 + mm) * n_theta + j, ok);
+                row += d_row; j += d_j;
+                if (j >= n_theta) { j -= n_theta; ++row; }
             }
         }
         cp_async_commit();                                 // (possibly empty) group: keeps the wait count uniform
@@ -363,20 +371,30 @@ __global__ void __launch_bounds__(64 * NCG, KS <= 8 ? LEG3_MINB : 1) legendre3_i
 #pragma unroll
     for (int nb = 0; nb < 2; ++nb) jok[nb] = (2 * cg + nb) * 8 < K2;
 
+    // item = tid + q * LEG3_THREADS of the (parity, degree index, [sign], shell) tile, shells fastest (contiguous 16-byte elements of
+    // one coefficient row).  SH and 2 SH divide the thread count, so the shell and the sign of a thread never change; the pair
+    // (degree index i, parity) is decomposed once and advanced with a carry (no runtime division per copy).
+    const int shl_t = tid % SH;
+    const int rest_t = tid / SH;
+    const int sign_t = both ? (rest_t & 1) : 0;
+    const int rest_t2 = both ? (rest_t >> 1) : rest_t;
+    const int i_t0 = rest_t2 % NP, par_t0 = rest_t2 / NP;
+    const int d_rest = (LEG3_THREADS / SH) >> (both ? 1 : 0);
+    const int d_i = d_rest % NP, d_par = d_rest / NP;
+    const int row_t = sign_t * (R / 2) + shl_t;
+    const int ms_t = sign_t ? -m : m;
     auto fetch = [&](int g, int buf) {
         if (g < n_groups) {
             double2* dst = raw + (size_t)buf * 2 * R * RS;
-            for (int item = tid; item < 2 * NP * R; item += LEG3_THREADS) {
-                const int shl = item % SH;                 // shells fastest: contiguous 16-byte elements of one coefficient row
-                int rest = item / SH;
-                const int sign = both ? (rest & 1) : 0;
-                if (both) rest >>= 1;
-                const int i = rest % NP, par = rest / NP;
+            const int sh = g * SH + shl_t;
+            const bool sh_ok = sh < S;
+            int i = i_t0, par = par_t0;
+            while (par < 2) {
                 const int l = m + par + 2 * i;
-                const int sh = g * SH + shl;
-                const bool ok = (l <= l_max) && (sh < S);
-                const int row = sign * (R / 2) + shl;
-                cp_async16(dst + ((size_t)par * R + row) * RS + i, c + (size_t)(ok ? l * (l + 1) + (sign ? -m : m) : 0) * c_stride + (ok ? sh : 0), ok);
+                const bool ok = sh_ok && (l <= l_max);
+                cp_async16(dst + ((size_t)par * R + row_t) * RS + i, c + (size_t)(ok ? l * (l + 1) + ms_t : 0) * c_stride + (ok ? sh : 0), ok);
+                i += d_i; par += d_par;
+                if (i >= NP) { i -= NP; ++par; }
             }
         }
         cp_async_commit();
