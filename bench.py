@@ -428,24 +428,28 @@ def run_ours(args):
     gather = None
     if world > 1:
         from xframe_b200.distributed import gather_results
-        loc = {'last_real_density': plan.mtip_grid('last_real'), 'final_error': plan.mtip_errors()[1]}
-        gather_results({'final_error': loc['final_error']}, total)          # warm-up: communicator set-up
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        g0.record()
-        full = gather_results(loc, total)
-        g1.record()
-        barrier()
-        gms = g0.elapsed_time(g1)
-        moved = (total - nb) * int(np.prod(plan.grid_shape)) * 16
-        ok = True
-        if rank == 0:
-            mine = full['last_real_density'][torch.as_tensor(ids, device=full['last_real_density'].device)]
-            ok = bool(torch.equal(mine, loc['last_real_density'])) and full['last_real_density'].shape[0] == total
-        gather = {'api': 'xframe_b200.distributed.gather_results (ncclGather of last_real_density + final_error to rank 0)',
-                  'bytes_over_nvlink': moved, 'ms': gms, 'GBps': moved / (gms * 1e-3) / 1e9 if gms > 0 else None, 'rank0_check': ok}
-        del full
-
+        need = nb * int(np.prod(plan.grid_shape)) * 16
+        fits = torch.tensor([1.0 if torch.cuda.mem_get_info()[0] > 1.3 * need + (2 << 30) else 0.0], dtype=torch.float64, device='cuda')
+        dist.all_reduce(fits, op=dist.ReduceOp.MIN)
+        if float(fits.item()) > 0:
+            loc = {'last_real_density': plan.mtip_grid('last_real'), 'final_error': plan.mtip_errors()[1]}
+            gather_results({'final_error': loc['final_error']}, total)          # warm-up: communicator set-up
+            barrier()
+            g0 = time.perf_counter()
+            full = gather_results(loc, total)                                   # NCCL send / recv in 1 GiB pieces, result in host memory on rank 0
+            barrier()
+            gms = (time.perf_counter() - g0) * 1e3
+            moved = (total - nb) * int(np.prod(plan.grid_shape)) * 16
+            ok = True
+            if rank == 0:
+                mine = full['last_real_density'][torch.as_tensor(ids)]
+                ok = bool(torch.equal(mine, loc['last_real_density'].cpu())) and full['last_real_density'].shape[0] == total
+            gather = {'api': 'xframe_b200.distributed.gather_results (NCCL send / recv of last_real_density + final_error to rank 0 in 1 GiB pieces, '
+                             'result in host memory; wall clock incl. the device-to-host copies on rank 0)',
+                      'bytes_over_nvlink': moved, 'ms': gms, 'GBps': moved / (gms * 1e-3) / 1e9 if gms > 0 else None, 'rank0_check': ok}
+            del full, loc
+        else:
+            gather = {'skipped': f'less than 1.3 x {need >> 20} MiB + 2 GiB of device memory free next to the working set for the staging copy of the shard'}
     if rank == 0:
         peak, peak_src = peaks()
         ab = algorithmic_bytes(nb)

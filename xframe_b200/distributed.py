@@ -15,14 +15,17 @@ def shard_run_ids(n_runs, rank, world):
     return [i for i in range(n_runs) if i % world == rank]
 
 
-def gather_results(local, n_runs, device=None):
+def gather_results(local, n_runs, device=None, chunk_bytes=1 << 30):
     """local: dict name -> tensor [n_local, ...] (same trailing shapes and dtypes on every rank, run order as
-    shard_run_ids).  Returns on rank 0 a dict name -> tensor [n_runs, ...] in global run order; None elsewhere."""
+    shard_run_ids).  Returns on rank 0 a dict name -> HOST tensor [n_runs, ...] in global run order; None elsewhere.
+
+    The runs travel rank by rank in pieces of at most chunk_bytes (NCCL send / recv over NVLink / NVSwitch on the GPU box, gloo in
+    the CPU test) through one staging buffer on rank 0 and land in host memory, where post_processing works on them
+    (reconstruct.py:160-183): at L=127 / N_r=256 the 512 densities of a full job are 64 GiB -- more than is free next to the
+    working set of rank 0's own shard."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return {k: v.clone() for k, v in local.items()}
+        return {k: v.detach().cpu().clone() for k, v in local.items()}
     world, rank = dist.get_world_size(), dist.get_rank()
-    counts = [len(shard_run_ids(n_runs, r, world)) for r in range(world)]
-    cap = max(counts)
     out = {}
     for name in sorted(local):
         t = local[name]
@@ -34,16 +37,25 @@ def gather_results(local, n_runs, device=None):
         is_cplx = t.is_complex()
         if is_cplx:
             t = torch.view_as_real(t)
-        pad = torch.zeros((cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        pad[:t.shape[0]] = t
-        bufs = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
-        dist.gather(pad, bufs, dst=0)                      # ncclGather over NVLink / NVSwitch on the GPU box
+        t = t.contiguous()
+        tail = tuple(t.shape[1:])
+        per_run = max(1, int(np.prod(tail)) * t.element_size())
+        step = max(1, int(chunk_bytes // per_run))
+        full = torch.empty((n_runs,) + tail, dtype=t.dtype) if rank == 0 else None
+        for r in range(world):
+            ids = shard_run_ids(n_runs, r, world)
+            for k0 in range(0, len(ids), step):
+                part = ids[k0:k0 + step]
+                if r == 0:
+                    if rank == 0:
+                        full[torch.as_tensor(part)] = t[k0:k0 + len(part)].cpu()
+                elif rank == r:
+                    dist.send(t[k0:k0 + len(part)].contiguous(), dst=0)
+                elif rank == 0:
+                    buf = torch.empty((len(part),) + tail, dtype=t.dtype, device=t.device)
+                    dist.recv(buf, src=r)
+                    full[torch.as_tensor(part)] = buf.cpu()
         if rank == 0:
-            full = torch.empty((n_runs,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-            for r in range(world):
-                ids = shard_run_ids(n_runs, r, world)
-                if ids:
-                    full[torch.as_tensor(ids, device=t.device)] = bufs[r][:len(ids)]
             if is_cplx:
                 full = torch.view_as_complex(full)
             if was_bool:
