@@ -147,3 +147,93 @@ __global__ void project2d_kernel(const double2* __restrict__ c_in, double2* __re
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Folded DFT of odd length N = 2M+1 (the circular-harmonic transform of the 2-D path) on the FP64 tensor cores.
+//   cos(2 pi j k / N) is even and sin odd under j -> N - j and under k -> N - k, so with
+//       e_0 = x_0, e_j = x_j + x_{N-j},  o_j = x_j - x_{N-j}            (j = 1..M)
+//       A_k = sum_j e_j cos(2 pi j k / N),  B_k = sum_j o_j sin(2 pi j k / N)      (k = 0..M)
+//   the forward transform is Y_k = A_k - i B_k, Y_{N-k} = A_k + i B_k and the inverse x_j = A'_j + i B'_j, x_{N-j} = A'_j - i B'_j
+//   with (e', o') built from (c_k, c_{N-k}): two real [H x H] matrices (H = M+1 padded to 16) instead of two [N x N] ones --
+//   a quarter of the flops of the dense product, and the transposition between the row layout [S][N] of the grids and the
+//   order-major layout [N][S] of the coefficients is done by the fold / combine kernels themselves.
+//   Row buffers: eo [2][S][H] (block 0 = e rows, block 1 = o rows), ab [2][S][H] (A rows, B rows).
+// ---------------------------------------------------------------------------------------------------------------------
+// forward fold: grid rows (slot view) -> eo
+__global__ void dft_fold_rows_kernel(SlotView grid, int shells_per_run, double2* __restrict__ eo, int S, int N, int H) {
+    const int M = N / 2;
+    const long long n = (long long)S * H;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const int s = (int)(idx / H), j = (int)(idx - (long long)s * H);
+        const int b = s / shells_per_run, r = s - b * shells_per_run;
+        const double2* x = slot_run_ptr(grid, b) + (long long)r * N;
+        double2 e = make_double2(0.0, 0.0), o = e;
+        if (j == 0) e = x[0];
+        else if (j <= M) {
+            const double2 u = x[j], v = x[N - j];
+            e = make_double2(u.x + v.x, u.y + v.y);
+            o = make_double2(u.x - v.x, u.y - v.y);
+        }
+        eo[idx] = e;
+        eo[n + idx] = o;
+    }
+}
+// forward combine (+ transposition): ab -> c2[k][s] = scale (A - i B), c2[N-k][s] = scale (A + i B)
+__global__ void dft_combine_to_orders_kernel(const double2* __restrict__ ab, double2* __restrict__ c2, int S, int N, int H, double scale) {
+    __shared__ double2 ta[32][33], tb[32][33];
+    const int M = N / 2;
+    const int k0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
+    const long long n = (long long)S * H;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {           // rows: k contiguous
+        const int s = s0 + i, k = k0 + threadIdx.x;
+        if (s < S && k <= M) { ta[i][threadIdx.x] = ab[(long long)s * H + k]; tb[i][threadIdx.x] = ab[n + (long long)s * H + k]; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {           // columns: s contiguous
+        const int k = k0 + i, s = s0 + threadIdx.x;
+        if (s < S && k <= M) {
+            const double2 a = ta[threadIdx.x][i], b = tb[threadIdx.x][i];
+            c2[(long long)k * S + s] = make_double2(scale * (a.x + b.y), scale * (a.y - b.x));                 // A - i B
+            if (k > 0) c2[(long long)(N - k) * S + s] = make_double2(scale * (a.x - b.y), scale * (a.y + b.x));   // A + i B
+        }
+    }
+}
+// inverse fold (+ transposition): c2[k][s] -> eo;  herm: only k <= M is valid and c_{N-k} = conj c_k, Im c_0 = 0 (irfft)
+__global__ void dft_fold_orders_kernel(const double2* __restrict__ c2, double2* __restrict__ eo, int S, int N, int H, int herm) {
+    __shared__ double2 te[32][33], to_[32][33];
+    const int M = N / 2;
+    const int k0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
+    const long long n = (long long)S * H;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {           // s contiguous
+        const int k = k0 + i, s = s0 + threadIdx.x;
+        double2 e = make_double2(0.0, 0.0), o = e;
+        if (s < S && k <= M) {
+            const double2 u = c2[(long long)k * S + s];
+            if (k == 0) e = herm ? make_double2(u.x, 0.0) : u;
+            else {
+                const double2 v = herm ? make_double2(u.x, -u.y) : c2[(long long)(N - k) * S + s];
+                e = make_double2(u.x + v.x, u.y + v.y);
+                o = make_double2(u.x - v.x, u.y - v.y);
+            }
+        }
+        te[i][threadIdx.x] = e; to_[i][threadIdx.x] = o;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {           // k contiguous
+        const int s = s0 + i, k = k0 + threadIdx.x;
+        if (s < S && k < H) { eo[(long long)s * H + k] = te[threadIdx.x][i]; eo[n + (long long)s * H + k] = to_[threadIdx.x][i]; }
+    }
+}
+// inverse combine: ab -> grid rows x[s][j] = A + i B, x[s][N-j] = A - i B
+__global__ void dft_combine_to_rows_kernel(const double2* __restrict__ ab, double2* __restrict__ rows, int S, int N, int H) {
+    const int M = N / 2;
+    const long long n = (long long)S * H, tot = (long long)S * (M + 1);
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < tot; idx += (long long)gridDim.x * blockDim.x) {
+        const int s = (int)(idx / (M + 1)), j = (int)(idx - (long long)s * (M + 1));
+        const double2 a = ab[(long long)s * H + j], b = ab[n + (long long)s * H + j];
+        double2* x = rows + (long long)s * N;
+        x[j] = make_double2(a.x - b.y, a.y + b.x);                                   // A + i B
+        if (j > 0) x[N - j] = make_double2(a.x + b.y, a.y - b.x);                    // A - i B
+    }
+}
+

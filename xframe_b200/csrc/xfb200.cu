@@ -35,6 +35,9 @@ struct xfb_plan {
     double2* v2d = nullptr; double2* unk2d = nullptr; int n_orders2d = 0, so_order2d = -1;
     // 2-D DFT as two real DMMA GEMMs per transform: cos / sin matrices [2][N][ldw], row-major temporaries [B*G]
     double* dft_cs = nullptr; int dft_ldw = 0; double2 *T2a = nullptr, *T2b = nullptr;
+    // folded DFT (polar.cuh): cos / sin half matrices [2][H][H], H = M+1 padded to 16; row buffers of max(N, 2H) complex per shell
+    double* dft_fold = nullptr; int dft_H = 0, dft_fold_on = 1; long long t2_run = 0;
+    std::map<int, std::pair<HankelTile*, int>> dft_fold_tiles;
     std::map<int, std::pair<HankelTile*, int>> dft_tiles;     // per number of shells S: tiles for the C pass and the S pass
     int hankel_skip = 0, hankel_n_sum = 0;
     double hk_fwd_scale = 0, hk_inv_scale = 0;
@@ -161,7 +164,7 @@ struct ScratchShift {
     void apply(long long s) {
         const long long b = (long long)b0 * s;
         mv(p->W0, b * p->G); mv(p->W1, b * p->G); mv(p->W2, b * p->G); mv(p->C0, b * p->C); mv(p->C1, b * p->C);
-        mv(p->T2a, b * p->G); mv(p->T2b, b * p->G);
+        mv(p->T2a, b * p->t2_run); mv(p->T2b, b * p->t2_run);
         if (p->dims == 3) { mv(p->A0, b * p->n_r * p->M2 * p->n_theta); mv(p->A0s, b * p->M2 * p->n_theta); mv(p->C0s, b * p->NLM); mv(p->rt0, b * p->n_theta * p->n_phi); }
         mv(p->xt, b * p->xt_run); mv(p->tt, b * p->xt_run); mv(p->g, b * p->g_run); mv(p->gn, b * p->g_run); mv(p->pp, b * p->g_run);
         mv(p->vw, b * p->vw_run); mv(p->sigma, b * (long long)p->orders.size() * p->sig_ld); mv(p->sweeps_dev, b * (long long)p->orders.size());
@@ -231,8 +234,22 @@ int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
                     cs[(size_t)(N + a) * p->dft_ldw + b] = (double)sinl(ang);
                 }
             if (dev_upload(p, &p->dft_cs, cs.data(), cs.size())) return 1;
-            if (dev_alloc(p, &p->T2a, B2 * p->G)) return 1;
-            if (dev_alloc(p, &p->T2b, B2 * p->G)) return 1;
+            {   // folded transform: cos / sin of 2 pi (j k mod N) / N for j, k = 0 .. M, zero padded to H
+                const int M = N / 2, H = (M + 1 + 15) & ~15;
+                p->dft_H = H;
+                std::vector<double> fw((size_t)2 * H * H, 0.0);
+                for (int a = 0; a <= M; ++a)
+                    for (int b = 0; b <= M; ++b) {
+                        const long double ang = 2.0L * 3.14159265358979323846264338327950288L * (long double)(((long long)a * b) % N) / (long double)N;
+                        fw[(size_t)a * H + b] = (double)cosl(ang);
+                        if (a > 0 && b > 0) fw[(size_t)H * H + (size_t)a * H + b] = (double)sinl(ang);
+                    }
+                if (dev_upload(p, &p->dft_fold, fw.data(), fw.size())) return 1;
+                if (const char* e = getenv("XFB_DFT_FOLD")) p->dft_fold_on = atoi(e) != 0;
+                p->t2_run = (long long)p->n_r * std::max(N, 2 * H);
+            }
+            if (dev_alloc(p, &p->T2a, B2 * (size_t)p->t2_run)) return 1;
+            if (dev_alloc(p, &p->T2b, B2 * (size_t)p->t2_run)) return 1;
             XFB_CUDA(cudaFuncSetAttribute(hankel2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hankel2_smem()));
         }
         XFB_CUDA(cudaFuncSetAttribute(dft2d_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dft_smem(p->n_phi)));
@@ -296,12 +313,13 @@ int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
 int xfb_plan_destroy(xfb_plan* p) {
     if (!p) return 0;
     void* ptrs[] = {p->tw, p->FE, p->FO, p->IE, p->IO, p->hankel_w, p->int_wt, p->q_pts, p->A0, p->C0, p->C1, p->W0, p->W1, p->W2, p->A0s, p->C0s, p->rt0, p->stage_out,
-                    p->v2d, p->unk2d, p->dft_cs, p->T2a, p->T2b, p->orders_dev, p->kind_dev, p->act_index_dev, p->radial_mask_dev, p->v0_dev, p->pd_dev, p->vt_dev,
+                    p->v2d, p->unk2d, p->dft_cs, p->dft_fold, p->T2a, p->T2b, p->orders_dev, p->kind_dev, p->act_index_dev, p->radial_mask_dev, p->v0_dev, p->pd_dev, p->vt_dev,
                     p->xt, p->tt, p->g, p->gn, p->vw, p->sigma, p->sweeps_dev, p->jac_counter, p->pp, p->gn_u, p->pp_u, p->sigma_u, p->i00, p->gemmY_dev, p->gemmY_tp, p->gemmM_dev, p->gemmT_dev, p->gemmM_tp, p->gemmT_tp,
                     p->init_support_dev, p->avg_mean, p->fix_int, p->fix_cand, p->d2_x, p->d2_b, p->d2_ref, p->d2_norm, p->d2_hist, p->d2_gemm, p->d2_tp, p->rho_pool, p->rh_pool, p->mask_pool, p->ls_ints, p->ls_dbl, p->partial, p->err, p->mm};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& kv : p->hk_cache) cudaFree(kv.second.first);
     for (auto& kv : p->dft_tiles) cudaFree(kv.second.first);
+    for (auto& kv : p->dft_fold_tiles) cudaFree(kv.second.first);
     for (auto& e : p->prof_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto e : p->ev_in) cudaEventDestroy(e);
     for (auto e : p->ev_comp) cudaEventDestroy(e);
@@ -373,6 +391,41 @@ static int dft2d_gemm_i(xfb_plan* p, const double2* rows_in, double2* rows_out, 
     return 0;
 }
 
+
+// Folded circular-harmonic transform (polar.cuh): fold -> ONE launch of the DMMA GEMM kernel over the stacked [2 S][H] row array
+// (rows [0, S): e rows x cos matrix, rows [S, 2 S): o rows x sin matrix) -> combine.  The row buffers are T2a (e | o) and T2b (A | B).
+static int dft2d_fold_gemm_i(xfb_plan* p, int S, cudaStream_t st) {
+    const int H = p->dft_H;
+    auto hit = p->dft_fold_tiles.find(S);
+    if (hit == p->dft_fold_tiles.end()) {
+        std::vector<HankelTile> tiles;
+        for (int blk = 0; blk < 2; ++blk)
+            for (int r = 0; r < S; r += HK_BM) tiles.push_back(HankelTile{blk, blk * S + r, (blk + 1) * S, 0});
+        HankelTile* dev = nullptr;
+        XFB_CUDA(cudaMalloc((void**)&dev, tiles.size() * sizeof(HankelTile)));
+        XFB_CUDA(cudaMemcpyAsync(dev, tiles.data(), tiles.size() * sizeof(HankelTile), cudaMemcpyHostToDevice, st));
+        XFB_CUDA(cudaStreamSynchronize(st));
+        hit = p->dft_fold_tiles.emplace(S, std::make_pair(dev, (int)tiles.size())).first;
+    }
+    dim3 g(hit->second.second, cdiv(H, HK_BN));
+    XFB_LAUNCH(p, PG_FFT, st, hankel2_kernel<<<g, 256, hankel2_smem(), st>>>(p->T2a, p->T2b, p->dft_fold, hit->second.first, H, H, 0, 1.0, 0, H, 0));
+    return 0;
+}
+static int dft2d_forward_folded_i(xfb_plan* p, SlotView in, int shells_per_run, double2* c_out, int S, cudaStream_t st) {
+    const int N = p->n_phi, H = p->dft_H;
+    XFB_LAUNCH(p, PG_FFT, st, dft_fold_rows_kernel<<<ew_blocks((long long)S * H), 256, 0, st>>>(in, shells_per_run, p->T2a, S, N, H));
+    if (dft2d_fold_gemm_i(p, S, st)) return 1;
+    XFB_LAUNCH(p, PG_FFT, st,
+               dft_combine_to_orders_kernel<<<dim3(cdiv(N / 2 + 1, 32), cdiv(S, 32)), dim3(32, 8), 0, st>>>(p->T2b, c_out, S, N, H, 1.0 / N));
+    return 0;
+}
+static int dft2d_inverse_folded_i(xfb_plan* p, const double2* c_in, double2* grid_out, int S, int herm, cudaStream_t st) {
+    const int N = p->n_phi, H = p->dft_H;
+    XFB_LAUNCH(p, PG_FFT, st, dft_fold_orders_kernel<<<dim3(cdiv(H, 32), cdiv(S, 32)), dim3(32, 8), 0, st>>>(c_in, p->T2a, S, N, H, herm));
+    if (dft2d_fold_gemm_i(p, S, st)) return 1;
+    XFB_LAUNCH(p, PG_FFT, st, dft_combine_to_rows_kernel<<<ew_blocks((long long)S * (N / 2 + 1)), 256, 0, st>>>(p->T2b, grid_out, S, N, H));
+    return 0;
+}
 
 // ---- v3 Legendre launch + the chunked (L2-resident intermediate) transform -------------------------------------------
 // CTAs per order m for a launch over S shells: every CTA should walk over several shell groups (the cp.async ring needs a
@@ -493,8 +546,10 @@ static int sht_forward_i(xfb_plan* p, SlotView in, int shells_per_run, double2* 
                          const double2* sub = nullptr, int real_only = 0, int* half_used = nullptr, int square = 0) {
     if (half_used) *half_used = 0;
     if (p->dims == 2) {   // circular harmonic transform: fft(x)/n_phi  (mathLibrary.py:469-475,484-490)
+        if (!sub && S <= p->max_batch * p->n_r && p->dft_fold_on && S % shells_per_run == 0)
+            return dft2d_forward_folded_i(p, in, shells_per_run, c_out, S, st);
         if (!sub && S <= p->max_batch * p->n_r) {
-            // DMMA path: rows (gathered out of their slots if needed) x [cos | sin] -> row-major coefficients -> [N][S]
+            // dense DMMA path: rows (gathered out of their slots if needed) x [cos | sin] -> row-major coefficients -> [N][S]
             // (real_only needs nothing here: the callers pass fields whose imaginary part is exactly zero)
             const double2* rows = in.base;
             const bool flat = !in.slot && (in.run_stride == (long long)shells_per_run * p->n_phi || S <= shells_per_run);
@@ -527,6 +582,7 @@ static int sht_forward_i(xfb_plan* p, SlotView in, int shells_per_run, double2* 
 static int sht_inverse_i(xfb_plan* p, const double2* c_in, double2* grid_out, int S, cudaStream_t st, int herm = 0,
                          const double2* mod_rho_hat = nullptr, SlotView mod_out = SlotView{}, int shells_per_run = 1) {
     if (p->dims == 2) {   // ifft(c * n_phi) / irfft(c * n_phi, n_phi)  (mathLibrary.py:478-482,492-496)
+        if (S <= p->max_batch * p->n_r && p->dft_fold_on) return dft2d_inverse_folded_i(p, c_in, grid_out, S, herm, st);
         if (S <= p->max_batch * p->n_r) {
             if (transpose_i(p, c_in, p->T2a, p->n_phi, S, st)) return 1;                 // [N][S] -> rows [S][N]
             if (herm) {
