@@ -82,6 +82,25 @@ def test_projection_golden(case):
         assert rel_l2(got[l] @ got[l].conj().T, m.rp.deg2_invariants[l]) < 1e-8
 
 
+def test_plan_can_be_retargeted_to_new_invariants(case):
+    """xfb_plan_set_projection twice on one plan: the second set of constants replaces the first."""
+    g, sd, m, plan = case
+    from xframe_b200.plan import Plan
+    p2 = Plan(m.l_max, len(m.rs), float(g['max_q']), n_theta=int(g['n_theta']), n_phi=int(g['n_phi']), max_batch=2)
+    try:
+        rng = np.random.default_rng(8)
+        other = [rng.standard_normal(np.asarray(v).shape) for v in m.rp.projection_matrices]
+        p2.set_projection(other, m.rp.radial_mask, 2.0)
+        x = T(np.stack([g['I_direct'], g['I_direct']]))
+        first = N(p2.project_invariants(x))
+        p2.set_projection(m.rp.projection_matrices, m.rp.radial_mask, m.rp.number_of_particles[0])
+        second = N(p2.project_invariants(x))
+        assert rel_l2(first[0], g['Iproj_direct']) > 1e-3
+        assert np.array_equal(second, N(plan.project_invariants(x)))
+    finally:
+        p2.close()
+
+
 def test_elementwise_golden(case):
     g, sd, m, plan = case
     from xframe_b200.plan import HIO, ER
@@ -396,8 +415,20 @@ def test_full_size_projection_and_iteration_against_oracle(full):
     rho_hat = m.ft(rho0)
     I = m.sh.forward_l(O.square_grid(rho_hat))
     Ip = m.rp.mtip_projection(I, m.rp.approximate_unknowns(I))
-    got = N(plan.project_invariants(T(np.concatenate(I, axis=1))[None]))[0]
+    got_t = plan.project_invariants(T(np.concatenate(I, axis=1))[None])
+    got = N(got_t)[0]
     assert rel_l2(got, np.concatenate(Ip, axis=1)) < 1e-6
+    # Separating "degenerate subspace" from "error" at full size: I'_l I'_l^H = V_l (P P^H) V_l^H does not depend on which orthonormal
+    # completion the SVD picks inside numerically degenerate subspaces, and the dropped directions (sigma < 1e-15 sigma_max) enter it
+    # quadratically -- so it must equal the measured invariants V_l V_l^H to rounding on every projected order (tolerance 1e-10, the
+    # FP64 bar of BASELINE.json configs[3]), for the device result AND for the reference formula.
+    Bp = N(plan.deg2_invariants(got_t))[0]
+    for l in range(0, 64, 2):
+        V = np.asarray(m.rp.projection_matrices[l]).real
+        want = V @ V.T if l else (V @ V.T) / m.rp.number_of_particles[0]
+        assert rel_l2(Bp[l], want) < 1e-10, (l, rel_l2(Bp[l], want))
+        ref_b = (Ip[l] @ Ip[l].conj().T).real
+        assert rel_l2(ref_b, want) < 1e-10, (l, 'reference formula')
     # one full iteration from the same state
     m.results['errors'] = {'real': {'l2_projection_diff': []}, 'reciprocal': {}, 'main': []}
     m.beta = 0.5

@@ -928,9 +928,23 @@ static int shrinkwrap_i(xfb_plan* p, SlotView rho, double sigma, double threshol
 
 extern "C" {
 
+// a plan can be re-targeted to new invariants: the projection constants and their per-run workspaces are released and rebuilt
+static void projection_release(xfb_plan* p) {
+    void** ptrs[] = {(void**)&p->orders_dev, (void**)&p->kind_dev, (void**)&p->act_index_dev, (void**)&p->radial_mask_dev, (void**)&p->v0_dev,
+                     (void**)&p->pd_dev, (void**)&p->vt_dev, (void**)&p->xt, (void**)&p->tt, (void**)&p->g, (void**)&p->gn, (void**)&p->vw,
+                     (void**)&p->sigma, (void**)&p->sweeps_dev, (void**)&p->pp, (void**)&p->gn_u, (void**)&p->pp_u, (void**)&p->sigma_u,
+                     (void**)&p->i00, (void**)&p->gemmM_dev, (void**)&p->gemmT_dev, (void**)&p->gemmY_dev, (void**)&p->gemmM_tp,
+                     (void**)&p->gemmT_tp, (void**)&p->gemmY_tp, (void**)&p->v2d, (void**)&p->unk2d, (void**)&p->d2_ref, (void**)&p->d2_norm};
+    cudaDeviceSynchronize();
+    for (void** q : ptrs) if (*q) { cudaFree(*q); *q = nullptr; }
+    p->orders.clear(); p->ncols_all.clear();
+    p->gemm_nb = -1; p->proj_calls = 0; p->unk_stamp = -1; p->unk_run = -1; p->last_proj_nb = 0; p->d2_metric = false;
+    p->has_proj = false;
+}
+
 int xfb_plan_set_projection(xfb_plan* p, const xfb_projection_desc* d) {
     if (!p || !d) XFB_FAIL("null argument");
-    if (p->has_proj) XFB_FAIL("projection already set on this plan");
+    if (p->has_proj) projection_release(p);
     if (p->dims != 3) XFB_FAIL("xfb_plan_set_projection is the 3-D setter; use xfb_plan_set_projection_2d");
     const int L = p->L, n_r = p->n_r;
     std::vector<int> kind(L + 1, ORD_PASS), act(L + 1, -1);
@@ -1047,7 +1061,7 @@ int xfb_plan_set_projection_2d(xfb_plan* p, int32_t n_orders, const double* v, c
                                int32_t so_order_id) {
     if (!p || !v || !radial_mask) XFB_FAIL("null argument");
     if (p->dims != 2) XFB_FAIL("xfb_plan_set_projection_2d needs a 2-D plan");
-    if (p->has_proj) XFB_FAIL("projection already set on this plan");
+    if (p->has_proj) projection_release(p);
     if (n_orders < 1 || n_orders > p->L + 1) XFB_FAIL("n_orders=%d outside 1..%d", n_orders, p->L + 1);
     if (dev_upload(p, &p->v2d, (const double2*)v, (size_t)n_orders * p->n_r)) return 1;
     if (dev_upload(p, &p->radial_mask_dev, radial_mask, (size_t)(p->L + 1) * p->n_r)) return 1;
