@@ -117,6 +117,8 @@ int xfb_plan_set_dual_stream(xfb_plan* p, int32_t on, int32_t min_batch, int32_t
 /* L2-resident phi-Fourier intermediate: runs per transform chunk (0 = unchunked) and streams (1..4) the chunks are spread over */
 int xfb_plan_set_sht_chunk(xfb_plan* p, int32_t runs_per_chunk, int32_t streams);
 /* diagnostics: Jacobi sweeps of the last projection, host array [n_batch][n_active_orders]; orders_out lists the orders */
+/* diagnostics: cycles per phase of the Jacobi kernel summed over all problems since the last call (library built with -DJAC_TIMING) */
+int xfb_debug_jacobi_phase_cycles(double* out8_host);
 int xfb_debug_jacobi_sweeps(xfb_plan* p, int32_t* out_host, int32_t capacity, int32_t* n_orders_out, int32_t* orders_out);
 
 /* ---- operator level: the harmonic-transform / Hankel / FT interfaces ---- */

@@ -45,6 +45,7 @@ EXPORTS = {
     'xfb_get_unknowns_2d': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'xfb_plan_set_real': (C.c_int, [C.c_void_p, C.POINTER(RealDesc), C.c_void_p]),
     'xfb_plan_workspace_bytes': (C.c_int64, [C.c_void_p]),
+    'xfb_debug_jacobi_phase_cycles': (C.c_int, [C.POINTER(C.c_double)]),
     'xfb_debug_jacobi_sweeps': (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     'xfb_plan_set_fused_ft_stab': (C.c_int, [C.c_void_p, C.c_int32]),
     'xfb_plan_set_dual_stream': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

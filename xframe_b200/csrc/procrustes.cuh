@@ -498,6 +498,19 @@ __device__ __forceinline__ void jacobi_active_list(const double* Gs, int ldg, in
     __syncthreads();
 }
 
+// Phase timing of the QR-preconditioned path (diagnostics, compiled in with -DJAC_TIMING only): cycles summed over all problems
+//   0 active list + gather, 1 first QR, 2 second QR, 3 sweeps, 4 final norms + polar product, 5 problems, 6 sweeps run
+__device__ unsigned long long g_jac_phase[8];
+#ifdef JAC_TIMING
+#define JAC_T0() long long jt_ = clock64()
+#define JAC_TICK(i) do { __syncthreads(); if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_jac_phase[i], (unsigned long long)(t_ - jt_)); jt_ = t_; } } while (0)
+#define JAC_COUNT(i, v) do { if (threadIdx.x == 0) atomicAdd(&g_jac_phase[i], (unsigned long long)(v)); } while (0)
+#else
+#define JAC_T0()
+#define JAC_TICK(i)
+#define JAC_COUNT(i, v)
+#endif
+
 // QR-preconditioned polar factor of one problem (Drmac-Veselic style preconditioning of the one-sided Jacobi SVD):
 //   G_a = Q1 R1 (active columns only, len x r);  R1^T = Q2 R2;  L = R2^T;  Jacobi on the columns of L with the same
 //   rotations applied to the columns of Q2:  L J = U~ Sigma,  W = Q2 J  =>  polar(R1) = U~ W^T =: P,  polar(G_a) = Q1 P.
@@ -515,6 +528,7 @@ __device__ __forceinline__ int jacobi_qr_problem(const double* __restrict__ g, i
     double* B = A + (size_t)r * ldg;    // [r][ldl]
     double* C = B + (size_t)r * ldl;    // [r][ldl]
     int* list2 = list + n;              // active columns of L (the caller reserved 2n ints)
+    JAC_T0();
     // ---- gather the active columns, zero the outputs (rows / entries of inactive columns stay zero)
     for (int i = tid; i < r * (ldg / 2); i += nthr) {
         const int a = i / (ldg / 2), e = i - a * (ldg / 2);
@@ -525,12 +539,15 @@ __device__ __forceinline__ int jacobi_qr_problem(const double* __restrict__ g, i
         reinterpret_cast<double2*>(pp)[i] = make_double2(0.0, 0.0);
     }
     __syncthreads();
+    JAC_TICK(0);
     mgs2_qr_dispatch<MAXV2>(A, ldg, len_g, r, B, ldl, nrm2, list2);     // A = Q1, B = columns of R1^T (nrm2 / list2 are free until the sweeps)
     for (int i = tid; i < r * (ldg / 2); i += nthr) {     // Q1 is final: rows list[a] of gn
         const int a = i / (ldg / 2), e = i - a * (ldg / 2);
         reinterpret_cast<double2*>(gn + (size_t)list[a] * ldg)[e] = reinterpret_cast<const double2*>(A)[i];
     }
+    JAC_TICK(1);
     mgs2_qr_dispatch<MAXV2>(B, ldl, r, r, C, ldl, nrm2, list2);         // B = Q2, C = columns of R2^T = L
+    JAC_TICK(2);
     int sweep = 0;
     for (; sweep < max_sweeps; ++sweep) {
         jacobi_active_list(C, ldl, r, nrm2, list2, sv_cutoff, s_nact, s_thr, s_rot);
@@ -544,6 +561,7 @@ __device__ __forceinline__ int jacobi_qr_problem(const double* __restrict__ g, i
         if (!rotated) { ++sweep; break; }
     }
     __syncthreads();
+    JAC_TICK(3);
     jacobi_active_list(C, ldl, r, nrm2, list2, sv_cutoff, s_nact, s_thr, s_rot);     // final norms
     const double thr_f = *s_thr;
     for (int i = tid; i < r; i += nthr) sigma[i] = sqrt(nrm2[i]);
@@ -581,6 +599,9 @@ __device__ __forceinline__ int jacobi_qr_problem(const double* __restrict__ g, i
         }
     }
     __syncthreads();
+    JAC_TICK(4);
+    JAC_COUNT(5, 1);
+    JAC_COUNT(6, sweep);
     return sweep;
 }
 

@@ -1423,6 +1423,17 @@ int xfb_debug_jacobi_sweeps(xfb_plan* p, int32_t* out_host, int32_t capacity, in
     return 0;
 }
 
+// diagnostics: phase cycle counters of the Jacobi kernel (zeros unless the library was built with -DJAC_TIMING); reset after reading
+int xfb_debug_jacobi_phase_cycles(double* out8_host) {
+    unsigned long long h[8] = {};
+    XFB_CUDA(cudaDeviceSynchronize());
+    XFB_CUDA(cudaMemcpyFromSymbol(h, g_jac_phase, sizeof(h)));
+    for (int i = 0; i < 8; ++i) out8_host[i] = (double)h[i];
+    unsigned long long z[8] = {};
+    XFB_CUDA(cudaMemcpyToSymbol(g_jac_phase, z, sizeof(z)));
+    return 0;
+}
+
 int xfb_plan_set_fused_ft_stab(xfb_plan* p, int32_t on) { p->fused_ft_stab = (on && p->dims == 3) ? 1 : 0; return 0; }
 
 // L2-resident phi-Fourier intermediate: runs per chunk (0 = one launch over the whole batch, the round-1
