@@ -145,32 +145,9 @@ __device__ __forceinline__ JBlockPair jacobi_block_pair(int i, int r, int nblkp)
     return bp;
 }
 
-// ---- "lazy" rotations (round 2) --------------------------------------------------------------------------------------------
-// Phase timing (tools/jacobi_phase_probe.py) puts a rotation step at ~1400 cycles, i.e. ~30 cycles per DEPENDENT FP64 operation of the
-// chain  dot -> shuffle reduce -> rotation parameters -> rotate -> shuffle, and the exact parameters (two dependent FP64 rsqrt
-// sequences) are more than half of those operations.  Any t gives an exactly orthonormal rotation
-//        x' = c (x - t y),  y' = c (y + t x),  c = 1 / sqrt(1 + t^2),
-// and an error of 1e-7 in t = tan(theta) only leaves 1e-7 of the pair's off-diagonal behind (the next sweep removes it: the
-// quadratic end game 1e-4 -> 1e-8 -> 1e-16 is not slowed down).  So:
-//   * t comes from a single-precision evaluation of |s2| / (|d| + sqrt(d^2 + s2^2)) on exponent-aligned inputs (MUFU.RSQ / MUFU.RCP,
-//     no FP64 special-function sequence on the chain);
-//   * the unnormalised pair (x - t y, y + t x) is formed right away (one FMA after t) and the next dot product starts from it; the
-//     common factor c follows off the critical path (FP64 rsqrt) as a PENDING scale of both columns, which the next step folds into
-//     its dot product as a scalar and into the columns in place while the reduction shuffles are in flight.
-// Squared norms are updated with the exact formula for the t actually used.
-__device__ __forceinline__ double jacobi_tan_approx(double d, double apq) {
-    const int ed = __double2hiint(d) & 0x7ff00000, ea = (__double2hiint(apq) & 0x7ff00000) + 0x00100000;     // s2 = 2 apq
-    const int e = max(ed, ea);
-    const double f = __hiloint2double(0x7fe00000 - e, 0);                 // 2^-(exponent of the larger operand): both land in [-2, 2]
-    const float df = __double2float_rn(d * f), sf = 2.0f * __double2float_rn(apq * f);
-    const float w = fmaf(df, df, sf * sf);
-    const float h = w * __frsqrt_rn(w);                                   // sqrt(d^2 + s2^2), w > 0 whenever the pair rotates
-    const float tt = __fdividef(fabsf(sf), fabsf(df) + h);
-    return (double)copysignf(tt, df * sf);
-}
-
-// Pass 1 of a block pair (one warp): load the 8 G columns, rotate the 16 cross pairs (and in round 0 the 6 + 6 pairs inside A and B)
-// in registers, store the columns, leave the rotation parameters in rb[JROT_STEPS][4] and rb[JROT_STEPS*4].x = 1 if anything rotated.
+// Pass 1 of a block pair (one warp): load the 8 G columns, rotate the 16 cross pairs (and in round 0 the 6 + 6 pairs
+// inside A and B) in registers, store the columns, leave the rotation parameters in rb[JROT_STEPS][4] and
+// rb[JROT_STEPS*4].x = 1 if anything rotated.
 template <int NV2>
 __device__ __forceinline__ void jacobi_g_pass(double* Gs, int ldg, const int* __restrict__ list, int nact, JBlockPair bp, bool intra,
                                               double thr, double tol, double2* rb, double* nrm2) {
@@ -181,107 +158,68 @@ __device__ __forceinline__ void jacobi_g_pass(double* Gs, int ldg, const int* __
     const int ca = va ? list[pa] : 0;
     const int pb0 = bb * 4 + grp, pb3 = bb * 4 + ((grp + 3) & 3);
     const bool vb0 = pb0 < nact, vb3 = pb3 < nact;
-    const double tol2 = tol * tol;
     bool any_rot = false;
     double2 x[NV2], y[NV2];
     jacobi_load_col<NV2>(x, Gs, (long long)ca * ldg, sub, va);
     jacobi_load_col<NV2>(y, Gs, (long long)(vb0 ? list[pb0] : 0) * ldg, sub, vb0);
-    // squared norms: computed once per sweep (jacobi_active_list), then carried in nrm2 [column] and updated by every rotation;
-    // they travel with the columns, and so do the pending scale factors px, py (true column = p * stored column)
+    // squared norms: computed once per sweep (jacobi_active_list), then carried in nrm2 [column] and updated by every
+    // rotation (|x'|^2 = |x|^2 - tan(theta) x.y), as LAPACK's one-sided Jacobi does; they travel with the columns
     const int cb0 = vb0 ? list[pb0] : 0;
     double nx = va ? nrm2[ca] : 0.0, ny = vb0 ? nrm2[cb0] : 0.0;
-    double px = 1.0, py = 1.0;
-    // one rotation of the pair (u, v) with squared norms (nu, nv) and pending factors (pu, pv): rotates BOTH columns when `both`
-    // (cross pairs: the group owns both), else only u (pairs inside a block: the partner group holds the mirrored pair and takes the
-    // bitwise mirrored decision -- the dot product, the exponent alignment and the float formula are symmetric under the exchange)
-    auto rotate = [&](double2 (&u)[NV2], double2 (&v)[NV2], double& nu, double& nv, double& pu, double& pv, bool valid, bool both, double2& out_cs) {
-        double apq = 0.0, apq2 = 0.0;
-#pragma unroll
-        for (int k = 0; k < NV2; ++k) { apq += u[k].x * v[k].x; apq2 += u[k].y * v[k].y; }
-        apq += apq2;
-        const double puv = pu * pv, nuv = nu * nv, d = nv - nu;            // off the chain: known before the dot product arrives
-        if (pu != 1.0) {                                                   // fold the pending factors into the columns (in flight with the reduction)
-#pragma unroll
-            for (int k = 0; k < NV2; ++k) { u[k].x *= pu; u[k].y *= pu; }
-        }
-        if (pv != 1.0) {
-#pragma unroll
-            for (int k = 0; k < NV2; ++k) { v[k].x *= pv; v[k].y *= pv; }
-        }
-        pu = 1.0; pv = 1.0;
-#pragma unroll
-        for (int off = JG / 2; off > 0; off >>= 1) apq += __shfl_xor_sync(0xffffffffu, apq, off);
-        apq *= puv;
-        const bool rot = valid && (nu > thr) && (nv > thr) && (apq * apq > tol2 * nuv);
-        out_cs = make_double2(1.0, 0.0);
-        if (rot) {
-            any_rot = true;
-            const double t = jacobi_tan_approx(d, apq);
-            if (both) {
-#pragma unroll
-                for (int k = 0; k < NV2; ++k) {
-                    const double2 a = u[k], b = v[k];
-                    u[k] = make_double2(fma(-t, b.x, a.x), fma(-t, b.y, a.y));
-                    v[k] = make_double2(fma(t, a.x, b.x), fma(t, a.y, b.y));
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < NV2; ++k) u[k] = make_double2(fma(-t, v[k].x, u[k].x), fma(-t, v[k].y, u[k].y));
-            }
-            // off the critical path: the common factor and the norms of the rotated columns
-            const double c2 = 1.0 / fma(t, t, 1.0), c = sqrt(c2), ta = 2.0 * t * apq, t2 = t * t;
-            const double nu_new = (nu - ta + t2 * nv) * c2, nv_new = (nv + ta + t2 * nu) * c2;
-            nu = nu_new; nv = nv_new;
-            pu = c; pv = c;
-            out_cs = make_double2(c, t * c);
-        }
-    };
     if (intra) {
 #pragma unroll
-        for (int t_ = 0; t_ < 3; ++t_) {                          // pairs inside A: partner group = grp ^ (t_+1)
-            const bool vp = (ba * 4 + (grp ^ (t_ + 1))) < nact;
+        for (int t = 0; t < 3; ++t) {                             // pairs inside A: partner group = grp ^ (t+1)
+            const bool vp = (ba * 4 + (grp ^ (t + 1))) < nact;
             double2 z[NV2];
 #pragma unroll
-            for (int k = 0; k < NV2; ++k) z[k] = shfl_d2(x[k], lane ^ (8 * (t_ + 1)));
-            double nz = __shfl_sync(0xffffffffu, nx, lane ^ (8 * (t_ + 1)));
-            double pz = __shfl_sync(0xffffffffu, px, lane ^ (8 * (t_ + 1)));
-            double2 cs;
-            rotate(x, z, nx, nz, px, pz, va && vp, false, cs);
-            if (sub == 0) rb[t_ * 4 + grp] = cs;
+            for (int k = 0; k < NV2; ++k) z[k] = shfl_d2(x[k], lane ^ (8 * (t + 1)));
+            const double nz = __shfl_sync(0xffffffffu, nx, lane ^ (8 * (t + 1)));
+            const JRot R = jacobi_pair_params<NV2>(x, z, nx, nz, va && vp, thr, tol);
+            if (R.sn != 0.0) {
+                any_rot = true;
+#pragma unroll
+                for (int k = 0; k < NV2; ++k) x[k] = make_double2(R.cs * x[k].x - R.sn * z[k].x, R.cs * x[k].y - R.sn * z[k].y);
+                nx -= R.tapq;
+            }
+            if (sub == 0) rb[t * 4 + grp] = make_double2(R.cs, R.sn);
         }
 #pragma unroll
-        for (int t_ = 0; t_ < 3; ++t_) {                          // pairs inside B
-            const bool vp = (bb * 4 + (grp ^ (t_ + 1))) < nact;
+        for (int t = 0; t < 3; ++t) {                             // pairs inside B
+            const bool vp = (bb * 4 + (grp ^ (t + 1))) < nact;
             double2 z[NV2];
 #pragma unroll
-            for (int k = 0; k < NV2; ++k) z[k] = shfl_d2(y[k], lane ^ (8 * (t_ + 1)));
-            double nz = __shfl_sync(0xffffffffu, ny, lane ^ (8 * (t_ + 1)));
-            double pz = __shfl_sync(0xffffffffu, py, lane ^ (8 * (t_ + 1)));
-            double2 cs;
-            rotate(y, z, ny, nz, py, pz, vb0 && vp, false, cs);
-            if (sub == 0) rb[(3 + t_) * 4 + grp] = cs;
+            for (int k = 0; k < NV2; ++k) z[k] = shfl_d2(y[k], lane ^ (8 * (t + 1)));
+            const double nz = __shfl_sync(0xffffffffu, ny, lane ^ (8 * (t + 1)));
+            const JRot R = jacobi_pair_params<NV2>(y, z, ny, nz, vb0 && vp, thr, tol);
+            if (R.sn != 0.0) {
+                any_rot = true;
+#pragma unroll
+                for (int k = 0; k < NV2; ++k) y[k] = make_double2(R.cs * y[k].x - R.sn * z[k].x, R.cs * y[k].y - R.sn * z[k].y);
+                ny -= R.tapq;
+            }
+            if (sub == 0) rb[(3 + t) * 4 + grp] = make_double2(R.cs, R.sn);
         }
     }
 #pragma unroll
-    for (int s_ = 0; s_ < 4; ++s_) {                               // cross pairs (A_g, B_(g+s)%4)
-        const bool vb = (bb * 4 + ((grp + s_) & 3)) < nact;
-        double2 cs;
-        rotate(x, y, nx, ny, px, py, va && vb, true, cs);
-        if (sub == 0) rb[(6 + s_) * 4 + grp] = cs;
-        if (s_ < 3) {
+    for (int s = 0; s < 4; ++s) {                                 // cross pairs (A_g, B_(g+s)%4)
+        const bool vb = (bb * 4 + ((grp + s) & 3)) < nact;
+        const JRot R = jacobi_pair_params<NV2>(x, y, nx, ny, va && vb, thr, tol);
+        if (R.sn != 0.0) {
+            any_rot = true;
+#pragma unroll
+            for (int k = 0; k < NV2; ++k) {
+                const double2 a = x[k], b = y[k];
+                x[k] = make_double2(R.cs * a.x - R.sn * b.x, R.cs * a.y - R.sn * b.y);
+                y[k] = make_double2(R.sn * a.x + R.cs * b.x, R.sn * a.y + R.cs * b.y);
+            }
+            nx -= R.tapq; ny += R.tapq;
+        }
+        if (sub == 0) rb[(6 + s) * 4 + grp] = make_double2(R.cs, R.sn);
+        if (s < 3) {
 #pragma unroll
             for (int k = 0; k < NV2; ++k) y[k] = shfl_d2(y[k], (lane + 8) & 31);       // B columns move to the previous group
             ny = __shfl_sync(0xffffffffu, ny, (lane + 8) & 31);
-            py = __shfl_sync(0xffffffffu, py, (lane + 8) & 31);
         }
-    }
-    if (px != 1.0) {
-#pragma unroll
-        for (int k = 0; k < NV2; ++k) { x[k].x *= px; x[k].y *= px; }
-    }
-    if (py != 1.0) {
-#pragma unroll
-        for (int k = 0; k < NV2; ++k) { y[k].x *= py; y[k].y *= py; }
     }
     jacobi_store_col<NV2>(x, Gs, (long long)ca * ldg, sub, va);
     const int cb3 = vb3 ? list[pb3] : 0;
@@ -465,15 +403,29 @@ __device__ __forceinline__ void mgs2_qr(double* A, int lda, int r, double* Rt, i
 #pragma unroll
             for (int t = 0; t < NV; ++t) { c += q[t].x * a[t].x; c2 += q[t].y * a[t].y; }
             c += c2;
+            // the task that holds the next pivot column also takes the FRESH squared norm of its columns in the same pass (second
+            // chain of FMAs, reduced by the same shuffle rounds): |a - c q|^2 = a.a - c^2 is then accurate to a few ulps whenever the
+            // projection removes less than half of the norm, and the fresh norm after the update (a second dot product and reduction
+            // on the critical path of every step) is only needed on the slow path
+            double aa = 0.0, aa2 = 0.0;
+            if (first) {
 #pragma unroll
-            for (int off = JG / 2; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+                for (int t = 0; t < NV; ++t) { aa += a[t].x * a[t].x; aa2 += a[t].y * a[t].y; }
+                aa += aa2;
+            }
+#pragma unroll
+            for (int off = JG / 2; off > 0; off >>= 1) {
+                c += __shfl_xor_sync(0xffffffffu, c, off);
+                if (first) aa += __shfl_xor_sync(0xffffffffu, aa, off);
+            }
 #pragma unroll
             for (int t = 0; t < NV; ++t) { a[t].x -= c * q[t].x; a[t].y -= c * q[t].y; }
             double c_tot = c;
-            double n2n = n2k - c * c;                      // |a - c q|^2 for a unit q
+            const double n2k_eff = first ? aa : n2k;
+            double n2n = n2k_eff - c * c;                  // |a - c q|^2 for a unit q
             // second pass only where the first one cancelled more than half of the squared norm (or the downdated norm
             // has lost its digits); decided per warp, a superfluous second pass is harmless
-            const bool slow = __any_sync(0xffffffffu, v && (c * c > 0.5 * n2k || n2n < 1e-6 * n2ref));
+            const bool slow = __any_sync(0xffffffffu, v && (c * c > 0.5 * n2k_eff || (!first && n2n < 1e-6 * n2ref)));
             if (slow) {
                 c = 0.0; c2 = 0.0;
 #pragma unroll
@@ -485,7 +437,7 @@ __device__ __forceinline__ void mgs2_qr(double* A, int lda, int r, double* Rt, i
                 for (int t = 0; t < NV; ++t) { a[t].x -= c * q[t].x; a[t].y -= c * q[t].y; }
                 c_tot += c;
             }
-            const bool fresh = slow || first;
+            const bool fresh = slow;
             if (fresh) n2n = jacobi_col_norm2<NV>(a);
             if (first && grp == 0) {                       // the first trailing column becomes q_{j+1} right away
                 const double inv = (n2n > 0.0) ? rsqrt(n2n) : 0.0, nrm = n2n * inv;     // one MUFU + Newton instead of sqrt and a division
@@ -497,7 +449,7 @@ __device__ __forceinline__ void mgs2_qr(double* A, int lda, int r, double* Rt, i
             if (v && sub == 0) {
                 Rt[(size_t)j * ldr + k] = c_tot;
                 n2c[k] = n2n;
-                if (fresh) nref[k] = __double2hiint(n2n);
+                if (fresh || first) nref[k] = __double2hiint(n2n);
             }
         }
     }
