@@ -88,15 +88,10 @@ def mgs2(A, selective=True):
             break
         t = slice(j + 1, r)
         c = q @ A[:, t]
-        nf = min(4, r - j - 1)                             # the warp task that holds the next pivot column: fresh a.a in the same pass
-        n2_eff = n2[t].copy()
-        n2_eff[:nf] = (A[:, j + 1:j + 1 + nf] * A[:, j + 1:j + 1 + nf]).sum(0)
         A[:, t] -= np.outer(q, c)
         R[j, t] += c
-        n2n = n2_eff - c * c
-        first = np.zeros(r - j - 1, bool)
-        first[:nf] = True
-        need = (c * c > 0.5 * n2_eff) | ((n2n < 1e-6 * nref[t]) & ~first) if selective else np.ones(r - j - 1, bool)
+        n2n = n2[t] - c * c
+        need = (c * c > 0.5 * n2[t]) | (n2n < 1e-6 * nref[t]) if selective else np.ones(r - j - 1, bool)
         for k0 in range(0, r - j - 1, 4):                  # warp granularity
             if need[k0:k0 + 4].any():
                 need[k0:k0 + 4] = True
@@ -106,9 +101,9 @@ def mgs2(A, selective=True):
             A[:, idx] -= np.outer(q, c2)
             R[j, idx] += c2
         n2[t] = n2n
-        n2[idx] = (A[:, idx] * A[:, idx]).sum(0)           # fresh norms only on the slow path
-        nref[idx] = n2[idx]
-        nref[j + 1:j + 1 + nf] = n2[j + 1:j + 1 + nf]
+        fresh = np.union1d(idx, np.arange(j + 1, min(r, j + 5)))
+        n2[fresh] = (A[:, fresh] * A[:, fresh]).sum(0)
+        nref[fresh] = n2[fresh]
     return Q, R
 
 

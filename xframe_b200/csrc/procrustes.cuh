@@ -403,29 +403,15 @@ __device__ __forceinline__ void mgs2_qr(double* A, int lda, int r, double* Rt, i
 #pragma unroll
             for (int t = 0; t < NV; ++t) { c += q[t].x * a[t].x; c2 += q[t].y * a[t].y; }
             c += c2;
-            // the task that holds the next pivot column also takes the FRESH squared norm of its columns in the same pass (second
-            // chain of FMAs, reduced by the same shuffle rounds): |a - c q|^2 = a.a - c^2 is then accurate to a few ulps whenever the
-            // projection removes less than half of the norm, and the fresh norm after the update (a second dot product and reduction
-            // on the critical path of every step) is only needed on the slow path
-            double aa = 0.0, aa2 = 0.0;
-            if (first) {
 #pragma unroll
-                for (int t = 0; t < NV; ++t) { aa += a[t].x * a[t].x; aa2 += a[t].y * a[t].y; }
-                aa += aa2;
-            }
-#pragma unroll
-            for (int off = JG / 2; off > 0; off >>= 1) {
-                c += __shfl_xor_sync(0xffffffffu, c, off);
-                if (first) aa += __shfl_xor_sync(0xffffffffu, aa, off);
-            }
+            for (int off = JG / 2; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
 #pragma unroll
             for (int t = 0; t < NV; ++t) { a[t].x -= c * q[t].x; a[t].y -= c * q[t].y; }
             double c_tot = c;
-            const double n2k_eff = first ? aa : n2k;
-            double n2n = n2k_eff - c * c;                  // |a - c q|^2 for a unit q
+            double n2n = n2k - c * c;                      // |a - c q|^2 for a unit q
             // second pass only where the first one cancelled more than half of the squared norm (or the downdated norm
             // has lost its digits); decided per warp, a superfluous second pass is harmless
-            const bool slow = __any_sync(0xffffffffu, v && (c * c > 0.5 * n2k_eff || (!first && n2n < 1e-6 * n2ref)));
+            const bool slow = __any_sync(0xffffffffu, v && (c * c > 0.5 * n2k || n2n < 1e-6 * n2ref));
             if (slow) {
                 c = 0.0; c2 = 0.0;
 #pragma unroll
@@ -437,7 +423,7 @@ __device__ __forceinline__ void mgs2_qr(double* A, int lda, int r, double* Rt, i
                 for (int t = 0; t < NV; ++t) { a[t].x -= c * q[t].x; a[t].y -= c * q[t].y; }
                 c_tot += c;
             }
-            const bool fresh = slow;
+            const bool fresh = slow || first;
             if (fresh) n2n = jacobi_col_norm2<NV>(a);
             if (first && grp == 0) {                       // the first trailing column becomes q_{j+1} right away
                 const double inv = (n2n > 0.0) ? rsqrt(n2n) : 0.0, nrm = n2n * inv;     // one MUFU + Newton instead of sqrt and a division
@@ -449,7 +435,7 @@ __device__ __forceinline__ void mgs2_qr(double* A, int lda, int r, double* Rt, i
             if (v && sub == 0) {
                 Rt[(size_t)j * ldr + k] = c_tot;
                 n2c[k] = n2n;
-                if (fresh || first) nref[k] = __double2hiint(n2n);
+                if (fresh) nref[k] = __double2hiint(n2n);
             }
         }
     }
