@@ -610,29 +610,57 @@ static int sht_inverse_i(xfb_plan* p, const double2* c_in, double2* grid_out, in
                               mod_out)) return 1);
     return 0;
 }
-static int hankel_i(xfb_plan* p, int dir, const double2* c_in, double2* c_out, int nb, cudaStream_t st) {
-    auto hit = p->hk_cache.find(nb);
-    if (hit == p->hk_cache.end()) {
-        std::vector<HankelTile> tiles;
-        if (p->dims == 2) {
-            // one weight matrix per DFT index j; order m = j (j <= M) or j - N: (-i)^m = (-i)^(m mod 4)
-            for (int j = 0; j < p->n_phi; ++j) {
-                const int m = (j <= p->L) ? j : j - p->n_phi;
-                const int r0 = j * nb, r1 = (j + 1) * nb;
-                for (int r = r0; r < r1; r += HK_BM) tiles.push_back(HankelTile{j, r, r1, ((m % 4) + 4) % 4});
-            }
-        } else {
-            for (int l = p->L; l >= 0; --l) {   // largest orders first
-                const int r0 = l * l * nb, r1 = (l + 1) * (l + 1) * nb;
-                for (int r = r0; r < r1; r += HK_BM) tiles.push_back(HankelTile{l, r, r1, l & 3});
-            }
-        }
-        HankelTile* dev = nullptr;
-        XFB_CUDA(cudaMalloc((void**)&dev, tiles.size() * sizeof(HankelTile)));
-        XFB_CUDA(cudaMemcpyAsync(dev, tiles.data(), tiles.size() * sizeof(HankelTile), cudaMemcpyHostToDevice, st));
-        XFB_CUDA(cudaStreamSynchronize(st));
-        hit = p->hk_cache.emplace(nb, std::make_pair(dev, (int)tiles.size())).first;
+// chunk schedule of the host pipeline (xfb_mtip_step_host): chunks of host_chunk runs for large batches, nb/8 (>= 4: below that the
+// kernels are latency bound) for small ones, so that a shard of 16 or 32 runs (the per-GPU share of 128 runs on 8 / 4 GPUs) is
+// pipelined as well; full chunks in the middle, tapered at both ends (1/4, 1/2) so that the exposed first copy-in and last
+// copy-out of the three-stage pipeline (copy-in | iterate | copy-out) are short
+static std::vector<int> host_chunk_sizes(const xfb_plan* p, int nb, int ft_stab) {
+    int chunk = p->host_chunk;
+    while (chunk > 4 && chunk * 8 > nb) chunk /= 2;
+    const bool pipelined = (!ft_stab || p->fused_ft_stab) && nb > chunk;   // W2 is free as H2D staging then
+    std::vector<int> sizes;
+    if (!pipelined) { sizes.push_back(nb); return sizes; }
+    const int cs = chunk;
+    std::vector<int> head, tail;
+    int left = nb;
+    for (int f = 4; f >= 2 && left > 4 * cs; f /= 2) {
+        const int h = std::max(1, cs / f);
+        head.push_back(h); tail.insert(tail.begin(), h); left -= 2 * h;
     }
+    sizes = head;
+    while (left > 0) { const int n = std::min(cs, left); sizes.push_back(n); left -= n; }
+    sizes.insert(sizes.end(), tail.begin(), tail.end());
+    return sizes;
+}
+
+// tile list of the Hankel GEMM for a batch of nb runs (cached per batch size; the first use of a size allocates, uploads and
+// synchronises -- xfb_mtip_init does that ahead for the batch and for the chunk sizes of the host pipeline)
+static int hankel_tiles_i(xfb_plan* p, int nb, cudaStream_t st) {
+    if (p->hk_cache.find(nb) != p->hk_cache.end()) return 0;
+    std::vector<HankelTile> tiles;
+    if (p->dims == 2) {
+        // one weight matrix per DFT index j; order m = j (j <= M) or j - N: (-i)^m = (-i)^(m mod 4)
+        for (int j = 0; j < p->n_phi; ++j) {
+            const int m = (j <= p->L) ? j : j - p->n_phi;
+            const int r0 = j * nb, r1 = (j + 1) * nb;
+            for (int r = r0; r < r1; r += HK_BM) tiles.push_back(HankelTile{j, r, r1, ((m % 4) + 4) % 4});
+        }
+    } else {
+        for (int l = p->L; l >= 0; --l) {   // largest orders first
+            const int r0 = l * l * nb, r1 = (l + 1) * (l + 1) * nb;
+            for (int r = r0; r < r1; r += HK_BM) tiles.push_back(HankelTile{l, r, r1, l & 3});
+        }
+    }
+    HankelTile* dev = nullptr;
+    XFB_CUDA(cudaMalloc((void**)&dev, tiles.size() * sizeof(HankelTile)));
+    XFB_CUDA(cudaMemcpyAsync(dev, tiles.data(), tiles.size() * sizeof(HankelTile), cudaMemcpyHostToDevice, st));
+    XFB_CUDA(cudaStreamSynchronize(st));
+    p->hk_cache.emplace(nb, std::make_pair(dev, (int)tiles.size()));
+    return 0;
+}
+static int hankel_i(xfb_plan* p, int dir, const double2* c_in, double2* c_out, int nb, cudaStream_t st) {
+    if (hankel_tiles_i(p, nb, st)) return 1;
+    auto hit = p->hk_cache.find(nb);
     p->hk_tiles = hit->second.first; p->hk_tiles_n = hit->second.second;
     dim3 g(p->hk_tiles_n, cdiv(p->n_r, HK_BN));
     if (p->hankel_tma && p->n_r % HK_BN == 0 && p->hankel_n_sum % HK_BK == 0) {
@@ -1254,6 +1282,11 @@ int xfb_mtip_init(xfb_plan* p, const double* rho0, int32_t nb, void* stream) {
     if (nb < 1 || nb > p->max_batch) XFB_FAIL("n_batch=%d outside plan capacity", nb);
     if (!p->has_proj || !p->has_real) XFB_FAIL("plan needs projection and real options before xfb_mtip_init");
     if (ensure_loop_alloc(p) || ensure_reduce_alloc(p)) return 1;
+    // everything that allocates or synchronises on the first use of a batch size happens here, not inside an iteration: tile lists
+    // of the Hankel GEMM for the batch and for the chunk sizes of the host pipeline, descriptors of the grouped GEMMs
+    if (hankel_tiles_i(p, nb, st)) return 1;
+    for (int n : host_chunk_sizes(p, nb, 1)) if (hankel_tiles_i(p, n, st)) return 1;
+    if (p->dims == 3 && !p->orders.empty() && build_gemm_groups(p, nb, st)) return 1;
     p->n_batch = nb; p->it_done = 0;
     const int B = p->max_batch, tb = 128, gb = cdiv(B, tb);
     auto fill_i = [&](int* q, int v) { fill_i32_kernel<<<gb, tb, 0, st>>>(q, v, B); p->launches++; };
@@ -1531,33 +1564,13 @@ int xfb_mtip_step_host(xfb_plan* p, int32_t method, int32_t ft_stab, double beta
     const int nb = p->n_batch;
     if (nb < 1) XFB_FAIL("xfb_mtip_init has not been called");
     const int eb = ew_blocks(p->G);
-    // chunk size: host_chunk runs for large batches, nb/8 (>= 4: below that the kernels are latency bound) for small
-    // ones, so that a shard of 16 or 32 runs (the per-GPU share of 128 runs on 8 / 4 GPUs) is pipelined as well
-    int chunk = p->host_chunk;
-    while (chunk > 4 && chunk * 8 > nb) chunk /= 2;
-    const bool pipelined = (!ft_stab || p->fused_ft_stab) && nb > chunk;   // W2 is free as H2D staging then
     if (!p->s_in) {
         XFB_CUDA(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
         XFB_CUDA(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
         XFB_CUDA(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
         if (dev_alloc(p, &p->stage_out, (size_t)p->max_batch * p->G)) return 1;
     }
-    // chunk schedule: full chunks of host_chunk runs in the middle, tapered at both ends (1/4, 1/2) so that the exposed
-    // first copy-in and last copy-out of the three-stage pipeline (copy-in | iterate | copy-out) are short
-    std::vector<int> sizes;
-    if (!pipelined) sizes.push_back(nb);
-    else {
-        const int cs = chunk;
-        std::vector<int> head, tail;
-        int left = nb;
-        for (int f = 4; f >= 2 && left > 4 * cs; f /= 2) {
-            const int h = std::max(1, cs / f);
-            head.push_back(h); tail.insert(tail.begin(), h); left -= 2 * h;
-        }
-        sizes = head;
-        while (left > 0) { const int n = std::min(cs, left); sizes.push_back(n); left -= n; }
-        sizes.insert(sizes.end(), tail.begin(), tail.end());
-    }
+    const std::vector<int> sizes = host_chunk_sizes(p, nb, ft_stab);
     const int nchunk = (int)sizes.size();
     std::vector<int> first(nchunk, 0);
     for (int c = 1; c < nchunk; ++c) first[c] = first[c - 1] + sizes[c - 1];
