@@ -66,3 +66,34 @@ def test_no_cpu_fallback():
         sh(7, mode_flag='real')
     ht = HarmonicTransform('complex', {'dimensions': 3, 'max_order': 7})
     assert set(ht.transforms_by_indices) == {'lm', 'ml', 'direct'} and ht.grid_param['thetas'].shape == (8,)
+
+
+def test_result_record_round_trip(tmp_path):
+    """results_io: the record of post_processing (reconstruct.py:160-183) written with the nested-dict rules of the reference's HDF5 saver
+    (hdf5_plugin.py:53-131; .npz carrier here, h5py is absent from the image) and read back unchanged."""
+    import numpy as np
+    from xframe_b200 import results_io as RIO
+    rng = np.random.default_rng(0)
+    shape = (4, 8, 16)
+    res = {str(i): {'real_density': rng.standard_normal(shape) + 1j * rng.standard_normal(shape), 'support_mask': rng.random(shape) > 0.5,
+                    'final_error': float(i) * 0.1, 'loop_iterations': np.int64(7),
+                    'error_dict': {'main': rng.random(5), 'real': {'l2_projection_diff': rng.random(5)}, 'reciprocal': {}},
+                    'fxs_unknowns': tuple(rng.standard_normal((min(2 * l + 1, 4), 2 * l + 1)) + 0j for l in range(3)),
+                    'n_particles_gradients': np.array([])} for i in (1, 0)}
+    record = {'configuration': {'internal_grid': {'real_grid': rng.random(shape + (3,)), 'reciprocal_grid': rng.random(shape + (3,))},
+                                'xray_wavelength': 1.23984, 'reciprocity_coefficient': 2.0},
+              'reconstruction_results': res, 'projection_matrices': [rng.standard_normal((4, min(2 * l + 1, 4))) + 0j for l in range(3)],
+              'stats': {'run_time': 1.5, 'structure_name': 'tutorial'}}
+    path = RIO.save_reconstructions(record, str(tmp_path / 'run_0'))
+    back = RIO.load_reconstructions(path)
+
+    def same(a, b):
+        if isinstance(a, dict):
+            return isinstance(b, dict) and list(a) == list(b) and all(same(a[k], b[k]) for k in a)
+        if isinstance(a, (list, tuple)):
+            return type(a) is type(b) and len(a) == len(b) and all(same(x, y) for x, y in zip(a, b))
+        if isinstance(a, str):
+            return a == b
+        return np.array_equal(np.asarray(a), np.asarray(b)) and np.asarray(a).dtype == np.asarray(b).dtype
+    assert list(back['reconstruction_results']) == ['1', '0']            # ranking order is kept
+    assert same(record, back)
