@@ -66,6 +66,12 @@ __global__ void mul_gauss_kernel(double2* __restrict__ data, const double* __res
     }
 }
 
+// Scalars of one iteration that change from step to step (HIO beta, error-history column, sub-loop iteration).  When an iteration is
+// replayed from a CUDA graph they are read from device memory (written by iter_params_kernel right before the graph launch) instead of
+// being kernel arguments frozen at capture time.
+struct IterParams { double beta; int it; int outer; int pad; };
+__global__ void iter_params_kernel(IterParams* ip, double beta, int it, int outer) { ip->beta = beta; ip->it = it; ip->outer = outer; ip->pad = 0; }
+
 struct RealDesc {
     int n_ops;
     int ops[4];          // 1 support, 2 value_threshold, 3 limit_imag, 4 average_center
@@ -123,7 +129,9 @@ __global__ void __launch_bounds__(RU_THREADS, RU_MINB) real_update_kernel(const 
                                                                  const int* __restrict__ enforce, const uint8_t* __restrict__ init_support,
                                                                  const double* __restrict__ wt, RealDesc rd, int method, double beta,
                                                                  int n_theta, int n_phi, int wt_div, long long per_run, double* __restrict__ partial,
-                                                                 const double2* __restrict__ rt0, const double2* __restrict__ avg_mean) {
+                                                                 const double2* __restrict__ rt0, const double2* __restrict__ avg_mean,
+                                                                 const IterParams* __restrict__ ip) {
+    if (ip) beta = ip->beta;
     const int b = blockIdx.y;
     const double2* ri = rho_ift + (long long)b * per_run;
     const double2* rt = rho_rt ? rho_rt + (long long)b * per_run : nullptr;
@@ -336,9 +344,10 @@ __device__ __forceinline__ int free_slot(int a, int b) {   // smallest slot in {
     for (int s = 0; s < 3; ++s) if (s != a && s != b) return s;
     return 0;
 }
-__global__ void loop_update_kernel(LoopState st, const double* __restrict__ err, int it, int n_batch, int outer_it) {
+__global__ void loop_update_kernel(LoopState st, const double* __restrict__ err, int it, int n_batch, int outer_it, const IterParams* __restrict__ ip) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_batch) return;
+    if (ip) { it = ip->it; outer_it = ip->outer; }
     const double num = err[b * 2], den = err[b * 2 + 1];
     const double e = (den != 0.0) ? num / den : INFINITY;
     if (it < st.hist_cap) st.hist[(long long)b * st.hist_cap + it] = e;

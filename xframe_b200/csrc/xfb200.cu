@@ -107,6 +107,10 @@ struct xfb_plan {
     int dual = 0, dual_min = 32, dual_big_sms = 50, dual_small_sms = 20; bool dual_active = false;
     cudaStream_t s_half = nullptr; cudaEvent_t ev_hfork = nullptr, ev_hjoin = nullptr, ev_stagger = nullptr; cudaEvent_t stagger_pending = nullptr;
     cudaEvent_t jac_fork[2] = {}, jac_join[2] = {};
+    // CUDA graph of one whole iteration per (method, ft_stab, non-FXS, batch): captured on the second call of a kind (the first runs
+    // eagerly and warms every lazily built table), replayed afterwards with the step's scalars in device memory (IterParams)
+    int use_graph = 1; IterParams* iter_params = nullptr; const IterParams* ip_active = nullptr;
+    std::map<int, cudaGraphExec_t> graphs; std::map<int, int> graph_warm, graph_launches; bool graph_broken = false;
     int run_base = 0, ctx = 0;                      // scratch of the current enqueue starts at this run; stream / event set in use
     int n_batch = 0, it_done = 0, outer_it = 0; bool non_fxs = false; double *fix_int = nullptr, *fix_cand = nullptr; double *partial = nullptr, *err = nullptr, *mm = nullptr; int red_blocks = 0;
     bool loop_alloc = false;
@@ -175,6 +179,12 @@ struct ScratchShift {
     ~ScratchShift() { p->run_base -= b0; apply(-1); }
 };
 
+
+// captured iterations bake the plan's constants (projection, real-space options, switches) into their kernel arguments
+static void graphs_invalidate(xfb_plan* p) {
+    for (auto& kv : p->graphs) cudaGraphExecDestroy(kv.second);
+    p->graphs.clear(); p->graph_warm.clear(); p->graph_launches.clear();
+}
 
 extern "C" {
 
@@ -292,6 +302,7 @@ int xfb_plan_create(xfb_plan** out, const xfb_plan_desc* d) {
     if (const char* e = getenv("XFB_SHT_STREAMS")) p->sht_streams = std::min(4, std::max(1, atoi(e)));
     if (const char* e = getenv("XFB_LEG_MINGROUPS")) p->leg_min_groups = std::max(0, atoi(e));
     if (const char* e = getenv("XFB_HANKEL_TMA")) p->hankel_tma = atoi(e) != 0;
+    if (const char* e = getenv("XFB_GRAPH")) p->use_graph = atoi(e) != 0;
     if (const char* e = getenv("XFB_DUAL")) p->dual = atoi(e) != 0;
     if (const char* e = getenv("XFB_DUAL_BIG")) p->dual_big_sms = std::max(1, atoi(e));
     if (const char* e = getenv("XFB_DUAL_SMALL")) p->dual_small_sms = std::max(1, atoi(e));
@@ -320,6 +331,8 @@ int xfb_plan_destroy(xfb_plan* p) {
     for (auto& kv : p->hk_cache) cudaFree(kv.second.first);
     for (auto& kv : p->dft_tiles) cudaFree(kv.second.first);
     for (auto& kv : p->dft_fold_tiles) cudaFree(kv.second.first);
+    for (auto& kv : p->graphs) cudaGraphExecDestroy(kv.second);
+    if (p->iter_params) cudaFree(p->iter_params);
     for (auto& e : p->prof_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto e : p->ev_in) cudaEventDestroy(e);
     for (auto e : p->ev_comp) cudaEventDestroy(e);
@@ -932,7 +945,7 @@ static int real_update_i(xfb_plan* p, int method, double beta, const double2* rh
     XFB_LAUNCH(p, PG_REAL_UPDATE, st,
                real_update_kernel<<<dim3(bpr, nb), RU_THREADS, 0, st>>>(rho_ift, rho_rt, prev, next, support, support_slot, support_slot_stride,
                                                                         enforce, p->init_support_dev, p->int_wt, p->rd, method, beta,
-                                                                        p->n_theta, p->n_phi, p->wt_div, p->G, p->partial, rt0, has_avg ? p->avg_mean : nullptr));
+                                                                        p->n_theta, p->n_phi, p->wt_div, p->G, p->partial, rt0, has_avg ? p->avg_mean : nullptr, p->ip_active));
     XFB_LAUNCH(p, PG_MISC, st, reduce_pairs_kernel<<<nb, 32, 0, st>>>(p->partial, bpr, err_out));
     return 0;
 }
@@ -972,6 +985,7 @@ static void projection_release(xfb_plan* p) {
 
 int xfb_plan_set_projection(xfb_plan* p, const xfb_projection_desc* d) {
     if (!p || !d) XFB_FAIL("null argument");
+    graphs_invalidate(p);
     if (p->has_proj) projection_release(p);
     if (p->dims != 3) XFB_FAIL("xfb_plan_set_projection is the 3-D setter; use xfb_plan_set_projection_2d");
     const int L = p->L, n_r = p->n_r;
@@ -1113,6 +1127,7 @@ int xfb_get_unknowns_2d(xfb_plan* p, int32_t run, double* out_dev, void* stream)
 int xfb_plan_set_real(xfb_plan* p, const xfb_real_desc* d, const uint8_t* init_support_host) {
     if (!p || !d || !init_support_host) XFB_FAIL("null argument");
     if (d->n_ops < 0 || d->n_ops > 4) XFB_FAIL("n_ops out of range");
+    graphs_invalidate(p);
     p->rd.n_ops = d->n_ops;
     for (int i = 0; i < 4; ++i) { p->rd.ops[i] = d->ops[i]; p->rd.considered[i] = d->hio_considered[i]; }
     p->rd.use_lo = d->use_lo; p->rd.use_hi = d->use_hi; p->rd.lo = d->lo; p->rd.hi = d->hi; p->rd.imag_limit = d->imag_limit;
@@ -1210,6 +1225,7 @@ int xfb_get_unknowns(xfb_plan* p, int32_t run, int32_t order, double* out_dev, v
 int xfb_plan_set_deg2_reference(xfb_plan* p, const double* bref_host, const double* norm_host) {
     if (!p || !bref_host || !norm_host) XFB_FAIL("null argument");
     if (p->dims != 3) XFB_FAIL("xfb_plan_set_deg2_reference: 3-D plans only");
+    graphs_invalidate(p);
     if (!p->has_proj) XFB_FAIL("set the projection constants first (the radial mask is shared)");
     const size_t n = (size_t)(p->L + 1) * p->n_r * p->n_r;
     if (!p->d2_ref) { if (dev_alloc(p, &p->d2_ref, n)) return 1; if (dev_alloc(p, &p->d2_norm, (size_t)p->L + 1)) return 1; }
@@ -1386,7 +1402,7 @@ static int iterate_range(xfb_plan* p, int b0, int nb, int method, int ft_stab, d
                           pv(p->rho_pool, p->ls.rho_next), mask, ls.mask_cur, pool_stride, ls.enforce_cur, err, nb, st)) return 1;
     }
     // 7. bookkeeping                                         (:924-939)
-    XFB_LAUNCH(p, PG_MISC, st, loop_update_kernel<<<cdiv(nb, 128), 128, 0, st>>>(ls, err, it_index, nb, p->outer_it));
+    XFB_LAUNCH(p, PG_MISC, st, loop_update_kernel<<<cdiv(nb, 128), 128, 0, st>>>(ls, err, it_index, nb, p->outer_it, p->ip_active));
     return 0;
 }
 
@@ -1399,8 +1415,46 @@ int xfb_mtip_iterate(xfb_plan* p, int32_t method, int32_t ft_stab, int32_t n_ite
     // kernels of the other half.  The runs are independent and every run's arithmetic is unchanged (bit-identical results).
     const bool dual = p->dual && p->dims == 3 && !p->jacobi_big && nb >= p->dual_min && n_iter > 0 && (!ft_stab || p->fused_ft_stab) && !p->sht_chunk;
     if (!dual) {
+        // graph replay needs: no per-launch profiling events, no host-side history offsets (deg2 metric), a 3-D plan
+        const bool graphable = p->use_graph && !p->graph_broken && !p->prof && !p->d2_metric && p->dims == 3 && !p->sht_chunk;
+        const int key = (method & 1) | ((ft_stab & 1) << 1) | ((p->non_fxs ? 1 : 0) << 2) | (nb << 3);
         for (int it = 0; it < n_iter; ++it) {
-            if (iterate_range(p, 0, nb, method, ft_stab, betas ? betas[it] : 0.0, p->it_done, st)) return 1;
+            const double beta = betas ? betas[it] : 0.0;
+            auto g = graphable ? p->graphs.find(key) : p->graphs.end();
+            if (graphable && g == p->graphs.end() && p->graph_warm[key] > 0) {
+                // second iteration of this kind: capture it (nothing executes during the capture), instantiate, then replay
+                if (!p->iter_params) { if (dev_alloc(p, &p->iter_params, 1)) return 1; }
+                const int64_t l0 = p->launches;
+                p->ip_active = p->iter_params;
+                cudaGraph_t graph = nullptr;
+                cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+                int rc = 1;
+                if (e == cudaSuccess) {
+                    rc = iterate_range(p, 0, nb, method, ft_stab, beta, p->it_done, st);
+                    e = cudaStreamEndCapture(st, &graph);
+                }
+                p->ip_active = nullptr;
+                cudaGraphExec_t exec = nullptr;
+                if (rc == 0 && e == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                    p->graph_launches[key] = (int)(p->launches - l0);
+                    p->launches = l0;
+                    g = p->graphs.emplace(key, exec).first;
+                } else {
+                    cudaGetLastError();                   // capture not possible here: stay on the eager path for good
+                    p->graph_broken = true;
+                    p->launches = l0;
+                }
+                if (graph) cudaGraphDestroy(graph);
+            }
+            if (graphable && !p->graph_broken && g != p->graphs.end()) {
+                iter_params_kernel<<<1, 1, 0, st>>>(p->iter_params, beta, p->it_done, p->outer_it);
+                XFB_CUDA(cudaGraphLaunch(g->second, st));
+                p->launches += p->graph_launches[key] + 1;
+                p->proj_calls++;                          // host bookkeeping of the replayed projection (cache stamp of xfb_get_unknowns)
+            } else {
+                if (iterate_range(p, 0, nb, method, ft_stab, beta, p->it_done, st)) return 1;
+                p->graph_warm[key]++;
+            }
             p->it_done++;
         }
         return 0;
@@ -1467,13 +1521,14 @@ int xfb_debug_jacobi_phase_cycles(double* out8_host) {
     return 0;
 }
 
-int xfb_plan_set_fused_ft_stab(xfb_plan* p, int32_t on) { p->fused_ft_stab = (on && p->dims == 3) ? 1 : 0; return 0; }
+int xfb_plan_set_fused_ft_stab(xfb_plan* p, int32_t on) { graphs_invalidate(p); p->fused_ft_stab = (on && p->dims == 3) ? 1 : 0; return 0; }
 
 // L2-resident phi-Fourier intermediate: runs per chunk (0 = one launch over the whole batch, the round-1
 // behaviour) and number of streams the chunks are spread over (1 .. 4).
 int xfb_plan_set_sht_chunk(xfb_plan* p, int32_t runs_per_chunk, int32_t streams) {
     if (!p) XFB_FAIL("null plan");
     if (runs_per_chunk < 0 || streams < 1 || streams > 4) XFB_FAIL("sht chunk: runs_per_chunk >= 0 and 1 <= streams <= 4");
+    graphs_invalidate(p);
     p->sht_chunk = runs_per_chunk; p->sht_streams = streams;
     return 0;
 }

@@ -48,13 +48,15 @@ def gather_results(local, n_runs, device=None, chunk_bytes=1 << 30):
                 part = ids[k0:k0 + step]
                 if r == 0:
                     if rank == 0:
-                        full[torch.as_tensor(part)] = t[k0:k0 + len(part)].cpu()
+                        for j, i in enumerate(part):           # straight into the run's (contiguous) row of the host result
+                            full[i].copy_(t[k0 + j])
                 elif rank == r:
                     dist.send(t[k0:k0 + len(part)].contiguous(), dst=0)
                 elif rank == 0:
                     buf = torch.empty((len(part),) + tail, dtype=t.dtype, device=t.device)
                     dist.recv(buf, src=r)
-                    full[torch.as_tensor(part)] = buf.cpu()
+                    for j, i in enumerate(part):
+                        full[i].copy_(buf[j])
         if rank == 0:
             if is_cplx:
                 full = torch.view_as_complex(full)
