@@ -184,6 +184,7 @@ int xfb_mtip_get_grid(xfb_plan* p, int32_t which, void* out_dev, void* stream);
 int xfb_mtip_get_errors(xfb_plan* p, double* hist_dev, int32_t hist_capacity, double* best_dev, int32_t* n_done_host, void* stream);
 /* counts kernels launched through this plan since creation (bench.py gpu_launches) */
 int64_t xfb_plan_launch_count(const xfb_plan* p);
+int64_t xfb_plan_graph_replays(const xfb_plan* p);   /* iterations replayed from a captured CUDA graph (diagnostics) */
 /* elapsed ms of the dominant kernel group between reset and now, measured with CUDA events on `stream` */
 int xfb_profile_enable(xfb_plan* p, int32_t on);
 int xfb_profile_read(xfb_plan* p, int32_t n_max, char* names /*n_max*32*/, double* ms, int64_t* launches, int32_t* n_out);

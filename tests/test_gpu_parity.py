@@ -659,6 +659,7 @@ def test_graph_replay_gives_the_same_bits(monkeypatch):
         plan.mtip_iterate(HIO, False, [0.3, 0.3, 0.3])
         unk = plan.unknowns(1)
         launches = plan.launch_count()
+        assert plan.graph_replays() == (0 if graph == '0' else 4 + 3 + 2)      # per kind of iteration: the first runs eagerly, the others are replays
         out.append((N(plan.mtip_grid('last_real')), N(plan.mtip_grid('best_real')), N(plan.mtip_errors()[0]), N(plan.mtip_errors()[1]),
                     N(plan.mtip_grid('best_support')), unk, launches))
         plan.close()

@@ -109,8 +109,9 @@ struct xfb_plan {
     cudaEvent_t jac_fork[2] = {}, jac_join[2] = {};
     // CUDA graph of one whole iteration per (method, ft_stab, non-FXS, batch): captured on the second call of a kind (the first runs
     // eagerly and warms every lazily built table), replayed afterwards with the step's scalars in device memory (IterParams)
-    int use_graph = 1; IterParams* iter_params = nullptr; const IterParams* ip_active = nullptr;
+    int use_graph = 1; long long graph_replays = 0; IterParams* iter_params = nullptr; const IterParams* ip_active = nullptr;
     std::map<int, cudaGraphExec_t> graphs; std::map<int, int> graph_warm, graph_launches; bool graph_broken = false;
+    cudaStream_t s_graph = nullptr; cudaEvent_t ev_gfork = nullptr, ev_gjoin = nullptr;      // the caller's stream may be the legacy default stream, which cannot be captured
     int run_base = 0, ctx = 0;                      // scratch of the current enqueue starts at this run; stream / event set in use
     int n_batch = 0, it_done = 0, outer_it = 0; bool non_fxs = false; double *fix_int = nullptr, *fix_cand = nullptr; double *partial = nullptr, *err = nullptr, *mm = nullptr; int red_blocks = 0;
     bool loop_alloc = false;
@@ -333,6 +334,8 @@ int xfb_plan_destroy(xfb_plan* p) {
     for (auto& kv : p->dft_fold_tiles) cudaFree(kv.second.first);
     for (auto& kv : p->graphs) cudaGraphExecDestroy(kv.second);
     if (p->iter_params) cudaFree(p->iter_params);
+    if (p->s_graph) cudaStreamDestroy(p->s_graph);
+    for (cudaEvent_t e : {p->ev_gfork, p->ev_gjoin}) if (e) cudaEventDestroy(e);
     for (auto& e : p->prof_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto e : p->ev_in) cudaEventDestroy(e);
     for (auto e : p->ev_comp) cudaEventDestroy(e);
@@ -1418,20 +1421,32 @@ int xfb_mtip_iterate(xfb_plan* p, int32_t method, int32_t ft_stab, int32_t n_ite
         // graph replay needs: no per-launch profiling events, no host-side history offsets (deg2 metric), a 3-D plan
         const bool graphable = p->use_graph && !p->graph_broken && !p->prof && !p->d2_metric && p->dims == 3 && !p->sht_chunk;
         const int key = (method & 1) | ((ft_stab & 1) << 1) | ((p->non_fxs ? 1 : 0) << 2) | (nb << 3);
+        // the iterations of a graphable call run on an internal stream forked from the caller's (the legacy default stream cannot be captured)
+        cudaStream_t ws = st;
+        if (graphable) {
+            if (!p->s_graph) {
+                XFB_CUDA(cudaStreamCreateWithFlags(&p->s_graph, cudaStreamNonBlocking));
+                XFB_CUDA(cudaEventCreateWithFlags(&p->ev_gfork, cudaEventDisableTiming));
+                XFB_CUDA(cudaEventCreateWithFlags(&p->ev_gjoin, cudaEventDisableTiming));
+            }
+            XFB_CUDA(cudaEventRecord(p->ev_gfork, st));
+            XFB_CUDA(cudaStreamWaitEvent(p->s_graph, p->ev_gfork, 0));
+            ws = p->s_graph;
+        }
         for (int it = 0; it < n_iter; ++it) {
             const double beta = betas ? betas[it] : 0.0;
             auto g = graphable ? p->graphs.find(key) : p->graphs.end();
-            if (graphable && g == p->graphs.end() && p->graph_warm[key] > 0) {
+            if (graphable && !p->graph_broken && g == p->graphs.end() && p->graph_warm[key] > 0) {
                 // second iteration of this kind: capture it (nothing executes during the capture), instantiate, then replay
                 if (!p->iter_params) { if (dev_alloc(p, &p->iter_params, 1)) return 1; }
                 const int64_t l0 = p->launches;
                 p->ip_active = p->iter_params;
                 cudaGraph_t graph = nullptr;
-                cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+                cudaError_t e = cudaStreamBeginCapture(ws, cudaStreamCaptureModeThreadLocal);
                 int rc = 1;
                 if (e == cudaSuccess) {
-                    rc = iterate_range(p, 0, nb, method, ft_stab, beta, p->it_done, st);
-                    e = cudaStreamEndCapture(st, &graph);
+                    rc = iterate_range(p, 0, nb, method, ft_stab, beta, p->it_done, ws);
+                    e = cudaStreamEndCapture(ws, &graph);
                 }
                 p->ip_active = nullptr;
                 cudaGraphExec_t exec = nullptr;
@@ -1447,15 +1462,20 @@ int xfb_mtip_iterate(xfb_plan* p, int32_t method, int32_t ft_stab, int32_t n_ite
                 if (graph) cudaGraphDestroy(graph);
             }
             if (graphable && !p->graph_broken && g != p->graphs.end()) {
-                iter_params_kernel<<<1, 1, 0, st>>>(p->iter_params, beta, p->it_done, p->outer_it);
-                XFB_CUDA(cudaGraphLaunch(g->second, st));
+                iter_params_kernel<<<1, 1, 0, ws>>>(p->iter_params, beta, p->it_done, p->outer_it);
+                XFB_CUDA(cudaGraphLaunch(g->second, ws));
                 p->launches += p->graph_launches[key] + 1;
+                p->graph_replays++;
                 p->proj_calls++;                          // host bookkeeping of the replayed projection (cache stamp of xfb_get_unknowns)
             } else {
-                if (iterate_range(p, 0, nb, method, ft_stab, beta, p->it_done, st)) return 1;
+                if (iterate_range(p, 0, nb, method, ft_stab, beta, p->it_done, ws)) return 1;
                 p->graph_warm[key]++;
             }
             p->it_done++;
+        }
+        if (graphable) {
+            XFB_CUDA(cudaEventRecord(p->ev_gjoin, ws));
+            XFB_CUDA(cudaStreamWaitEvent(st, p->ev_gjoin, 0));
         }
         return 0;
     }
@@ -1509,6 +1529,9 @@ int xfb_debug_jacobi_sweeps(xfb_plan* p, int32_t* out_host, int32_t capacity, in
     if (n > 0 && out_host) XFB_CUDA(cudaMemcpy(out_host, p->sweeps_dev, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
     return 0;
 }
+
+// diagnostics: iterations replayed from a captured CUDA graph so far
+int64_t xfb_plan_graph_replays(const xfb_plan* p) { return p ? p->graph_replays : 0; }
 
 // diagnostics: phase cycle counters of the Jacobi kernel (zeros unless the library was built with -DJAC_TIMING); reset after reading
 int xfb_debug_jacobi_phase_cycles(double* out8_host) {

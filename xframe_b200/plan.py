@@ -173,6 +173,9 @@ class Plan:
     def workspace_bytes(self):
         return int(self.lib.xfb_plan_workspace_bytes(self.h))
 
+    def graph_replays(self):
+        return int(self.lib.xfb_plan_graph_replays(self.h))
+
     def launch_count(self):
         return int(self.lib.xfb_plan_launch_count(self.h))
 
