@@ -113,6 +113,33 @@ def test_projection_and_pointwise(case):
     assert np.array_equal(N(plan.shrinkwrap(T(g['rho0'])[None], 12.5, 0.09))[0], g['sw_mask'])
 
 
+def test_average_center_and_ignored_names_2d(case):
+    """The real projection chain in 2-D (fxs_Projections.py:96-130, dimension 2 branch: mean over the angular axis of the first shells)."""
+    import copy
+    g, sd, plan, ps = case
+    from xframe_b200.plan import Plan, ER
+    from xframe_b200 import setup_host as S
+    popt = copy.deepcopy(sd['projections']['real']['projections'])
+    popt['apply'] = ['average_center', 'support', 'assert_real', 'value_threshold']
+    popt['average_center'] = {'max_radial_id': 3}
+    p2 = Plan(int(g['m_max']), int(g['n_r']), float(g['max_q']), max_batch=2, dimensions=2)
+    try:
+        sup0 = S.initial_support(p2, popt['support']['initial_support'])
+        p2.set_real(popt['apply'], sup0, popt['value_threshold']['threshold'], popt['limit_imag']['threshold'], average_center_shells=3)
+        assert p2.real_projections == ('average_center', 'support', 'value_threshold')
+        m = O2.MTIP2D(sd, data_2d(g))
+        rp = O.RealProjection(popt, m.real_grid)
+        rng = np.random.default_rng(4)
+        x = np.stack([g['x_grid'], g['x_grid'] * (1 + 0.2 * rng.standard_normal(g['x_grid'].shape))])
+        sup = torch.ones((2,) + p2.grid_shape, dtype=torch.uint8, device='cuda')
+        nxt, _ = p2.real_update(ER, 0.0, T(x), T(x), sup)
+        for b in range(2):
+            want, _ = rp.projection(x[b].copy())
+            assert rel_l2(N(nxt)[b], want) < 1e-13
+    finally:
+        p2.close()
+
+
 def test_full_loop_against_reference(case):
     g, sd, plan, ps = case
     if 'so_freedom' in g and bool(g['so_freedom']):
