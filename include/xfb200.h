@@ -183,6 +183,9 @@ int xfb_mtip_get_grid(xfb_plan* p, int32_t which, void* out_dev, void* stream);
 /* error history [n_batch][n_done] (real l2_projection_diff), best_error [n_batch], n_done */
 int xfb_mtip_get_errors(xfb_plan* p, double* hist_dev, int32_t hist_capacity, double* best_dev, int32_t* n_done_host, void* stream);
 /* counts kernels launched through this plan since creation (bench.py gpu_launches) */
+/* GPU-access layer, second named kernel: `apply_matrix` of the reference's framework demo (tests/test_framework_integration.py:230-309):
+ * out[nq][nvec] = matrix[nq][nq] . vect[nq][nvec], float64, device pointers */
+int xfb_apply_matrix(const double* matrix_dev, const double* vect_dev, double* out_dev, int64_t nq, int64_t nvec, void* stream);
 int64_t xfb_plan_launch_count(const xfb_plan* p);
 int64_t xfb_plan_graph_replays(const xfb_plan* p);   /* iterations replayed from a captured CUDA graph (diagnostics) */
 /* elapsed ms of the dominant kernel group between reset and now, measured with CUDA events on `stream` */

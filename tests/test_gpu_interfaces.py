@@ -127,6 +127,32 @@ def test_gpu_access_layer_runs_the_hankel_process():
         GA.ClProcess(kd)
 
 
+def test_gpu_access_layer_runs_the_apply_matrix_demo():
+    """The GPU demo of the reference's framework test (tests/test_framework_integration.py:230-309): its kernel_dict for `apply_matrix`,
+    verbatim, through ClProcess / add_gpu_process; the reference asserts (result == matrix @ vects).all() for 10 x 10 times 10 x 5."""
+    from xframe_b200 import gpu_access as GA
+    rng = np.random.default_rng(12)
+    nq, nvec = 10, 5
+    matrix, vects = rng.random((nq, nq)), rng.random((nq, nvec))
+    kd = {'kernel': '__kernel void apply_matrix(...) {...}', 'name': 'gpu_func',
+          'functions': ({'name': 'apply_matrix', 'dtypes': (float, float, float, np.int64, np.int64),
+                         'shapes': ((nq, nvec), matrix.shape, (nq, nvec), None, None, None),
+                         'arg_roles': ('output', 'const_input', 'input', 'const_input', 'const_input'),
+                         'const_inputs': (None, matrix, None, np.int64(nq), np.int64(nvec)),
+                         'global_range': (nq, nvec), 'local_range': None},)}
+    fn = GA.comm_module.add_gpu_process(GA.openCL_plugin.ClProcess(kd))
+    result = fn(vects)
+    expected = matrix @ vects
+    assert result.shape == expected.shape and result.dtype == np.float64
+    assert np.allclose(result, expected, rtol=4e-16, atol=0)            # q ascending, one FMA per term: at most an ulp from BLAS
+    # a larger case against a sequential sum
+    nq, nvec = 64, 7
+    matrix, vects = rng.standard_normal((nq, nq)), rng.standard_normal((nq, nvec))
+    kd['functions'][0].update(shapes=((nq, nvec), matrix.shape, (nq, nvec), None, None, None), const_inputs=(None, matrix, None, np.int64(nq), np.int64(nvec)))
+    fn = GA.comm_module.add_gpu_process(GA.openCL_plugin.ClProcess(kd))
+    assert rel_l2(fn(vects), matrix @ vects) < 1e-15
+
+
 def test_unknowns_match_the_reference_formula():
     """fxs_unknowns (approximate_unknowns, fxs_Projections.py:752-767).  Only V_l unk_l is observable; unk_l itself is
     compared where PD_l I_l is well conditioned, and must be a partial isometry everywhere."""

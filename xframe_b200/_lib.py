@@ -79,6 +79,7 @@ EXPORTS = {
     'xfb_mtip_shrinkwrap_center': (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p]),
     'xfb_mtip_get_grid': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'xfb_mtip_get_errors': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
+    'xfb_apply_matrix': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     'xfb_plan_launch_count': (C.c_int64, [C.c_void_p]),
     'xfb_plan_graph_replays': (C.c_int64, [C.c_void_p]),
     'xfb_profile_enable': (C.c_int, [C.c_void_p, C.c_int32]),

@@ -1530,6 +1530,25 @@ int xfb_debug_jacobi_sweeps(xfb_plan* p, int32_t* out_host, int32_t capacity, in
     return 0;
 }
 
+// Second precompiled kernel of the GPU-access layer: the `apply_matrix` demo of the reference's framework test
+// (tests/test_framework_integration.py:230-309): out[i][j] = sum_q matrix[i][q] vect[q][j], q ascending with one FMA per term (the
+// OpenCL kernel's loop under the default FP contraction).  No plan needed; all pointers are device pointers.
+__global__ void apply_matrix_kernel(double* __restrict__ out, const double* __restrict__ matrix, const double* __restrict__ vect, long long nq, long long nvec) {
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= nq * nvec) return;
+    const long long i = idx / nvec, j = idx - i * nvec;
+    double value = 0.0;
+    for (long long q = 0; q < nq; ++q) value = fma(matrix[i * nq + q], vect[q * nvec + j], value);
+    out[idx] = value;
+}
+int xfb_apply_matrix(const double* matrix_dev, const double* vect_dev, double* out_dev, int64_t nq, int64_t nvec, void* stream) {
+    if (!matrix_dev || !vect_dev || !out_dev || nq < 1 || nvec < 1) XFB_FAIL("xfb_apply_matrix: bad arguments");
+    const long long n = nq * nvec;
+    apply_matrix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out_dev, matrix_dev, vect_dev, nq, nvec);
+    XFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // diagnostics: iterations replayed from a captured CUDA graph so far
 int64_t xfb_plan_graph_replays(const xfb_plan* p) { return p ? p->graph_replays : 0; }
 

@@ -12,7 +12,8 @@ surface so `hankel_transforms.generate_spherical_ht_gpu`-style callers work unch
 
 The one deliberate restriction: a ClProcess names a PRECOMPILED kernel.  Arbitrary OpenCL source in
 kernel_dict['kernel'] cannot be honoured; the function name selects the device routine
-(today: 'apply_weights' = the Hankel contraction of hankel_transforms.py:660-766) and anything else raises XfbError.
+('apply_weights' = the Hankel contraction of hankel_transforms.py:660-766, 'apply_matrix' = the matrix-times-vectors demo of
+the reference's framework test, tests/test_framework_integration.py:230-309) and anything else raises XfbError.
 """
 import ctypes as C
 
@@ -62,7 +63,7 @@ class ClFunction:
 class ClProcess:
     """openCL_plugin.py:302-358.  `run` is assembled by `assemble_run()` (the reference does this in the GPU worker)."""
 
-    _KNOWN = ('apply_weights',)
+    _KNOWN = ('apply_weights', 'apply_matrix')
 
     def __init__(self, process_data, context_data=False, device=None):
         self.dict = process_data
@@ -82,8 +83,36 @@ class ClProcess:
         if self.n_functions != 1:
             raise XfbError("ClProcess: chained functions are not supported by the CUDA backend")
 
+    def _assemble_apply_matrix(self, f):
+        """apply_matrix(out[nq, nvec], matrix[nq, nq], vect[nq, nvec], nq, nvec): the GPU demo of the reference's framework test
+        (tests/test_framework_integration.py:230-309) on the precompiled CUDA kernel xfb_apply_matrix."""
+        import torch
+        lib = load()
+        mat = np.ascontiguousarray(np.asarray(f.const_inputs[1], dtype=np.float64))
+        nq, nvec = (int(v) for v in f.shapes[0])
+        if mat.shape != (nq, nq) or tuple(f.shapes[2]) != (nq, nvec):
+            raise XfbError(f"apply_matrix: unexpected shapes matrix{mat.shape} out({nq},{nvec})")
+        dev = torch.device('cuda', torch.cuda.current_device() if self.device is None else self.device)
+        mat_d = torch.from_numpy(mat).to(dev)
+
+        def run(vect):
+            was_torch = isinstance(vect, torch.Tensor)
+            x = vect if was_torch else torch.from_numpy(np.ascontiguousarray(vect, dtype=np.float64))
+            x = x.to(device=dev, dtype=torch.float64).contiguous()
+            if tuple(x.shape) != (nq, nvec):
+                raise ValueError(f"apply_matrix input shape {tuple(x.shape)} != {(nq, nvec)}")
+            out = torch.empty((nq, nvec), dtype=torch.float64, device=dev)
+            with torch.cuda.device(dev):
+                check(lib.xfb_apply_matrix(C.c_void_p(mat_d.data_ptr()), C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), nq, nvec,
+                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            return out if was_torch else out.cpu().numpy()
+        self.run = run
+        return run
+
     def assemble_run(self):
         f = self.functions[0]
+        if f.name == 'apply_matrix':
+            return self._assemble_apply_matrix(f)
         # apply_weights(out[nq, nlm], w[n_sum, nq, nl], rho[nq, nlm], nq, nlm, nl)   hankel_transforms.py:672-740
         w = np.asarray(f.const_inputs[1])
         nq, nlm = (int(v) for v in f.shapes[0])
