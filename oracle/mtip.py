@@ -393,6 +393,15 @@ class ReciprocalProjection:
                 mask[:] = ((qs >= region[0]) & (qs < region[1]))[None, :]
             else:
                 mask[:] = True
+        elif mopt['type'] == 'from_projection_matrices':          # :593-598
+            for part, lim in zip(mask, np.asarray(data['data_projection_matrices_q_id_limits']['I1I1'])):
+                part[:] = (qs > dq[int(lim[0])]) & (qs < dq[int(lim[1]) - 1])
+        elif mopt['type'] == 'manual' and mopt['manual']['type'] == 'order_dependent_line':     # :618-623, mathLibrary.py:1131-1137
+            p1, p2 = (np.asarray(v, dtype=float) for v in mopt['manual']['order_dependent_line'])
+            d = p2 - p1
+            rot = np.array([[0, 1], [-1, 0]]) @ d
+            grid = np.stack(np.meshgrid(np.arange(l_max + 1, dtype=float), qs, indexing='ij'), axis=-1) - p1
+            mask = (-1 * np.sum(grid * rot[None, None, :], axis=-1)) >= 0
         else:
             raise AssertionError('q_mask type not restated')
         self.radial_mask = mask & data_mask

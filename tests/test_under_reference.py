@@ -47,6 +47,7 @@ def synthetic_invariants(sd):
     sdd = copy.deepcopy(sd)
     sdd['grid'].update(n_radial_points=n_r, max_q=float(max_q))
     sdd['projections']['real']['projections']['apply'] = ['support', 'value_threshold', 'limit_imag']
+    sdd['projections']['reciprocal']['q_mask'] = {'type': 'none'}
     om = O.MTIP(sdd, {'data_radial_points': O.radial_grids('midpoint', max_q, n_r, 2.0)[1], 'average_intensity': np.ones(n_r),
                       'max_order': l_max,
                       'data_projection_matrices': [np.zeros((n_r, min(n_r, 2 * l + 1)), complex) for l in range(l_max + 1)]})
@@ -162,6 +163,35 @@ def test_invariant_extraction_matches_reference():
         # on the scale of the even orders
         scale = np.linalg.norm(b) if l % 2 == 0 else np.linalg.norm(Bl_ref[0])
         assert np.linalg.norm(a - b) <= 1e-10 * scale, l
+
+
+@needs_ref
+@pytest.mark.parametrize('q_mask', [
+    {'type': 'none'},
+    {'type': 'from_projection_matrices'},
+    {'type': 'manual', 'manual': {'type': 'region', 'region': [0.01, 0.03]}},
+    {'type': 'manual', 'manual': {'type': 'region', 'region': [False, 0.025]}},
+    {'type': 'manual', 'manual': {'type': 'order_dependent_line', 'order_dependent_line': [[2, 0.004], [14, 0.03]]}},
+])
+def test_radial_mask_types_match_reference(q_mask):
+    """generate_radial_mask (fxs_Projections.py:578-629) for every q_mask type against setup_host.ProjectionSetup (host-side setup,
+    numpy like the reference's): the mask that selects which radial points of an order the projection overwrites."""
+    from oracle.sht import sh
+    from xframe_b200 import setup_host as S
+    sd = reference_test_settings(gpu=False, n_r=16)
+    sd['projections']['reciprocal']['q_mask'] = q_mask
+    inv = synthetic_invariants(sd)
+    n_q = len(inv['data_radial_points'])
+    inv['data_projection_matrices_q_id_limits'] = {'I1I1': np.array([[l % 3, n_q - (l % 4)] for l in range(16)])}
+    RH.import_reference(sh_class=sh)
+    rec, m = RH.make_mtip(sd, inv)
+    ref_mask = np.asarray(m.rprojection.radial_mask)
+    ps = S.ProjectionSetup(np.asarray(rec.MTIP.reciprocal_radial_points), dict(inv), 15, sd['projections']['reciprocal'])
+    assert ps.radial_mask.shape == (16, 16)
+    assert np.array_equal(ps.radial_mask, np.broadcast_to(ref_mask, (16, 16)))
+    assert np.array_equal(np.broadcast_to(O.MTIP(sd, dict(inv)).rp.radial_mask, (16, 16)), ps.radial_mask)        # the oracle's restatement
+    if q_mask['type'] != 'none':
+        assert not ps.radial_mask.all() and ps.radial_mask.any()
 
 
 @needs_ref

@@ -17,6 +17,43 @@ def midpoint_rule(samples, pts):                               # mathLibrary.py:
     return (pts[1] - pts[0]) * np.sum(samples, axis=0)
 
 
+def radial_mask(qs, dq, n_orders, mopt, data):
+    """generate_radial_mask (fxs_Projections.py:578-629): (custom mask [n_orders, N_q] or True, data mask); the projection uses their AND.
+    Types: none; from_projection_matrices (per order the q range the data's projection matrices cover, `data_projection_matrices_q_id_limits`
+    of the invariants record); manual / region; manual / order_dependent_line (half plane of the (order, q) grid left of a line)."""
+    nq = len(qs)
+    mask = np.full((n_orders, nq), False)
+    data_mask = mask | ((qs >= dq.min()) & (qs <= dq.max()))                                           # :585-586
+    mtype = mopt['type']
+    if mtype == 'none':
+        return True, data_mask
+    if mtype == 'from_projection_matrices':                                                            # :593-598
+        limits = data.get('data_projection_matrices_q_id_limits', False)
+        if isinstance(limits, bool) or isinstance(limits.get('I1I1', False), bool):
+            raise XfbError("q_mask: from_projection_matrices needs data_projection_matrices_q_id_limits['I1I1'] in the invariants record")
+        for part, lim in zip(mask, np.asarray(limits['I1I1'])):
+            part[:] = (qs > dq[int(lim[0])]) & (qs < dq[int(lim[1]) - 1])
+        return mask, data_mask
+    if mtype == 'manual' and mopt['manual']['type'] == 'region':                                       # :603-617
+        lo, hi = mopt['manual']['region']
+        if (lo == False) and (hi != False):      # noqa: E712
+            mask[:] = (qs < hi)[None, :]
+        elif (lo != False) and (hi == False):    # noqa: E712
+            mask[:] = (qs >= lo)[None, :]
+        elif (lo != False) and (hi != False):    # noqa: E712
+            mask[:] = ((qs >= lo) & (qs < hi))[None, :]
+        else:
+            mask[:] = True
+        return mask, data_mask
+    if mtype == 'manual' and mopt['manual']['type'] == 'order_dependent_line':                         # :618-623, mathLibrary.py:1131-1137
+        p1, p2 = (np.asarray(v, dtype=float) for v in mopt['manual']['order_dependent_line'])
+        d = p2 - p1
+        rot = np.array([d[1], -d[0]])
+        grid = np.stack(np.meshgrid(np.arange(n_orders, dtype=float), qs, indexing='ij'), axis=-1) - p1
+        return (-(grid * rot[None, None, :]).sum(axis=-1)) >= 0, data_mask
+    raise XfbError(f"q_mask type '{mtype}' is not known (none, from_projection_matrices, manual / region, manual / order_dependent_line)")
+
+
 class ProjectionSetup:
     """Final V_l, radial mask and integrated intensity for a reconstruction grid `qs`."""
 
@@ -55,23 +92,7 @@ class ProjectionSetup:
             p *= 2
         self.projection_matrices = proj
         nq = len(qs)
-        mask = np.full((l_max + 1, nq), False)
-        data_mask = mask | ((qs >= dq.min()) & (qs <= dq.max()))                                       # :585-586
-        mopt = ropt.get('q_mask', {'type': 'none'})
-        if mopt['type'] == 'none':
-            mask = True
-        elif mopt['type'] == 'manual' and mopt['manual']['type'] == 'region':                          # :603-617
-            lo, hi = mopt['manual']['region']
-            if (lo == False) and (hi != False):      # noqa: E712
-                mask[:] = (qs < hi)[None, :]
-            elif (lo != False) and (hi == False):    # noqa: E712
-                mask[:] = (qs >= lo)[None, :]
-            elif (lo != False) and (hi != False):    # noqa: E712
-                mask[:] = ((qs >= lo) & (qs < hi))[None, :]
-            else:
-                mask[:] = True
-        else:
-            raise XfbError(f"q_mask type '{mopt['type']}' is not supported by xframe_b200 (none, manual/region)")
+        mask, data_mask = radial_mask(qs, dq, l_max + 1, ropt.get('q_mask', {'type': 'none'}), data)
         self.radial_mask = np.ascontiguousarray(np.broadcast_to(mask & data_mask, (l_max + 1, nq)))
 
     def apply_to(self, plan, sv_cutoff=1e-15):
@@ -115,10 +136,8 @@ class ProjectionSetup2D:
         if ropt.get('use_averaged_intensity', False):
             proj[0] = avg.astype(complex)
         self.projection_matrices = proj                                                                # no *2 in 2-D (:710-713 is 3-D only)
-        mopt = ropt.get('q_mask', {'type': 'none'})
-        if mopt['type'] != 'none':
-            raise XfbError("2-D path: only q_mask type 'none' is supported")
-        self.radial_mask = np.ascontiguousarray(np.broadcast_to((qs >= dq.min()) & (qs <= dq.max()), (m_max + 1, len(qs))))
+        mask, data_mask = radial_mask(qs, dq, m_max + 1, ropt.get('q_mask', {'type': 'none'}), data)
+        self.radial_mask = np.ascontiguousarray(np.broadcast_to(mask & data_mask, (m_max + 1, len(qs))))
         so = ropt.get('SO_freedom', {'use': False})
         self.use_SO_freedom = bool(so.get('use', False))
         self.radial_high_pass = so.get('radial_high_pass', 0.2)
